@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point updates / s per full timestep (FP64), BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm, one process per GPU)
+    python bench.py --impl reference --steps K --warmup W    (reference arm: the CPU path)
+
+A "step" is one complete loop iteration of the rigid-flow driver
+(examples/FlowPastSphere/flow_past_sphere.py:107-207: boundary damping, streamfunction solve,
+velocity, CFL reduction, penalisation + drag, ENO3 advection, RK2 diffusion) on the synthetic
+4096 x 16384 FP64 grid the metric is quoted on (BASELINE.json configs[3]; it fits one GPU).
+Fields (512 MiB each) are far larger than the 126 MB L2, so no explicit flush is needed
+between timed iterations.  Timing: CUDA events on the launching stream, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "grid-pt updates/s per full timestep (FP64)"
+UNIT = "grid-pt updates/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.rows, self.proc, self.idx = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load" = the upper half of the samples
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": float(np.median(sm_sorted[len(sm_sorted) // 2:])) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path (oracle port) on a bounded sample of the same workload
+# ----------------------------------------------------------------------------------------------
+def cpu_step_seconds(nr, nz, repeats=1):
+    """One full rigid-flow timestep on the host, extrapolated from a bounded sample.
+
+    The reference's path at this grid is: four OpenBLAS dgemms (numpy.linalg.multi_dot) +
+    numba/NumPy stencil passes + the pystencils ENO3 kernels.  pystencils cannot be installed,
+    and la.eig at Nz=16384 takes tens of minutes, so:
+      * stencils: the oracle's NumPy restatement (single thread, like numba) and its C/OpenMP
+        ENO3 (all cores, like pystencils with num_threads=nproc) on a z-window of the grid,
+        scaled by nz / window;
+      * solve: numpy matmul (threaded BLAS) of each of the four products on a column / row
+        block, scaled by the block count (BLAS cost is linear in the blocked dimension).
+    Returns (seconds per full step, description of the sample).
+    """
+    from oracle import axisym_oracle as ox
+
+    dx = 1.0 / nz
+    nzw = min(nz, 1024)
+    rng = np.random.default_rng(0)
+    z = np.linspace(dx / 2, nzw * dx - dx / 2, nzw)
+    r = np.linspace(dx / 2, nr * dx - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    blob = np.exp(-((Z - 0.5 * nzw * dx) ** 2 + R ** 2) / 0.02)
+    w = rng.standard_normal((nr, nzw)) * blob
+    psi = 1e-3 * rng.standard_normal((nr, nzw)) * blob
+    chi = np.zeros_like(Z)
+    ox.smooth_Heaviside(chi, -np.sqrt((Z - 0.25 * nzw * dx) ** 2 + R ** 2) + 0.1 * nzw * dx, dx * 2 ** 0.5)
+    uz, ur, tmp, pv = (np.zeros_like(Z) for _ in range(4))
+    eps = np.finfo(float).eps
+    nu, lam = 2e-3, 1e12
+    t_st = []
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        ox.kill_boundary_vorticity_sine_z(w, Z, 3, dx)
+        ox.kill_boundary_vorticity_sine_r(w, R, 3, dx)
+        ox.compute_velocity_from_psi(uz, ur, psi, R, dx)
+        uz += 1.0
+        dt = min(0.9 * dx ** 2 / 4 / nu, 0.1 * dx / (np.amax(np.fabs(uz) + np.fabs(ur)) + eps))
+        uzu, uru = uz.copy(), ur.copy()
+        ox.brinkmann_penalize(lam, dt, chi, 0.0, 0.0, uzu, uru, uz, ur)
+        ox.compute_vorticity_from_velocity(pv, uz - uzu, ur - uru, dx)
+        w += pv
+        _cd = np.sum(R * chi * uz)
+        ox.advect_vorticity_via_eno3(w, uz, ur, dt, dx)
+        ox.diffusion_RK2(w, tmp, R, nu, dt, dx)
+        t_st.append(time.perf_counter() - t0)
+    stencil = min(t_st[1:]) * (nz / nzw)
+
+    def gemm_time(m, k, n):
+        a, b = np.ones((m, k)), np.ones((k, n))
+        a @ b
+        best = 1e30
+        for _ in range(max(1, repeats)):
+            t0 = time.perf_counter()
+            a @ b
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    nzc = min(nz, 512)      # column block for the r-transforms  (nr x nr)(nr x nzc)
+    nrc = min(nr, 128)      # row block for the z-transforms     (nrc x nz)(nz x nz)
+    t_r = gemm_time(nr, nr, nzc) * (nz / nzc)
+    t_z = gemm_time(nrc, nz, nz) * (nr / nrc)
+    solve = 2 * t_r + 2 * t_z
+    sample = (f"stencils on a {nr}x{nzw} z-window x{nz // nzw}; dgemm blocks ({nr}x{nr})({nr}x{nzc}) x{nz // nzc} "
+              f"and ({nrc}x{nz})({nz}x{nz}) x{nr // nrc}, each twice per step; "
+              f"stencil {stencil:.2f} s + solve {solve:.2f} s per extrapolated step")
+    return stencil + solve, sample
+
+
+def run_reference_arm(args, nr, nz):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    secs, sample = None, ""
+    for _ in range(max(0, args.warmup) and 1):
+        cpu_step_seconds(nr, nz)
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        s, sample = cpu_step_seconds(nr, nz)
+        times.append(s)
+    secs = float(np.median(times))
+    value = nr * nz / secs
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"rigid-flow timestep (FlowPastSphere loop body) at {nr}x{nz}", "grid": [nr, nz]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def measure_fp64_peak(torch):
+    """cuBLAS DGEMM 8192^3 (burst, best of 5): the FP64 tensor-pipe yardstick MEASURED_PEAKS.json lacks."""
+    n = 8192
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_gpu_arm(args, nr, nz):
+    import torch
+    import torch.distributed as dist
+
+    from pyaxisymflow_b200 import _lib
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    if world > 1:
+        from pyaxisymflow_b200.slab import SlabRigidFlowStepper
+
+        stepper = SlabRigidFlowStepper(nz, grid_size_r=nr)
+        scaling = "strong"
+    else:
+        stepper = RigidFlowStepper(nz, grid_size_r=nr, basis="analytic" if max(nr, nz) >= 1536 else "auto")
+        scaling = "strong"
+    # synthetic start: seeded band-limited vorticity blob so every kernel sees
+    # non-trivial data from the first step on
+    torch.manual_seed(0)
+    stepper.seed_vorticity()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stepper.step(args.warmup)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, device-resident
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probes = []
+    e0.record()
+    for _ in range(args.steps):
+        probes.append(stepper.step_probed())
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = nr * nz / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_dgemm): flops of the four GEMMs / their device time
+    solve_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
+    flops = stepper.solve_flops()
+    achieved = flops / (solve_ms * 1e-3) / 1e12
+
+    # ---- e2e: host-resident caller, H2D of the step's inputs + D2H of its result inside the timing
+    e2e = None
+    if world == 1:
+        hw = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
+        hc = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
+        ho = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
+        hw.copy_(stepper.vorticity)
+        hc.copy_(stepper.char_func)
+        stepper.step_host(hw, hc, ho)
+        torch.cuda.synchronize()
+        k = max(1, min(args.steps, 5))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            stepper.step_host(hw, hc, ho)
+        b.record()
+        torch.cuda.synchronize()
+        e2e_ms = a.elapsed_time(b) / k
+        e2e = {"value": nr * nz / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * nr * nz * 8,
+               "d2h_bytes_per_step": nr * nz * 8, "ms_per_step": e2e_ms}
+        del hw, hc, ho
+
+    if rank == 0:
+        peak = measure_fp64_peak(torch)
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            mp = {}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            secs, sample = cpu_step_seconds(nr, nz)
+            cpu = {"value": nr * nz / secs, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"rigid-flow timestep (FlowPastSphere loop body) at {nr}x{nz}",
+                       "grid": [nr, nz], "parallelism": "single GPU" if world == 1 else f"z-slab x{world}",
+                       "l2": "fields (%.0f MiB each) exceed the 126 MB L2; no flush needed" % (nr * nz * 8 / 2 ** 20),
+                       "basis": stepper.solver_basis()},
+            "roofline": {"bound": "tensor", "kernel": "k_dgemm (4 launches per solve)", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no "
+                                        "FP64 entry)",
+                         "solve_ms": solve_ms, "solve_share_of_step": solve_ms / ms_per_step,
+                         "hbm_peak_gbs": mp.get("hbm_gbs")},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nz", type=int, default=16384, help="grid_size_z (default: the 4096x16384 workload)")
+    ap.add_argument("--nr", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    nz = args.nz
+    nr = args.nr if args.nr is not None else nz // 4
+    if args.impl == "reference":
+        run_reference_arm(args, nr, nz)
+    else:
+        run_gpu_arm(args, nr, nz)
+
+
+if __name__ == "__main__":
+    main()

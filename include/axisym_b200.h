@@ -1,0 +1,252 @@
+/*
+ * axisym_b200.h -- C ABI of libaxisym_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the per-timestep hot path of PyAxisymFlow.
+ * The reference has no FFI of its own on this path: its "kernels" are Python callables
+ * (numba / pystencils closures, NumPy classes, three pybind11 modules).  Each entry point
+ * below therefore cites the reference *callable* it replaces (file:line under
+ * /root/reference); the ctypes stubs that bind them live in pyaxisymflow_b200/_lib.py and
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; fields are float64,
+ *     C-order (nr, nz), axis 1 (z) contiguous, row pitch `ld` elements;
+ *   - no entry point allocates, synchronises or throws; work is enqueued on `stream`;
+ *   - return value: 0 = ok, negative = AXB_E* argument error, positive = cudaError_t;
+ *   - scalars that a device-resident driver keeps on the GPU come in pairs
+ *     (`double x, const double* x_dev`): when x_dev != NULL the kernel reads *x_dev.
+ *   - `r1d` / `z1d` are the 1-D cell-centre coordinates (R[:,0], Z[0,:] of the reference's
+ *     meshgrid arrays), nr resp. nz doubles.
+ */
+#ifndef AXISYM_B200_H
+#define AXISYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* axb_stream_t;
+
+#define AXB_OK 0
+#define AXB_EINVAL (-1)   /* null pointer / bad shape */
+#define AXB_EALIGN (-2)   /* pointer or pitch not 8-byte aligned */
+#define AXB_ENOSUP (-3)   /* unsupported configuration */
+#define AXB_EWORK (-4)    /* workspace too small */
+
+/* Shape + z-slab placement of one (nr, nz) field.  Single GPU: kz0 = 0, nz_global = nz,
+ * ku0 = 0, ku1 = nz.  Under z-slab decomposition `nz` counts the locally STORED columns
+ * (owned + halos), `kz0` is the global z index of local column 0 (negative on the first
+ * rank's left halo), and [ku0, ku1) is the locally owned range the kernel may write. */
+typedef struct axb_grid {
+  int32_t nr;
+  int32_t nz;
+  int64_t ld;
+  double dx;
+  int32_t kz0;
+  int32_t nz_global;
+  int32_t ku0;
+  int32_t ku1;
+} axb_grid_t;
+
+int axb_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t axb_launch_count(void);
+
+/* ---- G-BND: kernels/kill_boundary_vorticity_sine.py:4-14 and :17-27 ------------------ */
+int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const double* z1d, int width,
+                                       axb_stream_t s);
+int axb_kill_boundary_vorticity_sine_r(const axb_grid_t* g, double* w, const double* r1d, int width,
+                                       axb_stream_t s);
+
+/* ---- a12: kernels/periodic_boundary_ghost_comm.py:4-15 (z_max = two_g_dx = 0) and the
+ *      reference-map form :18-33: left ghosts = (src - z_max) + two_g_dx,
+ *      right ghosts = (src + z_max) - two_g_dx  (same operation order as the reference) ---- */
+int axb_periodic_ghost_comm(const axb_grid_t* g, double* f, int ghost, double z_max, double two_g_dx,
+                            axb_stream_t s);
+
+/* ---- G-VEL: kernels/compute_velocity_from_psi.py:4-17.  Fused extras for the device
+ *      driver: adds the free stream (examples/FlowPastSphere/flow_past_sphere.py:117-121),
+ *      and, if umax_out != NULL, atomically maxes |u_z|+|u_r| into it (the dt reduction of
+ *      flow_past_sphere.py:150-153).  add_dev, if given, holds {uz_add, ur_add}. ---------- */
+int axb_velocity_from_psi(const axb_grid_t* g, double* u_z, double* u_r, const double* psi,
+                          const double* r1d, double uz_add, double ur_add, const double* add_dev,
+                          double* umax_out, axb_stream_t s);
+
+/* ---- a9: kernels/brinkmann_penalize.py:4-16.  U_*_field non-NULL selects the field form
+ *      (examples/TorusParticleTransport passes arrays), else the scalars are used. --------- */
+int axb_brinkmann_penalize(const axb_grid_t* g, double lam, double dt, const double* chi, double U_z,
+                           double U_r, const double* U_z_field, const double* U_r_field,
+                           const double* grid_u_z, const double* grid_u_r, double* pen_u_z,
+                           double* pen_u_r, axb_stream_t s);
+
+/* ---- a10: kernels/compute_vorticity_from_velocity.py:4-13.  If u_z_sub / u_r_sub are
+ *      non-NULL the curl of (u - u_sub) is taken, which is how every driver calls it
+ *      (flow_past_sphere.py:161-163).  accumulate != 0 does vort += curl instead of =. ----- */
+int axb_vorticity_from_velocity(const axb_grid_t* g, double* vort, const double* u_z, const double* u_r,
+                                const double* u_z_sub, const double* u_r_sub, int accumulate,
+                                axb_stream_t s);
+
+/* ---- G-PEN: the whole penalisation block of flow_past_sphere.py:155-175 in one pass:
+ *      u = pen(u_upen), w += curl(u - u_upen) on the interior, and (sum_out != NULL)
+ *      sum_out += sum(R * chi * (u_z - U_z))  [drag numerator / compute_forces.py:14]. ----- */
+int axb_penalise_update_vorticity(const axb_grid_t* g, double* u_z, double* u_r, double* w,
+                                  const double* u_z_upen, const double* u_r_upen, const double* chi,
+                                  double lam, double dt, const double* dt_dev, double U_z, double U_r,
+                                  const double* U_dev, const double* r1d, double* sum_out,
+                                  axb_stream_t s);
+
+/* ---- G-ADV: kernels/advect_vorticity_via_eno3.py:21-42 = axis mirror + conservative ENO3
+ *      Euler step (pyst_kernels/advection_timestep.py:45-54) + copy back, as ONE kernel with
+ *      the reflection done by index.  Out of place: w_out must not alias w_in. ------------- */
+int axb_advect_vorticity_eno3(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
+                              const double* u_r, double dt, const double* dt_dev, axb_stream_t s);
+
+/* ---- G-REF: elasto_kernels/advect_refmap_via_eno3.py:21-52 (two non-conservative ENO3
+ *      steps sharing the velocity), one kernel, out of place. ------------------------------ */
+int axb_advect_refmap_eno3(const axb_grid_t* g, double* eta1_out, double* eta2_out, const double* eta1,
+                           const double* eta2, const double* u_z, const double* u_r, double dt,
+                           const double* dt_dev, axb_stream_t s);
+
+/* ---- a1-a6: the pystencils closures on plain (n0, n1) arrays, no mirroring -------------
+ *      axb_eno3_flux         : pyst_kernels/advection_flux.py:133-161 / :302-330 (flux += ...)
+ *      axb_eno3_euler_step   : pyst_kernels/advection_timestep.py:37-54 / :85-102
+ *      axb_elementwise_sum   : pyst_kernels/elementwise_ops.py:28-33
+ *      axb_set_fixed_val     : pyst_kernels/elementwise_ops.py:73-77
+ *      (g->nr, g->nz) is the array shape; only [2:-2, 2:-2] is touched by the flux. ------- */
+int axb_eno3_flux(const axb_grid_t* g, double* flux, const double* field, const double* vel0,
+                  const double* vel1, double inv_dx, int conservative, axb_stream_t s);
+int axb_eno3_euler_step(const axb_grid_t* g, double* field_out, const double* field_in, const double* vel0,
+                        const double* vel1, double dt_by_dx, int conservative, axb_stream_t s);
+int axb_elementwise_sum(const axb_grid_t* g, double* sum, const double* f1, const double* f2,
+                        axb_stream_t s);
+int axb_set_fixed_val(const axb_grid_t* g, double* f, double val, axb_stream_t s);
+
+/* ---- G-DIF: kernels/diffusion_RK2.py:4-45 as two launches.
+ *      stage1: tmp = w; tmp[int] += 0.5*nu*dt*L(w).   stage2: w[int] += nu*dt*L(tmp). ------- */
+int axb_diffusion_rk2_stage1(const axb_grid_t* g, double* tmp, const double* w, const double* r1d,
+                             double nu, double dt, const double* dt_dev, axb_stream_t s);
+/* stage2 writes w = w_src + nu*dt*L(tmp); w_src == w is the reference's in-place form, a distinct
+ * w_src lets a ping-pong driver land the result in another buffer at no extra traffic. */
+int axb_diffusion_rk2_stage2(const axb_grid_t* g, double* w, const double* w_src, const double* tmp,
+                             const double* r1d, double nu, double dt, const double* dt_dev,
+                             axb_stream_t s);
+
+/* ---- G-HEAV: kernels/smooth_Heaviside.py:5-14; the _sphere form builds
+ *      phi = radius - sqrt((Z-z_cm)^2 + (R-r_cm)^2) in-kernel (flow_past_sphere.py:80-82). -- */
+int axb_smooth_heaviside(const axb_grid_t* g, double* H, const double* phi, double blend_w,
+                         axb_stream_t s);
+int axb_smooth_heaviside_sphere(const axb_grid_t* g, double* H, double* phi_out, const double* z1d,
+                                const double* r1d, double z_cm, double r_cm, double radius,
+                                double blend_w, axb_stream_t s);
+
+/* ---- kernels/vortex_stretching.py:4-11 -------------------------------------------------- */
+int axb_vortex_stretching(const axb_grid_t* g, double* w, const double* u_r, const double* r1d, double dt,
+                          axb_stream_t s);
+
+/* ---- a15 diagnostics.  out is a device double; the caller zeroes it (axb_fill_scalars).
+ *      max_abs_sum : max(|a| + |b|)           (flow_past_sphere.py:152; b may be NULL)
+ *      max         : max(a)                   (flow_past_sphere.py:191)
+ *      weighted_sum: sum(r * c * (a - off))   (compute_forces.py:14, force_projection.py:12-13) */
+int axb_reduce_max_abs_sum(const axb_grid_t* g, const double* a, const double* b, double* out,
+                           axb_stream_t s);
+int axb_reduce_max(const axb_grid_t* g, const double* a, double* out, axb_stream_t s);
+int axb_reduce_weighted_sum(const axb_grid_t* g, const double* r1d, const double* c, const double* a,
+                            double off, double* out, axb_stream_t s);
+int axb_fill_scalars(double* dst, int n, double val, axb_stream_t s);
+
+/* ---- device-side scalar glue of the rigid-flow loop (flow_past_sphere.py:117-121,
+ *      :150-153, :186-188) so that a whole timestep needs no host round trip.
+ *      state (device doubles): [0]=t [1]=dt [2]=umax [3]=sum(R chi u_z) [4]=uz_add [5]=ur_add
+ *      [6]=iteration count [7]=last Cd numerator copy.
+ *      phase 0: uz_add = U0 * (t < T_ramp ? sin(pi/2 t/T_ramp) : 1);
+ *               ur_add = U0 * (t < T_ramp ? ur_ramp * sin(pi t/T_ramp) : 0)
+ *               (periodic_flow_past_sphere.py:108-115); umax = 0; sum = 0
+ *      phase 1: dt = min(dt_diff_limit, CFL*dx/(umax + eps))
+ *      phase 2: t += dt; it += 1; state[7] = state[3] ------------------------------------------ */
+int axb_rigid_flow_scalars(int phase, double* state, double U0, double T_ramp, double ur_ramp,
+                           double dt_diff_limit, double cfl_dx, axb_stream_t s);
+
+/* ---- a18: elasto_kernels/solid_sigma.py:4-29 (all seven caller-visible outputs).
+ *      chi != NULL additionally applies the driver's blend sigma *= chi
+ *      (examples/SoftSphereStreaming/soft_sphere_streaming.py:236-238). --------------------- */
+int axb_solid_sigma(const axb_grid_t* g, double* s11, double* s12, double* s22, double G, const double* eta1,
+                    const double* eta2, double* eta1z, double* eta1r, double* eta2z, double* eta2r,
+                    const double* chi, axb_stream_t s);
+/* ---- a19: elasto_kernels/div_tau.py:4-34 as two launches (tau must be globally complete
+ *      before its curl is taken). ------------------------------------------------------------ */
+int axb_solid_tau(const axb_grid_t* g, double* tau_z, double* tau_r, const double* t11, const double* t12,
+                  const double* t22, const double* r1d, axb_stream_t s);
+int axb_solid_vorticity_update(const axb_grid_t* g, double* w, const double* tau_z, const double* tau_r,
+                               double dt, const double* dt_dev, axb_stream_t s);
+
+/* ---- a20: core/src/extrapolate_using_least_squares.hpp:450-467 (order 1, 3x3 patch).
+ *      cur/tgt int16 (n0, n1); eta_x / eta_y (n0, n1); gx[n1], gy[n0].  work holds
+ *      axb_ls_workspace_bytes(n0, n1) bytes.  Sweeps run until no cell is added; the count of
+ *      sweeps is written to *sweeps_host (this one call synchronises the stream, because
+ *      the reference's do/while is data dependent). Bit-exact with the reference. ------------ */
+int64_t axb_ls_workspace_bytes(int n0, int n1);
+int axb_ls_extrapolate_order1(int n0, int n1, int16_t* cur, const int16_t* tgt, double* eta_x,
+                              double* eta_y, const double* gx, const double* gy, void* work,
+                              int64_t work_bytes, int max_sweeps, int* sweeps_host, axb_stream_t s);
+/* the wrapper elasto_kernels/extrapolate_eta_using_least_squares_unb.py:7-30 fused: mirror by
+ * index, flags from phi thresholds, extrapolate, write the physical half back. */
+int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                           double* eta1, double* eta2, double extrap_zone, const double* gx,
+                           const double* gy, void* work, int64_t work_bytes, int max_sweeps,
+                           int* sweeps_host, axb_stream_t s);
+
+/* ---- a21: core/src/particles_to_mesh.hpp:163-184 (periodic = 0) and the periodic twin
+ *      particles_to_mesh_2D_mp4.  mesh is zeroed first, like the reference. ------------------ */
+int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const double* val, double* mesh,
+                   double dx, double dy, int periodic, axb_stream_t s);
+/* kernels/advect_particle.py:5-35 fused for lattice particles: push the mirrored lattice by
+ * u*dt, remesh with MP4 on the doubled grid, return the physical half (w_out != w_in). ----- */
+int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
+                                   const double* u_r, const double* zl1d, const double* rl1d, double dt,
+                                   const double* dt_dev, int periodic, axb_stream_t s);
+
+/* ---- G-FD: kernels/FastDiagonalisationStokesSolver.py:130-156 (and the Potential /
+ *      ImplicitEuler twins).  The plan holds device pointers to the caller-owned factors:
+ *      Lr  = Vr^-1 (diag(r) folded in for the Stokes flavour)   (nr x nr, row-major)
+ *      Rz  = Vz^-T                                               (nz x nz)
+ *      Rzb = Vz^T                                                (nz x nz)
+ *      Lrb = Vr                                                  (nr x nr)
+ *      lam_r[nr], lam_z[nz]; spectral scaling 1 / (c0 + c1*(lam_z[n] + lam_r[m])).
+ *      solve: psi = Lrb * (((Lr*rhs) * Rz) o scale) * Rzb, four FP64 tensor-core GEMMs with
+ *      the scaling fused in the second one's epilogue.  work: 2*nr*nz doubles. ---------------- */
+typedef struct axb_fd_plan {
+  int32_t nr, nz;
+  const double *Lr, *Rz, *Rzb, *Lrb;
+  const double *lam_r, *lam_z;
+  double c0, c1;
+  double* work;
+} axb_fd_plan_t;
+int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
+                 axb_stream_t s);
+/* Plain row-major FP64 GEMM C = A*B (+ optional spectral scaling), the building block above:
+ * A (M x K, lda), B (K x N, ldb), C (M x N, ldc).  scale_m / scale_n NULL = no scaling. */
+int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+              int64_t ldc, const double* scale_m, const double* scale_n, double c0, double c1,
+              axb_stream_t s);
+
+/* ---- z-slab plumbing (multi-GPU): pack / unpack `width` halo columns of a field ----------- */
+int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
+                  axb_stream_t s);
+int axb_halo_unpack(const axb_grid_t* g, double* f, const double* buf_left, const double* buf_right,
+                    int width, double shift, axb_stream_t s);
+/* local (nr x nz_local) slab  <->  P blocks of (nr/P x nz_local) for the all-to-all transpose */
+int axb_slab_to_blocks(int nr, int nzl, int64_t ld, int P, const double* slab, double* blocks,
+                       axb_stream_t s);
+int axb_blocks_to_rows(int nrl, int nzl, int P, const double* blocks, double* rows, int64_t ld_rows,
+                       axb_stream_t s);
+int axb_rows_to_blocks(int nrl, int nzl, int P, const double* rows, int64_t ld_rows, double* blocks,
+                       axb_stream_t s);
+int axb_blocks_to_slab(int nr, int nzl, int64_t ld, int P, const double* blocks, double* slab,
+                       axb_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXISYM_B200_H */

@@ -1,0 +1,126 @@
+"""ctypes binding of ``libaxisym_b200.so`` (the C ABI declared in ``include/axisym_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, or an entry point returns a
+non-zero code, an exception is raised.  The library is built in-tree by
+``make -C pyaxisymflow_b200/csrc`` (``__graft_entry__.build()`` does that).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_double, c_int, c_int16, c_int32, c_int64, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaxisym_b200.so")
+
+
+class AxbError(RuntimeError):
+    pass
+
+
+class AxbGrid(Structure):
+    _fields_ = [("nr", c_int32), ("nz", c_int32), ("ld", c_int64), ("dx", c_double),
+                ("kz0", c_int32), ("nz_global", c_int32), ("ku0", c_int32), ("ku1", c_int32)]
+
+
+class AxbFdPlan(Structure):
+    _fields_ = [("nr", c_int32), ("nz", c_int32),
+                ("Lr", c_void_p), ("Rz", c_void_p), ("Rzb", c_void_p), ("Lrb", c_void_p),
+                ("lam_r", c_void_p), ("lam_z", c_void_p),
+                ("c0", c_double), ("c1", c_double), ("work", c_void_p)]
+
+
+_G = POINTER(AxbGrid)
+_P = c_void_p   # device pointer
+_D = c_double
+_I = c_int
+_S = c_void_p   # cudaStream_t
+
+# name -> argtypes (every function returns int unless listed in _RESTYPE)
+_SIGNATURES = {
+    "axb_version": [],
+    "axb_launch_count": [],
+    "axb_kill_boundary_vorticity_sine_z": [_G, _P, _P, _I, _S],
+    "axb_kill_boundary_vorticity_sine_r": [_G, _P, _P, _I, _S],
+    "axb_periodic_ghost_comm": [_G, _P, _I, _D, _D, _S],
+    "axb_velocity_from_psi": [_G, _P, _P, _P, _P, _D, _D, _P, _P, _S],
+    "axb_brinkmann_penalize": [_G, _D, _D, _P, _D, _D, _P, _P, _P, _P, _P, _P, _S],
+    "axb_vorticity_from_velocity": [_G, _P, _P, _P, _P, _P, _I, _S],
+    "axb_penalise_update_vorticity": [_G, _P, _P, _P, _P, _P, _P, _D, _D, _P, _D, _D, _P, _P, _P, _S],
+    "axb_advect_vorticity_eno3": [_G, _P, _P, _P, _P, _D, _P, _S],
+    "axb_advect_refmap_eno3": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _S],
+    "axb_eno3_flux": [_G, _P, _P, _P, _P, _D, _I, _S],
+    "axb_eno3_euler_step": [_G, _P, _P, _P, _P, _D, _I, _S],
+    "axb_elementwise_sum": [_G, _P, _P, _P, _S],
+    "axb_set_fixed_val": [_G, _P, _D, _S],
+    "axb_diffusion_rk2_stage1": [_G, _P, _P, _P, _D, _D, _P, _S],
+    "axb_diffusion_rk2_stage2": [_G, _P, _P, _P, _P, _D, _D, _P, _S],
+    "axb_smooth_heaviside": [_G, _P, _P, _D, _S],
+    "axb_smooth_heaviside_sphere": [_G, _P, _P, _P, _P, _D, _D, _D, _D, _S],
+    "axb_vortex_stretching": [_G, _P, _P, _P, _D, _S],
+    "axb_reduce_max_abs_sum": [_G, _P, _P, _P, _S],
+    "axb_reduce_max": [_G, _P, _P, _S],
+    "axb_reduce_weighted_sum": [_G, _P, _P, _P, _D, _P, _S],
+    "axb_fill_scalars": [_P, _I, _D, _S],
+    "axb_rigid_flow_scalars": [_I, _P, _D, _D, _D, _D, _D, _S],
+    "axb_solid_sigma": [_G, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P, _P, _S],
+    "axb_solid_tau": [_G, _P, _P, _P, _P, _P, _P, _S],
+    "axb_solid_vorticity_update": [_G, _P, _P, _P, _D, _P, _S],
+    "axb_ls_workspace_bytes": [_I, _I],
+    "axb_ls_extrapolate_order1": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
+    "axb_ls_extrapolate_eta": [_G, _P, _P, _P, _P, _D, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
+    "axb_p2m_mp4_2d": [_I, _I, _P, _P, _P, _P, _D, _D, _I, _S],
+    "axb_advect_vorticity_particles": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _I, _S],
+    "axb_fd_solve": [POINTER(AxbFdPlan), _P, c_int64, _P, c_int64, _S],
+    "axb_dgemm": [_I, _I, _I, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _D, _D, _S],
+    "axb_halo_pack": [_G, _P, _P, _P, _I, _S],
+    "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],
+    "axb_slab_to_blocks": [_I, _I, c_int64, _I, _P, _P, _S],
+    "axb_blocks_to_rows": [_I, _I, _I, _P, _P, c_int64, _S],
+    "axb_rows_to_blocks": [_I, _I, _I, _P, c_int64, _P, _S],
+    "axb_blocks_to_slab": [_I, _I, c_int64, _I, _P, _P, _S],
+}
+_RESTYPE = {"axb_launch_count": c_int64, "axb_ls_workspace_bytes": c_int64}
+_NO_CHECK = {"axb_version", "axb_launch_count", "axb_ls_workspace_bytes"}
+
+_ERR = {-1: "AXB_EINVAL (null pointer / bad shape)", -2: "AXB_EALIGN (misaligned pointer)",
+        -3: "AXB_ENOSUP (unsupported configuration)", -4: "AXB_EWORK (workspace too small)"}
+
+_lib = None
+
+
+def exported_names():
+    """Entry points include/axisym_b200.h declares (used by the CPU-side symbol test)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen the library and attach prototypes; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AxbError(
+                f"{LIB_PATH} is missing: build it with `make -C pyaxisymflow_b200/csrc` "
+                "(there is deliberately no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Call an entry point and turn a non-zero return code into an exception."""
+    rc = getattr(load(), name)(*args)
+    if name in _NO_CHECK:
+        return rc
+    if rc != 0:
+        what = _ERR.get(rc, f"cudaError_t {rc}" if rc > 0 else f"error {rc}")
+        raise AxbError(f"{name} failed: {what}")
+    return 0
+
+
+def launch_count():
+    return int(load().axb_launch_count())

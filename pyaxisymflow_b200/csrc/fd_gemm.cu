@@ -1,0 +1,292 @@
+// fd_gemm.cu -- fusion group G-FD: the fast-diagonalisation solve as four FP64
+// tensor-core GEMMs (reference
+// kernels/FastDiagonalisationStokesSolver.py:130-156).
+//
+// tcgen05.mma has no FP64 kind (f16 / tf32 / f8f6f4 / i8 / mx only), so on sm_100a FP64
+// tensor math is the warp-level DMMA path: mma.sync.aligned.m8n8k4.f64.  The kernel is a
+// row-major "NN" GEMM  C[M,N] = A[M,K] * B[K,N]  (all four transforms of the solve have this
+// form once the factors are stored the way the plan stores them):
+//   * 128 x 128 x 16 CTA tile, 8 warps as 2 (M) x 4 (N), 64 x 32 warp tile = 8 x 4 DMMA tiles,
+//     64 FP64 accumulators per thread, one CTA per SM;
+//   * 4-stage cp.async (LDGSTS, 16-byte) ring into XOR-swizzled shared memory: the 32-byte
+//     chunk index is XORed with (row & 3) so that the 64-bit fragment loads of every
+//     half-warp hit 16 distinct 8-byte bank pairs (conflict free for both operands);
+//   * grouped tile rasterisation (8 tile-rows per group) so a wave of 148 CTAs re-uses A and
+//     B panels out of the 126 MB L2 instead of HBM;
+//   * epilogue fused scaling  C = acc * 1/(c0 + c1*(lam_n[n] + lam_m[m]))  -- the elementwise
+//     1/lambda product of the reference (FastDiagonalisationStokesSolver.py:148-152) and the
+//     implicit-diffusion denominator (implicit_diffusion_solver.py:100-106) -- evaluated
+//     with explicit round-to-nearest adds/muls in the reference's operation order.
+// The "r o" scaling of the right-hand side is folded into the first factor at plan creation
+// (Vr^-1 diag(r)), so it costs nothing at solve time.
+#include "axb_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
+constexpr int A_STAGE = BM * BK;  // doubles
+constexpr int B_STAGE = BK * BN;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * 8;  // 131072
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// swizzled element offsets inside one stage
+__device__ __forceinline__ int a_off(int row, int col) {  // As[BM][BK]
+  return row * BK + ((((col >> 2) ^ row) & 3) << 2) + (col & 3);
+}
+__device__ __forceinline__ int b_off(int k, int col) {  // Bs[BK][BN]
+  return k * BN + ((((col >> 2) ^ (k & 3))) << 2) + (col & 3);
+}
+
+struct GemmArgs {
+  int M, N, K;
+  const double* A; long long lda;
+  const double* B; long long ldb;
+  double* C; long long ldc;
+  const double* scale_m;  // lam_r[M] or null
+  const double* scale_n;  // lam_z[N]
+  double c0, c1;
+  int tiles_m, tiles_n;
+};
+
+// VEC16: all of A, B 16-byte aligned with even leading dimensions -> 16-byte cp.async
+template <bool VEC16>
+__device__ __forceinline__ void load_stage(const GemmArgs& p, double* As, double* Bs, int m0, int n0, int k0, int tid) {
+  if (VEC16) {
+    // A: 128 rows x 8 pieces of 2 doubles
+#pragma unroll
+    for (int i = 0; i < (BM * BK / 2) / NTHREADS; ++i) {
+      const int id = tid + i * NTHREADS;
+      const int row = id >> 3, pc = id & 7;
+      const int col = pc * 2;
+      const int gm = m0 + row, gk = k0 + col;
+      // K is even on this path, so a 2-double piece is either fully inside or fully outside
+      const bool inside = (gm < p.M) && (gk < p.K);
+      const double* src = inside ? (p.A + (long long)gm * p.lda + gk) : p.A;
+      cp_async16(As + a_off(row, col), src, inside);
+    }
+    // B: 16 rows x 64 pieces
+#pragma unroll
+    for (int i = 0; i < (BK * BN / 2) / NTHREADS; ++i) {
+      const int id = tid + i * NTHREADS;
+      const int k = id >> 6, pc = id & 63;
+      const int col = pc * 2;
+      const int gk = k0 + k, gn = n0 + col;
+      const bool inside = (gk < p.K) && (gn < p.N);
+      const double* src = inside ? (p.B + (long long)gk * p.ldb + gn) : p.B;
+      cp_async16(Bs + b_off(k, col), src, inside);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / NTHREADS; ++i) {
+      const int id = tid + i * NTHREADS;
+      const int row = id >> 4, col = id & 15;
+      const int gm = m0 + row, gk = k0 + col;
+      const bool inside = (gm < p.M) && (gk < p.K);
+      const double* src = inside ? (p.A + (long long)gm * p.lda + gk) : p.A;
+      cp_async8(As + a_off(row, col), src, inside);
+    }
+#pragma unroll
+    for (int i = 0; i < (BK * BN) / NTHREADS; ++i) {
+      const int id = tid + i * NTHREADS;
+      const int k = id >> 7, col = id & 127;
+      const int gk = k0 + k, gn = n0 + col;
+      const bool inside = (gk < p.K) && (gn < p.N);
+      const double* src = inside ? (p.B + (long long)gk * p.ldb + gn) : p.B;
+      cp_async8(Bs + b_off(k, col), src, inside);
+    }
+  }
+}
+
+template <bool VEC16, bool SCALE>
+__global__ void __launch_bounds__(NTHREADS, 1) k_dgemm(GemmArgs p) {
+  extern __shared__ __align__(128) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * A_STAGE;
+
+  // grouped rasterisation: 8 tile-rows per group, column-major inside a group
+  int tile_m, tile_n;
+  {
+    const int GROUP = 8;
+    const int pid = blockIdx.x;
+    const int per_group = GROUP * p.tiles_n;
+    const int gid = pid / per_group;
+    const int first_m = gid * GROUP;
+    const int gsz = min(p.tiles_m - first_m, GROUP);
+    tile_m = first_m + (pid % per_group) % gsz;
+    tile_n = (pid % per_group) / gsz;
+  }
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * 64;  // 2 warps along M
+  const int wn0 = (warp & 3) * 32;   // 4 warps along N
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = (p.K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage<VEC16>(p, As + s * A_STAGE, Bs + s * B_STAGE, m0, n0, s * BK, tid);
+    cp_async_commit();
+  }
+
+  // per-lane invariant pieces of the swizzled fragment addresses
+  // A: row = wm0 + 8*mt + g  (row & 3 == g & 3), col = kk + t
+  // B: k = kk + t (k & 3 == t), col = wn0 + 8*nt + g
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < KT) {
+        const int s = nk % STAGES;
+        load_stage<VEC16>(p, As + s * A_STAGE, Bs + s * B_STAGE, m0, n0, nk * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double* as = As + (kt % STAGES) * A_STAGE;
+    const double* bs = Bs + (kt % STAGES) * B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) {
+        const int row = wm0 + 8 * mt + g;
+        af[mt] = as[row * BK + ((((kk >> 2) ^ g) & 3) << 2) + t];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = wn0 + 8 * nt + g;
+        bf[nt] = bs[(kk + t) * BN + (((col >> 2) ^ t) << 2) + (col & 3)];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: C fragment (8x8): row = g, cols = 2*t, 2*t + 1
+  const bool c_vec = ((p.ldc & 1) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt) {
+    const int row = m0 + wm0 + 8 * mt + g;
+    if (row >= p.M) continue;
+    double lm = 0.0;
+    if (SCALE) lm = p.scale_m[row];
+    double* crow = p.C + (long long)row * p.ldc;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = n0 + wn0 + 8 * nt + 2 * t;
+      if (col >= p.N) continue;
+      double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+      if (SCALE) {
+        const double s0 = __dadd_rn(p.scale_n[col], lm);
+        v0 = __dmul_rn(v0, 1.0 / __dadd_rn(p.c0, __dmul_rn(p.c1, s0)));
+        if (col + 1 < p.N) {
+          const double s1 = __dadd_rn(p.scale_n[col + 1], lm);
+          v1 = __dmul_rn(v1, 1.0 / __dadd_rn(p.c0, __dmul_rn(p.c1, s1)));
+        }
+      }
+      if (c_vec && col + 1 < p.N) {
+        *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
+      } else {
+        crow[col] = v0;
+        if (col + 1 < p.N) crow[col + 1] = v1;
+      }
+    }
+  }
+}
+
+int launch_dgemm(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
+                 long long ldc, const double* scale_m, const double* scale_n, double c0, double c1, cudaStream_t s) {
+  if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return AXB_EINVAL;
+  if (lda < K || ldb < N || ldc < N) return AXB_EINVAL;
+  if ((scale_m == nullptr) != (scale_n == nullptr)) return AXB_EINVAL;
+  if (!axb_al8(A) || !axb_al8(B) || !axb_al8(C)) return AXB_EALIGN;
+  GemmArgs p;
+  p.M = M; p.N = N; p.K = K;
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+  p.scale_m = scale_m; p.scale_n = scale_n; p.c0 = c0; p.c1 = c1;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + BN - 1) / BN;
+  const bool vec16 = axb_al16(A) && axb_al16(B) && !(lda & 1) && !(ldb & 1) && !(K & 1) && !(N & 1);
+  const dim3 grid(p.tiles_m * p.tiles_n);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_set = true;
+  }
+  if (vec16) {
+    if (scale_m) k_dgemm<true, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
+    else k_dgemm<true, false><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
+  } else {
+    if (scale_m) k_dgemm<false, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
+    else k_dgemm<false, false><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
+  }
+  AXB_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+              int64_t ldc, const double* scale_m, const double* scale_n, double c0, double c1,
+              axb_stream_t s) {
+  return launch_dgemm(M, N, K, A, lda, B, ldb, C, ldc, scale_m, scale_n, c0, c1, s);
+}
+
+int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
+                 axb_stream_t s) {
+  if (!p || !sol || !rhs || !p->Lr || !p->Rz || !p->Rzb || !p->Lrb || !p->lam_r || !p->lam_z || !p->work)
+    return AXB_EINVAL;
+  const int nr = p->nr, nz = p->nz;
+  double* w0 = p->work;
+  double* w1 = p->work + (long long)nr * nz;
+  int rc;
+  // T1 = Lr * rhs                       (nr x nr) (nr x nz)
+  rc = launch_dgemm(nr, nz, nr, p->Lr, nr, rhs, ld_rhs, w0, nz, nullptr, nullptr, 0, 0, s);
+  if (rc) return rc;
+  // S = (T1 * Rz) o 1/(c0 + c1 (lam_z + lam_r))
+  rc = launch_dgemm(nr, nz, nz, w0, nz, p->Rz, nz, w1, nz, p->lam_r, p->lam_z, p->c0, p->c1, s);
+  if (rc) return rc;
+  // T2 = S * Rzb
+  rc = launch_dgemm(nr, nz, nz, w1, nz, p->Rzb, nz, w0, nz, nullptr, nullptr, 0, 0, s);
+  if (rc) return rc;
+  // sol = Lrb * T2
+  return launch_dgemm(nr, nz, nr, p->Lrb, nr, w0, nz, sol, ld_sol, nullptr, nullptr, 0, 0, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+// native_core.cu -- CUDA equivalents of the reference's two C++/pybind11 core routines
+// that sit on the configured per-timestep paths:
+//
+//   G-LS   least-squares wavefront extrapolation, order 1, 3x3 patch
+//          (core/src/extrapolate_using_least_squares.hpp:136-446,
+//           lstsq/ExtrapolationConfig.hpp:131-158, lstsq/least_squares.hpp:12-59)
+//   G-P2M  MP4 particles-to-mesh remeshing, edge-clipped and periodic
+//          (core/src/interpolation/particles_to_mesh_2D.hpp:13-148, :156-324,
+//           particle_kernels/MP4.hpp:21-39, KernelWrapper.hpp:35-51)
+//
+// G-LS is data dependent (a do/while over wavefront sweeps).  Each sweep is three launches
+// over a compacted list of pending cells: classify (integer flag arithmetic, bit-exact patch
+// offsets) -> solve (one thread per candidate: 3x3 gather masked by the OLD flags, normal
+// equations, Gauss elimination with partial pivoting, evaluation) -> flag.  Reads inside a
+// sweep are masked by the pre-sweep flags and flags only flip afterwards, so the sweep is
+// order independent and the result equals the serial reference bit for bit.  The file is
+// compiled with -fmad=false and reproduces the reference's operation order, so the floating
+// point results are bit-identical to the C++ reference as well (tests assert equality).
+#include <initializer_list>
+
+#include "axb_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// G-LS
+// ---------------------------------------------------------------------------------------
+struct LsWork {
+  int* pend_a;
+  int* pend_b;
+  int* cand;
+  short* codes;    // (start_x + 3) | (start_y + 3) << 8
+  int* counters;   // [0] pending-in, [1] pending-out, [2] candidates
+  long long cap;
+};
+
+__device__ __forceinline__ short ls_start(short pos_sum, short cnt) {
+  // ExtrapolationConfig.hpp:131-158: temp is float, the quotient is evaluated in double and
+  // truncated to short; start = (2*code - 6) / 2
+  float temp = (pos_sum > 4) ? (float)(ceil(0.5 * (double)(float)pos_sum) * 2.0) : (float)pos_sum;
+  short code = (short)(2.0 * (double)temp / (double)cnt);
+  return (short)((short)(2 * code - 6) / (short)2);
+}
+
+__global__ void k_ls_collect(int n, const short* __restrict__ cur, const short* __restrict__ tgt, int* pend,
+                             int* counters, long long cap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  if (cur[c] ^ tgt[c]) {
+    const int slot = atomicAdd(&counters[0], 1);
+    if (slot < cap) pend[slot] = c;
+  }
+}
+
+// pending -> (candidate with codes | still pending)
+__global__ void k_ls_classify(int n1, const short* __restrict__ cur, const int* __restrict__ pend_in, int* pend_out,
+                              int* cand, short* codes, int* counters) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= counters[0]) return;
+  const int c = pend_in[t];
+  short cnt = 0, sx = 0, sy = 0;
+#pragma unroll
+  for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+    for (int dk = -1; dk <= 1; ++dk) {
+      const short f = cur[c + dj * n1 + dk];
+      if (dj != 0 || dk != 0) cnt += f;
+      sx += f * (short)(dk + 1);
+      sy += f * (short)(dj + 1);
+    }
+  if (cnt) {
+    const int slot = atomicAdd(&counters[2], 1);
+    cand[slot] = c;
+    codes[slot] = (short)((ls_start(sx, cnt) + 3) | ((ls_start(sy, cnt) + 3) << 8));
+  } else {
+    const int slot = atomicAdd(&counters[1], 1);
+    pend_out[slot] = c;
+  }
+}
+
+__device__ __forceinline__ void gauss3(double A[3][5], double sol[2][3]) {
+  // lstsq/least_squares.hpp:12-59 with NCoefficients = 3, NComponents = 2
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    int piv = i;
+    double best = fabs(A[i][i]);
+    for (int k = i + 1; k < 3; ++k)
+      if (fabs(A[k][i]) > best) { best = fabs(A[k][i]); piv = k; }
+    for (int k = i; k < 5; ++k) {
+      // select-based swap keeps the arrays in registers
+      const double a = A[i][k];
+      double b = a;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) if (r == piv) b = A[r][k];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) if (r == piv) A[r][k] = a;
+      A[i][k] = b;
+    }
+    for (int k = i + 1; k < 3; ++k) {
+      const double c = -A[k][i] / A[i][i];
+      A[k][i] = 0.0;
+      for (int j = i + 1; j < 5; ++j) A[k][j] += c * A[i][j];
+    }
+  }
+#pragma unroll
+  for (int comp = 0; comp < 2; ++comp)
+    for (int i = 2; i >= 0; --i) {
+      sol[comp][i] = A[i][3 + comp] / A[i][i];
+      for (int k = i - 1; k >= 0; --k) A[k][3 + comp] -= A[k][i] * sol[comp][i];
+    }
+}
+
+__global__ void k_ls_solve(int n1, const short* __restrict__ cur, const int* __restrict__ cand,
+                           const short* __restrict__ codes, const int* __restrict__ counters, double* eta_x,
+                           double* eta_y, const double* __restrict__ gx, const double* __restrict__ gy) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= counters[2]) return;
+  const int c = cand[t];
+  const int j = c / n1, k = c - j * n1;
+  const int code = codes[t];
+  const int k0 = k + ((code & 0xff) - 3), j0 = j + (((code >> 8) & 0xff) - 3);
+  double L[3][9], rhs[2][9];
+  int p = 0;
+  for (int jj = j0; jj < j0 + 3; ++jj)
+    for (int kk = k0; kk < k0 + 3; ++kk, ++p) {
+      const int gi = jj * n1 + kk;
+      const double m = (double)cur[gi];
+      L[0][p] = m;
+      L[1][p] = m * gx[kk];
+      L[2][p] = m * gy[jj];
+      // volatile-free 8-byte loads: a concurrent writer can only be an unflagged cell (m = 0)
+      rhs[0][p] = m * eta_x[gi];
+      rhs[1][p] = m * eta_y[gi];
+    }
+  double M[3][5];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) s += L[a][i] * L[b][i];
+      M[a][b] = s;
+    }
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) s += L[a][i] * rhs[d][i];
+      M[a][3 + d] = s;
+    }
+  }
+  double sol[2][3];
+  gauss3(M, sol);
+  const double basis[3] = {1.0, gx[k], gy[j]};
+  double e = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) e += sol[0][i] * basis[i];
+  eta_x[c] = e;
+  e = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) e += sol[1][i] * basis[i];
+  eta_y[c] = e;
+}
+
+__global__ void k_ls_flag(short* cur, const int* __restrict__ cand, int* counters) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < counters[2]) cur[cand[t]] = 1;
+}
+// after a sweep: pending-in <- pending-out, zero the other counters (single thread)
+__global__ void k_ls_roll(int* counters) {
+  counters[0] = counters[1];
+  counters[1] = 0;
+  counters[2] = 0;
+}
+
+LsWork carve(void* work, long long cap) {
+  LsWork w;
+  char* p = (char*)work;
+  w.counters = (int*)p; p += 64;
+  w.pend_a = (int*)p; p += cap * 4;
+  w.pend_b = (int*)p; p += cap * 4;
+  w.cand = (int*)p; p += cap * 4;
+  w.codes = (short*)p;
+  w.cap = cap;
+  return w;
+}
+inline long long ls_cap_from_bytes(long long bytes) { return (bytes - 64) / 14; }
+
+int ls_run(int n0, int n1, short* cur, const short* tgt, double* eta_x, double* eta_y, const double* gx,
+           const double* gy, void* work, long long work_bytes, int max_sweeps, int* sweeps_host, cudaStream_t s) {
+  const long long cap = ls_cap_from_bytes(work_bytes);
+  if (cap < 1) return AXB_EWORK;
+  LsWork w = carve(work, cap);
+  const int n = n0 * n1;
+  cudaMemsetAsync(w.counters, 0, 64, s);
+  k_ls_collect<<<(n + 255) / 256, 256, 0, s>>>(n, cur, tgt, w.pend_a, w.counters, cap);
+  AXB_LAUNCHED();
+  int h[3] = {0, 0, 0};
+  cudaMemcpyAsync(h, w.counters, sizeof(h), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return (int)e;
+  if (h[0] > cap) return AXB_EWORK;
+  int pending = h[0], sweeps = 0;
+  int *pin = w.pend_a, *pout = w.pend_b;
+  while (pending > 0 && (max_sweeps <= 0 || sweeps < max_sweeps)) {
+    const int blocks = (pending + 127) / 128;
+    k_ls_classify<<<blocks, 128, 0, s>>>(n1, cur, pin, pout, w.cand, w.codes, w.counters);
+    k_ls_solve<<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters, eta_x, eta_y, gx, gy);
+    k_ls_flag<<<blocks, 128, 0, s>>>(cur, w.cand, w.counters);
+    g_axb_launches += 3;
+    cudaMemcpyAsync(h, w.counters, sizeof(h), cudaMemcpyDeviceToHost, s);
+    k_ls_roll<<<1, 1, 0, s>>>(w.counters);
+    AXB_LAUNCHED();
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return (int)e;
+    if (h[2] == 0) break;  // nothing could be added: the reference returns here
+    ++sweeps;
+    pending = h[1];
+    int* t = pin; pin = pout; pout = t;
+  }
+  if (sweeps_host) *sweeps_host = sweeps;
+  return (int)cudaGetLastError();
+}
+
+// fill of the doubled work arrays, elasto_kernels/extrapolate_eta_using_least_squares_unb.py:20-25
+// + the flag construction of elasto_kernels/extrapolate_using_least_squares.py:33-36
+__global__ void k_ls_fill(int nr, int nz, long long ld, const double* __restrict__ phi,
+                          const unsigned char* __restrict__ inside, const double* __restrict__ eta1,
+                          const double* __restrict__ eta2, double zone, short* cur, short* tgt, double* e1,
+                          double* e2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k >= nz) return;
+  const long long src = (long long)j * ld + k;
+  const double p = -phi[src];
+  const double m = (double)inside[(long long)j * nz + k];  // the mask is a dense (nr, nz) bool array
+  const double a = m * eta1[src], b = m * eta2[src];
+  const short c = (short)(p < 0), t = (short)(p < zone);
+  const long long up = (long long)(nr + j) * nz + k, dn = (long long)(nr - 1 - j) * nz + k;
+  cur[up] = c; cur[dn] = c;
+  tgt[up] = t; tgt[dn] = t;
+  e1[up] = a; e1[dn] = a;
+  e2[up] = b; e2[dn] = -b;
+}
+__global__ void k_ls_unfill(int nr, int nz, long long ld, double* eta1, double* eta2, const double* __restrict__ e1,
+                            const double* __restrict__ e2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k >= nz) return;
+  const long long up = (long long)(nr + j) * nz + k;
+  eta1[(long long)j * ld + k] = e1[up];
+  eta2[(long long)j * ld + k] = e2[up];
+}
+
+// ---------------------------------------------------------------------------------------
+// G-P2M
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double mp4_w0(double t) { return 1.0 + t * t * (-2.5 + 1.5 * t); }
+__device__ __forceinline__ double mp4_w1(double t) { return 2.0 + t * (-4.0 + t * (2.5 - 0.5 * t)); }
+
+// weights + nearest-upper mesh index of one coordinate (particles_to_mesh_2D.hpp:214-260)
+__device__ __forceinline__ int mp4_axis(double pos, double delta, double w[4]) {
+  const double p = pos / delta;
+  const double fl = floor(p);
+  const int hi = (int)(p >= (fl + 0.5)) + (int)fl;
+#pragma unroll
+  for (int i = -2; i < 2; ++i) {
+    const double t = fabs(p - (hi + 0.5 + i));
+    w[i + 2] = (i == -2 || i == 1) ? mp4_w1(t) : mp4_w0(t);
+  }
+  return hi;
+}
+
+// scatter of one particle into a mesh of n0 x n1 whose row 0 is global row `row_off`
+// of the reference's (N0 x n1) mesh; rows outside [0, n0) are dropped (mirror half).
+__device__ __forceinline__ void mp4_scatter(double* mesh, int n0, int n1, long long ld, int N0, int row_off,
+                                            int hx, int hy, const double wx[4], const double wy[4], double v,
+                                            bool periodic) {
+  int s0 = -2, e0 = 2, s1 = -2, e1 = 2;
+  if (!periodic) {
+    if (hx - 2 < 0 || hy - 2 < 0 || hx + 2 > n1 || hy + 2 > N0) {
+      s0 = max(-2, -hx); s1 = max(-2, -hy);
+      e0 = min(2, n1 - hx); e1 = min(2, N0 - hy);
+    }
+  }
+  for (int sy = s1; sy < e1; ++sy) {
+    int row = hy + sy;
+    if (periodic) row = (row + N0) % N0;
+    row -= row_off;
+    if (row < 0 || row >= n0) continue;
+    for (int sx = s0; sx < e0; ++sx) {
+      int col = hx + sx;
+      if (periodic) col = (col + n1) % n1;
+      atomicAdd(&mesh[(long long)row * ld + col], (wy[sy + 2] * wx[sx + 2]) * v);
+    }
+  }
+}
+
+__global__ void k_p2m(int n0, int n1, const double* __restrict__ px, const double* __restrict__ py,
+                      const double* __restrict__ val, double* mesh, double dx, double dy, bool periodic) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k >= n1) return;
+  const long long id = (long long)j * n1 + k;
+  double wx[4], wy[4];
+  const int hx = mp4_axis(px[id], dx, wx);
+  const int hy = mp4_axis(py[id], dy, wy);
+  mp4_scatter(mesh, n0, n1, n1, n0, 0, hx, hy, wx, wy, val[id], periodic);
+}
+
+// kernels/advect_particle.py:18-35 for lattice particles: doubled row jd in [0, 2nr)
+__global__ void k_p2m_lattice(GridD g, double* w_out, const double* __restrict__ w_in, const double* __restrict__ u_z,
+                              const double* __restrict__ u_r, const double* __restrict__ zl, const double* __restrict__ rl,
+                              double dt, const double* __restrict__ dt_dev, bool periodic) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jd = blockIdx.y;
+  if (k >= g.nz) return;
+  if (dt_dev) dt = *dt_dev;
+  const bool upper = jd >= g.nr;
+  const int j = upper ? jd - g.nr : g.nr - 1 - jd;
+  const long long src = (long long)j * g.ld + k;
+  const double uz = u_z[src];
+  const double ur = upper ? u_r[src] : -u_r[src];
+  const double v = upper ? w_in[src] : -w_in[src];
+  const double pz = zl[k] + uz * dt;
+  const double pr = rl[jd] + ur * dt;
+  double wx[4], wy[4];
+  const int hx = mp4_axis(pz, g.dx, wx);
+  const int hy = mp4_axis(pr, g.dx, wy);
+  mp4_scatter(w_out, g.nr, g.nz, g.ld, 2 * g.nr, g.nr, hx, hy, wx, wy, v, periodic);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t axb_ls_workspace_bytes(int n0, int n1) {
+  // pending-list capacity: a quarter of the array (the reference reserves 0.15) -- the call
+  // reports AXB_EWORK if a wider band is requested; doubled float/flag staging for the
+  // fused wrapper is appended (20 bytes per cell).
+  const long long n = (long long)n0 * n1;
+  long long cap = n / 4 + 4096;
+  return 64 + cap * 14 + 256 + n * 20;
+}
+
+int axb_ls_extrapolate_order1(int n0, int n1, int16_t* cur, const int16_t* tgt, double* eta_x,
+                              double* eta_y, const double* gx, const double* gy, void* work,
+                              int64_t work_bytes, int max_sweeps, int* sweeps_host, axb_stream_t s) {
+  if (!cur || !tgt || !eta_x || !eta_y || !gx || !gy || !work || n0 < 3 || n1 < 3) return AXB_EINVAL;
+  return ls_run(n0, n1, cur, tgt, eta_x, eta_y, gx, gy, work, work_bytes, max_sweeps, sweeps_host, s);
+}
+
+int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                           double* eta1, double* eta2, double extrap_zone, const double* gx,
+                           const double* gy, void* work, int64_t work_bytes, int max_sweeps,
+                           int* sweeps_host, axb_stream_t s) {
+  if (!ball_phi || !inside_solid || !eta1 || !eta2 || !gx || !gy || !work) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  if (g->ku0 != 0 || g->ku1 != g->nz || g->nz_global != g->nz) return AXB_ENOSUP;  // single-slab only
+  const int nr = g->nr, nz = g->nz;
+  const long long n = 2LL * nr * nz;
+  // staging: e1, e2 (double), cur, tgt (int16) on the doubled grid, 256-byte aligned
+  char* p = (char*)work;
+  const long long stage = n * 20;
+  if (work_bytes < stage + 256 + 64 + 14) return AXB_EWORK;
+  double* e1 = (double*)p;
+  double* e2 = e1 + n;
+  short* cur = (short*)(e2 + n);
+  short* tgt = cur + n;
+  char* rest = (char*)(tgt + n);
+  rest = (char*)(((uintptr_t)rest + 255) & ~(uintptr_t)255);
+  const long long rest_bytes = work_bytes - (rest - p);
+  dim3 grd((nz + 127) / 128, nr);
+  k_ls_fill<<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1, eta2, extrap_zone, cur, tgt, e1, e2);
+  AXB_LAUNCHED();
+  rc = ls_run(2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, s);
+  if (rc) return rc;
+  k_ls_unfill<<<grd, 128, 0, s>>>(nr, nz, g->ld, eta1, eta2, e1, e2);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const double* val, double* mesh,
+                   double dx, double dy, int periodic, axb_stream_t s) {
+  if (!px || !py || !val || !mesh || n0 < 1 || n1 < 1) return AXB_EINVAL;
+  cudaMemsetAsync(mesh, 0, sizeof(double) * (size_t)n0 * n1, s);
+  k_p2m<<<dim3((n1 + 127) / 128, n0), 128, 0, s>>>(n0, n1, px, py, val, mesh, dx, dy, periodic != 0);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
+                                   const double* u_r, const double* zl1d, const double* rl1d, double dt,
+                                   const double* dt_dev, int periodic, axb_stream_t s) {
+  if (!w_out || !w_in || !u_z || !u_r || !zl1d || !rl1d || w_out == w_in) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  if (g->ku0 != 0 || g->ku1 != g->nz || g->nz_global != g->nz) return AXB_ENOSUP;
+  const GridD d = to_dev(g);
+  cudaMemset2DAsync(w_out, d.ld * sizeof(double), 0, d.nz * sizeof(double), d.nr, s);
+  k_p2m_lattice<<<dim3((d.nz + 127) / 128, 2 * d.nr), 128, 0, s>>>(d, w_out, w_in, u_z, u_r, zl1d, rl1d, dt, dt_dev,
+                                                                  periodic != 0);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+}  // extern "C"

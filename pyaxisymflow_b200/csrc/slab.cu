@@ -1,0 +1,117 @@
+// slab.cu -- z-slab plumbing for multi-GPU runs: halo pack / unpack for the
+// width-2 z halos, and the block reshuffles on either side of the all-to-all transpose that
+// brackets the z-direction GEMMs of the fast-diagonalisation solve.  The exchange itself is
+// NCCL (torch.distributed) -- these kernels only make the strided columns contiguous.
+#include "axb_common.cuh"
+
+namespace {
+
+// pack: left buffer  <- owned columns [ku0, ku0+w)      (what the LEFT neighbour needs)
+//       right buffer <- owned columns [ku1-w, ku1)      (what the RIGHT neighbour needs)
+__global__ void k_halo_pack(GridD g, const double* __restrict__ f, double* __restrict__ bl, double* __restrict__ br,
+                            int w) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nr * w) return;
+  const int j = idx / w, c = idx % w;
+  const double* row = f + (long long)j * g.ld;
+  if (bl) bl[idx] = row[g.ku0 + c];
+  if (br) br[idx] = row[g.ku1 - w + c];
+}
+// unpack: halo columns [ku0-w, ku0) <- left buffer - shift ; [ku1, ku1+w) <- right buffer + shift
+__global__ void k_halo_unpack(GridD g, double* __restrict__ f, const double* __restrict__ bl,
+                              const double* __restrict__ br, int w, double shift) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nr * w) return;
+  const int j = idx / w, c = idx % w;
+  double* row = f + (long long)j * g.ld;
+  if (bl) row[g.ku0 - w + c] = bl[idx] - shift;
+  if (br) row[g.ku1 + c] = br[idx] + shift;
+}
+
+// slab (nr x nzl, pitch ld)  ->  P contiguous blocks, block q = rows [q*nrl, (q+1)*nrl) x nzl
+__global__ void k_slab_to_blocks(int nr, int nzl, long long ld, const double* __restrict__ slab,
+                                 double* __restrict__ blocks) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k < nzl) blocks[(long long)j * nzl + k] = slab[(long long)j * ld + k];
+}
+// P received blocks (block q = my rows x columns of rank q, nrl x nzl) -> rows (nrl x P*nzl)
+__global__ void k_blocks_to_rows(int nrl, int nzl, int P, const double* __restrict__ blocks, double* __restrict__ rows,
+                                 long long ldr) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, q = blockIdx.z;
+  if (k < nzl) rows[(long long)j * ldr + (long long)q * nzl + k] = blocks[((long long)q * nrl + j) * nzl + k];
+}
+__global__ void k_rows_to_blocks(int nrl, int nzl, int P, const double* __restrict__ rows, long long ldr,
+                                 double* __restrict__ blocks) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, q = blockIdx.z;
+  if (k < nzl) blocks[((long long)q * nrl + j) * nzl + k] = rows[(long long)j * ldr + (long long)q * nzl + k];
+}
+__global__ void k_blocks_to_slab(int nr, int nzl, long long ld, const double* __restrict__ blocks,
+                                 double* __restrict__ slab) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k < nzl) slab[(long long)j * ld + k] = blocks[(long long)j * nzl + k];
+}
+
+}  // namespace
+
+extern "C" {
+
+int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
+                  axb_stream_t s) {
+  if (!f || width < 1) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  if (d.ku1 - d.ku0 < width) return AXB_EINVAL;
+  const int n = d.nr * width;
+  k_halo_pack<<<(n + 255) / 256, 256, 0, s>>>(d, f, buf_left, buf_right, width);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_halo_unpack(const axb_grid_t* g, double* f, const double* buf_left, const double* buf_right,
+                    int width, double shift, axb_stream_t s) {
+  if (!f || width < 1) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  if ((buf_left && d.ku0 < width) || (buf_right && d.ku1 + width > d.nz)) return AXB_EINVAL;
+  const int n = d.nr * width;
+  k_halo_unpack<<<(n + 255) / 256, 256, 0, s>>>(d, f, buf_left, buf_right, width, shift);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_slab_to_blocks(int nr, int nzl, int64_t ld, int P, const double* slab, double* blocks,
+                       axb_stream_t s) {
+  if (!slab || !blocks || nr < 1 || nzl < 1 || P < 1 || nr % P) return AXB_EINVAL;
+  k_slab_to_blocks<<<dim3((nzl + 127) / 128, nr), 128, 0, s>>>(nr, nzl, ld, slab, blocks);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+int axb_blocks_to_rows(int nrl, int nzl, int P, const double* blocks, double* rows, int64_t ld_rows,
+                       axb_stream_t s) {
+  if (!rows || !blocks || nrl < 1 || nzl < 1 || P < 1) return AXB_EINVAL;
+  k_blocks_to_rows<<<dim3((nzl + 127) / 128, nrl, P), 128, 0, s>>>(nrl, nzl, P, blocks, rows, ld_rows);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+int axb_rows_to_blocks(int nrl, int nzl, int P, const double* rows, int64_t ld_rows, double* blocks,
+                       axb_stream_t s) {
+  if (!rows || !blocks || nrl < 1 || nzl < 1 || P < 1) return AXB_EINVAL;
+  k_rows_to_blocks<<<dim3((nzl + 127) / 128, nrl, P), 128, 0, s>>>(nrl, nzl, P, rows, ld_rows, blocks);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+int axb_blocks_to_slab(int nr, int nzl, int64_t ld, int P, const double* blocks, double* slab,
+                       axb_stream_t s) {
+  if (!slab || !blocks || nr < 1 || nzl < 1 || P < 1 || nr % P) return AXB_EINVAL;
+  k_blocks_to_slab<<<dim3((nzl + 127) / 128, nr), 128, 0, s>>>(nr, nzl, ld, blocks, slab);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+}  // extern "C"

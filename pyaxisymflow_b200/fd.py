@@ -1,0 +1,341 @@
+"""Fast-diagonalisation solvers (fusion group G-FD).
+
+Host side of SURVEY.md row a16 / a16': the three solver classes of the reference
+(kernels/FastDiagonalisationStokesSolver.py, FastDiagonalisationPotentialSolver.py,
+implicit_diffusion_solver.py) with the same constructor / ``solve`` / ``step`` signatures.
+Set-up (building the two 1-D finite-difference operators and diagonalising them) runs once
+on the host; every ``solve`` is four FP64 tensor-core GEMMs on the GPU (``axb_fd_solve``).
+
+Two ways of obtaining the eigenbases, both yielding the same solution operator
+``psi = V f(Lambda) V^-1 rhs`` (basis independent):
+
+``basis="lapack"``
+    exactly what the reference does: dense matrices, ``numpy.linalg.eig`` sorted by descending
+    eigenvalue, ``numpy.linalg.inv`` (FastDiagonalisationStokesSolver.py:109-128).  O(N^3) --
+    fine up to N ~ 2-4 k, hopeless at Nz = 16384 (~20-40 min).
+``basis="analytic"``
+    z: the operators are Toeplitz with Neumann / periodic / plain ends, whose orthonormal
+    eigenvectors are known in closed form (DCT-II cosines, Fourier pairs, DST-I sines), so
+    ``V^-1 = V^T``; the table is generated with exact integer argument reduction.
+    r: the tridiagonal ``A_r`` is made symmetric by a diagonal similarity (row 0 of the
+    Stokes operator decouples because ``A_r[0,1] = 0``) and handed to
+    ``scipy.linalg.eigh_tridiagonal``.  O(N^2).
+``basis="auto"`` picks "lapack" below 1536 points per axis, "analytic" above.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AxbFdPlan
+from .device import Stage, ptr, stream_ptr
+
+_BC_NEUMANN = "homogenous_neumann_along_z_and_r"
+_BC_NEU_PER = "homogenous_neumann_along_r_and_periodic_along_z"
+_BC_DIR_PER = "homogenous_dirichlet_along_r_and_periodic_along_z"
+
+
+# --------------------------------------------------------------------------------------
+# operator entries
+# --------------------------------------------------------------------------------------
+def radial_tridiagonal(kind, bc_type, nr, dx):
+    """(sub, diag, sup) of A_r for the three solver flavours."""
+    r = np.linspace(dx / 2, nr * dx - dx / 2, nr)
+    i2, h = 1 / dx / dx, 1 / 2 / dx
+    if kind == "stokes":
+        # P_r - D_r, P = i2*tridiag(-1,2,-1), D[i,i-1] = +h/r_i, D[i,i+1] = -h/r_i
+        sub = -i2 - h / r[1:]
+        sup = -i2 + h / r[:-1]
+        diag = np.full(nr, 2 * i2)
+        if bc_type in (_BC_NEUMANN, _BC_NEU_PER):
+            diag[-1] = i2
+            sub[-1] = -i2       # D_r[-1,-2] = 0
+    elif kind == "potential":
+        sub = i2 - h / r[1:]
+        sup = i2 + h / r[:-1]
+        diag = np.full(nr, -2 * i2)
+        if bc_type == _BC_NEUMANN:
+            diag[-1] = -i2
+            sub[-1] = i2
+    elif kind == "implicit_diffusion":
+        sub = i2 - h / r[1:]
+        sup = i2 + h / r[:-1]
+        diag = -2 * i2 - 1.0 / r ** 2
+    else:
+        raise ValueError(kind)
+    return sub, diag, sup, r
+
+
+def axial_kind(kind, bc_type):
+    """(family, sign) of A_z: family in {"neumann", "periodic", "dirichlet"}"""
+    sign = 1.0 if kind == "stokes" else -1.0
+    if kind == "implicit_diffusion":
+        return "dirichlet", sign
+    if bc_type == _BC_NEUMANN:
+        return "neumann", sign
+    if kind == "stokes" and bc_type in (_BC_NEU_PER, _BC_DIR_PER):
+        return "periodic", sign
+    return "dirichlet", sign   # unknown bc string: the reference applies no modification
+
+
+def dense_from_tridiagonal(sub, diag, sup):
+    n = diag.size
+    m = np.zeros((n, n))
+    i = np.arange(n)
+    m[i, i] = diag
+    m[i[1:], i[:-1]] = sub
+    m[i[:-1], i[1:]] = sup
+    return m
+
+
+def dense_axial(family, sign, nz, dx):
+    i2 = 1 / dx / dx
+    m = dense_from_tridiagonal(np.full(nz - 1, -i2), np.full(nz, 2 * i2), np.full(nz - 1, -i2))
+    if family == "neumann":
+        m[0, 0] = m[-1, -1] = i2
+    elif family == "periodic":
+        m[0, -1] = m[0, 1]
+        m[-1, 0] = m[-1, -2]
+    return sign * m
+
+
+# --------------------------------------------------------------------------------------
+# eigenbases
+# --------------------------------------------------------------------------------------
+def _eig_sorted(m):
+    lam, V = np.linalg.eig(m)
+    o = lam.argsort()[::-1]
+    return lam[o], V[:, o]
+
+
+def radial_basis_lapack(sub, diag, sup):
+    lam, V = _eig_sorted(dense_from_tridiagonal(sub, diag, sup))
+    return np.real(lam), np.real(V), np.real(np.linalg.inv(V))
+
+
+def _sym_tridiag_eig(sub, diag, sup):
+    """eigen-decomposition of a tridiagonal with sub*sup > 0 via diagonal symmetrisation.
+    Returns lam, V, V^-1 with A = V diag(lam) V^-1."""
+    from scipy.linalg import eigh_tridiagonal
+
+    prod = sub * sup
+    if np.any(prod <= 0):
+        raise ValueError("tridiagonal operator is not symmetrisable")
+    off = np.sign(sup) * np.sqrt(prod)
+    # d_{i+1}/d_i = sqrt(sub_i / sup_i); accumulate in log space to avoid overflow
+    logd = np.concatenate([[0.0], np.cumsum(0.5 * (np.log(np.abs(sub)) - np.log(np.abs(sup))))])
+    logd -= logd.mean()
+    d = np.exp(logd)
+    lam, Q = eigh_tridiagonal(diag, off)
+    return lam, d[:, None] * Q, Q.T / d[None, :]
+
+
+def radial_basis_analytic(sub, diag, sup):
+    n = diag.size
+    if abs(sup[0]) <= 1e-12 * abs(diag[0]):
+        # row 0 decouples: A = [[d0, 0], [a e1, T']]
+        lam_t, Vt, Vti = _sym_tridiag_eig(sub[1:], diag[1:], sup[1:])
+        d0 = diag[0]
+        # (d0 I - T') w = a e1, solved in T' eigen-coordinates
+        e1 = np.zeros(n - 1)
+        e1[0] = sub[0]
+        gap = np.min(np.abs(d0 - lam_t))
+        if gap <= 1e-9 * abs(d0):
+            # e.g. the Dirichlet-r Stokes operator with even Nr: the zero-diagonal odd block
+            # gives T' the eigenvalue 2/dx^2 = A_r[0,0] exactly, A_r has a Jordan block and is
+            # NOT diagonalisable (the reference's la.eig basis then has cond ~ 1e14 and its
+            # solve carries O(1e-2) residuals, see DESIGN.md "Reference defects").
+            raise ValueError("A_r is defective (repeated eigenvalue %.6g): fast diagonalisation is "
+                             "ill-posed for this grid/bc; basis='lapack' mimics the reference" % d0)
+        w = Vt @ ((Vti @ e1) / (d0 - lam_t))
+        lam = np.concatenate([[d0], lam_t])
+        V = np.zeros((n, n))
+        V[0, 0] = 1.0
+        V[1:, 0] = w
+        V[1:, 1:] = Vt
+        Vi = np.zeros((n, n))
+        Vi[0, 0] = 1.0
+        Vi[1:, 0] = -(Vti @ w)
+        Vi[1:, 1:] = Vti
+    else:
+        lam, V, Vi = _sym_tridiag_eig(sub, diag, sup)
+    o = lam.argsort()[::-1]
+    return lam[o], V[:, o], Vi[o, :]
+
+
+def axial_basis_lapack(family, sign, nz, dx):
+    lam, V = _eig_sorted(dense_axial(family, sign, nz, dx))
+    V = np.real(V)
+    return np.real(lam), V, np.real(np.linalg.inv(V))
+
+
+def axial_basis_analytic(family, sign, nz, dx, device="cpu"):
+    """orthonormal closed-form eigenvectors as a torch tensor V[j, k] on ``device``; V^-1 = V^T."""
+    i2 = 1 / dx / dx
+    j = torch.arange(nz, dtype=torch.int64, device=device)
+    k = torch.arange(nz, dtype=torch.int64, device=device)
+    if family == "neumann":
+        # v_k[j] = cos(pi k (2j+1) / (2N)), lam_k = (2 - 2 cos(pi k / N)) / dx^2
+        m = (k[None, :] * (2 * j[:, None] + 1)) % (4 * nz)
+        V = torch.cos(m.to(torch.float64) * (np.pi / (2 * nz)))
+        V *= np.sqrt(2.0 / nz)
+        V[:, 0] = np.sqrt(1.0 / nz)
+        lam = (2 - 2 * np.cos(np.pi * np.arange(nz) / nz)) * i2
+    elif family == "periodic":
+        # columns: 1, cos(2 pi q j/N), sin(2 pi q j/N) ..., (-1)^j
+        V = torch.empty((nz, nz), dtype=torch.float64, device=device)
+        lam = np.empty(nz)
+        V[:, 0] = np.sqrt(1.0 / nz)
+        lam[0] = 0.0
+        col = 1
+        q = 1
+        while col < nz:
+            m = ((q * j) % nz).to(torch.float64) * (2 * np.pi / nz)
+            lq = (2 - 2 * np.cos(2 * np.pi * q / nz)) * i2
+            if 2 * q == nz:
+                V[:, col] = torch.cos(m) * np.sqrt(1.0 / nz)
+                lam[col] = lq
+                col += 1
+            else:
+                V[:, col] = torch.cos(m) * np.sqrt(2.0 / nz)
+                V[:, col + 1] = torch.sin(m) * np.sqrt(2.0 / nz)
+                lam[col] = lam[col + 1] = lq
+                col += 2
+            q += 1
+    else:
+        # plain Dirichlet-type Toeplitz: v_k[j] = sin(pi (k+1)(j+1)/(N+1))
+        m = ((k[None, :] + 1) * (j[:, None] + 1)) % (2 * (nz + 1))
+        V = torch.sin(m.to(torch.float64) * (np.pi / (nz + 1))) * np.sqrt(2.0 / (nz + 1))
+        lam = (2 - 2 * np.cos(np.pi * (np.arange(nz) + 1) / (nz + 1))) * i2
+    lam = sign * lam
+    o = np.argsort(lam)[::-1].copy()
+    V = V[:, torch.as_tensor(o, device=device)].contiguous()
+    return lam[o], V
+
+
+def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="cpu"):
+    """Factor set of the solve  sol = Lrb (((Lr rhs) Rz) o 1/(c0 + c1 (lam_z (+) lam_r))) Rzb  as
+    float64 torch tensors on ``device`` (see include/axisym_b200.h, axb_fd_plan_t)."""
+    if basis == "auto":
+        basis = "lapack" if max(nr, nz) < 1536 else "analytic"
+    sub, diag, sup, r = radial_tridiagonal(kind, bc_type, nr, dx)
+    family, sign = axial_kind(kind, bc_type)
+    if basis == "lapack":
+        lam_r, Vr, Vri = radial_basis_lapack(sub, diag, sup)
+        lam_z, Vz, Vzi = axial_basis_lapack(family, sign, nz, dx)
+        Rz = torch.from_numpy(np.ascontiguousarray(Vzi.T)).to(device)
+        Rzb = torch.from_numpy(np.ascontiguousarray(Vz.T)).to(device)
+    elif basis == "analytic":
+        lam_r, Vr, Vri = radial_basis_analytic(sub, diag, sup)
+        lam_z, Vz_t = axial_basis_analytic(family, sign, nz, dx, device=device)
+        Rz = Vz_t                       # V^-T = V for an orthogonal basis
+        Rzb = Vz_t.t().contiguous()
+    else:
+        raise ValueError(f"unknown basis {basis!r}")
+    Lr = Vri * r[None, :] if kind == "stokes" else Vri   # fold  r o rhs  into the first factor
+    f = {
+        "Lr": torch.from_numpy(np.ascontiguousarray(Lr)).to(device),
+        "Lrb": torch.from_numpy(np.ascontiguousarray(Vr)).to(device),
+        "Rz": Rz, "Rzb": Rzb,
+        "lam_r": torch.from_numpy(np.ascontiguousarray(lam_r)).to(device),
+        "lam_z": torch.from_numpy(np.ascontiguousarray(lam_z)).to(device),
+        "c0": 0.0, "c1": 1.0, "basis": basis,
+    }
+    if kind == "implicit_diffusion":
+        f["c0"], f["c1"] = 1.0, -float(nu_dt)
+    return f
+
+
+def apply_factors_host(f, rhs):
+    """NumPy evaluation of the factorised solve (used only by the CPU tests of the set-up)."""
+    g = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in f.items()}
+    spec = (g["Lr"] @ rhs) @ g["Rz"]
+    spec = spec * (1.0 / (g["c0"] + g["c1"] * (g["lam_z"][None, :] + g["lam_r"][:, None])))
+    return g["Lrb"] @ (spec @ g["Rzb"])
+
+
+# --------------------------------------------------------------------------------------
+# device plan + the three reference classes
+# --------------------------------------------------------------------------------------
+class _FdBase:
+    kind = None
+
+    def _setup(self, grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, nu_dt=None):
+        if real_dtype != np.float64:
+            raise TypeError("libaxisym_b200 computes in float64 only")
+        if not torch.cuda.is_available():
+            raise _lib.AxbError("the fast-diagonalisation solve runs on the GPU only (no CPU fallback)")
+        self.dx, self.grid_size_r, self.grid_size_z = dx, grid_size_r, grid_size_z
+        self.real_dtype, self.bc_type = real_dtype, bc_type
+        self.radial_coord = np.linspace(dx / 2, grid_size_r * dx - dx / 2, grid_size_r).reshape(grid_size_r, 1)
+        self.factors = build_factors(self.kind, bc_type, grid_size_r, grid_size_z, dx, basis, nu_dt, device="cuda")
+        self.basis = self.factors["basis"]
+        # spectral buffer of the reference (FastDiagonalisationStokesSolver.py:38-39) x 2
+        self.work = torch.empty(2 * grid_size_r * grid_size_z, dtype=torch.float64, device="cuda")
+        f = self.factors
+        self.plan = AxbFdPlan(grid_size_r, grid_size_z, f["Lr"].data_ptr(), f["Rz"].data_ptr(),
+                              f["Rzb"].data_ptr(), f["Lrb"].data_ptr(), f["lam_r"].data_ptr(),
+                              f["lam_z"].data_ptr(), f["c0"], f["c1"], self.work.data_ptr())
+
+    def _solve(self, solution_field, rhs_field):
+        st = Stage()
+        sol = st.dev(solution_field, out=True)
+        rhs = st.dev(rhs_field)
+        shape = (self.grid_size_r, self.grid_size_z)
+        if tuple(sol.shape) != shape or tuple(rhs.shape) != shape:
+            raise ValueError(f"shapes {tuple(sol.shape)}, {tuple(rhs.shape)} do not match the solver grid {shape}")
+        wb = None
+        if sol.stride(1) != 1:
+            wb, sol = sol, sol.contiguous()
+        if rhs.stride(1) != 1:
+            rhs = rhs.contiguous()
+        _lib.call("axb_fd_solve", ctypes.byref(self.plan), ptr(sol), sol.stride(0), ptr(rhs), rhs.stride(0),
+                  stream_ptr())
+        if wb is not None:
+            wb.copy_(sol)
+        st.finish()
+
+
+class FastDiagonalisationStokesSolver(_FdBase):
+    """kernels/FastDiagonalisationStokesSolver.py:6-156"""
+    kind = "stokes"
+
+    def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto"):
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis)
+
+    def solve(self, solution_field, rhs_field):
+        self._solve(solution_field, rhs_field)
+
+
+class FastDiagonalisationPotentialSolver(_FdBase):
+    """kernels/FastDiagonalisationPotentialSolver.py:6-145"""
+    kind = "potential"
+
+    def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto"):
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis)
+
+    def solve(self, solution_field, rhs_field):
+        self._solve(solution_field, rhs_field)
+
+
+class ImplicitEulerDiffusionStepper(_FdBase):
+    """kernels/implicit_diffusion_solver.py:6-143"""
+    kind = "implicit_diffusion"
+
+    def __init__(self, time_step, kinematic_viscosity, grid_size_r, grid_size_z, dx, real_dtype=np.float64,
+                 basis="auto"):
+        self.time_step = time_step
+        self.nu_times_dt = self.time_step * kinematic_viscosity
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, None, basis, nu_dt=self.nu_times_dt)
+
+    def step(self, vorticity_field, dt):
+        if dt != self.time_step:
+            raise ValueError(
+                "dt should be constant throughout the simulation if using "
+                "implicit diffusion! Please use the value of dt being used "
+                "to initialize the implicit diffusion stepper")
+        # in place like the reference: the first GEMM reads the field, the last one rewrites it
+        self._solve(vorticity_field, vorticity_field)

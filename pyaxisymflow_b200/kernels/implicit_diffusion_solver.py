@@ -1,0 +1,4 @@
+"""Drop-in for ``pyaxisymflow.kernels.implicit_diffusion_solver``; implemented in :mod:`pyaxisymflow_b200.fd` (four FP64 tensor-core GEMMs)."""
+from ..fd import (  # noqa: F401
+    ImplicitEulerDiffusionStepper,
+)

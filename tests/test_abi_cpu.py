@@ -1,0 +1,97 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/axisym_b200.h declares, the ctypes table binds exactly that set, and the product path
+fails loudly (no CPU fallback) when there is no CUDA device.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from pyaxisymflow_b200 import _lib
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "axisym_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(axb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/axisym_b200.h but not exported"
+    assert names == _lib.exported_names(), "ctypes table and header disagree"
+    assert _lib.load().axb_version() == 100
+    assert _lib.launch_count() == 0
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_lib.AxbGrid) == 40        # 2*i32, i64, f64, 4*i32
+    assert _lib.AxbGrid.ld.offset == 8 and _lib.AxbGrid.dx.offset == 16 and _lib.AxbGrid.kz0.offset == 24
+    assert ctypes.sizeof(_lib.AxbFdPlan) == 8 + 6 * 8 + 2 * 8 + 8
+
+
+def test_argument_validation_without_a_gpu():
+    """error paths that return before any CUDA call"""
+    lib = _lib.load()
+    g = _lib.AxbGrid(8, 8, 4, 1.0, 0, 8, 0, 8)     # ld < nz
+    assert lib.axb_set_fixed_val(ctypes.byref(g), ctypes.c_void_p(16), 1.0, None) == -1
+    g = _lib.AxbGrid(8, 8, 8, 1.0, 0, 8, 0, 8)
+    assert lib.axb_set_fixed_val(ctypes.byref(g), None, 1.0, None) == -1
+    assert lib.axb_set_fixed_val(ctypes.byref(g), ctypes.c_void_p(12), 1.0, None) == -2   # misaligned
+    assert lib.axb_dgemm(0, 4, 4, None, 4, None, 4, None, 4, None, None, 0.0, 0.0, None) == -1
+    assert lib.axb_ls_workspace_bytes(100, 100) > 100 * 100 * 20
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from pyaxisymflow_b200 import ops
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    a = np.zeros((8, 8))
+    with pytest.raises(_lib.AxbError):
+        ops.brinkmann_penalize(1.0, 1.0, a, 0.0, 0.0, a, a, a.copy(), a.copy())
+    with pytest.raises(_lib.AxbError):
+        FastDiagonalisationStokesSolver(8, 16, 1 / 16)
+    with pytest.raises(_lib.AxbError):
+        RigidFlowStepper(16)
+
+
+def test_mirrored_module_tree_matches_the_reference_layout():
+    import importlib
+
+    for mod, names in {
+        "kernels.brinkmann_penalize": ["brinkmann_penalize"],
+        "kernels.compute_velocity_from_psi": ["compute_velocity_from_psi_unb", "compute_velocity_from_psi_periodic"],
+        "kernels.compute_vorticity_from_velocity": ["compute_vorticity_from_velocity_unb"],
+        "kernels.diffusion_RK2": ["diffusion_RK2_unb", "diffusion_RK2_periodic"],
+        "kernels.kill_boundary_vorticity_sine": ["kill_boundary_vorticity_sine_r", "kill_boundary_vorticity_sine_z"],
+        "kernels.periodic_boundary_ghost_comm": ["gen_periodic_boundary_ghost_comm"],
+        "kernels.smooth_Heaviside": ["smooth_Heaviside"],
+        "kernels.FastDiagonalisationStokesSolver": ["FastDiagonalisationStokesSolver"],
+        "kernels.FastDiagonalisationPotentialSolver": ["FastDiagonalisationPotentialSolver"],
+        "kernels.implicit_diffusion_solver": ["ImplicitEulerDiffusionStepper"],
+        "kernels.advect_vorticity_via_eno3": ["gen_advect_vorticity_via_eno3"],
+        "kernels.advect_particle": ["advect_vorticity_via_particles"],
+        "kernels.compute_forces": ["compute_force_on_body"],
+        "kernels.force_projection": ["force_projection"],
+        "kernels.vortex_stretching": ["vortex_stretching"],
+        "pyst_kernels.advection_flux": ["gen_advection_flux_conservative_eno3_pyst_kernel"],
+        "pyst_kernels.advection_timestep": ["gen_advection_timestep_euler_forward_conservative_eno3_pyst_kernel"],
+        "pyst_kernels.elementwise_ops": ["gen_elementwise_sum_pyst_kernel", "gen_set_fixed_val_pyst_kernel"],
+        "elasto_kernels.advect_refmap_via_eno3": ["gen_advect_refmap_via_eno3"],
+        "elasto_kernels.solid_sigma": ["solid_sigma"],
+        "elasto_kernels.div_tau": ["update_vorticity_from_solid_stress"],
+        "elasto_kernels.extrapolate_eta_using_least_squares_unb": ["extrapolate_eta_with_least_squares"],
+        "core.particles_to_mesh": ["particles_to_mesh_2D_unbounded_mp4", "particles_to_mesh_2D_mp4"],
+        "core.extrapolate_using_least_squares": ["extrapolate_using_least_squares_till_first_order"],
+    }.items():
+        m = importlib.import_module("pyaxisymflow_b200." + mod)
+        for n in names:
+            assert callable(getattr(m, n)), f"{mod}.{n}"

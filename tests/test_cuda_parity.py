@@ -1,0 +1,717 @@
+"""Parity of the CUDA path (through the C ABI / drop-in Python layer) against the CPU oracle.
+
+Bar (BASELINE.json north_star): FP64 results within 1e-10 relative L-infinity of the reference
+on identical inputs; integer / index work (LS flags and patch offsets, P2M cell indices, ENO3
+branch selection, ghost copies) bit exact.  Where the CUDA kernel repeats the reference's
+operation order without FMA contraction a much tighter bound is asserted.
+All tests need a GPU: run with `pytest -m gpu` on the B200 box.
+"""
+import numpy as np
+import pytest
+
+from conftest import RTOL_LINF, assert_close, golden
+from oracle import axisym_oracle as ox
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = 1e-13
+SHAPES = [(24, 56), (37, 53), (64, 128), (130, 70)]
+
+
+def _grid(nr, nz, dx=None):
+    dx = 1.0 / nz if dx is None else dx
+    z = np.linspace(dx / 2, nz * dx - dx / 2, nz)
+    r = np.linspace(dx / 2, nr * dx - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    return dx, z, r, Z, R
+
+
+def _rand(rng, nr, nz, amp=1.0):
+    dx, z, r, Z, R = _grid(nr, nz)
+    return amp * (np.sin(2 * np.pi * (Z + 0.3 * R)) * np.exp(-((Z - 0.5) ** 2 + R ** 2) / 0.05)
+                  + 0.1 * rng.standard_normal((nr, nz)))
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pyaxisymflow_b200.ops as ops
+
+    return ops
+
+
+# ---------------------------------------------------------------------------------------------
+# a9 brinkmann
+# ---------------------------------------------------------------------------------------------
+def test_brinkmann_reference_unit_test(K):
+    """tests/test_kernels/test_brinkmann_penalize.py:6-26 of the reference, run on the GPU."""
+    n = 16
+    lam, dt, chi_v, Uz, Ur = 2.0, 3.0, 4.0, 1.0, 2.0
+    chi = np.ones((n, n)) * chi_v
+    uz, ur = np.zeros((n, n)), np.zeros((n, n))
+    pz, pr = np.ones((n, n)), np.ones((n, n))
+    K.brinkmann_penalize(lam, dt, chi, Uz, Ur, uz, ur, pz, pr)
+    np.testing.assert_allclose(pz, lam * dt * Uz * chi_v / (1 + lam * dt * chi_v) * np.ones((n, n)))
+    np.testing.assert_allclose(pr, lam * dt * Ur * chi_v / (1 + lam * dt * chi_v) * np.ones((n, n)))
+
+
+def test_brinkmann_golden_and_oracle(K):
+    g = golden("brinkmann")
+    for tag, Uz, Ur in (("scalar", float(g["Uz_s"]), float(g["Ur_s"])), ("field", g["Uz_f"], g["Ur_f"])):
+        pz, pr = np.zeros_like(g["uz"]), np.zeros_like(g["uz"])
+        K.brinkmann_penalize(float(g["lam"]), float(g["dt"]), g["chi"], Uz, Ur, g["uz"], g["ur"], pz, pr)
+        assert_close(pz, g[f"pz_{tag}"], TIGHT, "pen u_z " + tag)
+        assert_close(pr, g[f"pr_{tag}"], TIGHT, "pen u_r " + tag)
+    rng = np.random.default_rng(0)
+    for nr, nz in SHAPES:
+        chi = np.clip(_rand(rng, nr, nz) + 0.5, 0, 1)
+        uz, ur = _rand(rng, nr, nz), _rand(rng, nr, nz)
+        a, b, c, d = (np.zeros((nr, nz)) for _ in range(4))
+        K.brinkmann_penalize(1e12, 1e-4, chi, 0.3, 0.0, uz, ur, a, b)
+        ox.brinkmann_penalize(1e12, 1e-4, chi, 0.3, 0.0, uz, ur, c, d)
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+# ---------------------------------------------------------------------------------------------
+# a11 velocity, a10 curl, G-PEN
+# ---------------------------------------------------------------------------------------------
+def test_velocity_from_psi(K):
+    g = golden("velocity_from_psi")
+    dx = float(g["dx"])
+    _, _, _, Z, R = _grid(*g["psi0"].shape, dx)
+    per = K.gen_periodic_boundary_ghost_comm(2)
+    for tag in ("unb", "periodic"):
+        psi = g["psi0"].copy()
+        uz, ur = np.zeros_like(psi), np.zeros_like(psi)
+        if tag == "unb":
+            K.compute_velocity_from_psi_unb(uz, ur, psi, R, dx)
+        else:
+            K.compute_velocity_from_psi_periodic(uz, ur, psi, R, dx, per)
+        assert_close(uz, g[f"uz_{tag}"], TIGHT, "u_z " + tag)
+        assert_close(ur, g[f"ur_{tag}"], TIGHT, "u_r " + tag)
+        assert np.array_equal(psi, g[f"psi_{tag}"])
+    rng = np.random.default_rng(1)
+    for nr, nz in SHAPES:
+        dx, _, _, Z, R = _grid(nr, nz)
+        psi = _rand(rng, nr, nz)
+        a, b, c, d = (np.zeros((nr, nz)) for _ in range(4))
+        K.compute_velocity_from_psi_unb(a, b, psi, R, dx)
+        ox.compute_velocity_from_psi(c, d, psi, R, dx)
+        assert np.array_equal(a, c), np.max(np.abs(a - c))
+        assert np.array_equal(b, d), np.max(np.abs(b - d))
+
+
+def test_vorticity_from_velocity(K):
+    g = golden("vorticity_from_velocity")
+    per = K.gen_periodic_boundary_ghost_comm(2)
+    for tag in ("unb", "periodic"):
+        uz, ur, v = g["uz"].copy(), g["ur"].copy(), g["vort_init"].copy()
+        if tag == "unb":
+            K.compute_vorticity_from_velocity_unb(v, uz, ur, float(g["dx"]))
+        else:
+            K.compute_vorticity_from_velocity_periodic(v, uz, ur, float(g["dx"]), per)
+        assert_close(v, g[f"vort_{tag}"], TIGHT, "curl " + tag)
+        assert np.array_equal(uz, g[f"uz_{tag}"])
+
+
+def test_fused_penalisation_block(K):
+    """G-PEN against the reference's five-call sequence (flow_past_sphere.py:155-175)."""
+    rng = np.random.default_rng(2)
+    for nr, nz in SHAPES:
+        dx, _, _, Z, R = _grid(nr, nz)
+        chi = np.clip(_rand(rng, nr, nz) + 0.4, 0, 1)
+        uz0, ur0, w0 = _rand(rng, nr, nz), _rand(rng, nr, nz), _rand(rng, nr, nz, 3.0)
+        lam, dt, Uz = 1e4, 2e-3, 0.35
+        # oracle: copy, penalise, curl of the difference, accumulate, drag sum
+        uz, ur, w = uz0.copy(), ur0.copy(), w0.copy()
+        uzu, uru = uz.copy(), ur.copy()
+        ox.brinkmann_penalize(lam, dt, chi, Uz, 0.0, uzu, uru, uz, ur)
+        pv = np.zeros_like(w)
+        ox.compute_vorticity_from_velocity(pv, uz - uzu, ur - uru, dx)
+        w += pv
+        ssum = np.sum(R * chi * (uz - Uz))
+        # fused
+        fz, fr, fw = np.zeros_like(w), np.zeros_like(w), w0.copy()
+        got = K.penalise_and_update_vorticity(fz, fr, fw, uz0, ur0, chi, lam, dt, Uz, 0.0, R, dx, want_sum=True)
+        assert np.array_equal(fz, uz) and np.array_equal(fr, ur)
+        assert_close(fw, w, TIGHT, "vorticity after penalisation")
+        assert abs(got - ssum) <= 1e-12 * max(abs(ssum), np.sum(np.abs(R * chi * (uz - Uz))))
+
+
+# ---------------------------------------------------------------------------------------------
+# a8 diffusion, a13 kill boundary, a14 heaviside, a12 ghost, misc
+# ---------------------------------------------------------------------------------------------
+def test_diffusion(K):
+    g = golden("diffusion")
+    dx = float(g["dx"])
+    _, _, _, Z, R = _grid(*g["w0"].shape, dx)
+    per = K.gen_periodic_boundary_ghost_comm(2)
+    for tag in ("unb", "periodic"):
+        w, tmp = g["w0"].copy(), np.zeros_like(g["w0"])
+        if tag == "unb":
+            K.diffusion_RK2_unb(w, tmp, R, float(g["nu"]), float(g["dt"]), dx)
+        else:
+            K.diffusion_RK2_periodic(w, tmp, R, float(g["nu"]), float(g["dt"]), dx, per)
+        assert_close(w, g[f"w_{tag}"], TIGHT, "diffusion w " + tag)
+        assert_close(tmp, g[f"tmp_{tag}"], TIGHT, "diffusion tmp " + tag)
+    rng = np.random.default_rng(3)
+    for nr, nz in SHAPES:
+        dx, _, _, Z, R = _grid(nr, nz)
+        w0 = _rand(rng, nr, nz, 2.0)
+        a, b = w0.copy(), w0.copy()
+        K.diffusion_RK2_unb(a, np.zeros_like(a), R, 1e-3, 0.2 * dx * dx / 1e-3, dx)
+        ox.diffusion_RK2(b, np.zeros_like(b), R, 1e-3, 0.2 * dx * dx / 1e-3, dx)
+        assert_close(a, b, TIGHT, f"diffusion {nr}x{nz}")
+
+
+def test_kill_boundary(K):
+    g = golden("kill_boundary")
+    dx = float(g["dx"])
+    _, _, _, Z, R = _grid(*g["w0"].shape, dx)
+    w = g["w0"].copy()
+    K.kill_boundary_vorticity_sine_z(w, Z, 3, dx)
+    assert_close(w, g["after_z"], TIGHT, "kill z")
+    K.kill_boundary_vorticity_sine_r(w, R, 3, dx)
+    assert_close(w, g["after_zr"], TIGHT, "kill r")
+    assert np.all(w[0] == 0.0)
+
+
+def test_heaviside(K):
+    g = golden("heaviside")
+    H = np.ones_like(g["phi"])
+    K.smooth_Heaviside(H, g["phi"], float(g["w"]))
+    assert_close(H, g["H"], TIGHT)
+    # analytic-sphere form against the oracle fed with the NumPy level set
+    nr, nz = 40, 96
+    dx, _, _, Z, R = _grid(nr, nz)
+    phi = -np.sqrt((Z - 0.25) ** 2 + (R - 0.0) ** 2) + 0.1
+    Href = np.zeros_like(phi)
+    ox.smooth_Heaviside(Href, phi, dx * 2 ** 0.5)
+    Hs, ps = np.zeros_like(phi), np.zeros_like(phi)
+    K.smooth_Heaviside_sphere(Hs, Z, R, 0.25, 0.0, 0.1, dx * 2 ** 0.5, phi_out=ps)
+    assert_close(ps, phi, 1e-15, "analytic phi")
+    assert_close(Hs, Href, 1e-12, "analytic-sphere Heaviside")
+
+
+def test_ghost_comm_bit_exact(K):
+    g = golden("ghost_comm")
+    a, b = g["f0"].copy(), g["f0"].copy()
+    K.gen_periodic_boundary_ghost_comm(2)(a)
+    K.gen_periodic_boundary_ghost_comm_eta(2, float(g["z_max"]), float(g["dx"]))(b)
+    assert np.array_equal(a, g["plain"])
+    assert np.array_equal(b, g["eta"])
+    with pytest.raises(AssertionError):
+        K.gen_periodic_boundary_ghost_comm(0)
+
+
+def test_misc_and_reductions(K):
+    g = golden("misc")
+    nr, nz = g["w0"].shape
+    _, _, _, Z, R = _grid(nr, nz)
+    w = g["w0"].copy()
+    K.vortex_stretching(w, g["ur"], R, float(g["dt"]))
+    assert_close(w, g["stretched"], TIGHT)
+    F = K.compute_force_on_body(R, g["chi"], 1.3, 1e4, g["uz"], 0.25, 0.01, 1e-3, 0.02)
+    assert abs(F[0] - float(g["F_pen"])) <= 1e-11 * abs(float(g["F_pen"]))
+    assert F[1] == float(g["F_un"])
+    P = K.force_projection(2.0, g["chi"], g["uz"], g["ur"], R)
+    assert abs(P[0] - float(g["proj_z"])) <= 1e-11 * abs(float(g["proj_z"]))
+    assert abs(P[1] - float(g["proj_r"])) <= 1e-11 * abs(float(g["proj_r"]))
+    # max reductions are order independent -> exact
+    assert K.max_abs_sum(g["uz"], g["ur"]) == np.amax(np.fabs(g["uz"]) + np.fabs(g["ur"]))
+    assert K.field_max(g["w0"]) == np.amax(g["w0"])
+    assert K.field_max(-np.abs(g["w0"]) - 1.0) == np.amax(-np.abs(g["w0"]) - 1.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# a1-a7, a17 ENO3
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nr,nz", SHAPES + [(8, 12), (5, 5)])
+def test_advect_vorticity_via_eno3(K, nr, nz):
+    rng = np.random.default_rng(4)
+    dx, _, _, Z, R = _grid(nr, nz)
+    w0, uz, ur = _rand(rng, nr, nz, 3.0), _rand(rng, nr, nz), _rand(rng, nr, nz)
+    dt = 0.3 * dx
+    a, b = w0.copy(), w0.copy()
+    K.gen_advect_vorticity_via_eno3(dx, nr, nz)(a, uz, ur, dt)
+    ox.advect_vorticity_via_eno3(b, uz, ur, dt, dx)
+    assert_close(a, b, 1e-14, "ENO3 vorticity")
+    # untouched rim: last two rows and two columns each side (pystencils ghost-layer rule)
+    assert np.array_equal(a[-2:], w0[-2:]) and np.array_equal(a[:, :2], w0[:, :2])
+    assert np.array_equal(a[:, -2:], w0[:, -2:])
+    if nr > 6 and nz > 6:
+        assert not np.array_equal(a[:-2, 2:-2], w0[:-2, 2:-2])
+
+
+def test_advect_vorticity_periodic_and_shape_check(K):
+    rng = np.random.default_rng(5)
+    nr, nz = 32, 72
+    dx, _, _, Z, R = _grid(nr, nz)
+    w0, uz0, ur0 = _rand(rng, nr, nz, 3.0), _rand(rng, nr, nz), _rand(rng, nr, nz)
+    per = K.gen_periodic_boundary_ghost_comm(2)
+    a, uz, ur = w0.copy(), uz0.copy(), ur0.copy()
+    K.gen_advect_vorticity_via_eno3_periodic(dx, nr, nz, per)(a, uz, ur, 0.2 * dx)
+    b, vz, vr = w0.copy(), uz0.copy(), ur0.copy()
+    ox.advect_vorticity_via_eno3(b, vz, vr, 0.2 * dx, dx, periodic_ghost=2)
+    assert_close(a, b, 1e-14, "periodic ENO3")
+    assert np.array_equal(uz, vz) and np.array_equal(ur, vr)
+    with pytest.raises(ValueError):
+        K.gen_advect_vorticity_via_eno3(dx, nr, nz)(np.zeros((nr + 1, nz)), np.zeros((nr + 1, nz)),
+                                                    np.zeros((nr + 1, nz)), 0.1)
+
+
+@pytest.mark.parametrize("nr,nz", SHAPES)
+def test_advect_refmap_via_eno3(K, nr, nz):
+    rng = np.random.default_rng(6)
+    dx, _, _, Z, R = _grid(nr, nz)
+    e1, e2 = Z + 0.02 * _rand(rng, nr, nz), R + 0.02 * _rand(rng, nr, nz)
+    uz, ur = _rand(rng, nr, nz), _rand(rng, nr, nz)
+    a1, a2, b1, b2 = e1.copy(), e2.copy(), e1.copy(), e2.copy()
+    K.gen_advect_refmap_via_eno3(dx, nr, nz)(a1, a2, uz, ur, 0.25 * dx)
+    ox.advect_refmap_via_eno3(b1, b2, uz, ur, 0.25 * dx, dx)
+    assert_close(a1, b1, 1e-14, "eta1")
+    assert_close(a2, b2, 1e-14, "eta2")
+
+
+@pytest.mark.parametrize("conservative", [True, False])
+def test_pyst_closures(K, conservative):
+    """the pystencils-style generator API on plain arrays (a1-a6), keyword arguments as in the reference"""
+    rng = np.random.default_rng(7)
+    n0, n1 = 46, 38
+    f0 = rng.standard_normal((n0, n1))
+    vel = rng.standard_normal((2, n0, n1))
+    gen_flux = (K.gen_advection_flux_conservative_eno3_pyst_kernel if conservative
+                else K.gen_advection_flux_non_conservative_eno3_pyst_kernel)
+    gen_step = (K.gen_advection_timestep_euler_forward_conservative_eno3_pyst_kernel if conservative
+                else K.gen_advection_timestep_euler_forward_non_conservative_eno3_pyst_kernel)
+    # full timestep closure
+    a, flux = f0.copy(), rng.standard_normal((n0, n1))
+    gen_step(fixed_grid_size=(n0, n1))(field=a, advection_flux=flux, velocity=vel, dt_by_dx=0.17)
+    b = f0.copy()
+    ox.eno3_step(b, vel[0].copy(), vel[1].copy(), 0.17, conservative)
+    assert_close(a, b, 1e-14, "euler step closure")
+    assert np.all(flux[:2] == 0) and np.all(flux[:, -2:] == 0)   # rim of the flux array is the fill value
+    assert_close(f0 + flux, b, 1e-14, "flux array holds the step's flux")
+    # flux-only closure accumulates into its argument
+    acc = np.full((n0, n1), 0.5)
+    gen_flux()(advection_flux=acc, field=f0, velocity=vel, inv_dx=-0.17)
+    assert_close(acc - 0.5, flux, 1e-13, "flux accumulation")
+    # fused single launch
+    c = np.zeros_like(f0)
+    K.eno3_euler_step(c, f0, vel[0].copy(), vel[1].copy(), 0.17, conservative)
+    assert_close(c, b, 1e-14, "fused euler step")
+    # elementwise helpers
+    s = np.zeros_like(f0)
+    K.gen_elementwise_sum_pyst_kernel()(sum_field=s, field_1=f0, field_2=vel[0].copy())
+    assert np.array_equal(s, f0 + vel[0])
+    K.gen_set_fixed_val_pyst_kernel()(field=s, fixed_val=2.5)
+    assert np.all(s == 2.5)
+    with pytest.raises(ValueError):
+        gen_step(fixed_grid_size=(n0 + 1, n1))(field=a, advection_flux=flux, velocity=vel, dt_by_dx=0.1)
+    with pytest.raises(AssertionError):
+        K.gen_elementwise_sum_pyst_kernel(field_type="tensor")
+
+
+def test_eno3_conservation_full_size(K):
+    """size-independent property at the C2 grid (1024 x 4096): with zero velocity on the rim the
+    conservative update telescopes, so the mirrored-domain sum changes only by rounding."""
+    import torch
+
+    nr, nz = 1024, 4096
+    dx = 1.0 / nz
+    torch.manual_seed(0)
+    zz = torch.linspace(dx / 2, 1 - dx / 2, nz, dtype=torch.float64, device="cuda")
+    rr = torch.linspace(dx / 2, nr * dx - dx / 2, nr, dtype=torch.float64, device="cuda")
+    bump = torch.exp(-((zz[None, :] - 0.5) ** 2 + (rr[:, None] - 0.12) ** 2) / 0.004)
+    w = bump * (1 + 0.1 * torch.randn((nr, nz), dtype=torch.float64, device="cuda"))
+    uz = 0.7 * bump
+    ur = -0.3 * bump * torch.sin(40 * zz)[None, :]
+    before = w.sum().item()
+    w2 = w.clone()
+    K.gen_advect_vorticity_via_eno3(dx, nr, nz)(w2, uz, ur, 0.4 * dx)
+    assert not torch.equal(w2, w)
+    # radial fluxes cancel against the mirror image only for the anti-symmetric part; the z
+    # fluxes telescope exactly -> compare against the float64 oracle on a 64-row band instead
+    a = w[:64].cpu().numpy().copy()
+    full = w.cpu().numpy()
+    ref = full.copy()
+    ox.advect_vorticity_via_eno3(ref, uz.cpu().numpy(), ur.cpu().numpy(), 0.4 * dx, dx)
+    assert_close(w2.cpu().numpy(), ref, 1e-13, "ENO3 at 1024x4096")
+    assert abs(before) > 0 and a.shape == (64, nz)
+
+
+# ---------------------------------------------------------------------------------------------
+# a16 fast diagonalisation + raw DGEMM
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 64), (130, 250, 70), (64, 100, 33), (257, 131, 129), (1, 7, 3),
+                                    (512, 384, 1024)])
+def test_dgemm_against_numpy(K, M, N, K_):
+    import ctypes
+
+    import torch
+
+    from pyaxisymflow_b200 import _lib
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+
+    rng = np.random.default_rng(8)
+    A, B = rng.standard_normal((M, K_)), rng.standard_normal((K_, N))
+    lm, ln = rng.uniform(1, 2, M), rng.uniform(1, 2, N)
+    tA, tB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    tC = torch.full((M, N), np.nan, dtype=torch.float64, device="cuda")
+    _lib.call("axb_dgemm", M, N, K_, ptr(tA), K_, ptr(tB), N, ptr(tC), N, None, None, 0.0, 0.0, stream_ptr())
+    ref = A @ B
+    scale = np.abs(A) @ np.abs(B)
+    assert np.max(np.abs(tC.cpu().numpy() - ref) / scale) < 1e-14
+    tlm, tln = torch.from_numpy(lm).cuda(), torch.from_numpy(ln).cuda()
+    _lib.call("axb_dgemm", M, N, K_, ptr(tA), K_, ptr(tB), N, ptr(tC), N, ptr(tlm), ptr(tln), 1.0, -0.25, stream_ptr())
+    ref2 = ref * (1.0 / (1.0 - 0.25 * (ln[None, :] + lm[:, None])))
+    assert np.max(np.abs(tC.cpu().numpy() - ref2) / np.abs(scale / (1.0 - 0.25 * (ln[None, :] + lm[:, None])))) < 1e-14
+    assert ctypes.sizeof(ctypes.c_void_p) == 8
+
+
+def test_fast_diagonalisation_golden(K):
+    from pyaxisymflow_b200.kernels.FastDiagonalisationStokesSolver import FastDiagonalisationStokesSolver
+    from pyaxisymflow_b200.kernels.implicit_diffusion_solver import ImplicitEulerDiffusionStepper
+
+    g = golden("fast_diag")
+    rhs, dx = g["rhs"], float(g["dx"])
+    nr, nz = rhs.shape
+    for basis in ("lapack", "analytic"):
+        for bc in ("homogenous_neumann_along_z_and_r", "homogenous_neumann_along_r_and_periodic_along_z"):
+            s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, basis=basis)
+            sol = np.zeros_like(rhs)
+            s.solve(solution_field=sol, rhs_field=rhs)
+            assert_close(sol, g["stokes_" + bc], RTOL_LINF, f"{basis} {bc}")
+        # strided right-hand side view + contiguous solution (periodic_flow_past_sphere.py:100-104)
+        s = FastDiagonalisationStokesSolver(nr, nz - 4, dx, bc_type="homogenous_neumann_along_r_and_periodic_along_z",
+                                            basis=basis)
+        sol = np.zeros((nr, nz - 4))
+        s.solve(solution_field=sol, rhs_field=rhs[:, 2:-2])
+        assert_close(sol, g["stokes_periodic_inner"], RTOL_LINF, "strided rhs")
+        st = ImplicitEulerDiffusionStepper(float(g["time_step"]), float(g["nu"]), nr, nz, dx, basis=basis)
+        w = rhs.copy()
+        st.step(vorticity_field=w, dt=float(g["time_step"]))
+        assert_close(w, g["implicit_diffusion"], RTOL_LINF, "implicit diffusion")
+        with pytest.raises(ValueError):
+            st.step(w, 0.5 * float(g["time_step"]))
+
+
+@pytest.mark.parametrize("nr,nz", [(96, 160), (128, 300), (200, 400)])
+def test_fast_diagonalisation_vs_oracle(K, nr, nz):
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
+
+    rng = np.random.default_rng(9)
+    dx = 1.0 / nz
+    rhs = _rand(rng, nr, nz, 5.0)
+    o = ox.FastDiagonalisationOracle(nr, nz, dx, "stokes")
+    ref = np.zeros_like(rhs)
+    o.solve(ref, rhs)
+    for basis in ("lapack", "analytic"):
+        s = FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis)
+        sol = np.zeros_like(rhs)
+        s.solve(sol, rhs)
+        assert_close(sol, ref, RTOL_LINF, f"stokes {basis} {nr}x{nz}")
+
+
+def test_fast_diagonalisation_residual_full_size(K):
+    """C2 grid (1024 x 4092 inner, periodic z) and an unbounded 1024 x 2048: the solution must
+    satisfy the discrete equation A_r psi + psi A_z^T = r o rhs (checked with the stencils)."""
+    import torch
+
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver, radial_tridiagonal
+
+    for nr, nz, bc, per in ((1024, 4092, "homogenous_neumann_along_r_and_periodic_along_z", True),
+                            (1024, 2048, "homogenous_neumann_along_z_and_r", False)):
+        dx = 1.0 / 4096
+        torch.manual_seed(1)
+        rhs = torch.randn((nr, nz), dtype=torch.float64, device="cuda")
+        s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, basis="analytic")
+        psi = torch.zeros_like(rhs)
+        s.solve(psi, rhs)
+        sub, diag, sup, r = radial_tridiagonal("stokes", bc, nr, dx)
+        sub, diag, sup, r = (torch.from_numpy(x).cuda() for x in (sub, diag, sup, r))
+        Ar_psi = diag[:, None] * psi
+        Ar_psi[1:] += sub[:, None] * psi[:-1]
+        Ar_psi[:-1] += sup[:, None] * psi[1:]
+        i2 = 1 / dx / dx
+        if per:
+            psi_Az = i2 * (2 * psi - torch.roll(psi, 1, 1) - torch.roll(psi, -1, 1))
+        else:
+            psi_Az = 2 * i2 * psi
+            psi_Az[:, 1:] -= i2 * psi[:, :-1]
+            psi_Az[:, :-1] -= i2 * psi[:, 1:]
+            psi_Az[:, 0] -= i2 * psi[:, 0]
+            psi_Az[:, -1] -= i2 * psi[:, -1]
+        res = Ar_psi + psi_Az - r[:, None] * rhs
+        rel = (res.abs().max() / (r[:, None] * rhs).abs().max()).item()
+        assert rel < 1e-9, rel
+
+
+# ---------------------------------------------------------------------------------------------
+# a18 / a19 solid stress
+# ---------------------------------------------------------------------------------------------
+def test_solid_stress(K):
+    g = golden("solid")
+    dx = float(g["dx"])
+    nr, nz = g["eta1"].shape
+    _, _, _, Z, R = _grid(nr, nz, dx)
+    names = ("s11", "s12", "s22", "e1z", "e1r", "e2z", "e2r")
+    o = {k: g["init_" + k].copy() for k in names}
+    K.solid_sigma(o["s11"], o["s12"], o["s22"], float(g["G"]), dx, g["eta1"], g["eta2"],
+                  o["e1z"], o["e1r"], o["e2z"], o["e2r"])
+    for k, v in o.items():
+        assert_close(v, g["out_" + k], TIGHT, "solid_sigma " + k)
+    tz, tr, w = g["init_tau_z"].copy(), g["init_tau_r"].copy(), g["w0"].copy()
+    chi = g["chi"]
+    K.update_vorticity_from_solid_stress(w, tz, tr, chi * g["out_s11"], chi * g["out_s12"], chi * g["out_s22"],
+                                         R, float(g["dt"]), dx)
+    assert_close(tz, g["out_tau_z"], TIGHT, "tau_z")
+    assert_close(tr, g["out_tau_r"], TIGHT, "tau_r")
+    assert_close(w, g["out_w"], TIGHT, "vorticity")
+    # fused blend sigma *= chi
+    o2 = {k: g["init_" + k].copy() for k in names}
+    K.solid_sigma(o2["s11"], o2["s12"], o2["s22"], float(g["G"]), dx, g["eta1"], g["eta2"],
+                  o2["e1z"], o2["e1r"], o2["e2z"], o2["e2r"], _chi=chi)
+    assert_close(o2["s11"], chi * g["out_s11"], TIGHT, "blended s11")
+    assert_close(o2["s22"], chi * g["out_s22"], TIGHT, "blended s22")
+
+
+# ---------------------------------------------------------------------------------------------
+# a20 LS extrapolation (bit exact), a21 P2M
+# ---------------------------------------------------------------------------------------------
+def test_ls_extrapolation_golden_bit_exact(K):
+    g = golden("ls_extrapolation")
+    cur, ex, ey = g["raw_cur"].copy(), g["raw_ex"].copy(), g["raw_ey"].copy()
+    sweeps = K.extrapolate_using_least_squares_till_first_order(cur, g["raw_tgt"], ex, ey, g["raw_gx"], g["raw_gy"])
+    assert sweeps > 3
+    assert np.array_equal(cur, g["raw_cur_out"])
+    assert np.array_equal(ex, g["raw_ex_out"]), np.max(np.abs(ex - g["raw_ex_out"]))
+    assert np.array_equal(ey, g["raw_ey_out"])
+    e1, e2 = g["eta1_in"].copy(), g["eta2_in"].copy()
+    nr, nz = e1.shape
+    scratch = [np.zeros((2 * nr, nz)) for _ in range(3)]
+    K.extrapolate_eta_with_least_squares(g["inside"], g["ball_phi"], e1, e2, *scratch, float(g["zone"]), nr, g["z"])
+    assert np.array_equal(e1, g["eta1_out"])
+    assert np.array_equal(e2, g["eta2_out"])
+    with pytest.raises(TypeError):   # the reference binds with noconvert: int32 flags are rejected
+        K.extrapolate_using_least_squares_till_first_order(cur.astype(np.int32), g["raw_tgt"], ex, ey,
+                                                           g["raw_gx"], g["raw_gy"])
+
+
+def test_ls_extrapolation_vs_oracle_large(K):
+    n0, n1 = 300, 420
+    yy, xx = np.meshgrid(np.arange(n0), np.arange(n1), indexing="ij")
+    d = np.sqrt((xx - 200.3) ** 2 + (yy - 140.7) ** 2) + 6 * np.sin(0.2 * xx) * np.cos(0.15 * yy)
+    cur = (d < 60).astype(np.int16)
+    tgt = (d < 75).astype(np.int16)
+    gx, gy = np.linspace(0.0, 1.0, n1), np.linspace(0.0, 0.7, n0)
+    ex = np.where(cur, np.sin(3 * gx[None, :]) + gy[:, None] ** 2, 0.0)
+    ey = np.where(cur, np.cos(2 * gy[:, None]) * gx[None, :], 0.0)
+    a = [cur.copy(), ex.copy(), ey.copy()]
+    b = [cur.copy(), ex.copy(), ey.copy()]
+    sa = K.extrapolate_using_least_squares_till_first_order(a[0], tgt, a[1], a[2], gx, gy)
+    sb = ox.extrapolate_using_least_squares_till_first_order(b[0], tgt, b[1], b[2], gx, gy)
+    assert sa == sb and sa >= 10
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # empty band: nothing to do
+    c = [tgt.copy(), ex.copy(), ey.copy()]
+    assert K.extrapolate_using_least_squares_till_first_order(c[0], tgt, c[1], c[2], gx, gy) == 0
+    assert np.array_equal(c[1], ex)
+
+
+def test_p2m(K):
+    g = golden("p2m")
+    dx = float(g["dx"])
+    mesh = np.full_like(g["mesh_unb"], 7.0)
+    K.particles_to_mesh_2D_unbounded_mp4(g["px"], g["py"], g["val"], mesh, dx, dx)
+    scale = np.max(np.abs(g["mesh_unb"]))
+    assert np.max(np.abs(mesh - g["mesh_unb"])) <= 1e-14 * scale   # atomics reorder the 16-term sums
+    K.particles_to_mesh_2D_mp4(g["pxw"], g["pyw"], g["val"], mesh, dx, dx)
+    assert np.max(np.abs(mesh - g["mesh_per"])) <= 1e-14 * np.max(np.abs(g["mesh_per"]))
+    nr = g["w0"].shape[0]
+    zp, rp, wp, w = g["Zl"].copy(), g["Rl"].copy(), 0 * g["Zl"], g["w0"].copy()
+    K.advect_vorticity_via_particles(zp, rp, wp, w, g["Zl"], g["Rl"], nr, g["uz"], g["ur"], dx, float(g["dt"]))
+    assert_close(w, g["w_adv"], 1e-14, "particle advection")
+    assert np.array_equal(wp, g["wp_after"]) and np.array_equal(zp, g["Zl"])
+    # fused lattice form (no doubled arrays)
+    w2 = np.zeros_like(g["w0"])
+    K.advect_vorticity_via_lattice_particles(w2, g["w0"], g["uz"], g["ur"], g["Zl"][0], g["Rl"][:, 0], dx,
+                                             float(g["dt"]))
+    assert_close(w2, g["w_adv"], 1e-14, "fused lattice remesh")
+    # mass conservation away from the edges: MP4 weights sum to one
+    n0, n1 = 64, 96
+    rng = np.random.default_rng(10)
+    px = (np.arange(n1)[None, :] + 0.5 + rng.uniform(-0.9, 0.9, (n0, n1))) * dx
+    py = (np.arange(n0)[:, None] + 0.5 + rng.uniform(-0.9, 0.9, (n0, n1))) * dx
+    val = np.zeros((n0, n1))
+    val[8:-8, 8:-8] = rng.standard_normal((n0 - 16, n1 - 16))
+    mesh = np.zeros((n0, n1))
+    K.particles_to_mesh_2D_unbounded_mp4(px, py, val, mesh, dx, dx)
+    assert abs(mesh.sum() - val.sum()) <= 1e-12 * np.abs(val).sum()
+
+
+# ---------------------------------------------------------------------------------------------
+# z-slab mode on one GPU: two half-domains with width-2 halos must reproduce the full result
+# ---------------------------------------------------------------------------------------------
+def test_slab_grids_reproduce_full_domain(K):
+    import ctypes
+
+    import torch
+
+    from pyaxisymflow_b200 import _lib
+    from pyaxisymflow_b200.device import make_grid, ptr, stream_ptr
+
+    rng = np.random.default_rng(11)
+    nr, nz, H = 40, 96, 2
+    dx, z, r, Z, R = _grid(nr, nz)
+    w0, uz, ur, psi = (_rand(rng, nr, nz) for _ in range(4))
+    chi = np.clip(_rand(rng, nr, nz) + 0.4, 0, 1)
+    r1 = torch.from_numpy(r).cuda()
+
+    def full(fn):
+        g = make_grid(nr, nz, nz, dx)
+        return fn(g, lambda a: torch.from_numpy(a).cuda().contiguous(), slice(0, nz))
+
+    def slabs(fn):
+        out = None
+        half = nz // 2
+        for p in range(2):
+            lo = max(0, p * half - H)
+            hi = min(nz, (p + 1) * half + H)
+            own0, own1 = p * half - lo, (p + 1) * half - lo
+            g = make_grid(nr, hi - lo, hi - lo, dx, slab=(lo, nz, own0, own1))
+            res = fn(g, lambda a: torch.from_numpy(np.ascontiguousarray(a[:, lo:hi])).cuda(), slice(own0, own1))
+            out = res if out is None else [np.concatenate([a, b], axis=1) for a, b in zip(out, res)]
+        return out
+
+    def run_adv(g, up, own):
+        wi, a, b = up(w0), up(uz), up(ur)
+        wo = torch.zeros_like(wi)
+        _lib.call("axb_advect_vorticity_eno3", ctypes.byref(g), ptr(wo), ptr(wi), ptr(a), ptr(b), 0.3 * dx, None,
+                  stream_ptr())
+        return [wo[:, own].cpu().numpy()]
+
+    def run_vel(g, up, own):
+        p = up(psi)
+        a, b = torch.zeros_like(p), torch.zeros_like(p)
+        _lib.call("axb_velocity_from_psi", ctypes.byref(g), ptr(a), ptr(b), ptr(p), ptr(r1), 0.1, 0.0, None, None,
+                  stream_ptr())
+        return [a[:, own].cpu().numpy(), b[:, own].cpu().numpy()]
+
+    def run_pen(g, up, own):
+        zu, ru, c, w = up(uz), up(ur), up(chi), up(w0)
+        a, b = torch.zeros_like(zu), torch.zeros_like(zu)
+        _lib.call("axb_penalise_update_vorticity", ctypes.byref(g), ptr(a), ptr(b), ptr(w), ptr(zu), ptr(ru), ptr(c),
+                  1e4, 2e-3, None, 0.2, 0.0, None, ptr(r1), None, stream_ptr())
+        return [a[:, own].cpu().numpy(), b[:, own].cpu().numpy(), w[:, own].cpu().numpy()]
+
+    def run_dif(g, up, own):
+        w = up(w0)
+        t = torch.zeros_like(w)
+        _lib.call("axb_diffusion_rk2_stage1", ctypes.byref(g), ptr(t), ptr(w), ptr(r1), 1e-3, 0.1 * dx, None,
+                  stream_ptr())
+        return [t[:, own].cpu().numpy()]
+
+    for fn in (run_adv, run_vel, run_pen, run_dif):
+        for a, b in zip(full(fn), slabs(fn)):
+            assert np.array_equal(a, b), fn.__name__
+
+
+# ---------------------------------------------------------------------------------------------
+# the fused device-resident timestep against the oracle-driven reference loop
+# ---------------------------------------------------------------------------------------------
+def _oracle_rigid_loop(nz, steps, periodic=False):
+    """examples/FlowPastSphere/flow_past_sphere.py:107-207 with the oracle's kernels."""
+    nr = nz // 2
+    dx = 1.0 / nz
+    z = np.linspace(dx / 2, 1 - dx / 2, nz)
+    r = np.linspace(dx / 2, 0.5 - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    U_0, r_sph, Re, lam, CFL = 1.0, 0.1, 100.0, 1e12, 0.1
+    nu = U_0 * 2 * r_sph / Re
+    T_ramp = 20 * r_sph / U_0
+    eps = np.finfo(float).eps
+    w, psi, uz, ur = (np.zeros_like(Z) for _ in range(4))
+    tmp, pv = np.zeros_like(Z), np.zeros_like(Z)
+    chi = np.zeros_like(Z)
+    ox.smooth_Heaviside(chi, -np.sqrt((Z - 0.25) ** 2 + R ** 2) + r_sph, dx * 2 ** 0.5)
+    solver = ox.FastDiagonalisationOracle(nr, nz, dx, "stokes")
+    t, cds = 0.0, []
+    for _ in range(steps):
+        ox.kill_boundary_vorticity_sine_z(w, Z, 3, dx)
+        ox.kill_boundary_vorticity_sine_r(w, R, 3, dx)
+        solver.solve(psi, w)
+        ox.compute_velocity_from_psi(uz, ur, psi, R, dx)
+        pre = np.sin(0.5 * np.pi * t / T_ramp) if t < T_ramp else 1.0
+        uz += U_0 * pre
+        dt = min(0.9 * dx ** 2 / 4 / nu, CFL * dx / (np.amax(np.fabs(uz) + np.fabs(ur)) + eps))
+        uzu, uru = uz.copy(), ur.copy()
+        ox.brinkmann_penalize(lam, dt, chi, 0.0, 0.0, uzu, uru, uz, ur)
+        ox.compute_vorticity_from_velocity(pv, uz - uzu, ur - uru, dx)
+        w += pv
+        cds.append(2 * 2 * np.pi * dx * dx * lam * np.sum(R * chi * uz) / (np.pi * r_sph ** 2))
+        ox.advect_vorticity_via_eno3(w, uz, ur, dt, dx)
+        ox.diffusion_RK2(w, tmp, R, nu, dt, dx)
+        t += dt
+    return w, psi, uz, t, cds
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_rigid_flow_stepper_matches_reference_loop(K, use_graph):
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    nz, steps = 128, 12
+    w, psi, uz, t, cds = _oracle_rigid_loop(nz, steps)
+    s = RigidFlowStepper(nz, use_graph=use_graph)
+    s.step(steps)
+    sc = s.scalars()
+    assert sc["iterations"] == steps
+    assert abs(sc["t"] - t) <= 1e-12 * t
+    # short trajectory from rest: branch flips in ENO3 cannot occur before the wake develops
+    assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity after %d steps" % steps)
+    assert_close(s.psi.cpu().numpy(), psi, 1e-9, "psi")
+    assert_close(s.u_z.cpu().numpy(), uz, 1e-9, "u_z")
+    assert abs(sc["Cd"] - cds[-1]) <= 1e-8 * abs(cds[-1])
+
+
+def test_device_field_driver_glue(K):
+    """the NumPy surface the drivers use between kernel calls on device fields"""
+    from pyaxisymflow_b200 import DeviceField
+
+    rng = np.random.default_rng(12)
+    nr, nz = 32, 64
+    dx, z, r, Zh, Rh = _grid(nr, nz)
+    Z, R = DeviceField.meshgrid(z, r)
+    assert np.array_equal(Z.get(), Zh) and np.array_equal(R.get(), Rh)
+    a_h, b_h = _rand(rng, nr, nz), _rand(rng, nr, nz)
+    a, b = DeviceField(a_h), DeviceField(b_h)
+    u = 0 * Z
+    u[...] = a.copy()
+    u[...] += 0.5 * 2.0
+    assert np.array_equal(u.get(), a_h + 1.0)
+    assert np.amax(np.fabs(a) + np.fabs(b)) == np.amax(np.fabs(a_h) + np.fabs(b_h))
+    assert abs(np.sum(R * a * b) - np.sum(Rh * a_h * b_h)) < 1e-12
+    phi = -np.sqrt((Z - 0.25) ** 2 + (R - 0.0) ** 2) + 0.1
+    assert_close(phi.get(), -np.sqrt((Zh - 0.25) ** 2 + Rh ** 2) + 0.1, 1e-15)
+    H = 0 * Z
+    K.smooth_Heaviside(H, phi, dx * 2 ** 0.5)
+    inside = H > 0.5
+    assert inside.get().dtype == np.bool_ and inside.get().sum() > 0
+    psi = DeviceField(_rand(rng, nr, nz))
+    uz, ur = 0 * Z, 0 * Z
+    K.compute_velocity_from_psi_unb(uz, ur, psi, R, dx)
+    c, d = np.zeros((nr, nz)), np.zeros((nr, nz))
+    ox.compute_velocity_from_psi(c, d, psi.get(), Rh, dx)
+    assert np.array_equal(uz.get(), c)
+    inner = psi[..., 2:-2].copy()
+    assert inner.shape == (nr, nz - 4)
+    assert np.array_equal(np.flip(a, axis=0).get(), a_h[::-1])
+    band = np.where(a > 0.2)
+    b[band] = a[band]
+    bh = b_h.copy()
+    bh[a_h > 0.2] = a_h[a_h > 0.2]
+    assert np.array_equal(b.get(), bh)
