@@ -1,0 +1,308 @@
+"""z-slab multi-GPU execution of the rigid-flow timestep.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the GPU box, gloo in the CPU
+tests of the host logic).  Rank ``p`` of ``P`` owns the columns ``[p Nz/P, (p+1) Nz/P)`` of
+every ``(Nr, Nz)`` field, stored as ``(Nr, Nz/P + 2 H)`` with a width-``H = 2`` halo -- the
+reference's ``ghost_size`` (periodic_flow_past_sphere.py:49).  The kernels of
+``libaxisym_b200`` take the slab placement in ``axb_grid_t`` (``kz0, nz_global, ku0, ku1``),
+apply the global-boundary formulas by *global* column index and only write owned columns.
+
+Communication per timestep
+  * halo exchanges with the two z-neighbours (point-to-point, 2 x Nr doubles per field and
+    side): psi (before G-VEL, width 2 so that the velocity is also valid on one halo column),
+    (vorticity, u_z) width 2 before G-ADV, the advected vorticity and the RK2 temporary width 1
+    before the two diffusion stages;
+  * one MAX all-reduce of a double for the CFL time step (and a SUM when the drag is read);
+  * the fast-diagonalisation solve: local r-transform GEMM on the slab, all-to-all transpose
+    to r-slabs ``(Nr/P, Nz)``, the two z-transform GEMMs (eigenvalue scaling fused in the first
+    one's epilogue) on whole rows, all-to-all back, local r back-transform.  Each all-to-all
+    moves ``Nr Nz 8 (P-1)/P^2`` bytes per rank.
+The r-direction (axis reflection, 1/r terms) is never split.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .device import make_grid, ptr, stream_ptr
+
+_call = _lib.call
+HALO = 2
+
+
+class SlabLayout:
+    """Pure index arithmetic of the decomposition (no device, no communication)."""
+
+    def __init__(self, nr, nz, world, rank, halo=HALO, periodic=False):
+        if nz % world or nr % world:
+            raise ValueError(f"grid {nr}x{nz} is not divisible by {world} ranks in both directions")
+        if nz // world < 2 * halo + 1:
+            raise ValueError("slabs are thinner than the stencil halo")
+        self.nr, self.nz, self.world, self.rank, self.halo, self.periodic = nr, nz, world, rank, halo, periodic
+        self.nzl = nz // world            # owned columns
+        self.nrl = nr // world            # owned rows in the transposed (r-slab) layout
+        self.nzs = self.nzl + 2 * halo    # stored columns
+        self.z_begin = rank * self.nzl    # global index of the first owned column
+        self.kz0 = self.z_begin - halo    # global index of local column 0
+        self.ku0, self.ku1 = halo, halo + self.nzl
+        self.r_begin = rank * self.nrl
+        left, right = rank - 1, rank + 1
+        if periodic:
+            left, right = left % world, right % world
+        self.left = left if left >= 0 else None
+        self.right = right if right < world else None
+
+    def grid(self, dx, ku0=None, ku1=None):
+        return make_grid(self.nr, self.nzs, self.nzs, dx,
+                         slab=(self.kz0, self.nz, self.ku0 if ku0 is None else ku0, self.ku1 if ku1 is None else ku1))
+
+    def owned(self, t):
+        """owned-column view of a stored slab field"""
+        return t[:, self.ku0:self.ku1]
+
+    def scatter_global(self, full):
+        """stored slab (with halos filled where they exist) cut out of a global array -- test helper"""
+        out = torch.zeros((self.nr, self.nzs), dtype=full.dtype, device=full.device)
+        lo, hi = max(0, self.kz0), min(self.nz, self.kz0 + self.nzs)
+        out[:, lo - self.kz0:hi - self.kz0] = full[:, lo:hi]
+        return out
+
+
+class SlabComm:
+    """Halo exchange, slab<->row transposes and scalar reductions on a SlabLayout."""
+
+    def __init__(self, layout, group=None):
+        self.L, self.group = layout, group
+        self._bufs = {}
+
+    # -- halos ----------------------------------------------------------------------------------
+    def _buffers(self, key, n, like):
+        b = self._bufs.get(key)
+        if b is None or b[0].numel() != n or b[0].device != like.device:
+            b = tuple(torch.empty(n, dtype=torch.float64, device=like.device) for _ in range(4))
+            self._bufs[key] = b
+        return b
+
+    def exchange(self, fields, width, dx=1.0):
+        """fill `width` halo columns of every field in `fields` from the z-neighbours"""
+        L = self.L
+        if L.world == 1 and not L.periodic:
+            return
+        n = L.nr * width
+        ops, pending = [], []
+        for i, f in enumerate(fields):
+            sl, sr, rl, rr = self._buffers((i, width), n, f)
+            if f.is_cuda:
+                g = L.grid(dx)
+                _call("axb_halo_pack", ctypes.byref(g), ptr(f), ptr(sl) if L.left is not None else None,
+                      ptr(sr) if L.right is not None else None, width, stream_ptr())
+            else:
+                sl.copy_(f[:, L.ku0:L.ku0 + width].reshape(-1))
+                sr.copy_(f[:, L.ku1 - width:L.ku1].reshape(-1))
+            if L.left is not None:
+                ops += [dist.P2POp(dist.isend, sl, L.left, self.group), dist.P2POp(dist.irecv, rl, L.left, self.group)]
+            if L.right is not None:
+                ops += [dist.P2POp(dist.isend, sr, L.right, self.group), dist.P2POp(dist.irecv, rr, L.right, self.group)]
+            pending.append((f, rl, rr))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for f, rl, rr in pending:
+            if f.is_cuda:
+                g = L.grid(dx)
+                _call("axb_halo_unpack", ctypes.byref(g), ptr(f), ptr(rl) if L.left is not None else None,
+                      ptr(rr) if L.right is not None else None, width, 0.0, stream_ptr())
+            else:
+                if L.left is not None:
+                    f[:, L.ku0 - width:L.ku0] = rl.view(L.nr, width)
+                if L.right is not None:
+                    f[:, L.ku1:L.ku1 + width] = rr.view(L.nr, width)
+
+    # -- transposes around the z-direction GEMMs ---------------------------------------------------
+    def slab_to_rows(self, t_slab, rows):
+        """(nr x nzl) contiguous slab  ->  (nrl x nz) rows.  Block q of the slab (rows of rank q) is
+        already contiguous, so the send side needs no packing."""
+        L = self.L
+        recv = torch.empty((L.world, L.nrl, L.nzl), dtype=torch.float64, device=t_slab.device)
+        dist.all_to_all_single(recv.view(-1), t_slab.reshape(-1), group=self.group)
+        if recv.is_cuda:
+            _call("axb_blocks_to_rows", L.nrl, L.nzl, L.world, ptr(recv), ptr(rows), rows.stride(0), stream_ptr())
+        else:
+            rows.copy_(recv.permute(1, 0, 2).reshape(L.nrl, L.nz))
+        return rows
+
+    def rows_to_slab(self, rows, t_slab):
+        """(nrl x nz) rows  ->  (nr x nzl) contiguous slab"""
+        L = self.L
+        send = torch.empty((L.world, L.nrl, L.nzl), dtype=torch.float64, device=rows.device)
+        if rows.is_cuda:
+            _call("axb_rows_to_blocks", L.nrl, L.nzl, L.world, ptr(rows), rows.stride(0), ptr(send), stream_ptr())
+        else:
+            send.copy_(rows.reshape(L.nrl, L.world, L.nzl).permute(1, 0, 2))
+        dist.all_to_all_single(t_slab.view(-1), send.view(-1), group=self.group)
+        return t_slab
+
+    def allreduce(self, t, op="max"):
+        if self.L.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def _cuda_gemm(C, A, B, scale_m=None, scale_n=None, c0=0.0, c1=1.0):
+    """C = A @ B (+ fused spectral scaling) through axb_dgemm; operands may be strided row views."""
+    M, K = A.shape
+    N = B.shape[1]
+    _call("axb_dgemm", M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0),
+          ptr(scale_m), ptr(scale_n), float(c0), float(c1), stream_ptr())
+
+
+class SlabFdSolver:
+    """Distributed fast-diagonalisation solve on z-slabs (factors replicated on every rank)."""
+
+    def __init__(self, layout, comm, factors, gemm=None):
+        self.L, self.comm, self.f = layout, comm, factors
+        self.gemm = gemm or _cuda_gemm
+        dev = factors["Lr"].device
+        L = layout
+        self.t_slab = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=dev)
+        self.rows_a = torch.empty((L.nrl, L.nz), dtype=torch.float64, device=dev)
+        self.rows_b = torch.empty((L.nrl, L.nz), dtype=torch.float64, device=dev)
+        self.lam_r_local = factors["lam_r"][L.r_begin:L.r_begin + L.nrl].contiguous()
+
+    def solve(self, psi_slab, rhs_slab):
+        L, f = self.L, self.f
+        self.gemm(self.t_slab, f["Lr"], L.owned(rhs_slab))                       # r-transform, local columns
+        self.comm.slab_to_rows(self.t_slab, self.rows_a)                          # all-to-all #1
+        self.gemm(self.rows_b, self.rows_a, f["Rz"], self.lam_r_local, f["lam_z"], f["c0"], f["c1"])
+        self.gemm(self.rows_a, self.rows_b, f["Rzb"])
+        self.comm.rows_to_slab(self.rows_a, self.t_slab)                          # all-to-all #2
+        self.gemm(L.owned(psi_slab), f["Lrb"], self.t_slab)                       # r back-transform
+
+    def flops_per_rank(self):
+        L = self.L
+        return 4.0 * L.nr * L.nr * L.nzl + 4.0 * L.nrl * L.nz * L.nz
+
+
+class SlabRigidFlowStepper:
+    """z-slab version of :class:`pyaxisymflow_b200.timestep.RigidFlowStepper` (same physics, same
+    kernels; see the module docstring for the exchanges)."""
+
+    def __init__(self, grid_size_z, grid_size_r=None, domain_AR=0.5, Re=100.0, U_0=1.0, r_sph=0.1, Z_cm=0.25,
+                 R_cm=0.0, brink_lam=1e12, CFL=0.1, basis="analytic", group=None):
+        from .fd import build_factors
+
+        if not torch.cuda.is_available():
+            raise _lib.AxbError("SlabRigidFlowStepper needs CUDA devices (no CPU fallback)")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nz = int(grid_size_z)
+        self.nr = int(grid_size_r) if grid_size_r is not None else int(domain_AR * grid_size_z)
+        self.dx = 1.0 / self.nz
+        self.L = L = SlabLayout(self.nr, self.nz, world, rank)
+        self.comm = SlabComm(L, group)
+        self.U_0, self.r_sph, self.brink_lam, self.CFL = U_0, r_sph, brink_lam, CFL
+        self.nu = U_0 * 2 * r_sph / Re
+        self.T_ramp = 20 * r_sph / U_0
+        self.dt_diff_limit = 0.9 * self.dx ** 2 / 4 / self.nu
+        dx, nr = self.dx, self.nr
+        z_full = np.linspace(0 + dx / 2, 1 - dx / 2, self.nz)
+        z_loc = np.zeros(L.nzs)
+        lo, hi = max(0, L.kz0), min(self.nz, L.kz0 + L.nzs)
+        z_loc[lo - L.kz0:hi - L.kz0] = z_full[lo:hi]
+        self.z1d = torch.from_numpy(z_loc).cuda()
+        self.r1d = torch.from_numpy(np.linspace(0 + dx / 2, nr * dx - dx / 2, nr)).cuda()
+
+        def field():
+            return torch.zeros((nr, L.nzs), dtype=torch.float64, device="cuda")
+
+        self.vorticity, self.psi = field(), field()
+        self.u_z, self.u_r, self.u_z_upen, self.u_r_upen = field(), field(), field(), field()
+        self.char_func, self._tmp, self._w2 = field(), field(), field()
+        self.state = torch.zeros(8, dtype=torch.float64, device="cuda")
+        self.grid = L.grid(dx)
+        # velocity is also evaluated on one halo column each side (needs the width-2 psi halo)
+        ext0 = L.ku0 - 1 if L.left is not None else L.ku0
+        ext1 = L.ku1 + 1 if L.right is not None else L.ku1
+        self.grid_ext = L.grid(dx, ext0, ext1)
+        # char_func on owned + halo columns directly (it is analytic)
+        gall = L.grid(dx, max(0, -L.kz0), min(L.nzs, self.nz - L.kz0))
+        _call("axb_smooth_heaviside_sphere", ctypes.byref(gall), ptr(self.char_func), None, ptr(self.z1d),
+              ptr(self.r1d), float(Z_cm), float(R_cm), float(r_sph), float(dx * 2 ** 0.5), stream_ptr())
+        self.factors = build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, self.nz, dx, basis,
+                                     device="cuda")
+        self.solver = SlabFdSolver(L, self.comm, self.factors)
+
+    def seed_vorticity(self, seed=0, amplitude=1.0):
+        """same global field as RigidFlowStepper.seed_vorticity, cut to this rank's slab"""
+        L = self.L
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(seed)
+        noise = torch.randn((self.nr, self.nz), dtype=torch.float64, device="cuda", generator=gen)
+        zf = torch.linspace(self.dx / 2, 1 - self.dx / 2, self.nz, dtype=torch.float64, device="cuda")
+        env = torch.exp(-((zf[None, :] - 0.5) ** 2 + self.r1d[:, None] ** 2) / 0.02)
+        self.vorticity.copy_(L.scatter_global(amplitude * noise * env))
+
+    def _enqueue(self, probe=None):
+        s = stream_ptr()
+        g, ge = ctypes.byref(self.grid), ctypes.byref(self.grid_ext)
+        st = self.state
+        sp = lambda i: ctypes.c_void_p(st.data_ptr() + 8 * i)  # noqa: E731
+        w, psi = self.vorticity, self.psi
+        sc = (self.U_0, self.T_ramp, 0.0, self.dt_diff_limit, self.CFL * self.dx)
+        _call("axb_rigid_flow_scalars", 0, ptr(st), *sc, s)
+        _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
+        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
+        if probe is not None:
+            probe[0].record()
+        self.solver.solve(psi, w)
+        if probe is not None:
+            probe[1].record()
+        self.comm.exchange([psi], 2, self.dx)
+        _call("axb_velocity_from_psi", ge, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(psi), ptr(self.r1d), 0.0, 0.0,
+              sp(4), sp(2), s)
+        self.comm.allreduce(st[2:3], "max")
+        _call("axb_rigid_flow_scalars", 1, ptr(st), *sc, s)
+        _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
+              ptr(self.u_r_upen), ptr(self.char_func), self.brink_lam, 0.0, sp(1), 0.0, 0.0, None, ptr(self.r1d),
+              sp(3), s)
+        self.comm.exchange([w, self.u_z], 2, self.dx)
+        _call("axb_advect_vorticity_eno3", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), 0.0, sp(1), s)
+        self.comm.exchange([self._w2], 1, self.dx)
+        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(self._w2), ptr(self.r1d), self.nu, 0.0, sp(1), s)
+        self.comm.exchange([self._tmp], 1, self.dx)
+        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0,
+              sp(1), s)
+        _call("axb_rigid_flow_scalars", 2, ptr(st), *sc, s)
+
+    def step(self, n=1):
+        for _ in range(n):
+            self._enqueue()
+
+    def step_probed(self):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._enqueue(probe=ev)
+        return ev
+
+    def solve_flops(self):
+        return self.solver.flops_per_rank()
+
+    def solver_basis(self):
+        return self.factors["basis"]
+
+    def scalars(self):
+        st = self.state.clone()
+        self.comm.allreduce(st[7:8], "sum")
+        st = st.cpu().numpy()
+        cd = 2 * 2 * np.pi * self.dx * self.dx * self.brink_lam * st[7] / (np.pi * self.r_sph ** 2)
+        return {"t": st[0], "dt": st[1], "umax": st[2], "iterations": int(st[6]), "Cd": cd}
+
+    def gather_vorticity(self):
+        """global (Nr, Nz) vorticity on every rank (diagnostics / tests)"""
+        L = self.L
+        mine = L.owned(self.vorticity).contiguous()
+        parts = [torch.empty_like(mine) for _ in range(L.world)]
+        dist.all_gather(parts, mine, group=self.comm.group)
+        return torch.cat(parts, dim=1)
