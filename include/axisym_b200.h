@@ -231,6 +231,10 @@ int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B
               int64_t ldc, const double* scale_m, const double* scale_n, double c0, double c1,
               axb_stream_t s);
 
+/* 0 (default): TMA + mbarrier pipeline when operands are 16-byte aligned; 1: force the LDGSTS
+ * (cp.async) variant.  Both feed the same DMMA main loop; tests exercise both. */
+int axb_dgemm_set_path(int force_ldgsts);
+
 /* ---- z-slab plumbing (multi-GPU): pack / unpack `width` halo columns of a field ----------- */
 int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
                   axb_stream_t s);

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "axb_advect_vorticity_particles": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _I, _S],
     "axb_fd_solve": [POINTER(AxbFdPlan), _P, c_int64, _P, c_int64, _S],
     "axb_dgemm": [_I, _I, _I, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _D, _D, _S],
+    "axb_dgemm_set_path": [_I],
     "axb_halo_pack": [_G, _P, _P, _P, _I, _S],
     "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],
     "axb_slab_to_blocks": [_I, _I, c_int64, _I, _P, _P, _S],

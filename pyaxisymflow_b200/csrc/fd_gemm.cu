@@ -19,6 +19,8 @@
 //     with explicit round-to-nearest adds/muls in the reference's operation order.
 // The "r o" scaling of the right-hand side is folded into the first factor at plan creation
 // (Vr^-1 diag(r)), so it costs nothing at solve time.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "axb_common.cuh"
 
 namespace {
@@ -225,6 +227,219 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm(GemmArgs p) {
   }
 }
 
+
+// =====================================================================================
+// TMA-fed variant (the default path): operands arrive as cp.async.bulk.tensor boxes with the
+// Blackwell swizzle mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (XOR of the 32-byte chunk index with
+// row & 3 inside 128-byte rows) -- exactly the bank-conflict-free layout of the LDGSTS variant
+// above, but written by the TMA engine: one elected thread issues 1 box for A (128 rows x 16 k)
+// and 8 boxes for B (16 k x 16 n each) per stage, so the eight DMMA warps spend no issue slots
+// on address arithmetic.  Producer/consumer hand-off is mbarrier based (full[s]: TMA
+// complete_tx; empty[s]: one arrive per warp), there is no CTA-wide barrier in the main loop,
+// so the two warps that share a tensor pipe drift out of phase and cover each other's
+// fragment-load bubbles.  Fragments are double-buffered in registers.
+// =====================================================================================
+constexpr int TMA_SMEM_BYTES = SMEM_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr unsigned STAGE_TX_BYTES = (A_STAGE + B_STAGE) * 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+template <bool SCALE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    k_dgemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned stage buffers (the swizzle is a function of the shared address bits)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  double* As = reinterpret_cast<double*>(base);
+  double* Bs = As + STAGES * A_STAGE;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Bs + STAGES * B_STAGE);
+  const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+
+  int tile_m, tile_n;
+  {
+    const int GROUP = 8;
+    const int pid = blockIdx.x;
+    const int per_group = GROUP * p.tiles_n;
+    const int gid = pid / per_group;
+    const int first_m = gid * GROUP;
+    const int gsz = min(p.tiles_m - first_m, GROUP);
+    tile_m = first_m + (pid % per_group) % gsz;
+    tile_n = (pid % per_group) / gsz;
+  }
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * 64;
+  const int wn0 = (warp & 3) * 32;
+  const int KT = (p.K + BK - 1) / BK;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, NTHREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int kt) {
+    const int s = kt % STAGES;
+    const unsigned bar = full0 + 8 * s;
+    mbar_expect_tx(bar, STAGE_TX_BYTES);
+    tma_load_2d(smem_u32(As + s * A_STAGE), &tmA, kt * BK, m0, bar);
+#pragma unroll
+    for (int i = 0; i < BN / 16; ++i)
+      tma_load_2d(smem_u32(Bs + s * B_STAGE + i * (BK * 16)), &tmB, n0 + 16 * i, kt * BK, bar);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < STAGES && s < KT; ++s) issue(s);
+  }
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // lane-invariant fragment offsets (doubles).  A: row*16 + (((kk>>2) ^ row) & 3)*4 + t with row & 3 == g & 3.
+  // B: box (col>>4) of 256 doubles, inside: k*16 + ((((col>>2)&3) ^ (k&3))<<2) + (col&3), k & 3 == t.
+  int a_row[8];
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt) a_row[mt] = (wm0 + 8 * mt + g) * BK + t;
+  int b_col[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = wn0 + 8 * nt + g;
+    b_col[nt] = (col >> 4) * (BK * 16) + t * 16 + ((((col >> 2) & 3) ^ t) << 2) + (col & 3);
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % STAGES;
+    if (tid == 0 && kt >= 1) {
+      const int kp = kt - 1 + STAGES;
+      if (kp < KT) {
+        mbar_wait(empty0 + 8 * ((kt - 1) % STAGES), ((kt - 1) / STAGES) & 1);
+        issue(kp);
+      }
+    }
+    mbar_wait(full0 + 8 * s, (kt / STAGES) & 1);
+    const double* as = As + s * A_STAGE;
+    const double* bs = Bs + s * B_STAGE;
+    double af[2][8], bf[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) af[0][mt] = as[a_row[mt] + (((0 ^ g) & 3) << 2)];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) bf[0][nt] = bs[b_col[nt]];
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      const int cur = k4 & 1, nxt = cur ^ 1;
+      if (k4 + 1 < BK / 4) {
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) af[nxt][mt] = as[a_row[mt] + ((((k4 + 1) ^ g) & 3) << 2)];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[nxt][nt] = bs[b_col[nt] + (k4 + 1) * 4 * 16];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+  }
+
+  const bool c_vec = ((p.ldc & 1) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt) {
+    const int row = m0 + wm0 + 8 * mt + g;
+    if (row >= p.M) continue;
+    double lm = 0.0;
+    if (SCALE) lm = p.scale_m[row];
+    double* crow = p.C + (long long)row * p.ldc;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = n0 + wn0 + 8 * nt + 2 * t;
+      if (col >= p.N) continue;
+      double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+      if (SCALE) {
+        const double s0 = __dadd_rn(p.scale_n[col], lm);
+        v0 = __dmul_rn(v0, 1.0 / __dadd_rn(p.c0, __dmul_rn(p.c1, s0)));
+        if (col + 1 < p.N) {
+          const double s1 = __dadd_rn(p.scale_n[col + 1], lm);
+          v1 = __dmul_rn(v1, 1.0 / __dadd_rn(p.c0, __dmul_rn(p.c1, s1)));
+        }
+      }
+      if (c_vec && col + 1 < p.N) {
+        *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
+      } else {
+        crow[col] = v0;
+        if (col + 1 < p.N) crow[col + 1] = v1;
+      }
+    }
+  }
+}
+
+// ---- host: tensor-map encoder through the runtime's driver entry point (no -lcuda needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+    cudaGetLastError();
+  }
+  return fn;
+}
+// 2-D row-major FP64 matrix (rows x cols, pitch ld): box = box_rows x 16 columns (128 bytes)
+bool encode_map(CUtensorMap* m, const double* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+int g_force_ldgsts = 0;  // axb_dgemm_set_path(1) forces the LDGSTS variant (tests exercise both)
+
 int launch_dgemm(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
                  long long ldc, const double* scale_m, const double* scale_n, double c0, double c1, cudaStream_t s) {
   if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return AXB_EINVAL;
@@ -245,7 +460,19 @@ int launch_dgemm(int M, int N, int K, const double* A, long long lda, const doub
     cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_dgemm_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES);
+    cudaFuncSetAttribute(k_dgemm_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES);
     attr_set = true;
+  }
+  // TMA path: needs 16-byte aligned bases and pitches (lda, ldb even)
+  if (!g_force_ldgsts && axb_al16(A) && axb_al16(B) && !(lda & 1) && !(ldb & 1)) {
+    CUtensorMap tmA, tmB;
+    if (encode_map(&tmA, A, M, K, lda, BM) && encode_map(&tmB, B, K, N, ldb, BK)) {
+      if (scale_m) k_dgemm_tma<true><<<grid, NTHREADS, TMA_SMEM_BYTES, s>>>(tmA, tmB, p);
+      else k_dgemm_tma<false><<<grid, NTHREADS, TMA_SMEM_BYTES, s>>>(tmA, tmB, p);
+      AXB_LAUNCHED();
+      return (int)cudaGetLastError();
+    }
   }
   if (vec16) {
     if (scale_m) k_dgemm<true, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
@@ -261,6 +488,11 @@ int launch_dgemm(int M, int N, int K, const double* A, long long lda, const doub
 }  // namespace
 
 extern "C" {
+
+int axb_dgemm_set_path(int force_ldgsts) {
+  g_force_ldgsts = force_ldgsts;
+  return AXB_OK;
+}
 
 int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
               int64_t ldc, const double* scale_m, const double* scale_n, double c0, double c1,

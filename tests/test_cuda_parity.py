@@ -346,9 +346,10 @@ def test_eno3_conservation_full_size(K):
 # ---------------------------------------------------------------------------------------------
 # a16 fast diagonalisation + raw DGEMM
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("M,N,K_", [(128, 128, 64), (130, 250, 70), (64, 100, 33), (257, 131, 129), (1, 7, 3),
-                                    (512, 384, 1024)])
-def test_dgemm_against_numpy(K, M, N, K_):
+                                    (512, 384, 1024), (256, 4092, 4092), (96, 36, 8), (300, 200, 20)])
+def test_dgemm_against_numpy(K, M, N, K_, path):
     import ctypes
 
     import torch
@@ -356,6 +357,7 @@ def test_dgemm_against_numpy(K, M, N, K_):
     from pyaxisymflow_b200 import _lib
     from pyaxisymflow_b200.device import ptr, stream_ptr
 
+    _lib.call("axb_dgemm_set_path", path)   # 0: TMA + mbarrier pipeline, 1: LDGSTS pipeline
     rng = np.random.default_rng(8)
     A, B = rng.standard_normal((M, K_)), rng.standard_normal((K_, N))
     lm, ln = rng.uniform(1, 2, M), rng.uniform(1, 2, N)
@@ -369,6 +371,19 @@ def test_dgemm_against_numpy(K, M, N, K_):
     _lib.call("axb_dgemm", M, N, K_, ptr(tA), K_, ptr(tB), N, ptr(tC), N, ptr(tlm), ptr(tln), 1.0, -0.25, stream_ptr())
     ref2 = ref * (1.0 / (1.0 - 0.25 * (ln[None, :] + lm[:, None])))
     assert np.max(np.abs(tC.cpu().numpy() - ref2) / np.abs(scale / (1.0 - 0.25 * (ln[None, :] + lm[:, None])))) < 1e-14
+    # strided operands (views with a larger pitch), as the periodic driver and the z-slabs use them
+    if K_ >= 8 and N >= 8:
+        big_a = torch.from_numpy(rng.standard_normal((M, K_ + 6))).cuda()
+        big_b = torch.from_numpy(rng.standard_normal((K_, N + 10))).cuda()
+        big_c = torch.zeros((M, N + 4), dtype=torch.float64, device="cuda")
+        va, vb, vc = big_a[:, 2:2 + K_], big_b[:, 4:4 + N], big_c[:, 2:2 + N]
+        _lib.call("axb_dgemm", M, N, K_, ptr(va), K_ + 6, ptr(vb), N + 10, ptr(vc), N + 4, None, None, 0.0, 0.0,
+                  stream_ptr())
+        refs = va.cpu().numpy() @ vb.cpu().numpy()
+        sc = np.abs(va.cpu().numpy()) @ np.abs(vb.cpu().numpy())
+        assert np.max(np.abs(vc.cpu().numpy() - refs) / sc) < 1e-14
+        assert torch.all(big_c[:, :2] == 0) and torch.all(big_c[:, 2 + N:] == 0)
+    _lib.call("axb_dgemm_set_path", 0)
     assert ctypes.sizeof(ctypes.c_void_p) == 8
 
 
