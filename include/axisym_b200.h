@@ -53,6 +53,9 @@ typedef struct axb_grid {
 int axb_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t axb_launch_count(void);
+/* 0 (default): row-marching kernels for G-VEL / G-PEN / G-ADV / G-REF / G-DIF (stencils_march.cu);
+ * 1: the 2-D tiled kernels (stencils.cu, eno3.cu) that repeat the reference's divisions bit for bit. */
+int axb_set_stencil_path(int legacy_tiled);
 
 /* ---- G-BND: kernels/kill_boundary_vorticity_sine.py:4-14 and :17-27 ------------------ */
 int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const double* z1d, int width,

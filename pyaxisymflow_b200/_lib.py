@@ -40,6 +40,7 @@ _S = c_void_p   # cudaStream_t
 _SIGNATURES = {
     "axb_version": [],
     "axb_launch_count": [],
+    "axb_set_stencil_path": [_I],
     "axb_kill_boundary_vorticity_sine_z": [_G, _P, _P, _I, _S],
     "axb_kill_boundary_vorticity_sine_r": [_G, _P, _P, _I, _S],
     "axb_periodic_ghost_comm": [_G, _P, _I, _D, _D, _S],

@@ -16,6 +16,7 @@
 #include <initializer_list>
 
 #include "axb_common.cuh"
+#include "axb_march.cuh"
 
 namespace {
 
@@ -176,6 +177,11 @@ int axb_advect_vorticity_eno3(const axb_grid_t* g, double* w_out, const double* 
   const GridD d = to_dev(g);
   if (d.nr < 5 || d.nzg < 5) return AXB_EINVAL;
   const bool vec = vec_ok(d, {w_out, w_in, u_z, u_r});
+  if (!g_axb_legacy_stencils) {
+    rc = march_eno3(1, true, true, false, d, w_out, nullptr, w_in, nullptr, u_z, u_r, 0.0, dt, dt_dev, -1.0, 0.0, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   k_eno3<1, true, true, false><<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, w_out, nullptr, w_in, nullptr, u_z, u_r, 0.0,
                                                                     dt, dt_dev, -1.0, 0.0, vec);
   AXB_LAUNCHED();
@@ -192,6 +198,12 @@ int axb_advect_refmap_eno3(const axb_grid_t* g, double* eta1_out, double* eta2_o
   const GridD d = to_dev(g);
   if (d.nr < 5 || d.nzg < 5) return AXB_EINVAL;
   const bool vec = vec_ok(d, {eta1_out, eta2_out, eta1, eta2, u_z, u_r});
+  if (!g_axb_legacy_stencils) {
+    rc = march_eno3(2, false, true, false, d, eta1_out, eta2_out, eta1, eta2, u_z, u_r, 0.0, dt, dt_dev, +1.0, -1.0,
+                    vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   k_eno3<2, false, true, false><<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, eta1_out, eta2_out, eta1, eta2, u_z, u_r,
                                                                      0.0, dt, dt_dev, +1.0, -1.0, vec);
   AXB_LAUNCHED();
@@ -206,6 +218,12 @@ int axb_eno3_flux(const axb_grid_t* g, double* flux, const double* field, const 
   const GridD d = to_dev(g);
   if (d.nr < 5 || d.nzg < 5) return AXB_OK;  // empty interior: nothing to do (pystencils loops are empty)
   const bool vec = vec_ok(d, {flux, field, vel0, vel1});
+  if (!g_axb_legacy_stencils) {
+    rc = march_eno3(1, conservative != 0, false, true, d, flux, nullptr, field, nullptr, vel0, vel1, inv_dx, 0.0,
+                    nullptr, 1.0, 1.0, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   if (conservative)
     k_eno3<1, true, false, true><<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, flux, nullptr, field, nullptr, vel0, vel1,
                                                                       inv_dx, 0.0, nullptr, 1.0, 1.0, vec);
@@ -225,6 +243,14 @@ int axb_eno3_euler_step(const axb_grid_t* g, double* field_out, const double* fi
   const bool vec = vec_ok(d, {field_out, field_in, vel0, vel1});
   // the kernel forms inv_dx = -(dt / dx); feed dt = dt_by_dx with dx = 1
   d.dx = 1.0;
+  if (d.nr < 5 || d.nzg < 5) {
+    // no interior: the step is a plain copy (the tiled kernel handles that case)
+  } else if (!g_axb_legacy_stencils) {
+    rc = march_eno3(1, conservative != 0, false, false, d, field_out, nullptr, field_in, nullptr, vel0, vel1, 0.0,
+                    dt_by_dx, nullptr, 1.0, 1.0, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   if (conservative)
     k_eno3<1, true, false, false><<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, field_out, nullptr, field_in, nullptr, vel0,
                                                                        vel1, 0.0, dt_by_dx, nullptr, 1.0, 1.0, vec);

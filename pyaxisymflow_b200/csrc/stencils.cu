@@ -12,6 +12,7 @@
 #include <initializer_list>
 
 #include "axb_common.cuh"
+#include "axb_march.cuh"
 
 namespace {
 
@@ -529,6 +530,11 @@ int axb_velocity_from_psi(const axb_grid_t* g, double* u_z, double* u_r, const d
   if (!u_z || !u_r || !psi || !r1d) return AXB_EINVAL;
   GRID_PROLOGUE(u_z, u_r, psi)
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
+  if (!g_axb_legacy_stencils) {
+    const int rc = march_velocity(d, u_z, u_r, psi, r1d, uz_add, ur_add, add_dev, umax_out, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   if (umax_out)
     k_velocity<true><<<grd, blk, 0, s>>>(d, u_z, u_r, psi, r1d, uz_add, ur_add, add_dev, umax_out, vec);
   else
@@ -574,6 +580,12 @@ int axb_penalise_update_vorticity(const axb_grid_t* g, double* u_z, double* u_r,
   if (u_z == u_z_upen || u_r == u_r_upen) return AXB_EINVAL;  // neighbours are read un-penalised
   if (sum_out && !r1d) return AXB_EINVAL;
   GRID_PROLOGUE(u_z, u_r, w, u_z_upen, u_r_upen, chi)
+  if (!g_axb_legacy_stencils) {
+    const int rc = march_penalise(d, u_z, u_r, w, u_z_upen, u_r_upen, chi, lam, dt, dt_dev, U_z, U_r, U_dev, r1d,
+                                  sum_out, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   if (sum_out)
     k_penalise<true><<<grd, blk, 0, s>>>(d, u_z, u_r, w, u_z_upen, u_r_upen, chi, lam, dt, dt_dev, U_z, U_r,
                                          U_dev, r1d, sum_out, vec);
@@ -588,6 +600,11 @@ int axb_diffusion_rk2_stage1(const axb_grid_t* g, double* tmp, const double* w, 
                              double nu, double dt, const double* dt_dev, axb_stream_t s) {
   if (!tmp || !w || !r1d || tmp == w) return AXB_EINVAL;
   GRID_PROLOGUE(tmp, w)
+  if (!g_axb_legacy_stencils) {
+    const int rc = march_diffusion(1, d, tmp, w, nullptr, r1d, nu, dt, dt_dev, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   k_diffusion<1><<<grd, blk, 0, s>>>(d, tmp, w, nullptr, r1d, nu, dt, dt_dev, vec);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
@@ -597,6 +614,11 @@ int axb_diffusion_rk2_stage2(const axb_grid_t* g, double* w, const double* w_src
                              axb_stream_t s) {
   if (!tmp || !w || !w_src || !r1d || tmp == w) return AXB_EINVAL;
   GRID_PROLOGUE(tmp, w, w_src)
+  if (!g_axb_legacy_stencils) {
+    const int rc = march_diffusion(2, d, w, tmp, w_src, r1d, nu, dt, dt_dev, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
   k_diffusion<2><<<grd, blk, 0, s>>>(d, w, tmp, w_src, r1d, nu, dt, dt_dev, vec);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();

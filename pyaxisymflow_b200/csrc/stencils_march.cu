@@ -1,0 +1,460 @@
+// stencils_march.cu -- row-marching versions of the four hot stencil passes of the rigid-flow
+// step (G-VEL, G-PEN, G-ADV/G-REF, G-DIF).
+//
+// Thread layout: a block is 128 threads = 256 adjacent z columns (two per thread, 128-bit
+// accesses) and marches over RB consecutive rows.  The r-direction neighbourhood lives in a
+// rolling register window, so every input row is loaded once per thread (the 2-D tiled
+// kernels of stencils.cu / eno3.cu re-load it for each of the 3-5 rows that use it, through
+// L1), z-neighbours of a row come from warp shuffles (lane +-1) with the two warp-edge lanes
+// falling back to L1 loads.  Per-row reciprocals 1/r are computed once per block into shared
+// memory, and FP64 divisions by the constants 2dx, dx^2 and r are multiplications by
+// reciprocals (<= 2 ulp from the reference's sequence of divisions; the parity bar is 1e-10).
+// In G-PEN each cell is penalised once and its velocity defect (u_pen - u) is kept in the
+// rolling window for the three rows that need it.  In G-ADV the r-direction face flux of row
+// j is re-used as the back face of row j+1.  Compiled with -fmad=false like stencils.cu.
+#include <math_constants.h>
+
+#include <initializer_list>
+
+#include "axb_common.cuh"
+#include "axb_march.cuh"
+
+namespace {
+
+constexpr int MT = 128;  // threads per block: 256 columns
+
+__device__ __forceinline__ const double* rowp(const double* f, long long ld, int j) { return f + (long long)j * ld; }
+__device__ __forceinline__ double* rowp(double* f, long long ld, int j) { return f + (long long)j * ld; }
+
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn_d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+// z-neighbours of a register pair: left = f[k-1], right = f[k+2].  Interior lanes take them from
+// the adjacent lanes' pairs, the warp-edge lanes (and lanes next to an inactive lane) load them.
+// `row` may be null when the caller guarantees interior lanes only.
+__device__ __forceinline__ void z_neighbours(const double2 c, const double* __restrict__ row, int k, int nz, int lane,
+                                             double& left, double& right) {
+  left = shfl_up_d(c.y);
+  right = shfl_dn_d(c.x);
+  if (lane == 0) left = (k >= 1) ? row[k - 1] : 0.0;
+  if (lane == 31 || k + 2 >= nz) right = (k + 2 < nz) ? row[k + 2] : 0.0;
+}
+
+struct Cols {
+  int k;
+  bool own0, own1;     // column k / k+1 is owned (inside [ku0, ku1))
+  bool int0, int1;     // ... and has both z neighbours inside the global domain (kg in [1, nzg-2])
+  bool valid;          // the pair starts inside the stored row
+  int ks;              // column used for stores: k, or an out-of-range column for parked lanes
+  int kg;
+};
+// Threads whose pair lies beyond the stored row stay alive (the kernels use full-mask warp shuffles):
+// they are parked on column 0 with every ownership flag false, so they load valid memory and never store.
+__device__ __forceinline__ Cols make_cols(const GridD& g) {
+  Cols c;
+  c.k = 2 * (blockIdx.x * MT + threadIdx.x);
+  c.valid = c.k < g.nz;
+  c.ks = c.valid ? c.k : (g.nz + 2);
+  if (!c.valid) c.k = 0;
+  c.kg = c.k + g.kz0;
+  c.own0 = c.valid && (c.k >= g.ku0) && (c.k < g.ku1);
+  c.own1 = c.valid && (c.k + 1 >= g.ku0) && (c.k + 1 < g.ku1);
+  c.int0 = c.own0 && (c.kg >= 1) && (c.kg <= g.nzg - 2);
+  c.int1 = c.own1 && (c.kg + 1 >= 1) && (c.kg + 1 <= g.nzg - 2);
+  return c;
+}
+
+// -------------------------------------------------------------------------------------
+// G-VEL
+// -------------------------------------------------------------------------------------
+template <bool REDUCE>
+__global__ void __launch_bounds__(MT)
+    km_velocity(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ psi,
+                const double* __restrict__ r1d, double uz_add, double ur_add, const double* __restrict__ add_dev,
+                double* umax_out, bool vec) {
+  extern __shared__ double s_inv[];
+  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
+  __syncthreads();
+  const Cols c = make_cols(g);
+  const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
+  double local_max = 0.0;
+  {
+    if (add_dev) { uz_add = add_dev[0]; ur_add = add_dev[1]; }
+    const double inv_h = 1.0 / (2 * g.dx);
+    double2 pm = make_double2(0, 0), pc = ld_pair(rowp(psi, g.ld, j0), k, nz, vec), pp = pc;
+    if (j0 > 0) pm = ld_pair(rowp(psi, g.ld, j0 - 1), k, nz, vec);
+    for (int j = j0; j < j1; ++j) {
+      const double* prow = rowp(psi, g.ld, j);
+      if (j + 1 < g.nr) pp = ld_pair(rowp(psi, g.ld, j + 1), k, nz, vec);
+      const double ir = s_inv[j - j0];
+      double2 uz;
+      if (j > 0 && j < g.nr - 1) {
+        uz.x = (pp.x - pm.x) * inv_h * ir;
+        uz.y = (pp.y - pm.y) * inv_h * ir;
+      } else if (j == 0) {
+        const double2 p2 = ld_pair(rowp(psi, g.ld, 2), k, nz, vec);
+        uz.x = (-p2.x + 4 * pp.x - 3 * pc.x) * inv_h * ir;
+        uz.y = (-p2.y + 4 * pp.y - 3 * pc.y) * inv_h * ir;
+      } else {
+        const double2 p2 = ld_pair(rowp(psi, g.ld, j - 2), k, nz, vec);
+        uz.x = (p2.x - 4 * pm.x + 3 * pc.x) * inv_h * ir;
+        uz.y = (p2.y - 4 * pm.y + 3 * pc.y) * inv_h * ir;
+      }
+      double left, right;
+      z_neighbours(pc, prow, k, nz, lane, left, right);
+      double2 ur = make_double2(0, 0);
+      if (c.int0) ur.x = -(pc.y - left) * inv_h * ir;
+      else if (c.own0 && c.kg == 0) ur.x = -(-right + 4 * pc.y - 3 * pc.x) * inv_h * ir;
+      else if (c.own0) ur.x = -(prow[k - 2] - 4 * left + 3 * pc.x) * inv_h * ir;         // kg == nzg-1
+      if (c.int1) ur.y = -(right - pc.x) * inv_h * ir;
+      else if (c.own1 && c.kg + 1 == g.nzg - 1) ur.y = -(left - 4 * pc.x + 3 * pc.y) * inv_h * ir;
+      else if (c.own1) ur.y = -(-prow[k + 3] + 4 * right - 3 * pc.y) * inv_h * ir;        // kg+1 == 0
+      uz.x += uz_add; uz.y += uz_add;
+      ur.x += ur_add; ur.y += ur_add;
+      st_pair(rowp(u_z, g.ld, j), c.ks, g.ku0, g.ku1, vec, uz);
+      st_pair(rowp(u_r, g.ld, j), c.ks, g.ku0, g.ku1, vec, ur);
+      if (REDUCE) {
+        if (c.own0) local_max = fmax(local_max, fabs(uz.x) + fabs(ur.x));
+        if (c.own1) local_max = fmax(local_max, fabs(uz.y) + fabs(ur.y));
+      }
+      pm = pc; pc = pp;
+    }
+  }
+  if (REDUCE) {
+    const double m = block_max(local_max);
+    if (threadIdx.x == 0 && m > 0.0) atomic_max_nonneg(umax_out, m);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// G-PEN
+// -------------------------------------------------------------------------------------
+struct PenRow {      // one penalised row pair
+  double2 dz;        // pen(u_z) - u_z
+  double2 pz, pr;    // penalised components
+  double2 dr;        // pen(u_r) - u_r
+  double2 chi;
+};
+__device__ __forceinline__ double pen_val(double u, double lamdt_chi, double U, double inv_den) {
+  return (u + lamdt_chi * U) * inv_den;
+}
+__device__ __forceinline__ PenRow pen_row(const double* __restrict__ uzu, const double* __restrict__ uru,
+                                         const double* __restrict__ chi, long long ld, int j, int k, int nz, bool vec,
+                                         double lamdt, double U_z, double U_r) {
+  PenRow r;
+  const double2 c = ld_pair(rowp(chi, ld, j), k, nz, vec);
+  const double2 z = ld_pair(rowp(uzu, ld, j), k, nz, vec);
+  const double2 q = ld_pair(rowp(uru, ld, j), k, nz, vec);
+  const double lx = lamdt * c.x, ly = lamdt * c.y;
+  const double ix = 1.0 / (1 + lx), iy = 1.0 / (1 + ly);
+  r.pz = make_double2(pen_val(z.x, lx, U_z, ix), pen_val(z.y, ly, U_z, iy));
+  r.pr = make_double2(pen_val(q.x, lx, U_r, ix), pen_val(q.y, ly, U_r, iy));
+  r.dz = make_double2(r.pz.x - z.x, r.pz.y - z.y);
+  r.dr = make_double2(r.pr.x - q.x, r.pr.y - q.y);
+  r.chi = c;
+  return r;
+}
+
+template <bool REDUCE>
+__global__ void __launch_bounds__(MT)
+    km_penalise(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, double* __restrict__ w,
+                const double* __restrict__ uzu, const double* __restrict__ uru, const double* __restrict__ chi,
+                double lam, double dt, const double* __restrict__ dt_dev, double U_z, double U_r,
+                const double* __restrict__ U_dev, const double* __restrict__ r1d, double* sum_out, bool vec) {
+  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  const Cols c = make_cols(g);
+  const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
+  double local = 0.0;
+  {
+    if (dt_dev) dt = *dt_dev;
+    if (U_dev) { U_z = U_dev[0]; U_r = U_dev[1]; }
+    const double lamdt = lam * dt;
+    const double inv_h = 1.0 / (2 * g.dx);
+    PenRow cur = pen_row(uzu, uru, chi, g.ld, j0, k, nz, vec, lamdt, U_z, U_r), nxt = cur;
+    double2 dz_m = make_double2(0, 0);
+    if (j0 > 0) dz_m = pen_row(uzu, uru, chi, g.ld, j0 - 1, k, nz, vec, lamdt, U_z, U_r).dz;
+    for (int j = j0; j < j1; ++j) {
+      if (j + 1 < g.nr) nxt = pen_row(uzu, uru, chi, g.ld, j + 1, k, nz, vec, lamdt, U_z, U_r);
+      st_pair(rowp(u_z, g.ld, j), c.ks, g.ku0, g.ku1, vec, cur.pz);
+      st_pair(rowp(u_r, g.ld, j), c.ks, g.ku0, g.ku1, vec, cur.pr);
+      if (REDUCE) {
+        const double r = r1d[j];
+        if (c.own0) local += r * cur.chi.x * (cur.pz.x - U_z);
+        if (c.own1) local += r * cur.chi.y * (cur.pz.y - U_z);
+      }
+      // z neighbours of the u_r defect: lanes +-1, warp-edge lanes recompute from memory
+      double dl = shfl_up_d(cur.dr.y), dr = shfl_dn_d(cur.dr.x);
+      if (j >= 1 && j < g.nr - 1) {
+        if (lane == 0 && c.int0) {
+          const double cc = rowp(chi, g.ld, j)[k - 1], uu = rowp(uru, g.ld, j)[k - 1];
+          const double l = lamdt * cc;
+          dl = pen_val(uu, l, U_r, 1.0 / (1 + l)) - uu;
+        }
+        if ((lane == 31 || k + 2 >= nz) && c.int1) {
+          const double cc = rowp(chi, g.ld, j)[k + 2], uu = rowp(uru, g.ld, j)[k + 2];
+          const double l = lamdt * cc;
+          dr = pen_val(uu, l, U_r, 1.0 / (1 + l)) - uu;
+        }
+        if (c.int0 || c.int1) {
+          double* wr = rowp(w, g.ld, j);
+          double2 wv = ld_pair(wr, k, nz, vec);
+          const double dzx = nxt.dz.x - dz_m.x, dzy = nxt.dz.y - dz_m.y;
+          if (c.int0) wv.x = wv.x + ((cur.dr.y - dl) * inv_h - dzx * inv_h);
+          if (c.int1) wv.y = wv.y + ((dr - cur.dr.x) * inv_h - dzy * inv_h);
+          st_pair(wr, k, c.int0 ? k : k + 1, c.int1 ? k + 2 : k + 1, vec, wv);
+        }
+      }
+      dz_m = cur.dz;
+      cur = nxt;
+    }
+  }
+  if (REDUCE) {
+    const double s = block_sum(local);
+    if (threadIdx.x == 0 && s != 0.0) atomicAdd(sum_out, s);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// G-DIF
+// -------------------------------------------------------------------------------------
+template <int STAGE>
+__global__ void __launch_bounds__(MT)
+    km_diffusion(GridD g, int RB, double* out, const double* __restrict__ in, const double* src2,
+                 const double* __restrict__ r1d, double nu, double dt, const double* __restrict__ dt_dev, bool vec) {
+  extern __shared__ double s_inv[];
+  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
+  __syncthreads();
+  const Cols c = make_cols(g);
+  const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
+  if (dt_dev) dt = *dt_dev;
+  const double coef = (STAGE == 1) ? (0.5 * nu * dt) : (nu * dt);
+  const double inv_dx2 = 1.0 / (g.dx * g.dx), inv_h = 1.0 / (2 * g.dx);
+  double2 pm = make_double2(0, 0), pc = ld_pair(rowp(in, g.ld, j0), k, nz, vec), pp = pc;
+  if (j0 > 0) pm = ld_pair(rowp(in, g.ld, j0 - 1), k, nz, vec);
+  for (int j = j0; j < j1; ++j) {
+    const double* irow = rowp(in, g.ld, j);
+    if (j + 1 < g.nr) pp = ld_pair(rowp(in, g.ld, j + 1), k, nz, vec);
+    double2 res;
+    if (STAGE == 1) res = pc;
+    else res = ld_pair(rowp(src2, g.ld, j), k, nz, vec);
+    double left, right;
+    z_neighbours(pc, irow, k, nz, lane, left, right);
+    if (j >= 1 && j < g.nr - 1) {
+      const double ir = s_inv[j - j0];
+      const double ir2 = ir * ir;
+      if (c.int0)
+        res.x += coef * ((pp.x + pm.x + pc.y + left - 4 * pc.x) * inv_dx2 + (pp.x - pm.x) * inv_h * ir - pc.x * ir2);
+      if (c.int1)
+        res.y += coef * ((pp.y + pm.y + right + pc.x - 4 * pc.y) * inv_dx2 + (pp.y - pm.y) * inv_h * ir - pc.y * ir2);
+    }
+    st_pair(rowp(out, g.ld, j), c.ks, g.ku0, g.ku1, vec, res);
+    pm = pc; pc = pp;
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// G-ADV / G-REF (and the plain-array pystencils forms)
+// -------------------------------------------------------------------------------------
+#define C13 (1.0 / 3.0)
+#define C56 (5.0 / 6.0)
+#define C16 (1.0 / 6.0)
+__device__ __forceinline__ double eno_face(double qm1, double q0, double qp1, double qp2, double v0, double vp1) {
+  const bool up = v0 > -vp1;
+  const double a = up ? qp1 : q0, b = up ? q0 : qp1, cc = up ? qm1 : qp2;
+  return C13 * a + C56 * b - C16 * cc;
+}
+template <bool MIRROR>
+__device__ __forceinline__ double2 ld_row_m(const double* f, long long ld, int jj, int k, int nz, bool vec, double sign) {
+  if (MIRROR && jj < 0) {
+    const double2 v = ld_pair(rowp(f, ld, -jj - 1), k, nz, vec);
+    return make_double2(sign * v.x, sign * v.y);
+  }
+  return ld_pair(rowp(f, ld, jj), k, nz, vec);
+}
+
+// NF fields share the velocity.  Row window per field: samples q[0..3] = rows j-1 .. j+2 (products
+// with u_r when CONS), centre values w0 = f[j], w1 = f[j+1], w2 = f[j+2]; per-thread rolling back face.
+template <int NF, bool CONS, bool MIRROR, bool FLUXONLY>
+__global__ void __launch_bounds__(MT)
+    km_eno3(GridD g, int RB, double* __restrict__ out0, double* __restrict__ out1, const double* __restrict__ in0,
+            const double* __restrict__ in1, const double* __restrict__ u_z, const double* __restrict__ u_r,
+            double inv_dx, double dt, const double* __restrict__ dt_dev, double sign0, double sign1, bool vec) {
+  const int j_lo = MIRROR ? 0 : 2, j_hi = g.nr - 3;   // rows that are advected
+  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  const Cols c = make_cols(g);
+  const int nz = g.nz, k = c.k;
+  if (!c.own0 && !c.own1) return;   // no shuffles in this kernel: idle threads may leave
+  if (dt_dev) dt = *dt_dev;
+  if (!FLUXONLY) inv_dx = -(dt / g.dx);
+  const bool ok0c = c.own0 && (c.kg >= 2) && (c.kg <= g.nzg - 3);
+  const bool ok1c = c.own1 && (c.kg + 1 >= 2) && (c.kg + 1 <= g.nzg - 3);
+  double* outs[2] = {out0, out1};
+  const double* ins[2] = {in0, in1};
+  const double signs[2] = {sign0, sign1};
+  const int jmin = MIRROR ? -2 : 0;
+
+  // rolling state: velocity rows j-1..j+2 (u_r), per field q rows j-1..j+2 and the centres
+  double2 vr[4];
+  double2 q[2][4], wc[2][3], Fb[2];
+  auto load_row = [&](int jj, double2& vrow, double2 qrow[2], double2 wrow[2]) {
+    const int jc = clampi(jj, jmin, g.nr - 1);
+    vrow = ld_row_m<MIRROR>(u_r, g.ld, jc, k, nz, vec, -1.0);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const double2 v = ld_row_m<MIRROR>(ins[f], g.ld, jc, k, nz, vec, signs[f]);
+      wrow[f] = v;
+      qrow[f] = CONS ? make_double2(v.x * vrow.x, v.y * vrow.y) : v;
+    }
+  };
+  // prime the window for row j0: rows j0-2 (only for the first back face), j0-1, j0, j0+1
+  double2 vm2, qm2[2], wtmp[2];
+  load_row(j0 - 2, vm2, qm2, wtmp);
+  {
+    double2 qq[2], ww[2];
+    load_row(j0 - 1, vr[0], qq, ww);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) q[f][0] = qq[f];
+    load_row(j0, vr[1], qq, ww);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { q[f][1] = qq[f]; wc[f][0] = ww[f]; }
+    load_row(j0 + 1, vr[2], qq, ww);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) { q[f][2] = qq[f]; wc[f][1] = ww[f]; }
+  }
+  // first back face (j0-1 | j0)
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    Fb[f].x = eno_face(qm2[f].x, q[f][0].x, q[f][1].x, q[f][2].x, vr[0].x, vr[1].x);
+    Fb[f].y = eno_face(qm2[f].y, q[f][0].y, q[f][1].y, q[f][2].y, vr[0].y, vr[1].y);
+  }
+
+  for (int j = j0; j < j1; ++j) {
+    {
+      double2 qq[2], ww[2];
+      load_row(j + 2, vr[3], qq, ww);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) { q[f][3] = qq[f]; wc[f][2] = ww[f]; }
+    }
+    const bool row_ok = (j >= j_lo) && (j <= j_hi);
+    const bool ok0 = row_ok && ok0c, ok1 = row_ok && ok1c;
+    // z direction: u_z at columns k-2 .. k+3 of row j
+    double vz[6];
+    if (ok0 || ok1) {
+      const double* uzr = rowp(u_z, g.ld, j);
+      const double2 cz = ld_pair(uzr, k, nz, vec);
+      const double2 lz = ld_pair(uzr, (k >= 2) ? k - 2 : k, nz, vec), rz = ld_pair(uzr, (k + 2 < nz) ? k + 2 : k, nz, vec);
+      vz[0] = lz.x; vz[1] = lz.y; vz[2] = cz.x; vz[3] = cz.y; vz[4] = rz.x; vz[5] = rz.y;
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      // front face (j | j+1) from rows j-1 .. j+2
+      double2 Ff;
+      Ff.x = eno_face(q[f][0].x, q[f][1].x, q[f][2].x, q[f][3].x, vr[1].x, vr[2].x);
+      Ff.y = eno_face(q[f][0].y, q[f][1].y, q[f][2].y, q[f][3].y, vr[1].y, vr[2].y);
+      const double2 cen = wc[f][0];
+      double2 o;
+      if (FLUXONLY) o = ld_pair(rowp(outs[f], g.ld, j), k, nz, vec);
+      else o = cen;
+      if (ok0 || ok1) {
+        const double* fr = rowp(ins[f], g.ld, j);
+        double qz[6];
+        {
+          const double2 l = ld_pair(fr, (k >= 2) ? k - 2 : k, nz, vec), r = ld_pair(fr, (k + 2 < nz) ? k + 2 : k, nz, vec);
+          qz[0] = l.x; qz[1] = l.y; qz[2] = cen.x; qz[3] = cen.y; qz[4] = r.x; qz[5] = r.y;
+        }
+        if (CONS) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) qz[i] *= vz[i];
+        }
+        const double Fz0 = eno_face(qz[0], qz[1], qz[2], qz[3], vz[1], vz[2]);
+        const double Fz1 = eno_face(qz[1], qz[2], qz[3], qz[4], vz[2], vz[3]);
+        const double Fz2 = eno_face(qz[2], qz[3], qz[4], qz[5], vz[3], vz[4]);
+        double a0 = FLUXONLY ? o.x : 0.0, a1 = FLUXONLY ? o.y : 0.0;
+        if (CONS) {
+          a0 = a0 + inv_dx * Fz1; a0 = a0 - inv_dx * Fz0; a0 = a0 + inv_dx * Ff.x; a0 = a0 - inv_dx * Fb[f].x;
+          a1 = a1 + inv_dx * Fz2; a1 = a1 - inv_dx * Fz1; a1 = a1 + inv_dx * Ff.y; a1 = a1 - inv_dx * Fb[f].y;
+        } else {
+          const double z0 = vz[2], z1 = vz[3], r0 = vr[1].x, r1 = vr[1].y;
+          a0 = a0 + inv_dx * Fz1 * z0; a0 = a0 - inv_dx * Fz0 * z0; a0 = a0 + inv_dx * Ff.x * r0; a0 = a0 - inv_dx * Fb[f].x * r0;
+          a1 = a1 + inv_dx * Fz2 * z1; a1 = a1 - inv_dx * Fz1 * z1; a1 = a1 + inv_dx * Ff.y * r1; a1 = a1 - inv_dx * Fb[f].y * r1;
+        }
+        if (FLUXONLY) { if (ok0) o.x = a0; if (ok1) o.y = a1; }
+        else { if (ok0) o.x = cen.x + a0; if (ok1) o.y = cen.y + a1; }
+      }
+      if (!FLUXONLY || ok0 || ok1) st_pair(rowp(outs[f], g.ld, j), k, g.ku0, g.ku1, vec, o);
+      Fb[f] = Ff;
+      q[f][0] = q[f][1]; q[f][1] = q[f][2]; q[f][2] = q[f][3];
+      wc[f][0] = wc[f][1]; wc[f][1] = wc[f][2];
+    }
+    vr[0] = vr[1]; vr[1] = vr[2]; vr[2] = vr[3];
+  }
+}
+
+inline int pick_rb(const GridD& d) {
+  // rows per block: as long as the grid still has >= ~16 blocks per SM keep the window start-up
+  // (1-4 extra row loads) amortised over 32 rows
+  const long long colb = ((d.nz + 1) / 2 + MT - 1) / MT;
+  for (int rb = 32; rb >= 8; rb >>= 1)
+    if (colb * ((d.nr + rb - 1) / rb) >= 148LL * 12) return rb;
+  return 8;
+}
+inline dim3 march_grid(const GridD& d, int rb) {
+  return dim3(((d.nz + 1) / 2 + MT - 1) / MT, (d.nr + rb - 1) / rb, 1);
+}
+
+}  // namespace
+
+int march_velocity(const GridD& d, double* u_z, double* u_r, const double* psi, const double* r1d, double uz_add,
+                   double ur_add, const double* add_dev, double* umax_out, bool vec, cudaStream_t s) {
+  const int rb = pick_rb(d);
+  if (umax_out)
+    km_velocity<true><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, u_z, u_r, psi, r1d, uz_add, ur_add,
+                                                                         add_dev, umax_out, vec);
+  else
+    km_velocity<false><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, u_z, u_r, psi, r1d, uz_add, ur_add,
+                                                                          add_dev, nullptr, vec);
+  return (int)cudaGetLastError();
+}
+
+int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const double* uzu, const double* uru,
+                   const double* chi, double lam, double dt, const double* dt_dev, double U_z, double U_r,
+                   const double* U_dev, const double* r1d, double* sum_out, bool vec, cudaStream_t s) {
+  const int rb = pick_rb(d);
+  if (sum_out)
+    km_penalise<true><<<march_grid(d, rb), MT, 0, s>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, U_r,
+                                                       U_dev, r1d, sum_out, vec);
+  else
+    km_penalise<false><<<march_grid(d, rb), MT, 0, s>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, U_r,
+                                                        U_dev, r1d, nullptr, vec);
+  return (int)cudaGetLastError();
+}
+
+int march_diffusion(int stage, const GridD& d, double* out, const double* in, const double* src2, const double* r1d,
+                    double nu, double dt, const double* dt_dev, bool vec, cudaStream_t s) {
+  const int rb = pick_rb(d);
+  if (stage == 1)
+    km_diffusion<1><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, out, in, src2, r1d, nu, dt, dt_dev, vec);
+  else
+    km_diffusion<2><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, out, in, src2, r1d, nu, dt, dt_dev, vec);
+  return (int)cudaGetLastError();
+}
+
+int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, double* out0, double* out1,
+               const double* in0, const double* in1, const double* u_z, const double* u_r, double inv_dx, double dt,
+               const double* dt_dev, double sign0, double sign1, bool vec, cudaStream_t s) {
+  const int rb = pick_rb(d);
+  const dim3 grd = march_grid(d, rb);
+#define LAUNCH(NF, C, M, F) \
+  km_eno3<NF, C, M, F><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, vec)
+  if (nf == 1 && cons && mirror && !fluxonly) LAUNCH(1, true, true, false);
+  else if (nf == 2 && !cons && mirror && !fluxonly) LAUNCH(2, false, true, false);
+  else if (nf == 1 && cons && !mirror && fluxonly) LAUNCH(1, true, false, true);
+  else if (nf == 1 && !cons && !mirror && fluxonly) LAUNCH(1, false, false, true);
+  else if (nf == 1 && cons && !mirror && !fluxonly) LAUNCH(1, true, false, false);
+  else if (nf == 1 && !cons && !mirror && !fluxonly) LAUNCH(1, false, false, false);
+  else return AXB_ENOSUP;
+#undef LAUNCH
+  return (int)cudaGetLastError();
+}
