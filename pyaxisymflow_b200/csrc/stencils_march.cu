@@ -64,6 +64,19 @@ __device__ __forceinline__ Cols make_cols(const GridD& g) {
   return c;
 }
 
+// Block-uniform test for the branch-free fast paths: all 256 columns of the block are owned and at
+// least `hz` columns away from the global z ends, rows [j0, j1) are a full chunk at least `hr` rows
+// away from both r ends, and 128-bit accesses are legal.  The fast and the general code evaluate the
+// same floating-point expressions, so a cell gets the same bits whichever path computes it.
+__device__ __forceinline__ bool block_interior(const GridD& g, int j0, int j1, int RB, int hr, int hz, bool vec) {
+  const int kb0 = 2 * blockIdx.x * MT, kb1 = kb0 + 2 * MT;
+  return vec && (j1 - j0 == RB) && (j0 >= hr) && (j1 + hr <= g.nr) && (kb0 >= g.ku0) && (kb1 <= g.ku1) &&
+         (kb0 + g.kz0 >= hz) && (kb1 - 1 + g.kz0 <= g.nzg - 1 - hz) && (kb0 - hz >= 0) && (kb1 - 1 + hz < g.nz);
+}
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+constexpr int UR = 4;   // rows per unrolled step of the fast paths (RB is a multiple of it)
+
 // -------------------------------------------------------------------------------------
 // G-VEL
 // -------------------------------------------------------------------------------------
@@ -79,8 +92,47 @@ __global__ void __launch_bounds__(MT)
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local_max = 0.0;
-  {
-    if (add_dev) { uz_add = add_dev[0]; ur_add = add_dev[1]; }
+  if (add_dev) { uz_add = add_dev[0]; ur_add = add_dev[1]; }
+  if (block_interior(g, j0, j1, RB, 1, 1, vec)) {
+    const double inv_h = 1.0 / (2 * g.dx);
+    const long long ld = g.ld;
+    const double* p = psi + (long long)(j0 - 1) * ld + k;
+    double2 pm = ld2(p), pc = ld2(p + ld);
+    p += 2 * ld;                                   // row j + 1
+    double* oz = u_z + (long long)j0 * ld + k;
+    double* orr = u_r + (long long)j0 * ld + k;
+    for (int jb = 0; jb < RB; jb += UR) {
+      double2 pn[UR];
+      double le[UR], re[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) pn[u] = ld2(p + u * ld);
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {                 // warp-edge z neighbours of rows j .. j+3
+        const double* rr = p + (u - 1) * ld;
+        le[u] = (lane == 0) ? rr[-1] : 0.0;
+        re[u] = (lane == 31) ? rr[2] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const double ir = s_inv[jb + u];
+        double left = shfl_up_d(pc.y), right = shfl_dn_d(pc.x);
+        if (lane == 0) left = le[u];
+        if (lane == 31) right = re[u];
+        double2 uz, ur;
+        uz.x = (pn[u].x - pm.x) * inv_h * ir;
+        uz.y = (pn[u].y - pm.y) * inv_h * ir;
+        ur.x = -(pc.y - left) * inv_h * ir;
+        ur.y = -(right - pc.x) * inv_h * ir;
+        uz.x += uz_add; uz.y += uz_add;
+        ur.x += ur_add; ur.y += ur_add;
+        st2(oz + u * ld, uz);
+        st2(orr + u * ld, ur);
+        if (REDUCE) local_max = fmax(local_max, fmax(fabs(uz.x) + fabs(ur.x), fabs(uz.y) + fabs(ur.y)));
+        pm = pc; pc = pn[u];
+      }
+      p += UR * ld; oz += UR * ld; orr += UR * ld;
+    }
+  } else {
     const double inv_h = 1.0 / (2 * g.dx);
     double2 pm = make_double2(0, 0), pc = ld_pair(rowp(psi, g.ld, j0), k, nz, vec), pp = pc;
     if (j0 > 0) pm = ld_pair(rowp(psi, g.ld, j0 - 1), k, nz, vec);
@@ -156,6 +208,22 @@ __device__ __forceinline__ PenRow pen_row(const double* __restrict__ uzu, const 
   return r;
 }
 
+__device__ __forceinline__ PenRow pen_from(double2 c, double2 z, double2 q, double lamdt, double U_z, double U_r) {
+  PenRow r;
+  const double lx = lamdt * c.x, ly = lamdt * c.y;
+  const double ix = 1.0 / (1 + lx), iy = 1.0 / (1 + ly);
+  r.pz = make_double2(pen_val(z.x, lx, U_z, ix), pen_val(z.y, ly, U_z, iy));
+  r.pr = make_double2(pen_val(q.x, lx, U_r, ix), pen_val(q.y, ly, U_r, iy));
+  r.dz = make_double2(r.pz.x - z.x, r.pz.y - z.y);
+  r.dr = make_double2(r.pr.x - q.x, r.pr.y - q.y);
+  r.chi = c;
+  return r;
+}
+__device__ __forceinline__ double pen_defect(double cc, double uu, double lamdt, double U) {
+  const double l = lamdt * cc;
+  return pen_val(uu, l, U, 1.0 / (1 + l)) - uu;
+}
+
 template <bool REDUCE>
 __global__ void __launch_bounds__(MT)
     km_penalise(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, double* __restrict__ w,
@@ -166,9 +234,56 @@ __global__ void __launch_bounds__(MT)
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local = 0.0;
-  {
-    if (dt_dev) dt = *dt_dev;
-    if (U_dev) { U_z = U_dev[0]; U_r = U_dev[1]; }
+  if (dt_dev) dt = *dt_dev;
+  if (U_dev) { U_z = U_dev[0]; U_r = U_dev[1]; }
+  if (block_interior(g, j0, j1, RB, 1, 1, vec)) {
+    const double lamdt = lam * dt;
+    const double inv_h = 1.0 / (2 * g.dx);
+    const long long ld = g.ld;
+    const long long off = (long long)(j0 - 1) * ld + k;
+    const double *pc_ = chi + off, *pz_ = uzu + off, *pr_ = uru + off;
+    double2 dz_m = pen_from(ld2(pc_), ld2(pz_), ld2(pr_), lamdt, U_z, U_r).dz;
+    PenRow cur = pen_from(ld2(pc_ + ld), ld2(pz_ + ld), ld2(pr_ + ld), lamdt, U_z, U_r);
+    pc_ += 2 * ld; pz_ += 2 * ld; pr_ += 2 * ld;           // row j + 1
+    double* oz = u_z + off + ld;
+    double* orr = u_r + off + ld;
+    double* wr = w + off + ld;
+    for (int jb = 0; jb < RB; jb += 2) {
+      // all loads of two rows first: rows j+1, j+2 of (chi, u_z, u_r), rows j, j+1 of w, warp-edge columns
+      const double2 c1 = ld2(pc_), z1 = ld2(pz_), q1 = ld2(pr_);
+      const double2 c2 = ld2(pc_ + ld), z2 = ld2(pz_ + ld), q2 = ld2(pr_ + ld);
+      double2 w0 = ld2(wr), w1 = ld2(wr + ld);
+      double ec[2] = {0, 0}, eu[2] = {0, 0};
+      if (lane == 0) {
+        ec[0] = pc_[-ld - 1]; eu[0] = pr_[-ld - 1]; ec[1] = pc_[-1]; eu[1] = pr_[-1];
+      } else if (lane == 31) {
+        ec[0] = pc_[-ld + 2]; eu[0] = pr_[-ld + 2]; ec[1] = pc_[2]; eu[1] = pr_[2];
+      }
+      const PenRow n1 = pen_from(c1, z1, q1, lamdt, U_z, U_r), n2 = pen_from(c2, z2, q2, lamdt, U_z, U_r);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const PenRow& nx = u ? n2 : n1;
+        st2(oz + u * ld, cur.pz);
+        st2(orr + u * ld, cur.pr);
+        if (REDUCE) {
+          const double r = r1d[j0 + jb + u];
+          local += r * cur.chi.x * (cur.pz.x - U_z);
+          local += r * cur.chi.y * (cur.pz.y - U_z);
+        }
+        double dl = shfl_up_d(cur.dr.y), dr = shfl_dn_d(cur.dr.x);
+        if (lane == 0) dl = pen_defect(ec[u], eu[u], lamdt, U_r);
+        if (lane == 31) dr = pen_defect(ec[u], eu[u], lamdt, U_r);
+        double2 wv = u ? w1 : w0;
+        const double dzx = nx.dz.x - dz_m.x, dzy = nx.dz.y - dz_m.y;
+        wv.x = wv.x + ((cur.dr.y - dl) * inv_h - dzx * inv_h);
+        wv.y = wv.y + ((dr - cur.dr.x) * inv_h - dzy * inv_h);
+        st2(wr + u * ld, wv);
+        dz_m = cur.dz;
+        cur = nx;
+      }
+      pc_ += 2 * ld; pz_ += 2 * ld; pr_ += 2 * ld; oz += 2 * ld; orr += 2 * ld; wr += 2 * ld;
+    }
+  } else {
     const double lamdt = lam * dt;
     const double inv_h = 1.0 / (2 * g.dx);
     PenRow cur = pen_row(uzu, uru, chi, g.ld, j0, k, nz, vec, lamdt, U_z, U_r), nxt = cur;
@@ -231,6 +346,47 @@ __global__ void __launch_bounds__(MT)
   if (dt_dev) dt = *dt_dev;
   const double coef = (STAGE == 1) ? (0.5 * nu * dt) : (nu * dt);
   const double inv_dx2 = 1.0 / (g.dx * g.dx), inv_h = 1.0 / (2 * g.dx);
+  if (block_interior(g, j0, j1, RB, 1, 1, vec)) {
+    const long long ld = g.ld;
+    const double* p = in + (long long)(j0 - 1) * ld + k;
+    double2 pm = ld2(p), pc = ld2(p + ld);
+    p += 2 * ld;
+    double* o = out + (long long)j0 * ld + k;
+    const double* s2 = (STAGE == 1) ? nullptr : src2 + (long long)j0 * ld + k;
+    for (int jb = 0; jb < RB; jb += UR) {
+      double2 pn[UR], sv[UR];
+      double le[UR], re[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) pn[u] = ld2(p + u * ld);
+      if (STAGE == 2) {
+#pragma unroll
+        for (int u = 0; u < UR; ++u) sv[u] = ld2(s2 + u * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const double* rr = p + (u - 1) * ld;
+        le[u] = (lane == 0) ? rr[-1] : 0.0;
+        re[u] = (lane == 31) ? rr[2] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const double ir = s_inv[jb + u];
+        const double ir2 = ir * ir;
+        double left = shfl_up_d(pc.y), right = shfl_dn_d(pc.x);
+        if (lane == 0) left = le[u];
+        if (lane == 31) right = re[u];
+        double2 res = (STAGE == 1) ? pc : sv[u];
+        const double2 pp = pn[u];
+        res.x += coef * ((pp.x + pm.x + pc.y + left - 4 * pc.x) * inv_dx2 + (pp.x - pm.x) * inv_h * ir - pc.x * ir2);
+        res.y += coef * ((pp.y + pm.y + right + pc.x - 4 * pc.y) * inv_dx2 + (pp.y - pm.y) * inv_h * ir - pc.y * ir2);
+        st2(o + u * ld, res);
+        pm = pc; pc = pp;
+      }
+      p += UR * ld; o += UR * ld;
+      if (STAGE == 2) s2 += UR * ld;
+    }
+    return;
+  }
   double2 pm = make_double2(0, 0), pc = ld_pair(rowp(in, g.ld, j0), k, nz, vec), pp = pc;
   if (j0 > 0) pm = ld_pair(rowp(in, g.ld, j0 - 1), k, nz, vec);
   for (int j = j0; j < j1; ++j) {
@@ -295,6 +451,81 @@ __global__ void __launch_bounds__(MT)
   const double signs[2] = {sign0, sign1};
   const int jmin = MIRROR ? -2 : 0;
 
+  if (!MIRROR ? block_interior(g, j0, j1, RB, 2, 2, vec) : block_interior(g, j0, j1, RB, 2, 2, vec)) {
+    // branch-free interior path: every load of a row is issued before any of it is consumed
+    const long long ld = g.ld;
+    const long long off = (long long)j0 * ld + k;
+    const double* pv = u_r + off - 2 * ld;              // row j - 2, advanced to j + 2 below
+    const double* pu = u_z + off;                       // row j
+    const double* pw[2] = {in0 + off - 2 * ld, (NF > 1 ? in1 : in0) + off - 2 * ld};
+    double* po[2] = {out0 + off, (NF > 1 ? out1 : out0) + off};
+    double2 v[4], qq[2][4], wcen[2][3], fb[2];
+    {
+      const double2 vm2 = ld2(pv);
+      v[0] = ld2(pv + ld); v[1] = ld2(pv + 2 * ld); v[2] = ld2(pv + 3 * ld);
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const double2 a = ld2(pw[f]), b = ld2(pw[f] + ld), c2 = ld2(pw[f] + 2 * ld), d2 = ld2(pw[f] + 3 * ld);
+        const double2 qm2 = CONS ? make_double2(a.x * vm2.x, a.y * vm2.y) : a;
+        qq[f][0] = CONS ? make_double2(b.x * v[0].x, b.y * v[0].y) : b;
+        qq[f][1] = CONS ? make_double2(c2.x * v[1].x, c2.y * v[1].y) : c2;
+        qq[f][2] = CONS ? make_double2(d2.x * v[2].x, d2.y * v[2].y) : d2;
+        wcen[f][0] = c2; wcen[f][1] = d2;
+        fb[f].x = eno_face(qm2.x, qq[f][0].x, qq[f][1].x, qq[f][2].x, v[0].x, v[1].x);
+        fb[f].y = eno_face(qm2.y, qq[f][0].y, qq[f][1].y, qq[f][2].y, v[0].y, v[1].y);
+      }
+    }
+    pv += 4 * ld;                                        // row j + 2
+    pw[0] += 4 * ld; pw[1] += 4 * ld;
+    for (int jb = 0; jb < RB; ++jb) {
+      // ---- loads
+      v[3] = ld2(pv);
+      const double2 uzc = ld2(pu), uzl = ld2(pu - 2), uzr = ld2(pu + 2);
+      double2 w3[2], wl[2], wrr[2], oo[2];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        w3[f] = ld2(pw[f]);
+        wl[f] = ld2(pw[f] - 2 * ld - 2);
+        wrr[f] = ld2(pw[f] - 2 * ld + 2);
+        if (FLUXONLY) oo[f] = ld2(po[f]);
+      }
+      const double vz[6] = {uzl.x, uzl.y, uzc.x, uzc.y, uzr.x, uzr.y};
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        qq[f][3] = CONS ? make_double2(w3[f].x * v[3].x, w3[f].y * v[3].y) : w3[f];
+        wcen[f][2] = w3[f];
+        double2 Ff;
+        Ff.x = eno_face(qq[f][0].x, qq[f][1].x, qq[f][2].x, qq[f][3].x, v[1].x, v[2].x);
+        Ff.y = eno_face(qq[f][0].y, qq[f][1].y, qq[f][2].y, qq[f][3].y, v[1].y, v[2].y);
+        const double2 cen = wcen[f][0];
+        double qz[6] = {wl[f].x, wl[f].y, cen.x, cen.y, wrr[f].x, wrr[f].y};
+        if (CONS) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) qz[i] *= vz[i];
+        }
+        const double Fz0 = eno_face(qz[0], qz[1], qz[2], qz[3], vz[1], vz[2]);
+        const double Fz1 = eno_face(qz[1], qz[2], qz[3], qz[4], vz[2], vz[3]);
+        const double Fz2 = eno_face(qz[2], qz[3], qz[4], qz[5], vz[3], vz[4]);
+        double a0 = FLUXONLY ? oo[f].x : 0.0, a1 = FLUXONLY ? oo[f].y : 0.0;
+        if (CONS) {
+          a0 = a0 + inv_dx * Fz1; a0 = a0 - inv_dx * Fz0; a0 = a0 + inv_dx * Ff.x; a0 = a0 - inv_dx * fb[f].x;
+          a1 = a1 + inv_dx * Fz2; a1 = a1 - inv_dx * Fz1; a1 = a1 + inv_dx * Ff.y; a1 = a1 - inv_dx * fb[f].y;
+        } else {
+          const double z0 = vz[2], z1 = vz[3], r0 = v[1].x, r1 = v[1].y;
+          a0 = a0 + inv_dx * Fz1 * z0; a0 = a0 - inv_dx * Fz0 * z0; a0 = a0 + inv_dx * Ff.x * r0; a0 = a0 - inv_dx * fb[f].x * r0;
+          a1 = a1 + inv_dx * Fz2 * z1; a1 = a1 - inv_dx * Fz1 * z1; a1 = a1 + inv_dx * Ff.y * r1; a1 = a1 - inv_dx * fb[f].y * r1;
+        }
+        st2(po[f], FLUXONLY ? make_double2(a0, a1) : make_double2(cen.x + a0, cen.y + a1));
+        fb[f] = Ff;
+        qq[f][0] = qq[f][1]; qq[f][1] = qq[f][2]; qq[f][2] = qq[f][3];
+        wcen[f][0] = wcen[f][1]; wcen[f][1] = wcen[f][2];
+        pw[f] += ld; po[f] += ld;
+      }
+      v[0] = v[1]; v[1] = v[2]; v[2] = v[3];
+      pv += ld; pu += ld;
+    }
+    return;
+  }
   // rolling state: velocity rows j-1..j+2 (u_r), per field q rows j-1..j+2 and the centres
   double2 vr[4];
   double2 q[2][4], wc[2][3], Fb[2];
