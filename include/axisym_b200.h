@@ -171,6 +171,24 @@ int axb_fill_scalars(double* dst, int n, double val, axb_stream_t s);
 int axb_rigid_flow_scalars(int phase, double* state, double U0, double T_ramp, double ur_ramp,
                            double dt_diff_limit, double cfl_dx, axb_stream_t s);
 
+/* ---- driver glue of the soft-sphere and particle loops ---------------
+ *      axb_axpy                  : y += a*x  (running averages, soft_sphere_streaming.py:179-180,
+ *                                  particle_in_bubble_oscillatory_flow.py:297-299)
+ *      axb_pin_level_set         : phi_orig = r_ball - sqrt((eta1-z_cm)^2 + (eta2-r_cm)^2);
+ *                                  phi[phi > thresh] = phi_orig      (soft_sphere_streaming.py:191-193)
+ *      axb_smooth_heaviside_mask : H = smooth_Heaviside(phi), mask = H > thresh (or >=) as a dense
+ *                                  (nr, nz) uint8                   (soft_sphere_streaming.py:205-206)
+ *      axb_add_bubble_flow       : breathing mode inside the bubble + exterior potential flow added
+ *                                  to (u_z, u_r)         (particle_in_bubble_oscillatory_flow.py:273-294) */
+int axb_axpy(const axb_grid_t* g, double* y, const double* x, double a, const double* a_dev, axb_stream_t s);
+int axb_pin_level_set(const axb_grid_t* g, double* phi, double* phi_orig, const double* eta1, const double* eta2,
+                      double z_cm, double r_cm, double r_ball, double thresh, axb_stream_t s);
+int axb_smooth_heaviside_mask(const axb_grid_t* g, double* H, uint8_t* mask, const double* phi, double blend_w,
+                              double thresh, int greater_equal, axb_stream_t s);
+int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
+                        const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble,
+                        double U_0, double sin_omega_t, axb_stream_t s);
+
 /* ---- a18: elasto_kernels/solid_sigma.py:4-29 (all seven caller-visible outputs).
  *      chi != NULL additionally applies the driver's blend sigma *= chi
  *      (examples/SoftSphereStreaming/soft_sphere_streaming.py:236-238). --------------------- */

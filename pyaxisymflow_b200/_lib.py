@@ -64,6 +64,10 @@ _SIGNATURES = {
     "axb_reduce_weighted_sum": [_G, _P, _P, _P, _D, _P, _S],
     "axb_fill_scalars": [_P, _I, _D, _S],
     "axb_rigid_flow_scalars": [_I, _P, _D, _D, _D, _D, _D, _S],
+    "axb_axpy": [_G, _P, _P, _D, _P, _S],
+    "axb_pin_level_set": [_G, _P, _P, _P, _P, _D, _D, _D, _D, _S],
+    "axb_smooth_heaviside_mask": [_G, _P, _P, _P, _D, _D, _I, _S],
+    "axb_add_bubble_flow": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D, _S],
     "axb_solid_sigma": [_G, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_tau": [_G, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_vorticity_update": [_G, _P, _P, _P, _D, _P, _S],

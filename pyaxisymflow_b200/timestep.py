@@ -171,3 +171,234 @@ class RigidFlowStepper:
         st = self.state.cpu().numpy()
         cd = 2 * 2 * np.pi * self.dx * self.dx * self.brink_lam * st[S_SUMCOPY] / (np.pi * self.r_sph ** 2)
         return {"t": st[S_T], "dt": st[S_DT], "umax": st[S_UMAX], "iterations": int(st[S_IT]), "Cd": cd}
+
+
+class _FieldSet:
+    """small helper: float64 CUDA fields of one (nr, nz) grid plus the ctypes grid descriptor"""
+
+    def __init__(self, nr, nz, dx):
+        self.nr, self.nz, self.dx = nr, nz, dx
+        self.grid = make_grid(nr, nz, nz, dx)
+        self.g = ctypes.byref(self.grid)
+
+    def new(self, n=1):
+        f = [torch.zeros((self.nr, self.nz), dtype=torch.float64, device="cuda") for _ in range(n)]
+        return f[0] if n == 1 else f
+
+
+class SoftSphereStepper:
+    """Loop body of ``examples/SoftSphereStreaming/soft_sphere_streaming.py:129-274`` (config C3):
+    a tethered hyperelastic sphere (reference-map solid) driven by an oscillating rigid core.
+
+    Per step: boundary damping, streamfunction solve, velocity (+CFL max), running averages,
+    ENO3 advection of both reference maps, level-set pinning, ENO3 vorticity advection, Heaviside +
+    inside mask, least-squares extrapolation of the maps, solid stress (blend fused), div(tau) and
+    its curl, moving-tether Heaviside, Brinkman penalisation (+curl), RK2 diffusion.
+    The narrow-band re-initialisation ``skfmm.distance`` (third party, soft_sphere_streaming.py:196-199)
+    is NOT part of this path: ``ball_phi`` is only pinned from the reference map.
+    One small D2H (the CFL max) per step, like the reference's ``np.amax``; the LS sweep loop
+    synchronises anyway.
+    """
+
+    def __init__(self, grid_size_z=256, domain_AR=0.5, grid_size_r=None, r_ball=0.15, freq=16.0, nond_AC=0.125,
+                 e=0.1, Cauchy=0.1, zeta=0.25, brink_lam=1e8, CFL=0.1, rho_f=1.0, Z_cm=0.5, R_cm=0.0, basis="auto"):
+        if not torch.cuda.is_available():
+            raise _lib.AxbError("SoftSphereStepper needs a CUDA device (no CPU fallback)")
+        nz = int(grid_size_z)
+        nr = int(grid_size_r) if grid_size_r is not None else int(domain_AR * nz)
+        dx = 1.0 / nz
+        self.F = F = _FieldSet(nr, nz, dx)
+        self.nr, self.nz, self.dx = nr, nz, dx
+        self.CFL, self.brink_lam, self.rho_f = CFL, brink_lam, rho_f
+        self.moll_zone = dx * 2
+        self.extrap_zone = self.moll_zone + 4 * dx
+        self.r_ball, self.Z_cm, self.R_cm, self.e = r_ball, Z_cm, R_cm, e
+        self.freq = freq
+        self.freqTimer_limit = 1 / freq
+        self.omega = 2 * np.pi * freq
+        self.U_0 = e * r_ball * self.omega
+        Rs = (e / nond_AC) ** 2
+        self.nu = e * self.U_0 * r_ball / Rs
+        self.G = e * rho_f * (r_ball * self.omega) ** 2 / Cauchy
+        self.fixed_rad = zeta * r_ball
+        self.eps = np.finfo(float).eps
+        z = np.linspace(0 + dx / 2, 1 - dx / 2, nz)
+        r = np.linspace(0 + dx / 2, nr * dx - dx / 2, nr)
+        self.z1d, self.r1d = torch.from_numpy(z).cuda(), torch.from_numpy(r).cuda()
+        # grid axes of the doubled array handed to the LS routine: the reference passes (z, z)
+        # (extrapolate_eta_using_least_squares_unb.py:27), which is z[:2 nr] for any aspect ratio
+        self.gy = torch.from_numpy(np.linspace(dx / 2, 2 * nr * dx - dx / 2, 2 * nr)).cuda()
+        (self.vorticity, self.psi, self.u_z, self.u_r, self.u_z_upen, self.u_r_upen, self._tmp, self._w2,
+         self.eta1, self.eta2, self._e1b, self._e2b, self.ball_phi, self.ball_char_func, self.tether_char_func,
+         self.s11, self.s12, self.s22, self.e1z, self.e1r, self.e2z, self.e2r, self.tau_z, self.tau_r,
+         self.avg_psi, self.avg_phi) = F.new(26)
+        self.inside_solid = torch.zeros((nr, nz), dtype=torch.uint8, device="cuda")
+        s = stream_ptr()
+        _call("axb_smooth_heaviside_sphere", F.g, ptr(self.ball_char_func), ptr(self.ball_phi), ptr(self.z1d),
+              ptr(self.r1d), Z_cm, R_cm, r_ball, self.moll_zone, s)
+        self.eta1.copy_(self.z1d[None, :].expand(nr, nz))
+        self.eta2.copy_(self.r1d[:, None].expand(nr, nz))
+        self.solver = FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis)
+        nbytes = int(_call("axb_ls_workspace_bytes", 2 * nr, nz))
+        self._ls_work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        self._ls_bytes = nbytes
+        self._umax = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self.t, self.freqTimer, self.it, self.dt = 0.0, 0.0, 0, 0.0
+        self.tEnd = 30 / freq
+
+    def step(self, n=1):
+        for _ in range(n):
+            self._one()
+
+    def _one(self):
+        F, s, g = self.F, stream_ptr(), self.F.g
+        dx, w = self.dx, self.vorticity
+        _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
+        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
+        _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ptr(self.psi), self.nz, ptr(w), self.nz, s)
+        self._umax.zero_()
+        _call("axb_velocity_from_psi", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.psi), ptr(self.r1d), 0.0, 0.0,
+              None, ptr(self._umax), s)
+        umax = float(self._umax)                       # the reference's np.amax round trip
+        dt = min(self.CFL * dx / np.sqrt(self.G / self.rho_f), self.CFL * dx / (umax + self.eps),
+                 0.9 * dx ** 2 / 4 / self.nu)
+        if self.freqTimer + dt > self.freqTimer_limit:
+            dt = self.freqTimer_limit - self.freqTimer
+        if self.t + dt > self.tEnd:
+            dt = self.tEnd - self.t
+        self.dt = dt
+        _call("axb_axpy", g, ptr(self.avg_psi), ptr(self.psi), dt, None, s)
+        _call("axb_axpy", g, ptr(self.avg_phi), ptr(self.ball_phi), dt, None, s)
+        _call("axb_advect_refmap_eno3", g, ptr(self._e1b), ptr(self._e2b), ptr(self.eta1), ptr(self.eta2),
+              ptr(self.u_z_upen), ptr(self.u_r_upen), dt, None, s)
+        self.eta1, self._e1b = self._e1b, self.eta1
+        self.eta2, self._e2b = self._e2b, self.eta2
+        _call("axb_pin_level_set", g, ptr(self.ball_phi), None, ptr(self.eta1), ptr(self.eta2), self.Z_cm, self.R_cm,
+              self.r_ball, -3 * dx, s)
+        _call("axb_advect_vorticity_eno3", g, ptr(self._w2), ptr(w), ptr(self.u_z_upen), ptr(self.u_r_upen), dt, None, s)
+        self.vorticity, self._w2 = self._w2, self.vorticity
+        w = self.vorticity
+        _call("axb_smooth_heaviside_mask", g, ptr(self.ball_char_func), ptr(self.inside_solid), ptr(self.ball_phi),
+              self.moll_zone, 0.5, 0, s)
+        sweeps = ctypes.c_int(0)
+        _call("axb_ls_extrapolate_eta", g, ptr(self.ball_phi), ptr(self.inside_solid), ptr(self.eta1), ptr(self.eta2),
+              self.extrap_zone, ptr(self.z1d), ptr(self.gy), ptr(self._ls_work), self._ls_bytes, 0,
+              ctypes.byref(sweeps), s)
+        self.ls_sweeps = sweeps.value
+        _call("axb_solid_sigma", g, ptr(self.s11), ptr(self.s12), ptr(self.s22), self.G, ptr(self.eta1), ptr(self.eta2),
+              ptr(self.e1z), ptr(self.e1r), ptr(self.e2z), ptr(self.e2r), ptr(self.ball_char_func), s)
+        _call("axb_solid_tau", g, ptr(self.tau_z), ptr(self.tau_r), ptr(self.s11), ptr(self.s12), ptr(self.s22),
+              ptr(self.r1d), s)
+        _call("axb_solid_vorticity_update", g, ptr(w), ptr(self.tau_z), ptr(self.tau_r), dt, None, s)
+        Z_cm_t = self.Z_cm + self.e * self.r_ball * np.sin(self.omega * self.t)
+        _call("axb_smooth_heaviside_sphere", g, ptr(self.tether_char_func), None, ptr(self.z1d), ptr(self.r1d), Z_cm_t,
+              self.R_cm, self.fixed_rad, self.moll_zone, s)
+        _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
+              ptr(self.u_r_upen), ptr(self.tether_char_func), self.brink_lam, dt, None,
+              self.U_0 * np.cos(self.omega * self.t), 0.0, None, ptr(self.r1d), None, s)
+        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(w), ptr(self.r1d), self.nu, dt, None, s)
+        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(w), ptr(self._tmp), ptr(self.r1d), self.nu, dt, None, s)
+        self.t += dt
+        self.freqTimer += dt
+        if self.freqTimer >= self.freqTimer_limit:
+            self.freqTimer = 0.0
+        self.it += 1
+
+
+class ParticleFlowStepper:
+    """Loop body of ``examples/ParticleOscillatoryFlowCases/particle_in_bubble_oscillatory_flow.py:159-358``
+    (one member of the config-C5 ensemble): a free rigid particle next to an oscillating bubble,
+    remeshed-vortex (MP4 particle) advection.  ``freq`` and ``e`` are the swept parameters.
+    Members of an ensemble on one GPU share the solver factors (``solver=``)."""
+
+    def __init__(self, grid_size_z=400, domain_AR=0.5, grid_size_r=None, freq=8.0, e=0.01, lambda_part=20.0,
+                 r0_bubble=0.25, rp=2.0, brink_lam=1e12, CFL=0.1, rho_f=1.0, rho_s=1.0, solver=None, basis="auto"):
+        if not torch.cuda.is_available():
+            raise _lib.AxbError("ParticleFlowStepper needs a CUDA device (no CPU fallback)")
+        nz = int(grid_size_z)
+        nr = int(grid_size_r) if grid_size_r is not None else int(domain_AR * nz)
+        dx = 1.0 / nz
+        self.F = F = _FieldSet(nr, nz, dx)
+        self.nr, self.nz, self.dx = nr, nz, dx
+        self.CFL, self.brink_lam, self.rho_f, self.rho_s = CFL, brink_lam, rho_f, rho_s
+        self.moll_zone = np.sqrt(2) * dx
+        self.freqTimer_limit = 1 / freq
+        self.omega = 2 * np.pi * freq
+        self.r0_bubble = r0_bubble
+        self.r_part = 0.2 * r0_bubble
+        self.nu = self.r_part ** 2 * self.omega / 3.0 / lambda_part
+        self.U_0 = e * r0_bubble * self.omega
+        self.eps = np.finfo(float).eps
+        z = np.linspace(0 + dx / 2, 1 - dx / 2, nz)
+        r = np.linspace(0 + dx / 2, nr * dx - dx / 2, nr)
+        self.z1d, self.r1d = torch.from_numpy(z).cuda(), torch.from_numpy(r).cuda()
+        self.rl_double = torch.from_numpy(np.linspace(dx / 2, 2 * nr * dx - dx / 2, 2 * nr)).cuda()
+        self.bubble_Z_cm, self.bubble_R_cm = 0.5 - rp * r0_bubble, 0.0
+        self.part_Z_cm, self.part_R_cm = self.bubble_Z_cm + rp * r0_bubble, 0.0
+        (self.vorticity, self.psi, self.u_z, self.u_r, self.u_z_upen, self.u_r_upen, self._tmp, self._w2,
+         self.bubble_char_func, self.part_char_func, self.avg_psi, self.avg_vort, self.avg_part_char_func) = F.new(13)
+        s = stream_ptr()
+        _call("axb_smooth_heaviside_sphere", F.g, ptr(self.bubble_char_func), None, ptr(self.z1d), ptr(self.r1d),
+              self.bubble_Z_cm, self.bubble_R_cm, r0_bubble, self.moll_zone, s)
+        _call("axb_smooth_heaviside_sphere", F.g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d),
+              self.part_Z_cm, self.part_R_cm, self.r_part, self.moll_zone, s)
+        self._acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+        ones = torch.ones((nr, nz), dtype=torch.float64, device="cuda")
+        _call("axb_reduce_weighted_sum", F.g, ptr(self.r1d), ptr(self.part_char_func), ptr(ones), 0.0, ptr(self._acc), s)
+        self.part_vol = float(self._acc[0])          # np.sum(part_char_func * R)
+        self.part_mass = rho_s * self.part_vol
+        del ones
+        self.solver = solver if solver is not None else FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis)
+        self.t, self.it, self.dt = 0.0, 0, 0.0
+        self.U_z_cm_part, self.diff = 0.0, 0.0
+        self.F_total = 0.0
+        self.trace = []       # per step: (t, dt, U_z_cm_part, part_Z_cm, F_total) at the start of the step
+
+    def step(self, n=1):
+        for _ in range(n):
+            self._one()
+
+    def _one(self):
+        s, g, dx = stream_ptr(), self.F.g, self.dx
+        w = self.vorticity
+        _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
+        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
+        _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ptr(self.psi), self.nz, ptr(w), self.nz, s)
+        _call("axb_velocity_from_psi", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.psi), ptr(self.r1d), 0.0, 0.0,
+              None, None, s)
+        self._acc.zero_()
+        _call("axb_reduce_max_abs_sum", g, ptr(w), None, ptr(self._acc), s)
+        wmax = float(self._acc[0])
+        dt = min(0.9 * dx ** 2 / 4 / self.nu, self.CFL / (wmax + self.eps), 0.01 * self.freqTimer_limit)
+        self.dt = dt
+        _call("axb_add_bubble_flow", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_char_func),
+              ptr(self.z1d), ptr(self.r1d), self.bubble_Z_cm, self.bubble_R_cm, self.r0_bubble, self.U_0,
+              np.sin(self.omega * self.t), s)
+        a = dt / self.freqTimer_limit
+        _call("axb_axpy", g, ptr(self.avg_part_char_func), ptr(self.part_char_func), a, None, s)
+        _call("axb_axpy", g, ptr(self.avg_psi), ptr(self.psi), a, None, s)
+        _call("axb_axpy", g, ptr(self.avg_vort), ptr(w), a, None, s)
+        _call("axb_smooth_heaviside_sphere", g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d),
+              self.part_Z_cm, self.part_R_cm, self.r_part, self.moll_zone, s)
+        self._acc.zero_()
+        _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
+              ptr(self.u_r_upen), ptr(self.part_char_func), self.brink_lam, dt, None, self.U_z_cm_part, 0.0, None,
+              ptr(self.r1d), ptr(self._acc), s)
+        _call("axb_advect_vorticity_particles", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), ptr(self.z1d),
+              ptr(self.rl_double), dt, None, 0, s)
+        self.vorticity, self._w2 = self._w2, self.vorticity
+        w = self.vorticity
+        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(w), ptr(self.r1d), self.nu, dt, None, s)
+        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(w), ptr(self._tmp), ptr(self.r1d), self.nu, dt, None, s)
+        # rigid-body update on the host (compute_forces.py:4-17, particle_in_bubble_oscillatory_flow.py:323-351)
+        F_pen = self.rho_f * self.brink_lam * float(self._acc[0])
+        F_un = (self.diff * self.part_vol) / dt
+        F_total = F_pen + F_un
+        self.F_total = F_total
+        self.trace.append((self.t, dt, self.U_z_cm_part, self.part_Z_cm, F_total))
+        U_old = self.U_z_cm_part
+        self.U_z_cm_part += 0.5 * dt * (self.diff / dt + (F_total / self.part_mass))
+        self.diff = dt * F_total / self.part_mass
+        self.part_Z_cm += U_old * dt + (0.5 * dt * dt * F_total / self.part_mass)
+        self.t += dt
+        self.it += 1

@@ -754,3 +754,215 @@ def test_device_field_driver_glue(K):
     bh = b_h.copy()
     bh[a_h > 0.2] = a_h[a_h > 0.2]
     assert np.array_equal(b.get(), bh)
+
+
+# ---------------------------------------------------------------------------------------------
+# configs C2 / C3 / C5: device-resident loop bodies against the oracle-driven reference loops
+# ---------------------------------------------------------------------------------------------
+def _oracle_periodic_loop(nz, steps):
+    """examples/PeriodicFlowPastSphere/periodic_flow_past_sphere.py:95-183 with the oracle's kernels"""
+    nr, dx, g = nz // 2, 1.0 / nz, 2
+    z = np.linspace(dx / 2, 1 - dx / 2, nz)
+    r = np.linspace(dx / 2, 0.5 - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    U_0, r_cyl, Re, lam, CFL = 1.0, 0.075, 100.0, 1e12, 0.1
+    nu = U_0 * 2 * r_cyl / Re
+    T_ramp = 20 * r_cyl / U_0
+    eps = np.finfo(float).eps
+    w, psi, uz, ur, tmp, pv, chi = (np.zeros_like(Z) for _ in range(7))
+    ox.smooth_Heaviside(chi, -np.sqrt((Z - 0.85) ** 2 + R ** 2) + r_cyl, dx * 2 ** 0.5)
+    solver = ox.FastDiagonalisationOracle(nr, nz - 2 * g, dx, "stokes", "homogenous_neumann_along_r_and_periodic_along_z")
+    t = 0.0
+    for _ in range(steps):
+        ox.kill_boundary_vorticity_sine_r(w, R, 3, dx)
+        inner = psi[:, g:-g].copy()
+        solver.solve(inner, w[:, g:-g])
+        psi[:, g:-g] = inner
+        ox.compute_velocity_from_psi(uz, ur, psi, R, dx, periodic_ghost=g)
+        px = np.sin(0.5 * np.pi * t / T_ramp) if t < T_ramp else 1.0
+        py = 5e-2 * np.sin(np.pi * t / T_ramp) if t < T_ramp else 0.0
+        uz += U_0 * px
+        ur += U_0 * py
+        dt = min(0.9 * dx ** 2 / 4 / nu, CFL * dx / (np.amax(np.fabs(uz) + np.fabs(ur)) + eps))
+        uzu, uru = uz.copy(), ur.copy()
+        ox.brinkmann_penalize(lam, dt, chi, 0.0, 0.0, uzu, uru, uz, ur)
+        dz, dr = uz - uzu, ur - uru
+        ox.compute_vorticity_from_velocity(pv, dz, dr, dx, periodic_ghost=g)
+        w += pv
+        ox.advect_vorticity_via_eno3(w, uz, ur, dt, dx)
+        ox.diffusion_RK2(w, tmp, R, nu, dt, dx, periodic_ghost=g)
+        t += dt
+    return w, psi, t
+
+
+def test_periodic_rigid_flow_stepper(K):
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    nz, steps = 128, 10
+    w, psi, t = _oracle_periodic_loop(nz, steps)
+    s = RigidFlowStepper(nz, periodic=True, r_sph=0.075, Z_cm=0.85)
+    s.step(steps)
+    assert abs(s.scalars()["t"] - t) <= 1e-12 * t
+    g = 2
+    assert_close(s.psi.cpu().numpy()[:, g:-g], psi[:, g:-g], 1e-9, "psi (periodic)")
+    assert_close(s.vorticity.cpu().numpy()[:, g:-g], w[:, g:-g], 1e-9, "vorticity (periodic)")
+
+
+def _oracle_soft_sphere_loop(nz, steps):
+    """examples/SoftSphereStreaming/soft_sphere_streaming.py:129-274 without the skfmm re-initialisation"""
+    nr, dx = nz // 2, 1.0 / nz
+    CFL, eps = 0.1, np.finfo(float).eps
+    lam, moll = 1e8, dx * 2
+    zone = moll + 4 * dx
+    r_ball, freq, e, rho_f, zeta = 0.15, 16.0, 0.1, 1.0, 0.25
+    omega = 2 * np.pi * freq
+    U_0 = e * r_ball * omega
+    nu = e * U_0 * r_ball / (e / 0.125) ** 2
+    G = e * rho_f * (r_ball * omega) ** 2 / 0.1
+    flim = 1 / freq
+    z = np.linspace(dx / 2, 1 - dx / 2, nz)
+    r = np.linspace(dx / 2, 0.5 - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    phi = -np.sqrt((Z - 0.5) ** 2 + R ** 2) + r_ball
+    chi, tchi = np.zeros_like(Z), np.zeros_like(Z)
+    ox.smooth_Heaviside(chi, phi, moll)
+    w, psi, uz, ur, tmp, pv = (np.zeros_like(Z) for _ in range(6))
+    eta1, eta2 = Z.copy(), R.copy()
+    names = ("s11", "s12", "s22", "e1z", "e1r", "e2z", "e2r", "tz", "tr")
+    a = {n: np.zeros_like(Z) for n in names}
+    avg_psi = np.zeros_like(Z)
+    solver = ox.FastDiagonalisationOracle(nr, nz, dx, "stokes")
+    t, ft = 0.0, 0.0
+    for _ in range(steps):
+        ox.kill_boundary_vorticity_sine_z(w, Z, 3, dx)
+        ox.kill_boundary_vorticity_sine_r(w, R, 3, dx)
+        solver.solve(psi, w)
+        ox.compute_velocity_from_psi(uz, ur, psi, R, dx)
+        dt = min(CFL * dx / np.sqrt(G / rho_f), CFL * dx / (np.amax(np.fabs(uz) + np.fabs(ur)) + eps), 0.9 * dx ** 2 / 4 / nu)
+        if ft + dt > flim:
+            dt = flim - ft
+        avg_psi += psi * dt
+        ox.advect_refmap_via_eno3(eta1, eta2, uz, ur, dt, dx)
+        phi_orig = -np.sqrt((eta1 - 0.5) ** 2 + (eta2 - 0.0) ** 2) + r_ball
+        band = phi > -3 * dx
+        phi[band] = phi_orig[band]
+        ox.advect_vorticity_via_eno3(w, uz, ur, dt, dx)
+        ox.smooth_Heaviside(chi, phi, moll)
+        inside = chi > 0.5
+        ox.extrapolate_eta_with_least_squares(inside, phi, eta1, eta2, zone, nr, z)
+        ox.solid_sigma(a["s11"], a["s12"], a["s22"], G, dx, eta1, eta2, a["e1z"], a["e1r"], a["e2z"], a["e2r"])
+        for n in ("s11", "s12", "s22"):
+            a[n][...] = chi * a[n]
+        ox.update_vorticity_from_solid_stress(w, a["tz"], a["tr"], a["s11"], a["s12"], a["s22"], R, dt, dx)
+        ox.smooth_Heaviside(tchi, -np.sqrt((Z - (0.5 + e * r_ball * np.sin(omega * t))) ** 2 + R ** 2) + zeta * r_ball, moll)
+        uzu, uru = uz.copy(), ur.copy()
+        ox.brinkmann_penalize(lam, dt, tchi, U_0 * np.cos(omega * t), 0.0, uzu, uru, uz, ur)
+        ox.compute_vorticity_from_velocity(pv, uz - uzu, ur - uru, dx)
+        w += pv
+        ox.diffusion_RK2(w, tmp, R, nu, dt, dx)
+        t += dt
+        ft += dt
+    return w, eta1, eta2, phi, avg_psi, t
+
+
+def test_soft_sphere_stepper(K):
+    from pyaxisymflow_b200.timestep import SoftSphereStepper
+
+    nz, steps = 64, 6
+    w, eta1, eta2, phi, avg_psi, t = _oracle_soft_sphere_loop(nz, steps)
+    s = SoftSphereStepper(nz)
+    s.step(steps)
+    assert abs(s.t - t) <= 1e-12 * t and s.ls_sweeps >= 4
+    assert_close(s.eta1.cpu().numpy(), eta1, 1e-10, "eta1")
+    assert_close(s.eta2.cpu().numpy(), eta2, 1e-10, "eta2")
+    assert_close(s.ball_phi.cpu().numpy(), phi, 1e-10, "ball_phi")
+    assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (soft sphere)")
+    assert_close(s.avg_psi.cpu().numpy(), avg_psi, 1e-9, "avg_psi")
+
+
+def _oracle_particle_loop(nz, steps, freq=8.0, e=0.01, trace=None):
+    """examples/ParticleOscillatoryFlowCases/particle_in_bubble_oscillatory_flow.py:159-358.
+
+    The penalisation force F = rho*lam*sum(R*chi*(u_z - U)) with lam = 1e12 is a sum of differences
+    that cancel to ~1e-9 of their operands, so the reference's own rigid-body feedback (F -> U ->
+    next step's penalisation) is only reproducible to ~1e-7 between any two summation orders.  When a
+    `trace` of the device run is given, the particle velocity / position entering each step are taken
+    from it, which isolates the field kernels (compared at 1e-9); the forces are compared separately."""
+    forces = []
+    nr, dx = nz // 2, 1.0 / nz
+    CFL, eps, lam, moll = 0.1, np.finfo(float).eps, 1e12, np.sqrt(2) * dx
+    flim, omega = 1 / freq, 2 * np.pi * freq
+    r0, rho_f, rho_s = 0.25, 1.0, 1.0
+    r_part = 0.2 * r0
+    nu = r_part ** 2 * omega / 3.0 / 20.0
+    U_0 = e * r0 * omega
+    z = np.linspace(dx / 2, 1 - dx / 2, nz)
+    r = np.linspace(dx / 2, 0.5 - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    bz, br = 0.5 - 2.0 * r0, 0.0
+    bchi = np.zeros_like(Z)
+    ox.smooth_Heaviside(bchi, -np.sqrt((Z - bz) ** 2 + (R - br) ** 2) + r0, moll)
+    inb = bchi >= 0.5
+    pz = bz + 2.0 * r0
+    pchi = np.zeros_like(Z)
+    ox.smooth_Heaviside(pchi, -np.sqrt((Z - pz) ** 2 + R ** 2) + r_part, moll)
+    part_vol = np.sum(pchi * R)
+    part_mass = rho_s * part_vol
+    w, psi, uz, ur, tmp, pv, avg_vort = (np.zeros_like(Z) for _ in range(7))
+    Zd, Rd = np.meshgrid(z, np.linspace(dx / 2, 2 * nr * dx - dx / 2, 2 * nr))
+    zp, rp_, wp = Zd.copy(), Rd.copy(), 0 * Zd
+    solver = ox.FastDiagonalisationOracle(nr, nz, dx, "stokes")
+    t, U, diff = 0.0, 0.0, 0.0
+    for _ in range(steps):
+        ox.kill_boundary_vorticity_sine_z(w, Z, 3, dx)
+        ox.kill_boundary_vorticity_sine_r(w, R, 3, dx)
+        solver.solve(psi, w)
+        ox.compute_velocity_from_psi(uz, ur, psi, R, dx)
+        if trace is not None:
+            U, pz = trace[len(forces)][2], trace[len(forces)][3]
+        dt = min(0.9 * dx ** 2 / 4 / nu, CFL / (np.amax(np.fabs(w)) + eps), 0.01 * flim)
+        s = np.sin(omega * t)
+        uz += inb * (U_0 * (Z - bz) * s / r0)
+        ur += inb * (U_0 * (R - br) * s / r0)
+        uz += (1.0 - inb) * U_0 * (Z - bz) * s * r0 ** 2 / ((Z - bz) ** 2 + (R - br) ** 2) ** 1.5
+        ur += (1.0 - inb) * U_0 * (R - br) * s * r0 ** 2 / ((Z - bz) ** 2 + (R - br) ** 2) ** 1.5
+        avg_vort += w * dt / flim
+        ox.smooth_Heaviside(pchi, -np.sqrt((Z - pz) ** 2 + R ** 2) + r_part, moll)
+        uzu, uru = uz.copy(), ur.copy()
+        ox.brinkmann_penalize(lam, dt, pchi, U, 0.0, uzu, uru, uz, ur)
+        ox.compute_vorticity_from_velocity(pv, uz - uzu, ur - uru, dx)
+        w += pv
+        F_pen, F_un = ox.compute_force_on_body(R, pchi, rho_f, lam, uz, U, part_vol, dt, diff)
+        F = F_pen + F_un
+        forces.append(F)
+        ox.advect_vorticity_via_particles(zp, rp_, wp, w, Zd, Rd, nr, uz, ur, dx, dt)
+        ox.diffusion_RK2(w, tmp, R, nu, dt, dx)
+        U_old = U
+        U += 0.5 * dt * (diff / dt + F / part_mass)
+        diff = dt * F / part_mass
+        pz += U_old * dt + (0.5 * dt * dt * F / part_mass)
+        t += dt
+    return w, avg_vort, t, pz, U, forces
+
+
+def test_particle_flow_stepper_and_ensemble(K):
+    from pyaxisymflow_b200.timestep import ParticleFlowStepper
+
+    nz, steps = 80, 8
+    s = ParticleFlowStepper(nz)
+    s.step(steps)
+    w, avg_vort, t, pz, U, forces = _oracle_particle_loop(nz, steps, trace=s.trace)
+    assert abs(s.t - t) <= 1e-12 * t
+    assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (particle case)")
+    assert_close(s.avg_vort.cpu().numpy(), avg_vort, 1e-9, "avg_vort")
+    for got, want in zip(s.trace, forces):
+        assert abs(got[4] - want) <= 1e-5 * max(abs(want), 1e-12), (got[4], want)
+    # free-running reference loop (its own rigid-body feedback): agreement to the conditioning of F
+    wf, _, tf, pzf, Uf, _ = _oracle_particle_loop(nz, steps)
+    assert_close(s.vorticity.cpu().numpy(), wf, 1e-5, "vorticity vs free-running reference loop")
+    assert abs(s.part_Z_cm - pzf) <= 1e-9
+    # two ensemble members sharing one set of solver factors, different sweep parameters
+    a = ParticleFlowStepper(nz, freq=16.0, e=0.02, solver=s.solver)
+    a.step(steps)
+    wa = _oracle_particle_loop(nz, steps, freq=16.0, e=0.02, trace=a.trace)[0]
+    assert_close(a.vorticity.cpu().numpy(), wa, 1e-9, "second ensemble member")
