@@ -205,18 +205,25 @@ def run_gpu_arm(args, nr, nz):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    if world > 1:
-        from pyaxisymflow_b200.slab import SlabRigidFlowStepper
+    basis = "analytic" if max(nr, nz) >= 1536 else "auto"
+    cases = 1
+    workload = f"rigid-flow timestep (FlowPastSphere loop body) at {nr}x{nz}"
+    if args.config == "c4":
+        if world > 1:
+            from pyaxisymflow_b200.slab import SlabRigidFlowStepper
 
-        stepper = SlabRigidFlowStepper(nz, grid_size_r=nr)
+            stepper = SlabRigidFlowStepper(nz, grid_size_r=nr)
+        else:
+            stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis)
         scaling = "strong"
+        # synthetic start: seeded band-limited vorticity blob so every kernel sees
+        # non-trivial data from the first step on
+        stepper.seed_vorticity()
     else:
-        stepper = RigidFlowStepper(nz, grid_size_r=nr, basis="analytic" if max(nr, nz) >= 1536 else "auto")
-        scaling = "strong"
-    # synthetic start: seeded band-limited vorticity blob so every kernel sees
-    # non-trivial data from the first step on
-    torch.manual_seed(0)
-    stepper.seed_vorticity()
+        stepper = _ConfigRunner(args.config, nr, nz, basis, args.cases)
+        scaling = "weak"          # independent cases / replicas per GPU, no communication
+        cases = stepper.cases * world
+        workload = stepper.workload
 
     def barrier():
         torch.cuda.synchronize()
@@ -247,16 +254,20 @@ def run_gpu_arm(args, nr, nz):
         ms = t.item()
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
-    value = nr * nz / (ms_per_step * 1e-3)
+    value = cases * nr * nz / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (k_dgemm): flops of the four GEMMs / their device time
-    solve_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
+    if probes and probes[0] is not None:
+        solve_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
+    else:
+        solve_ms = stepper.solve_probe()
+    solves_per_step = getattr(stepper, "cases", 1)
     flops = stepper.solve_flops()
     achieved = flops / (solve_ms * 1e-3) / 1e12
 
     # ---- e2e: host-resident caller, H2D of the step's inputs + D2H of its result inside the timing
     e2e = None
-    if world == 1:
+    if world == 1 and args.config == "c4":
         hw = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
         hc = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
         ho = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
@@ -283,7 +294,7 @@ def run_gpu_arm(args, nr, nz):
         except OSError:
             mp = {}
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "c4":
             secs, sample = cpu_step_seconds(nr, nz)
             cpu = {"value": nr * nz / secs, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": sample}
@@ -291,15 +302,16 @@ def run_gpu_arm(args, nr, nz):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"rigid-flow timestep (FlowPastSphere loop body) at {nr}x{nz}",
-                       "grid": [nr, nz], "parallelism": "single GPU" if world == 1 else f"z-slab x{world}",
+            "config": {"workload": workload, "name": args.config, "cases": cases,
+                       "grid": [nr, nz], "parallelism": "single GPU" if world == 1 else (
+                           f"z-slab x{world}" if args.config == "c4" else f"{world} independent replicas"),
                        "l2": "fields (%.0f MiB each) exceed the 126 MB L2; no flush needed" % (nr * nz * 8 / 2 ** 20),
                        "basis": stepper.solver_basis()},
             "roofline": {"bound": "tensor", "kernel": "k_dgemm (4 launches per solve)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no "
                                         "FP64 entry)",
-                         "solve_ms": solve_ms, "solve_share_of_step": solve_ms / ms_per_step,
+                         "solve_ms": solve_ms, "solve_share_of_step": solves_per_step * solve_ms / ms_per_step,
                          "hbm_peak_gbs": mp.get("hbm_gbs")},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -308,19 +320,91 @@ def run_gpu_arm(args, nr, nz):
         dist.destroy_process_group()
 
 
+class _ConfigRunner:
+    """BASELINE.json configs other than the headline one, behind the stepper interface bench uses:
+    c2 periodic flow past a sphere, c3 soft-sphere streaming, c5 particle ensemble (cases per GPU)."""
+
+    def __init__(self, name, nr, nz, basis, cases):
+        import torch
+
+        from pyaxisymflow_b200.timestep import ParticleFlowStepper, RigidFlowStepper, SoftSphereStepper
+
+        self.torch = torch
+        self.cases = 1
+        if name == "c2":
+            self.members = [RigidFlowStepper(nz, grid_size_r=nr, periodic=True, r_sph=0.075, Z_cm=0.85, basis=basis)]
+            self.members[0].seed_vorticity()
+            self.workload = f"PeriodicFlowPastSphere loop body at {nr}x{nz} (periodic z, ghost 2)"
+        elif name == "c3":
+            self.members = [SoftSphereStepper(nz, grid_size_r=nr, basis=basis)]
+            self.workload = (f"SoftSphereStreaming loop body at {nr}x{nz} (reference-map solid; skfmm "
+                             "re-initialisation excluded on both arms)")
+        else:
+            first = ParticleFlowStepper(nz, grid_size_r=nr, basis=basis)
+            self.members = [first]
+            freqs = [4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0, 32.0]
+            for i in range(1, cases):
+                self.members.append(ParticleFlowStepper(nz, grid_size_r=nr, freq=freqs[i % 8],
+                                                        e=0.005 * (1 + (i // 8) % 8), solver=first.solver))
+            self.cases = cases
+            self.workload = f"ensemble of {cases} ParticleOscillatoryFlowCases per GPU at {nr}x{nz} (MP4 remeshing)"
+        self.solver = self.members[0].solver
+        self.vorticity = self.members[0].vorticity
+        self.char_func = None
+
+    def step(self, n=1):
+        for _ in range(n):
+            for m in self.members:
+                m.step(1)
+
+    def step_probed(self):
+        self.step(1)
+        return None
+
+    def solve_probe(self, reps=3):
+        """device time of one solve of one member, measured outside the timed steps"""
+        t = self.torch
+        m = self.members[0]
+        per = getattr(m, "periodic", False)
+        sol = m.psi[:, 2:-2] if per else m.psi
+        rhs = m.vorticity[:, 2:-2] if per else m.vorticity
+        keep = sol.clone()
+        m.solver.solve(sol, rhs)
+        a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            m.solver.solve(sol, rhs)
+        b.record()
+        t.cuda.synchronize()
+        sol.copy_(keep)
+        return a.elapsed_time(b) / reps
+
+    def solve_flops(self):
+        nr, nz = self.solver.grid_size_r, self.solver.grid_size_z
+        return 4.0 * nr * nz * (nr + nz)
+
+    def solver_basis(self):
+        return self.solver.basis
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nz", type=int, default=16384, help="grid_size_z (default: the 4096x16384 workload)")
+    ap.add_argument("--nz", type=int, default=None, help="grid_size_z (default: the configuration's own)")
     ap.add_argument("--nr", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c4", choices=["c4", "c2", "c3", "c5"],
+                    help="c4 (default): 4096x16384 rigid flow, the configuration the metric is quoted on; "
+                         "c2: periodic 1024x4096; c3: soft sphere 2048x8192; c5: particle ensemble 1024x2048")
+    ap.add_argument("--cases", type=int, default=8, help="ensemble members per GPU (c5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    nz = args.nz
-    nr = args.nr if args.nr is not None else nz // 4
+    defaults = {"c4": (4096, 16384), "c2": (1024, 4096), "c3": (2048, 8192), "c5": (1024, 2048)}
+    nz = args.nz if args.nz is not None else defaults[args.config][1]
+    nr = args.nr if args.nr is not None else (nz // 4 if args.config != "c5" else nz // 2)
     if args.impl == "reference":
         run_reference_arm(args, nr, nz)
     else:

@@ -19,6 +19,8 @@
 //     with explicit round-to-nearest adds/muls in the reference's operation order.
 // The "r o" scaling of the right-hand side is folded into the first factor at plan creation
 // (Vr^-1 diag(r)), so it costs nothing at solve time.
+#include <cstdlib>
+
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "axb_common.cuh"
@@ -69,6 +71,7 @@ struct GemmArgs {
   const double* scale_n;  // lam_z[N]
   double c0, c1;
   int tiles_m, tiles_n;
+  int group;   // tile-rows per rasterisation group
 };
 
 // VEC16: all of A, B 16-byte aligned with even leading dimensions -> 16-byte cp.async
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm(GemmArgs p) {
   // grouped rasterisation: 8 tile-rows per group, column-major inside a group
   int tile_m, tile_n;
   {
-    const int GROUP = 8;
+    const int GROUP = p.group;
     const int pid = blockIdx.x;
     const int per_group = GROUP * p.tiles_n;
     const int gid = pid / per_group;
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   int tile_m, tile_n;
   {
-    const int GROUP = 8;
+    const int GROUP = p.group;
     const int pid = blockIdx.x;
     const int per_group = GROUP * p.tiles_n;
     const int gid = pid / per_group;
@@ -427,15 +430,20 @@ EncodeTiledFn get_encoder() {
   return fn;
 }
 // 2-D row-major FP64 matrix (rows x cols, pitch ld): box = box_rows x 16 columns (128 bytes)
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 bool encode_map(CUtensorMap* m, const double* ptr, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) return false;
+  static const int promo = env_int("AXB_GEMM_L2PROMO", 2);   // 0 none, 1 64B, 2 128B, 3 256B
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
   const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, (CUtensorMapL2promotion)promo,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 int g_force_ldgsts = 0;  // axb_dgemm_set_path(1) forces the LDGSTS variant (tests exercise both)
@@ -452,6 +460,8 @@ int launch_dgemm(int M, int N, int K, const double* A, long long lda, const doub
   p.scale_m = scale_m; p.scale_n = scale_n; p.c0 = c0; p.c1 = c1;
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + BN - 1) / BN;
+  static const int group = env_int("AXB_GEMM_GROUP", 8);
+  p.group = group < 1 ? 1 : group;
   const bool vec16 = axb_al16(A) && axb_al16(B) && !(lda & 1) && !(ldb & 1) && !(K & 1) && !(N & 1);
   const dim3 grid(p.tiles_m * p.tiles_n);
   static bool attr_set = false;
