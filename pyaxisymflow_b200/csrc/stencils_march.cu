@@ -80,20 +80,25 @@ constexpr int UR = 4;   // rows per unrolled step of the fast paths (RB is a mul
 // -------------------------------------------------------------------------------------
 // G-VEL
 // -------------------------------------------------------------------------------------
-template <bool REDUCE>
+// PATH: 1 = branch-free interior blocks only, 2 = the general (edge) blocks only.  Every operation is
+// launched as the pair <1>, <2>: the two kernels get their own register allocation (the interior one
+// is the hot one), blocks that belong to the other kernel leave at once.
+template <bool REDUCE, int PATH>
 __global__ void __launch_bounds__(MT)
     km_velocity(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ psi,
                 const double* __restrict__ r1d, double uz_add, double ur_add, const double* __restrict__ add_dev,
                 double* umax_out, bool vec) {
   extern __shared__ double s_inv[];
   const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
+  if ((PATH == 1) != interior) return;
   for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
   __syncthreads();
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local_max = 0.0;
   if (add_dev) { uz_add = add_dev[0]; ur_add = add_dev[1]; }
-  if (block_interior(g, j0, j1, RB, 1, 1, vec)) {
+  if (PATH == 1) {
     const double inv_h = 1.0 / (2 * g.dx);
     const long long ld = g.ld;
     const double* p = psi + (long long)(j0 - 1) * ld + k;
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(MT)
       }
       p += UR * ld; oz += UR * ld; orr += UR * ld;
     }
-  } else {
+  } else if (PATH == 2) {
     const double inv_h = 1.0 / (2 * g.dx);
     double2 pm = make_double2(0, 0), pc = ld_pair(rowp(psi, g.ld, j0), k, nz, vec), pp = pc;
     if (j0 > 0) pm = ld_pair(rowp(psi, g.ld, j0 - 1), k, nz, vec);
@@ -224,7 +229,7 @@ __device__ __forceinline__ double pen_defect(double cc, double uu, double lamdt,
   return pen_val(uu, l, U, 1.0 / (1 + l)) - uu;
 }
 
-template <bool REDUCE>
+template <bool REDUCE, int PATH>
 __global__ void __launch_bounds__(MT)
     km_penalise(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, double* __restrict__ w,
                 const double* __restrict__ uzu, const double* __restrict__ uru, const double* __restrict__ chi,
@@ -234,9 +239,11 @@ __global__ void __launch_bounds__(MT)
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local = 0.0;
+  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
+  if ((PATH == 1) != interior) return;
   if (dt_dev) dt = *dt_dev;
   if (U_dev) { U_z = U_dev[0]; U_r = U_dev[1]; }
-  if (block_interior(g, j0, j1, RB, 1, 1, vec)) {
+  if (PATH == 1) {
     const double lamdt = lam * dt;
     const double inv_h = 1.0 / (2 * g.dx);
     const long long ld = g.ld;
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(MT)
       }
       pc_ += 2 * ld; pz_ += 2 * ld; pr_ += 2 * ld; oz += 2 * ld; orr += 2 * ld; wr += 2 * ld;
     }
-  } else {
+  } else if (PATH == 2) {
     const double lamdt = lam * dt;
     const double inv_h = 1.0 / (2 * g.dx);
     PenRow cur = pen_row(uzu, uru, chi, g.ld, j0, k, nz, vec, lamdt, U_z, U_r), nxt = cur;
@@ -333,12 +340,14 @@ __global__ void __launch_bounds__(MT)
 // -------------------------------------------------------------------------------------
 // G-DIF
 // -------------------------------------------------------------------------------------
-template <int STAGE>
+template <int STAGE, int PATH>
 __global__ void __launch_bounds__(MT)
     km_diffusion(GridD g, int RB, double* out, const double* __restrict__ in, const double* src2,
                  const double* __restrict__ r1d, double nu, double dt, const double* __restrict__ dt_dev, bool vec) {
   extern __shared__ double s_inv[];
   const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
+  if ((PATH == 1) != interior) return;
   for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
   __syncthreads();
   const Cols c = make_cols(g);
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(MT)
   if (dt_dev) dt = *dt_dev;
   const double coef = (STAGE == 1) ? (0.5 * nu * dt) : (nu * dt);
   const double inv_dx2 = 1.0 / (g.dx * g.dx), inv_h = 1.0 / (2 * g.dx);
-  if (block_interior(g, j0, j1, RB, 1, 1, vec)) {
+  if (PATH == 1) {
     const long long ld = g.ld;
     const double* p = in + (long long)(j0 - 1) * ld + k;
     double2 pm = ld2(p), pc = ld2(p + ld);
@@ -387,6 +396,7 @@ __global__ void __launch_bounds__(MT)
     }
     return;
   }
+  if (PATH != 2) return;
   double2 pm = make_double2(0, 0), pc = ld_pair(rowp(in, g.ld, j0), k, nz, vec), pp = pc;
   if (j0 > 0) pm = ld_pair(rowp(in, g.ld, j0 - 1), k, nz, vec);
   for (int j = j0; j < j1; ++j) {
@@ -432,13 +442,15 @@ __device__ __forceinline__ double2 ld_row_m(const double* f, long long ld, int j
 
 // NF fields share the velocity.  Row window per field: samples q[0..3] = rows j-1 .. j+2 (products
 // with u_r when CONS), centre values w0 = f[j], w1 = f[j+1], w2 = f[j+2]; per-thread rolling back face.
-template <int NF, bool CONS, bool MIRROR, bool FLUXONLY>
+template <int NF, bool CONS, bool MIRROR, bool FLUXONLY, int PATH>
 __global__ void __launch_bounds__(MT)
     km_eno3(GridD g, int RB, double* __restrict__ out0, double* __restrict__ out1, const double* __restrict__ in0,
             const double* __restrict__ in1, const double* __restrict__ u_z, const double* __restrict__ u_r,
             double inv_dx, double dt, const double* __restrict__ dt_dev, double sign0, double sign1, bool vec) {
   const int j_lo = MIRROR ? 0 : 2, j_hi = g.nr - 3;   // rows that are advected
   const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  const bool interior = block_interior(g, j0, j1, RB, 2, 2, vec);
+  if ((PATH == 1) != interior) return;
   const Cols c = make_cols(g);
   const int nz = g.nz, k = c.k;
   if (!c.own0 && !c.own1) return;   // no shuffles in this kernel: idle threads may leave
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(MT)
   const double signs[2] = {sign0, sign1};
   const int jmin = MIRROR ? -2 : 0;
 
-  if (!MIRROR ? block_interior(g, j0, j1, RB, 2, 2, vec) : block_interior(g, j0, j1, RB, 2, 2, vec)) {
+  if (PATH == 1) {
     // branch-free interior path: every load of a row is issued before any of it is consumed
     const long long ld = g.ld;
     const long long off = (long long)j0 * ld + k;
@@ -526,6 +538,7 @@ __global__ void __launch_bounds__(MT)
     }
     return;
   }
+  if (PATH != 2) return;
   // rolling state: velocity rows j-1..j+2 (u_r), per field q rows j-1..j+2 and the centres
   double2 vr[4];
   double2 q[2][4], wc[2][3], Fb[2];
@@ -640,12 +653,11 @@ inline dim3 march_grid(const GridD& d, int rb) {
 int march_velocity(const GridD& d, double* u_z, double* u_r, const double* psi, const double* r1d, double uz_add,
                    double ur_add, const double* add_dev, double* umax_out, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
-  if (umax_out)
-    km_velocity<true><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, u_z, u_r, psi, r1d, uz_add, ur_add,
-                                                                         add_dev, umax_out, vec);
-  else
-    km_velocity<false><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, u_z, u_r, psi, r1d, uz_add, ur_add,
-                                                                          add_dev, nullptr, vec);
+#define VEL(R, P) km_velocity<R, P><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, u_z, u_r, psi, r1d, uz_add, \
+                                                                                     ur_add, add_dev, umax_out, vec)
+  if (umax_out) { VEL(true, 1); VEL(true, 2); }
+  else { VEL(false, 1); VEL(false, 2); }
+#undef VEL
   return (int)cudaGetLastError();
 }
 
@@ -653,22 +665,22 @@ int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const do
                    const double* chi, double lam, double dt, const double* dt_dev, double U_z, double U_r,
                    const double* U_dev, const double* r1d, double* sum_out, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
-  if (sum_out)
-    km_penalise<true><<<march_grid(d, rb), MT, 0, s>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, U_r,
-                                                       U_dev, r1d, sum_out, vec);
-  else
-    km_penalise<false><<<march_grid(d, rb), MT, 0, s>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, U_r,
-                                                        U_dev, r1d, nullptr, vec);
+#define PEN(R, P) km_penalise<R, P><<<march_grid(d, rb), MT, 0, s>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, \
+                                                                   U_r, U_dev, r1d, sum_out, vec)
+  if (sum_out) { PEN(true, 1); PEN(true, 2); }
+  else { PEN(false, 1); PEN(false, 2); }
+#undef PEN
   return (int)cudaGetLastError();
 }
 
 int march_diffusion(int stage, const GridD& d, double* out, const double* in, const double* src2, const double* r1d,
                     double nu, double dt, const double* dt_dev, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
-  if (stage == 1)
-    km_diffusion<1><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, out, in, src2, r1d, nu, dt, dt_dev, vec);
-  else
-    km_diffusion<2><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, out, in, src2, r1d, nu, dt, dt_dev, vec);
+#define DIF(S, P) km_diffusion<S, P><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, out, in, src2, r1d, nu, dt, \
+                                                                                      dt_dev, vec)
+  if (stage == 1) { DIF(1, 1); DIF(1, 2); }
+  else { DIF(2, 1); DIF(2, 2); }
+#undef DIF
   return (int)cudaGetLastError();
 }
 
@@ -677,8 +689,13 @@ int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, do
                const double* dt_dev, double sign0, double sign1, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
   const dim3 grd = march_grid(d, rb);
-#define LAUNCH(NF, C, M, F) \
-  km_eno3<NF, C, M, F><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, vec)
+#define LAUNCH(NF, C, M, F)                                                                                              \
+  do {                                                                                                                  \
+    km_eno3<NF, C, M, F, 1><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, \
+                                               vec);                                                                    \
+    km_eno3<NF, C, M, F, 2><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, \
+                                               vec);                                                                    \
+  } while (0)
   if (nf == 1 && cons && mirror && !fluxonly) LAUNCH(1, true, true, false);
   else if (nf == 2 && !cons && mirror && !fluxonly) LAUNCH(2, false, true, false);
   else if (nf == 1 && cons && !mirror && fluxonly) LAUNCH(1, true, false, true);
