@@ -307,7 +307,7 @@ def run_gpu_arm(args, nr, nz):
                            f"z-slab x{world}" if args.config == "c4" else f"{world} independent replicas"),
                        "l2": "fields (%.0f MiB each) exceed the 126 MB L2; no flush needed" % (nr * nz * 8 / 2 ** 20),
                        "basis": stepper.solver_basis()},
-            "roofline": {"bound": "tensor", "kernel": "k_dgemm (4 launches per solve)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": stepper.solve_kernel_note(), "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no "
                                         "FP64 entry)",
@@ -380,11 +380,13 @@ class _ConfigRunner:
         return a.elapsed_time(b) / reps
 
     def solve_flops(self):
-        nr, nz = self.solver.grid_size_r, self.solver.grid_size_z
-        return 4.0 * nr * nz * (nr + nz)
+        return self.solver.flops()
 
     def solver_basis(self):
         return self.solver.basis
+
+    def solve_kernel_note(self):
+        return self.members[0].solver.kernel_note()
 
 
 def main():

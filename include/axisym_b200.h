@@ -237,13 +237,31 @@ int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const dou
  *      lam_r[nr], lam_z[nz]; spectral scaling 1 / (c0 + c1*(lam_z[n] + lam_r[m])).
  *      solve: psi = Lrb * (((Lr*rhs) * Rz) o scale) * Rzb, four FP64 tensor-core GEMMs with
  *      the scaling fused in the second one's epilogue.  work: 2*nr*nz doubles. ---------------- */
+/*      Parity-split z-transform (n_leaves > 0): the cosine / sine eigenvectors of the uniform-grid
+ *      z operator satisfy V[N-1-j, k] = (-1)^k V[j, k], so after folding a row into its even and
+ *      odd parts (x[j] +- x[N-1-j], j < N/2) the even modes only see the even part and the odd
+ *      modes the odd part: one N x N product becomes two N/2 x N/2 ones (half the flops).  For the
+ *      Neumann (DCT-II) family the even branch is again a DCT-II and is split recursively.  The
+ *      folded column layout is [E_L | O_L | ... | O_1]; leaf i multiplies columns
+ *      [leaf_off[i], leaf_off[i] + leaf_n[i]) by leaf_fwd[i] (forward) / leaf_bwd[i] (backward),
+ *      fold_len[] lists the segment lengths folded in order (N, N/2, ...), lam_z is in folded
+ *      column order.  Rz / Rzb may be NULL in that case. */
+#define AXB_FD_MAX_LEAVES 8
 typedef struct axb_fd_plan {
   int32_t nr, nz;
   const double *Lr, *Rz, *Rzb, *Lrb;
   const double *lam_r, *lam_z;
   double c0, c1;
   double* work;
+  int32_t n_leaves, n_folds;
+  int32_t leaf_n[AXB_FD_MAX_LEAVES], leaf_off[AXB_FD_MAX_LEAVES], fold_len[AXB_FD_MAX_LEAVES];
+  const double* leaf_fwd[AXB_FD_MAX_LEAVES];
+  const double* leaf_bwd[AXB_FD_MAX_LEAVES];
 } axb_fd_plan_t;
+/* in-place parity fold (inverse = 0: y[j] = x[j] + x[n-1-j], y[n/2+j] = x[j] - x[n-1-j]) or unfold
+ * (inverse = 1: x[j] = y[j] + y[n/2+j], x[n-1-j] = y[j] - y[n/2+j]) of the first n columns of every
+ * row of X (rows x >= n, pitch ld); n must be a multiple of 4. */
+int axb_fd_fold(int rows, int n, double* X, int64_t ld, int inverse, axb_stream_t s);
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s);
 /* Plain row-major FP64 GEMM C = A*B (+ optional spectral scaling), the building block above:

@@ -27,7 +27,10 @@ class AxbFdPlan(Structure):
     _fields_ = [("nr", c_int32), ("nz", c_int32),
                 ("Lr", c_void_p), ("Rz", c_void_p), ("Rzb", c_void_p), ("Lrb", c_void_p),
                 ("lam_r", c_void_p), ("lam_z", c_void_p),
-                ("c0", c_double), ("c1", c_double), ("work", c_void_p)]
+                ("c0", c_double), ("c1", c_double), ("work", c_void_p),
+                ("n_leaves", c_int32), ("n_folds", c_int32),
+                ("leaf_n", c_int32 * 8), ("leaf_off", c_int32 * 8), ("fold_len", c_int32 * 8),
+                ("leaf_fwd", c_void_p * 8), ("leaf_bwd", c_void_p * 8)]
 
 
 _G = POINTER(AxbGrid)
@@ -79,6 +82,7 @@ _SIGNATURES = {
     "axb_fd_solve": [POINTER(AxbFdPlan), _P, c_int64, _P, c_int64, _S],
     "axb_dgemm": [_I, _I, _I, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _D, _D, _S],
     "axb_dgemm_set_path": [_I],
+    "axb_fd_fold": [_I, _I, _P, c_int64, _I, _S],
     "axb_halo_pack": [_G, _P, _P, _P, _I, _S],
     "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],
     "axb_slab_to_blocks": [_I, _I, c_int64, _I, _P, _P, _S],

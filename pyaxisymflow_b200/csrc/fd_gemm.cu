@@ -495,9 +495,41 @@ int launch_dgemm(int M, int N, int K, const double* A, long long lda, const doub
   return (int)cudaGetLastError();
 }
 
+// in-place parity fold / unfold of the first n columns: one thread owns the index quadruple
+// {j, n-1-j, j', n-1-j'} with j' = n/2-1-j, which is closed under the permutation
+__global__ void k_fd_fold(int rows, int n, double* __restrict__ X, long long ld, int inverse) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  const int h = n >> 1;
+  if (j >= (n >> 2)) return;
+  double* row = X + (long long)m * ld;
+  const int jp = h - 1 - j;
+  const double a0 = row[j], a1 = row[h + jp];      // pair j :  (j, n-1-j)   [n-1-j  = h + jp]
+  const double b0 = row[jp], b1 = row[h + j];      // pair j':  (jp, n-1-jp) [n-1-jp = h + j ]
+  if (!inverse) {
+    row[j] = a0 + a1; row[h + j] = a0 - a1;
+    row[jp] = b0 + b1; row[h + jp] = b0 - b1;
+  } else {
+    // here (a0, b1) = (y[j], y[h+j]) and (b0, a1) = (y[jp], y[h+jp])
+    row[j] = a0 + b1; row[h + jp] = a0 - b1;       // x[j], x[n-1-j]
+    row[jp] = b0 + a1; row[h + j] = b0 - a1;       // x[jp], x[n-1-jp]
+  }
+}
+
+int launch_fold(int rows, int n, double* X, long long ld, int inverse, cudaStream_t s) {
+  if (rows < 1 || n < 4 || (n & 3) || !X || ld < n) return AXB_EINVAL;
+  k_fd_fold<<<dim3(((n >> 2) + 127) / 128, rows), 128, 0, s>>>(rows, n, X, ld, inverse);
+  AXB_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
+
+int axb_fd_fold(int rows, int n, double* X, int64_t ld, int inverse, axb_stream_t s) {
+  return launch_fold(rows, n, X, ld, inverse, s);
+}
 
 int axb_dgemm_set_path(int force_ldgsts) {
   g_force_ldgsts = force_ldgsts;
@@ -512,8 +544,7 @@ int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B
 
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s) {
-  if (!p || !sol || !rhs || !p->Lr || !p->Rz || !p->Rzb || !p->Lrb || !p->lam_r || !p->lam_z || !p->work)
-    return AXB_EINVAL;
+  if (!p || !sol || !rhs || !p->Lr || !p->Lrb || !p->lam_r || !p->lam_z || !p->work) return AXB_EINVAL;
   const int nr = p->nr, nz = p->nz;
   double* w0 = p->work;
   double* w1 = p->work + (long long)nr * nz;
@@ -521,6 +552,31 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
   // T1 = Lr * rhs                       (nr x nr) (nr x nz)
   rc = launch_dgemm(nr, nz, nr, p->Lr, nr, rhs, ld_rhs, w0, nz, nullptr, nullptr, 0, 0, s);
   if (rc) return rc;
+  if (p->n_leaves > 0) {
+    // parity-split z transforms (see include/axisym_b200.h)
+    if (p->n_leaves > AXB_FD_MAX_LEAVES || p->n_folds > AXB_FD_MAX_LEAVES) return AXB_EINVAL;
+    for (int f = 0; f < p->n_folds; ++f) {
+      rc = launch_fold(nr, p->fold_len[f], w0, nz, 0, s);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < p->n_leaves; ++i) {
+      const int n = p->leaf_n[i], off = p->leaf_off[i];
+      rc = launch_dgemm(nr, n, n, w0 + off, nz, p->leaf_fwd[i], n, w1 + off, nz, p->lam_r, p->lam_z + off, p->c0,
+                        p->c1, s);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < p->n_leaves; ++i) {
+      const int n = p->leaf_n[i], off = p->leaf_off[i];
+      rc = launch_dgemm(nr, n, n, w1 + off, nz, p->leaf_bwd[i], n, w0 + off, nz, nullptr, nullptr, 0, 0, s);
+      if (rc) return rc;
+    }
+    for (int f = p->n_folds - 1; f >= 0; --f) {
+      rc = launch_fold(nr, p->fold_len[f], w0, nz, 1, s);
+      if (rc) return rc;
+    }
+    return launch_dgemm(nr, nz, nr, p->Lrb, nr, w0, nz, sol, ld_sol, nullptr, nullptr, 0, 0, s);
+  }
+  if (!p->Rz || !p->Rzb) return AXB_EINVAL;
   // S = (T1 * Rz) o 1/(c0 + c1 (lam_z + lam_r))
   rc = launch_dgemm(nr, nz, nz, w0, nz, p->Rz, nz, w1, nz, p->lam_r, p->lam_z, p->c0, p->c1, s);
   if (rc) return rc;

@@ -216,13 +216,92 @@ def axial_basis_analytic(family, sign, nz, dx, device="cpu"):
     return lam[o], V
 
 
-def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="cpu"):
+def axial_natural_block(family, nz, rows, modes, device="cpu"):
+    """rows x len(modes) block V[j, k] (j < rows, k in modes, natural mode order) of the orthonormal
+    closed-form z eigenvectors, generated with exact integer argument reduction."""
+    j = torch.arange(rows, dtype=torch.int64, device=device)
+    k = torch.as_tensor(modes, dtype=torch.int64, device=device)
+    if family == "neumann":
+        m = (k[None, :] * (2 * j[:, None] + 1)) % (4 * nz)
+        V = torch.cos(m.to(torch.float64) * (np.pi / (2 * nz))) * np.sqrt(2.0 / nz)
+        V[:, k == 0] = np.sqrt(1.0 / nz)
+        return V
+    if family == "dirichlet":
+        m = ((k[None, :] + 1) * (j[:, None] + 1)) % (2 * (nz + 1))
+        return torch.sin(m.to(torch.float64) * (np.pi / (nz + 1))) * np.sqrt(2.0 / (nz + 1))
+    raise ValueError(family)
+
+
+def axial_natural_eigenvalues(family, sign, nz, dx):
+    i2 = 1 / dx / dx
+    k = np.arange(nz)
+    if family == "neumann":
+        return sign * (2 - 2 * np.cos(np.pi * k / nz)) * i2
+    return sign * (2 - 2 * np.cos(np.pi * (k + 1) / (nz + 1))) * i2
+
+
+def split_levels(family, nz, requested="auto", min_leaf=256):
+    """number of parity-split levels of the z transform (0 = dense N x N products)"""
+    if family not in ("neumann", "dirichlet"):
+        return 0
+    cap = 3 if family == "neumann" else 1      # only the DCT-II even branch is self-similar
+    if requested != "auto":
+        cap = min(cap, int(requested))
+        min_leaf = 4                            # explicit request: split as asked (tests use small grids)
+    L = 0
+    while L < cap and nz % (2 ** (L + 1) * 2) == 0 and nz // 2 ** (L + 1) >= min_leaf:
+        L += 1
+    return L
+
+
+def axial_split_plan(family, sign, nz, dx, levels, device="cpu"):
+    """Leaves of the parity-split z transform: column layout [E_L | O_L | ... | O_1].
+    Returns dict(leaf_n, leaf_off, fold_len, fwd, bwd, lam_z (folded order), modes)."""
+    lam_nat = axial_natural_eigenvalues(family, sign, nz, dx)
+    L = levels
+    nL = nz // 2 ** L
+    leaves = [("E", L, np.arange(0, nz, 2 ** L), nL)]
+    for lev in range(L, 0, -1):
+        leaves.append(("O", lev, np.arange(2 ** (lev - 1), nz, 2 ** lev), nz // 2 ** lev))
+    off, plan = 0, {"leaf_n": [], "leaf_off": [], "fwd": [], "bwd": [], "modes": []}
+    lam = np.empty(nz)
+    for _, _, modes, n in leaves:
+        assert modes.size == n
+        F = axial_natural_block(family, nz, n, modes, device=device)
+        plan["leaf_n"].append(n)
+        plan["leaf_off"].append(off)
+        plan["fwd"].append(F.contiguous())
+        plan["bwd"].append(F.t().contiguous())
+        plan["modes"].append(modes)
+        lam[off:off + n] = lam_nat[modes]
+        off += n
+    plan["fold_len"] = [nz // 2 ** lev for lev in range(L)]
+    plan["lam_z"] = lam
+    return plan
+
+
+def fold_host(x, n, inverse=False):
+    """NumPy restatement of axb_fd_fold (CPU tests of the set-up only)"""
+    h = n // 2
+    y = x.copy()
+    if not inverse:
+        a, b = x[:, :h], x[:, n - 1:h - 1:-1] if h > 0 else x[:, :0]
+        y[:, :h], y[:, h:n] = a + b, a - b
+    else:
+        e, o = x[:, :h], x[:, h:n]
+        y[:, :h] = e + o
+        y[:, n - 1:h - 1:-1] = e - o
+    return y
+
+
+def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="cpu", split="auto"):
     """Factor set of the solve  sol = Lrb (((Lr rhs) Rz) o 1/(c0 + c1 (lam_z (+) lam_r))) Rzb  as
     float64 torch tensors on ``device`` (see include/axisym_b200.h, axb_fd_plan_t)."""
     if basis == "auto":
         basis = "lapack" if max(nr, nz) < 1536 else "analytic"
     sub, diag, sup, r = radial_tridiagonal(kind, bc_type, nr, dx)
     family, sign = axial_kind(kind, bc_type)
+    zsplit = None
     if basis == "lapack":
         lam_r, Vr, Vri = radial_basis_lapack(sub, diag, sup)
         lam_z, Vz, Vzi = axial_basis_lapack(family, sign, nz, dx)
@@ -230,9 +309,14 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
         Rzb = torch.from_numpy(np.ascontiguousarray(Vz.T)).to(device)
     elif basis == "analytic":
         lam_r, Vr, Vri = radial_basis_analytic(sub, diag, sup)
-        lam_z, Vz_t = axial_basis_analytic(family, sign, nz, dx, device=device)
-        Rz = Vz_t                       # V^-T = V for an orthogonal basis
-        Rzb = Vz_t.t().contiguous()
+        levels = split_levels(family, nz, split)
+        if levels > 0:
+            zsplit = axial_split_plan(family, sign, nz, dx, levels, device=device)
+            lam_z, Rz, Rzb = zsplit["lam_z"], None, None
+        else:
+            lam_z, Vz_t = axial_basis_analytic(family, sign, nz, dx, device=device)
+            Rz = Vz_t                       # V^-T = V for an orthogonal basis
+            Rzb = Vz_t.t().contiguous()
     else:
         raise ValueError(f"unknown basis {basis!r}")
     Lr = Vri * r[None, :] if kind == "stokes" else Vri   # fold  r o rhs  into the first factor
@@ -242,7 +326,7 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
         "Rz": Rz, "Rzb": Rzb,
         "lam_r": torch.from_numpy(np.ascontiguousarray(lam_r)).to(device),
         "lam_z": torch.from_numpy(np.ascontiguousarray(lam_z)).to(device),
-        "c0": 0.0, "c1": 1.0, "basis": basis,
+        "c0": 0.0, "c1": 1.0, "basis": basis, "zsplit": zsplit,
     }
     if kind == "implicit_diffusion":
         f["c0"], f["c1"] = 1.0, -float(nu_dt)
@@ -252,18 +336,60 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
 def apply_factors_host(f, rhs):
     """NumPy evaluation of the factorised solve (used only by the CPU tests of the set-up)."""
     g = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in f.items()}
-    spec = (g["Lr"] @ rhs) @ g["Rz"]
-    spec = spec * (1.0 / (g["c0"] + g["c1"] * (g["lam_z"][None, :] + g["lam_r"][:, None])))
-    return g["Lrb"] @ (spec @ g["Rzb"])
+    scale = 1.0 / (g["c0"] + g["c1"] * (g["lam_z"][None, :] + g["lam_r"][:, None]))
+    zs = f.get("zsplit")
+    if zs is None:
+        spec = ((g["Lr"] @ rhs) @ g["Rz"]) * scale
+        return g["Lrb"] @ (spec @ g["Rzb"])
+    t = g["Lr"] @ rhs
+    for n in zs["fold_len"]:
+        t = fold_host(t, n)
+    spec = np.empty_like(t)
+    for n, off, F in zip(zs["leaf_n"], zs["leaf_off"], zs["fwd"]):
+        spec[:, off:off + n] = t[:, off:off + n] @ F.cpu().numpy()
+    spec *= scale
+    for n, off, B in zip(zs["leaf_n"], zs["leaf_off"], zs["bwd"]):
+        t[:, off:off + n] = spec[:, off:off + n] @ B.cpu().numpy()
+    for n in reversed(zs["fold_len"]):
+        t = fold_host(t, n, inverse=True)
+    return g["Lrb"] @ t
 
 
 # --------------------------------------------------------------------------------------
 # device plan + the three reference classes
 # --------------------------------------------------------------------------------------
+def make_plan(nr, nz, f, work):
+    """axb_fd_plan_t over a factor set living on the GPU"""
+    p = AxbFdPlan()
+    p.nr, p.nz = nr, nz
+    p.Lr, p.Lrb = f["Lr"].data_ptr(), f["Lrb"].data_ptr()
+    p.Rz = f["Rz"].data_ptr() if f["Rz"] is not None else None
+    p.Rzb = f["Rzb"].data_ptr() if f["Rzb"] is not None else None
+    p.lam_r, p.lam_z = f["lam_r"].data_ptr(), f["lam_z"].data_ptr()
+    p.c0, p.c1, p.work = f["c0"], f["c1"], work.data_ptr()
+    zs = f.get("zsplit")
+    p.n_leaves = p.n_folds = 0
+    if zs is not None:
+        p.n_leaves, p.n_folds = len(zs["leaf_n"]), len(zs["fold_len"])
+        for i, (n, off, F, B) in enumerate(zip(zs["leaf_n"], zs["leaf_off"], zs["fwd"], zs["bwd"])):
+            p.leaf_n[i], p.leaf_off[i] = n, off
+            p.leaf_fwd[i], p.leaf_bwd[i] = F.data_ptr(), B.data_ptr()
+        for i, n in enumerate(zs["fold_len"]):
+            p.fold_len[i] = n
+    return p
+
+
+def solve_flops(nr, nz, f):
+    """floating-point operations one solve executes with this factor set"""
+    zs = f.get("zsplit")
+    z = 2.0 * nr * nz * nz if zs is None else sum(2.0 * nr * n * n for n in zs["leaf_n"])
+    return 2 * (2.0 * nr * nr * nz) + 2 * z
+
+
 class _FdBase:
     kind = None
 
-    def _setup(self, grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, nu_dt=None):
+    def _setup(self, grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, nu_dt=None, split="auto"):
         if real_dtype != np.float64:
             raise TypeError("libaxisym_b200 computes in float64 only")
         if not torch.cuda.is_available():
@@ -271,14 +397,13 @@ class _FdBase:
         self.dx, self.grid_size_r, self.grid_size_z = dx, grid_size_r, grid_size_z
         self.real_dtype, self.bc_type = real_dtype, bc_type
         self.radial_coord = np.linspace(dx / 2, grid_size_r * dx - dx / 2, grid_size_r).reshape(grid_size_r, 1)
-        self.factors = build_factors(self.kind, bc_type, grid_size_r, grid_size_z, dx, basis, nu_dt, device="cuda")
+        self.factors = build_factors(self.kind, bc_type, grid_size_r, grid_size_z, dx, basis, nu_dt, device="cuda",
+                                     split=split)
         self.basis = self.factors["basis"]
         # spectral buffer of the reference (FastDiagonalisationStokesSolver.py:38-39) x 2
         self.work = torch.empty(2 * grid_size_r * grid_size_z, dtype=torch.float64, device="cuda")
         f = self.factors
-        self.plan = AxbFdPlan(grid_size_r, grid_size_z, f["Lr"].data_ptr(), f["Rz"].data_ptr(),
-                              f["Rzb"].data_ptr(), f["Lrb"].data_ptr(), f["lam_r"].data_ptr(),
-                              f["lam_z"].data_ptr(), f["c0"], f["c1"], self.work.data_ptr())
+        self.plan = make_plan(grid_size_r, grid_size_z, f, self.work)
 
     def _solve(self, solution_field, rhs_field):
         st = Stage()
@@ -303,11 +428,23 @@ class FastDiagonalisationStokesSolver(_FdBase):
     """kernels/FastDiagonalisationStokesSolver.py:6-156"""
     kind = "stokes"
 
-    def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto"):
-        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis)
+    def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto",
+                 split="auto"):
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, split=split)
 
     def solve(self, solution_field, rhs_field):
         self._solve(solution_field, rhs_field)
+
+    def flops(self):
+        return solve_flops(self.grid_size_r, self.grid_size_z, self.factors)
+
+    def kernel_note(self):
+        zs = self.factors.get("zsplit")
+        if zs is None:
+            return "k_dgemm_tma (4 launches per solve: 2 r-transforms + 2 dense z-transforms)"
+        n = len(zs["leaf_n"])
+        return (f"k_dgemm_tma ({2 + 2 * n} launches per solve: 2 r-transforms + 2x{n} parity-split z leaves "
+                f"{zs['leaf_n']}; flops = executed, {self.flops() / (4.0 * self.grid_size_r * self.grid_size_z * (self.grid_size_r + self.grid_size_z)):.3f} of the dense count)")
 
 
 class FastDiagonalisationPotentialSolver(_FdBase):
@@ -326,10 +463,10 @@ class ImplicitEulerDiffusionStepper(_FdBase):
     kind = "implicit_diffusion"
 
     def __init__(self, time_step, kinematic_viscosity, grid_size_r, grid_size_z, dx, real_dtype=np.float64,
-                 basis="auto"):
+                 basis="auto", split="auto"):
         self.time_step = time_step
         self.nu_times_dt = self.time_step * kinematic_viscosity
-        self._setup(grid_size_r, grid_size_z, dx, real_dtype, None, basis, nu_dt=self.nu_times_dt)
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, None, basis, nu_dt=self.nu_times_dt, split=split)
 
     def step(self, vorticity_field, dt):
         if dt != self.time_step:

@@ -160,12 +160,17 @@ def _cuda_gemm(C, A, B, scale_m=None, scale_n=None, c0=0.0, c1=1.0):
           ptr(scale_m), ptr(scale_n), float(c0), float(c1), stream_ptr())
 
 
+def _cuda_fold(x, n, inverse):
+    _call("axb_fd_fold", x.shape[0], n, ptr(x), x.stride(0), int(inverse), stream_ptr())
+
+
 class SlabFdSolver:
     """Distributed fast-diagonalisation solve on z-slabs (factors replicated on every rank)."""
 
-    def __init__(self, layout, comm, factors, gemm=None):
+    def __init__(self, layout, comm, factors, gemm=None, fold=None):
         self.L, self.comm, self.f = layout, comm, factors
         self.gemm = gemm or _cuda_gemm
+        self.fold = fold or _cuda_fold
         dev = factors["Lr"].device
         L = layout
         self.t_slab = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=dev)
@@ -177,14 +182,28 @@ class SlabFdSolver:
         L, f = self.L, self.f
         self.gemm(self.t_slab, f["Lr"], L.owned(rhs_slab))                       # r-transform, local columns
         self.comm.slab_to_rows(self.t_slab, self.rows_a)                          # all-to-all #1
-        self.gemm(self.rows_b, self.rows_a, f["Rz"], self.lam_r_local, f["lam_z"], f["c0"], f["c1"])
-        self.gemm(self.rows_a, self.rows_b, f["Rzb"])
+        zs = f.get("zsplit")
+        if zs is None:
+            self.gemm(self.rows_b, self.rows_a, f["Rz"], self.lam_r_local, f["lam_z"], f["c0"], f["c1"])
+            self.gemm(self.rows_a, self.rows_b, f["Rzb"])
+        else:                                                                     # parity-split z transforms
+            for n in zs["fold_len"]:
+                self.fold(self.rows_a, n, False)
+            for n, off, F in zip(zs["leaf_n"], zs["leaf_off"], zs["fwd"]):
+                self.gemm(self.rows_b[:, off:off + n], self.rows_a[:, off:off + n], F, self.lam_r_local,
+                          f["lam_z"][off:off + n], f["c0"], f["c1"])
+            for n, off, B in zip(zs["leaf_n"], zs["leaf_off"], zs["bwd"]):
+                self.gemm(self.rows_a[:, off:off + n], self.rows_b[:, off:off + n], B)
+            for n in reversed(zs["fold_len"]):
+                self.fold(self.rows_a, n, True)
         self.comm.rows_to_slab(self.rows_a, self.t_slab)                          # all-to-all #2
         self.gemm(L.owned(psi_slab), f["Lrb"], self.t_slab)                       # r back-transform
 
     def flops_per_rank(self):
         L = self.L
-        return 4.0 * L.nr * L.nr * L.nzl + 4.0 * L.nrl * L.nz * L.nz
+        zs = self.f.get("zsplit")
+        z = 2.0 * L.nz * L.nz if zs is None else sum(2.0 * n * n for n in zs["leaf_n"])
+        return 4.0 * L.nr * L.nr * L.nzl + 2.0 * L.nrl * z
 
 
 class SlabRigidFlowStepper:
@@ -291,6 +310,12 @@ class SlabRigidFlowStepper:
 
     def solver_basis(self):
         return self.factors["basis"]
+
+    def solve_kernel_note(self):
+        zs = self.factors.get("zsplit")
+        n = 0 if zs is None else len(zs["leaf_n"])
+        return (f"k_dgemm_tma per rank: 2 slab r-transforms + {'2 dense' if zs is None else '2x%d parity-split' % n} "
+                "z-transforms on r-slabs, 2 NCCL all-to-all in between")
 
     def scalars(self):
         st = self.state.clone()

@@ -144,11 +144,13 @@ class RigidFlowStepper:
         return ev
 
     def solve_flops(self):
-        nr, nz = self.solver.grid_size_r, self.solver.grid_size_z
-        return 4.0 * nr * nz * (nr + nz)
+        return self.solver.flops()
 
     def solver_basis(self):
         return self.solver.basis
+
+    def solve_kernel_note(self):
+        return self.solver.kernel_note()
 
     def seed_vorticity(self, seed=0, amplitude=1.0):
         """seeded band-limited blob (SURVEY.md 8d synthetic input (ii)): N(0,1) * exp(-((Z-1/2)^2+R^2)/0.02)"""

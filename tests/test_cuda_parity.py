@@ -455,6 +455,52 @@ def test_fast_diagonalisation_vs_oracle(K, nr, nz):
         assert_close(sol, ref, RTOL_LINF, f"stokes {basis} {nr}x{nz}")
 
 
+@pytest.mark.parametrize("nr,nz,split", [(96, 160, 1), (96, 160, 2), (64, 256, 3), (40, 1024, "auto")])
+def test_fast_diagonalisation_parity_split(K, nr, nz, split):
+    """parity-split z transforms (folded even/odd leaves, half to a third of the flops) against the oracle"""
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver, ImplicitEulerDiffusionStepper
+
+    rng = np.random.default_rng(13)
+    dx = 1.0 / nz
+    rhs = _rand(rng, nr, nz, 5.0)
+    o = ox.FastDiagonalisationOracle(nr, nz, dx, "stokes")
+    ref = np.zeros_like(rhs)
+    o.solve(ref, rhs)
+    s = FastDiagonalisationStokesSolver(nr, nz, dx, basis="analytic", split=split)
+    assert s.factors["zsplit"] is not None and s.plan.n_leaves >= 2
+    assert s.flops() < 0.75 * 4.0 * nr * nz * (nr + nz)
+    sol = np.zeros_like(rhs)
+    s.solve(sol, rhs)
+    assert_close(sol, ref, RTOL_LINF, f"split {split}")
+    dense = FastDiagonalisationStokesSolver(nr, nz, dx, basis="analytic", split=0)
+    sol0 = np.zeros_like(rhs)
+    dense.solve(sol0, rhs)
+    assert_close(sol, sol0, 1e-12, "split vs dense")
+    # the Dirichlet-type (implicit diffusion) family splits once
+    o2 = ox.FastDiagonalisationOracle(nr, nz, dx, "implicit_diffusion", nu_dt=0.3 * dx * dx)
+    ref2 = np.zeros_like(rhs)
+    o2.solve(ref2, rhs)
+    st = ImplicitEulerDiffusionStepper(0.3 * dx * dx / 2e-3, 2e-3, nr, nz, dx, basis="analytic", split=1)
+    assert st.plan.n_leaves == 2
+    w = rhs.copy()
+    st.step(w, 0.3 * dx * dx / 2e-3)
+    assert_close(w, ref2, RTOL_LINF, "implicit diffusion, split")
+    # the fold kernel itself
+    x = rng.standard_normal((7, 64 + 5))
+    t = torch.from_numpy(x).cuda()
+    _lib.call("axb_fd_fold", 7, 64, ptr(t), t.stride(0), 0, stream_ptr())
+    want = x.copy()
+    want[:, :64] = fd.fold_host(x[:, :64], 64)
+    assert np.array_equal(t.cpu().numpy(), want)
+    _lib.call("axb_fd_fold", 7, 64, ptr(t), t.stride(0), 1, stream_ptr())
+    assert np.allclose(t.cpu().numpy()[:, :64], 2 * x[:, :64], rtol=1e-15, atol=1e-15)
+    assert np.array_equal(t.cpu().numpy()[:, 64:], x[:, 64:])
+
+
 def test_fast_diagonalisation_residual_full_size(K):
     """C2 grid (1024 x 4092 inner, periodic z) and an unbounded 1024 x 2048: the solution must
     satisfy the discrete equation A_r psi + psi A_z^T = r o rhs (checked with the stencils)."""

@@ -74,3 +74,27 @@ def test_analytic_basis_solves_the_operator(nr, nz):
         assert np.max(np.abs(res)) <= 1e-9 * np.max(np.abs(r[:, None] * rhs))
         g = fd.build_factors("stokes", bc, nr, nz, dx, "lapack")
         assert_close(psi, fd.apply_factors_host(g, rhs), 1e-10, "analytic vs lapack " + bc)
+
+
+def test_parity_split_z_transform_equals_dense():
+    """The folded [E_L | O_L | ... | O_1] leaf products reproduce the dense N x N transforms."""
+    rng = np.random.default_rng(5)
+    for kind, bc, nr, nz, kw in (("stokes", BCS[0], 40, 2048, {}), ("implicit_diffusion", None, 24, 1024, {"nu_dt": 1e-7})):
+        dx = 1.0 / nz
+        rhs = rng.standard_normal((nr, nz))
+        dense = fd.build_factors(kind, bc, nr, nz, dx, "analytic", split=0, **kw)
+        ref = fd.apply_factors_host(dense, rhs)
+        assert dense["zsplit"] is None
+        for split in (1, 2, "auto"):
+            f = fd.build_factors(kind, bc, nr, nz, dx, "analytic", split=split, **kw)
+            zs = f["zsplit"]
+            assert zs is not None and sum(zs["leaf_n"]) == nz and zs["leaf_off"][0] == 0
+            assert_close(fd.apply_factors_host(f, rhs), ref, 1e-13, f"{kind} split={split}")
+            assert fd.solve_flops(nr, nz, f) < 0.6 * fd.solve_flops(nr, nz, dense)
+    # fold / unfold are inverse up to the factor 2 carried by the orthonormal bases
+    x = rng.standard_normal((3, 64))
+    y = fd.fold_host(fd.fold_host(x, 64), 64, inverse=True)
+    assert np.allclose(y, 2 * x)
+    # no split for periodic z or odd sizes
+    assert fd.build_factors("stokes", BCS[1], 24, 1024, 1 / 1024, "analytic")["zsplit"] is None
+    assert fd.split_levels("neumann", 1022) == 0 and fd.split_levels("neumann", 16384) == 3

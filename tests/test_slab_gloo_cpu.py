@@ -28,6 +28,10 @@ def _torch_gemm(C, A, B, scale_m=None, scale_n=None, c0=0.0, c1=1.0):
     C.copy_(out)
 
 
+def _torch_fold(x, n, inverse):
+    x.copy_(torch.from_numpy(fd.fold_host(x.numpy(), n, inverse)))
+
+
 def _worker(rank, world, port, nr, nz, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -62,16 +66,21 @@ def _worker(rank, world, port, nr, nz, q):
         assert torch.equal(back, slab), "rows -> slab"
         # ---- distributed solve data flow against the single-process factor application
         dx = 1.0 / nz
-        fac = fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx, "analytic")
-        ref = torch.from_numpy(fd.apply_factors_host(fac, full.numpy()))
-        solver = SlabFdSolver(L, comm, fac, gemm=_torch_gemm)
-        rhs_slab = L.scatter_global(full)
-        psi_slab = torch.zeros_like(rhs_slab)
-        solver.solve(psi_slab, rhs_slab)
-        got = L.owned(psi_slab)
-        want = ref[:, L.z_begin:L.z_begin + L.nzl]
-        err = (got - want).abs().max().item() / ref.abs().max().item()
-        assert err < 1e-12, f"distributed solve differs by {err:.2e}"
+        for split in (0, 1):          # dense and parity-split z transforms
+            fac = fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx, "analytic", split=split)
+            if split:
+                fac["zsplit"] = fd.axial_split_plan("neumann", 1.0, nz, dx, 1)   # force one level on this small grid
+                fac["lam_z"] = torch.from_numpy(fac["zsplit"]["lam_z"])
+                fac["Rz"] = fac["Rzb"] = None
+            ref = torch.from_numpy(fd.apply_factors_host(fac, full.numpy()))
+            solver = SlabFdSolver(L, comm, fac, gemm=_torch_gemm, fold=_torch_fold)
+            rhs_slab = L.scatter_global(full)
+            psi_slab = torch.zeros_like(rhs_slab)
+            solver.solve(psi_slab, rhs_slab)
+            got = L.owned(psi_slab)
+            want = ref[:, L.z_begin:L.z_begin + L.nzl]
+            err = (got - want).abs().max().item() / ref.abs().max().item()
+            assert err < 1e-12, f"distributed solve (split={split}) differs by {err:.2e}"
         # ---- reductions
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         assert comm.allreduce(t.clone(), "max").item() == world
