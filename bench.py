@@ -208,13 +208,20 @@ def run_gpu_arm(args, nr, nz):
     basis = "analytic" if max(nr, nz) >= 1536 else "auto"
     cases = 1
     workload = f"rigid-flow timestep (FlowPastSphere loop body) at {nr}x{nz}"
-    if args.config == "c4":
+    if args.config == "c1":
+        # the reference's own CPU-runnable case (FlowPastSphere CLI default 128x256): launch bound, so the
+        # whole step is replayed as one CUDA graph
+        stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis, use_graph=True)
+        stepper.seed_vorticity()
+        scaling = "weak"
+        workload = f"rigid-flow timestep (FlowPastSphere CLI default) at {nr}x{nz}, one CUDA graph per step"
+    elif args.config == "c4":
         if world > 1:
             from pyaxisymflow_b200.slab import SlabRigidFlowStepper
 
             stepper = SlabRigidFlowStepper(nz, grid_size_r=nr)
         else:
-            stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis)
+            stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis, r_method=args.r_method)
         scaling = "strong"
         # synthetic start: seeded band-limited vorticity blob so every kernel sees
         # non-trivial data from the first step on
@@ -243,7 +250,11 @@ def run_gpu_arm(args, nr, nz):
     probes = []
     e0.record()
     for _ in range(args.steps):
-        probes.append(stepper.step_probed())
+        if args.config == "c1":
+            stepper.step(1)
+            probes.append(None)
+        else:
+            probes.append(stepper.step_probed())
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -259,15 +270,25 @@ def run_gpu_arm(args, nr, nz):
     # ---- roofline of the dominant kernel (k_dgemm): flops of the four GEMMs / their device time
     if probes and probes[0] is not None:
         solve_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
-    else:
+    elif hasattr(stepper, "solve_probe"):
         solve_ms = stepper.solve_probe()
+    else:
+        sol = stepper.psi.clone()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stepper.solver.solve(sol, stepper.vorticity)
+        a.record()
+        for _ in range(5):
+            stepper.solver.solve(sol, stepper.vorticity)
+        b.record()
+        torch.cuda.synchronize()
+        solve_ms = a.elapsed_time(b) / 5
     solves_per_step = getattr(stepper, "cases", 1)
     flops = stepper.solve_flops()
     achieved = flops / (solve_ms * 1e-3) / 1e12
 
     # ---- e2e: host-resident caller, H2D of the step's inputs + D2H of its result inside the timing
     e2e = None
-    if world == 1 and args.config == "c4":
+    if world == 1 and args.config in ("c4", "c1"):
         hw = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
         hc = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
         ho = torch.empty((nr, nz), dtype=torch.float64).pin_memory()
@@ -294,10 +315,17 @@ def run_gpu_arm(args, nr, nz):
         except OSError:
             mp = {}
         cpu = None
-        if world == 1 and not args.no_cpu and args.config == "c4":
+        if world == 1 and not args.no_cpu and args.config in ("c4", "c1"):
             secs, sample = cpu_step_seconds(nr, nz)
             cpu = {"value": nr * nz / secs, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": sample}
+        traffic = None
+        try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+            if world == 1 and tj.get("grid") == [nr, nz]:
+                traffic = tj["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
@@ -308,7 +336,7 @@ def run_gpu_arm(args, nr, nz):
                        "l2": "fields (%.0f MiB each) exceed the 126 MB L2; no flush needed" % (nr * nz * 8 / 2 ** 20),
                        "basis": stepper.solver_basis()},
             "roofline": {"bound": "tensor", "kernel": stepper.solve_kernel_note(), "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no "
                                         "FP64 entry)",
                          "solve_ms": solve_ms, "solve_share_of_step": solves_per_step * solve_ms / ms_per_step,
@@ -398,15 +426,18 @@ def main():
     ap.add_argument("--nz", type=int, default=None, help="grid_size_z (default: the configuration's own)")
     ap.add_argument("--nr", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--config", default="c4", choices=["c4", "c2", "c3", "c5"],
+    ap.add_argument("--config", default="c4", choices=["c4", "c1", "c2", "c3", "c5"],
                     help="c4 (default): 4096x16384 rigid flow, the configuration the metric is quoted on; "
                          "c2: periodic 1024x4096; c3: soft sphere 2048x8192; c5: particle ensemble 1024x2048")
     ap.add_argument("--cases", type=int, default=8, help="ensemble members per GPU (c5)")
+    ap.add_argument("--r-method", default="eigen", choices=["eigen", "tridiagonal"],
+                    help="r direction of the solve: eigen-decomposition GEMMs (the reference's algorithm, default) "
+                         "or a batched tridiagonal solve per z-mode (single GPU, c4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    defaults = {"c4": (4096, 16384), "c2": (1024, 4096), "c3": (2048, 8192), "c5": (1024, 2048)}
+    defaults = {"c4": (4096, 16384), "c1": (128, 256), "c2": (1024, 4096), "c3": (2048, 8192), "c5": (1024, 2048)}
     nz = args.nz if args.nz is not None else defaults[args.config][1]
-    nr = args.nr if args.nr is not None else (nz // 4 if args.config != "c5" else nz // 2)
+    nr = args.nr if args.nr is not None else (nz // 4 if args.config not in ("c5", "c1") else nz // 2)
     if args.impl == "reference":
         run_reference_arm(args, nr, nz)
     else:

@@ -257,11 +257,27 @@ typedef struct axb_fd_plan {
   int32_t leaf_n[AXB_FD_MAX_LEAVES], leaf_off[AXB_FD_MAX_LEAVES], fold_len[AXB_FD_MAX_LEAVES];
   const double* leaf_fwd[AXB_FD_MAX_LEAVES];
   const double* leaf_bwd[AXB_FD_MAX_LEAVES];
+  /* Optional direct r solve (r_tridiagonal != 0): the r operator A_r is tridiagonal, so after the
+   * forward z transform every z-mode k is an independent tridiagonal system
+   * (c0 I + c1 (A_r + lam_z[k] I)) x = rhs_k, solved by a batched Thomas sweep instead of the two
+   * r-direction GEMMs (Lr / Lrb / lam_r are then unused and may be NULL).  r_sub / r_sup have nr-1
+   * entries, r_diag nr; r_scale (nr entries or NULL) multiplies the right-hand side rows first (the
+   * r o rhs of the Stokes flavour).  Same solution as the eigen-decomposition to rounding. */
+  int32_t r_tridiagonal;
+  const double *r_sub, *r_diag, *r_sup, *r_scale;
 } axb_fd_plan_t;
 /* in-place parity fold (inverse = 0: y[j] = x[j] + x[n-1-j], y[n/2+j] = x[j] - x[n-1-j]) or unfold
  * (inverse = 1: x[j] = y[j] + y[n/2+j], x[n-1-j] = y[j] - y[n/2+j]) of the first n columns of every
  * row of X (rows x >= n, pitch ld); n must be a multiple of 4. */
 int axb_fd_fold(int rows, int n, double* X, int64_t ld, int inverse, axb_stream_t s);
+/* same, out of place: the first n columns of src rows are folded into dst (src == dst allowed) */
+int axb_fd_fold2(int rows, int n, const double* src, int64_t ld_src, double* dst, int64_t ld_dst, int inverse,
+                 axb_stream_t s);
+/* batched Thomas solve down the rows: for every column k < nz of X (nr x nz, pitch ld), in place,
+ * (c0 I + c1 (tridiag(sub, diag, sup) + lam[k] I)) x = X[:, k] * scale.  scratch: nr*nz doubles. */
+int axb_tridiag_solve_columns(int nr, int nz, double* X, int64_t ld, const double* sub, const double* diag,
+                              const double* sup, const double* lam, const double* scale, double c0, double c1,
+                              double* scratch, axb_stream_t s);
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s);
 /* Plain row-major FP64 GEMM C = A*B (+ optional spectral scaling), the building block above:

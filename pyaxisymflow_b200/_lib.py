@@ -30,7 +30,9 @@ class AxbFdPlan(Structure):
                 ("c0", c_double), ("c1", c_double), ("work", c_void_p),
                 ("n_leaves", c_int32), ("n_folds", c_int32),
                 ("leaf_n", c_int32 * 8), ("leaf_off", c_int32 * 8), ("fold_len", c_int32 * 8),
-                ("leaf_fwd", c_void_p * 8), ("leaf_bwd", c_void_p * 8)]
+                ("leaf_fwd", c_void_p * 8), ("leaf_bwd", c_void_p * 8),
+                ("r_tridiagonal", c_int32),
+                ("r_sub", c_void_p), ("r_diag", c_void_p), ("r_sup", c_void_p), ("r_scale", c_void_p)]
 
 
 _G = POINTER(AxbGrid)
@@ -83,6 +85,8 @@ _SIGNATURES = {
     "axb_dgemm": [_I, _I, _I, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _D, _D, _S],
     "axb_dgemm_set_path": [_I],
     "axb_fd_fold": [_I, _I, _P, c_int64, _I, _S],
+    "axb_fd_fold2": [_I, _I, _P, c_int64, _P, c_int64, _I, _S],
+    "axb_tridiag_solve_columns": [_I, _I, _P, c_int64, _P, _P, _P, _P, _P, _D, _D, _P, _S],
     "axb_halo_pack": [_G, _P, _P, _P, _I, _S],
     "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],
     "axb_slab_to_blocks": [_I, _I, c_int64, _I, _P, _P, _S],

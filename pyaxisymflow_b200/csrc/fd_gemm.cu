@@ -497,15 +497,16 @@ int launch_dgemm(int M, int N, int K, const double* A, long long lda, const doub
 
 // in-place parity fold / unfold of the first n columns: one thread owns the index quadruple
 // {j, n-1-j, j', n-1-j'} with j' = n/2-1-j, which is closed under the permutation
-__global__ void k_fd_fold(int rows, int n, double* __restrict__ X, long long ld, int inverse) {
+__global__ void k_fd_fold(int rows, int n, const double* src, long long ld_src, double* X, long long ld, int inverse) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   const int h = n >> 1;
   if (j >= (n >> 2)) return;
   double* row = X + (long long)m * ld;
+  const double* in = src + (long long)m * ld_src;
   const int jp = h - 1 - j;
-  const double a0 = row[j], a1 = row[h + jp];      // pair j :  (j, n-1-j)   [n-1-j  = h + jp]
-  const double b0 = row[jp], b1 = row[h + j];      // pair j':  (jp, n-1-jp) [n-1-jp = h + j ]
+  const double a0 = in[j], a1 = in[h + jp];        // pair j :  (j, n-1-j)   [n-1-j  = h + jp]
+  const double b0 = in[jp], b1 = in[h + j];        // pair j':  (jp, n-1-jp) [n-1-jp = h + j ]
   if (!inverse) {
     row[j] = a0 + a1; row[h + j] = a0 - a1;
     row[jp] = b0 + b1; row[h + jp] = b0 - b1;
@@ -516,9 +517,75 @@ __global__ void k_fd_fold(int rows, int n, double* __restrict__ X, long long ld,
   }
 }
 
-int launch_fold(int rows, int n, double* X, long long ld, int inverse, cudaStream_t s) {
-  if (rows < 1 || n < 4 || (n & 3) || !X || ld < n) return AXB_EINVAL;
-  k_fd_fold<<<dim3(((n >> 2) + 127) / 128, rows), 128, 0, s>>>(rows, n, X, ld, inverse);
+int launch_fold(int rows, int n, const double* src, long long ld_src, double* X, long long ld, int inverse,
+                cudaStream_t s) {
+  if (rows < 1 || n < 4 || (n & 3) || !X || !src || ld < n || ld_src < n) return AXB_EINVAL;
+  k_fd_fold<<<dim3(((n >> 2) + 127) / 128, rows), 128, 0, s>>>(rows, n, src, ld_src, X, ld, inverse);
+  AXB_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+// plain strided row copy (used when the r solve is direct and no fold level exists)
+__global__ void k_copy_rows(int n, const double* __restrict__ src, long long ld_src, double* __restrict__ dst,
+                            long long ld_dst) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[(long long)blockIdx.y * ld_dst + k] = src[(long long)blockIdx.y * ld_src + k];
+}
+
+// Batched Thomas algorithm, one thread per column (z-mode); rows are visited in order, so the
+// accesses of a warp are coalesced and the next PF rows of the right-hand side are prefetched.
+// Forward sweep stores c' in `cp` and d' in X, backward sweep overwrites X with the solution.
+constexpr int TPF = 8;
+__global__ void __launch_bounds__(128)
+    k_thomas(int nr, int nz, double* __restrict__ X, long long ld, const double* __restrict__ sub,
+             const double* __restrict__ diag, const double* __restrict__ sup, const double* __restrict__ lam,
+             const double* __restrict__ scale, double c0, double c1, double* __restrict__ cp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nz) return;
+  const double lk = lam[k];
+  double* x = X + k;
+  double* c = cp + k;
+  double cprev = 0.0, dprev = 0.0;
+  for (int m0 = 0; m0 < nr; m0 += TPF) {
+    double d[TPF];
+#pragma unroll
+    for (int u = 0; u < TPF; ++u)
+      if (m0 + u < nr) d[u] = x[(long long)(m0 + u) * ld];
+#pragma unroll
+    for (int u = 0; u < TPF; ++u) {
+      const int m = m0 + u;
+      if (m >= nr) break;
+      const double b = c0 + c1 * (diag[m] + lk);
+      const double a = (m > 0) ? c1 * sub[m - 1] : 0.0;
+      const double cu = (m < nr - 1) ? c1 * sup[m] : 0.0;
+      const double rhs = scale ? d[u] * scale[m] : d[u];
+      const double den = b - a * cprev;
+      cprev = cu / den;
+      dprev = (rhs - a * dprev) / den;
+      c[(long long)m * nz] = cprev;
+      x[(long long)m * ld] = dprev;
+    }
+  }
+  double xn = 0.0;
+  for (int m0 = nr - 1; m0 >= 0; m0 -= TPF) {
+    double d[TPF], cc[TPF];
+#pragma unroll
+    for (int u = 0; u < TPF; ++u)
+      if (m0 - u >= 0) { d[u] = x[(long long)(m0 - u) * ld]; cc[u] = c[(long long)(m0 - u) * nz]; }
+#pragma unroll
+    for (int u = 0; u < TPF; ++u) {
+      const int m = m0 - u;
+      if (m < 0) break;
+      xn = d[u] - cc[u] * xn;          // c'_{nr-1} = 0, so the first step is x = d'
+      x[(long long)m * ld] = xn;
+    }
+  }
+}
+
+int launch_thomas(int nr, int nz, double* X, long long ld, const double* sub, const double* diag, const double* sup,
+                  const double* lam, const double* scale, double c0, double c1, double* scratch, cudaStream_t s) {
+  if (nr < 2 || nz < 1 || !X || !sub || !diag || !sup || !lam || !scratch || ld < nz) return AXB_EINVAL;
+  k_thomas<<<(nz + 127) / 128, 128, 0, s>>>(nr, nz, X, ld, sub, diag, sup, lam, scale, c0, c1, scratch);
   AXB_LAUNCHED();
   return (int)cudaGetLastError();
 }
@@ -528,7 +595,16 @@ int launch_fold(int rows, int n, double* X, long long ld, int inverse, cudaStrea
 extern "C" {
 
 int axb_fd_fold(int rows, int n, double* X, int64_t ld, int inverse, axb_stream_t s) {
-  return launch_fold(rows, n, X, ld, inverse, s);
+  return launch_fold(rows, n, X, ld, X, ld, inverse, s);
+}
+int axb_fd_fold2(int rows, int n, const double* src, int64_t ld_src, double* dst, int64_t ld_dst, int inverse,
+                 axb_stream_t s) {
+  return launch_fold(rows, n, src, ld_src, dst, ld_dst, inverse, s);
+}
+int axb_tridiag_solve_columns(int nr, int nz, double* X, int64_t ld, const double* sub, const double* diag,
+                              const double* sup, const double* lam, const double* scale, double c0, double c1,
+                              double* scratch, axb_stream_t s) {
+  return launch_thomas(nr, nz, X, ld, sub, diag, sup, lam, scale, c0, c1, scratch, s);
 }
 
 int axb_dgemm_set_path(int force_ldgsts) {
@@ -544,11 +620,47 @@ int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B
 
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s) {
-  if (!p || !sol || !rhs || !p->Lr || !p->Lrb || !p->lam_r || !p->lam_z || !p->work) return AXB_EINVAL;
+  if (!p || !sol || !rhs || !p->lam_z || !p->work) return AXB_EINVAL;
   const int nr = p->nr, nz = p->nz;
   double* w0 = p->work;
   double* w1 = p->work + (long long)nr * nz;
   int rc;
+  if (p->r_tridiagonal) {
+    // z transform (parity-split leaves or dense) -> batched tridiagonal r solve per z-mode -> back
+    if (!p->r_sub || !p->r_diag || !p->r_sup) return AXB_EINVAL;
+    if (p->n_leaves > AXB_FD_MAX_LEAVES || p->n_folds > AXB_FD_MAX_LEAVES) return AXB_EINVAL;
+    if (p->n_leaves > 0) {
+      for (int f = 0; f < p->n_folds; ++f) {      // first level folds rhs -> w0, deeper levels in place
+        rc = launch_fold(nr, p->fold_len[f], f == 0 ? rhs : w0, f == 0 ? ld_rhs : nz, w0, nz, 0, s);
+        if (rc) return rc;
+      }
+      for (int i = 0; i < p->n_leaves; ++i) {
+        const int n = p->leaf_n[i], off = p->leaf_off[i];
+        rc = launch_dgemm(nr, n, n, w0 + off, nz, p->leaf_fwd[i], n, w1 + off, nz, nullptr, nullptr, 0, 0, s);
+        if (rc) return rc;
+      }
+    } else {
+      if (!p->Rz || !p->Rzb) return AXB_EINVAL;
+      rc = launch_dgemm(nr, nz, nz, rhs, ld_rhs, p->Rz, nz, w1, nz, nullptr, nullptr, 0, 0, s);
+      if (rc) return rc;
+    }
+    rc = launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
+    if (rc) return rc;
+    if (p->n_leaves > 0) {
+      for (int i = 0; i < p->n_leaves; ++i) {
+        const int n = p->leaf_n[i], off = p->leaf_off[i];
+        rc = launch_dgemm(nr, n, n, w1 + off, nz, p->leaf_bwd[i], n, w0 + off, nz, nullptr, nullptr, 0, 0, s);
+        if (rc) return rc;
+      }
+      for (int f = p->n_folds - 1; f >= 0; --f) {  // the last unfold (full length) lands in sol
+        rc = launch_fold(nr, p->fold_len[f], w0, nz, f == 0 ? sol : w0, f == 0 ? ld_sol : nz, 1, s);
+        if (rc) return rc;
+      }
+      return AXB_OK;
+    }
+    return launch_dgemm(nr, nz, nz, w1, nz, p->Rzb, nz, sol, ld_sol, nullptr, nullptr, 0, 0, s);
+  }
+  if (!p->Lr || !p->Lrb || !p->lam_r) return AXB_EINVAL;
   // T1 = Lr * rhs                       (nr x nr) (nr x nz)
   rc = launch_dgemm(nr, nz, nr, p->Lr, nr, rhs, ld_rhs, w0, nz, nullptr, nullptr, 0, 0, s);
   if (rc) return rc;
@@ -556,7 +668,7 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
     // parity-split z transforms (see include/axisym_b200.h)
     if (p->n_leaves > AXB_FD_MAX_LEAVES || p->n_folds > AXB_FD_MAX_LEAVES) return AXB_EINVAL;
     for (int f = 0; f < p->n_folds; ++f) {
-      rc = launch_fold(nr, p->fold_len[f], w0, nz, 0, s);
+      rc = launch_fold(nr, p->fold_len[f], w0, nz, w0, nz, 0, s);
       if (rc) return rc;
     }
     for (int i = 0; i < p->n_leaves; ++i) {
@@ -571,7 +683,7 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
       if (rc) return rc;
     }
     for (int f = p->n_folds - 1; f >= 0; --f) {
-      rc = launch_fold(nr, p->fold_len[f], w0, nz, 1, s);
+      rc = launch_fold(nr, p->fold_len[f], w0, nz, w0, nz, 1, s);
       if (rc) return rc;
     }
     return launch_dgemm(nr, nz, nr, p->Lrb, nr, w0, nz, sol, ld_sol, nullptr, nullptr, 0, 0, s);

@@ -111,9 +111,21 @@ def _eig_sorted(m):
     return lam[o], V[:, o]
 
 
+class _ComplexBasis(Exception):
+    """la.eig returned complex conjugate pairs for a (numerically) repeated real eigenvalue"""
+
+
+def _real_or_raise(lam, V):
+    if np.iscomplexobj(lam) or np.iscomplexobj(V):
+        if np.max(np.abs(np.imag(lam))) > 0 or np.max(np.abs(np.imag(V))) > 0:
+            raise _ComplexBasis()
+        lam, V = np.real(lam), np.real(V)
+    return lam, V
+
+
 def radial_basis_lapack(sub, diag, sup):
-    lam, V = _eig_sorted(dense_from_tridiagonal(sub, diag, sup))
-    return np.real(lam), np.real(V), np.real(np.linalg.inv(V))
+    lam, V = _real_or_raise(*_eig_sorted(dense_from_tridiagonal(sub, diag, sup)))
+    return lam, V, np.linalg.inv(V)
 
 
 def _sym_tridiag_eig(sub, diag, sup):
@@ -167,9 +179,8 @@ def radial_basis_analytic(sub, diag, sup):
 
 
 def axial_basis_lapack(family, sign, nz, dx):
-    lam, V = _eig_sorted(dense_axial(family, sign, nz, dx))
-    V = np.real(V)
-    return np.real(lam), V, np.real(np.linalg.inv(V))
+    lam, V = _real_or_raise(*_eig_sorted(dense_axial(family, sign, nz, dx)))
+    return lam, V, np.linalg.inv(V)
 
 
 def axial_basis_analytic(family, sign, nz, dx, device="cpu"):
@@ -294,7 +305,31 @@ def fold_host(x, n, inverse=False):
     return y
 
 
-def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="cpu", split="auto"):
+def thomas_host(x, sub, diag, sup, lam, scale, c0, c1):
+    """NumPy restatement of axb_tridiag_solve_columns (all columns at once; CPU tests only)"""
+    nr = x.shape[0]
+    cp = np.zeros_like(x)
+    d = np.array(x, dtype=np.float64)
+    cprev = np.zeros(x.shape[1])
+    dprev = np.zeros(x.shape[1])
+    for m in range(nr):
+        b = c0 + c1 * (diag[m] + lam)
+        a = c1 * sub[m - 1] if m > 0 else 0.0
+        cu = c1 * sup[m] if m < nr - 1 else 0.0
+        rhs = d[m] * (scale[m] if scale is not None else 1.0)
+        den = b - a * cprev
+        cprev = cu / den
+        dprev = (rhs - a * dprev) / den
+        cp[m], d[m] = cprev, dprev
+    xn = np.zeros(x.shape[1])
+    for m in range(nr - 1, -1, -1):
+        xn = d[m] - cp[m] * xn
+        d[m] = xn
+    return d
+
+
+def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="cpu", split="auto",
+                  r_method="eigen"):
     """Factor set of the solve  sol = Lrb (((Lr rhs) Rz) o 1/(c0 + c1 (lam_z (+) lam_r))) Rzb  as
     float64 torch tensors on ``device`` (see include/axisym_b200.h, axb_fd_plan_t)."""
     if basis == "auto":
@@ -303,12 +338,23 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
     family, sign = axial_kind(kind, bc_type)
     zsplit = None
     if basis == "lapack":
-        lam_r, Vr, Vri = radial_basis_lapack(sub, diag, sup)
-        lam_z, Vz, Vzi = axial_basis_lapack(family, sign, nz, dx)
-        Rz = torch.from_numpy(np.ascontiguousarray(Vzi.T)).to(device)
-        Rzb = torch.from_numpy(np.ascontiguousarray(Vz.T)).to(device)
+        try:
+            lam_r, Vr, Vri = radial_basis_lapack(sub, diag, sup)
+            lam_z, Vz, Vzi = axial_basis_lapack(family, sign, nz, dx)
+            Rz = torch.from_numpy(np.ascontiguousarray(Vzi.T)).to(device)
+            Rzb = torch.from_numpy(np.ascontiguousarray(Vz.T)).to(device)
+        except _ComplexBasis:
+            # degenerate periodic pairs came back as complex conjugates (the reference then carries
+            # complex arrays and drops the imaginary part on assignment); the solution operator is
+            # basis independent, so use the real closed-form basis instead
+            basis = "analytic"
+    if basis == "lapack":
+        pass
     elif basis == "analytic":
-        lam_r, Vr, Vri = radial_basis_analytic(sub, diag, sup)
+        if r_method == "tridiagonal":
+            lam_r = Vr = Vri = None       # the r direction is solved directly, no eigen-decomposition
+        else:
+            lam_r, Vr, Vri = radial_basis_analytic(sub, diag, sup)
         levels = split_levels(family, nz, split)
         if levels > 0:
             zsplit = axial_split_plan(family, sign, nz, dx, levels, device=device)
@@ -319,14 +365,20 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
             Rzb = Vz_t.t().contiguous()
     else:
         raise ValueError(f"unknown basis {basis!r}")
-    Lr = Vri * r[None, :] if kind == "stokes" else Vri   # fold  r o rhs  into the first factor
+    def dev(a):
+        return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+    if r_method == "tridiagonal" and basis != "analytic":
+        raise ValueError("r_method='tridiagonal' needs basis='analytic'")
+    tri = None
+    if r_method == "tridiagonal":
+        tri = {"sub": dev(sub), "diag": dev(diag), "sup": dev(sup), "scale": dev(r) if kind == "stokes" else None}
+        Lr = None
+    else:
+        Lr = Vri * r[None, :] if kind == "stokes" else Vri   # fold  r o rhs  into the first factor
     f = {
-        "Lr": torch.from_numpy(np.ascontiguousarray(Lr)).to(device),
-        "Lrb": torch.from_numpy(np.ascontiguousarray(Vr)).to(device),
-        "Rz": Rz, "Rzb": Rzb,
-        "lam_r": torch.from_numpy(np.ascontiguousarray(lam_r)).to(device),
-        "lam_z": torch.from_numpy(np.ascontiguousarray(lam_z)).to(device),
-        "c0": 0.0, "c1": 1.0, "basis": basis, "zsplit": zsplit,
+        "Lr": dev(Lr), "Lrb": dev(Vr), "Rz": Rz, "Rzb": Rzb, "lam_r": dev(lam_r), "lam_z": dev(lam_z),
+        "c0": 0.0, "c1": 1.0, "basis": basis, "zsplit": zsplit, "tri": tri, "r_method": r_method,
     }
     if kind == "implicit_diffusion":
         f["c0"], f["c1"] = 1.0, -float(nu_dt)
@@ -336,8 +388,27 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
 def apply_factors_host(f, rhs):
     """NumPy evaluation of the factorised solve (used only by the CPU tests of the set-up)."""
     g = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in f.items()}
-    scale = 1.0 / (g["c0"] + g["c1"] * (g["lam_z"][None, :] + g["lam_r"][:, None]))
     zs = f.get("zsplit")
+    if f.get("tri") is not None:
+        tri = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in f["tri"].items()}
+        t = np.array(rhs, dtype=np.float64)
+        if zs is None:
+            spec = t @ g["Rz"]
+        else:
+            for n in zs["fold_len"]:
+                t = fold_host(t, n)
+            spec = np.empty_like(t)
+            for n, off, F in zip(zs["leaf_n"], zs["leaf_off"], zs["fwd"]):
+                spec[:, off:off + n] = t[:, off:off + n] @ F.cpu().numpy()
+        spec = thomas_host(spec, tri["sub"], tri["diag"], tri["sup"], g["lam_z"], tri["scale"], g["c0"], g["c1"])
+        if zs is None:
+            return spec @ g["Rzb"]
+        for n, off, B in zip(zs["leaf_n"], zs["leaf_off"], zs["bwd"]):
+            t[:, off:off + n] = spec[:, off:off + n] @ B.cpu().numpy()
+        for n in reversed(zs["fold_len"]):
+            t = fold_host(t, n, inverse=True)
+        return t
+    scale = 1.0 / (g["c0"] + g["c1"] * (g["lam_z"][None, :] + g["lam_r"][:, None]))
     if zs is None:
         spec = ((g["Lr"] @ rhs) @ g["Rz"]) * scale
         return g["Lrb"] @ (spec @ g["Rzb"])
@@ -362,10 +433,16 @@ def make_plan(nr, nz, f, work):
     """axb_fd_plan_t over a factor set living on the GPU"""
     p = AxbFdPlan()
     p.nr, p.nz = nr, nz
-    p.Lr, p.Lrb = f["Lr"].data_ptr(), f["Lrb"].data_ptr()
-    p.Rz = f["Rz"].data_ptr() if f["Rz"] is not None else None
-    p.Rzb = f["Rzb"].data_ptr() if f["Rzb"] is not None else None
-    p.lam_r, p.lam_z = f["lam_r"].data_ptr(), f["lam_z"].data_ptr()
+    opt = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    p.Lr, p.Lrb = opt(f["Lr"]), opt(f["Lrb"])
+    p.Rz, p.Rzb = opt(f["Rz"]), opt(f["Rzb"])
+    p.lam_r, p.lam_z = opt(f["lam_r"]), f["lam_z"].data_ptr()
+    tri = f.get("tri")
+    p.r_tridiagonal = 0
+    if tri is not None:
+        p.r_tridiagonal = 1
+        p.r_sub, p.r_diag, p.r_sup = tri["sub"].data_ptr(), tri["diag"].data_ptr(), tri["sup"].data_ptr()
+        p.r_scale = opt(tri["scale"])
     p.c0, p.c1, p.work = f["c0"], f["c1"], work.data_ptr()
     zs = f.get("zsplit")
     p.n_leaves = p.n_folds = 0
@@ -383,13 +460,16 @@ def solve_flops(nr, nz, f):
     """floating-point operations one solve executes with this factor set"""
     zs = f.get("zsplit")
     z = 2.0 * nr * nz * nz if zs is None else sum(2.0 * nr * n * n for n in zs["leaf_n"])
+    if f.get("tri") is not None:
+        return 2 * z + 10.0 * nr * nz          # GEMM flops + the Thomas sweeps
     return 2 * (2.0 * nr * nr * nz) + 2 * z
 
 
 class _FdBase:
     kind = None
 
-    def _setup(self, grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, nu_dt=None, split="auto"):
+    def _setup(self, grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, nu_dt=None, split="auto",
+               r_method="eigen"):
         if real_dtype != np.float64:
             raise TypeError("libaxisym_b200 computes in float64 only")
         if not torch.cuda.is_available():
@@ -397,8 +477,10 @@ class _FdBase:
         self.dx, self.grid_size_r, self.grid_size_z = dx, grid_size_r, grid_size_z
         self.real_dtype, self.bc_type = real_dtype, bc_type
         self.radial_coord = np.linspace(dx / 2, grid_size_r * dx - dx / 2, grid_size_r).reshape(grid_size_r, 1)
+        if r_method == "tridiagonal" and basis == "auto":
+            basis = "analytic"
         self.factors = build_factors(self.kind, bc_type, grid_size_r, grid_size_z, dx, basis, nu_dt, device="cuda",
-                                     split=split)
+                                     split=split, r_method=r_method)
         self.basis = self.factors["basis"]
         # spectral buffer of the reference (FastDiagonalisationStokesSolver.py:38-39) x 2
         self.work = torch.empty(2 * grid_size_r * grid_size_z, dtype=torch.float64, device="cuda")
@@ -429,8 +511,8 @@ class FastDiagonalisationStokesSolver(_FdBase):
     kind = "stokes"
 
     def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto",
-                 split="auto"):
-        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, split=split)
+                 split="auto", r_method="eigen"):
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, split=split, r_method=r_method)
 
     def solve(self, solution_field, rhs_field):
         self._solve(solution_field, rhs_field)
@@ -440,10 +522,12 @@ class FastDiagonalisationStokesSolver(_FdBase):
 
     def kernel_note(self):
         zs = self.factors.get("zsplit")
+        tri = self.factors.get("tri") is not None
+        rpart = "batched tridiagonal r solve" if tri else "2 r-transforms"
         if zs is None:
-            return "k_dgemm_tma (4 launches per solve: 2 r-transforms + 2 dense z-transforms)"
+            return f"k_dgemm_tma ({2 if tri else 4} launches per solve: {rpart} + 2 dense z-transforms)"
         n = len(zs["leaf_n"])
-        return (f"k_dgemm_tma ({2 + 2 * n} launches per solve: 2 r-transforms + 2x{n} parity-split z leaves "
+        return (f"k_dgemm_tma ({(0 if tri else 2) + 2 * n} launches per solve: {rpart} + 2x{n} parity-split z leaves "
                 f"{zs['leaf_n']}; flops = executed, {self.flops() / (4.0 * self.grid_size_r * self.grid_size_z * (self.grid_size_r + self.grid_size_z)):.3f} of the dense count)")
 
 
@@ -463,10 +547,11 @@ class ImplicitEulerDiffusionStepper(_FdBase):
     kind = "implicit_diffusion"
 
     def __init__(self, time_step, kinematic_viscosity, grid_size_r, grid_size_z, dx, real_dtype=np.float64,
-                 basis="auto", split="auto"):
+                 basis="auto", split="auto", r_method="eigen"):
         self.time_step = time_step
         self.nu_times_dt = self.time_step * kinematic_viscosity
-        self._setup(grid_size_r, grid_size_z, dx, real_dtype, None, basis, nu_dt=self.nu_times_dt, split=split)
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, None, basis, nu_dt=self.nu_times_dt, split=split,
+                    r_method=r_method)
 
     def step(self, vorticity_field, dt):
         if dt != self.time_step:

@@ -501,6 +501,59 @@ def test_fast_diagonalisation_parity_split(K, nr, nz, split):
     assert np.array_equal(t.cpu().numpy()[:, 64:], x[:, 64:])
 
 
+@pytest.mark.parametrize("nr,nz,bc", [(96, 160, "homogenous_neumann_along_z_and_r"),
+                                      (64, 256, "homogenous_neumann_along_z_and_r"),
+                                      (48, 124, "homogenous_neumann_along_r_and_periodic_along_z"),
+                                      (37, 90, "homogenous_neumann_along_z_and_r")])
+def test_fast_diagonalisation_tridiagonal_r(K, nr, nz, bc):
+    """optional direct r solve (batched Thomas per z-mode) against the oracle's eigen-decomposition"""
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver, ImplicitEulerDiffusionStepper
+
+    rng = np.random.default_rng(14)
+    dx = 1.0 / nz
+    rhs = _rand(rng, nr, nz, 5.0)
+    ref = fd.apply_factors_host(fd.build_factors("stokes", bc, nr, nz, dx, "analytic", split=0), rhs)
+    for split in (0, "auto", 2):
+        s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, r_method="tridiagonal", split=split)
+        assert s.plan.r_tridiagonal == 1 and s.factors["Lr"] is None
+        sol = np.zeros_like(rhs)
+        s.solve(sol, rhs)
+        assert_close(sol, ref, RTOL_LINF, f"tridiagonal r, split {split}, {bc}")
+    o2 = ox.FastDiagonalisationOracle(nr, nz, dx, "implicit_diffusion", nu_dt=0.3 * dx * dx)
+    ref2 = np.zeros_like(rhs)
+    o2.solve(ref2, rhs)
+    st = ImplicitEulerDiffusionStepper(0.3 * dx * dx / 2e-3, 2e-3, nr, nz, dx, r_method="tridiagonal")
+    w = rhs.copy()
+    st.step(w, 0.3 * dx * dx / 2e-3)
+    assert_close(w, ref2, RTOL_LINF, "implicit diffusion, tridiagonal r")
+    # the batched Thomas kernel on its own against the NumPy restatement
+    sub, diag, sup, r = fd.radial_tridiagonal("stokes", bc, nr, dx)
+    lam = rng.uniform(0.0, 5.0, nz)
+    x = rng.standard_normal((nr, nz))
+    want = fd.thomas_host(x, sub, diag, sup, lam, r, 0.0, 1.0)
+    tx = torch.from_numpy(x).cuda()
+    dev = [torch.from_numpy(a).cuda() for a in (sub, diag, sup, lam, r)]
+    scratch = torch.empty_like(tx)
+    _lib.call("axb_tridiag_solve_columns", nr, nz, ptr(tx), nz, *(ptr(a) for a in dev), 0.0, 1.0, ptr(scratch),
+              stream_ptr())
+    assert_close(tx.cpu().numpy(), want, 1e-13, "batched Thomas")
+
+
+def test_rigid_flow_stepper_tridiagonal_r(K):
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    nz, steps = 128, 12
+    w, psi, uz, t, cds = _oracle_rigid_loop(nz, steps)
+    s = RigidFlowStepper(nz, r_method="tridiagonal")
+    s.step(steps)
+    assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (tridiagonal r solve)")
+    assert_close(s.psi.cpu().numpy(), psi, 1e-9, "psi (tridiagonal r solve)")
+
+
 def test_fast_diagonalisation_residual_full_size(K):
     """C2 grid (1024 x 4092 inner, periodic z) and an unbounded 1024 x 2048: the solution must
     satisfy the discrete equation A_r psi + psi A_z^T = r o rhs (checked with the stencils)."""
