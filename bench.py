@@ -205,7 +205,7 @@ def run_gpu_arm(args, nr, nz):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    basis = "analytic" if max(nr, nz) >= 1536 else "auto"
+    basis = "auto"
     cases = 1
     workload = f"rigid-flow timestep (FlowPastSphere loop body) at {nr}x{nz}"
     if args.config == "c1":
@@ -221,7 +221,8 @@ def run_gpu_arm(args, nr, nz):
 
             stepper = SlabRigidFlowStepper(nz, grid_size_r=nr)
         else:
-            stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis, r_method=args.r_method)
+            stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis, r_method=args.r_method,
+                                       z_method=args.z_method)
         scaling = "strong"
         # synthetic start: seeded band-limited vorticity blob so every kernel sees
         # non-trivial data from the first step on
@@ -430,9 +431,12 @@ def main():
                     help="c4 (default): 4096x16384 rigid flow, the configuration the metric is quoted on; "
                          "c2: periodic 1024x4096; c3: soft sphere 2048x8192; c5: particle ensemble 1024x2048")
     ap.add_argument("--cases", type=int, default=8, help="ensemble members per GPU (c5)")
-    ap.add_argument("--r-method", default="eigen", choices=["eigen", "tridiagonal"],
-                    help="r direction of the solve: eigen-decomposition GEMMs (the reference's algorithm, default) "
-                         "or a batched tridiagonal solve per z-mode (single GPU, c4)")
+    ap.add_argument("--r-method", default="auto", choices=["auto", "eigen", "tridiagonal"],
+                    help="r direction of the solve: eigen-decomposition GEMMs (the reference's algorithm) or a "
+                         "batched tridiagonal solve per z-mode (auto: tridiagonal on grids too large for la.eig)")
+    ap.add_argument("--z-method", default="auto", choices=["auto", "gemm", "fft"],
+                    help="z transforms of the solve: GEMMs with the eigenvector matrix (parity-split) or "
+                         "shared-memory FFT cosine transforms (auto: fft where available with the tridiagonal r solve)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     defaults = {"c4": (4096, 16384), "c1": (128, 256), "c2": (1024, 4096), "c3": (2048, 8192), "c5": (1024, 2048)}

@@ -265,7 +265,24 @@ typedef struct axb_fd_plan {
    * r o rhs of the Stokes flavour).  Same solution as the eigen-decomposition to rounding. */
   int32_t r_tridiagonal;
   const double *r_sub, *r_diag, *r_sup, *r_scale;
+  /* Optional FFT z transforms (z_fft != 0; needs r_tridiagonal, the Neumann-z family and
+   * nz = 2^p, 64 <= nz <= 16384): the Neumann eigenvectors are cos(pi k (2j+1) / (2 nz)), so the
+   * forward / backward z transforms are a DCT-II / DCT-III of every row, done by axb_dct2_rows /
+   * axb_dct3_rows in one pass over HBM each.  z_tables as described at axb_dct2_rows; lam_z in
+   * natural mode order k = 0..nz-1.  Rz / Rzb / leaves are then unused. */
+  int32_t z_fft;
+  const double* z_tables;
 } axb_fd_plan_t;
+/* Row-wise cosine transforms through a shared-memory FFT (n = 2^p, 64 <= n <= 16384):
+ *   axb_dct2_rows: dst[m, k] = s_k * sum_j src[m, j] cos(pi k (2j+1) / (2n)), s_0 = scale0, s_k = scale
+ *   axb_dct3_rows: dst[m, j] =       sum_k src[m, k] cos(pi k (2j+1) / (2n))
+ * so dct3(dct2(x, 1/n, 2/n)) = x.  tables: 3n/2 + 2 complex numbers (re, im pairs of doubles),
+ *   [exp(-2 pi i k / (n/2)), k < n/2 | exp(-2 pi i k / n), k <= n/2 | exp(-i pi k / (2n)), k <= n/2].
+ * src and dst must not overlap. */
+int axb_dct2_rows(int rows, int n, const double* src, int64_t ld_src, double* dst, int64_t ld_dst,
+                  const double* tables, double scale0, double scale, axb_stream_t s);
+int axb_dct3_rows(int rows, int n, const double* src, int64_t ld_src, double* dst, int64_t ld_dst,
+                  const double* tables, axb_stream_t s);
 /* in-place parity fold (inverse = 0: y[j] = x[j] + x[n-1-j], y[n/2+j] = x[j] - x[n-1-j]) or unfold
  * (inverse = 1: x[j] = y[j] + y[n/2+j], x[n-1-j] = y[j] - y[n/2+j]) of the first n columns of every
  * row of X (rows x >= n, pitch ld); n must be a multiple of 4. */

@@ -25,6 +25,9 @@
 
 #include "axb_common.cuh"
 
+int launch_dct_rows(int inverse, int rows, int N, const double* src, long long ld_src, double* dst, long long ld_dst,
+                    const double* tabs, double scale0, double scale, cudaStream_t st);   // zfft.cu
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
@@ -629,6 +632,15 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
     // z transform (parity-split leaves or dense) -> batched tridiagonal r solve per z-mode -> back
     if (!p->r_sub || !p->r_diag || !p->r_sup) return AXB_EINVAL;
     if (p->n_leaves > AXB_FD_MAX_LEAVES || p->n_folds > AXB_FD_MAX_LEAVES) return AXB_EINVAL;
+    if (p->z_fft) {
+      // DCT-II of every row -> Thomas per z-mode -> DCT-III: three HBM-bound launches
+      if (!p->z_tables || rhs == w1 || sol == w1) return AXB_EINVAL;
+      rc = launch_dct_rows(0, nr, nz, rhs, ld_rhs, w1, nz, p->z_tables, 1.0 / nz, 2.0 / nz, s);
+      if (rc) return rc;
+      rc = launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
+      if (rc) return rc;
+      return launch_dct_rows(1, nr, nz, w1, nz, sol, ld_sol, p->z_tables, 1.0, 1.0, s);
+    }
     if (p->n_leaves > 0) {
       for (int f = 0; f < p->n_folds; ++f) {      // first level folds rhs -> w0, deeper levels in place
         rc = launch_fold(nr, p->fold_len[f], f == 0 ? rhs : w0, f == 0 ? ld_rhs : nz, w0, nz, 0, s);

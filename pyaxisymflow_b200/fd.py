@@ -291,6 +291,24 @@ def axial_split_plan(family, sign, nz, dx, levels, device="cpu"):
     return plan
 
 
+def fft_eligible(family, nz):
+    """the shared-memory FFT transforms cover the Neumann-z family at nz = 2^p, 64 <= nz <= 16384"""
+    return family == "neumann" and 64 <= nz <= 16384 and (nz & (nz - 1)) == 0
+
+
+def dct_tables(nz):
+    """twiddle tables of axb_dct2_rows / axb_dct3_rows as one (3 nz / 2 + 2, 2) float64 array"""
+    M = nz // 2
+    km = np.arange(M)
+    k = np.arange(M + 1)
+    tab = np.concatenate([np.exp(-2j * np.pi * km / M), np.exp(-2j * np.pi * k / nz),
+                          np.exp(-1j * np.pi * k / (2 * nz))])
+    # exact values where cos / sin are known, so the quarter points carry no rounding
+    tab[M // 4 * np.arange(4)] = [1, -1j, -1, 1j]
+    tab[M + M // 2] = -1j
+    return np.ascontiguousarray(np.stack([tab.real, tab.imag], axis=1))
+
+
 def fold_host(x, n, inverse=False):
     """NumPy restatement of axb_fd_fold (CPU tests of the set-up only)"""
     h = n // 2
@@ -329,7 +347,7 @@ def thomas_host(x, sub, diag, sup, lam, scale, c0, c1):
 
 
 def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="cpu", split="auto",
-                  r_method="eigen"):
+                  r_method="eigen", z_method="gemm"):
     """Factor set of the solve  sol = Lrb (((Lr rhs) Rz) o 1/(c0 + c1 (lam_z (+) lam_r))) Rzb  as
     float64 torch tensors on ``device`` (see include/axisym_b200.h, axb_fd_plan_t)."""
     if basis == "auto":
@@ -355,8 +373,15 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
             lam_r = Vr = Vri = None       # the r direction is solved directly, no eigen-decomposition
         else:
             lam_r, Vr, Vri = radial_basis_analytic(sub, diag, sup)
+        if z_method == "auto":
+            z_method = "fft" if (r_method == "tridiagonal" and fft_eligible(family, nz)) else "gemm"
         levels = split_levels(family, nz, split)
-        if levels > 0:
+        if z_method == "fft":
+            if r_method != "tridiagonal" or not fft_eligible(family, nz):
+                raise ValueError("z_method='fft' needs r_method='tridiagonal', the Neumann-z family and "
+                                 "nz = 2^p with 64 <= nz <= 16384")
+            lam_z, Rz, Rzb = axial_natural_eigenvalues(family, sign, nz, dx), None, None
+        elif levels > 0:
             zsplit = axial_split_plan(family, sign, nz, dx, levels, device=device)
             lam_z, Rz, Rzb = zsplit["lam_z"], None, None
         else:
@@ -370,6 +395,13 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
 
     if r_method == "tridiagonal" and basis != "analytic":
         raise ValueError("r_method='tridiagonal' needs basis='analytic'")
+    if z_method == "auto":
+        z_method = "gemm"
+    if z_method not in ("gemm", "fft") or (z_method == "fft" and basis != "analytic"):
+        raise ValueError(f"z_method {z_method!r} is not available with basis {basis!r}")
+    zfft = None
+    if z_method == "fft":
+        zfft = {"tables": dev(dct_tables(nz)), "family": family, "sign": sign, "dx": dx}
     tri = None
     if r_method == "tridiagonal":
         tri = {"sub": dev(sub), "diag": dev(diag), "sup": dev(sup), "scale": dev(r) if kind == "stokes" else None}
@@ -379,6 +411,7 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
     f = {
         "Lr": dev(Lr), "Lrb": dev(Vr), "Rz": Rz, "Rzb": Rzb, "lam_r": dev(lam_r), "lam_z": dev(lam_z),
         "c0": 0.0, "c1": 1.0, "basis": basis, "zsplit": zsplit, "tri": tri, "r_method": r_method,
+        "zfft": zfft, "z_method": z_method,
     }
     if kind == "implicit_diffusion":
         f["c0"], f["c1"] = 1.0, -float(nu_dt)
@@ -392,6 +425,12 @@ def apply_factors_host(f, rhs):
     if f.get("tri") is not None:
         tri = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in f["tri"].items()}
         t = np.array(rhs, dtype=np.float64)
+        if f.get("zfft") is not None:
+            # DCT-II / DCT-III written as products with the orthonormal cosine basis (host check only)
+            zf = f["zfft"]
+            V = axial_natural_block(zf["family"], t.shape[1], t.shape[1], np.arange(t.shape[1])).numpy()
+            spec = thomas_host(t @ V, tri["sub"], tri["diag"], tri["sup"], g["lam_z"], tri["scale"], g["c0"], g["c1"])
+            return spec @ V.T
         if zs is None:
             spec = t @ g["Rz"]
         else:
@@ -444,6 +483,9 @@ def make_plan(nr, nz, f, work):
         p.r_sub, p.r_diag, p.r_sup = tri["sub"].data_ptr(), tri["diag"].data_ptr(), tri["sup"].data_ptr()
         p.r_scale = opt(tri["scale"])
     p.c0, p.c1, p.work = f["c0"], f["c1"], work.data_ptr()
+    p.z_fft = 0
+    if f.get("zfft") is not None:
+        p.z_fft, p.z_tables = 1, f["zfft"]["tables"].data_ptr()
     zs = f.get("zsplit")
     p.n_leaves = p.n_folds = 0
     if zs is not None:
@@ -459,6 +501,8 @@ def make_plan(nr, nz, f, work):
 def solve_flops(nr, nz, f):
     """floating-point operations one solve executes with this factor set"""
     zs = f.get("zsplit")
+    if f.get("zfft") is not None:
+        return 2 * (2.5 * nr * nz * np.log2(nz)) + 10.0 * nr * nz     # two real FFTs per row + Thomas
     z = 2.0 * nr * nz * nz if zs is None else sum(2.0 * nr * n * n for n in zs["leaf_n"])
     if f.get("tri") is not None:
         return 2 * z + 10.0 * nr * nz          # GEMM flops + the Thomas sweeps
@@ -469,7 +513,7 @@ class _FdBase:
     kind = None
 
     def _setup(self, grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, nu_dt=None, split="auto",
-               r_method="eigen"):
+               r_method="auto", z_method="auto"):
         if real_dtype != np.float64:
             raise TypeError("libaxisym_b200 computes in float64 only")
         if not torch.cuda.is_available():
@@ -477,10 +521,17 @@ class _FdBase:
         self.dx, self.grid_size_r, self.grid_size_z = dx, grid_size_r, grid_size_z
         self.real_dtype, self.bc_type = real_dtype, bc_type
         self.radial_coord = np.linspace(dx / 2, grid_size_r * dx - dx / 2, grid_size_r).reshape(grid_size_r, 1)
+        # "auto": grids too large for la.eig (basis left to "auto", >= 1536 points a side) take the direct
+        # r solve and, where the z family allows, the FFT z transforms; everything else follows the
+        # reference's eigen-decomposition.
+        if r_method == "auto":
+            r_method = "tridiagonal" if (basis == "auto" and max(grid_size_r, grid_size_z) >= 1536) else "eigen"
         if r_method == "tridiagonal" and basis == "auto":
             basis = "analytic"
+        if r_method != "tridiagonal" and z_method == "auto":
+            z_method = "gemm"
         self.factors = build_factors(self.kind, bc_type, grid_size_r, grid_size_z, dx, basis, nu_dt, device="cuda",
-                                     split=split, r_method=r_method)
+                                     split=split, r_method=r_method, z_method=z_method)
         self.basis = self.factors["basis"]
         # spectral buffer of the reference (FastDiagonalisationStokesSolver.py:38-39) x 2
         self.work = torch.empty(2 * grid_size_r * grid_size_z, dtype=torch.float64, device="cuda")
@@ -511,8 +562,9 @@ class FastDiagonalisationStokesSolver(_FdBase):
     kind = "stokes"
 
     def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto",
-                 split="auto", r_method="eigen"):
-        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, split=split, r_method=r_method)
+                 split="auto", r_method="auto", z_method="auto"):
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, split=split, r_method=r_method,
+                    z_method=z_method)
 
     def solve(self, solution_field, rhs_field):
         self._solve(solution_field, rhs_field)
@@ -521,6 +573,9 @@ class FastDiagonalisationStokesSolver(_FdBase):
         return solve_flops(self.grid_size_r, self.grid_size_z, self.factors)
 
     def kernel_note(self):
+        if self.factors.get("zfft") is not None:
+            return ("k_dct2_rows + k_thomas + k_dct3_rows (3 launches per solve: shared-memory FFT cosine "
+                    "transforms along z, batched tridiagonal solve along r)")
         zs = self.factors.get("zsplit")
         tri = self.factors.get("tri") is not None
         rpart = "batched tridiagonal r solve" if tri else "2 r-transforms"
@@ -536,7 +591,8 @@ class FastDiagonalisationPotentialSolver(_FdBase):
     kind = "potential"
 
     def __init__(self, grid_size_r, grid_size_z, dx, real_dtype=np.float64, bc_type=_BC_NEUMANN, basis="auto"):
-        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis)
+        # the all-Neumann potential operator is singular; keep the reference's eigen-decomposition for it
+        self._setup(grid_size_r, grid_size_z, dx, real_dtype, bc_type, basis, r_method="eigen", z_method="gemm")
 
     def solve(self, solution_field, rhs_field):
         self._solve(solution_field, rhs_field)
@@ -547,11 +603,11 @@ class ImplicitEulerDiffusionStepper(_FdBase):
     kind = "implicit_diffusion"
 
     def __init__(self, time_step, kinematic_viscosity, grid_size_r, grid_size_z, dx, real_dtype=np.float64,
-                 basis="auto", split="auto", r_method="eigen"):
+                 basis="auto", split="auto", r_method="auto", z_method="auto"):
         self.time_step = time_step
         self.nu_times_dt = self.time_step * kinematic_viscosity
         self._setup(grid_size_r, grid_size_z, dx, real_dtype, None, basis, nu_dt=self.nu_times_dt, split=split,
-                    r_method=r_method)
+                    r_method=r_method, z_method=z_method)
 
     def step(self, vorticity_field, dt):
         if dt != self.time_step:

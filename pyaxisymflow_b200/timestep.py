@@ -37,7 +37,7 @@ class RigidFlowStepper:
 
     def __init__(self, grid_size_z, domain_AR=0.5, Re=100.0, U_0=1.0, r_sph=0.1, Z_cm=0.25, R_cm=0.0,
                  brink_lam=1e12, CFL=0.1, T_ramp=None, periodic=False, ghost_size=2, basis="auto",
-                 grid_size_r=None, use_graph=False, r_method="eigen"):
+                 grid_size_r=None, use_graph=False, r_method="auto", z_method="auto"):
         if not torch.cuda.is_available():
             raise _lib.AxbError("RigidFlowStepper needs a CUDA device (no CPU fallback)")
         self.nz = int(grid_size_z)
@@ -69,9 +69,10 @@ class RigidFlowStepper:
             g = self.ghost
             self.solver = FastDiagonalisationStokesSolver(
                 nr, nz - 2 * g, dx, bc_type="homogenous_neumann_along_r_and_periodic_along_z", basis=basis,
-                r_method=r_method)
+                r_method=r_method, z_method=z_method)
         else:
-            self.solver = FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis, r_method=r_method)
+            self.solver = FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis, r_method=r_method,
+                                                          z_method=z_method)
         if self.periodic:
             _call("axb_periodic_ghost_comm", ctypes.byref(self.grid), ptr(self.char_func), self.ghost, 0.0, 0.0,
                   stream_ptr())

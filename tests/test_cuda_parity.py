@@ -518,8 +518,9 @@ def test_fast_diagonalisation_tridiagonal_r(K, nr, nz, bc):
     rhs = _rand(rng, nr, nz, 5.0)
     ref = fd.apply_factors_host(fd.build_factors("stokes", bc, nr, nz, dx, "analytic", split=0), rhs)
     for split in (0, "auto", 2):
-        s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, r_method="tridiagonal", split=split)
-        assert s.plan.r_tridiagonal == 1 and s.factors["Lr"] is None
+        s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, r_method="tridiagonal", z_method="gemm",
+                                            split=split)
+        assert s.plan.r_tridiagonal == 1 and s.plan.z_fft == 0 and s.factors["Lr"] is None
         sol = np.zeros_like(rhs)
         s.solve(sol, rhs)
         assert_close(sol, ref, RTOL_LINF, f"tridiagonal r, split {split}, {bc}")
@@ -527,6 +528,7 @@ def test_fast_diagonalisation_tridiagonal_r(K, nr, nz, bc):
     ref2 = np.zeros_like(rhs)
     o2.solve(ref2, rhs)
     st = ImplicitEulerDiffusionStepper(0.3 * dx * dx / 2e-3, 2e-3, nr, nz, dx, r_method="tridiagonal")
+    assert st.plan.z_fft == 0          # Dirichlet-type z operator: no cosine transform
     w = rhs.copy()
     st.step(w, 0.3 * dx * dx / 2e-3)
     assert_close(w, ref2, RTOL_LINF, "implicit diffusion, tridiagonal r")
@@ -543,12 +545,86 @@ def test_fast_diagonalisation_tridiagonal_r(K, nr, nz, bc):
     assert_close(tx.cpu().numpy(), want, 1e-13, "batched Thomas")
 
 
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_dct_rows_against_matrix(K, n):
+    """shared-memory FFT cosine transforms against the dense cosine matrix (exact argument reduction)"""
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+
+    rng = np.random.default_rng(n)
+    rows = 37 if n <= 4096 else 5
+    x = rng.standard_normal((rows, n))
+    tabs = torch.from_numpy(fd.dct_tables(n)).cuda()
+    V = fd.axial_natural_block("neumann", n, n, np.arange(n)).numpy()      # orthonormal: c_k cos(...)
+    ck = np.full(n, np.sqrt(2.0 / n))
+    ck[0] = np.sqrt(1.0 / n)
+    for pitch_pad, offset in ((0, 0), (3, 1)):                             # aligned and odd-pitch / odd-offset views
+        src = torch.zeros((rows, n + pitch_pad + offset), dtype=torch.float64, device="cuda")
+        sv = src[:, offset:offset + n]
+        sv.copy_(torch.from_numpy(x))
+        dst = torch.zeros_like(src)
+        dv = dst[:, offset:offset + n]
+        _lib.call("axb_dct2_rows", rows, n, ptr(sv), sv.stride(0), ptr(dv), dv.stride(0), ptr(tabs), 1.0 / n, 2.0 / n,
+                  stream_ptr())
+        got = dv.cpu().numpy()
+        want = (x @ V) * ck[None, :]                                       # s_k sum_j x_j cos = c_k^2/c_k ...
+        assert_close(got, want, 2e-14 * np.sqrt(n), f"DCT-II n={n} offset={offset}")
+        back = torch.zeros_like(src)
+        bv = back[:, offset:offset + n]
+        _lib.call("axb_dct3_rows", rows, n, ptr(dv), dv.stride(0), ptr(bv), bv.stride(0), ptr(tabs), stream_ptr())
+        assert_close(bv.cpu().numpy(), x, 1e-14 * np.log2(n), f"DCT-III(DCT-II) n={n} offset={offset}")
+        if offset:
+            assert float(dst[:, 0].abs().max()) == 0.0 and float(dst[:, offset + n:].abs().max()) == 0.0
+    with pytest.raises(_lib.AxbError):
+        _lib.call("axb_dct2_rows", rows, 96, ptr(sv), sv.stride(0), ptr(dv), dv.stride(0), ptr(tabs), 1.0, 1.0,
+                  stream_ptr())
+
+
+@pytest.mark.parametrize("nr,nz", [(96, 64), (50, 256), (128, 1024), (33, 4096)])
+def test_fast_diagonalisation_fft_z(K, nr, nz):
+    """DCT + Thomas solve against the oracle's eigen-decomposition solve"""
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
+
+    rng = np.random.default_rng(15)
+    dx = 1.0 / nz
+    rhs = _rand(rng, nr, nz, 5.0)
+    s = FastDiagonalisationStokesSolver(nr, nz, dx, r_method="tridiagonal", z_method="fft")
+    assert s.plan.z_fft == 1 and s.plan.r_tridiagonal == 1
+    sol = np.zeros_like(rhs)
+    s.solve(sol, rhs)
+    if nz <= 1024:
+        o = ox.FastDiagonalisationOracle(nr, nz, dx, "stokes")
+        ref = np.zeros_like(rhs)
+        o.solve(ref, rhs)
+    else:
+        from pyaxisymflow_b200 import fd
+        ref = fd.apply_factors_host(fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx,
+                                                     "analytic", split=0), rhs)
+    assert_close(sol, ref, RTOL_LINF, f"fft z / tridiagonal r solve {nr}x{nz}")
+    with pytest.raises(ValueError):
+        FastDiagonalisationStokesSolver(nr, 96, dx, r_method="tridiagonal", z_method="fft")
+
+
+def test_rigid_flow_stepper_fft(K):
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    nz, steps = 128, 12
+    w, psi, uz, t, cds = _oracle_rigid_loop(nz, steps)
+    s = RigidFlowStepper(nz, r_method="tridiagonal", z_method="fft")
+    assert s.solver.plan.z_fft == 1
+    s.step(steps)
+    assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (fft solve)")
+    assert_close(s.psi.cpu().numpy(), psi, 1e-9, "psi (fft solve)")
+
+
 def test_rigid_flow_stepper_tridiagonal_r(K):
     from pyaxisymflow_b200.timestep import RigidFlowStepper
 
     nz, steps = 128, 12
     w, psi, uz, t, cds = _oracle_rigid_loop(nz, steps)
-    s = RigidFlowStepper(nz, r_method="tridiagonal")
+    s = RigidFlowStepper(nz, r_method="tridiagonal", z_method="gemm")
     s.step(steps)
     assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (tridiagonal r solve)")
     assert_close(s.psi.cpu().numpy(), psi, 1e-9, "psi (tridiagonal r solve)")

@@ -98,3 +98,40 @@ def test_parity_split_z_transform_equals_dense():
     # no split for periodic z or odd sizes
     assert fd.build_factors("stokes", BCS[1], 24, 1024, 1 / 1024, "analytic")["zsplit"] is None
     assert fd.split_levels("neumann", 1022) == 0 and fd.split_levels("neumann", 16384) == 3
+
+
+@pytest.mark.parametrize("n", [64, 128, 512, 2048])
+def test_dct_kernel_model_and_tables(n):
+    """tools/dct_model.py restates the FFT-based cosine transforms of zfft.cu step by step in NumPy,
+    reading the same packed twiddle table: both directions against the dense cosine matrix"""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "dct_model", os.path.join(os.path.dirname(__file__), "..", "tools", "dct_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    V = fd.axial_natural_block("neumann", n, n, np.arange(n)).numpy()
+    ck = np.full(n, np.sqrt(2.0 / n))
+    ck[0] = np.sqrt(1.0 / n)
+    assert_close(m.dct2(x), (x @ V) / ck, 1e-13, "DCT-II model")
+    assert_close(m.dct3(x), V @ (x / ck), 1e-13, "DCT-III model")
+
+
+def test_fft_factors_solve_the_operator():
+    nr, nz = 40, 128
+    dx = 1.0 / nz
+    rng = np.random.default_rng(5)
+    rhs = rng.standard_normal((nr, nz))
+    ref = fd.apply_factors_host(fd.build_factors("stokes", BCS[0], nr, nz, dx, "analytic", split=0), rhs)
+    f = fd.build_factors("stokes", BCS[0], nr, nz, dx, "analytic", r_method="tridiagonal", z_method="fft")
+    assert f["zfft"] is not None and f["Rz"] is None and f["zsplit"] is None
+    assert_close(fd.apply_factors_host(f, rhs), ref, 1e-12, "fft factor set")
+    assert fd.build_factors("stokes", BCS[0], nr, 96, dx, "analytic", r_method="tridiagonal",
+                            z_method="auto")["zfft"] is None
+    with pytest.raises(ValueError):
+        fd.build_factors("stokes", BCS[0], nr, nz, dx, "analytic", z_method="fft")      # needs the direct r solve
+    with pytest.raises(ValueError):
+        fd.build_factors("stokes", BCS[1], nr, nz, dx, "analytic", r_method="tridiagonal", z_method="fft")

@@ -6,7 +6,7 @@ from pyaxisymflow_b200.timestep import RigidFlowStepper
 
 nz = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-s = RigidFlowStepper(nz, grid_size_r=nz // 4, basis="analytic")
+s = RigidFlowStepper(nz, grid_size_r=nz // 4)
 s.seed_vorticity()
 torch.cuda.synchronize()
 s.step(steps)
