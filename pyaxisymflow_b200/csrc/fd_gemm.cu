@@ -28,6 +28,10 @@
 int launch_dct_rows(int inverse, int rows, int N, const double* src, long long ld_src, double* dst, long long ld_dst,
                     const double* tabs, double scale0, double scale, cudaStream_t st);   // zfft.cu
 
+bool tri_fast_ok(int nz, const double* X, long long ld, const double* inv);                // tridiag.cu
+int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* inv, const double* sub,
+                        const double* sup, const double* scale, double c1, cudaStream_t s);
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
@@ -628,6 +632,11 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
   double* w0 = p->work;
   double* w1 = p->work + (long long)nr * nz;
   int rc;
+  auto r_solve = [&]() -> int {
+    if (tri_fast_ok(nz, w1, nz, p->r_inv_pivots))
+      return launch_tri_factored(nr, nz, w1, nz, p->r_inv_pivots, p->r_sub, p->r_sup, p->r_scale, p->c1, s);
+    return launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
+  };
   if (p->r_tridiagonal) {
     // z transform (parity-split leaves or dense) -> batched tridiagonal r solve per z-mode -> back
     if (!p->r_sub || !p->r_diag || !p->r_sup) return AXB_EINVAL;
@@ -637,7 +646,7 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
       if (!p->z_tables || rhs == w1 || sol == w1) return AXB_EINVAL;
       rc = launch_dct_rows(0, nr, nz, rhs, ld_rhs, w1, nz, p->z_tables, 1.0 / nz, 2.0 / nz, s);
       if (rc) return rc;
-      rc = launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
+      rc = r_solve();
       if (rc) return rc;
       return launch_dct_rows(1, nr, nz, w1, nz, sol, ld_sol, p->z_tables, 1.0, 1.0, s);
     }
@@ -656,7 +665,7 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
       rc = launch_dgemm(nr, nz, nz, rhs, ld_rhs, p->Rz, nz, w1, nz, nullptr, nullptr, 0, 0, s);
       if (rc) return rc;
     }
-    rc = launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
+    rc = r_solve();
     if (rc) return rc;
     if (p->n_leaves > 0) {
       for (int i = 0; i < p->n_leaves; ++i) {

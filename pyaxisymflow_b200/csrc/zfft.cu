@@ -114,6 +114,30 @@ __device__ __forceinline__ void fft_pass(double2* s, int M, int Ns, int t0, int 
   __syncthreads();
 }
 
+// The last pass (Ns * R == M) writes every butterfly back to the slots it read, so it needs no
+// barrier between the reads and the writes and the butterflies of a thread can run one by one.
+template <int R>
+__device__ __forceinline__ void fft_last_pass(double2* s, int M, int t0, int T, bool live,
+                                              const double2* __restrict__ tabM) {
+  constexpr int B = EPT / R;
+  const int Ns = M / R;
+  if (live) {
+#pragma unroll 2
+    for (int b = 0; b < B; ++b) {
+      const int j = t0 + b * T;                                     // j < Ns
+      double2 v[R];
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = s[pad(j + t * Ns)];
+#pragma unroll
+      for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tabM[t * j]);   // exp(-2 pi i j t / M)
+      dft<R>(v);
+#pragma unroll
+      for (int t = 0; t < R; ++t) s[pad(j + t * Ns)] = v[t];
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void fft_row(double2* s, int M, int logM, int t0, int T, bool live,
                                         const double2* __restrict__ tabM) {
   int Ns = 1;
@@ -122,9 +146,9 @@ __device__ __forceinline__ void fft_row(double2* s, int M, int logM, int t0, int
     Ns <<= 4;
   }
   switch (logM & 3) {
-    case 1: fft_pass<2>(s, M, Ns, t0, T, live, tabM); break;
-    case 2: fft_pass<4>(s, M, Ns, t0, T, live, tabM); break;
-    case 3: fft_pass<8>(s, M, Ns, t0, T, live, tabM); break;
+    case 1: fft_last_pass<2>(s, M, t0, T, live, tabM); break;
+    case 2: fft_last_pass<4>(s, M, t0, T, live, tabM); break;
+    case 3: fft_last_pass<8>(s, M, t0, T, live, tabM); break;
     default: break;
   }
 }

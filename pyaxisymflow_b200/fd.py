@@ -468,6 +468,18 @@ def apply_factors_host(f, rhs):
 # --------------------------------------------------------------------------------------
 # device plan + the three reference classes
 # --------------------------------------------------------------------------------------
+def factor_pivots(nr, nz, f):
+    """reciprocal LU pivots of the nz tridiagonal r systems (axb_tridiag_factor_columns), kept with the
+    factor set on the GPU; needs nz % 16 == 0 (otherwise the solve recomputes the pivots every time)"""
+    tri = f.get("tri")
+    if tri is None or nz % 16 or not f["lam_z"].is_cuda:
+        return
+    inv = torch.empty((nr, nz), dtype=torch.float64, device=f["lam_z"].device)
+    _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(tri["sub"]), ptr(tri["diag"]), ptr(tri["sup"]),
+              ptr(f["lam_z"]), float(f["c0"]), float(f["c1"]), ptr(inv), stream_ptr())
+    tri["inv"] = inv
+
+
 def make_plan(nr, nz, f, work):
     """axb_fd_plan_t over a factor set living on the GPU"""
     p = AxbFdPlan()
@@ -483,6 +495,9 @@ def make_plan(nr, nz, f, work):
         p.r_sub, p.r_diag, p.r_sup = tri["sub"].data_ptr(), tri["diag"].data_ptr(), tri["sup"].data_ptr()
         p.r_scale = opt(tri["scale"])
     p.c0, p.c1, p.work = f["c0"], f["c1"], work.data_ptr()
+    p.r_inv_pivots = None
+    if tri is not None and tri.get("inv") is not None:
+        p.r_inv_pivots = tri["inv"].data_ptr()
     p.z_fft = 0
     if f.get("zfft") is not None:
         p.z_fft, p.z_tables = 1, f["zfft"]["tables"].data_ptr()
@@ -536,6 +551,7 @@ class _FdBase:
         # spectral buffer of the reference (FastDiagonalisationStokesSolver.py:38-39) x 2
         self.work = torch.empty(2 * grid_size_r * grid_size_z, dtype=torch.float64, device="cuda")
         f = self.factors
+        factor_pivots(grid_size_r, grid_size_z, f)
         self.plan = make_plan(grid_size_r, grid_size_z, f, self.work)
 
     def _solve(self, solution_field, rhs_field):

@@ -543,6 +543,20 @@ def test_fast_diagonalisation_tridiagonal_r(K, nr, nz, bc):
     _lib.call("axb_tridiag_solve_columns", nr, nz, ptr(tx), nz, *(ptr(a) for a in dev), 0.0, 1.0, ptr(scratch),
               stream_ptr())
     assert_close(tx.cpu().numpy(), want, 1e-13, "batched Thomas")
+    # factored form: pivots once, then two streaming sweeps (needs nz % 16 == 0)
+    if nz % 16 == 0:
+        for c0, c1, scale in ((0.0, 1.0, dev[4]), (1.0, -0.05 * dx * dx, None)):
+            want = fd.thomas_host(x, sub, diag, sup, lam, r if scale is not None else None, c0, c1)
+            inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
+            _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), c0, c1,
+                      ptr(inv), stream_ptr())
+            tx = torch.from_numpy(x).cuda()
+            _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(dev[0]), ptr(dev[2]),
+                      ptr(scale), c1, stream_ptr())
+            assert_close(tx.cpu().numpy(), want, 1e-13, f"factored tridiagonal solve c0={c0}")
+        assert s.plan.r_inv_pivots
+    else:
+        assert not s.plan.r_inv_pivots
 
 
 @pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
