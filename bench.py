@@ -219,7 +219,7 @@ def run_gpu_arm(args, nr, nz):
         if world > 1:
             from pyaxisymflow_b200.slab import SlabRigidFlowStepper
 
-            stepper = SlabRigidFlowStepper(nz, grid_size_r=nr)
+            stepper = SlabRigidFlowStepper(nz, grid_size_r=nr, r_method=args.r_method, z_method=args.z_method)
         else:
             stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis, r_method=args.r_method,
                                        z_method=args.z_method)
@@ -286,6 +286,8 @@ def run_gpu_arm(args, nr, nz):
     solves_per_step = getattr(stepper, "cases", 1)
     flops = stepper.solve_flops()
     achieved = flops / (solve_ms * 1e-3) / 1e12
+    # DCT + sweep solve: bandwidth bound, so the roofline is algorithmic HBM bytes / device time
+    hbm_bytes = stepper.solve_hbm_bytes() if hasattr(stepper, "solve_hbm_bytes") else None
 
     # ---- e2e: host-resident caller, H2D of the step's inputs + D2H of its result inside the timing
     e2e = None
@@ -310,11 +312,11 @@ def run_gpu_arm(args, nr, nz):
         del hw, hc, ho
 
     if rank == 0:
-        peak = measure_fp64_peak(torch)
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             mp = {}
+        peak = measure_fp64_peak(torch) if hbm_bytes is None else None
         cpu = None
         if world == 1 and not args.no_cpu and args.config in ("c4", "c1"):
             secs, sample = cpu_step_seconds(nr, nz)
@@ -322,7 +324,8 @@ def run_gpu_arm(args, nr, nz):
                    "sample": sample}
         traffic = None
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this workload
-            tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles",
+                                             "gemm_traffic.json" if hbm_bytes is None else "solve_traffic.json")))
             if world == 1 and tj.get("grid") == [nr, nz]:
                 traffic = tj["dram_bytes_per_launch"]
         except (OSError, ValueError, KeyError):
@@ -336,12 +339,8 @@ def run_gpu_arm(args, nr, nz):
                            f"z-slab x{world}" if args.config == "c4" else f"{world} independent replicas"),
                        "l2": "fields (%.0f MiB each) exceed the 126 MB L2; no flush needed" % (nr * nz * 8 / 2 ** 20),
                        "basis": stepper.solver_basis()},
-            "roofline": {"bound": "tensor", "kernel": stepper.solve_kernel_note(), "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no "
-                                        "FP64 entry)",
-                         "solve_ms": solve_ms, "solve_share_of_step": solves_per_step * solve_ms / ms_per_step,
-                         "hbm_peak_gbs": mp.get("hbm_gbs")},
+            "roofline": roofline(stepper, mp, peak, achieved, hbm_bytes, traffic, solve_ms,
+                                 solves_per_step * solve_ms / ms_per_step),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -411,11 +410,33 @@ class _ConfigRunner:
     def solve_flops(self):
         return self.solver.flops()
 
+    def solve_hbm_bytes(self):
+        return self.members[0].solver.hbm_bytes()
+
     def solver_basis(self):
         return self.solver.basis
 
     def solve_kernel_note(self):
         return self.members[0].solver.kernel_note()
+
+
+def roofline(stepper, mp, fp64_peak, tflops, hbm_bytes, traffic, solve_ms, share):
+    """roofline object of the dominant operation, the fast-diagonalisation solve: tensor bound on the GEMM
+    paths (FP64 DMMA, peak = cuBLAS DGEMM measured in this run), HBM bound on the DCT + sweep path (peak =
+    MEASURED_PEAKS.json's copy bandwidth, else the profiling guide's fallback)."""
+    if hbm_bytes is None:
+        return {"bound": "tensor", "kernel": stepper.solve_kernel_note(), "achieved": tflops, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": tflops / fp64_peak, "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "solve_ms": solve_ms, "solve_share_of_step": share, "hbm_peak_gbs": mp.get("hbm_gbs")}
+    peak = mp.get("hbm_gbs")
+    src = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)"
+    if not peak:
+        peak, src = 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
+    gbs = hbm_bytes / (solve_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": stepper.solve_kernel_note(), "achieved": gbs, "peak": peak, "unit": "GB/s",
+            "frac": gbs / peak, "traffic": traffic, "peak_source": src, "launches": 4,
+            "algorithmic_bytes": hbm_bytes, "solve_ms": solve_ms, "solve_share_of_step": share}
 
 
 def main():

@@ -9,14 +9,17 @@
 // streaming sweeps without a division:
 //     forward :  y_m = rhs_m * scale_m - (a_m / den_{m-1}) y_{m-1}
 //     backward:  x_m = (y_m - u_m x_{m+1}) / den_m
-// One 16-lane CTA owns 16 adjacent columns (128-byte row segments) and walks down the rows; the
-// right-hand side and the reciprocal pivots arrive through an 8-stage cp.async ring in shared
-// memory, so each SM keeps ~100 KB of loads in flight although only 16384 chains exist.
+// A CTA of TC threads owns TC adjacent columns (TC = 128: 1 KB row segments, so every visit of a
+// DRAM page moves a useful amount) and walks down the rows in lockstep; the right-hand side and the
+// reciprocal pivots arrive through an 8-stage cp.async ring in shared memory, so each SM keeps
+// ~100 KB of loads in flight although only nz chains exist.
+#include <cuda.h>   // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
+#include <stdlib.h>
+
 #include "axb_common.cuh"
 
 namespace {
 
-constexpr int TC = 16;   // columns per CTA
 constexpr int TR = 8;    // rows per stage
 constexpr int TS = 8;    // stages
 
@@ -49,10 +52,11 @@ __global__ void __launch_bounds__(128)
 
 // stage `st` <- rows [m0, m0 + TR) (DIR = +1) or [m0 - TR + 1, m0] walked downwards (DIR = -1); row u of
 // the stage is m0 + DIR * u.  16 lanes x 16 bytes cover two 128-byte row segments per instruction.
-template <int DIR>
+template <int DIR, int TC>
 __device__ __forceinline__ void issue_stage(double* sx, double* sp, int st, int m0, int nr, const double* __restrict__ X,
                                             long long ld, const double* __restrict__ inv, int nz, int k0, int lane) {
-  const int half = lane >> 3, c = (lane & 7) * 2;
+  constexpr int LPR = TC / 2;                                  // lanes per row (16 bytes each)
+  const int half = lane / LPR, c = (lane % LPR) * 2;
 #pragma unroll
   for (int u2 = 0; u2 < TR; u2 += 2) {
     const int u = u2 + half;
@@ -65,66 +69,278 @@ __device__ __forceinline__ void issue_stage(double* sx, double* sp, int st, int 
 }
 
 // DIR = +1: forward elimination in place (X <- y); DIR = -1: back substitution in place (X <- x).
-template <int DIR>
+template <int TC>
+__device__ __forceinline__ void cta_sync() {
+  if constexpr (TC <= 32) __syncwarp((TC == 32) ? 0xffffffffu : ((1u << TC) - 1u));
+  else __syncthreads();
+}
+
+template <int DIR, int TC>
 __global__ void __launch_bounds__(TC)
     k_tri_sweep(int nr, int nz, double* __restrict__ X, long long ld, const double* __restrict__ inv,
                 const double* __restrict__ lo, const double* __restrict__ up, const double* __restrict__ scale,
                 double c1) {
-  __shared__ __align__(16) double sx[TS * TR * TC];
-  __shared__ __align__(16) double sp[TS * TR * TC];
+  extern __shared__ __align__(16) double tri_smem[];
+  double* sx = tri_smem;
+  double* sp = tri_smem + TS * TR * TC;
   const int lane = threadIdx.x;
   const int k0 = blockIdx.x * TC;
   const int nb = (nr + TR - 1) / TR;
   const int start = (DIR > 0) ? 0 : nr - 1;
 #pragma unroll
   for (int i = 0; i < TS - 1; ++i) {
-    if (i < nb) issue_stage<DIR>(sx, sp, i, start + DIR * i * TR, nr, X, ld, inv, nz, k0, lane);
+    if (i < nb) issue_stage<DIR, TC>(sx, sp, i, start + DIR * i * TR, nr, X, ld, inv, nz, k0, lane);
     cp_commit();
   }
   double carry = 0.0;        // y_{m-1} (forward) / x_{m+1} (backward)
   double pprev = 0.0;        // 1 / den_{m-1} (forward only)
   for (int i = 0; i < nb; ++i) {
-    __syncwarp(0xffffu);                                             // stage (i - 1) % TS is free again
+    cta_sync<TC>();                                             // stage (i - 1) % TS is free again
     const int nxt = i + TS - 1;
-    if (nxt < nb) issue_stage<DIR>(sx, sp, nxt % TS, start + DIR * nxt * TR, nr, X, ld, inv, nz, k0, lane);
+    if (nxt < nb) issue_stage<DIR, TC>(sx, sp, nxt % TS, start + DIR * nxt * TR, nr, X, ld, inv, nz, k0, lane);
     cp_commit();
     cp_wait<TS - 1>();
-    __syncwarp(0xffffu);
+    cta_sync<TC>();
     const int st = i % TS;
+    // all loads of the stage first (no control flow in between), then the dependent chain: with only
+    // ~3.5 warps per SM the latency has to be hidden inside the thread
+    double r[TR], p[TR], co[TR], sc[TR];
 #pragma unroll
     for (int u = 0; u < TR; ++u) {
       const int m = start + DIR * (i * TR + u);
-      if (m < 0 || m >= nr) break;
-      const double r = sx[(st * TR + u) * TC + lane];
-      const double p = sp[(st * TR + u) * TC + lane];
+      const int mc = m < 0 ? 0 : (m >= nr ? nr - 1 : m);
+      r[u] = sx[(st * TR + u) * TC + lane];
+      p[u] = sp[(st * TR + u) * TC + lane];
       if (DIR > 0) {
-        const double a = (m > 0) ? c1 * lo[m - 1] : 0.0;
-        const double rhs = scale ? r * scale[m] : r;
-        carry = rhs - (a * pprev) * carry;
-        pprev = p;
+        co[u] = (mc > 0) ? c1 * lo[mc - 1] : 0.0;
+        sc[u] = scale ? scale[mc] : 1.0;
       } else {
-        const double cu = (m < nr - 1) ? c1 * up[m] : 0.0;
-        carry = (r - cu * carry) * p;
+        co[u] = (mc < nr - 1) ? c1 * up[mc] : 0.0;
       }
-      X[(long long)m * ld + k0 + lane] = carry;
+    }
+#pragma unroll
+    for (int u = 0; u < TR; ++u) {
+      const int m = start + DIR * (i * TR + u);
+      if (DIR > 0) {
+        carry = r[u] * sc[u] - (co[u] * pprev) * carry;
+        pprev = p[u];
+      } else {
+        carry = (r[u] - co[u] * carry) * p[u];
+      }
+      if (m >= 0 && m < nr) X[(long long)m * ld + k0 + lane] = carry;
     }
   }
+}
+
+// ---- TMA variant -----------------------------------------------------------------------------
+// One warp per CTA owns 32 columns.  Lane 0 keeps TS - 1 boxes (8 rows x 32 columns of the field and of
+// the pivots) in flight with cp.async.bulk.tensor + mbarrier complete_tx; the warp consumes a box per
+// iteration and the finished rows leave through a double-buffered TMA store, so the instruction
+// stream of the only warp is the dependent chain and little else.  Out-of-range rows / columns are
+// zero-filled on load and clipped on store by the tensor map.
+constexpr int WC = 32;   // columns per warp
+constexpr int WS = 8;    // stages
+constexpr int W_STAGE = TR * WC;                       // doubles per box
+
+__device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mb_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "TRI_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra TRI_DONE;\n"
+      "bra TRI_WAIT;\n"
+      "TRI_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_ld(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_st(const CUtensorMap* map, int c0, int c1, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(
+                   reinterpret_cast<unsigned long long>(map)),
+               "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(32)
+    k_tri_sweep_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP, int nr,
+                    const double* __restrict__ lo, const double* __restrict__ up, const double* __restrict__ scale,
+                    double c1) {
+  __shared__ __align__(128) double sx[WS * W_STAGE];
+  __shared__ __align__(128) double sp[WS * W_STAGE];
+  __shared__ __align__(128) double so[2 * W_STAGE];
+  __shared__ __align__(8) unsigned long long bars[WS];
+  const int lane = threadIdx.x;
+  const int k0 = blockIdx.x * WC;
+  const int nb = (nr + TR - 1) / TR;
+  // first row of box i: the same row-0-aligned boxes walked down (forward) or up (backward); only the
+  // box at the far end can stick out (beyond nr: zero-filled loads, clipped stores -- TMA stores do
+  // not take negative coordinates)
+  auto row0 = [&](int i) { return (DIR > 0) ? i * TR : (nb - 1 - i) * TR; };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < WS; ++i) mb_init(s_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < WS - 1; ++i) {
+      if (i < nb) {
+        mb_expect(s_u32(&bars[i]), 2 * W_STAGE * 8);
+        tma_ld(s_u32(sx + i * W_STAGE), &tmX, k0, row0(i), s_u32(&bars[i]));
+        tma_ld(s_u32(sp + i * W_STAGE), &tmP, k0, row0(i), s_u32(&bars[i]));
+      }
+    }
+  }
+  __syncwarp();
+  double carry = 0.0, pprev = 0.0;
+  for (int i = 0; i < nb; ++i) {
+    __syncwarp();                                             // box (i - 1) % WS has been consumed
+    const int nxt = i + WS - 1;
+    if (lane == 0 && nxt < nb) {
+      const int st = nxt % WS;
+      mb_expect(s_u32(&bars[st]), 2 * W_STAGE * 8);
+      tma_ld(s_u32(sx + st * W_STAGE), &tmX, k0, row0(nxt), s_u32(&bars[st]));
+      tma_ld(s_u32(sp + st * W_STAGE), &tmP, k0, row0(nxt), s_u32(&bars[st]));
+    }
+    const int st = i % WS;
+    mb_wait(s_u32(&bars[st]), (i / WS) & 1);
+    const int m0 = row0(i);
+    double r[TR], p[TR], co[TR], sc[TR];
+#pragma unroll
+    for (int u = 0; u < TR; ++u) {
+      const int m = m0 + u;
+      const int mc = m < 0 ? 0 : (m >= nr ? nr - 1 : m);
+      r[u] = sx[st * W_STAGE + u * WC + lane];
+      p[u] = sp[st * W_STAGE + u * WC + lane];
+      if (DIR > 0) {
+        co[u] = (mc > 0) ? c1 * lo[mc - 1] : 0.0;
+        sc[u] = scale ? scale[mc] : 1.0;
+      } else {
+        co[u] = (mc < nr - 1) ? c1 * up[mc] : 0.0;
+      }
+    }
+    double* ob = so + (i & 1) * W_STAGE;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");   // store i - 2 has left ob
+    __syncwarp();
+    if (DIR > 0) {
+#pragma unroll
+      for (int u = 0; u < TR; ++u) {
+        carry = r[u] * sc[u] - (co[u] * pprev) * carry;
+        pprev = p[u];
+        ob[u * WC + lane] = carry;
+      }
+    } else {
+#pragma unroll
+      for (int u = TR - 1; u >= 0; --u) {
+        carry = (r[u] - co[u] * carry) * p[u];
+        ob[u * WC + lane] = carry;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_st(&tmX, k0, m0, s_u32(ob));
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tri_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+    cudaGetLastError();
+  }
+  return fn;
+}
+bool tri_map(CUtensorMap* m, const double* ptr, int nr, int nz, long long ld) {
+  EncodeTiledFn enc = tri_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)nz, (cuuint64_t)nr};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  const cuuint32_t box[2] = {(cuuint32_t)WC, (cuuint32_t)TR};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
 
 bool tri_fast_ok(int nz, const double* X, long long ld, const double* inv) {
-  return inv && (nz % TC == 0) && axb_al16(X) && axb_al16(inv) && (ld % 2 == 0);
+  return inv && (nz % 16 == 0) && axb_al16(X) && axb_al16(inv) && (ld % 2 == 0);
+}
+
+template <int TC>
+static void launch_sweeps(int nr, int nz, double* X, long long ld, const double* inv, const double* sub,
+                          const double* sup, const double* scale, double c1, cudaStream_t s) {
+  constexpr size_t smem = 2 * TS * TR * TC * sizeof(double);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(k_tri_sweep<1, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tri_sweep<-1, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  k_tri_sweep<1, TC><<<nz / TC, TC, smem, s>>>(nr, nz, X, ld, inv, sub, sup, scale, c1);
+  AXB_LAUNCHED();
+  k_tri_sweep<-1, TC><<<nz / TC, TC, smem, s>>>(nr, nz, X, ld, inv, sub, sup, scale, c1);
+  AXB_LAUNCHED();
 }
 
 int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* inv, const double* sub,
                         const double* sup, const double* scale, double c1, cudaStream_t s) {
   if (nr < 2 || nz < 1 || !X || !inv || !sub || !sup || ld < nz) return AXB_EINVAL;
   if (!tri_fast_ok(nz, X, ld, inv)) return AXB_EINVAL;
-  k_tri_sweep<1><<<nz / TC, TC, 0, s>>>(nr, nz, X, ld, inv, sub, sup, scale, c1);
-  AXB_LAUNCHED();
-  k_tri_sweep<-1><<<nz / TC, TC, 0, s>>>(nr, nz, X, ld, inv, sub, sup, scale, c1);
-  AXB_LAUNCHED();
+  // widest column block that divides nz and still leaves >= ~1 CTA per SM
+  static int force = -1;
+  if (force < 0) {
+    const char* e = getenv("AXB_TRI_COLS");     // 16 / 32 / 64 / 128: cp.async variants; unset: TMA
+    force = e ? atoi(e) : 0;
+  }
+  if (force == 0) {
+    CUtensorMap tmX, tmP;
+    if (tri_map(&tmX, X, nr, nz, ld) && tri_map(&tmP, inv, nr, nz, nz)) {
+      const int grid = (nz + WC - 1) / WC;
+      k_tri_sweep_tma<1><<<grid, 32, 0, s>>>(tmX, tmP, nr, sub, sup, scale, c1);
+      AXB_LAUNCHED();
+      k_tri_sweep_tma<-1><<<grid, 32, 0, s>>>(tmX, tmP, nr, sub, sup, scale, c1);
+      AXB_LAUNCHED();
+      return (int)cudaGetLastError();
+    }
+  }
+  int tc = 16;
+  if (nz % 128 == 0 && nz >= 128 * 96) tc = 128;
+  else if (nz % 64 == 0 && nz >= 64 * 96) tc = 64;
+  else if (nz % 32 == 0) tc = 32;
+  if ((force == 16 || force == 32 || force == 64 || force == 128) && nz % force == 0) tc = force;
+  switch (tc) {
+    case 128: launch_sweeps<128>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
+    case 64: launch_sweeps<64>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
+    case 32: launch_sweeps<32>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
+    default: launch_sweeps<16>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
+  }
   return (int)cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@
 namespace {
 
 constexpr int EPT = 16;  // complex points per thread and pass
+constexpr double RH = 0.70710678118654752440;
 
 __device__ __forceinline__ int pad(int i) { return i + (i >> 4); }   // one spare slot per 16: pass-1 stores
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -212,10 +213,14 @@ __global__ void __launch_bounds__(512)
         const double2 zk = s[pad(k)], zm = s[pad(M - k)];
         const double ex = 0.5 * (zk.x + zm.x), ey = 0.5 * (zk.y - zm.y);
         const double2 d = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y + zm.y));
-        const double2 p = cmul(tb.N[k], d);
+        // one table read per k: exp(-i pi (M-k) / 2N) = exp(-i pi / 4) conj(q), exp(-2 pi i k / N) = q^4
+        const double2 q = tb.Q[k];
+        const double2 qm = make_double2(RH * (q.x - q.y), -RH * (q.x + q.y));
+        const double2 q2 = cmul(q, q);
+        const double2 p = cmul(cmul(q2, q2), d);
         const double2 vk = make_double2(ex + p.y, ey - p.x);
         const double2 vm = make_double2(ex - p.y, -ey - p.x);
-        const double2 a = cmul(tb.Q[k], vk), b = cmul(tb.Q[M - k], vm);
+        const double2 a = cmul(q, vk), b = cmul(qm, vm);
         X[k] = a.x * scale;
         X[N - k] = -a.y * scale;
         X[M - k] = b.x * scale;
@@ -248,13 +253,15 @@ __global__ void __launch_bounds__(512)
 #pragma unroll
       for (int i = 0; i < EPT / 2; ++i) {
         const int k = 1 + t0 + i * T;
-        const double2 qk = tb.Q[k], qm = tb.Q[M - k];
+        const double2 qk = tb.Q[k];
+        const double2 qm = make_double2(RH * (qk.x - qk.y), -RH * (qk.x + qk.y));
+        const double2 q2 = cmul(qk, qk);
         // B_k = conj(q_k) (a_k - i a_{N-k}) / 2
         const double2 bk = cmul(make_double2(qk.x, -qk.y), make_double2(0.5 * a[k], -0.5 * a[N - k]));
         const double2 bm = cmul(make_double2(qm.x, -qm.y), make_double2(0.5 * a[M - k], -0.5 * a[M + k]));
         const double sx = bk.x + bm.x, sy = bk.y - bm.y;
         const double2 dd = make_double2(bk.x - bm.x, bk.y + bm.y);
-        const double2 wn = tb.N[k];
+        const double2 wn = cmul(q2, q2);
         const double2 q = cmul(make_double2(wn.x, -wn.y), dd);
         s[pad(k)] = make_double2(sy + q.x, sx - q.y);               // swapped
         s[pad(M - k)] = make_double2(-sy + q.x, sx + q.y);

@@ -513,6 +513,16 @@ def make_plan(nr, nz, f, work):
     return p
 
 
+def solve_hbm_bytes(nr, nz, f):
+    """algorithmic HBM bytes of one solve on the DCT + factored-sweep path ("Solve: HBM
+    accounting"): DCT-II reads the right-hand side and writes the spectrum (16 B/pt), each sweep reads the
+    field and the pivots and writes the field (24 B/pt, twice), DCT-III reads and writes (16 B/pt)."""
+    if f.get("zfft") is None:
+        return None
+    tri = f.get("tri") or {}
+    return (16 + 16 + (48 if tri.get("inv") is not None else 40)) * float(nr) * nz
+
+
 def solve_flops(nr, nz, f):
     """floating-point operations one solve executes with this factor set"""
     zs = f.get("zsplit")
@@ -588,10 +598,15 @@ class FastDiagonalisationStokesSolver(_FdBase):
     def flops(self):
         return solve_flops(self.grid_size_r, self.grid_size_z, self.factors)
 
+    def hbm_bytes(self):
+        """algorithmic HBM bytes per solve when the solve is bandwidth bound (DCT path), else None"""
+        return solve_hbm_bytes(self.grid_size_r, self.grid_size_z, self.factors)
+
     def kernel_note(self):
         if self.factors.get("zfft") is not None:
-            return ("k_dct2_rows + k_thomas + k_dct3_rows (3 launches per solve: shared-memory FFT cosine "
-                    "transforms along z, batched tridiagonal solve along r)")
+            return ("fast-diagonalisation solve = k_dct2_rows + k_tri_sweep<fwd> + k_tri_sweep<bwd> + k_dct3_rows "
+                    "(4 launches: shared-memory FFT cosine transforms along z, factored tridiagonal sweeps along r; "
+                    "80 algorithmic B/grid-pt)")
         zs = self.factors.get("zsplit")
         tri = self.factors.get("tri") is not None
         rpart = "batched tridiagonal r solve" if tri else "2 r-transforms"

@@ -164,22 +164,101 @@ def _cuda_fold(x, n, inverse):
     _call("axb_fd_fold", x.shape[0], n, ptr(x), x.stride(0), int(inverse), stream_ptr())
 
 
-class SlabFdSolver:
-    """Distributed fast-diagonalisation solve on z-slabs (factors replicated on every rank)."""
+def _cuda_dct(dst, src, tables, inverse):
+    rows, n = src.shape
+    if inverse:
+        _call("axb_dct3_rows", rows, n, ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(tables), stream_ptr())
+    else:
+        _call("axb_dct2_rows", rows, n, ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(tables), 1.0 / n, 2.0 / n,
+              stream_ptr())
 
-    def __init__(self, layout, comm, factors, gemm=None, fold=None):
+
+class _CudaTridiagonal:
+    """r solve of this rank's z-modes (columns [z_begin, z_begin + nzl) of the spectral field)"""
+
+    def __init__(self, L, f):
+        tri = f["tri"]
+        self.tri, self.c0, self.c1 = tri, float(f["c0"]), float(f["c1"])
+        self.lam = f["lam_z"][L.z_begin:L.z_begin + L.nzl].contiguous()
+        self.inv = None
+        if L.nzl % 16 == 0:
+            self.inv = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=self.lam.device)
+            _call("axb_tridiag_factor_columns", L.nr, L.nzl, ptr(tri["sub"]), ptr(tri["diag"]), ptr(tri["sup"]),
+                  ptr(self.lam), self.c0, self.c1, ptr(self.inv), stream_ptr())
+        else:
+            self.scratch = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=self.lam.device)
+
+    def __call__(self, x):
+        nr, nzl = x.shape
+        tri = self.tri
+        if self.inv is not None:
+            _call("axb_tridiag_solve_factored", nr, nzl, ptr(x), x.stride(0), ptr(self.inv), ptr(tri["sub"]),
+                  ptr(tri["sup"]), ptr(tri["scale"]), self.c1, stream_ptr())
+        else:
+            _call("axb_tridiag_solve_columns", nr, nzl, ptr(x), x.stride(0), ptr(tri["sub"]), ptr(tri["diag"]),
+                  ptr(tri["sup"]), ptr(self.lam), ptr(tri["scale"]), self.c0, self.c1, ptr(self.scratch), stream_ptr())
+
+
+class SlabFdSolver:
+    """Distributed fast-diagonalisation solve on z-slabs (factors replicated on every rank).
+
+    eigen r method:       r GEMM on the slab -> all-to-all -> z transforms on rows -> all-to-all -> r GEMM
+    tridiagonal r method: all-to-all -> forward z transform on rows (GEMM leaves or DCT-II) -> all-to-all ->
+                          r solves of this rank's z-modes -> all-to-all -> backward z transform -> all-to-all
+    ``gemm`` / ``fold`` / ``dct`` / ``tri`` are injectable so the plumbing runs on CPU in the gloo tests."""
+
+    def __init__(self, layout, comm, factors, gemm=None, fold=None, dct=None, tri=None):
         self.L, self.comm, self.f = layout, comm, factors
         self.gemm = gemm or _cuda_gemm
         self.fold = fold or _cuda_fold
-        dev = factors["Lr"].device
+        self.dct = dct or _cuda_dct
+        dev = factors["lam_z"].device
         L = layout
         self.t_slab = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=dev)
         self.rows_a = torch.empty((L.nrl, L.nz), dtype=torch.float64, device=dev)
         self.rows_b = torch.empty((L.nrl, L.nz), dtype=torch.float64, device=dev)
-        self.lam_r_local = factors["lam_r"][L.r_begin:L.r_begin + L.nrl].contiguous()
+        self.tri = None
+        if factors.get("tri") is not None:
+            self.tri = tri or _CudaTridiagonal(L, factors)
+        else:
+            self.lam_r_local = factors["lam_r"][L.r_begin:L.r_begin + L.nrl].contiguous()
+
+    def _z_transform(self, inverse):
+        """rows_a -> rows_a (GEMM leaves, through rows_b) or rows_a -> rows_b (DCT); returns the result buffer"""
+        f = self.f
+        if f.get("zfft") is not None:
+            self.dct(self.rows_b, self.rows_a, f["zfft"]["tables"], inverse)
+            return self.rows_b
+        zs = f.get("zsplit")
+        if zs is None:
+            self.gemm(self.rows_b, self.rows_a, f["Rzb"] if inverse else f["Rz"])
+            return self.rows_b
+        if not inverse:
+            for n in zs["fold_len"]:
+                self.fold(self.rows_a, n, False)
+        for n, off, F in zip(zs["leaf_n"], zs["leaf_off"], zs["bwd"] if inverse else zs["fwd"]):
+            self.gemm(self.rows_b[:, off:off + n], self.rows_a[:, off:off + n], F)
+        if inverse:
+            for n in reversed(zs["fold_len"]):
+                self.fold(self.rows_b, n, True)
+        return self.rows_b
+
+    def _solve_tridiagonal(self, psi_slab, rhs_slab):
+        L = self.L
+        self.t_slab.copy_(L.owned(rhs_slab))
+        self.comm.slab_to_rows(self.t_slab, self.rows_a)                          # all-to-all #1
+        spec = self._z_transform(False)
+        self.comm.rows_to_slab(spec, self.t_slab)                                 # all-to-all #2: modes of this rank
+        self.tri(self.t_slab)
+        self.comm.slab_to_rows(self.t_slab, self.rows_a)                          # all-to-all #3
+        out = self._z_transform(True)
+        self.comm.rows_to_slab(out, self.t_slab)                                  # all-to-all #4
+        L.owned(psi_slab).copy_(self.t_slab)
 
     def solve(self, psi_slab, rhs_slab):
         L, f = self.L, self.f
+        if self.tri is not None:
+            return self._solve_tridiagonal(psi_slab, rhs_slab)
         self.gemm(self.t_slab, f["Lr"], L.owned(rhs_slab))                       # r-transform, local columns
         self.comm.slab_to_rows(self.t_slab, self.rows_a)                          # all-to-all #1
         zs = f.get("zsplit")
@@ -201,6 +280,9 @@ class SlabFdSolver:
 
     def flops_per_rank(self):
         L = self.L
+        if self.tri is not None:
+            from .fd import solve_flops
+            return solve_flops(L.nr, L.nz, self.f) / L.world
         zs = self.f.get("zsplit")
         z = 2.0 * L.nz * L.nz if zs is None else sum(2.0 * n * n for n in zs["leaf_n"])
         return 4.0 * L.nr * L.nr * L.nzl + 2.0 * L.nrl * z
@@ -211,7 +293,8 @@ class SlabRigidFlowStepper:
     kernels; see the module docstring for the exchanges)."""
 
     def __init__(self, grid_size_z, grid_size_r=None, domain_AR=0.5, Re=100.0, U_0=1.0, r_sph=0.1, Z_cm=0.25,
-                 R_cm=0.0, brink_lam=1e12, CFL=0.1, basis="analytic", group=None):
+                 R_cm=0.0, brink_lam=1e12, CFL=0.1, basis="analytic", group=None, r_method="auto",
+                 z_method="auto"):
         from .fd import build_factors
 
         if not torch.cuda.is_available():
@@ -250,8 +333,12 @@ class SlabRigidFlowStepper:
         gall = L.grid(dx, max(0, -L.kz0), min(L.nzs, self.nz - L.kz0))
         _call("axb_smooth_heaviside_sphere", ctypes.byref(gall), ptr(self.char_func), None, ptr(self.z1d),
               ptr(self.r1d), float(Z_cm), float(R_cm), float(r_sph), float(dx * 2 ** 0.5), stream_ptr())
+        if r_method == "auto":          # same rule as the single-GPU solver classes
+            r_method = "tridiagonal" if max(nr, self.nz) >= 1536 else "eigen"
+        if r_method != "tridiagonal" and z_method == "auto":
+            z_method = "gemm"
         self.factors = build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, self.nz, dx, basis,
-                                     device="cuda")
+                                     device="cuda", r_method=r_method, z_method=z_method)
         self.solver = SlabFdSolver(L, self.comm, self.factors)
 
     def seed_vorticity(self, seed=0, amplitude=1.0):
@@ -308,12 +395,24 @@ class SlabRigidFlowStepper:
     def solve_flops(self):
         return self.solver.flops_per_rank()
 
+    def solve_hbm_bytes(self):
+        """per-rank algorithmic HBM bytes of the solve on the DCT path (the all-to-all traffic is NVLink's)"""
+        from .fd import solve_hbm_bytes
+        b = solve_hbm_bytes(self.nr, self.nz, self.factors)
+        return None if b is None else b / self.L.world
+
     def solver_basis(self):
         return self.factors["basis"]
 
     def solve_kernel_note(self):
         zs = self.factors.get("zsplit")
         n = 0 if zs is None else len(zs["leaf_n"])
+        if self.factors.get("zfft") is not None:
+            return ("per rank: k_dct2_rows / k_dct3_rows on r-slabs, k_tri_sweep on this rank's z-modes, "
+                    "4 NCCL all-to-all in between")
+        if self.factors.get("tri") is not None:
+            return (f"per rank: {'2 dense' if zs is None else '2x%d parity-split' % n} k_dgemm_tma z-transforms on "
+                    "r-slabs, k_tri_sweep on this rank's z-modes, 4 NCCL all-to-all in between")
         return (f"k_dgemm_tma per rank: 2 slab r-transforms + {'2 dense' if zs is None else '2x%d parity-split' % n} "
                 "z-transforms on r-slabs, 2 NCCL all-to-all in between")
 

@@ -148,6 +148,9 @@ class RigidFlowStepper:
     def solve_flops(self):
         return self.solver.flops()
 
+    def solve_hbm_bytes(self):
+        return self.solver.hbm_bytes()
+
     def solver_basis(self):
         return self.solver.basis
 

@@ -621,6 +621,31 @@ def test_fast_diagonalisation_fft_z(K, nr, nz):
         FastDiagonalisationStokesSolver(nr, 96, dx, r_method="tridiagonal", z_method="fft")
 
 
+@pytest.mark.parametrize("nr,nz", [(33, 12288), (21, 6144), (19, 96)])
+def test_factored_tridiagonal_column_blocks(K, nr, nz):
+    """the 128-, 64- and 32-column variants of the streamed sweeps"""
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+
+    rng = np.random.default_rng(nz)
+    dx = 1.0 / nz
+    sub, diag, sup, r = fd.radial_tridiagonal("stokes", "homogenous_neumann_along_z_and_r", nr, dx)
+    lam = fd.axial_natural_eigenvalues("neumann", 1.0, nz, dx)
+    lam[0] = lam[1]                                    # keep every system well conditioned
+    x = rng.standard_normal((nr, nz))
+    want = fd.thomas_host(x, sub, diag, sup, lam, r, 0.0, 1.0)
+    dev = [torch.from_numpy(a).cuda() for a in (sub, diag, sup, lam, r)]
+    inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
+    _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), 0.0, 1.0,
+              ptr(inv), stream_ptr())
+    tx = torch.from_numpy(x).cuda()
+    _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(dev[0]), ptr(dev[2]), ptr(dev[4]), 1.0,
+              stream_ptr())
+    assert_close(tx.cpu().numpy(), want, 1e-12, f"factored sweeps {nr}x{nz}")
+
+
 def test_rigid_flow_stepper_fft(K):
     from pyaxisymflow_b200.timestep import RigidFlowStepper
 

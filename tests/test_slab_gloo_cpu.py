@@ -32,6 +32,26 @@ def _torch_fold(x, n, inverse):
     x.copy_(torch.from_numpy(fd.fold_host(x.numpy(), n, inverse)))
 
 
+def _host_dct(dst, src, tables, inverse):
+    n = src.shape[1]
+    V = fd.axial_natural_block("neumann", n, n, np.arange(n))          # orthonormal cosine basis
+    ck = torch.full((n,), np.sqrt(2.0 / n), dtype=torch.float64)
+    ck[0] = np.sqrt(1.0 / n)
+    dst.copy_((src / ck) @ V.T if inverse else (src @ V) * ck)
+
+
+class _HostTridiagonal:
+    def __init__(self, L, f):
+        self.t = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in f["tri"].items()}
+        self.lam = f["lam_z"].numpy()[L.z_begin:L.z_begin + L.nzl]
+        self.c0, self.c1 = f["c0"], f["c1"]
+
+    def __call__(self, x):
+        t = self.t
+        x.copy_(torch.from_numpy(fd.thomas_host(x.numpy(), t["sub"], t["diag"], t["sup"], self.lam, t["scale"],
+                                                self.c0, self.c1)))
+
+
 def _worker(rank, world, port, nr, nz, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -81,6 +101,17 @@ def _worker(rank, world, port, nr, nz, q):
             want = ref[:, L.z_begin:L.z_begin + L.nzl]
             err = (got - want).abs().max().item() / ref.abs().max().item()
             assert err < 1e-12, f"distributed solve (split={split}) differs by {err:.2e}"
+        # ---- the same with the direct r solve: GEMM z transforms (dense / split) and cosine transforms
+        for z_method, split in (("gemm", 0), ("gemm", 1), ("fft", 0)):
+            fac = fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx, "analytic", split=split,
+                                   r_method="tridiagonal", z_method=z_method)
+            ref = torch.from_numpy(fd.apply_factors_host(fac, full.numpy()))
+            solver = SlabFdSolver(L, comm, fac, gemm=_torch_gemm, fold=_torch_fold, dct=_host_dct,
+                                  tri=_HostTridiagonal(L, fac))
+            psi_slab = torch.zeros_like(rhs_slab)
+            solver.solve(psi_slab, rhs_slab)
+            err = (L.owned(psi_slab) - ref[:, L.z_begin:L.z_begin + L.nzl]).abs().max().item() / ref.abs().max().item()
+            assert err < 1e-12, f"distributed tridiagonal solve ({z_method}, split={split}) differs by {err:.2e}"
         # ---- reductions
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         assert comm.allreduce(t.clone(), "max").item() == world

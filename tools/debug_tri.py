@@ -1,0 +1,28 @@
+"""factored tridiagonal sweeps on a small grid (for compute-sanitizer): python tools/debug_tri.py nr nz"""
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from pyaxisymflow_b200 import _lib, fd  # noqa: E402
+from pyaxisymflow_b200.device import ptr, stream_ptr  # noqa: E402
+
+nr, nz = int(sys.argv[1]), int(sys.argv[2])
+rng = np.random.default_rng(0)
+dx = 1.0 / nz
+sub, diag, sup, r = fd.radial_tridiagonal("stokes", "homogenous_neumann_along_z_and_r", nr, dx)
+lam = fd.axial_natural_eigenvalues("neumann", 1.0, nz, dx)
+lam[0] = lam[1]
+x = rng.standard_normal((nr, nz))
+want = fd.thomas_host(x, sub, diag, sup, lam, r, 0.0, 1.0)
+dev = [torch.from_numpy(a).cuda() for a in (sub, diag, sup, lam, r)]
+inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
+_lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), 0.0, 1.0, ptr(inv),
+          stream_ptr())
+tx = torch.from_numpy(x).cuda()
+_lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(dev[0]), ptr(dev[2]), ptr(dev[4]), 1.0,
+          stream_ptr())
+torch.cuda.synchronize()
+got = tx.cpu().numpy()
+print(nr, nz, "rel err", np.abs(got - want).max() / np.abs(want).max())
