@@ -272,10 +272,12 @@ typedef struct axb_fd_plan {
    * natural mode order k = 0..nz-1.  Rz / Rzb / leaves are then unused. */
   int32_t z_fft;
   const double* z_tables;
-  /* Optional reciprocal LU pivots of the nz tridiagonal systems (nr x nz, pitch nz), filled once by
-   * axb_tridiag_factor_columns: the r solve is then two division-free streaming sweeps
-   * (axb_tridiag_solve_factored).  NULL: the pivots are recomputed inside every solve. */
+  /* Optional reciprocal LU pivots of the nz tridiagonal systems (nr x nz, pitch nz) and per-row
+   * coefficients (nr x 4), both filled once by axb_tridiag_factor_columns: the r solve is then two
+   * division-free streaming sweeps (axb_tridiag_solve_factored).  NULL: the pivots are recomputed
+   * inside every solve. */
   const double* r_inv_pivots;
+  const double* r_row_coef;
 } axb_fd_plan_t;
 /* Row-wise cosine transforms through a shared-memory FFT (n = 2^p, 64 <= n <= 16384):
  *   axb_dct2_rows: dst[m, k] = s_k * sum_j src[m, j] cos(pi k (2j+1) / (2n)), s_0 = scale0, s_k = scale
@@ -300,12 +302,15 @@ int axb_tridiag_solve_columns(int nr, int nz, double* X, int64_t ld, const doubl
                               const double* sup, const double* lam, const double* scale, double c0, double c1,
                               double* scratch, axb_stream_t s);
 /* Factored form of the same solve.  axb_tridiag_factor_columns writes 1 / den[m, k] (the LU pivots of
- * column k's system) into inv_pivots (nr x nz, pitch nz); axb_tridiag_solve_factored then solves in
- * place with the right-hand sides in X.  Needs nz % 16 == 0, X and inv_pivots 16-byte aligned, ld even. */
+ * column k's system) into inv_pivots (nr x nz, pitch nz) and the row coefficients
+ * {c1 sub[m-1], scale[m] (1 if scale is NULL), c1 sup[m], 0} into row_coef (nr x 4);
+ * axb_tridiag_solve_factored then solves in place with the right-hand sides in X (two TMA-streamed
+ * sweeps).  Needs nz % 16 == 0, X / inv_pivots / row_coef 16-byte aligned, ld even. */
 int axb_tridiag_factor_columns(int nr, int nz, const double* sub, const double* diag, const double* sup,
-                               const double* lam, double c0, double c1, double* inv_pivots, axb_stream_t s);
-int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const double* inv_pivots, const double* sub,
-                               const double* sup, const double* scale, double c1, axb_stream_t s);
+                               const double* lam, const double* scale, double c0, double c1, double* inv_pivots,
+                               double* row_coef, axb_stream_t s);
+int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const double* inv_pivots,
+                               const double* row_coef, axb_stream_t s);
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s);
 /* Plain row-major FP64 GEMM C = A*B (+ optional spectral scaling), the building block above:

@@ -33,7 +33,8 @@ class AxbFdPlan(Structure):
                 ("leaf_fwd", c_void_p * 8), ("leaf_bwd", c_void_p * 8),
                 ("r_tridiagonal", c_int32),
                 ("r_sub", c_void_p), ("r_diag", c_void_p), ("r_sup", c_void_p), ("r_scale", c_void_p),
-                ("z_fft", c_int32), ("z_tables", c_void_p), ("r_inv_pivots", c_void_p)]
+                ("z_fft", c_int32), ("z_tables", c_void_p), ("r_inv_pivots", c_void_p),
+                ("r_row_coef", c_void_p)]
 
 
 _G = POINTER(AxbGrid)
@@ -89,8 +90,8 @@ _SIGNATURES = {
     "axb_fd_fold2": [_I, _I, _P, c_int64, _P, c_int64, _I, _S],
     "axb_dct2_rows": [_I, _I, _P, c_int64, _P, c_int64, _P, _D, _D, _S],
     "axb_dct3_rows": [_I, _I, _P, c_int64, _P, c_int64, _P, _S],
-    "axb_tridiag_factor_columns": [_I, _I, _P, _P, _P, _P, _D, _D, _P, _S],
-    "axb_tridiag_solve_factored": [_I, _I, _P, c_int64, _P, _P, _P, _P, _D, _S],
+    "axb_tridiag_factor_columns": [_I, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _S],
+    "axb_tridiag_solve_factored": [_I, _I, _P, c_int64, _P, _P, _S],
     "axb_tridiag_solve_columns": [_I, _I, _P, c_int64, _P, _P, _P, _P, _P, _D, _D, _P, _S],
     "axb_halo_pack": [_G, _P, _P, _P, _I, _S],
     "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],

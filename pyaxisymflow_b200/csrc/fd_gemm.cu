@@ -29,8 +29,8 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
                     const double* tabs, double scale0, double scale, cudaStream_t st);   // zfft.cu
 
 bool tri_fast_ok(int nz, const double* X, long long ld, const double* inv);                // tridiag.cu
-int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* inv, const double* sub,
-                        const double* sup, const double* scale, double c1, cudaStream_t s);
+int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* inv, const double* rc,
+                        cudaStream_t s);
 
 namespace {
 
@@ -633,8 +633,8 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
   double* w1 = p->work + (long long)nr * nz;
   int rc;
   auto r_solve = [&]() -> int {
-    if (tri_fast_ok(nz, w1, nz, p->r_inv_pivots))
-      return launch_tri_factored(nr, nz, w1, nz, p->r_inv_pivots, p->r_sub, p->r_sup, p->r_scale, p->c1, s);
+    if (p->r_row_coef && tri_fast_ok(nz, w1, nz, p->r_inv_pivots))
+      return launch_tri_factored(nr, nz, w1, nz, p->r_inv_pivots, p->r_row_coef, s);
     return launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
   };
   if (p->r_tridiagonal) {

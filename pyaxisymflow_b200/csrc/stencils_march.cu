@@ -13,6 +13,7 @@
 // rolling window for the three rows that need it.  In G-ADV the r-direction face flux of row
 // j is re-used as the back face of row j+1.  Compiled with -fmad=false like stencils.cu.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include <initializer_list>
 
@@ -648,16 +649,60 @@ inline dim3 march_grid(const GridD& d, int rb) {
   return dim3(((d.nz + 1) / 2 + MT - 1) / MT, (d.nr + rb - 1) / rb, 1);
 }
 
+// The edge kernel of a pair (few blocks, latency bound: 40-90 us at 4096 x 16384) runs on a side stream
+// forked from and joined back into the caller's stream, so it hides behind the interior kernel.  The two
+// kernels write disjoint cells and only read the operation's inputs.  Works under stream capture (the
+// side stream joins the capture through the fork event).
+struct EdgeFork {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+  bool ok = false;
+};
+inline EdgeFork* edge_fork() {
+  static thread_local EdgeFork f[16];
+  static const bool off = getenv("AXB_EDGE_SERIAL") != nullptr;
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  EdgeFork& e = f[dev];
+  if (e.device != dev) {
+    e.device = dev;
+    e.ok = cudaStreamCreateWithFlags(&e.side, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming) == cudaSuccess;
+    cudaGetLastError();
+  }
+  return e.ok ? &e : nullptr;
+}
+// stream the edge kernel goes to (falls back to the caller's stream)
+inline cudaStream_t edge_begin(cudaStream_t s, EdgeFork*& f) {
+  f = edge_fork();
+  if (f && cudaEventRecord(f->fork, s) == cudaSuccess && cudaStreamWaitEvent(f->side, f->fork, 0) == cudaSuccess)
+    return f->side;
+  f = nullptr;
+  cudaGetLastError();
+  return s;
+}
+inline void edge_end(cudaStream_t s, EdgeFork* f) {
+  if (!f) return;
+  cudaEventRecord(f->join, f->side);
+  cudaStreamWaitEvent(s, f->join, 0);
+}
+
 }  // namespace
 
 int march_velocity(const GridD& d, double* u_z, double* u_r, const double* psi, const double* r1d, double uz_add,
                    double ur_add, const double* add_dev, double* umax_out, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
-#define VEL(R, P) km_velocity<R, P><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, u_z, u_r, psi, r1d, uz_add, \
-                                                                                     ur_add, add_dev, umax_out, vec)
-  if (umax_out) { VEL(true, 1); VEL(true, 2); }
-  else { VEL(false, 1); VEL(false, 2); }
+  EdgeFork* ef;
+  cudaStream_t se = edge_begin(s, ef);
+#define VEL(R, P, ST) km_velocity<R, P><<<march_grid(d, rb), MT, rb * sizeof(double), ST>>>(d, rb, u_z, u_r, psi, r1d, uz_add, \
+                                                                                      ur_add, add_dev, umax_out, vec)
+  if (umax_out) { VEL(true, 2, se); VEL(true, 1, s); }
+  else { VEL(false, 2, se); VEL(false, 1, s); }
 #undef VEL
+  edge_end(s, ef);
   return (int)cudaGetLastError();
 }
 
@@ -665,22 +710,28 @@ int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const do
                    const double* chi, double lam, double dt, const double* dt_dev, double U_z, double U_r,
                    const double* U_dev, const double* r1d, double* sum_out, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
-#define PEN(R, P) km_penalise<R, P><<<march_grid(d, rb), MT, 0, s>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, \
-                                                                   U_r, U_dev, r1d, sum_out, vec)
-  if (sum_out) { PEN(true, 1); PEN(true, 2); }
-  else { PEN(false, 1); PEN(false, 2); }
+  EdgeFork* ef;
+  cudaStream_t se = edge_begin(s, ef);
+#define PEN(R, P, ST) km_penalise<R, P><<<march_grid(d, rb), MT, 0, ST>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, \
+                                                                    U_r, U_dev, r1d, sum_out, vec)
+  if (sum_out) { PEN(true, 2, se); PEN(true, 1, s); }
+  else { PEN(false, 2, se); PEN(false, 1, s); }
 #undef PEN
+  edge_end(s, ef);
   return (int)cudaGetLastError();
 }
 
 int march_diffusion(int stage, const GridD& d, double* out, const double* in, const double* src2, const double* r1d,
                     double nu, double dt, const double* dt_dev, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
-#define DIF(S, P) km_diffusion<S, P><<<march_grid(d, rb), MT, rb * sizeof(double), s>>>(d, rb, out, in, src2, r1d, nu, dt, \
-                                                                                      dt_dev, vec)
-  if (stage == 1) { DIF(1, 1); DIF(1, 2); }
-  else { DIF(2, 1); DIF(2, 2); }
+  EdgeFork* ef;
+  cudaStream_t se = edge_begin(s, ef);
+#define DIF(S, P, ST) km_diffusion<S, P><<<march_grid(d, rb), MT, rb * sizeof(double), ST>>>(d, rb, out, in, src2, r1d, nu, dt, \
+                                                                                       dt_dev, vec)
+  if (stage == 1) { DIF(1, 2, se); DIF(1, 1, s); }
+  else { DIF(2, 2, se); DIF(2, 1, s); }
 #undef DIF
+  edge_end(s, ef);
   return (int)cudaGetLastError();
 }
 
@@ -689,12 +740,14 @@ int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, do
                const double* dt_dev, double sign0, double sign1, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
   const dim3 grd = march_grid(d, rb);
-#define LAUNCH(NF, C, M, F)                                                                                              \
-  do {                                                                                                                  \
-    km_eno3<NF, C, M, F, 1><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, \
-                                               vec);                                                                    \
-    km_eno3<NF, C, M, F, 2><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, \
-                                               vec);                                                                    \
+  EdgeFork* ef;
+  cudaStream_t se = edge_begin(s, ef);
+#define LAUNCH(NF, C, M, F)                                                                                               \
+  do {                                                                                                                   \
+    km_eno3<NF, C, M, F, 2><<<grd, MT, 0, se>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, \
+                                                vec);                                                                    \
+    km_eno3<NF, C, M, F, 1><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1,  \
+                                               vec);                                                                     \
   } while (0)
   if (nf == 1 && cons && mirror && !fluxonly) LAUNCH(1, true, true, false);
   else if (nf == 2 && !cons && mirror && !fluxonly) LAUNCH(2, false, true, false);
@@ -702,7 +755,8 @@ int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, do
   else if (nf == 1 && !cons && !mirror && fluxonly) LAUNCH(1, false, false, true);
   else if (nf == 1 && cons && !mirror && !fluxonly) LAUNCH(1, true, false, false);
   else if (nf == 1 && !cons && !mirror && !fluxonly) LAUNCH(1, false, false, false);
-  else return AXB_ENOSUP;
+  else { edge_end(s, ef); return AXB_ENOSUP; }
 #undef LAUNCH
+  edge_end(s, ef);
   return (int)cudaGetLastError();
 }

@@ -32,6 +32,17 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// row_coef[m] = { c1 sub[m-1] (0 at m = 0), scale[m] (1 without scale), c1 sup[m] (0 at m = nr-1), 0 }
+__global__ void k_tri_row_coef(int nr, const double* __restrict__ sub, const double* __restrict__ sup,
+                               const double* __restrict__ scale, double c1, double* __restrict__ rc) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nr) return;
+  rc[4 * m + 0] = (m > 0) ? c1 * sub[m - 1] : 0.0;
+  rc[4 * m + 1] = scale ? scale[m] : 1.0;
+  rc[4 * m + 2] = (m < nr - 1) ? c1 * sup[m] : 0.0;
+  rc[4 * m + 3] = 0.0;
+}
+
 __global__ void __launch_bounds__(128)
     k_tri_factor(int nr, int nz, const double* __restrict__ sub, const double* __restrict__ diag,
                  const double* __restrict__ sup, const double* __restrict__ lam, double c0, double c1,
@@ -78,8 +89,7 @@ __device__ __forceinline__ void cta_sync() {
 template <int DIR, int TC>
 __global__ void __launch_bounds__(TC)
     k_tri_sweep(int nr, int nz, double* __restrict__ X, long long ld, const double* __restrict__ inv,
-                const double* __restrict__ lo, const double* __restrict__ up, const double* __restrict__ scale,
-                double c1) {
+                const double* __restrict__ rc) {
   extern __shared__ __align__(16) double tri_smem[];
   double* sx = tri_smem;
   double* sp = tri_smem + TS * TR * TC;
@@ -112,10 +122,10 @@ __global__ void __launch_bounds__(TC)
       r[u] = sx[(st * TR + u) * TC + lane];
       p[u] = sp[(st * TR + u) * TC + lane];
       if (DIR > 0) {
-        co[u] = (mc > 0) ? c1 * lo[mc - 1] : 0.0;
-        sc[u] = scale ? scale[mc] : 1.0;
+        co[u] = rc[4 * mc];
+        sc[u] = rc[4 * mc + 1];
       } else {
-        co[u] = (mc < nr - 1) ? c1 * up[mc] : 0.0;
+        co[u] = rc[4 * mc + 2];
       }
     }
 #pragma unroll
@@ -141,6 +151,7 @@ __global__ void __launch_bounds__(TC)
 constexpr int WC = 32;   // columns per warp
 constexpr int WS = 8;    // stages
 constexpr int W_STAGE = TR * WC;                       // doubles per box
+constexpr unsigned STAGE_TX = (2 * W_STAGE + 4 * TR) * 8;   // bytes landing on a stage's mbarrier
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(unsigned bar, unsigned count) {
@@ -175,11 +186,11 @@ __device__ __forceinline__ void tma_st(const CUtensorMap* map, int c0, int c1, u
 
 template <int DIR>
 __global__ void __launch_bounds__(32)
-    k_tri_sweep_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP, int nr,
-                    const double* __restrict__ lo, const double* __restrict__ up, const double* __restrict__ scale,
-                    double c1) {
+    k_tri_sweep_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP,
+                    const __grid_constant__ CUtensorMap tmC, int nr) {
   __shared__ __align__(128) double sx[WS * W_STAGE];
   __shared__ __align__(128) double sp[WS * W_STAGE];
+  __shared__ __align__(128) double sc4[WS * TR * 4];         // row coefficients of the boxes in flight
   __shared__ __align__(128) double so[2 * W_STAGE];
   __shared__ __align__(8) unsigned long long bars[WS];
   const int lane = threadIdx.x;
@@ -197,9 +208,10 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
     for (int i = 0; i < WS - 1; ++i) {
       if (i < nb) {
-        mb_expect(s_u32(&bars[i]), 2 * W_STAGE * 8);
+        mb_expect(s_u32(&bars[i]), STAGE_TX);
         tma_ld(s_u32(sx + i * W_STAGE), &tmX, k0, row0(i), s_u32(&bars[i]));
         tma_ld(s_u32(sp + i * W_STAGE), &tmP, k0, row0(i), s_u32(&bars[i]));
+        tma_ld(s_u32(sc4 + i * TR * 4), &tmC, 0, row0(i), s_u32(&bars[i]));
       }
     }
   }
@@ -210,9 +222,10 @@ __global__ void __launch_bounds__(32)
     const int nxt = i + WS - 1;
     if (lane == 0 && nxt < nb) {
       const int st = nxt % WS;
-      mb_expect(s_u32(&bars[st]), 2 * W_STAGE * 8);
+      mb_expect(s_u32(&bars[st]), STAGE_TX);
       tma_ld(s_u32(sx + st * W_STAGE), &tmX, k0, row0(nxt), s_u32(&bars[st]));
       tma_ld(s_u32(sp + st * W_STAGE), &tmP, k0, row0(nxt), s_u32(&bars[st]));
+      tma_ld(s_u32(sc4 + st * TR * 4), &tmC, 0, row0(nxt), s_u32(&bars[st]));
     }
     const int st = i % WS;
     mb_wait(s_u32(&bars[st]), (i / WS) & 1);
@@ -220,15 +233,14 @@ __global__ void __launch_bounds__(32)
     double r[TR], p[TR], co[TR], sc[TR];
 #pragma unroll
     for (int u = 0; u < TR; ++u) {
-      const int m = m0 + u;
-      const int mc = m < 0 ? 0 : (m >= nr ? nr - 1 : m);
       r[u] = sx[st * W_STAGE + u * WC + lane];
       p[u] = sp[st * W_STAGE + u * WC + lane];
       if (DIR > 0) {
-        co[u] = (mc > 0) ? c1 * lo[mc - 1] : 0.0;
-        sc[u] = scale ? scale[mc] : 1.0;
+        const double2 c = *reinterpret_cast<const double2*>(sc4 + (st * TR + u) * 4);   // broadcast read
+        co[u] = c.x;
+        sc[u] = c.y;
       } else {
-        co[u] = (mc < nr - 1) ? c1 * up[mc] : 0.0;
+        co[u] = sc4[(st * TR + u) * 4 + 2];
       }
     }
     double* ob = so + (i & 1) * W_STAGE;
@@ -275,12 +287,12 @@ EncodeTiledFn tri_encoder() {
   }
   return fn;
 }
-bool tri_map(CUtensorMap* m, const double* ptr, int nr, int nz, long long ld) {
+bool tri_map(CUtensorMap* m, const double* ptr, int nr, int nz, long long ld, int box_cols = WC) {
   EncodeTiledFn enc = tri_encoder();
   if (!enc) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)nz, (cuuint64_t)nr};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-  const cuuint32_t box[2] = {(cuuint32_t)WC, (cuuint32_t)TR};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)TR};
   const cuuint32_t estr[2] = {1u, 1u};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -294,8 +306,8 @@ bool tri_fast_ok(int nz, const double* X, long long ld, const double* inv) {
 }
 
 template <int TC>
-static void launch_sweeps(int nr, int nz, double* X, long long ld, const double* inv, const double* sub,
-                          const double* sup, const double* scale, double c1, cudaStream_t s) {
+static void launch_sweeps(int nr, int nz, double* X, long long ld, const double* inv, const double* rc,
+                          cudaStream_t s) {
   constexpr size_t smem = 2 * TS * TR * TC * sizeof(double);
   static bool once = false;
   if (!once) {
@@ -303,15 +315,15 @@ static void launch_sweeps(int nr, int nz, double* X, long long ld, const double*
     cudaFuncSetAttribute(k_tri_sweep<-1, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     once = true;
   }
-  k_tri_sweep<1, TC><<<nz / TC, TC, smem, s>>>(nr, nz, X, ld, inv, sub, sup, scale, c1);
+  k_tri_sweep<1, TC><<<nz / TC, TC, smem, s>>>(nr, nz, X, ld, inv, rc);
   AXB_LAUNCHED();
-  k_tri_sweep<-1, TC><<<nz / TC, TC, smem, s>>>(nr, nz, X, ld, inv, sub, sup, scale, c1);
+  k_tri_sweep<-1, TC><<<nz / TC, TC, smem, s>>>(nr, nz, X, ld, inv, rc);
   AXB_LAUNCHED();
 }
 
-int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* inv, const double* sub,
-                        const double* sup, const double* scale, double c1, cudaStream_t s) {
-  if (nr < 2 || nz < 1 || !X || !inv || !sub || !sup || ld < nz) return AXB_EINVAL;
+int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* inv, const double* rc,
+                        cudaStream_t s) {
+  if (nr < 2 || nz < 1 || !X || !inv || !rc || ld < nz) return AXB_EINVAL;
   if (!tri_fast_ok(nz, X, ld, inv)) return AXB_EINVAL;
   // widest column block that divides nz and still leaves >= ~1 CTA per SM
   static int force = -1;
@@ -320,12 +332,12 @@ int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* i
     force = e ? atoi(e) : 0;
   }
   if (force == 0) {
-    CUtensorMap tmX, tmP;
-    if (tri_map(&tmX, X, nr, nz, ld) && tri_map(&tmP, inv, nr, nz, nz)) {
+    CUtensorMap tmX, tmP, tmC;
+    if (tri_map(&tmX, X, nr, nz, ld) && tri_map(&tmP, inv, nr, nz, nz) && tri_map(&tmC, rc, nr, 4, 4, 4)) {
       const int grid = (nz + WC - 1) / WC;
-      k_tri_sweep_tma<1><<<grid, 32, 0, s>>>(tmX, tmP, nr, sub, sup, scale, c1);
+      k_tri_sweep_tma<1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
       AXB_LAUNCHED();
-      k_tri_sweep_tma<-1><<<grid, 32, 0, s>>>(tmX, tmP, nr, sub, sup, scale, c1);
+      k_tri_sweep_tma<-1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
       AXB_LAUNCHED();
       return (int)cudaGetLastError();
     }
@@ -336,10 +348,10 @@ int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* i
   else if (nz % 32 == 0) tc = 32;
   if ((force == 16 || force == 32 || force == 64 || force == 128) && nz % force == 0) tc = force;
   switch (tc) {
-    case 128: launch_sweeps<128>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
-    case 64: launch_sweeps<64>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
-    case 32: launch_sweeps<32>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
-    default: launch_sweeps<16>(nr, nz, X, ld, inv, sub, sup, scale, c1, s); break;
+    case 128: launch_sweeps<128>(nr, nz, X, ld, inv, rc, s); break;
+    case 64: launch_sweeps<64>(nr, nz, X, ld, inv, rc, s); break;
+    case 32: launch_sweeps<32>(nr, nz, X, ld, inv, rc, s); break;
+    default: launch_sweeps<16>(nr, nz, X, ld, inv, rc, s); break;
   }
   return (int)cudaGetLastError();
 }
@@ -347,16 +359,19 @@ int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* i
 extern "C" {
 
 int axb_tridiag_factor_columns(int nr, int nz, const double* sub, const double* diag, const double* sup,
-                               const double* lam, double c0, double c1, double* inv_pivots, axb_stream_t s) {
-  if (nr < 2 || nz < 1 || !sub || !diag || !sup || !lam || !inv_pivots) return AXB_EINVAL;
+                               const double* lam, const double* scale, double c0, double c1, double* inv_pivots,
+                               double* row_coef, axb_stream_t s) {
+  if (nr < 2 || nz < 1 || !sub || !diag || !sup || !lam || !inv_pivots || !row_coef) return AXB_EINVAL;
   k_tri_factor<<<(nz + 127) / 128, 128, 0, (cudaStream_t)s>>>(nr, nz, sub, diag, sup, lam, c0, c1, inv_pivots);
+  AXB_LAUNCHED();
+  k_tri_row_coef<<<(nr + 127) / 128, 128, 0, (cudaStream_t)s>>>(nr, sub, sup, scale, c1, row_coef);
   AXB_LAUNCHED();
   return (int)cudaGetLastError();
 }
 
-int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const double* inv_pivots, const double* sub,
-                               const double* sup, const double* scale, double c1, axb_stream_t s) {
-  return launch_tri_factored(nr, nz, X, ld, inv_pivots, sub, sup, scale, c1, (cudaStream_t)s);
+int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const double* inv_pivots, const double* row_coef,
+                               axb_stream_t s) {
+  return launch_tri_factored(nr, nz, X, ld, inv_pivots, row_coef, (cudaStream_t)s);
 }
 
 }  // extern "C"

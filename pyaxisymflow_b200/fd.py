@@ -475,9 +475,10 @@ def factor_pivots(nr, nz, f):
     if tri is None or nz % 16 or not f["lam_z"].is_cuda:
         return
     inv = torch.empty((nr, nz), dtype=torch.float64, device=f["lam_z"].device)
+    rc = torch.empty((nr, 4), dtype=torch.float64, device=f["lam_z"].device)
     _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(tri["sub"]), ptr(tri["diag"]), ptr(tri["sup"]),
-              ptr(f["lam_z"]), float(f["c0"]), float(f["c1"]), ptr(inv), stream_ptr())
-    tri["inv"] = inv
+              ptr(f["lam_z"]), ptr(tri["scale"]), float(f["c0"]), float(f["c1"]), ptr(inv), ptr(rc), stream_ptr())
+    tri["inv"], tri["row_coef"] = inv, rc
 
 
 def make_plan(nr, nz, f, work):
@@ -495,9 +496,9 @@ def make_plan(nr, nz, f, work):
         p.r_sub, p.r_diag, p.r_sup = tri["sub"].data_ptr(), tri["diag"].data_ptr(), tri["sup"].data_ptr()
         p.r_scale = opt(tri["scale"])
     p.c0, p.c1, p.work = f["c0"], f["c1"], work.data_ptr()
-    p.r_inv_pivots = None
+    p.r_inv_pivots = p.r_row_coef = None
     if tri is not None and tri.get("inv") is not None:
-        p.r_inv_pivots = tri["inv"].data_ptr()
+        p.r_inv_pivots, p.r_row_coef = tri["inv"].data_ptr(), tri["row_coef"].data_ptr()
     p.z_fft = 0
     if f.get("zfft") is not None:
         p.z_fft, p.z_tables = 1, f["zfft"]["tables"].data_ptr()

@@ -183,8 +183,9 @@ class _CudaTridiagonal:
         self.inv = None
         if L.nzl % 16 == 0:
             self.inv = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=self.lam.device)
+            self.rc = torch.empty((L.nr, 4), dtype=torch.float64, device=self.lam.device)
             _call("axb_tridiag_factor_columns", L.nr, L.nzl, ptr(tri["sub"]), ptr(tri["diag"]), ptr(tri["sup"]),
-                  ptr(self.lam), self.c0, self.c1, ptr(self.inv), stream_ptr())
+                  ptr(self.lam), ptr(tri["scale"]), self.c0, self.c1, ptr(self.inv), ptr(self.rc), stream_ptr())
         else:
             self.scratch = torch.empty((L.nr, L.nzl), dtype=torch.float64, device=self.lam.device)
 
@@ -192,8 +193,7 @@ class _CudaTridiagonal:
         nr, nzl = x.shape
         tri = self.tri
         if self.inv is not None:
-            _call("axb_tridiag_solve_factored", nr, nzl, ptr(x), x.stride(0), ptr(self.inv), ptr(tri["sub"]),
-                  ptr(tri["sup"]), ptr(tri["scale"]), self.c1, stream_ptr())
+            _call("axb_tridiag_solve_factored", nr, nzl, ptr(x), x.stride(0), ptr(self.inv), ptr(self.rc), stream_ptr())
         else:
             _call("axb_tridiag_solve_columns", nr, nzl, ptr(x), x.stride(0), ptr(tri["sub"]), ptr(tri["diag"]),
                   ptr(tri["sup"]), ptr(self.lam), ptr(tri["scale"]), self.c0, self.c1, ptr(self.scratch), stream_ptr())

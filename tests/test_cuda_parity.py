@@ -548,11 +548,11 @@ def test_fast_diagonalisation_tridiagonal_r(K, nr, nz, bc):
         for c0, c1, scale in ((0.0, 1.0, dev[4]), (1.0, -0.05 * dx * dx, None)):
             want = fd.thomas_host(x, sub, diag, sup, lam, r if scale is not None else None, c0, c1)
             inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
-            _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), c0, c1,
-                      ptr(inv), stream_ptr())
+            rc = torch.empty((nr, 4), dtype=torch.float64, device="cuda")
+            _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]),
+                      ptr(scale), c0, c1, ptr(inv), ptr(rc), stream_ptr())
             tx = torch.from_numpy(x).cuda()
-            _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(dev[0]), ptr(dev[2]),
-                      ptr(scale), c1, stream_ptr())
+            _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(rc), stream_ptr())
             assert_close(tx.cpu().numpy(), want, 1e-13, f"factored tridiagonal solve c0={c0}")
         assert s.plan.r_inv_pivots
     else:
@@ -638,11 +638,11 @@ def test_factored_tridiagonal_column_blocks(K, nr, nz):
     want = fd.thomas_host(x, sub, diag, sup, lam, r, 0.0, 1.0)
     dev = [torch.from_numpy(a).cuda() for a in (sub, diag, sup, lam, r)]
     inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
-    _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), 0.0, 1.0,
-              ptr(inv), stream_ptr())
+    rc = torch.empty((nr, 4), dtype=torch.float64, device="cuda")
+    _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), ptr(dev[4]), 0.0,
+              1.0, ptr(inv), ptr(rc), stream_ptr())
     tx = torch.from_numpy(x).cuda()
-    _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(dev[0]), ptr(dev[2]), ptr(dev[4]), 1.0,
-              stream_ptr())
+    _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(rc), stream_ptr())
     assert_close(tx.cpu().numpy(), want, 1e-12, f"factored sweeps {nr}x{nz}")
 
 

@@ -18,11 +18,11 @@ x = rng.standard_normal((nr, nz))
 want = fd.thomas_host(x, sub, diag, sup, lam, r, 0.0, 1.0)
 dev = [torch.from_numpy(a).cuda() for a in (sub, diag, sup, lam, r)]
 inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
-_lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), 0.0, 1.0, ptr(inv),
-          stream_ptr())
+rc = torch.empty((nr, 4), dtype=torch.float64, device="cuda")
+_lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), ptr(dev[4]), 0.0, 1.0,
+          ptr(inv), ptr(rc), stream_ptr())
 tx = torch.from_numpy(x).cuda()
-_lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(dev[0]), ptr(dev[2]), ptr(dev[4]), 1.0,
-          stream_ptr())
+_lib.call("axb_tridiag_solve_factored", nr, nz, ptr(tx), nz, ptr(inv), ptr(rc), stream_ptr())
 torch.cuda.synchronize()
 got = tx.cpu().numpy()
 print(nr, nz, "rel err", np.abs(got - want).max() / np.abs(want).max())
