@@ -246,7 +246,7 @@ def run_gpu_arm(args, nr, nz):
     if rank == 0:
         sampler.start()
     # ---- timed region: exactly K steps, device-resident
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + getattr(stepper, "launches_replayed", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     probes = []
     e0.record()
@@ -259,7 +259,7 @@ def run_gpu_arm(args, nr, nz):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + getattr(stepper, "launches_replayed", 0) - launches0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -14,6 +14,7 @@
 // them all, __syncthreads, then writes its radix-16 (last pass: radix 2/4/8) butterflies to the
 // auto-sort positions.  Twiddles come from exactly rounded host tables.
 #include <math.h>
+#include <stdlib.h>
 
 #include "axb_common.cuh"
 
@@ -287,6 +288,252 @@ __global__ void __launch_bounds__(512)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for M = 2 * 16^P (N = 64, 1024, 16384): the 16 points a thread owns stay
+// in registers from pass to pass and shared memory is only the exchange medium -- real parts
+// first, then imaginary parts, so the exchange buffer is half a row.  The freed shared memory
+// holds the NEXT row, fetched by a bulk async copy (TMA, mbarrier complete_tx) while the current one
+// is transformed: the HBM read is off the critical path.  The last radix-2 stage of the FFT is
+// folded into the untangling step (DCT-II) / the output step (DCT-III), which then work on
+// index quadruples {k, k + M/2, M/2 - k, M - k}.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pd(int p) { return p + (p >> 4); }
+__device__ __forceinline__ unsigned rr_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rr_mb_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "RR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra RR_DONE;\n"
+      "bra RR_WAIT;\n"
+      "RR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// untangle one k (1 <= k <= M/2): zk = Z[k], zm = Z[M - k], q = exp(-i pi k / 2N)
+__device__ __forceinline__ void dct2_emit(double* __restrict__ X, int k, int M, int N, double2 zk, double2 zm, double2 q,
+                                          double scale) {
+  const double ex = 0.5 * (zk.x + zm.x), ey = 0.5 * (zk.y - zm.y);
+  const double2 d = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y + zm.y));
+  const double2 qm = make_double2(RH * (q.x - q.y), -RH * (q.x + q.y));
+  const double2 q2 = cmul(q, q);
+  const double2 p = cmul(cmul(q2, q2), d);
+  const double2 vk = make_double2(ex + p.y, ey - p.x);
+  const double2 vm = make_double2(ex - p.y, -ey - p.x);
+  const double2 a = cmul(q, vk), b = cmul(qm, vm);
+  X[k] = a.x * scale;
+  X[N - k] = -a.y * scale;
+  X[M - k] = b.x * scale;
+  X[M + k] = -b.y * scale;
+}
+// inverse of the above: spectrum entries a[k], a[N-k], a[M-k], a[M+k] -> Z[k], Z[M-k] (stored swapped)
+__device__ __forceinline__ void dct3_pair(double ak, double ank, double amk, double apk, double2 qk, double2& zk,
+                                          double2& zm) {
+  const double2 qm = make_double2(RH * (qk.x - qk.y), -RH * (qk.x + qk.y));
+  const double2 q2 = cmul(qk, qk);
+  const double2 bk = cmul(make_double2(qk.x, -qk.y), make_double2(0.5 * ak, -0.5 * ank));
+  const double2 bm = cmul(make_double2(qm.x, -qm.y), make_double2(0.5 * amk, -0.5 * apk));
+  const double sx = bk.x + bm.x, sy = bk.y - bm.y;
+  const double2 dd = make_double2(bk.x - bm.x, bk.y + bm.y);
+  const double2 wn = cmul(q2, q2);
+  const double2 q = cmul(make_double2(wn.x, -wn.y), dd);
+  zk = make_double2(sy + q.x, sx - q.y);
+  zm = make_double2(-sy + q.x, sx + q.y);
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(512, 1)
+    k_dct_rows_rr(int rows, int N, int logM, int rpc, const double* __restrict__ src, long long ld_src,
+                  double* __restrict__ dst, long long ld_dst, const double2* __restrict__ tabs, double scale0,
+                  double scale) {
+  extern __shared__ __align__(128) unsigned char rr_smem[];
+  const int M = N >> 1, H = M >> 1, T = M >> 4;
+  const int rl = threadIdx.x >> (logM - 4), j = threadIdx.x - rl * T;
+  const int EXS = M + (M >> 4) + 16;                                   // doubles per row of the exchange buffer
+  double* stage_all = reinterpret_cast<double*>(rr_smem);
+  double* ex_all = stage_all + (size_t)rpc * N;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(ex_all + (size_t)rpc * EXS);
+  const double* st = stage_all + (size_t)rl * N;
+  double* ex = ex_all + (size_t)rl * EXS;
+  const Tabs tb = split_tabs(tabs, M);
+  const int P = (logM - 1) >> 2;                                       // radix-16 passes
+  const unsigned bar_a = rr_u32(bar);
+
+  auto issue = [&](int rb) {                                           // thread 0: fetch row block rb
+    const int r0 = rb * rpc;
+    const int nl = min(rpc, rows - r0);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_a), "r"(nl * N * 8) : "memory");
+    for (int q = 0; q < nl; ++q) {
+      const double* g = src + (long long)(r0 + q) * ld_src;
+      const unsigned d = rr_u32(stage_all + (size_t)q * N);
+      for (int c = 0; c < N * 8; c += 32768) {                         // <= 32 KB per copy
+        const int bytes = min(32768, N * 8 - c);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d + c),
+            "l"(reinterpret_cast<const char*>(g) + c), "r"(bytes), "r"(bar_a)
+            : "memory");
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_a), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (blockIdx.x * rpc < rows) issue(blockIdx.x);
+  }
+  __syncthreads();
+
+  int it = 0;
+  for (int rb = blockIdx.x; rb * rpc < rows; rb += gridDim.x, ++it) {
+    const int row = rb * rpc + rl;
+    const bool live = row < rows;
+    rr_mb_wait(bar_a, it & 1);
+    double2 v[16];
+    double2 mir[8];
+    if (!INV) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int n = j + t * T;                                       // < M/2
+        v[t] = make_double2(st[4 * n], st[4 * n + 2]);
+      }
+#pragma unroll
+      for (int t = 8; t < 16; ++t) {
+        const int n = M - 1 - (j + t * T);                             // mirrored half
+        v[t] = make_double2(st[4 * n + 3], st[4 * n + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int k = j + t * T;                                       // < M/2
+        if (k == 0) {
+          const double a0 = st[0], am = st[M] * RH;
+          v[0] = make_double2(a0 - am, a0 + am);                       // Z[0], stored swapped (im, re)
+          double2 dummy;
+          dct3_pair(st[H], st[N - H], st[M - H], st[M + H], make_double2(0.92387953251128675613, -0.38268343236508977173),
+                    mir[0], dummy);                                    // Z[M/2]
+        } else {
+          dct3_pair(st[k], st[N - k], st[M - k], st[M + k], tb.Q[k], v[t], mir[t]);
+        }
+      }
+    }
+    __syncthreads();                                                   // the staged rows have been consumed
+    if (threadIdx.x == 0 && (rb + (int)gridDim.x) * rpc < rows) issue(rb + gridDim.x);
+    if (INV) {
+      // Z[M - k] belongs to the thread that owns slot (M - k) / T of butterfly (M - k) % T
+      double2* ex2 = reinterpret_cast<double2*>(ex);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int k = j + t * T;
+        const int np = (k == 0) ? H : M - k;
+        ex2[((np >> (logM - 4)) - 8) * T + (np & (T - 1))] = mir[t];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[8 + u] = ex2[u * T + j];
+      __syncthreads();
+    }
+    // ---- P radix-16 Stockham passes; outputs of pass p sit at base + t * Ns
+    int Ns = 1, base = j * 16;
+#pragma unroll 1
+    for (int p = 0; p < P; ++p) {
+      const int jm = j & (Ns - 1);
+      if (Ns > 1) {
+        const int step = jm * (T >> (4 * p));
+        double2 wa[4], wb[4];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { wb[q] = tb.M[q * step]; wa[q] = tb.M[4 * q * step]; }
+#pragma unroll
+        for (int t = 1; t < 16; ++t) {
+          const int a = t >> 2, c = t & 3;
+          const double2 w = (a == 0) ? wb[c] : (c == 0 ? wa[a] : cmul(wa[a], wb[c]));
+          v[t] = cmul(v[t], w);
+        }
+      }
+      dft<16>(v);
+      base = (j - jm) * 16 + jm;
+      if (p + 1 < P) {                                                 // exchange into the next pass' layout
+#pragma unroll
+        for (int t = 0; t < 16; ++t) ex[pd(base + t * Ns)] = v[t].x;
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t].x = ex[pd(j + t * T)];
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) ex[pd(base + t * Ns)] = v[t].y;
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t].y = ex[pd(j + t * T)];
+        __syncthreads();
+        Ns <<= 4;
+      }
+    }
+    // ---- last exchange: quadruples for the folded radix-2 stage
+    double2 e0 = make_double2(0.0, 0.0), eh = make_double2(0.0, 0.0);
+    const int off = INV ? 0 : 1;                                       // DCT-II quads start at k = 1
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) ex[pd(base + t * Ns)] = half ? v[t].y : v[t].x;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = off + j + i * T;
+        const int hk = INV ? H - 1 - k : H - k, mk = INV ? M - 1 - k : M - k;
+        const double r0 = ex[pd(k)], r1 = ex[pd(k + H)], r2 = ex[pd(hk)], r3 = ex[pd(mk)];
+        if (half) { v[4 * i].y = r0; v[4 * i + 1].y = r1; v[4 * i + 2].y = r2; v[4 * i + 3].y = r3; }
+        else { v[4 * i].x = r0; v[4 * i + 1].x = r1; v[4 * i + 2].x = r2; v[4 * i + 3].x = r3; }
+      }
+      if (!INV && j == 0) {
+        if (half) { e0.y = ex[0]; eh.y = ex[pd(H)]; }
+        else { e0.x = ex[0]; eh.x = ex[pd(H)]; }
+      }
+      __syncthreads();
+    }
+    if (live) {
+      double* out = dst + (long long)row * ld_dst;
+      if (!INV) {
+        if (j == 0) {
+          const double2 z0 = cadd(e0, eh), zh = csub(e0, eh);
+          out[0] = (z0.x + z0.y) * scale0;
+          out[M] = (z0.x - z0.y) * RH * scale;
+          dct2_emit(out, H, M, N, zh, zh, make_double2(0.92387953251128675613, -0.38268343236508977173), scale);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = 1 + j + i * T;                                 // 1 .. M/4
+          const double2 w = tb.M[k];
+          const double2 wb = cmul(w, v[4 * i + 1]);
+          const double2 cwd = cmul(make_double2(w.x, -w.y), v[4 * i + 3]);
+          const double2 z_k = cadd(v[4 * i], wb), z_kh = csub(v[4 * i], wb);          // Z[k], Z[k + M/2]
+          const double2 z_hk = csub(v[4 * i + 2], cwd), z_mk = cadd(v[4 * i + 2], cwd);   // Z[M/2 - k], Z[M - k]
+          const double2 q = tb.Q[k];
+          // exp(-i pi (M/2 - k) / 2N) = exp(-i pi / 8) conj(q)
+          const double2 q2 = cmul(make_double2(0.92387953251128675613, -0.38268343236508977173),
+                                  make_double2(q.x, -q.y));
+          dct2_emit(out, k, M, N, z_k, z_mk, q, scale);
+          dct2_emit(out, H - k, M, N, z_hk, z_kh, q2, scale);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = j + i * T;                                     // 0 .. M/4 - 1
+          const int n2 = H - 1 - n;
+          const double2 wb = cmul(tb.M[n], v[4 * i + 1]);
+          const double2 wd = cmul(tb.M[n2], v[4 * i + 3]);
+          const double2 z_n = cadd(v[4 * i], wb), z_nh = csub(v[4 * i], wb);          // z[n], z[n + M/2]
+          const double2 z_c = cadd(v[4 * i + 2], wd), z_m = csub(v[4 * i + 2], wd);   // z[M/2-1-n], z[M-1-n]
+          // stored swapped: (.y, .x) = (re, im)
+          *reinterpret_cast<double2*>(out + 4 * n) = make_double2(z_n.y, z_m.x);
+          *reinterpret_cast<double2*>(out + 4 * n + 2) = make_double2(z_n.x, z_m.y);
+          *reinterpret_cast<double2*>(out + 4 * n2) = make_double2(z_c.y, z_nh.x);
+          *reinterpret_cast<double2*>(out + 4 * n2 + 2) = make_double2(z_c.x, z_nh.y);
+        }
+      }
+    }
+  }
+}
+
 int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -313,6 +560,35 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
     cudaFuncSetAttribute(k_dct2_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_dct3_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_dct3_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  static int rr_off = -1;
+  if (rr_off < 0) rr_off = getenv("AXB_DCT_SMEM") ? 1 : 0;
+  if (vec && !rr_off && ((ilog2(M) - 1) % 4 == 0)) {
+    // register-resident kernel with the next row prefetched by TMA
+    int rr_rpc = 1;
+    while (rr_rpc * T < 128) rr_rpc *= 2;
+    const size_t rr_bytes = ((size_t)rr_rpc * N + (size_t)rr_rpc * (M + (M >> 4) + 16)) * sizeof(double) + 16;
+    static bool rr_once = false;
+    if (!rr_once) {
+      cudaFuncSetAttribute(k_dct_rows_rr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_dct_rows_rr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      rr_once = true;
+    }
+    const int rr_blocks = (rows + rr_rpc - 1) / rr_rpc;
+    int rr_res = (int)((227u * 1024u) / (rr_bytes + 1024));
+    const int by_regs = 512 / (rr_rpc * T);                 // 128 registers per thread
+    if (rr_res > by_regs) rr_res = by_regs;
+    if (rr_res < 1) rr_res = 1;
+    const int rr_grid = rr_blocks < sms * rr_res ? rr_blocks : sms * rr_res;
+    const double2* tbp = reinterpret_cast<const double2*>(tabs);
+    if (!inverse)
+      k_dct_rows_rr<false><<<rr_grid, rr_rpc * T, rr_bytes, st>>>(rows, N, ilog2(M), rr_rpc, src, ld_src, dst, ld_dst,
+                                                                   tbp, scale0, scale);
+    else
+      k_dct_rows_rr<true><<<rr_grid, rr_rpc * T, rr_bytes, st>>>(rows, N, ilog2(M), rr_rpc, src, ld_src, dst, ld_dst,
+                                                                  tbp, scale0, scale);
+    AXB_LAUNCHED();
+    return (int)cudaGetLastError();
   }
   const int per_sm = (int)((227u * 1024u) / (smem + 1024));
   const int resident = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);

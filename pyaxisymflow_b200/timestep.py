@@ -78,6 +78,8 @@ class RigidFlowStepper:
                   stream_ptr())
         self._graph = None
         self._use_graph = use_graph
+        self.graph_launches = 0          # kernels inside the captured step
+        self.launches_replayed = 0       # kernels launched through graph replays so far
 
     # -- one step, enqueued on the current stream ---------------------------------------------
     def _enqueue(self, probe=None):
@@ -130,11 +132,14 @@ class RigidFlowStepper:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 self._graph = torch.cuda.CUDAGraph()
+                before = _lib.launch_count()
                 with torch.cuda.graph(self._graph, stream=side):
                     self._enqueue()
+                self.graph_launches = _lib.launch_count() - before    # kernels one replay launches
                 n -= 1
             for _ in range(n):
                 self._graph.replay()
+                self.launches_replayed += self.graph_launches
         else:
             for _ in range(n):
                 self._enqueue()
