@@ -323,11 +323,28 @@ int axb_dgemm(int M, int N, int K, const double* A, int64_t lda, const double* B
  * (cp.async) variant.  Both feed the same DMMA main loop; tests exercise both. */
 int axb_dgemm_set_path(int force_ldgsts);
 
+/* ---- transposes over peer memory: rank `me` stores, for every peer q < P, the block
+ *      src[q * src_peer_stride + i * ld_src + c]  (i < rows, c < cols)  into
+ *      peer_ptrs[q][dst_off + i * ld_dst + c],
+ *      peer_ptrs[q] being rank q's destination buffer mapped into this process (NVLink peer memory).
+ *      slab -> rows: src_peer_stride = (nr/P) * nzl, ld_src = nzl, dst_off = me * nzl, ld_dst = nz;
+ *      rows -> slab: src_peer_stride = nzl, ld_src = nz, dst_off = me * (nr/P) * nzl, ld_dst = nzl.
+ *      The caller synchronises the ranks (a device-side barrier) before the destinations are read. */
+#define AXB_MAX_PEERS 16
+int axb_peer_block_put(int P, int me, const uint64_t* peer_ptrs, int64_t dst_off, int64_t ld_dst, const double* src,
+                       int64_t src_peer_stride, int64_t ld_src, int rows, int cols, axb_stream_t s);
+
 /* ---- z-slab plumbing (multi-GPU): pack / unpack `width` halo columns of a field ----------- */
 int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
                   axb_stream_t s);
 int axb_halo_unpack(const axb_grid_t* g, double* f, const double* buf_left, const double* buf_right,
                     int width, double shift, axb_stream_t s);
+/* the same exchange over peer memory: the first / last `width` owned columns of f are stored into the right
+ * halo of left_peer_field (+ shift) / the left halo of right_peer_field (- shift), the neighbours' copies of
+ * the same field mapped into this process (NULL = no neighbour on that side).  The caller synchronises the
+ * ranks before the halos are read. */
+int axb_halo_put(const axb_grid_t* g, const double* f, double* left_peer_field, double* right_peer_field, int width,
+                 double shift, axb_stream_t s);
 /* local (nr x nz_local) slab  <->  P blocks of (nr/P x nz_local) for the all-to-all transpose */
 int axb_slab_to_blocks(int nr, int nzl, int64_t ld, int P, const double* slab, double* blocks,
                        axb_stream_t s);

@@ -97,6 +97,8 @@ _SIGNATURES = {
     "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],
     "axb_slab_to_blocks": [_I, _I, c_int64, _I, _P, _P, _S],
     "axb_blocks_to_rows": [_I, _I, _I, _P, _P, c_int64, _S],
+    "axb_halo_put": [_G, _P, _P, _P, _I, _D, _S],
+    "axb_peer_block_put": [_I, _I, _P, c_int64, c_int64, _P, c_int64, c_int64, _I, _I, _S],
     "axb_rows_to_blocks": [_I, _I, _I, _P, c_int64, _P, _S],
     "axb_blocks_to_slab": [_I, _I, c_int64, _I, _P, _P, _S],
 }

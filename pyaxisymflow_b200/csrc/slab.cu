@@ -28,6 +28,18 @@ __global__ void k_halo_unpack(GridD g, double* __restrict__ f, const double* __r
   if (br) row[g.ku1 + c] = br[idx] + shift;
 }
 
+// halo exchange over peer memory: my first / last `w` owned columns go straight into the right halo of the
+// left neighbour / the left halo of the right neighbour (all slabs share one layout)
+__global__ void k_halo_put(GridD g, const double* __restrict__ f, double* __restrict__ left_peer,
+                           double* __restrict__ right_peer, int w, double shift) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nr * w) return;
+  const int j = idx / w, c = idx % w;
+  const long long row = (long long)j * g.ld;
+  if (left_peer) left_peer[row + g.ku1 + c] = f[row + g.ku0 + c] + shift;
+  if (right_peer) right_peer[row + g.ku0 - w + c] = f[row + g.ku1 - w + c] - shift;
+}
+
 // slab (nr x nzl, pitch ld)  ->  P contiguous blocks, block q = rows [q*nrl, (q+1)*nrl) x nzl
 __global__ void k_slab_to_blocks(int nr, int nzl, long long ld, const double* __restrict__ slab,
                                  double* __restrict__ blocks) {
@@ -57,6 +69,31 @@ __global__ void k_blocks_to_slab(int nr, int nzl, long long ld, const double* __
 
 }  // namespace
 
+// ---- transposes over peer memory (NVLink): every rank stores its blocks straight into the peers'
+// destination buffers in their final layout, so the all-to-all needs no pack / unpack passes and no
+// library call.  peers.p[q] is rank q's destination buffer (mapped into this process).
+struct PeerPtrs {
+  double* p[AXB_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256)
+    k_peer_block_put(PeerPtrs peers, int P, int me, long long dst_off, long long ld_dst, const double* __restrict__ src,
+                     long long src_peer_stride, long long ld_src, int rows, int cols, bool vec) {
+  const int q = (me + 1 + blockIdx.x) % P;                    // peers interleaved: all links busy at once
+  const int i = blockIdx.y;
+  const double* s = src + (long long)q * src_peer_stride + (long long)i * ld_src;
+  double* d = peers.p[q] + dst_off + (long long)i * ld_dst;
+  const int c0 = (blockIdx.z * 256 + threadIdx.x) * 4;
+  if (c0 >= cols) return;
+  if (vec && c0 + 3 < cols) {
+    const double2 a = *reinterpret_cast<const double2*>(s + c0);
+    const double2 b = *reinterpret_cast<const double2*>(s + c0 + 2);
+    *reinterpret_cast<double2*>(d + c0) = a;
+    *reinterpret_cast<double2*>(d + c0 + 2) = b;
+  } else {
+    for (int c = c0; c < cols && c < c0 + 4; ++c) d[c] = s[c];
+  }
+}
+
 extern "C" {
 
 int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
@@ -81,6 +118,19 @@ int axb_halo_unpack(const axb_grid_t* g, double* f, const double* buf_left, cons
   if ((buf_left && d.ku0 < width) || (buf_right && d.ku1 + width > d.nz)) return AXB_EINVAL;
   const int n = d.nr * width;
   k_halo_unpack<<<(n + 255) / 256, 256, 0, s>>>(d, f, buf_left, buf_right, width, shift);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_halo_put(const axb_grid_t* g, const double* f, double* left_peer_field, double* right_peer_field, int width,
+                 double shift, axb_stream_t s) {
+  if (!f || width < 1) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  if (d.ku0 < width || d.ku1 + width > d.nz || d.ku1 - d.ku0 < width) return AXB_EINVAL;
+  const int n = d.nr * width;
+  k_halo_put<<<(n + 255) / 256, 256, 0, s>>>(d, f, left_peer_field, right_peer_field, width, shift);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
@@ -114,4 +164,19 @@ int axb_blocks_to_slab(int nr, int nzl, int64_t ld, int P, const double* blocks,
   AXB_RETURN_LAST();
 }
 
+int axb_peer_block_put(int P, int me, const uint64_t* peer_ptrs, int64_t dst_off, int64_t ld_dst, const double* src,
+                       int64_t src_peer_stride, int64_t ld_src, int rows, int cols, axb_stream_t s) {
+  if (P < 1 || P > AXB_MAX_PEERS || me < 0 || me >= P || !peer_ptrs || !src || rows < 1 || cols < 1) return AXB_EINVAL;
+  PeerPtrs pp;
+  bool vec = axb_al16(src) && (ld_src % 2 == 0) && (ld_dst % 2 == 0) && (dst_off % 2 == 0) && (src_peer_stride % 2 == 0);
+  for (int q = 0; q < P; ++q) {
+    pp.p[q] = reinterpret_cast<double*>(peer_ptrs[q]);
+    if (!pp.p[q]) return AXB_EINVAL;
+    vec = vec && axb_al16(pp.p[q]);
+  }
+  k_peer_block_put<<<dim3(P, rows, (cols + 1023) / 1024), 256, 0, (cudaStream_t)s>>>(pp, P, me, dst_off, ld_dst, src,
+                                                                                    src_peer_stride, ld_src, rows, cols, vec);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
 }  // extern "C"

@@ -22,6 +22,7 @@ The r-direction (axis reflection, 1/r terms) is never split.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -78,6 +79,31 @@ class SlabComm:
     def __init__(self, layout, group=None):
         self.L, self.group = layout, group
         self._bufs = {}
+        self._peer_fields = {}          # data_ptr -> (symmetric-memory handle, peer base pointers)
+
+    # -- fields in peer-mapped memory: their halos are exchanged by direct NVLink stores -----------
+    def symmetric_field(self, shape):
+        """zero-initialised float64 field whose copies on all ranks are mapped into every process"""
+        import torch.distributed._symmetric_memory as symm
+
+        t = symm.empty(tuple(shape), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+        t.zero_()
+        h = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        if h.buffer_ptrs[self.L.rank] != t.data_ptr():
+            raise RuntimeError("symmetric buffer does not start at the tensor's data pointer")
+        self._peer_fields[t.data_ptr()] = (h, list(h.buffer_ptrs))
+        return t
+
+    def _exchange_peer(self, fields, width, dx):
+        L = self.L
+        g = L.grid(dx)
+        h = None
+        for f in fields:
+            h, ptrs = self._peer_fields[f.data_ptr()]
+            _call("axb_halo_put", ctypes.byref(g), ptr(f),
+                  ctypes.c_void_p(ptrs[L.left]) if L.left is not None else None,
+                  ctypes.c_void_p(ptrs[L.right]) if L.right is not None else None, width, 0.0, stream_ptr())
+        h.barrier(channel=1)             # one device-side barrier closes the whole batch
 
     # -- halos ----------------------------------------------------------------------------------
     def _buffers(self, key, n, like):
@@ -92,6 +118,8 @@ class SlabComm:
         L = self.L
         if L.world == 1 and not L.periodic:
             return
+        if L.world > 1 and fields and all(f.is_cuda and f.data_ptr() in self._peer_fields for f in fields):
+            return self._exchange_peer(fields, width, dx)
         n = L.nr * width
         ops, pending = [], []
         for i, f in enumerate(fields):
@@ -152,6 +180,43 @@ class SlabComm:
         return t
 
 
+class PeerTranspose:
+    """slab <-> rows transposes through peer-mapped (symmetric) buffers: every rank stores its blocks
+    straight into the destination buffers of its peers over NVLink (``axb_peer_block_put``) and a
+    device-side barrier closes the exchange -- no pack / unpack passes, no collective library call."""
+
+    def __init__(self, layout, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        L = self.L = layout
+        g = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.slab = symm.empty((L.nr, L.nzl), dtype=torch.float64, device=dev)
+        self.rows = symm.empty((L.nrl, L.nz), dtype=torch.float64, device=dev)
+        self.h_slab = symm.rendezvous(self.slab, g)
+        self.h_rows = symm.rendezvous(self.rows, g)
+        if self.h_slab.buffer_ptrs[L.rank] != self.slab.data_ptr() or self.h_rows.buffer_ptrs[L.rank] != self.rows.data_ptr():
+            raise RuntimeError("symmetric buffers do not start at the tensors' data pointers")
+        self.slab_ptrs = (ctypes.c_uint64 * L.world)(*self.h_slab.buffer_ptrs)
+        self.rows_ptrs = (ctypes.c_uint64 * L.world)(*self.h_rows.buffer_ptrs)
+
+    def slab_to_rows(self, src):
+        """(nr x nzl) local slab (any pitch) -> the (nrl x nz) row buffers of all ranks; returns this rank's"""
+        L = self.L
+        _call("axb_peer_block_put", L.world, L.rank, self.rows_ptrs, L.rank * L.nzl, L.nz, ptr(src),
+              L.nrl * src.stride(0), src.stride(0), L.nrl, L.nzl, stream_ptr())
+        self.h_rows.barrier(channel=0)
+        return self.rows
+
+    def rows_to_slab(self, src):
+        """(nrl x nz) local rows -> the (nr x nzl) slab buffers of all ranks; returns this rank's"""
+        L = self.L
+        _call("axb_peer_block_put", L.world, L.rank, self.slab_ptrs, L.rank * L.nrl * L.nzl, L.nzl, ptr(src),
+              L.nzl, src.stride(0), L.nrl, L.nzl, stream_ptr())
+        self.h_slab.barrier(channel=0)
+        return self.slab
+
+
 def _cuda_gemm(C, A, B, scale_m=None, scale_n=None, c0=0.0, c1=1.0):
     """C = A @ B (+ fused spectral scaling) through axb_dgemm; operands may be strided row views."""
     M, K = A.shape
@@ -207,8 +272,9 @@ class SlabFdSolver:
                           r solves of this rank's z-modes -> all-to-all -> backward z transform -> all-to-all
     ``gemm`` / ``fold`` / ``dct`` / ``tri`` are injectable so the plumbing runs on CPU in the gloo tests."""
 
-    def __init__(self, layout, comm, factors, gemm=None, fold=None, dct=None, tri=None):
+    def __init__(self, layout, comm, factors, gemm=None, fold=None, dct=None, tri=None, peer=None):
         self.L, self.comm, self.f = layout, comm, factors
+        self.peer = peer
         self.gemm = gemm or _cuda_gemm
         self.fold = fold or _cuda_fold
         self.dct = dct or _cuda_dct
@@ -223,21 +289,23 @@ class SlabFdSolver:
         else:
             self.lam_r_local = factors["lam_r"][L.r_begin:L.r_begin + L.nrl].contiguous()
 
-    def _z_transform(self, inverse):
-        """rows_a -> rows_a (GEMM leaves, through rows_b) or rows_a -> rows_b (DCT); returns the result buffer"""
+    def _z_transform(self, inverse, rows_in=None):
+        """z transform of whole rows: rows_in (default rows_a; folded in place on the GEMM-leaf path) ->
+        rows_b, which is returned"""
         f = self.f
+        rows_a = self.rows_a if rows_in is None else rows_in
         if f.get("zfft") is not None:
-            self.dct(self.rows_b, self.rows_a, f["zfft"]["tables"], inverse)
+            self.dct(self.rows_b, rows_a, f["zfft"]["tables"], inverse)
             return self.rows_b
         zs = f.get("zsplit")
         if zs is None:
-            self.gemm(self.rows_b, self.rows_a, f["Rzb"] if inverse else f["Rz"])
+            self.gemm(self.rows_b, rows_a, f["Rzb"] if inverse else f["Rz"])
             return self.rows_b
         if not inverse:
             for n in zs["fold_len"]:
-                self.fold(self.rows_a, n, False)
+                self.fold(rows_a, n, False)
         for n, off, F in zip(zs["leaf_n"], zs["leaf_off"], zs["bwd"] if inverse else zs["fwd"]):
-            self.gemm(self.rows_b[:, off:off + n], self.rows_a[:, off:off + n], F)
+            self.gemm(self.rows_b[:, off:off + n], rows_a[:, off:off + n], F)
         if inverse:
             for n in reversed(zs["fold_len"]):
                 self.fold(self.rows_b, n, True)
@@ -245,6 +313,14 @@ class SlabFdSolver:
 
     def _solve_tridiagonal(self, psi_slab, rhs_slab):
         L = self.L
+        if self.peer is not None:                                                 # transposes over peer memory
+            pt = self.peer
+            spec = self._z_transform(False, pt.slab_to_rows(L.owned(rhs_slab)))
+            modes = pt.rows_to_slab(spec)
+            self.tri(modes)
+            out = self._z_transform(True, pt.slab_to_rows(modes))
+            L.owned(psi_slab).copy_(pt.rows_to_slab(out))
+            return
         self.t_slab.copy_(L.owned(rhs_slab))
         self.comm.slab_to_rows(self.t_slab, self.rows_a)                          # all-to-all #1
         spec = self._z_transform(False)
@@ -320,9 +396,21 @@ class SlabRigidFlowStepper:
         def field():
             return torch.zeros((nr, L.nzs), dtype=torch.float64, device="cuda")
 
-        self.vorticity, self.psi = field(), field()
-        self.u_z, self.u_r, self.u_z_upen, self.u_r_upen = field(), field(), field(), field()
-        self.char_func, self._tmp, self._w2 = field(), field(), field()
+        # the five fields whose halos travel live in peer-mapped memory when the box allows it
+        xfield, self.peer_halos = field, False
+        if world > 1 and not os.environ.get("AXB_SLAB_NCCL"):
+            try:
+                probe = self.comm.symmetric_field((nr, L.nzs))
+                xfield, self.peer_halos = (lambda: self.comm.symmetric_field((nr, L.nzs))), True
+                self.vorticity = probe
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[pyaxisymflow_b200] peer-memory halos unavailable ({e!r}); using NCCL send/recv", flush=True)
+        if not self.peer_halos:
+            self.vorticity = field()
+        self.psi = xfield()
+        self.u_z, self.u_r, self.u_z_upen, self.u_r_upen = xfield(), field(), field(), field()
+        self.char_func, self._tmp, self._w2 = field(), xfield(), xfield()
         self.state = torch.zeros(8, dtype=torch.float64, device="cuda")
         self.grid = L.grid(dx)
         # velocity is also evaluated on one halo column each side (needs the width-2 psi halo)
@@ -339,7 +427,15 @@ class SlabRigidFlowStepper:
             z_method = "gemm"
         self.factors = build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, self.nz, dx, basis,
                                      device="cuda", r_method=r_method, z_method=z_method)
-        self.solver = SlabFdSolver(L, self.comm, self.factors)
+        self.peer = None
+        if self.factors.get("tri") is not None and world > 1 and not os.environ.get("AXB_SLAB_NCCL"):
+            try:
+                self.peer = PeerTranspose(L, group)
+            except Exception as e:  # noqa: BLE001  (no peer mapping on this box: NCCL all-to-all instead)
+                if rank == 0:
+                    print(f"[pyaxisymflow_b200] peer-memory transposes unavailable ({e!r}); using NCCL all-to-all",
+                          flush=True)
+        self.solver = SlabFdSolver(L, self.comm, self.factors, peer=self.peer)
 
     def seed_vorticity(self, seed=0, amplitude=1.0):
         """same global field as RigidFlowStepper.seed_vorticity, cut to this rank's slab"""
@@ -408,8 +504,9 @@ class SlabRigidFlowStepper:
         zs = self.factors.get("zsplit")
         n = 0 if zs is None else len(zs["leaf_n"])
         if self.factors.get("zfft") is not None:
-            return ("per rank: k_dct2_rows / k_dct3_rows on r-slabs, k_tri_sweep on this rank's z-modes, "
-                    "4 NCCL all-to-all in between")
+            how = ("4 transposes over NVLink peer memory (k_peer_block_put + device barrier)" if self.peer is not None
+                   else "4 NCCL all-to-all")
+            return ("per rank: k_dct_rows on r-slabs, k_tri_sweep on this rank's z-modes, " + how + " in between")
         if self.factors.get("tri") is not None:
             return (f"per rank: {'2 dense' if zs is None else '2x%d parity-split' % n} k_dgemm_tma z-transforms on "
                     "r-slabs, k_tri_sweep on this rank's z-modes, 4 NCCL all-to-all in between")
