@@ -52,6 +52,13 @@ def test_dirichlet_r_even_nr_is_a_defective_operator():
     assert_close(fd.apply_factors_host(f, rhs), g["stokes_" + BCS[2]], 1e-2, "dirichlet lapack")
     with pytest.raises(ValueError, match="defective"):
         fd.build_factors("stokes", BCS[2], nr, nz, dx, "analytic")
+    # the direct r solve needs no eigenvectors and solves the equation the reference misses
+    t = fd.build_factors("stokes", BCS[2], nr, nz, dx, "analytic", r_method="tridiagonal")
+    psi = fd.apply_factors_host(t, rhs)
+    sub, diag, sup, r = fd.radial_tridiagonal("stokes", BCS[2], nr, dx)
+    res = (fd.dense_from_tridiagonal(sub, diag, sup) @ psi + psi @ fd.dense_axial(*fd.axial_kind("stokes", BCS[2]), nz, dx).T
+           - r[:, None] * rhs)
+    assert np.max(np.abs(res)) <= 1e-9 * np.max(np.abs(r[:, None] * rhs))
     # odd Nr is fine
     f = fd.build_factors("stokes", BCS[2], nr - 1, nz, dx, "analytic")
     h = fd.build_factors("stokes", BCS[2], nr - 1, nz, dx, "lapack")
