@@ -311,14 +311,26 @@ __device__ __forceinline__ void rr_mb_wait(unsigned bar, unsigned parity) {
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// untangle one k (1 <= k <= M/2): zk = Z[k], zm = Z[M - k], q = exp(-i pi k / 2N)
+// Q[k] = exp(-i pi k / 2N), 0 <= k <= M/2, from the shared-memory copy of its first M/8 + 1 entries:
+// Q[M/2 - k] = exp(-i pi / 8) conj(Q[k]),  Q[M/4 - k] = exp(-i pi / 16) conj(Q[k])
+__device__ __forceinline__ double2 q_at(const double2* __restrict__ tq, int k, int M) {
+  const bool r1 = k > (M >> 2);
+  const int k1 = r1 ? (M >> 1) - k : k;
+  const bool r2 = k1 > (M >> 3);
+  const int k2 = r2 ? (M >> 2) - k1 : k1;
+  double2 q = tq[k2];
+  if (r2) q = cmul(make_double2(0.98078528040323044913, -0.19509032201612826785), make_double2(q.x, -q.y));
+  if (r1) q = cmul(make_double2(0.92387953251128675613, -0.38268343236508977173), make_double2(q.x, -q.y));
+  return q;
+}
+
+// untangle one k (1 <= k <= M/2): zk = Z[k], zm = Z[M - k], q = exp(-i pi k / 2N), tn = q^4 = exp(-2 pi i k / N)
 __device__ __forceinline__ void dct2_emit(double* __restrict__ X, int k, int M, int N, double2 zk, double2 zm, double2 q,
-                                          double scale) {
+                                          double2 tn, double scale) {
   const double ex = 0.5 * (zk.x + zm.x), ey = 0.5 * (zk.y - zm.y);
   const double2 d = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y + zm.y));
   const double2 qm = make_double2(RH * (q.x - q.y), -RH * (q.x + q.y));
-  const double2 q2 = cmul(q, q);
-  const double2 p = cmul(cmul(q2, q2), d);
+  const double2 p = cmul(tn, d);
   const double2 vk = make_double2(ex + p.y, ey - p.x);
   const double2 vm = make_double2(ex - p.y, -ey - p.x);
   const double2 a = cmul(q, vk), b = cmul(qm, vm);
@@ -359,6 +371,24 @@ __global__ void __launch_bounds__(512, 1)
   const Tabs tb = split_tabs(tabs, M);
   const int P = (logM - 1) >> 2;                                       // radix-16 passes
   const unsigned bar_a = rr_u32(bar);
+  // on-chip copies of the tables: Q[0 .. M/8] and, per pass p >= 1, the base twiddles w^1 and w^4 of its
+  // 16^p residues (everything else is derived by conjugate reflections, squarings and products)
+  double2* tq = reinterpret_cast<double2*>(bar + 2);
+  double2* tw = tq + (M >> 3) + 1;
+  for (int i = threadIdx.x; i <= (M >> 3); i += blockDim.x) tq[i] = tb.Q[i];
+  {
+    int off = 0;
+    for (int p = 1; p < P; ++p) {
+      const int ns = 1 << (4 * p);
+      for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const int step = i * (T >> (4 * p));
+        tw[off + i] = tb.M[step];
+        tw[off + ns + i] = tb.M[4 * step];
+      }
+      off += 2 * ns;
+    }
+  }
+  const double2 wm1 = tb.M[1];                                         // exp(-2 pi i / M)
 
   auto issue = [&](int rb) {                                           // thread 0: fetch row block rb
     const int r0 = rb * rpc;
@@ -413,7 +443,7 @@ __global__ void __launch_bounds__(512, 1)
           dct3_pair(st[H], st[N - H], st[M - H], st[M + H], make_double2(0.92387953251128675613, -0.38268343236508977173),
                     mir[0], dummy);                                    // Z[M/2]
         } else {
-          dct3_pair(st[k], st[N - k], st[M - k], st[M + k], tb.Q[k], v[t], mir[t]);
+          dct3_pair(st[k], st[N - k], st[M - k], st[M + k], q_at(tq, k, M), v[t], mir[t]);
         }
       }
     }
@@ -434,15 +464,19 @@ __global__ void __launch_bounds__(512, 1)
       __syncthreads();
     }
     // ---- P radix-16 Stockham passes; outputs of pass p sit at base + t * Ns
-    int Ns = 1, base = j * 16;
+    int Ns = 1, base = j * 16, twoff = 0;
 #pragma unroll 1
     for (int p = 0; p < P; ++p) {
       const int jm = j & (Ns - 1);
       if (Ns > 1) {
-        const int step = jm * (T >> (4 * p));
         double2 wa[4], wb[4];
-#pragma unroll
-        for (int q = 1; q < 4; ++q) { wb[q] = tb.M[q * step]; wa[q] = tb.M[4 * q * step]; }
+        wb[1] = tw[twoff + jm];
+        wa[1] = tw[twoff + Ns + jm];
+        wb[2] = cmul(wb[1], wb[1]);
+        wb[3] = cmul(wb[2], wb[1]);
+        wa[2] = cmul(wa[1], wa[1]);
+        wa[3] = cmul(wa[2], wa[1]);
+        twoff += 2 * Ns;
 #pragma unroll
         for (int t = 1; t < 16; ++t) {
           const int a = t >> 2, c = t & 3;
@@ -497,30 +531,39 @@ __global__ void __launch_bounds__(512, 1)
           const double2 z0 = cadd(e0, eh), zh = csub(e0, eh);
           out[0] = (z0.x + z0.y) * scale0;
           out[M] = (z0.x - z0.y) * RH * scale;
-          dct2_emit(out, H, M, N, zh, zh, make_double2(0.92387953251128675613, -0.38268343236508977173), scale);
+          dct2_emit(out, H, M, N, zh, zh, make_double2(0.92387953251128675613, -0.38268343236508977173),
+                    make_double2(0.0, -1.0), scale);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = 1 + j + i * T;                                 // 1 .. M/4
-          const double2 w = tb.M[k];
+          const double2 q = q_at(tq, k, M);
+          const double2 qq = cmul(q, q);
+          const double2 tn = cmul(qq, qq);                              // exp(-2 pi i k / N)
+          const double2 w = cmul(tn, tn);                               // exp(-2 pi i k / M)
           const double2 wb = cmul(w, v[4 * i + 1]);
           const double2 cwd = cmul(make_double2(w.x, -w.y), v[4 * i + 3]);
           const double2 z_k = cadd(v[4 * i], wb), z_kh = csub(v[4 * i], wb);          // Z[k], Z[k + M/2]
           const double2 z_hk = csub(v[4 * i + 2], cwd), z_mk = cadd(v[4 * i + 2], cwd);   // Z[M/2 - k], Z[M - k]
-          const double2 q = tb.Q[k];
-          // exp(-i pi (M/2 - k) / 2N) = exp(-i pi / 8) conj(q)
+          // exp(-i pi (M/2 - k) / 2N) = exp(-i pi / 8) conj(q); its 4th power is -i conj(tn)
           const double2 q2 = cmul(make_double2(0.92387953251128675613, -0.38268343236508977173),
                                   make_double2(q.x, -q.y));
-          dct2_emit(out, k, M, N, z_k, z_mk, q, scale);
-          dct2_emit(out, H - k, M, N, z_hk, z_kh, q2, scale);
+          dct2_emit(out, k, M, N, z_k, z_mk, q, tn, scale);
+          dct2_emit(out, H - k, M, N, z_hk, z_kh, q2, make_double2(-tn.y, -tn.x), scale);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int n = j + i * T;                                     // 0 .. M/4 - 1
           const int n2 = H - 1 - n;
-          const double2 wb = cmul(tb.M[n], v[4 * i + 1]);
-          const double2 wd = cmul(tb.M[n2], v[4 * i + 3]);
+          // exp(-2 pi i n / M) = Q[n]^8; exp(-2 pi i (M/2 - 1 - n) / M) = -conj(exp(-2 pi i (n + 1) / M))
+          const double2 q = q_at(tq, n, M);
+          const double2 qq = cmul(q, q);
+          const double2 q4 = cmul(qq, qq);
+          const double2 wn = cmul(q4, q4);
+          const double2 w1 = cmul(wn, wm1);
+          const double2 wb = cmul(wn, v[4 * i + 1]);
+          const double2 wd = cmul(make_double2(-w1.x, w1.y), v[4 * i + 3]);
           const double2 z_n = cadd(v[4 * i], wb), z_nh = csub(v[4 * i], wb);          // z[n], z[n + M/2]
           const double2 z_c = cadd(v[4 * i + 2], wd), z_m = csub(v[4 * i + 2], wd);   // z[M/2-1-n], z[M-1-n]
           // stored swapped: (.y, .x) = (re, im)
@@ -567,7 +610,10 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
     // register-resident kernel with the next row prefetched by TMA
     int rr_rpc = 1;
     while (rr_rpc * T < 128) rr_rpc *= 2;
-    const size_t rr_bytes = ((size_t)rr_rpc * N + (size_t)rr_rpc * (M + (M >> 4) + 16)) * sizeof(double) + 16;
+    int tw_entries = 0;
+    for (int p = 1; p < (ilog2(M) - 1) / 4; ++p) tw_entries += 2 << (4 * p);
+    const size_t rr_bytes = ((size_t)rr_rpc * N + (size_t)rr_rpc * (M + (M >> 4) + 16)) * sizeof(double) + 16 +
+                            ((size_t)(M >> 3) + 1 + tw_entries) * sizeof(double2);
     static bool rr_once = false;
     if (!rr_once) {
       cudaFuncSetAttribute(k_dct_rows_rr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -185,6 +185,51 @@ class RigidFlowStepper:
         return {"t": st[S_T], "dt": st[S_DT], "umax": st[S_UMAX], "iterations": int(st[S_IT]), "Cd": cd}
 
 
+class HostStepPipeline:
+    """Streams host-resident cases through one :class:`RigidFlowStepper`: every :meth:`submit` does what
+    ``step_host`` does (pinned vorticity + characteristic function in, one step, vorticity out), but the
+    H2D copy of case k+1 and the D2H copy of case k-1 run on their own streams and overlap the step of
+    case k (double-buffered device staging, PCIe is full duplex).  Results are the same as calling
+    ``step_host`` case by case; call :meth:`drain` before reading the last outputs."""
+
+    def __init__(self, stepper):
+        self.st = stepper
+        like = stepper.vorticity
+        self.in_w = [torch.empty_like(like) for _ in range(2)]
+        self.in_c = [torch.empty_like(like) for _ in range(2)]
+        self.out = [torch.empty_like(like) for _ in range(2)]
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ev = lambda: [torch.cuda.Event() for _ in range(2)]  # noqa: E731
+        self.ev_in, self.ev_in_free, self.ev_out, self.ev_out_free = ev(), ev(), ev(), ev()
+        self.k = 0
+
+    def submit(self, vorticity_host, char_func_host, out_host):
+        st, b = self.st, self.k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_in_free[b])          # the step two cases ago has consumed staging b
+            self.in_w[b].copy_(vorticity_host, non_blocking=True)
+            self.in_c[b].copy_(char_func_host, non_blocking=True)
+            self.ev_in[b].record(self.s_in)
+        main.wait_event(self.ev_in[b])
+        st.vorticity.copy_(self.in_w[b])
+        st.char_func.copy_(self.in_c[b])
+        self.ev_in_free[b].record(main)
+        st.step(1)
+        main.wait_event(self.ev_out_free[b])                  # the D2H two cases ago has left out[b]
+        self.out[b].copy_(st.vorticity)
+        self.ev_out[b].record(main)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_out[b])
+            out_host.copy_(self.out[b], non_blocking=True)
+            self.ev_out_free[b].record(self.s_out)
+        self.k += 1
+
+    def drain(self):
+        self.s_out.synchronize()
+        torch.cuda.current_stream().synchronize()
+
+
 class _FieldSet:
     """small helper: float64 CUDA fields of one (nr, nz) grid plus the ctypes grid descriptor"""
 

@@ -658,6 +658,38 @@ def test_rigid_flow_stepper_fft(K):
     assert_close(s.psi.cpu().numpy(), psi, 1e-9, "psi (fft solve)")
 
 
+def test_host_step_pipeline_matches_step_host(K):
+    """the overlapped host pipeline returns what the serial host call returns, case by case"""
+    import torch
+
+    from pyaxisymflow_b200.timestep import HostStepPipeline, RigidFlowStepper
+
+    nz = 128
+    s = RigidFlowStepper(nz)
+    s.seed_vorticity(seed=3)
+    chi = s.char_func.clone()
+    rng = np.random.default_rng(8)
+    cases = [torch.from_numpy(rng.standard_normal((nz // 2, nz)) * 1e-2).pin_memory() for _ in range(5)]
+    hc = chi.cpu().pin_memory()
+    want = []
+    for c in cases:
+        out = torch.empty_like(c).pin_memory()
+        s.step_host(c, hc, out)
+        torch.cuda.synchronize()
+        want.append(out.clone())
+    s2 = RigidFlowStepper(nz)
+    pipe = HostStepPipeline(s2)
+    outs = [torch.empty_like(c).pin_memory() for c in cases]
+    for c, o in zip(cases, outs):
+        pipe.submit(c, hc, o)
+    pipe.drain()
+    # same time step history is not shared (dt depends on the state), so compare the first case exactly
+    # and the others against a fresh serial run with the same history
+    assert torch.equal(outs[0], want[0])
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
+
+
 def test_rigid_flow_stepper_tridiagonal_r(K):
     from pyaxisymflow_b200.timestep import RigidFlowStepper
 
