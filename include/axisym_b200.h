@@ -135,6 +135,11 @@ int axb_diffusion_rk2_stage1(const axb_grid_t* g, double* tmp, const double* w, 
 int axb_diffusion_rk2_stage2(const axb_grid_t* g, double* w, const double* w_src, const double* tmp,
                              const double* r1d, double nu, double dt, const double* dt_dev,
                              axb_stream_t s);
+/* Both stages in one pass over HBM (16 instead of 40 B/pt): w = w_src + nu dt L(tmp), tmp = w_src + nu dt/2
+ * L(w_src) held on chip (row-marching kernels; needs a width-2 halo of w_src on z-slabs).  Same bits as
+ * stage1 followed by stage2.  tmp is only used (as scratch) by the 2-D tiled code path; w != w_src. */
+int axb_diffusion_rk2_fused(const axb_grid_t* g, double* w, const double* w_src, double* tmp, const double* r1d,
+                            double nu, double dt, const double* dt_dev, axb_stream_t s);
 
 /* ---- G-HEAV: kernels/smooth_Heaviside.py:5-14; the _sphere form builds
  *      phi = radius - sqrt((Z-z_cm)^2 + (R-r_cm)^2) in-kernel (flow_past_sphere.py:80-82). -- */

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "axb_set_fixed_val": [_G, _P, _D, _S],
     "axb_diffusion_rk2_stage1": [_G, _P, _P, _P, _D, _D, _P, _S],
     "axb_diffusion_rk2_stage2": [_G, _P, _P, _P, _P, _D, _D, _P, _S],
+    "axb_diffusion_rk2_fused": [_G, _P, _P, _P, _P, _D, _D, _P, _S],
     "axb_smooth_heaviside": [_G, _P, _P, _D, _S],
     "axb_smooth_heaviside_sphere": [_G, _P, _P, _P, _P, _D, _D, _D, _D, _S],
     "axb_vortex_stretching": [_G, _P, _P, _P, _D, _S],

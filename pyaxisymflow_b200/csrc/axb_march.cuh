@@ -9,6 +9,8 @@ int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const do
                    const double* U_dev, const double* r1d, double* sum_out, bool vec, cudaStream_t s);
 int march_diffusion(int stage, const GridD& d, double* out, const double* in, const double* src2, const double* r1d,
                     double nu, double dt, const double* dt_dev, bool vec, cudaStream_t s);
+int march_diffusion_fused(const GridD& d, double* out, const double* in, const double* r1d, double nu, double dt,
+                          const double* dt_dev, bool vec, cudaStream_t s);
 int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, double* out0, double* out1,
                const double* in0, const double* in1, const double* u_z, const double* u_r, double inv_dx, double dt,
                const double* dt_dev, double sign0, double sign1, bool vec, cudaStream_t s);

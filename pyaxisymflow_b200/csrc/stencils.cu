@@ -624,6 +624,24 @@ int axb_diffusion_rk2_stage2(const axb_grid_t* g, double* w, const double* w_src
   AXB_RETURN_LAST();
 }
 
+int axb_diffusion_rk2_fused(const axb_grid_t* g, double* w, const double* w_src, double* tmp, const double* r1d,
+                            double nu, double dt, const double* dt_dev, axb_stream_t s) {
+  if (!w || !w_src || !r1d || w == w_src) return AXB_EINVAL;
+  GRID_PROLOGUE(w, w_src)
+  if (!g_axb_legacy_stencils) {
+    const int rc = march_diffusion_fused(d, w, w_src, r1d, nu, dt, dt_dev, vec, s);
+    AXB_LAUNCHED();
+    return rc;
+  }
+  // 2-D tiled path: the two stages through the caller's scratch field
+  if (!tmp || tmp == w || tmp == w_src) return AXB_EINVAL;
+  k_diffusion<1><<<grd, blk, 0, s>>>(d, tmp, w_src, nullptr, r1d, nu, dt, dt_dev, vec);
+  AXB_LAUNCHED();
+  k_diffusion<2><<<grd, blk, 0, s>>>(d, w, tmp, w_src, r1d, nu, dt, dt_dev, vec);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
 int axb_smooth_heaviside(const axb_grid_t* g, double* H, const double* phi, double blend_w,
                          axb_stream_t s) {
   if (!H || !phi) return AXB_EINVAL;

@@ -422,6 +422,144 @@ __global__ void __launch_bounds__(MT)
 }
 
 // -------------------------------------------------------------------------------------
+// G-DIF, both RK2 stages in one pass (kernels/diffusion_RK2.py:4-45): out = w + nu dt L(tmp),
+// tmp = w + nu dt / 2 L(w) on interior cells and tmp = w elsewhere.  tmp never goes to memory: a
+// block keeps a rolling window of three w rows and three tmp rows; the z-neighbours of tmp come from the
+// adjacent lanes, the two warp-edge lanes evaluate tmp on their ghost column themselves (one more
+// rolling w column + one load per row).  Same expressions, evaluated in the same order, as the two
+// km_diffusion stages, so the result has the same bits.  16 B/pt instead of 40.
+// -------------------------------------------------------------------------------------
+struct DifK {
+  double c1, c2, inv_dx2, inv_h;
+};
+// w + c * L(w) at one cell: up / down = r-neighbours, zp / zm = the z-neighbours k+1 / k-1
+__device__ __forceinline__ double dif_cell(double base, double c, double up, double dn, double zp, double zm, double ctr,
+                                           double ir, double ir2, const DifK& K) {
+  return base + c * ((up + dn + zp + zm - 4 * ctr) * K.inv_dx2 + (up - dn) * K.inv_h * ir - ctr * ir2);
+}
+
+template <int PATH>
+__global__ void __launch_bounds__(MT)
+    km_diffusion_fused(GridD g, int RB, double* __restrict__ out, const double* __restrict__ in,
+                       const double* __restrict__ r1d, double nu, double dt, const double* __restrict__ dt_dev, bool vec) {
+  extern __shared__ double s_inv[];          // 1 / r for rows j0 - 1 .. j1
+  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  const bool interior = block_interior(g, j0, j1, RB, 2, 2, vec);
+  if ((PATH == 1) != interior) return;
+  for (int i = threadIdx.x; i < j1 - j0 + 2; i += MT) {
+    const int j = j0 - 1 + i;
+    s_inv[i] = (j >= 0 && j < g.nr) ? 1.0 / r1d[j] : 0.0;
+  }
+  __syncthreads();
+  const Cols c = make_cols(g);
+  const int lane = threadIdx.x & 31, k = c.k;
+  if (dt_dev) dt = *dt_dev;
+  DifK K;
+  K.c1 = 0.5 * nu * dt;
+  K.c2 = nu * dt;
+  K.inv_dx2 = 1.0 / (g.dx * g.dx);
+  K.inv_h = 1.0 / (2 * g.dx);
+  if (PATH == 1) {
+    const long long ld = g.ld;
+    // ghost column of the warp-edge lanes: k - 1 (lane 0) or k + 2 (lane 31); gz = its outer z-neighbour
+    const bool edge = (lane == 0) || (lane == 31);
+    const int kg = (lane == 0) ? k - 1 : k + 2;
+    const int go = (lane == 0) ? k - 2 : k + 3;
+    // tmp row t from w rows t-1, t, t+1 (wm, wc, wp); returns the pair and the ghost-column value
+    auto tmp_row = [&](int t, const double2& wm, const double2& wc, const double2& wp, double gm, double gc, double gp,
+                       double gout, double2& tv, double& tg) {
+      const double ir = s_inv[t - j0 + 1], ir2 = ir * ir;
+      double left = shfl_up_d(wc.y), right = shfl_dn_d(wc.x);
+      if (lane == 0) left = gc;
+      if (lane == 31) right = gc;
+      tv.x = dif_cell(wc.x, K.c1, wp.x, wm.x, wc.y, left, wc.x, ir, ir2, K);
+      tv.y = dif_cell(wc.y, K.c1, wp.y, wm.y, right, wc.x, wc.y, ir, ir2, K);
+      // ghost column: its z-neighbours are (own pair element, gout) in k+1 / k-1 order
+      tg = (lane == 0) ? dif_cell(gc, K.c1, gp, gm, wc.x, gout, gc, ir, ir2, K)
+                       : dif_cell(gc, K.c1, gp, gm, gout, wc.y, gc, ir, ir2, K);
+    };
+    const double* p = in + (long long)(j0 - 2) * ld;
+    double2 w0 = ld2(p + k), w1 = ld2(p + ld + k), w2 = ld2(p + 2 * ld + k), w3 = ld2(p + 3 * ld + k);   // rows j0-2 .. j0+1
+    double g0 = 0, g1 = 0, g2 = 0, g3 = 0, o1 = 0, o2 = 0;
+    if (edge) {
+      g0 = p[kg]; g1 = p[ld + kg]; g2 = p[2 * ld + kg]; g3 = p[3 * ld + kg];
+      o1 = p[ld + go]; o2 = p[2 * ld + go];
+    }
+    double2 tm, tc;
+    double tgm, tgc;
+    tmp_row(j0 - 1, w0, w1, w2, g0, g1, g2, o1, tm, tgm);
+    tmp_row(j0, w1, w2, w3, g1, g2, g3, o2, tc, tgc);
+    // window now: wa = w[j-1] (unused), wb = w[j], wc_ = w[j+1]
+    double2 wb = w2, wcn = w3;
+    double gb = g2, gcn = g3;
+    p += 4 * ld;                                 // row j + 2
+    double* o = out + (long long)j0 * ld + k;
+    (void)tgm;
+    for (int jb = 0; jb < RB; jb += UR) {
+      double2 pn[UR];
+      double gn[UR], on[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) pn[u] = ld2(p + u * ld + k);
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        gn[u] = edge ? p[u * ld + kg] : 0.0;                 // w[j+2][ghost]
+        on[u] = edge ? p[(u - 1) * ld + go] : 0.0;           // w[j+1][outer]
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const int j = j0 + jb + u;
+        double2 tn;
+        double tgn;
+        tmp_row(j + 1, wb, wcn, pn[u], gb, gcn, gn[u], on[u], tn, tgn);
+        const double ir = s_inv[j - j0 + 1], ir2 = ir * ir;
+        double left = shfl_up_d(tc.y), right = shfl_dn_d(tc.x);
+        if (lane == 0) left = tgc;
+        if (lane == 31) right = tgc;
+        double2 res;
+        res.x = dif_cell(wb.x, K.c2, tn.x, tm.x, tc.y, left, tc.x, ir, ir2, K);
+        res.y = dif_cell(wb.y, K.c2, tn.y, tm.y, right, tc.x, tc.y, ir, ir2, K);
+        st2(o + u * ld, res);
+        tm = tc; tc = tn; tgc = tgn;
+        wb = wcn; wcn = pn[u];
+        gb = gcn; gcn = gn[u];
+      }
+      p += UR * ld; o += UR * ld;
+    }
+    return;
+  }
+  if (PATH != 2) return;
+  // general blocks: every cell from memory, boundary rules applied cell by cell
+  const int nz = g.nz;
+  auto cell_interior = [&](int j, int kk) {
+    const int kgl = kk + g.kz0;
+    return j >= 1 && j < g.nr - 1 && kgl >= 1 && kgl <= g.nzg - 2 && kk >= 1 && kk + 1 < nz;
+  };
+  auto tmp_at = [&](int j, int kk) -> double {
+    const double* r0 = rowp(in, g.ld, j);
+    const double v = r0[kk];
+    if (!cell_interior(j, kk)) return v;
+    const double ir = 1.0 / r1d[j], ir2 = ir * ir;
+    return dif_cell(v, K.c1, rowp(in, g.ld, j + 1)[kk], rowp(in, g.ld, j - 1)[kk], r0[kk + 1], r0[kk - 1], v, ir, ir2, K);
+  };
+  for (int j = j0; j < j1; ++j) {
+    const double ir = s_inv[j - j0 + 1], ir2 = ir * ir;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = k + e;
+      const bool own = e ? c.own1 : c.own0;
+      if (!own) continue;
+      const double w = rowp(in, g.ld, j)[kk];
+      double res = w;
+      if (cell_interior(j, kk)) {
+        const double tcv = tmp_at(j, kk);
+        res = dif_cell(w, K.c2, tmp_at(j + 1, kk), tmp_at(j - 1, kk), tmp_at(j, kk + 1), tmp_at(j, kk - 1), tcv, ir, ir2, K);
+      }
+      rowp(out, g.ld, j)[kk] = res;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
 // G-ADV / G-REF (and the plain-array pystencils forms)
 // -------------------------------------------------------------------------------------
 #define C13 (1.0 / 3.0)
@@ -731,6 +869,17 @@ int march_diffusion(int stage, const GridD& d, double* out, const double* in, co
   if (stage == 1) { DIF(1, 2, se); DIF(1, 1, s); }
   else { DIF(2, 2, se); DIF(2, 1, s); }
 #undef DIF
+  edge_end(s, ef);
+  return (int)cudaGetLastError();
+}
+
+int march_diffusion_fused(const GridD& d, double* out, const double* in, const double* r1d, double nu, double dt,
+                          const double* dt_dev, bool vec, cudaStream_t s) {
+  const int rb = pick_rb(d);
+  EdgeFork* ef;
+  cudaStream_t se = edge_begin(s, ef);
+  km_diffusion_fused<2><<<march_grid(d, rb), MT, (rb + 2) * sizeof(double), se>>>(d, rb, out, in, r1d, nu, dt, dt_dev, vec);
+  km_diffusion_fused<1><<<march_grid(d, rb), MT, (rb + 2) * sizeof(double), s>>>(d, rb, out, in, r1d, nu, dt, dt_dev, vec);
   edge_end(s, ef);
   return (int)cudaGetLastError();
 }

@@ -8,15 +8,17 @@ reference's ``ghost_size`` (periodic_flow_past_sphere.py:49).  The kernels of
 apply the global-boundary formulas by *global* column index and only write owned columns.
 
 Communication per timestep
-  * halo exchanges with the two z-neighbours (point-to-point, 2 x Nr doubles per field and
-    side): psi (before G-VEL, width 2 so that the velocity is also valid on one halo column),
-    (vorticity, u_z) width 2 before G-ADV, the advected vorticity and the RK2 temporary width 1
-    before the two diffusion stages;
+  * halo exchanges with the two z-neighbours (2 x Nr doubles per field and side, stored straight
+    into the neighbours' halo columns over NVLink peer memory, NCCL send/recv as the fall-back):
+    psi (before G-VEL, width 2 so that the velocity is also valid on one halo column),
+    (vorticity, u_z) width 2 before G-ADV, the advected vorticity width 2 before the fused RK2
+    diffusion pass (which evaluates its intermediate field on one halo column itself);
   * one MAX all-reduce of a double for the CFL time step (and a SUM when the drag is read);
-  * the fast-diagonalisation solve: local r-transform GEMM on the slab, all-to-all transpose
-    to r-slabs ``(Nr/P, Nz)``, the two z-transform GEMMs (eigenvalue scaling fused in the first
-    one's epilogue) on whole rows, all-to-all back, local r back-transform.  Each all-to-all
-    moves ``Nr Nz 8 (P-1)/P^2`` bytes per rank.
+  * the fast-diagonalisation solve: transpose to r-slabs ``(Nr/P, Nz)``, cosine transform of whole
+    rows, transpose to z-mode slabs, tridiagonal r sweeps of this rank's modes, and the same two
+    transposes back around the inverse transform (eigen-decomposition path: local r GEMM, transpose,
+    z GEMMs, transpose, local r GEMM).  Each transpose moves ``Nr Nz 8 (P-1)/P^2`` bytes per rank,
+    written directly into the peers' buffers (``axb_peer_block_put``) or through NCCL all-to-all.
 The r-direction (axis reflection, 1/r terms) is never split.
 """
 from __future__ import annotations
@@ -472,10 +474,8 @@ class SlabRigidFlowStepper:
               sp(3), s)
         self.comm.exchange([w, self.u_z], 2, self.dx)
         _call("axb_advect_vorticity_eno3", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), 0.0, sp(1), s)
-        self.comm.exchange([self._w2], 1, self.dx)
-        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(self._w2), ptr(self.r1d), self.nu, 0.0, sp(1), s)
-        self.comm.exchange([self._tmp], 1, self.dx)
-        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0,
+        self.comm.exchange([self._w2], 2, self.dx)            # width 2: the fused RK2 evaluates tmp on one halo column
+        _call("axb_diffusion_rk2_fused", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0,
               sp(1), s)
         _call("axb_rigid_flow_scalars", 2, ptr(st), *sc, s)
 

@@ -116,11 +116,14 @@ class RigidFlowStepper:
         _call("axb_advect_vorticity_eno3", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), 0.0, sp(S_DT), s)
         if self.periodic:
             _call("axb_periodic_ghost_comm", g, ptr(self._w2), self.ghost, 0.0, 0.0, s)
-        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(self._w2), ptr(self.r1d), self.nu, 0.0, sp(S_DT), s)
         if self.periodic:
+            _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(self._w2), ptr(self.r1d), self.nu, 0.0, sp(S_DT), s)
             _call("axb_periodic_ghost_comm", g, ptr(self._tmp), self.ghost, 0.0, 0.0, s)
-        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0,
-              sp(S_DT), s)
+            _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0,
+                  sp(S_DT), s)
+        else:       # both RK2 stages in one pass, the intermediate field stays on chip
+            _call("axb_diffusion_rk2_fused", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0,
+                  sp(S_DT), s)
         _call("axb_rigid_flow_scalars", 2, ptr(st), self.U_0, self.T_ramp, self.ur_ramp, self.dt_diff_limit, self.CFL * self.dx, s)
 
     def step(self, n=1):
