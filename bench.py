@@ -222,7 +222,7 @@ def run_gpu_arm(args, nr, nz):
             stepper = SlabRigidFlowStepper(nz, grid_size_r=nr, r_method=args.r_method, z_method=args.z_method)
         else:
             stepper = RigidFlowStepper(nz, grid_size_r=nr, basis=basis, r_method=args.r_method,
-                                       z_method=args.z_method)
+                                       z_method=args.z_method, use_graph=not args.no_graph)
         scaling = "strong"
         # synthetic start: seeded band-limited vorticity blob so every kernel sees
         # non-trivial data from the first step on
@@ -239,7 +239,11 @@ def run_gpu_arm(args, nr, nz):
             dist.barrier()
             torch.cuda.synchronize()
 
-    stepper.step(args.warmup)
+    if args.config == "c1":
+        stepper.step(args.warmup)
+    else:                                   # the same call as the timed loop (graph capture happens here)
+        for _ in range(args.warmup):
+            stepper.step_probed()
     barrier()
 
     sampler = ClockSampler(local)
@@ -470,6 +474,9 @@ def main():
                     help="c4 (default): 4096x16384 rigid flow, the configuration the metric is quoted on; "
                          "c2: periodic 1024x4096; c3: soft sphere 2048x8192; c5: particle ensemble 1024x2048")
     ap.add_argument("--cases", type=int, default=8, help="ensemble members per GPU (c5)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="c4, 1 GPU: launch the step kernel by kernel instead of replaying CUDA graphs (before / "
+                         "solve / after, with the roofline events between them)")
     ap.add_argument("--r-method", default="auto", choices=["auto", "eigen", "tridiagonal"],
                     help="r direction of the solve: eigen-decomposition GEMMs (the reference's algorithm) or a "
                          "batched tridiagonal solve per z-mode (auto: tridiagonal on grids too large for la.eig)")

@@ -77,24 +77,30 @@ class RigidFlowStepper:
             _call("axb_periodic_ghost_comm", ctypes.byref(self.grid), ptr(self.char_func), self.ghost, 0.0, 0.0,
                   stream_ptr())
         self._graph = None
+        self._graphs3 = None
         self._use_graph = use_graph
         self.graph_launches = 0          # kernels inside the captured step
         self.launches_replayed = 0       # kernels launched through graph replays so far
 
     # -- one step, enqueued on the current stream ---------------------------------------------
-    def _enqueue(self, probe=None):
+    def _enqueue(self, probe=None, parts=(0, 1, 2)):
+        """parts: 0 = everything before the solve, 1 = the solve, 2 = everything after it"""
         s = stream_ptr()
         g = ctypes.byref(self.grid)
         st = self.state
         sp = lambda i: ctypes.c_void_p(st.data_ptr() + 8 * i)  # noqa: E731
         w, psi = self.vorticity, self.psi
-        _call("axb_rigid_flow_scalars", 0, ptr(st), self.U_0, self.T_ramp, self.ur_ramp, self.dt_diff_limit, self.CFL * self.dx, s)
-        if not self.periodic:
-            _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
-        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
+        if 0 in parts:
+            _call("axb_rigid_flow_scalars", 0, ptr(st), self.U_0, self.T_ramp, self.ur_ramp, self.dt_diff_limit,
+                  self.CFL * self.dx, s)
+            if not self.periodic:
+                _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
+            _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
         if probe is not None:
             probe[0].record()
-        if self.periodic:
+        if 1 not in parts:
+            pass
+        elif self.periodic:
             gh = self.ghost
             off = 8 * gh
             _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ctypes.c_void_p(psi.data_ptr() + off), self.nz,
@@ -104,6 +110,8 @@ class RigidFlowStepper:
             _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ptr(psi), self.nz, ptr(w), self.nz, s)
         if probe is not None:
             probe[1].record()
+        if 2 not in parts:
+            return
         _call("axb_velocity_from_psi", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(psi), ptr(self.r1d), 0.0, 0.0,
               sp(S_UZADD), sp(S_UMAX), s)
         _call("axb_rigid_flow_scalars", 1, ptr(st), self.U_0, self.T_ramp, self.ur_ramp, self.dt_diff_limit, self.CFL * self.dx, s)
@@ -147,10 +155,33 @@ class RigidFlowStepper:
             for _ in range(n):
                 self._enqueue()
 
+    def _capture(self, parts):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            self._enqueue(parts=parts)
+        return graph, _lib.launch_count() - before
+
     def step_probed(self):
-        """one step with CUDA events around the four GEMMs of the solve (bench.py's roofline leg)"""
+        """one step with CUDA events around the solve (bench.py's roofline leg).  With ``use_graph`` the step
+        is replayed as three graphs (before / solve / after) so that the events sit between graph launches."""
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        self._enqueue(probe=ev)
+        if not self._use_graph:
+            self._enqueue(probe=ev)
+            return ev
+        if self._graphs3 is None:
+            self._enqueue()                          # warm-up outside capture (sets kernel attributes)
+            torch.cuda.synchronize()
+            self._graphs3 = [self._capture((p,)) for p in (0, 1, 2)]
+        (g0, n0), (g1, n1), (g2, n2) = self._graphs3
+        g0.replay()
+        ev[0].record()
+        g1.replay()
+        ev[1].record()
+        g2.replay()
+        self.launches_replayed += n0 + n1 + n2
         return ev
 
     def solve_flops(self):
