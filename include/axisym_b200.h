@@ -316,6 +316,14 @@ int axb_tridiag_factor_columns(int nr, int nz, const double* sub, const double* 
                                double* row_coef, axb_stream_t s);
 int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const double* inv_pivots,
                                const double* row_coef, axb_stream_t s);
+/* Partition (SPIKE) form of the r solve when the rows are split over ranks (multi-GPU r-slabs): every rank
+ * solves its own diagonal block (axb_tridiag_solve_factored on its rows: g), the first / last rows of all
+ * ranks' g are gathered into G (n_iface = 2 * ranks rows of nz), and
+ *   X[m, k] = g[m, k] - V[m, k] xl[k] - W[m, k] xr[k],  xl = sum_i CL[i, k] G[i, k], xr = sum_i CR[i, k] G[i, k]
+ * with the spikes V = T_p^-1 (a e_first), W = T_p^-1 (u e_last) and the rows CL / CR of the inverted reduced
+ * interface system, all operator-only and prepared once (pyaxisymflow_b200/slab.py).  X, V, W: rows x nz. */
+int axb_tridiag_partition_correct(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
+                                  const double* G, const double* CL, const double* CR, int n_iface, axb_stream_t s);
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s);
 /* Plain row-major FP64 GEMM C = A*B (+ optional spectral scaling), the building block above:

@@ -301,6 +301,33 @@ bool tri_map(CUtensorMap* m, const double* ptr, int nr, int nz, long long ld, in
 
 }  // namespace
 
+// Partition (SPIKE) correction for an r range split over ranks: after the local solve g of this rank's
+// rows, x = g - V xl - W xr with the two neighbouring interface unknowns
+//   xl[k] = sum_i CL[i][k] G[i][k],  xr[k] = sum_i CR[i][k] G[i][k]      (i < n_iface = 2 * ranks),
+// G = the first / last local-solve rows of every rank, CL / CR = rows of the inverted reduced system.
+__global__ void __launch_bounds__(128)
+    k_tri_partition_correct(int rows, int nz, double* __restrict__ X, long long ld, const double* __restrict__ V,
+                            const double* __restrict__ W, const double* __restrict__ G, const double* __restrict__ CL,
+                            const double* __restrict__ CR, int n_iface, int rows_per_block) {
+  const int k = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (k >= nz) return;
+  const bool two = k + 1 < nz;
+  double xl0 = 0, xl1 = 0, xr0 = 0, xr1 = 0;
+  for (int i = 0; i < n_iface; ++i) {
+    const long long o = (long long)i * nz + k;
+    const double g0 = G[o], g1 = two ? G[o + 1] : 0.0;
+    xl0 += CL[o] * g0;
+    xr0 += CR[o] * g0;
+    if (two) { xl1 += CL[o + 1] * g1; xr1 += CR[o + 1] * g1; }
+  }
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(rows, m0 + rows_per_block);
+  for (int m = m0; m < m1; ++m) {
+    const long long o = (long long)m * ld + k, t = (long long)m * nz + k;
+    X[o] = (X[o] - V[t] * xl0) - W[t] * xr0;
+    if (two) X[o + 1] = (X[o + 1] - V[t + 1] * xl1) - W[t + 1] * xr1;
+  }
+}
+
 bool tri_fast_ok(int nz, const double* X, long long ld, const double* inv) {
   return inv && (nz % 16 == 0) && axb_al16(X) && axb_al16(inv) && (ld % 2 == 0);
 }
@@ -365,6 +392,16 @@ int axb_tridiag_factor_columns(int nr, int nz, const double* sub, const double* 
   k_tri_factor<<<(nz + 127) / 128, 128, 0, (cudaStream_t)s>>>(nr, nz, sub, diag, sup, lam, c0, c1, inv_pivots);
   AXB_LAUNCHED();
   k_tri_row_coef<<<(nr + 127) / 128, 128, 0, (cudaStream_t)s>>>(nr, sub, sup, scale, c1, row_coef);
+  AXB_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int axb_tridiag_partition_correct(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
+                                  const double* G, const double* CL, const double* CR, int n_iface, axb_stream_t s) {
+  if (rows < 1 || nz < 1 || !X || !V || !W || !G || !CL || !CR || n_iface < 2 || ld < nz) return AXB_EINVAL;
+  const int rpb = 32;
+  k_tri_partition_correct<<<dim3((nz / 2 + 128) / 128, (rows + rpb - 1) / rpb), 128, 0, (cudaStream_t)s>>>(
+      rows, nz, X, ld, V, W, G, CL, CR, n_iface, rpb);
   AXB_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -266,6 +266,113 @@ class _CudaTridiagonal:
                   ptr(tri["sup"]), ptr(self.lam), ptr(tri["scale"]), self.c0, self.c1, ptr(self.scratch), stream_ptr())
 
 
+class PartitionedTridiagonal:
+    """r solve with the ROWS split over the ranks (r-slab layout, every rank holds all z-modes): the
+    partition / SPIKE method.  Each rank solves its own diagonal block T_p g = rhs (the factored sweeps on
+    its rows), the first and last row of every rank's g are gathered (2 P rows of Nz doubles), and
+    x = g - V xl - W xr with the spikes V = T_p^-1 (a e_first), W = T_p^-1 (u e_last) and the two neighbouring
+    interface unknowns xl, xr taken from the inverted 2P x 2P reduced system.  Everything but g is operator
+    only and prepared here once.  Compared with transposing to z-mode slabs and back this trades two
+    all-to-all transposes for a 2 P Nz gather and one 32 B/pt correction pass."""
+
+    def __init__(self, layout, factors, group=None, peer_ptrs=None, host=False):
+        from . import fd
+
+        L, f = self.L, self.f = layout, factors
+        tri = f["tri"]
+        self.group, self.host = group, host
+        c0, c1 = float(f["c0"]), float(f["c1"])
+        r0, r1, n = L.r_begin, L.r_begin + L.nrl, L.nrl
+        sub, diag, sup, scale, lam = tri["sub"], tri["diag"], tri["sup"], tri["scale"], f["lam_z"]
+        self.sub_l, self.diag_l, self.sup_l = sub[r0:r1 - 1].contiguous(), diag[r0:r1].contiguous(), sup[r0:r1 - 1].contiguous()
+        self.scale_l = None if scale is None else scale[r0:r1].contiguous()
+        self.lam, self.c0, self.c1 = lam, c0, c1
+        dev = lam.device
+        if not host:
+            self.inv = torch.empty((n, L.nz), dtype=torch.float64, device=dev)
+            self.rc = torch.empty((n, 4), dtype=torch.float64, device=dev)
+            _call("axb_tridiag_factor_columns", n, L.nz, ptr(self.sub_l), ptr(self.diag_l), ptr(self.sup_l), ptr(lam),
+                  ptr(self.scale_l), c0, c1, ptr(self.inv), ptr(self.rc), stream_ptr())
+            self.rc_unit = self.rc.clone()
+            self.rc_unit[:, 1] = 1.0
+        # spikes: unit-scaled local solves of a e_first and u e_last
+        self.V = torch.zeros((n, L.nz), dtype=torch.float64, device=dev)
+        self.W = torch.zeros((n, L.nz), dtype=torch.float64, device=dev)
+        if L.rank > 0:
+            self.V[0] = c1 * float(sub[r0 - 1])
+            self._local_solve(self.V, unit=True)
+        if L.rank < L.world - 1:
+            self.W[-1] = c1 * float(sup[r1 - 1])
+            self._local_solve(self.W, unit=True)
+        # reduced interface system, inverted once on the host: unknowns (first, last) of every rank
+        mine = torch.stack([self.V[0], self.V[-1], self.W[0], self.W[-1]]).contiguous()
+        parts = [torch.empty_like(mine) for _ in range(L.world)]
+        if L.world > 1:
+            dist.all_gather(parts, mine, group=group)
+        else:
+            parts = [mine]
+        co = torch.stack(parts).cpu().numpy()                      # (P, 4, nz)
+        P2 = 2 * L.world
+        R = np.zeros((L.nz, P2, P2))
+        for p in range(L.world):
+            for a in (0, 1):
+                i = 2 * p + a
+                R[:, i, i] = 1.0
+                if p > 0:
+                    R[:, i, 2 * (p - 1) + 1] = co[p, a]
+                if p < L.world - 1:
+                    R[:, i, 2 * (p + 1)] = co[p, 2 + a]
+        Rinv = np.linalg.inv(R)
+        CL = Rinv[:, 2 * (L.rank - 1) + 1, :].T if L.rank > 0 else np.zeros((P2, L.nz))
+        CR = Rinv[:, 2 * (L.rank + 1), :].T if L.rank < L.world - 1 else np.zeros((P2, L.nz))
+        self.CL = torch.from_numpy(np.ascontiguousarray(CL)).to(dev)
+        self.CR = torch.from_numpy(np.ascontiguousarray(CR)).to(dev)
+        self.n_iface = P2
+        # gathered interface rows: peer-mapped buffer filled by direct stores, or a plain all-gather
+        self.G, self.G_ptrs, self.G_handle = None, None, None
+        if peer_ptrs is not None:
+            self.G, self.G_handle, ptrs = peer_ptrs((P2, L.nz))
+            self.G_ptrs = (ctypes.c_uint64 * L.world)(*ptrs)
+        else:
+            self.G = torch.zeros((P2, L.nz), dtype=torch.float64, device=dev)
+        _ = fd
+
+    def _local_solve(self, x, unit=False):
+        from . import fd
+
+        n, nz = x.shape
+        if self.host:
+            x.copy_(torch.from_numpy(fd.thomas_host(
+                x.numpy(), self.sub_l.numpy(), self.diag_l.numpy(), self.sup_l.numpy(), self.lam.numpy(),
+                None if (unit or self.scale_l is None) else self.scale_l.numpy(), self.c0, self.c1)))
+            return
+        _call("axb_tridiag_solve_factored", n, nz, ptr(x), x.stride(0), ptr(self.inv),
+              ptr(self.rc_unit if unit else self.rc), stream_ptr())
+
+    def __call__(self, x):
+        """x: this rank's rows of the spectral right-hand side (nrl x nz), solved in place"""
+        L = self.L
+        n, nz = x.shape
+        self._local_solve(x)
+        if self.G_ptrs is not None:                   # rows 0 and n-1 straight into every rank's G over NVLink
+            _call("axb_peer_block_put", L.world, L.rank, self.G_ptrs, L.rank * 2 * nz, nz, ptr(x), 0,
+                  (n - 1) * x.stride(0), 2, nz, stream_ptr())
+            self.G_handle.barrier(channel=0)
+        else:
+            mine = torch.stack([x[0], x[-1]]).contiguous()
+            if L.world > 1:
+                dist.all_gather_into_tensor(self.G.view(-1), mine.view(-1), group=self.group)
+            else:
+                self.G.copy_(mine)
+        if self.host:
+            xl = (self.CL * self.G).sum(0)
+            xr = (self.CR * self.G).sum(0)
+            x.copy_((x - self.V * xl) - self.W * xr)
+            return
+        _call("axb_tridiag_partition_correct", n, nz, ptr(x), x.stride(0), ptr(self.V), ptr(self.W), ptr(self.G),
+              ptr(self.CL), ptr(self.CR), self.n_iface, stream_ptr())
+
+
 class SlabFdSolver:
     """Distributed fast-diagonalisation solve on z-slabs (factors replicated on every rank).
 
@@ -274,9 +381,10 @@ class SlabFdSolver:
                           r solves of this rank's z-modes -> all-to-all -> backward z transform -> all-to-all
     ``gemm`` / ``fold`` / ``dct`` / ``tri`` are injectable so the plumbing runs on CPU in the gloo tests."""
 
-    def __init__(self, layout, comm, factors, gemm=None, fold=None, dct=None, tri=None, peer=None):
+    def __init__(self, layout, comm, factors, gemm=None, fold=None, dct=None, tri=None, peer=None, part=None):
         self.L, self.comm, self.f = layout, comm, factors
         self.peer = peer
+        self.part = part          # PartitionedTridiagonal: r solve in the r-slab layout (2 transposes per solve)
         self.gemm = gemm or _cuda_gemm
         self.fold = fold or _cuda_fold
         self.dct = dct or _cuda_dct
@@ -291,14 +399,15 @@ class SlabFdSolver:
         else:
             self.lam_r_local = factors["lam_r"][L.r_begin:L.r_begin + L.nrl].contiguous()
 
-    def _z_transform(self, inverse, rows_in=None):
+    def _z_transform(self, inverse, rows_in=None, rows_out=None):
         """z transform of whole rows: rows_in (default rows_a; folded in place on the GEMM-leaf path) ->
-        rows_b, which is returned"""
+        rows_out (default rows_b; DCT path only), which is returned"""
         f = self.f
         rows_a = self.rows_a if rows_in is None else rows_in
         if f.get("zfft") is not None:
-            self.dct(self.rows_b, rows_a, f["zfft"]["tables"], inverse)
-            return self.rows_b
+            out = self.rows_b if rows_out is None else rows_out
+            self.dct(out, rows_a, f["zfft"]["tables"], inverse)
+            return out
         zs = f.get("zsplit")
         if zs is None:
             self.gemm(self.rows_b, rows_a, f["Rzb"] if inverse else f["Rz"])
@@ -315,6 +424,23 @@ class SlabFdSolver:
 
     def _solve_tridiagonal(self, psi_slab, rhs_slab):
         L = self.L
+        if self.part is not None and self.f.get("zfft") is not None:
+            # r-slab rows all the way: transpose, DCT-II, partitioned r solve, DCT-III, transpose
+            pt = self.peer
+            if pt is not None:
+                rows = pt.slab_to_rows(L.owned(rhs_slab))
+            else:
+                self.t_slab.copy_(L.owned(rhs_slab))
+                rows = self.comm.slab_to_rows(self.t_slab, self.rows_a)
+            spec = self._z_transform(False, rows)                                 # -> rows_b
+            self.part(spec)
+            out = self._z_transform(True, spec, rows)                             # back into the row buffer
+            if pt is not None:
+                L.owned(psi_slab).copy_(pt.rows_to_slab(out))
+            else:
+                self.comm.rows_to_slab(out, self.t_slab)
+                L.owned(psi_slab).copy_(self.t_slab)
+            return
         if self.peer is not None:                                                 # transposes over peer memory
             pt = self.peer
             spec = self._z_transform(False, pt.slab_to_rows(L.owned(rhs_slab)))
@@ -437,7 +563,15 @@ class SlabRigidFlowStepper:
                 if rank == 0:
                     print(f"[pyaxisymflow_b200] peer-memory transposes unavailable ({e!r}); using NCCL all-to-all",
                           flush=True)
-        self.solver = SlabFdSolver(L, self.comm, self.factors, peer=self.peer)
+        self.part = None
+        if self.factors.get("zfft") is not None and world > 1 and not os.environ.get("AXB_SLAB_TRANSPOSE4"):
+            def peer_buf(shape):
+                t = self.comm.symmetric_field(shape)
+                h, ptrs = self.comm._peer_fields[t.data_ptr()]
+                return t, h, ptrs
+            self.part = PartitionedTridiagonal(L, self.factors, group,
+                                               peer_ptrs=peer_buf if self.peer is not None else None)
+        self.solver = SlabFdSolver(L, self.comm, self.factors, peer=self.peer, part=self.part)
 
     def seed_vorticity(self, seed=0, amplitude=1.0):
         """same global field as RigidFlowStepper.seed_vorticity, cut to this rank's slab"""
@@ -495,6 +629,8 @@ class SlabRigidFlowStepper:
         """per-rank algorithmic HBM bytes of the solve on the DCT path (the all-to-all traffic is NVLink's)"""
         from .fd import solve_hbm_bytes
         b = solve_hbm_bytes(self.nr, self.nz, self.factors)
+        if b is not None and self.part is not None:
+            b += 32.0 * self.nr * self.nz                      # the partition correction pass
         return None if b is None else b / self.L.world
 
     def solver_basis(self):
@@ -503,6 +639,11 @@ class SlabRigidFlowStepper:
     def solve_kernel_note(self):
         zs = self.factors.get("zsplit")
         n = 0 if zs is None else len(zs["leaf_n"])
+        if self.factors.get("zfft") is not None and self.part is not None:
+            how = ("over NVLink peer memory (k_peer_block_put + device barrier)" if self.peer is not None
+                   else "by NCCL all-to-all / all-gather")
+            return ("per rank: k_dct_rows and the partitioned r solve (k_tri_sweep on the rank's own rows + "
+                    "k_tri_partition_correct) on r-slabs; 2 transposes + one 2P-row interface gather " + how)
         if self.factors.get("zfft") is not None:
             how = ("4 transposes over NVLink peer memory (k_peer_block_put + device barrier)" if self.peer is not None
                    else "4 NCCL all-to-all")

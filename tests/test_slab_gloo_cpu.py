@@ -112,6 +112,18 @@ def _worker(rank, world, port, nr, nz, q):
             solver.solve(psi_slab, rhs_slab)
             err = (L.owned(psi_slab) - ref[:, L.z_begin:L.z_begin + L.nzl]).abs().max().item() / ref.abs().max().item()
             assert err < 1e-12, f"distributed tridiagonal solve ({z_method}, split={split}) differs by {err:.2e}"
+        # ---- r solve partitioned over the ranks (r-slab rows all the way, 2 transposes per solve)
+        from pyaxisymflow_b200.slab import PartitionedTridiagonal
+
+        fac = fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx, "analytic",
+                               r_method="tridiagonal", z_method="fft")
+        ref = torch.from_numpy(fd.apply_factors_host(fac, full.numpy()))
+        part = PartitionedTridiagonal(L, fac, None, host=True)
+        solver = SlabFdSolver(L, comm, fac, dct=_host_dct, tri=_HostTridiagonal(L, fac), part=part)
+        psi_slab = torch.zeros_like(rhs_slab)
+        solver.solve(psi_slab, rhs_slab)
+        err = (L.owned(psi_slab) - ref[:, L.z_begin:L.z_begin + L.nzl]).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-12, f"partitioned r solve differs by {err:.2e}"
         # ---- reductions
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         assert comm.allreduce(t.clone(), "max").item() == world
