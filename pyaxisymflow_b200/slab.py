@@ -15,9 +15,10 @@ Communication per timestep
     diffusion pass (which evaluates its intermediate field on one halo column itself);
   * one MAX all-reduce of a double for the CFL time step (and a SUM when the drag is read);
   * the fast-diagonalisation solve: transpose to r-slabs ``(Nr/P, Nz)``, cosine transform of whole
-    rows, transpose to z-mode slabs, tridiagonal r sweeps of this rank's modes, and the same two
-    transposes back around the inverse transform (eigen-decomposition path: local r GEMM, transpose,
-    z GEMMs, transpose, local r GEMM).  Each transpose moves ``Nr Nz 8 (P-1)/P^2`` bytes per rank,
+    rows, r solve partitioned over the ranks (own-block sweeps + a 2P-row interface gather + one
+    correction pass, :class:`PartitionedTridiagonal`), inverse transform, transpose back.  (Other
+    flows: transposes to z-mode slabs around plain r sweeps, ``AXB_SLAB_TRANSPOSE4``; the
+    eigen-decomposition path: local r GEMM, transpose, z GEMMs, transpose, local r GEMM.)  Each transpose moves ``Nr Nz 8 (P-1)/P^2`` bytes per rank,
     written directly into the peers' buffers (``axb_peer_block_put``) or through NCCL all-to-all.
 The r-direction (axis reflection, 1/r terms) is never split.
 """
