@@ -47,6 +47,17 @@ def test_argument_validation_without_a_gpu():
     assert lib.axb_set_fixed_val(ctypes.byref(g), ctypes.c_void_p(12), 1.0, None) == -2   # misaligned
     assert lib.axb_dgemm(0, 4, 4, None, 4, None, 4, None, 4, None, None, 0.0, 0.0, None) == -1
     assert lib.axb_ls_workspace_bytes(100, 100) > 100 * 100 * 20
+    # the solve's building blocks reject unsupported shapes before touching the device
+    p16 = ctypes.c_void_p(16)
+    assert lib.axb_dct2_rows(4, 96, p16, 96, ctypes.c_void_p(4096), 96, p16, 1.0, 1.0, None) == -1      # not 2^p
+    assert lib.axb_dct3_rows(4, 32768, p16, 32768, ctypes.c_void_p(1 << 20), 32768, p16, None) == -1    # > 16384
+    assert lib.axb_dct2_rows(4, 256, p16, 128, ctypes.c_void_p(4096), 256, p16, 1.0, 1.0, None) == -1   # pitch < n
+    assert lib.axb_tridiag_solve_factored(1, 64, p16, 64, p16, p16, None) == -1                         # nr < 2
+    assert lib.axb_tridiag_solve_factored(8, 40, p16, 40, p16, p16, None) == -1                         # nz % 16
+    assert lib.axb_tridiag_partition_correct(8, 64, p16, 32, p16, p16, p16, p16, p16, 4, None) == -1    # pitch < nz
+    ptrs = (ctypes.c_uint64 * 2)(16, 0)
+    assert lib.axb_peer_block_put(2, 0, ptrs, 0, 64, p16, 0, 64, 2, 64, None) == -1                     # null peer
+    assert lib.axb_peer_block_put(17, 0, ptrs, 0, 64, p16, 0, 64, 2, 64, None) == -1                    # > AXB_MAX_PEERS
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
