@@ -623,6 +623,38 @@ class SlabRigidFlowStepper:
         self._enqueue(probe=ev)
         return ev
 
+    def step_host(self, vorticity_slab_host, char_func_slab_host, out_slab_host):
+        """End-to-end form for host-resident callers: this rank's owned columns (pinned ``(Nr, Nz/P)`` host
+        arrays) in, one step, owned vorticity columns out; every rank moves its share over its own PCIe link."""
+        L = self.L
+        L.owned(self.vorticity).copy_(vorticity_slab_host, non_blocking=True)
+        L.owned(self.char_func).copy_(char_func_slab_host, non_blocking=True)
+        self._refresh_char_halo()                            # the penalisation reads chi one column into the halo
+        self.step(1)
+        out_slab_host.copy_(L.owned(self.vorticity), non_blocking=True)
+
+    def _refresh_char_halo(self):
+        """halo columns of the characteristic function after a host upload (plain NCCL send/recv: it is not one
+        of the peer-mapped fields)"""
+        L = self.L
+        if L.world == 1:
+            return
+        f = self.char_func
+        n = L.nr * 2
+        sl, sr, rl, rr = (torch.empty(n, dtype=torch.float64, device=f.device) for _ in range(4))
+        g = L.grid(self.dx)
+        _call("axb_halo_pack", ctypes.byref(g), ptr(f), ptr(sl) if L.left is not None else None,
+              ptr(sr) if L.right is not None else None, 2, stream_ptr())
+        ops = []
+        if L.left is not None:
+            ops += [dist.P2POp(dist.isend, sl, L.left, self.comm.group), dist.P2POp(dist.irecv, rl, L.left, self.comm.group)]
+        if L.right is not None:
+            ops += [dist.P2POp(dist.isend, sr, L.right, self.comm.group), dist.P2POp(dist.irecv, rr, L.right, self.comm.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        _call("axb_halo_unpack", ctypes.byref(g), ptr(f), ptr(rl) if L.left is not None else None,
+              ptr(rr) if L.right is not None else None, 2, 0.0, stream_ptr())
+
     def solve_flops(self):
         return self.solver.flops_per_rank()
 
