@@ -13,8 +13,10 @@
 // The FFT is an in-place Stockham auto-sort: every thread owns 16 complex points per pass, reads
 // them all, __syncthreads, then writes its radix-16 (last pass: radix 2/4/8) butterflies to the
 // auto-sort positions.  Twiddles come from exactly rounded host tables.
+#include <cuda.h>   // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "axb_common.cuh"
 
@@ -356,9 +358,9 @@ __device__ __forceinline__ void dct3_pair(double ak, double ank, double amk, dou
 
 template <bool INV>
 __global__ void __launch_bounds__(512, 1)
-    k_dct_rows_rr(int rows, int N, int logM, int rpc, const double* __restrict__ src, long long ld_src,
-                  double* __restrict__ dst, long long ld_dst, const double2* __restrict__ tabs, double scale0,
-                  double scale) {
+    k_dct_rows_rr(const __grid_constant__ CUtensorMap tmS, int split, int rows, int N, int logM, int rpc,
+                  const double* __restrict__ src, long long ld_src, double* __restrict__ dst, long long ld_dst,
+                  const double2* __restrict__ tabs, double scale0, double scale) {
   extern __shared__ __align__(128) unsigned char rr_smem[];
   const int M = N >> 1, H = M >> 1, T = M >> 4;
   const int rl = threadIdx.x >> (logM - 4), j = threadIdx.x - rl * T;
@@ -397,6 +399,18 @@ __global__ void __launch_bounds__(512, 1)
     for (int q = 0; q < nl; ++q) {
       const double* g = src + (long long)(r0 + q) * ld_src;
       const unsigned d = rr_u32(stage_all + (size_t)q * N);
+      if (split) {
+        // the row viewed as quadruples (x[4n .. 4n+3]): two tensor loads with a 2-element inner box stage
+        // A[n] = (x[4n], x[4n+1]) in st[0 .. N/2) and B[n] = (x[4n+2], x[4n+3]) in st[N/2 .. N)
+#pragma unroll
+        for (int par = 0; par < 2; ++par)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(
+                  d + par * (N * 4)),
+              "l"(reinterpret_cast<unsigned long long>(&tmS)), "r"(2 * par), "r"(0), "r"(0), "r"(r0 + q), "r"(bar_a)
+              : "memory");
+        continue;
+      }
       for (int c = 0; c < N * 8; c += 32768) {                         // <= 32 KB per copy
         const int bytes = min(32768, N * 8 - c);
         asm volatile(
@@ -421,7 +435,21 @@ __global__ void __launch_bounds__(512, 1)
     rr_mb_wait(bar_a, it & 1);
     double2 v[16];
     double2 mir[8];
-    if (!INV) {
+    if (!INV && split) {
+      // staged as A[n] = (x[4n], x[4n+1]), B[n] = (x[4n+2], x[4n+3]): conflict-free 128-bit reads
+      const double2* qa = reinterpret_cast<const double2*>(st);
+      const double2* qb = reinterpret_cast<const double2*>(st + (N >> 1));
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int n = j + t * T;                                       // < M/2
+        v[t] = make_double2(qa[n].x, qb[n].x);
+      }
+#pragma unroll
+      for (int t = 8; t < 16; ++t) {
+        const int n = M - 1 - (j + t * T);                             // mirrored half
+        v[t] = make_double2(qb[n].y, qa[n].y);
+      }
+    } else if (!INV) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int n = j + t * T;                                       // < M/2
@@ -585,6 +613,24 @@ int ilog2(int v) {
 
 }  // namespace
 
+typedef CUresult (*DctEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static DctEncodeFn dct_encoder() {
+  static DctEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (DctEncodeFn)f;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
 int launch_dct_rows(int inverse, int rows, int N, const double* src, long long ld_src, double* dst, long long ld_dst,
                     const double* tabs, double scale0, double scale, cudaStream_t st) {
   if (rows < 1 || !src || !dst || !tabs || ld_src < N || ld_dst < N) return AXB_EINVAL;
@@ -627,12 +673,31 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
     if (rr_res < 1) rr_res = 1;
     const int rr_grid = rr_blocks < sms * rr_res ? rr_blocks : sms * rr_res;
     const double2* tbp = reinterpret_cast<const double2*>(tabs);
+    // DCT-II: the row is staged as two arrays of pairs by tensor loads with a 2-element inner box over the
+    // (quadruple, 4) view of the row, so the first pass reads conflict-free 128-bit pairs
+    CUtensorMap tmS;
+    memset(&tmS, 0, sizeof(tmS));
+    int split = 0;
+    static int lin = -1;
+    if (lin < 0) lin = getenv("AXB_DCT_LINEAR") ? 1 : 0;
+    if (!inverse && !lin) {
+      if (DctEncodeFn enc = dct_encoder()) {
+        const cuuint64_t quads = N / 4, mid = quads < 256 ? quads : 256;
+        const cuuint64_t dims[4] = {4, mid, quads / mid, (cuuint64_t)rows};
+        const cuuint64_t strides[3] = {32, mid * 32, (cuuint64_t)ld_src * 8};
+        const cuuint32_t box[4] = {2u, (cuuint32_t)mid, (cuuint32_t)(quads / mid), 1u};
+        const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        split = enc(&tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(src), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+    }
     if (!inverse)
-      k_dct_rows_rr<false><<<rr_grid, rr_rpc * T, rr_bytes, st>>>(rows, N, ilog2(M), rr_rpc, src, ld_src, dst, ld_dst,
-                                                                   tbp, scale0, scale);
+      k_dct_rows_rr<false><<<rr_grid, rr_rpc * T, rr_bytes, st>>>(tmS, split, rows, N, ilog2(M), rr_rpc, src, ld_src, dst,
+                                                                   ld_dst, tbp, scale0, scale);
     else
-      k_dct_rows_rr<true><<<rr_grid, rr_rpc * T, rr_bytes, st>>>(rows, N, ilog2(M), rr_rpc, src, ld_src, dst, ld_dst,
-                                                                  tbp, scale0, scale);
+      k_dct_rows_rr<true><<<rr_grid, rr_rpc * T, rr_bytes, st>>>(tmS, 0, rows, N, ilog2(M), rr_rpc, src, ld_src, dst,
+                                                                  ld_dst, tbp, scale0, scale);
     AXB_LAUNCHED();
     return (int)cudaGetLastError();
   }
