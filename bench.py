@@ -19,6 +19,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv and any(a.startswith("--impl") for a in sys.argv):
+    # the reference arm uses every host core; torchrun pins OMP_NUM_THREADS=1 for its workers, and the BLAS /
+    # OpenMP runtimes read the variables when they are loaded (i.e. before `import numpy`)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
