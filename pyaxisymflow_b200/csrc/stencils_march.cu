@@ -495,16 +495,23 @@ __global__ void __launch_bounds__(MT)
     p += 4 * ld;                                 // row j + 2
     double* o = out + (long long)j0 * ld + k;
     (void)tgm;
-    for (int jb = 0; jb < RB; jb += UR) {
-      double2 pn[UR];
-      double gn[UR], on[UR];
+    // software pipeline: the loads of the next UR rows are issued before the current UR rows are computed
+    // (this pass has a single input field, so one batch of loads in flight does not cover the HBM latency)
+    double2 pn[UR], pq[UR];
+    double gn[UR], on[UR], gq[UR], oq[UR];
+    auto fetch = [&](double2 (&a)[UR], double (&gg)[UR], double (&oo)[UR]) {
 #pragma unroll
-      for (int u = 0; u < UR; ++u) pn[u] = ld2(p + u * ld + k);
+      for (int u = 0; u < UR; ++u) a[u] = ld2(p + u * ld + k);
 #pragma unroll
       for (int u = 0; u < UR; ++u) {
-        gn[u] = edge ? p[u * ld + kg] : 0.0;                 // w[j+2][ghost]
-        on[u] = edge ? p[(u - 1) * ld + go] : 0.0;           // w[j+1][outer]
+        gg[u] = edge ? p[u * ld + kg] : 0.0;                 // w[j+2][ghost]
+        oo[u] = edge ? p[(u - 1) * ld + go] : 0.0;           // w[j+1][outer]
       }
+    };
+    fetch(pn, gn, on);
+    for (int jb = 0; jb < RB; jb += UR) {
+      p += UR * ld;
+      if (jb + UR < RB) fetch(pq, gq, oq);
 #pragma unroll
       for (int u = 0; u < UR; ++u) {
         const int j = j0 + jb + u;
@@ -523,7 +530,9 @@ __global__ void __launch_bounds__(MT)
         wb = wcn; wcn = pn[u];
         gb = gcn; gcn = gn[u];
       }
-      p += UR * ld; o += UR * ld;
+#pragma unroll
+      for (int u = 0; u < UR; ++u) { pn[u] = pq[u]; gn[u] = gq[u]; on[u] = oq[u]; }
+      o += UR * ld;
     }
     return;
   }
