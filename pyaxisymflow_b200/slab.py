@@ -277,8 +277,6 @@ class PartitionedTridiagonal:
     all-to-all transposes for a 2 P Nz gather and one 32 B/pt correction pass."""
 
     def __init__(self, layout, factors, group=None, peer_ptrs=None, host=False):
-        from . import fd
-
         L, f = self.L, self.f = layout, factors
         tri = f["tri"]
         self.group, self.host = group, host
@@ -336,7 +334,6 @@ class PartitionedTridiagonal:
             self.G_ptrs = (ctypes.c_uint64 * L.world)(*ptrs)
         else:
             self.G = torch.zeros((P2, L.nz), dtype=torch.float64, device=dev)
-        _ = fd
 
     def _local_solve(self, x, unit=False):
         from . import fd
