@@ -153,6 +153,18 @@ int axb_smooth_heaviside_sphere(const axb_grid_t* g, double* H, double* phi_out,
 int axb_vortex_stretching(const axb_grid_t* g, double* w, const double* u_r, const double* r1d, double dt,
                           axb_stream_t s);
 
+/* ---- kernels/compute_velocity_from_phi.py:4-17 (velocity of a potential:
+ *      u_z = d(phi)/dz, u_r = d(phi)/dr; centred inside, 2nd-order one-sided at the ends). ---- */
+int axb_velocity_from_phi(const axb_grid_t* g, double* u_z, double* u_r, const double* phi, axb_stream_t s);
+
+/* ---- kernels/update_baroclinic_vorticity.py.  mode 0 = update_baroclinic_vorticity
+ *      (:5-35), 1 = ..._penal (:38-67; penal_z/penal_r required), 2 = ..._diff_penal (:70-127;
+ *      also r1d and nu).  w[1:-1,1:-1] += dt (Du_z/Dt d(rho)/dr - Du_r/Dt d(rho)/dz) / rho. ---- */
+int axb_baroclinic_vorticity_update(const axb_grid_t* g, double* w, const double* u_z, const double* u_r,
+                                    const double* old_u_z, const double* old_u_r, const double* density,
+                                    const double* penal_z, const double* penal_r, const double* r1d, double nu,
+                                    double dt, int mode, axb_stream_t s);
+
 /* ---- a15 diagnostics.  out is a device double; the caller zeroes it (axb_fill_scalars).
  *      max_abs_sum : max(|a| + |b|)           (flow_past_sphere.py:152; b may be NULL)
  *      max         : max(a)                   (flow_past_sphere.py:191)

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "axb_smooth_heaviside": [_G, _P, _P, _D, _S],
     "axb_smooth_heaviside_sphere": [_G, _P, _P, _P, _P, _D, _D, _D, _D, _S],
     "axb_vortex_stretching": [_G, _P, _P, _P, _D, _S],
+    "axb_velocity_from_phi": [_G, _P, _P, _P, _S],
+    "axb_baroclinic_vorticity_update": [_G, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I, _S],
     "axb_reduce_max_abs_sum": [_G, _P, _P, _P, _S],
     "axb_reduce_max": [_G, _P, _P, _S],
     "axb_reduce_weighted_sum": [_G, _P, _P, _P, _D, _P, _S],

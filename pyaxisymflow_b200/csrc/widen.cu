@@ -1,0 +1,178 @@
+// widen.cu -- kernels of the SURVEY.md section 8f "next" rows (sm_100a).
+//
+//   8f-2  kernels/compute_velocity_from_phi.py:4-17        -> axb_velocity_from_phi
+//   8f-4  kernels/update_baroclinic_vorticity.py:4-127     -> axb_baroclinic_vorticity_update
+//
+// Same conventions as stencils.cu: a thread owns two adjacent z columns, a block covers
+// 64 columns x 8 rows (r-neighbours through L1), global z index decides the one-sided ends so
+// the kernels also run on z-slabs.  Compiled with -fmad=false; the operation order is the
+// reference's NumPy/numba expression order, so results are bit-identical to the oracle.
+#include <initializer_list>
+
+#include "axb_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ const double* rowp(const double* f, long long ld, int j) { return f + (long long)j * ld; }
+__device__ __forceinline__ double* rowp(double* f, long long ld, int j) { return f + (long long)j * ld; }
+
+// -------------------------------------------------------------------------------------
+// 8f-2  u_z = d(phi)/dz, u_r = d(phi)/dr, centred inside, second-order one-sided at the ends
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TBX* TBY)
+    k_velocity_phi(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ phi,
+                   bool vec) {
+  const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
+  const int j = blockIdx.y * TBY + threadIdx.y;
+  if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
+  const double h = 2 * g.dx;
+  const int nz = g.nz;
+  const double* pc = rowp(phi, g.ld, j);
+  double2 ur;
+  if (j > 0 && j < g.nr - 1) {
+    const double2 up = ld_pair(rowp(phi, g.ld, j + 1), k, nz, vec);
+    const double2 dn = ld_pair(rowp(phi, g.ld, j - 1), k, nz, vec);
+    ur.x = (up.x - dn.x) / h;
+    ur.y = (up.y - dn.y) / h;
+  } else if (j == 0) {
+    const double2 p0 = ld_pair(pc, k, nz, vec);
+    const double2 p1 = ld_pair(rowp(phi, g.ld, 1), k, nz, vec);
+    const double2 p2 = ld_pair(rowp(phi, g.ld, 2), k, nz, vec);
+    ur.x = (-p2.x + 4 * p1.x - 3 * p0.x) / h;
+    ur.y = (-p2.y + 4 * p1.y - 3 * p0.y) / h;
+  } else {
+    const double2 p0 = ld_pair(pc, k, nz, vec);
+    const double2 p1 = ld_pair(rowp(phi, g.ld, j - 1), k, nz, vec);
+    const double2 p2 = ld_pair(rowp(phi, g.ld, j - 2), k, nz, vec);
+    ur.x = (p2.x - 4 * p1.x + 3 * p0.x) / h;
+    ur.y = (p2.y - 4 * p1.y + 3 * p0.y) / h;
+  }
+  double v[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int kk = k + c;
+    v[c] = 0.0;
+    if (kk < g.ku0 || kk >= g.ku1) continue;
+    const int kg = kk + g.kz0;
+    if (kg > 0 && kg < g.nzg - 1) {
+      v[c] = (pc[kk + 1] - pc[kk - 1]) / h;
+    } else if (kg == 0) {
+      v[c] = (-pc[kk + 2] + 4 * pc[kk + 1] - 3 * pc[kk]) / h;
+    } else if (kg == g.nzg - 1) {
+      v[c] = (pc[kk - 2] - 4 * pc[kk - 1] + 3 * pc[kk]) / h;
+    }
+  }
+  st_pair(rowp(u_z, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(v[0], v[1]));
+  st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, ur);
+}
+
+// -------------------------------------------------------------------------------------
+// 8f-4  baroclinic vorticity source.  MODE 0: update_baroclinic_vorticity (:5-35),
+//       MODE 1: ..._penal (:38-67), MODE 2: ..._diff_penal (:70-127).
+// -------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(TBX* TBY)
+    k_baroclinic(GridD g, double* __restrict__ w, const double* __restrict__ u_z, const double* __restrict__ u_r,
+                 const double* __restrict__ o_z, const double* __restrict__ o_r, const double* __restrict__ rho,
+                 const double* __restrict__ p_z, const double* __restrict__ p_r, const double* __restrict__ r1d,
+                 double nu, double dt) {
+  const int k0 = 2 * (blockIdx.x * TBX + threadIdx.x);
+  const int j = blockIdx.y * TBY + threadIdx.y;
+  if (j < 1 || j >= g.nr - 1) return;
+  const double h = 2 * g.dx;
+  const double* zc = rowp(u_z, g.ld, j);
+  const double* zu = rowp(u_z, g.ld, j + 1);
+  const double* zd = rowp(u_z, g.ld, j - 1);
+  const double* rc = rowp(u_r, g.ld, j);
+  const double* ru = rowp(u_r, g.ld, j + 1);
+  const double* rd = rowp(u_r, g.ld, j - 1);
+  const double* dc = rowp(rho, g.ld, j);
+  const double* du = rowp(rho, g.ld, j + 1);
+  const double* dd = rowp(rho, g.ld, j - 1);
+  const double* ozc = rowp(o_z, g.ld, j);
+  const double* orc = rowp(o_r, g.ld, j);
+  double* out = rowp(w, g.ld, j);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int k = k0 + c;
+    if (k < g.ku0 || k >= g.ku1) continue;
+    const int kg = k + g.kz0;
+    if (kg < 1 || kg > g.nzg - 2) continue;
+    const double uz = zc[k], ur = rc[k];
+    double Dz = (uz - ozc[k]) / dt + uz * (zc[k + 1] - zc[k - 1]) / h + ur * (zu[k] - zd[k]) / h;
+    double Dr = (ur - orc[k]) / dt + uz * (rc[k + 1] - rc[k - 1]) / h + ur * (ru[k] - rd[k]) / h;
+    if (MODE >= 1) {
+      Dz = Dz - rowp(p_z, g.ld, j)[k];
+      Dr = Dr - rowp(p_r, g.ld, j)[k];
+    }
+    if (MODE == 2) {
+      const double r = r1d[j];
+      const double dx2 = g.dx * g.dx;
+      const double lz = (zu[k] + zd[k] + zc[k + 1] + zc[k - 1] - 4 * uz) / dx2 + (zu[k] - zd[k]) / h / r;
+      const double lr =
+          (ru[k] + rd[k] + rc[k + 1] + rc[k - 1] - 4 * ur) / dx2 + (ru[k] - rd[k]) / h / r - ur * (1.0 / (r * r));
+      Dz = Dz - nu * lz;
+      Dr = Dr - nu * lr;
+    }
+    const double src = dt * (Dz * (du[k] - dd[k]) / h - Dr * (dc[k + 1] - dc[k - 1]) / h) / dc[k];
+    out[k] = out[k] + src;
+  }
+}
+
+inline int al_check(std::initializer_list<const void*> ptrs) {
+  for (const void* p : ptrs)
+    if (p && !axb_al8(p)) return AXB_EALIGN;
+  return AXB_OK;
+}
+inline bool vec_ok(const GridD& g, std::initializer_list<const void*> ptrs) {
+  if (g.ld & 1) return false;
+  for (const void* p : ptrs)
+    if (p && !axb_al16(p)) return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int axb_velocity_from_phi(const axb_grid_t* g, double* u_z, double* u_r, const double* phi, axb_stream_t s) {
+  if (!u_z || !u_r || !phi) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  rc = al_check({u_z, u_r, phi});
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
+  const bool vec = vec_ok(d, {u_z, u_r, phi});
+  k_velocity_phi<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, phi, vec);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_baroclinic_vorticity_update(const axb_grid_t* g, double* w, const double* u_z, const double* u_r,
+                                    const double* old_u_z, const double* old_u_r, const double* density,
+                                    const double* penal_z, const double* penal_r, const double* r1d, double nu,
+                                    double dt, int mode, axb_stream_t s) {
+  if (!w || !u_z || !u_r || !old_u_z || !old_u_r || !density) return AXB_EINVAL;
+  if (mode < 0 || mode > 2) return AXB_EINVAL;
+  if (mode >= 1 && (!penal_z || !penal_r)) return AXB_EINVAL;
+  if (mode == 2 && !r1d) return AXB_EINVAL;
+  if (w == u_z || w == u_r || w == density) return AXB_EINVAL;  // neighbours are read while w is written
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  rc = al_check({w, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r, r1d});
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  if (d.nr < 3 || d.nzg < 3) return AXB_OK;  // no interior: the reference's slices are empty
+  const dim3 blk(TBX, TBY), grd = grid2d(d);
+  if (mode == 0)
+    k_baroclinic<0><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, nullptr, nullptr, nullptr, 0.0, dt);
+  else if (mode == 1)
+    k_baroclinic<1><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r, nullptr, 0.0, dt);
+  else
+    k_baroclinic<2><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r, r1d, nu, dt);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+}  // extern "C"

@@ -221,6 +221,48 @@ def vortex_stretching(vorticity, u_r, R, dt):
     st.finish()
 
 
+# --------------------------------------------------------------------------------------
+# kernels/compute_velocity_from_phi.py, kernels/update_baroclinic_vorticity.py  
+# --------------------------------------------------------------------------------------
+def compute_velocity_from_phi_unb(u_z, u_r, phi, dx):
+    """kernels/compute_velocity_from_phi.py:4-17"""
+    st = Stage()
+    (uz, ur), (p,), ld = st.fields(outs=[u_z, u_r], ins=[phi])
+    g = make_grid(p.shape[0], p.shape[1], ld, dx)
+    _call("axb_velocity_from_phi", ctypes.byref(g), ptr(uz), ptr(ur), ptr(p), stream_ptr())
+    st.finish()
+
+
+def _baroclinic(mode, vorticity, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r, R, nu, dt, dx):
+    st = Stage()
+    ins = [u_z, u_r, old_u_z, old_u_r, density] + ([penal_z, penal_r] if mode >= 1 else [])
+    (w,), tin, ld = st.fields(outs=[vorticity], ins=ins)
+    uz, ur, oz, orr, rho = tin[:5]
+    pz, pr = (tin[5], tin[6]) if mode >= 1 else (None, None)
+    g = make_grid(w.shape[0], w.shape[1], ld, dx)
+    r1 = coord_1d(st, R, 0, w.shape[0]) if mode == 2 else None
+    _call("axb_baroclinic_vorticity_update", ctypes.byref(g), ptr(w), ptr(uz), ptr(ur), ptr(oz), ptr(orr), ptr(rho),
+          ptr(pz), ptr(pr), ptr(r1), float(nu), float(dt), mode, stream_ptr())
+    st.finish()
+
+
+def update_baroclinic_vorticity(vorticity, u_z, u_r, old_u_z, old_u_r, density, dt, dx):
+    """kernels/update_baroclinic_vorticity.py:4-35"""
+    _baroclinic(0, vorticity, u_z, u_r, old_u_z, old_u_r, density, None, None, None, 0.0, dt, dx)
+
+
+def update_baroclinic_vorticity_penal(vorticity, u_z, u_r, old_u_z, old_u_r, density, penal_term_z, penal_term_r,
+                                      dt, dx):
+    """kernels/update_baroclinic_vorticity.py:38-67"""
+    _baroclinic(1, vorticity, u_z, u_r, old_u_z, old_u_r, density, penal_term_z, penal_term_r, None, 0.0, dt, dx)
+
+
+def update_baroclinic_vorticity_diff_penal(vorticity, u_z, u_r, old_u_z, old_u_r, density, penal_term_z,
+                                           penal_term_r, R, nu, dt, dx):
+    """kernels/update_baroclinic_vorticity.py:70-127"""
+    _baroclinic(2, vorticity, u_z, u_r, old_u_z, old_u_r, density, penal_term_z, penal_term_r, R, nu, dt, dx)
+
+
 def _reduce(name, fields, R=None, off=0.0, init=0.0):
     st = Stage()
     _, tins, ld = st.fields(ins=fields)
