@@ -234,7 +234,7 @@ def run_gpu_arm(args, nr, nz):
         # non-trivial data from the first step on
         stepper.seed_vorticity()
     else:
-        stepper = _ConfigRunner(args.config, nr, nz, basis, args.cases)
+        stepper = _ConfigRunner(args.config, nr, nz, basis, args.cases, reinit=args.reinit)
         scaling = "weak"          # independent cases / replicas per GPU, no communication
         cases = stepper.cases * world
         workload = stepper.workload
@@ -406,7 +406,7 @@ class _ConfigRunner:
     """BASELINE.json configs other than the headline one, behind the stepper interface bench uses:
     c2 periodic flow past a sphere, c3 soft-sphere streaming, c5 particle ensemble (cases per GPU)."""
 
-    def __init__(self, name, nr, nz, basis, cases):
+    def __init__(self, name, nr, nz, basis, cases, reinit=False):
         import torch
 
         from pyaxisymflow_b200.timestep import ParticleFlowStepper, RigidFlowStepper, SoftSphereStepper
@@ -418,9 +418,13 @@ class _ConfigRunner:
             self.members[0].seed_vorticity()
             self.workload = f"PeriodicFlowPastSphere loop body at {nr}x{nz} (periodic z, ghost 2)"
         elif name == "c3":
-            self.members = [SoftSphereStepper(nz, grid_size_r=nr, basis=basis)]
-            self.workload = (f"SoftSphereStreaming loop body at {nr}x{nz} (reference-map solid; skfmm "
-                             "re-initialisation excluded on both arms)")
+            # Z_cm off the grid's mirror plane when re-initialising: exact ties make the marcher (and the GPU
+            # iteration) order/rounding dependent and cost extra sweeps
+            self.members = [SoftSphereStepper(nz, grid_size_r=nr, basis=basis, reinit_levelset=reinit,
+                                              Z_cm=0.47 if reinit else 0.5)]
+            self.workload = (f"SoftSphereStreaming loop body at {nr}x{nz} (reference-map solid; "
+                             + ("narrow-band level-set re-initialisation on the GPU included)" if reinit else
+                                "skfmm re-initialisation excluded on both arms)"))
         else:
             first = ParticleFlowStepper(nz, grid_size_r=nr, basis=basis)
             self.members = [first]
@@ -506,6 +510,8 @@ def main():
                     help="c4 (default): 4096x16384 rigid flow, the configuration the metric is quoted on; "
                          "c2: periodic 1024x4096; c3: soft sphere 2048x8192; c5: particle ensemble 1024x2048")
     ap.add_argument("--cases", type=int, default=8, help="ensemble members per GPU (c5)")
+    ap.add_argument("--reinit", action="store_true",
+                    help="c3: include the narrow-band level-set re-initialisation (csrc/reinit.cu) in the step")
     ap.add_argument("--no-graph", action="store_true",
                     help="c4, 1 GPU: launch the step kernel by kernel instead of replaying CUDA graphs (before / "
                          "solve / after, with the roofline events between them)")

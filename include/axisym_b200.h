@@ -165,6 +165,20 @@ int axb_baroclinic_vorticity_update(const axb_grid_t* g, double* w, const double
                                     const double* penal_z, const double* penal_r, const double* r1d, double nu,
                                     double dt, int mode, axb_stream_t s);
 
+/* ---- narrow-band level-set re-initialisation, the drivers' third-party call
+ *      `skfmm.distance(phi, dx=dx, narrow=narrow)` (soft_sphere_streaming.py:196-199; scikit-fmm
+ *      2022.8.15, poetry.lock:628-629 -- not vendored, parity unpinned).  In place: cells the marcher
+ *      would return unmasked (accepted |distance| <= narrow plus the tentative ring) are overwritten with
+ *      their signed distance, the others keep their value (`ball_phi[mask] = bad_phi[mask]`).
+ *      mask_out (may be NULL): nr*nz bytes, 1 = masked.  order = 1 or 2 (skfmm default 2).
+ *      work: axb_reinit_workspace_bytes(nr, nz) bytes, 256-byte aligned.  Whole-domain grids only.
+ *      SYNCHRONISES the stream (convergence flag).  info_host[0] = sweeps, info_host[1] = status bits:
+ *      1 no zero contour (skfmm: ValueError), 2 negative discriminant (skfmm: RuntimeError),
+ *      4 no fixed point within the sweep bound. ---- */
+int64_t axb_reinit_workspace_bytes(int nr, int nz);
+int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int order, unsigned char* mask_out,
+                        void* work, int64_t work_bytes, int* info_host, axb_stream_t s);
+
 /* ---- a15 diagnostics.  out is a device double; the caller zeroes it (axb_fill_scalars).
  *      max_abs_sum : max(|a| + |b|)           (flow_past_sphere.py:152; b may be NULL)
  *      max         : max(a)                   (flow_past_sphere.py:191)

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "axb_vortex_stretching": [_G, _P, _P, _P, _D, _S],
     "axb_velocity_from_phi": [_G, _P, _P, _P, _S],
     "axb_baroclinic_vorticity_update": [_G, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I, _S],
+    "axb_reinit_workspace_bytes": [_I, _I],
+    "axb_reinit_distance": [_G, _P, _D, _I, _P, _P, c_int64, POINTER(c_int), _S],
     "axb_reduce_max_abs_sum": [_G, _P, _P, _P, _S],
     "axb_reduce_max": [_G, _P, _P, _S],
     "axb_reduce_weighted_sum": [_G, _P, _P, _P, _D, _P, _S],
@@ -106,8 +108,8 @@ _SIGNATURES = {
     "axb_rows_to_blocks": [_I, _I, _I, _P, c_int64, _P, _S],
     "axb_blocks_to_slab": [_I, _I, c_int64, _I, _P, _P, _S],
 }
-_RESTYPE = {"axb_launch_count": c_int64, "axb_ls_workspace_bytes": c_int64}
-_NO_CHECK = {"axb_version", "axb_launch_count", "axb_ls_workspace_bytes"}
+_RESTYPE = {"axb_launch_count": c_int64, "axb_ls_workspace_bytes": c_int64, "axb_reinit_workspace_bytes": c_int64}
+_NO_CHECK = {"axb_version", "axb_launch_count", "axb_ls_workspace_bytes", "axb_reinit_workspace_bytes"}
 
 _ERR = {-1: "AXB_EINVAL (null pointer / bad shape)", -2: "AXB_EALIGN (misaligned pointer)",
         -3: "AXB_ENOSUP (unsupported configuration)", -4: "AXB_EWORK (workspace too small)"}

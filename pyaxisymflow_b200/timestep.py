@@ -285,14 +285,18 @@ class SoftSphereStepper:
     ENO3 advection of both reference maps, level-set pinning, ENO3 vorticity advection, Heaviside +
     inside mask, least-squares extrapolation of the maps, solid stress (blend fused), div(tau) and
     its curl, moving-tether Heaviside, Brinkman penalisation (+curl), RK2 diffusion.
-    The narrow-band re-initialisation ``skfmm.distance`` (third party, soft_sphere_streaming.py:196-199)
-    is NOT part of this path: ``ball_phi`` is only pinned from the reference map.
+    The narrow-band re-initialisation ``skfmm.distance`` (third party, soft_sphere_streaming.py:196-199,
+    SURVEY.md 8f-3) runs on the GPU when ``reinit_levelset=True`` (``csrc/reinit.cu``, band =
+    ``extrap_zone`` like the driver's ``reinit_band``); by default it is left out, which is what
+    BASELINE.md's config-C3 timing excludes on both the CPU and the GPU side, and ``ball_phi`` is only
+    pinned from the reference map.
     One small D2H (the CFL max) per step, like the reference's ``np.amax``; the LS sweep loop
     synchronises anyway.
     """
 
     def __init__(self, grid_size_z=256, domain_AR=0.5, grid_size_r=None, r_ball=0.15, freq=16.0, nond_AC=0.125,
-                 e=0.1, Cauchy=0.1, zeta=0.25, brink_lam=1e8, CFL=0.1, rho_f=1.0, Z_cm=0.5, R_cm=0.0, basis="auto"):
+                 e=0.1, Cauchy=0.1, zeta=0.25, brink_lam=1e8, CFL=0.1, rho_f=1.0, Z_cm=0.5, R_cm=0.0, basis="auto",
+                 reinit_levelset=False):
         if not torch.cuda.is_available():
             raise _lib.AxbError("SoftSphereStepper needs a CUDA device (no CPU fallback)")
         nz = int(grid_size_z)
@@ -334,6 +338,11 @@ class SoftSphereStepper:
         self._ls_work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         self._ls_bytes = nbytes
         self._umax = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self._reinit = None
+        if reinit_levelset:
+            from .reinit import NarrowBandReinit
+
+            self._reinit = NarrowBandReinit(nr, nz)
         self.t, self.freqTimer, self.it, self.dt = 0.0, 0.0, 0, 0.0
         self.tEnd = 30 / freq
 
@@ -366,6 +375,9 @@ class SoftSphereStepper:
         self.eta2, self._e2b = self._e2b, self.eta2
         _call("axb_pin_level_set", g, ptr(self.ball_phi), None, ptr(self.eta1), ptr(self.eta2), self.Z_cm, self.R_cm,
               self.r_ball, -3 * dx, s)
+        if self._reinit is not None:
+            # reinit level set (soft_sphere_streaming.py:195-199): unreached cells keep their value
+            self._reinit(self.ball_phi, dx, self.extrap_zone)
         _call("axb_advect_vorticity_eno3", g, ptr(self._w2), ptr(w), ptr(self.u_z_upen), ptr(self.u_r_upen), dt, None, s)
         self.vorticity, self._w2 = self._w2, self.vorticity
         w = self.vorticity

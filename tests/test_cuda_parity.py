@@ -1099,8 +1099,9 @@ def test_periodic_rigid_flow_stepper(K):
     assert_close(s.vorticity.cpu().numpy()[:, g:-g], w[:, g:-g], 1e-9, "vorticity (periodic)")
 
 
-def _oracle_soft_sphere_loop(nz, steps):
-    """examples/SoftSphereStreaming/soft_sphere_streaming.py:129-274 without the skfmm re-initialisation"""
+def _oracle_soft_sphere_loop(nz, steps, reinit=False, Z_cm=0.5):
+    """examples/SoftSphereStreaming/soft_sphere_streaming.py:129-274; the skfmm re-initialisation (:195-199)
+    only with ``reinit`` (restated fast marching, oracle.fmm_distance)"""
     nr, dx = nz // 2, 1.0 / nz
     CFL, eps = 0.1, np.finfo(float).eps
     lam, moll = 1e8, dx * 2
@@ -1114,7 +1115,7 @@ def _oracle_soft_sphere_loop(nz, steps):
     z = np.linspace(dx / 2, 1 - dx / 2, nz)
     r = np.linspace(dx / 2, 0.5 - dx / 2, nr)
     Z, R = np.meshgrid(z, r)
-    phi = -np.sqrt((Z - 0.5) ** 2 + R ** 2) + r_ball
+    phi = -np.sqrt((Z - Z_cm) ** 2 + R ** 2) + r_ball
     chi, tchi = np.zeros_like(Z), np.zeros_like(Z)
     ox.smooth_Heaviside(chi, phi, moll)
     w, psi, uz, ur, tmp, pv = (np.zeros_like(Z) for _ in range(6))
@@ -1134,9 +1135,13 @@ def _oracle_soft_sphere_loop(nz, steps):
             dt = flim - ft
         avg_psi += psi * dt
         ox.advect_refmap_via_eno3(eta1, eta2, uz, ur, dt, dx)
-        phi_orig = -np.sqrt((eta1 - 0.5) ** 2 + (eta2 - 0.0) ** 2) + r_ball
+        phi_orig = -np.sqrt((eta1 - Z_cm) ** 2 + (eta2 - 0.0) ** 2) + r_ball
         band = phi > -3 * dx
         phi[band] = phi_orig[band]
+        if reinit:
+            bad_phi = phi.copy()
+            marched = ox.fmm_distance(phi, dx, narrow=zone)
+            phi = np.where(marched.mask, bad_phi, marched.data)
         ox.advect_vorticity_via_eno3(w, uz, ur, dt, dx)
         ox.smooth_Heaviside(chi, phi, moll)
         inside = chi > 0.5
@@ -1145,7 +1150,7 @@ def _oracle_soft_sphere_loop(nz, steps):
         for n in ("s11", "s12", "s22"):
             a[n][...] = chi * a[n]
         ox.update_vorticity_from_solid_stress(w, a["tz"], a["tr"], a["s11"], a["s12"], a["s22"], R, dt, dx)
-        ox.smooth_Heaviside(tchi, -np.sqrt((Z - (0.5 + e * r_ball * np.sin(omega * t))) ** 2 + R ** 2) + zeta * r_ball, moll)
+        ox.smooth_Heaviside(tchi, -np.sqrt((Z - (Z_cm + e * r_ball * np.sin(omega * t))) ** 2 + R ** 2) + zeta * r_ball, moll)
         uzu, uru = uz.copy(), ur.copy()
         ox.brinkmann_penalize(lam, dt, tchi, U_0 * np.cos(omega * t), 0.0, uzu, uru, uz, ur)
         ox.compute_vorticity_from_velocity(pv, uz - uzu, ur - uru, dx)

@@ -110,3 +110,149 @@ def test_baroclinic(K):
             assert np.array_equal(a, b), (nr, nz, mode)
             # the rim is not touched
             assert np.array_equal(a[0], w0[0]) and np.array_equal(a[:, -1], w0[:, -1])
+
+
+# ---------------------------------------------------------------------------------------------
+# 8f-3 narrow-band re-initialisation (csrc/reinit.cu) against the restated marcher
+# (oracle.fmm_distance; scikit-fmm is third party and not vendored: parity unpinned).
+# ---------------------------------------------------------------------------------------------
+def _sphere(nr, nz, zc, rc, rad):
+    dx = 1.0 / nz
+    z = np.linspace(dx / 2, 1 - dx / 2, nz)
+    r = np.linspace(dx / 2, nr * dx - dx / 2, nr)
+    Z, R = np.meshgrid(z, r)
+    return dx, Z, R, rad - np.sqrt((Z - zc) ** 2 + (R - rc) ** 2)
+
+
+def _check_against_marcher(got, ref, phi, what):
+    assert isinstance(got, np.ma.MaskedArray)
+    assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(ref)), what + ": masks differ"
+    seen = ~np.ma.getmaskarray(ref)
+    scale = np.max(np.abs(ref.data[seen]))
+    err = np.max(np.abs(got.data[seen] - ref.data[seen])) / scale
+    assert err <= 1e-12, f"{what}: relative Linf {err:.3e}"
+    return int(np.count_nonzero(got.data[seen] != ref.data[seen]))
+
+
+def test_reinit_matches_marcher(K):
+    from pyaxisymflow_b200 import reinit
+
+    rng = np.random.default_rng(21)
+    inexact = 0
+    for case, (nr, nz) in enumerate([(40, 91), (57, 73), (31, 44), (64, 128), (45, 200), (130, 70)]):
+        dx, Z, R, true = _sphere(nr, nz, rng.uniform(0.3, 0.7), rng.uniform(0, 0.1), rng.uniform(0.08, 0.25))
+        phi = true * (1 + rng.uniform(0, 0.5) * np.sin(rng.uniform(2, 12) * Z + rng.uniform(2, 12) * R))
+        for order in (1, 2):
+            band = rng.uniform(2, 8) * dx
+            ref = ox.fmm_distance(phi, dx, narrow=band, order=order)
+            keep = phi.copy()
+            got = reinit.distance(phi, dx=dx, narrow=band, order=order)
+            assert np.array_equal(phi, keep)                 # like skfmm.distance: the input is not modified
+            inexact += _check_against_marcher(got, ref, phi, f"case {case} order {order}")
+    assert inexact == 0, f"{inexact} cells differ from the marcher in the last bits"
+    # a band thinner than a cell (front flags decide what is usable) and a strided view
+    dx, Z, R, true = _sphere(48, 100, 0.523, 0.033, 0.2)
+    phi = true * (1 + 0.2 * np.sin(6 * Z))
+    _check_against_marcher(reinit.distance(phi, dx=dx, narrow=0.6 * dx), ox.fmm_distance(phi, dx, narrow=0.6 * dx), phi, "thin")
+    view = phi[:, 3:-5]
+    _check_against_marcher(reinit.distance(view, dx=dx, narrow=4 * dx), ox.fmm_distance(view, dx, narrow=4 * dx), view, "view")
+
+
+def test_reinit_errors_and_device_path(K):
+    import torch
+    from pyaxisymflow_b200 import reinit
+    from pyaxisymflow_b200.device import DeviceField
+
+    with pytest.raises(ValueError):
+        reinit.distance(np.ones((16, 16)), dx=0.1, narrow=0.3)          # no zero contour (skfmm: ValueError)
+    with pytest.raises(ValueError):
+        reinit.distance(np.ones((16, 16)), dx=0.1, narrow=0.0)
+    dx, Z, R, true = _sphere(64, 160, 0.45, 0.0, 0.2)
+    phi = true * (1 + 0.3 * np.sin(8 * Z + 3 * R))
+    ref = ox.fmm_distance(phi, dx, narrow=5 * dx)
+    d, mask = reinit.distance(DeviceField(torch.from_numpy(phi).cuda()), dx=dx, narrow=5 * dx)
+    assert np.array_equal(mask.cpu().numpy(), np.ma.getmaskarray(ref))
+    seen = ~np.ma.getmaskarray(ref)
+    assert np.max(np.abs(d.t.cpu().numpy()[seen] - ref.data[seen])) <= 1e-12 * 5 * dx
+    # in-place form used by the stepper: unreached cells keep their old value
+    t = torch.from_numpy(phi).cuda()
+    r = reinit.NarrowBandReinit(64, 160)
+    r(t, dx, 5 * dx)
+    out = t.cpu().numpy()
+    assert np.array_equal(out[~seen], phi[~seen]) and np.max(np.abs(out[seen] - ref.data[seen])) <= 1e-12 * 5 * dx
+    assert 5 <= r.sweeps <= 60
+    with pytest.raises(ValueError):
+        r(torch.zeros(8, 8, dtype=torch.float64, device="cuda"), dx, 5 * dx)
+
+
+def test_reinit_terminates_on_rough_and_colliding_input(K):
+    """the marcher is order dependent where fronts collide or the level set is noisy; the GPU iteration must
+    still terminate with a defined result close to it (and identical front cells)."""
+    from pyaxisymflow_b200 import reinit
+
+    dx, Z, R, a = _sphere(18, 36, 0.3, 0.05, 0.1)
+    b = 0.12 - np.sqrt((Z - 0.62) ** 2 + (R - 0.1) ** 2)
+    phi = np.maximum(a, b) * (1 + 0.3 * np.sin(5 * Z + 7 * R))
+    ref = ox.fmm_distance(phi, dx, narrow=5.7 * dx)
+    got = reinit.distance(phi, dx=dx, narrow=5.7 * dx)
+    assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(ref))
+    seen = ~np.ma.getmaskarray(ref)
+    assert np.max(np.abs(got.data[seen] - ref.data[seen])) <= 5e-3 * dx
+    rng = np.random.default_rng(5)
+    dx, Z, R, true = _sphere(30, 48, 0.5, 0.04, 0.2)
+    noisy = true + 0.2 * dx * rng.standard_normal(true.shape)
+    got = reinit.distance(noisy, dx=dx, narrow=5 * dx)
+    front_d, front = ox.fmm_initial_front(noisy, dx)
+    assert np.array_equal(got.data[front], front_d[front]) and not np.ma.getmaskarray(got)[front].any()
+    seen = ~np.ma.getmaskarray(got)
+    assert np.all(np.sign(got.data[seen]) == np.sign(noisy[seen]))
+
+
+def test_reinit_full_size_against_marcher(K):
+    """config-C3 size (2048 x 8192): same cells, same values as the marcher; signed-distance sanity."""
+    import torch
+    from pyaxisymflow_b200 import reinit
+
+    nr, nz = 2048, 8192
+    dx, Z, R, true = _sphere(nr, nz, 0.47, 0.0, 0.15)
+    phi = true * (1 + 0.2 * np.sin(9 * Z + 5 * R))
+    band = 6 * dx
+    ref = ox.fmm_distance(phi, dx, narrow=band)
+    t = torch.from_numpy(phi).cuda()
+    mask = torch.empty((nr, nz), dtype=torch.uint8, device="cuda")
+    r = reinit.NarrowBandReinit(nr, nz)
+    r(t, dx, band, mask_out=mask)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t2 = torch.from_numpy(phi).cuda()
+    ev0.record()
+    r(t2, dx, band)
+    ev1.record()
+    torch.cuda.synchronize()
+    print(f"\nreinit 2048x8192, band 6 dx: {ev0.elapsed_time(ev1):.3f} ms, {r.sweeps} sweeps")
+    got = t.cpu().numpy()
+    m = mask.cpu().numpy().astype(bool)
+    assert np.array_equal(m, np.ma.getmaskarray(ref))
+    seen = ~m
+    assert np.array_equal(got[m], phi[m])
+    assert np.max(np.abs(got[seen] - ref.data[seen])) <= 1e-12 * band
+    acc = seen & (np.abs(got) <= band)
+    assert np.max(np.abs(got - true)[acc]) <= 0.35 * dx          # the marcher's own accuracy (first-order front)
+    assert np.array_equal(t2.cpu().numpy(), got)                 # deterministic
+
+
+def test_soft_sphere_stepper_with_reinit(K):
+    """config-C3 loop INCLUDING the level-set re-initialisation (soft_sphere_streaming.py:195-199)."""
+    from test_cuda_parity import _oracle_soft_sphere_loop
+    from pyaxisymflow_b200.timestep import SoftSphereStepper
+
+    nz, steps = 64, 6
+    w, eta1, eta2, phi, avg_psi, t = _oracle_soft_sphere_loop(nz, steps, reinit=True, Z_cm=0.47)
+    s = SoftSphereStepper(nz, Z_cm=0.47, reinit_levelset=True)
+    s.step(steps)
+    assert abs(s.t - t) <= 1e-12 * t and s.ls_sweeps >= 4
+    assert_close(s.ball_phi.cpu().numpy(), phi, 1e-10, "ball_phi (re-initialised)")
+    assert_close(s.eta1.cpu().numpy(), eta1, 1e-10, "eta1")
+    assert_close(s.eta2.cpu().numpy(), eta2, 1e-10, "eta2")
+    assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (soft sphere, reinit)")
+    assert_close(s.avg_psi.cpu().numpy(), avg_psi, 1e-9, "avg_psi")
