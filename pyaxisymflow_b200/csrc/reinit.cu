@@ -9,64 +9,85 @@
 // that restatement on the CPU.
 //
 // The marcher accepts one cell at a time from a heap -- serial.  Here the same upwind update is iterated
-// to its fixed point by all band cells at once (Jacobi, two buffers, so the result does not depend on
-// scheduling):
-//   k_reinit_front   whole grid, 8 B/pt read: cells whose 4-neighbourhood straddles the zero contour get the
-//                    distance from the linear crossings (identical to the marcher's first step); they mark
-//                    the 64x8-cell tiles within reach of the band;
-//   k_reinit_compact active tiles -> list (the sweeps only visit those: O(band) work, L2 resident);
-//   k_reinit_sweep   every non-front cell of the active tiles recomputes its value from the neighbours the
-//                    marcher would have frozen before it: front cells and cells with |value| <= narrow that
-//                    are causally smaller than the result (a dimension whose upwind value is not below the
-//                    2-D result is dropped).  Second order where the two upwind cells are usable and
-//                    monotone, else first order -- distance_marcher's selection rule, literally.
-//                    A state that repeats with period 2 (tied neighbours flipping in the last bits) also ends
-//                    the iteration (k_reinit_pick keeps the value of smaller magnitude).  After `free_iter`
-//                    sweeps values may only shrink in magnitude: where two fronts collide inside the band the
-//                    second-order selection can otherwise flip for ever.
+// to its fixed point by all band cells at once:
+//   k_reinit_front   whole grid, 8 B/pt read + 1 B/pt flag: cells whose 4-neighbourhood straddles the zero
+//                    contour get the distance from the linear crossings (identical to the marcher's first
+//                    step); they mark the 32x32-cell tiles within reach of the band;
+//   k_reinit_compact active tiles -> list;  k_reinit_fill: the two value buffers of those tiles;
+//   k_reinit_sweep   one block per active tile: tile + halo of 2 in shared memory, up to `inner` Jacobi
+//                    iterations on chip (halo frozen; ends early when the tile is stationary), tiles whose
+//                    neighbourhood did not change in the previous launch are skipped.  Every non-front cell
+//                    recomputes its value from the neighbours the marcher would have frozen before it: front
+//                    cells and cells with |value| <= narrow that are causally smaller than the result (a
+//                    dimension whose upwind value is not below the 2-D result is dropped).  Second order where
+//                    the two upwind cells are usable and monotone, else first order -- distance_marcher's
+//                    selection rule, literally.  On a smooth contour the band settles in 2-3 launches; what
+//                    remains are dependency chains of ~sqrt(2 R W) cells along the contour where it is axis
+//                    aligned (one cell per iteration), a handful of tiles.  After `free_launch` launches values
+//                    may only shrink in magnitude: where two fronts collide inside the band, or neighbours are
+//                    exactly tied, the second-order selection can otherwise flip for ever.
 //   k_reinit_ring    accepted cells -> phi; cells next to an accepted cell get the marcher's tentative value
 //                    (update from all accepted neighbours, no causality filter); everything else keeps its
 //                    old value (the driver's `ball_phi[mask] = bad_phi[mask]`).
-// Wherever the distance field is smooth the fixed point equals the marcher's result bit for bit (same
-// expressions, -fmad=false).  The entry synchronises (convergence flag), like the LS extrapolation.
+// The fixed point does not depend on the iteration order; wherever the distance field is smooth it equals the
+// marcher's result bit for bit (same expressions, -fmad=false).  The entry synchronises (convergence flag),
+// like the LS extrapolation.
 #include <float.h>
 
 #include "axb_common.cuh"
 
 namespace {
 
-constexpr int TW = 64, TH = 8;  // tile = 64 columns x 8 rows, one thread per cell
+constexpr int TW = 32, TH = 32;  // tile = 32 columns x 32 rows, one thread per cell
+constexpr int HALO = 2, SW = TW + 2 * HALO, SH = TH + 2 * HALO;
 constexpr double MAXD = DBL_MAX;
 
-struct Ctr {  // device counters (changed / changed2 adjacent: reset together)
-  int n_active, changed, changed2, negdet, has_front;
+struct Ctr {  // device counters
+  int n_active, changed, negdet, has_front;
 };
 
-__device__ __forceinline__ bool usable(double d, double narrow, const unsigned char* __restrict__ flag,
-                                       long long idx) {
-  return fabs(d) <= narrow || (flag != nullptr && flag[idx] != 0);
+// cell values / front flags as the update sees them
+struct GlobalAcc {  // dense (nr, nz) buffers; cells of inactive tiles were never initialised: unreached
+  const double* __restrict__ d;
+  const unsigned char* __restrict__ f;
+  const int* __restrict__ tile_flag;
+  int nz, ntc;
+  __device__ __forceinline__ double val(int jj, int kk) const {
+    return tile_flag[(jj / TH) * ntc + kk / TW] ? d[(long long)jj * nz + kk] : MAXD;
+  }
+  __device__ __forceinline__ bool flg(int jj, int kk) const { return f[(long long)jj * nz + kk] != 0; }
+};
+struct TileAcc {  // shared-memory tile with halo, origin (j0, k0) = global index of element [0][0]
+  const double (*d)[SW];
+  const unsigned char (*f)[SW];
+  int j0, k0;
+  __device__ __forceinline__ double val(int jj, int kk) const { return d[jj - j0][kk - k0]; }
+  __device__ __forceinline__ bool flg(int jj, int kk) const { return f[jj - j0][kk - k0] != 0; }
+};
+
+template <class Acc>
+__device__ __forceinline__ bool usable(const Acc& A, double v, double narrow, int jj, int kk) {
+  return fabs(v) <= narrow || A.flg(jj, kk);
 }
 
 // (value1, value2) of one dimension: distance_marcher's selection among the usable neighbours
-__device__ __forceinline__ void upwind(const double* __restrict__ d, const unsigned char* __restrict__ flag,
-                                       double narrow, int nr, int nz, int j, int k, int dim, int order, double& v1,
-                                       double& v2) {
+template <class Acc>
+__device__ __forceinline__ void upwind(const Acc& A, double narrow, int nr, int nz, int j, int k, int dim, int order,
+                                       double& v1, double& v2) {
   v1 = MAXD;
   v2 = MAXD;
 #pragma unroll
   for (int s = -1; s <= 1; s += 2) {
     const int jj = dim == 0 ? j + s : j, kk = dim == 0 ? k : k + s;
     if (jj < 0 || jj >= nr || kk < 0 || kk >= nz) continue;
-    const long long i1 = (long long)jj * nz + kk;
-    const double dn = d[i1];
-    if (!usable(dn, narrow, flag, i1)) continue;
+    const double dn = A.val(jj, kk);
+    if (!usable(A, dn, narrow, jj, kk)) continue;
     if (fabs(dn) < fabs(v1)) {
       v1 = dn;
       const int j2 = dim == 0 ? j + 2 * s : j, k2 = dim == 0 ? k : k + 2 * s;
       if (order == 2 && j2 >= 0 && j2 < nr && k2 >= 0 && k2 < nz) {
-        const long long i2 = (long long)j2 * nz + k2;
-        const double d2 = d[i2];
-        if (usable(d2, narrow, flag, i2) && ((d2 <= v1 && v1 >= 0) || (d2 >= v1 && v1 <= 0))) v2 = d2;
+        const double d2 = A.val(j2, k2);
+        if (usable(A, d2, narrow, j2, k2) && ((d2 <= v1 && v1 >= 0) || (d2 >= v1 && v1 <= 0))) v2 = d2;
       }
     }
   }
@@ -97,14 +118,13 @@ __device__ __forceinline__ bool quadratic(double a, double b, double c, bool pos
 
 // new value of cell (j, k).  CAUSAL: the sweep form (returns MAXD when nothing usable); otherwise the
 // marcher's tentative value from all usable neighbours (`ok` false on a negative discriminant).
-template <bool CAUSAL>
-__device__ __forceinline__ double update_cell(const double* __restrict__ d, const unsigned char* __restrict__ flag,
-                                              double narrow, int nr, int nz, int j, int k, double dx, int order,
-                                              bool positive, bool& ok) {
+template <bool CAUSAL, class Acc>
+__device__ __forceinline__ double update_cell(const Acc& A, double narrow, int nr, int nz, int j, int k, double dx,
+                                              int order, bool positive, bool& ok) {
   const double idx2 = 1 / dx / dx;
   double v1[2], v2[2];
-  upwind(d, flag, narrow, nr, nz, j, k, 0, order, v1[0], v2[0]);
-  upwind(d, flag, narrow, nr, nz, j, k, 1, order, v1[1], v2[1]);
+  upwind(A, narrow, nr, nz, j, k, 0, order, v1[0], v2[0]);
+  upwind(A, narrow, nr, nz, j, k, 1, order, v1[1], v2[1]);
   const bool h0 = v1[0] < MAXD, h1 = v1[1] < MAXD;
   ok = true;
   if (!h0 && !h1) return MAXD;
@@ -134,8 +154,8 @@ __device__ __forceinline__ double update_cell(const double* __restrict__ d, cons
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TW* TH)
     k_reinit_front(int nr, int nz, long long ld, double dx, const double* __restrict__ phi, double* __restrict__ dA,
-                   double* __restrict__ dB, unsigned char* __restrict__ flag, int* __restrict__ tile_flag, int reach,
-                   int ntr, int ntc, Ctr* ctr) {
+                   unsigned char* __restrict__ flag, int* __restrict__ tile_flag, int reach, int ntr, int ntc,
+                   Ctr* ctr) {
   const int k = blockIdx.x * TW + threadIdx.x;
   const int j = blockIdx.y * TH + threadIdx.y;
   if (j >= nr || k >= nz) return;
@@ -172,10 +192,9 @@ __global__ void __launch_bounds__(TW* TH)
     }
   }
   const long long i = (long long)j * nz + k;
-  dA[i] = dist;
-  dB[i] = dist;
   flag[i] = front ? 1 : 0;
   if (front) {
+    dA[i] = dist;  // the other cells of the active tiles are filled by k_reinit_fill
     ctr->has_front = 1;
     const int t0 = max(j - reach, 0) / TH, t1 = min(j + reach, nr - 1) / TH;
     const int c0 = max(k - reach, 0) / TW, c1 = min(k + reach, nz - 1) / TW;
@@ -189,25 +208,41 @@ __global__ void k_reinit_compact(const int* __restrict__ tile_flag, int ntiles, 
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const int on = tile_flag[t] != 0;
-  chg_a[t] = on;  // "changed before the first sweep": every active tile is visited once
+  chg_a[t] = on;  // "changed before the first launch": every active tile is visited once
   chg_b[t] = 0;
   if (on) tile_list[atomicAdd(&ctr->n_active, 1)] = t;
 }
 
-// One Jacobi sweep over the active tiles.  `chg_prev[t]` says whether tile t changed in the previous sweep;
-// a tile whose own and neighbouring tiles (the stencil reaches 2 cells, less than a tile) did not change has
-// nothing to do: its inputs are what they were, and both buffers already hold its values.  Late sweeps, when
-// only the long tangential dependency chains near the axis-aligned points of the contour are still moving,
-// therefore touch a handful of tiles.
+// both value buffers of the active tiles: front distance (written by k_reinit_front) or "unreached"
+__global__ void __launch_bounds__(TW* TH)
+    k_reinit_fill(int nr, int nz, double* __restrict__ dA, double* __restrict__ dB,
+                  const unsigned char* __restrict__ flag, const int* __restrict__ tile_list, int ntc) {
+  const int t = tile_list[blockIdx.x];
+  const int k = (t % ntc) * TW + threadIdx.x;
+  const int j = (t / ntc) * TH + threadIdx.y;
+  if (j >= nr || k >= nz) return;
+  const long long i = (long long)j * nz + k;
+  const double v = flag[i] ? dA[i] : MAXD;
+  dA[i] = v;
+  dB[i] = v;
+}
+
+// One launch = up to `inner` Jacobi iterations of every active tile in shared memory.  `chg_prev[t]` says whether
+// tile t changed in the previous launch; a tile whose own and neighbouring tiles did not change has nothing to do
+// (its inputs are what they were and both global buffers already hold its values).
 __global__ void __launch_bounds__(TW* TH)
     k_reinit_sweep(int nr, int nz, long long ld, double dx, const double* __restrict__ phi,
                    const double* __restrict__ din, double* __restrict__ dout, const unsigned char* __restrict__ flag,
-                   bool use_flag, const int* __restrict__ tile_list, int ntr, int ntc, const int* __restrict__ chg_prev,
-                   int* __restrict__ chg_cur, double narrow, int order, int monotone, Ctr* ctr) {
+                   const int* __restrict__ tile_flag, const int* __restrict__ tile_list, int ntr, int ntc,
+                   const int* __restrict__ chg_prev, int* __restrict__ chg_cur, double narrow, int order,
+                   int monotone, int inner, Ctr* ctr) {
+  __shared__ double sd[2][SH][SW];
+  __shared__ unsigned char sf[SH][SW];
   __shared__ int s_act;
+  const int tid = threadIdx.y * TW + threadIdx.x;
   const int t = tile_list[blockIdx.x];
   const int tj = t / ntc, tc = t % ntc;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
+  if (tid == 0) {
     int a = 0;
     for (int dj = -1; dj <= 1; ++dj)
       for (int dc = -1; dc <= 1; ++dc) {
@@ -218,60 +253,70 @@ __global__ void __launch_bounds__(TW* TH)
   }
   __syncthreads();
   if (!s_act) {  // block-uniform
-    if (threadIdx.x == 0 && threadIdx.y == 0) chg_cur[t] = 0;
+    if (tid == 0) chg_cur[t] = 0;
     return;
   }
-  const int k = tc * TW + threadIdx.x;
-  const int j = tj * TH + threadIdx.y;
-  int c1 = 0, c2 = 0;
-  if (j < nr && k < nz) {
-    const long long i = (long long)j * nz + k;
-    if (!flag[i]) {  // front cells are fixed (both buffers hold their distance)
-      const double cur = din[i];
-      bool ok;
-      double r = update_cell<true>(din, use_flag ? flag : nullptr, narrow, nr, nz, j, k, dx, order,
-                                   phi[(long long)j * ld + k] > DBL_EPSILON, ok);
-      if (monotone && !(fabs(r) < fabs(cur))) r = cur;
-      const double before = dout[i];  // the state two sweeps ago
-      dout[i] = r;
-      c1 = __double_as_longlong(r) != __double_as_longlong(cur);
-      c2 = __double_as_longlong(r) != __double_as_longlong(before);
+  const int j0 = tj * TH - HALO, k0 = tc * TW - HALO;
+  for (int idx = tid; idx < SH * SW; idx += TW * TH) {
+    const int lj = idx / SW, lk = idx % SW;
+    const int jj = j0 + lj, kk = k0 + lk;
+    double v = MAXD;
+    unsigned char fl = 0;
+    if (jj >= 0 && jj < nr && kk >= 0 && kk < nz && tile_flag[(jj / TH) * ntc + kk / TW]) {
+      const long long i = (long long)jj * nz + kk;
+      v = din[i];
+      fl = flag[i];
     }
+    sd[0][lj][lk] = v;
+    sd[1][lj][lk] = v;
+    sf[lj][lk] = fl;
+  }
+  __syncthreads();
+  const int lj = threadIdx.y + HALO, lk = threadIdx.x + HALO;
+  const int j = j0 + lj, k = k0 + lk;
+  const bool inside = j < nr && k < nz;
+  const bool active = inside && !sf[lj][lk];  // front cells are fixed
+  const bool positive = inside ? (phi[(long long)j * ld + k] > DBL_EPSILON) : false;
+  const double start = sd[0][lj][lk];
+  int b = 0;
+  for (int q = 0; q < inner; ++q) {
+    int ch = 0;
+    if (active) {
+      const double cur = sd[b][lj][lk];
+      TileAcc A{sd[b], sf, j0, k0};
+      bool ok;
+      double r = update_cell<true>(A, narrow, nr, nz, j, k, dx, order, positive, ok);
+      if (monotone && !(fabs(r) < fabs(cur))) r = cur;
+      sd[b ^ 1][lj][lk] = r;
+      ch = __double_as_longlong(r) != __double_as_longlong(cur);
+    }
+    b ^= 1;
+    if (!__syncthreads_or(ch)) break;  // also orders this iteration's writes before the next one's reads
+  }
+  int c1 = 0;
+  if (active) {
+    const double fin = sd[b][lj][lk];
+    dout[(long long)j * nz + k] = fin;
+    c1 = __double_as_longlong(fin) != __double_as_longlong(start);
   }
   const int any1 = __syncthreads_or(c1);
-  const int any2 = __syncthreads_or(c2);
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
+  if (tid == 0) {
     chg_cur[t] = any1;
     if (any1) ctr->changed = 1;
-    if (any2) ctr->changed2 = 1;
   }
-}
-
-// period-2 cycle (tied neighbours that take each other as upwind cell when the rounding of the 2-D root says
-// so; the two states differ in the last bits): keep, per cell, the value of smaller magnitude.
-// `older` = state n, `latest` = state n+1 (== state n-1); the result goes to `latest`.
-__global__ void __launch_bounds__(TW* TH)
-    k_reinit_pick(int nr, int nz, const double* __restrict__ older, double* __restrict__ latest,
-                  const unsigned char* __restrict__ flag, const int* __restrict__ tile_list, int ntc) {
-  const int t = tile_list[blockIdx.x];
-  const int k = (t % ntc) * TW + threadIdx.x;
-  const int j = (t / ntc) * TH + threadIdx.y;
-  if (j >= nr || k >= nz) return;
-  const long long i = (long long)j * nz + k;
-  if (flag[i]) return;
-  const double a = older[i], b = latest[i];
-  latest[i] = fabs(a) <= fabs(b) ? a : b;
 }
 
 __global__ void __launch_bounds__(TW* TH)
     k_reinit_ring(int nr, int nz, long long ld, double dx, double* __restrict__ phi, const double* __restrict__ d,
-                  const unsigned char* __restrict__ flag, const int* __restrict__ tile_list, int ntc, double narrow,
-                  int order, unsigned char* __restrict__ mask_out, Ctr* ctr) {
+                  const unsigned char* __restrict__ flag, const int* __restrict__ tile_flag,
+                  const int* __restrict__ tile_list, int ntc, double narrow, int order,
+                  unsigned char* __restrict__ mask_out, Ctr* ctr) {
   const int t = tile_list[blockIdx.x];
   const int k = (t % ntc) * TW + threadIdx.x;
   const int j = (t / ntc) * TH + threadIdx.y;
   if (j >= nr || k >= nz) return;
   const long long i = (long long)j * nz + k;
+  const GlobalAcc A{d, flag, tile_flag, nz, ntc};
   const double mine = d[i];
   // accepted = what the marcher froze: front cells and cells whose value is within the band
   if (fabs(mine) <= narrow || flag[i]) {
@@ -280,14 +325,13 @@ __global__ void __launch_bounds__(TW* TH)
     return;
   }
   bool touches = false;
-  if (j > 0) touches |= fabs(d[i - nz]) <= narrow || flag[i - nz];
-  if (j < nr - 1) touches |= fabs(d[i + nz]) <= narrow || flag[i + nz];
-  if (k > 0) touches |= fabs(d[i - 1]) <= narrow || flag[i - 1];
-  if (k < nz - 1) touches |= fabs(d[i + 1]) <= narrow || flag[i + 1];
+  if (j > 0) touches |= usable(A, A.val(j - 1, k), narrow, j - 1, k);
+  if (j < nr - 1) touches |= usable(A, A.val(j + 1, k), narrow, j + 1, k);
+  if (k > 0) touches |= usable(A, A.val(j, k - 1), narrow, j, k - 1);
+  if (k < nz - 1) touches |= usable(A, A.val(j, k + 1), narrow, j, k + 1);
   if (!touches) return;
   bool ok;
-  const double r = update_cell<false>(d, flag, narrow, nr, nz, j, k, dx, order,
-                                      phi[(long long)j * ld + k] > DBL_EPSILON, ok);
+  const double r = update_cell<false>(A, narrow, nr, nz, j, k, dx, order, phi[(long long)j * ld + k] > DBL_EPSILON, ok);
   if (!ok) {
     ctr->negdet = 1;
     return;
@@ -309,8 +353,8 @@ int64_t axb_reinit_workspace_bytes(int nr, int nz) {
   return 2 * align256(8 * n) + align256(n) + 4 * align256(4 * ntiles) + 256;
 }
 
-// info_host[0] = sweeps run, info_host[1] = status bits: 1 no zero contour, 2 negative discriminant in the
-// tentative ring, 4 sweeps did not reach a fixed point within the bound.
+// info_host[0] = sweep launches run, info_host[1] = status bits: 1 no zero contour, 2 negative discriminant in
+// the tentative ring, 4 no fixed point within the launch bound.
 int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int order, unsigned char* mask_out,
                         void* work, int64_t work_bytes, int* info_host, axb_stream_t s) {
   if (!phi || !work || !info_host) return AXB_EINVAL;
@@ -340,21 +384,23 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   const double wcells = ceil(narrow / g->dx);
   if (wcells > 1.0e6) return AXB_EINVAL;
   const int W = (int)wcells;
-  const int reach = W + 3;  // accepted cells lie within W cells of a front cell, the ring one further, +1 slack
-  // sweeps needed on a smooth contour: ~2W across the band plus the tangential dependency chains where the
-  // contour is axis aligned, ~sqrt(2 R W) cells for a radius of curvature of R cells (<= the grid size)
+  // accepted cells lie within W (+1) cells of a front cell, the tentative ring one further, its stencil two more
+  const int reach = W + 4;
+  // on-chip iterations per launch: a dependency chain advances one cell per iteration, a tile is 32 cells wide
+  const int inner = 40;
+  // launches needed on a smooth contour: 2-3 for the band, then the chains along the contour where it is axis
+  // aligned, ~sqrt(2 R W) cells for a radius of curvature of R cells (<= the grid size), ~TW cells per launch
   const int longest = nr > nz ? nr : nz;
-  const int free_iter = 8 * W + 64 + (int)ceil(2.0 * sqrt(2.0 * (double)longest * (double)W));
-  const int max_iter = 2 * free_iter;
-  const bool use_flag = narrow < g->dx;  // front distances are <= dx: flags only matter for thinner bands
+  const int chain = 2 * W + (int)ceil(2.0 * sqrt(2.0 * (double)longest * (double)W));
+  const int free_launch = 8 + 2 * ((chain + TW - 1) / TW);
+  const int max_launch = 2 * free_launch;
 
   cudaError_t e;
   if ((e = cudaMemsetAsync(tile_flag, 0, align256(4 * ntiles), s)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(ctr, 0, sizeof(Ctr), s)) != cudaSuccess) return (int)e;
   if (mask_out && (e = cudaMemsetAsync(mask_out, 1, n, s)) != cudaSuccess) return (int)e;
   const dim3 blk(TW, TH);
-  k_reinit_front<<<dim3(ntc, ntr), blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, dA, dB, flag, tile_flag, reach, ntr, ntc,
-                                               ctr);
+  k_reinit_front<<<dim3(ntc, ntr), blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, dA, flag, tile_flag, reach, ntr, ntc, ctr);
   AXB_LAUNCHED();
   k_reinit_compact<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(tile_flag, (int)ntiles, tile_list, chg_prev,
                                                                     chg_cur, ctr);
@@ -368,37 +414,29 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
     return AXB_OK;
   }
   const int nact = h.n_active;
+  k_reinit_fill<<<nact, blk, 0, s>>>(nr, nz, dA, dB, flag, tile_list, ntc);
+  AXB_LAUNCHED();
   double *din = dA, *dout = dB;
   int it = 0;
   bool converged = false;
-  while (it < max_iter && !converged) {
-    // a group of sweeps, the last one with the change flag armed
-    const int group = (it < W) ? (W - it) : (it < 4 * W + 16 ? 4 : 8);
-    for (int q = 0; q < group && it < max_iter; ++q) {
-      const bool last = (q == group - 1) || (it + 1 == max_iter);
-      if (last && (e = cudaMemsetAsync(&ctr->changed, 0, 2 * sizeof(int), s)) != cudaSuccess) return (int)e;
-      ++it;
-      k_reinit_sweep<<<nact, blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, din, dout, flag, use_flag, tile_list, ntr, ntc,
-                                          chg_prev, chg_cur, narrow, order, it > free_iter ? 1 : 0, ctr);
-      AXB_LAUNCHED();
-      double* tmp = din; din = dout; dout = tmp;
-      int* tc_ = chg_prev; chg_prev = chg_cur; chg_cur = tc_;
-    }
+  while (it < max_launch && !converged) {
+    if ((e = cudaMemsetAsync(&ctr->changed, 0, sizeof(int), s)) != cudaSuccess) return (int)e;
+    ++it;
+    k_reinit_sweep<<<nact, blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, din, dout, flag, tile_flag, tile_list, ntr, ntc,
+                                        chg_prev, chg_cur, narrow, order, it > free_launch ? 1 : 0, inner, ctr);
+    AXB_LAUNCHED();
+    double* tmp = din; din = dout; dout = tmp;
+    int* tc_ = chg_prev; chg_prev = chg_cur; chg_cur = tc_;
+    if (it == 1) continue;  // the band cannot settle in one launch (tile halos are frozen within a launch)
     if ((e = cudaMemcpyAsync(&h, ctr, sizeof(Ctr), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return (int)e;
     converged = (h.changed == 0);
-    if (!converged && h.changed2 == 0) {
-      // state n+1 == state n-1: `din` holds n+1, `dout` holds n
-      k_reinit_pick<<<nact, blk, 0, s>>>(nr, nz, dout, din, flag, tile_list, ntc);
-      AXB_LAUNCHED();
-      converged = true;
-    }
   }
   info_host[0] = it;
   if (!converged) info_host[1] |= 4;
   // `din` now holds the latest values
-  k_reinit_ring<<<nact, blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, din, flag, tile_list, ntc, narrow, order, mask_out,
-                                     ctr);
+  k_reinit_ring<<<nact, blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, din, flag, tile_flag, tile_list, ntc, narrow, order,
+                                     mask_out, ctr);
   AXB_LAUNCHED();
   if ((e = cudaMemcpyAsync(&h, ctr, sizeof(Ctr), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return (int)e;

@@ -1,0 +1,178 @@
+"""Output on either side of the timestep loop: restart files and field dumps taken from
+device-resident fields without stalling the loop.
+
+The reference's drivers write ``np.savez("restart.npz", t=..., vorticity=..., ...)`` and reload it with
+``np.load`` (``examples/ParticleOscillatoryFlowCases/particle_in_bubble_oscillatory_flow.py:129-147, 236-257``),
+and dump ``.vti`` images through ``utils/dump_vtk.py``.  Here a :class:`FieldSnapshotter` copies the fields into
+pinned host buffers on a side stream (ordered after the work already queued on the compute stream, so it sees a
+consistent step) and hands them to a worker thread that does the file I/O; the compute stream is never
+synchronised.  ``save_npz`` / ``load_npz`` keep the reference's on-disk format: a plain ``.npz`` with the same
+keys, readable by ``np.load`` on either side.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+
+import numpy as np
+import torch
+
+from .device import DeviceField
+
+
+def _as_tensor(x):
+    if isinstance(x, DeviceField):
+        return x.t
+    return x
+
+
+class FieldSnapshotter:
+    """Asynchronous device->host snapshots.  ``snapshot(items, sink)`` returns at once; ``sink(host_dict)`` runs in
+    the worker thread when the copies have landed.  ``depth`` snapshots may be in flight (pinned buffers are
+    recycled per (shape, dtype)); a further call blocks until one has been written."""
+
+    def __init__(self, depth=2):
+        self.depth = int(depth)
+        self._cuda = torch.cuda.is_available()
+        self._side = torch.cuda.Stream() if self._cuda else None
+        self._pool = {}
+        self._slots = threading.Semaphore(self.depth)
+        self._q = queue.Queue()
+        self._err = None
+        self._worker = threading.Thread(target=self._run, daemon=True)
+        self._worker.start()
+
+    def _buffer(self, t):
+        key = (tuple(t.shape), t.dtype)
+        free = self._pool.setdefault(key, [])
+        if free:
+            return free.pop()
+        return torch.empty(t.shape, dtype=t.dtype, pin_memory=self._cuda)
+
+    def snapshot(self, items, sink):
+        if self._err is not None:
+            err, self._err = self._err, None
+            raise err
+        self._slots.acquire()
+        host, used = {}, []
+        event = None
+        dev = {k: _as_tensor(v) for k, v in items.items()}
+        cuda_items = {k: v for k, v in dev.items() if isinstance(v, torch.Tensor) and v.is_cuda}
+        if cuda_items:
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                for k, v in cuda_items.items():
+                    buf = self._buffer(v)
+                    buf.copy_(v, non_blocking=True)
+                    v.record_stream(self._side)
+                    used.append(buf)
+                    host[k] = buf
+                event = torch.cuda.Event()
+                event.record(self._side)
+        for k, v in dev.items():
+            if k in host:
+                continue
+            if isinstance(v, torch.Tensor):
+                host[k] = v.clone()
+            elif isinstance(v, np.ndarray):
+                host[k] = v.copy()           # the caller may overwrite it before the worker runs
+            else:
+                host[k] = v
+        self._q.put((host, used, event, sink))
+
+    def _run(self):
+        while True:
+            job = self._q.get()
+            if job is None:
+                return
+            host, used, event, sink = job
+            try:
+                if event is not None:
+                    event.synchronize()
+                sink({k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in host.items()})
+            except BaseException as e:       # surfaced by the next snapshot() / wait()
+                self._err = e
+            finally:
+                for buf in used:
+                    self._pool.setdefault((tuple(buf.shape), buf.dtype), []).append(buf)
+                self._slots.release()
+                self._q.task_done()
+
+    def wait(self):
+        self._q.join()
+        if self._err is not None:
+            err, self._err = self._err, None
+            raise err
+
+    def close(self):
+        self.wait()
+        self._q.put(None)
+
+
+_default = None
+
+
+def _snapshotter():
+    global _default
+    if _default is None:
+        _default = FieldSnapshotter()
+    return _default
+
+
+def save_npz(path, asynchronous=False, **items):
+    """``np.savez(path, **items)`` where items may live on the GPU.  With ``asynchronous`` the call returns once the
+    copies are queued; ``wait()`` (or the next save) surfaces I/O errors."""
+    snap = _snapshotter()
+    snap.snapshot(items, lambda host: np.savez(path, **host))
+    if not asynchronous:
+        snap.wait()
+
+
+def wait():
+    if _default is not None:
+        _default.wait()
+
+
+def load_npz(path):
+    """dict of NumPy arrays / scalars, like ``np.load`` (0-d arrays stay 0-d, as the drivers ``float(...)`` them)"""
+    with np.load(path) as f:
+        return {k: f[k] for k in f.files}
+
+
+# --------------------------------------------------------------------------------------
+# restart files of the device-resident steppers (keys follow the reference's restart.npz where it has them)
+# --------------------------------------------------------------------------------------
+_STATE = {
+    "RigidFlowStepper": (["vorticity"], []),
+    "SoftSphereStepper": (["vorticity", "eta1", "eta2", "ball_phi", "avg_psi", "avg_phi"], ["t", "freqTimer", "it"]),
+    "ParticleFlowStepper": (["vorticity", "avg_psi", "avg_vort", "avg_part_char_func"],
+                            ["t", "it", "U_z_cm_part", "diff", "part_Z_cm", "F_total"]),
+}
+
+
+def save_restart(stepper, path="restart.npz", asynchronous=False):
+    """particle_in_bubble_oscillatory_flow.py:236-257 for a device-resident stepper"""
+    fields, scalars = _STATE[type(stepper).__name__]
+    items = {k: getattr(stepper, k) for k in fields}
+    if type(stepper).__name__ == "RigidFlowStepper":
+        sc = stepper.scalars()
+        items["t"], items["it"] = sc["t"], sc["it"]
+    for k in scalars:
+        items[k] = getattr(stepper, k)
+    save_npz(path, asynchronous=asynchronous, **items)
+
+
+def load_restart(stepper, path="restart.npz"):
+    """particle_in_bubble_oscillatory_flow.py:129-147: fields are copied in place, scalars restored"""
+    data = load_npz(path)
+    fields, scalars = _STATE[type(stepper).__name__]
+    for k in fields:
+        getattr(stepper, k).copy_(torch.from_numpy(np.ascontiguousarray(data[k])))
+    if type(stepper).__name__ == "RigidFlowStepper":
+        stepper.set_time(float(data["t"]), int(data["it"]))
+    for k in scalars:
+        cur = getattr(stepper, k)
+        setattr(stepper, k, type(cur)(data[k]))
+    if type(stepper).__name__ == "ParticleFlowStepper":
+        stepper.refresh_body()
+    return stepper

@@ -180,7 +180,7 @@ def test_reinit_errors_and_device_path(K):
     r(t, dx, 5 * dx)
     out = t.cpu().numpy()
     assert np.array_equal(out[~seen], phi[~seen]) and np.max(np.abs(out[seen] - ref.data[seen])) <= 1e-12 * 5 * dx
-    assert 5 <= r.sweeps <= 60
+    assert 2 <= r.sweeps <= 12
     with pytest.raises(ValueError):
         r(torch.zeros(8, 8, dtype=torch.float64, device="cuda"), dx, 5 * dx)
 
@@ -229,7 +229,7 @@ def test_reinit_full_size_against_marcher(K):
     r(t2, dx, band)
     ev1.record()
     torch.cuda.synchronize()
-    print(f"\nreinit 2048x8192, band 6 dx: {ev0.elapsed_time(ev1):.3f} ms, {r.sweeps} sweeps")
+    print(f"\nreinit 2048x8192, band 6 dx: {ev0.elapsed_time(ev1):.3f} ms, {r.sweeps} sweep launches")
     got = t.cpu().numpy()
     m = mask.cpu().numpy().astype(bool)
     assert np.array_equal(m, np.ma.getmaskarray(ref))

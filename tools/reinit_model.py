@@ -1,16 +1,16 @@
 """Model of the GPU narrow-band re-initialisation (csrc/reinit.cu) in plain Python/NumPy.
 
 The fast-marching method accepts cells one at a time from a heap; the GPU instead iterates the
-SAME upwind update to its fixed point, all cells at once (Jacobi, two buffers):
+SAME upwind update to its fixed point, all band cells at once:
 
   step 1  front cells (4-neighbourhood straddles the zero contour): distance from the linear
           crossings -- identical to the marcher's first step, purely local;
   step 2  repeat until nothing changes: every other cell recomputes its value from the neighbours
           that the marcher would have frozen before it -- front cells and cells whose current
           |value| <= narrow, and *causally* smaller than the result (a dimension whose upwind
-          value is not below the 2-D result is dropped and the 1-D result used);
-          (a state that repeats with period 2 -- tied neighbours flipping in the last bits -- also ends
-          the iteration: per cell the value of smaller magnitude is kept)
+          value is not below the 2-D result is dropped and the 1-D result used).  The iteration is
+          organised like the kernel: 32x32 tiles, up to 40 Jacobi iterations per tile and launch with
+          the other tiles' values frozen;
   step 3  cells not accepted (|value| > narrow) that touch an accepted cell get the marcher's
           tentative value (update from all accepted neighbours, no causality filter), everything
           else stays masked.
@@ -86,50 +86,68 @@ def update_cell(d, ok, phi, j, k, dx, order, causal):
     return _quadratic(a, b, c, pos)
 
 
-def reinit(phi, dx, narrow, order=2, free_iter=None, max_iter=None):
-    """returns (distance, unmasked, iterations).  distance is MAXD where masked.
+TH = TW = 32      # csrc/reinit.cu: tile shape, on-chip iterations per launch
+INNER = 40
 
-    The first ``free_iter`` sweeps recompute every cell from scratch (this reaches the marcher's result
-    wherever the distance field is smooth).  Where two fronts collide inside the band the second-order
-    update can flip between two upwind selections for ever, so after ``free_iter`` sweeps values may
-    only decrease in magnitude, which terminates; ``max_iter`` bounds the total."""
+
+def launch_bounds(shape, narrow, dx):
+    """(free_launch, max_launch) exactly as axb_reinit_distance computes them"""
     w = int(np.ceil(narrow / dx))
-    if free_iter is None:
-        free_iter = 8 * w + 64 + int(np.ceil(2.0 * np.sqrt(2.0 * max(np.shape(phi)) * w)))
-    max_iter = 2 * free_iter if max_iter is None else max_iter
+    chain = 2 * w + int(np.ceil(2.0 * np.sqrt(2.0 * max(shape) * w)))
+    free_launch = 8 + 2 * ((chain + TW - 1) // TW)
+    return free_launch, 2 * free_launch
+
+
+def reinit(phi, dx, narrow, order=2, free_launch=None, max_launch=None):
+    """returns (distance, unmasked, launches).  distance is MAXD where masked.
+
+    One launch = every tile iterates up to INNER times on its own cells with the values of the other tiles
+    frozen (what a thread block does in shared memory), ending early when the tile is stationary.  The
+    iteration ends when a launch changes no tile.  After ``free_launch`` launches values may only decrease in
+    magnitude: where two fronts collide inside the band, or neighbours are exactly tied, the second-order
+    update can otherwise flip between two upwind selections for ever."""
     from oracle.axisym_oracle import fmm_initial_front
 
     phi = np.asarray(phi, dtype=np.float64)
     nr, nz = phi.shape
+    fl, ml = launch_bounds(phi.shape, narrow, dx)
+    free_launch = fl if free_launch is None else free_launch
+    max_launch = ml if max_launch is None else max_launch
     d, front = fmm_initial_front(phi, dx)
-    it, converged, prev = 0, False, None
-    while it < max_iter:
-        it += 1
-        ok = front | (np.abs(d) <= narrow)
-        monotone = it > free_iter
-        # every non-front cell is recomputed from scratch; without a usable neighbour it is unreached (MAXD)
-        new = d.copy() if monotone else np.where(front, d, MAXD)
-        reach = np.zeros_like(ok)
-        reach[1:] |= ok[:-1]; reach[:-1] |= ok[1:]; reach[:, 1:] |= ok[:, :-1]; reach[:, :-1] |= ok[:, 1:]
-        for j, k in zip(*np.nonzero(reach & ~front)):
-            r = update_cell(d, ok, phi, j, k, dx, order, causal=True)
-            r = MAXD if r is None else r
-            if monotone and not abs(r) < abs(d[j, k]):
-                r = d[j, k]
-            new[j, k] = r
-        if np.array_equal(new, d):
-            converged = True
-            break
-        if prev is not None and np.array_equal(new, prev):
-            # period-2 cycle: two neighbours with (nearly) tied values each take the other as upwind cell when
-            # the rounding of the 2-D root says so; the two states differ in the last bits.  Keep, per cell,
-            # the value of smaller magnitude.
-            d = np.where(np.abs(d) <= np.abs(new), d, new)
-            converged = True
-            break
-        prev, d = d, new
+    launch, converged = 0, False
+    while launch < max_launch and not converged:
+        launch += 1
+        monotone = launch > free_launch
+        new = d.copy()
+        for tj in range(0, nr, TH):
+            for tk in range(0, nz, TW):
+                ja, jb, ka, kb = max(tj - 2, 0), min(tj + TH + 2, nr), max(tk - 2, 0), min(tk + TW + 2, nz)
+                if not np.any(front[ja:jb, ka:kb] | (np.abs(d[ja:jb, ka:kb]) <= narrow)):
+                    continue                      # nothing usable within reach: every cell stays / becomes MAXD
+                loc = d.copy()                    # the tile's view: other tiles frozen at the launch start
+                own = np.zeros_like(front)
+                own[tj:tj + TH, tk:tk + TW] = True
+                cells = list(zip(*np.nonzero(own & ~front)))
+                for _ in range(INNER):
+                    ok = front | (np.abs(loc) <= narrow)
+                    nxt = loc.copy()
+                    changed = False
+                    for j, k in cells:
+                        r = update_cell(loc, ok, phi, j, k, dx, order, causal=True)
+                        r = MAXD if r is None else r
+                        if monotone and not abs(r) < abs(loc[j, k]):
+                            r = loc[j, k]
+                        if r != loc[j, k]:
+                            changed = True
+                        nxt[j, k] = r
+                    loc = nxt
+                    if not changed:
+                        break
+                new[tj:tj + TH, tk:tk + TW] = loc[tj:tj + TH, tk:tk + TW]
+        converged = np.array_equal(new, d)
+        d = new
     if not converged:
-        raise RuntimeError("reinit model: no fixed point within the sweep bound")
+        raise RuntimeError("reinit model: no fixed point within the launch bound")
     acc = front | (np.abs(d) <= narrow)
     out = np.where(acc, d, MAXD)
     reach = np.zeros_like(acc)
@@ -140,4 +158,4 @@ def reinit(phi, dx, narrow, order=2, free_iter=None, max_iter=None):
         if r is None:
             raise RuntimeError("Negative discriminant in distance marcher quadratic.")
         out[j, k] = r
-    return out, acc | ring, it
+    return out, acc | ring, launch
