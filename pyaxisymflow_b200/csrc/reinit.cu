@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(TW* TH)
                    int monotone, int inner, Ctr* ctr) {
   __shared__ double sd[2][SH][SW];
   __shared__ unsigned char sf[SH][SW];
+  __shared__ unsigned char sc[2][SH][SW];  // "changed in the last iteration", per cell and buffer parity
   __shared__ int s_act;
   const int tid = threadIdx.y * TW + threadIdx.x;
   const int t = tile_list[blockIdx.x];
@@ -270,6 +271,8 @@ __global__ void __launch_bounds__(TW* TH)
     sd[0][lj][lk] = v;
     sd[1][lj][lk] = v;
     sf[lj][lk] = fl;
+    sc[0][lj][lk] = 0;  // halo, front and outside cells never change within a launch
+    sc[1][lj][lk] = 0;
   }
   __syncthreads();
   const int lj = threadIdx.y + HALO, lk = threadIdx.x + HALO;
@@ -283,12 +286,19 @@ __global__ void __launch_bounds__(TW* TH)
     int ch = 0;
     if (active) {
       const double cur = sd[b][lj][lk];
-      TileAcc A{sd[b], sf, j0, k0};
-      bool ok;
-      double r = update_cell<true>(A, narrow, nr, nz, j, k, dx, order, positive, ok);
-      if (monotone && !(fabs(r) < fabs(cur))) r = cur;
+      double r = cur;
+      // a cell whose eight stencil inputs did not change in the last iteration would recompute the value it has
+      const bool need = q == 0 || sc[b][lj - 1][lk] || sc[b][lj + 1][lk] || sc[b][lj][lk - 1] || sc[b][lj][lk + 1] ||
+                        sc[b][lj - 2][lk] || sc[b][lj + 2][lk] || sc[b][lj][lk - 2] || sc[b][lj][lk + 2];
+      if (need) {
+        TileAcc A{sd[b], sf, j0, k0};
+        bool ok;
+        r = update_cell<true>(A, narrow, nr, nz, j, k, dx, order, positive, ok);
+        if (monotone && !(fabs(r) < fabs(cur))) r = cur;
+        ch = __double_as_longlong(r) != __double_as_longlong(cur);
+      }
       sd[b ^ 1][lj][lk] = r;
-      ch = __double_as_longlong(r) != __double_as_longlong(cur);
+      sc[b ^ 1][lj][lk] = (unsigned char)ch;
     }
     b ^= 1;
     if (!__syncthreads_or(ch)) break;  // also orders this iteration's writes before the next one's reads
@@ -342,6 +352,14 @@ __global__ void __launch_bounds__(TW* TH)
 
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
+// pinned host mirror of the counters (a pageable destination makes every read-back a staged, slower copy);
+// allocated once per process, the drivers are single threaded (SURVEY.md 8b "Threading")
+Ctr* host_ctr() {
+  static Ctr* p = nullptr;
+  if (!p && cudaHostAlloc((void**)&p, sizeof(Ctr), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+  return p;
+}
+
 }  // namespace
 
 extern "C" {
@@ -387,7 +405,7 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   // accepted cells lie within W (+1) cells of a front cell, the tentative ring one further, its stencil two more
   const int reach = W + 4;
   // on-chip iterations per launch: a dependency chain advances one cell per iteration, a tile is 32 cells wide
-  const int inner = 40;
+  const int inner = 64;
   // launches needed on a smooth contour: 2-3 for the band, then the chains along the contour where it is axis
   // aligned, ~sqrt(2 R W) cells for a radius of curvature of R cells (<= the grid size), ~TW cells per launch
   const int longest = nr > nz ? nr : nz;
@@ -405,7 +423,9 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   k_reinit_compact<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(tile_flag, (int)ntiles, tile_list, chg_prev,
                                                                     chg_cur, ctr);
   AXB_LAUNCHED();
-  Ctr h;
+  Ctr* hp = host_ctr();
+  if (!hp) return (int)cudaErrorMemoryAllocation;
+  Ctr& h = *hp;
   if ((e = cudaMemcpyAsync(&h, ctr, sizeof(Ctr), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return (int)e;
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
@@ -427,7 +447,9 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
     AXB_LAUNCHED();
     double* tmp = din; din = dout; dout = tmp;
     int* tc_ = chg_prev; chg_prev = chg_cur; chg_cur = tc_;
-    if (it == 1) continue;  // the band cannot settle in one launch (tile halos are frozen within a launch)
+    // the band cannot settle in one launch (tile halos are frozen within a launch); afterwards look at the flag
+    // after every second launch -- a launch that finds every tile stationary costs a few microseconds
+    if (it == 1 || ((it & 1) == 0 && it < max_launch)) continue;
     if ((e = cudaMemcpyAsync(&h, ctr, sizeof(Ctr), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return (int)e;
     converged = (h.changed == 0);

@@ -9,7 +9,7 @@ SAME upwind update to its fixed point, all band cells at once:
           that the marcher would have frozen before it -- front cells and cells whose current
           |value| <= narrow, and *causally* smaller than the result (a dimension whose upwind
           value is not below the 2-D result is dropped and the 1-D result used).  The iteration is
-          organised like the kernel: 32x32 tiles, up to 40 Jacobi iterations per tile and launch with
+          organised like the kernel: 32x32 tiles, up to 64 Jacobi iterations per tile and launch with
           the other tiles' values frozen;
   step 3  cells not accepted (|value| > narrow) that touch an accepted cell get the marcher's
           tentative value (update from all accepted neighbours, no causality filter), everything
@@ -87,7 +87,7 @@ def update_cell(d, ok, phi, j, k, dx, order, causal):
 
 
 TH = TW = 32      # csrc/reinit.cu: tile shape, on-chip iterations per launch
-INNER = 40
+INNER = 64
 
 
 def launch_bounds(shape, narrow, dx):
