@@ -57,12 +57,12 @@ struct GlobalAcc {  // dense (nr, nz) buffers; cells of inactive tiles were neve
   }
   __device__ __forceinline__ bool flg(int jj, int kk) const { return f[(long long)jj * nz + kk] != 0; }
 };
-struct TileAcc {  // shared-memory tile with halo, origin (j0, k0) = global index of element [0][0]
+struct TileAcc {  // shared-memory tile with halo, origin (j0, k0) = global index of element [0][0]; flag bit 0 = front
   const double (*d)[SW];
   const unsigned char (*f)[SW];
   int j0, k0;
   __device__ __forceinline__ double val(int jj, int kk) const { return d[jj - j0][kk - k0]; }
-  __device__ __forceinline__ bool flg(int jj, int kk) const { return f[jj - j0][kk - k0] != 0; }
+  __device__ __forceinline__ bool flg(int jj, int kk) const { return (f[jj - j0][kk - k0] & 1) != 0; }
 };
 
 template <class Acc>
@@ -112,16 +112,15 @@ __device__ __forceinline__ bool quadratic(double a, double b, double c, bool pos
   c = c - 1;
   const double det = b * b - 4 * a * c;
   if (det < 0) return false;
-  r = positive ? (-b + sqrt(det)) / 2.0 / a : (-b - sqrt(det)) / 2.0 / a;
+  r = positive ? (-b + sqrt(det)) * 0.5 / a : (-b - sqrt(det)) * 0.5 / a;  // x / 2.0 == x * 0.5 exactly
   return true;
 }
 
 // new value of cell (j, k).  CAUSAL: the sweep form (returns MAXD when nothing usable); otherwise the
 // marcher's tentative value from all usable neighbours (`ok` false on a negative discriminant).
 template <bool CAUSAL, class Acc>
-__device__ __forceinline__ double update_cell(const Acc& A, double narrow, int nr, int nz, int j, int k, double dx,
+__device__ __forceinline__ double update_cell(const Acc& A, double narrow, int nr, int nz, int j, int k, double idx2,
                                               int order, bool positive, bool& ok) {
-  const double idx2 = 1 / dx / dx;
   double v1[2], v2[2];
   upwind(A, narrow, nr, nz, j, k, 0, order, v1[0], v2[0]);
   upwind(A, narrow, nr, nz, j, k, 1, order, v1[1], v2[1]);
@@ -152,54 +151,85 @@ __device__ __forceinline__ double update_cell(const Acc& A, double narrow, int n
 }
 
 // -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TW* TH)
-    k_reinit_front(int nr, int nz, long long ld, double dx, const double* __restrict__ phi, double* __restrict__ dA,
-                   unsigned char* __restrict__ flag, int* __restrict__ tile_flag, int reach, int ntr, int ntc,
-                   Ctr* ctr) {
-  const int k = blockIdx.x * TW + threadIdx.x;
-  const int j = blockIdx.y * TH + threadIdx.y;
-  if (j >= nr || k >= nz) return;
-  const double p = phi[(long long)j * ld + k];
-  double dist = MAXD;
-  bool front = false;
+// distance of a cell whose 4-neighbourhood straddles the zero contour (the marcher's initial front).
+// q[dim][side] are the neighbours (side 0: index - 1, side 1: index + 1), h[dim][side] whether they exist.
+__device__ __forceinline__ bool front_cell(double p, const double q[2][2], const bool h[2][2], double dx, double& dist) {
   if (p == 0.0) {
     dist = 0.0;
-    front = true;
-  } else {
-    double ldist[2] = {0.0, 0.0};
-    bool borders = false;
+    return true;
+  }
+  double ldist[2] = {0.0, 0.0};
+  bool borders = false;
 #pragma unroll
-    for (int dim = 0; dim < 2; ++dim) {
+  for (int dim = 0; dim < 2; ++dim) {
 #pragma unroll
-      for (int s = -1; s <= 1; s += 2) {
-        const int jj = dim == 0 ? j + s : j, kk = dim == 0 ? k : k + s;
-        if (jj < 0 || jj >= nr || kk < 0 || kk >= nz) continue;
-        const double q = phi[(long long)jj * ld + kk];
-        if (p * q < 0) {
-          borders = true;
-          const double c = dx * p / (p - q);
-          if (ldist[dim] == 0 || ldist[dim] > c) ldist[dim] = c;
+    for (int s = 0; s < 2; ++s) {
+      if (h[dim][s] && p * q[dim][s] < 0) {
+        borders = true;
+        const double c = dx * p / (p - q[dim][s]);
+        if (ldist[dim] == 0 || ldist[dim] > c) ldist[dim] = c;
+      }
+    }
+  }
+  if (!borders) return false;
+  double dsum = 0.0;
+#pragma unroll
+  for (int dim = 0; dim < 2; ++dim)
+    if (ldist[dim] > 0) dsum += 1 / ldist[dim] / ldist[dim];
+  dist = p < 0 ? -sqrt(1 / dsum) : sqrt(1 / dsum);
+  return true;
+}
+
+constexpr int FT = 128, FR = 8;  // front pass: 128 threads x 2 columns, marching over 8 rows
+
+// Whole-grid pass, 8 B/pt read + 1 B/pt written: a thread owns two adjacent columns and walks down FR rows with
+// the r-neighbourhood in registers (every row of phi is loaded once; the z neighbours of the pair come from L1).
+__global__ void __launch_bounds__(FT)
+    k_reinit_front(int nr, int nz, long long ld, double dx, const double* __restrict__ phi, double* __restrict__ dA,
+                   unsigned char* __restrict__ flag, int* __restrict__ tile_flag, int reach, int ntr, int ntc, bool vec,
+                   Ctr* ctr) {
+  const int k = 2 * (blockIdx.x * FT + threadIdx.x);
+  if (k >= nz) return;
+  const int ja = blockIdx.y * FR, jb = min(ja + FR, nr);
+  const bool has1 = k + 1 < nz, hasl = k > 0, hasr = k + 2 < nz;
+  double2 prev = make_double2(0, 0), cur = ld_pair(phi + (long long)ja * ld, k, nz, vec), next = cur;
+  if (ja > 0) prev = ld_pair(phi + (long long)(ja - 1) * ld, k, nz, vec);
+  for (int j = ja; j < jb; ++j) {
+    const double* row = phi + (long long)j * ld;
+    const bool hasu = j + 1 < nr, hasd = j > 0;
+    if (hasu) next = ld_pair(row + ld, k, nz, vec);
+    const double left = hasl ? row[k - 1] : 0.0, right = hasr ? row[k + 2] : 0.0;
+    // cheap test first: no sign change (and no exact zero) in the pair's neighbourhood -> nothing to do
+    const bool quiet0 = cur.x != 0.0 && !(hasd && cur.x * prev.x < 0) && !(hasu && cur.x * next.x < 0) &&
+                        !(hasl && cur.x * left < 0) && !(has1 && cur.x * cur.y < 0);
+    const bool quiet1 = !has1 || (cur.y != 0.0 && !(hasd && cur.y * prev.y < 0) && !(hasu && cur.y * next.y < 0) &&
+                                  !(cur.y * cur.x < 0) && !(hasr && cur.y * right < 0));
+    unsigned char f0 = 0, f1 = 0;
+    if (!(quiet0 && quiet1)) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c == 1 && !has1) continue;
+        const double p = c ? cur.y : cur.x;
+        const double q[2][2] = {{c ? prev.y : prev.x, c ? next.y : next.x}, {c ? cur.x : left, c ? right : cur.y}};
+        const bool h[2][2] = {{hasd, hasu}, {c ? true : hasl, c ? hasr : has1}};
+        double dist;
+        if (front_cell(p, q, h, dx, dist)) {
+          const int kk = k + c;
+          (c ? f1 : f0) = 1;
+          dA[(long long)j * nz + kk] = dist;  // the other cells of the active tiles are filled by k_reinit_fill
+          ctr->has_front = 1;
+          const int t0 = max(j - reach, 0) / TH, t1 = min(j + reach, nr - 1) / TH;
+          const int c0 = max(kk - reach, 0) / TW, c1 = min(kk + reach, nz - 1) / TW;
+          for (int t = t0; t <= t1 && t < ntr; ++t)
+            for (int cc = c0; cc <= c1 && cc < ntc; ++cc) tile_flag[t * ntc + cc] = 1;
         }
       }
     }
-    if (borders) {
-      double dsum = 0.0;
-#pragma unroll
-      for (int dim = 0; dim < 2; ++dim)
-        if (ldist[dim] > 0) dsum += 1 / ldist[dim] / ldist[dim];
-      dist = p < 0 ? -sqrt(1 / dsum) : sqrt(1 / dsum);
-      front = true;
-    }
-  }
-  const long long i = (long long)j * nz + k;
-  flag[i] = front ? 1 : 0;
-  if (front) {
-    dA[i] = dist;  // the other cells of the active tiles are filled by k_reinit_fill
-    ctr->has_front = 1;
-    const int t0 = max(j - reach, 0) / TH, t1 = min(j + reach, nr - 1) / TH;
-    const int c0 = max(k - reach, 0) / TW, c1 = min(k + reach, nz - 1) / TW;
-    for (int t = t0; t <= t1 && t < ntr; ++t)
-      for (int c = c0; c <= c1 && c < ntc; ++c) tile_flag[t * ntc + c] = 1;
+    unsigned char* frow = flag + (long long)j * nz;
+    frow[k] = f0;
+    if (has1) frow[k + 1] = f1;
+    prev = cur;
+    cur = next;
   }
 }
 
@@ -231,14 +261,16 @@ __global__ void __launch_bounds__(TW* TH)
 // tile t changed in the previous launch; a tile whose own and neighbouring tiles did not change has nothing to do
 // (its inputs are what they were and both global buffers already hold its values).
 __global__ void __launch_bounds__(TW* TH)
-    k_reinit_sweep(int nr, int nz, long long ld, double dx, const double* __restrict__ phi,
+    k_reinit_sweep(int nr, int nz, long long ld, double idx2, const double* __restrict__ phi,
                    const double* __restrict__ din, double* __restrict__ dout, const unsigned char* __restrict__ flag,
                    const int* __restrict__ tile_flag, const int* __restrict__ tile_list, int ntr, int ntc,
                    const int* __restrict__ chg_prev, int* __restrict__ chg_cur, double narrow, int order,
                    int monotone, int inner, Ctr* ctr) {
   __shared__ double sd[2][SH][SW];
-  __shared__ unsigned char sf[SH][SW];
+  __shared__ unsigned char sf[SH][SW];     // bit 0: front cell, bit 1: phi > eps (own cells)
   __shared__ unsigned char sc[2][SH][SW];  // "changed in the last iteration", per cell and buffer parity
+  __shared__ unsigned short s_list[TW * TH];
+  __shared__ int s_n[2];
   __shared__ int s_act;
   const int tid = threadIdx.y * TW + threadIdx.x;
   const int t = tile_list[blockIdx.x];
@@ -251,6 +283,8 @@ __global__ void __launch_bounds__(TW* TH)
         if (pj >= 0 && pj < ntr && pc >= 0 && pc < ntc) a |= chg_prev[pj * ntc + pc];
       }
     s_act = a;
+    s_n[0] = 0;
+    s_n[1] = 0;
   }
   __syncthreads();
   if (!s_act) {  // block-uniform
@@ -278,27 +312,40 @@ __global__ void __launch_bounds__(TW* TH)
   const int lj = threadIdx.y + HALO, lk = threadIdx.x + HALO;
   const int j = j0 + lj, k = k0 + lk;
   const bool inside = j < nr && k < nz;
-  const bool active = inside && !sf[lj][lk];  // front cells are fixed
-  const bool positive = inside ? (phi[(long long)j * ld + k] > DBL_EPSILON) : false;
+  const bool active = inside && !(sf[lj][lk] & 1);  // front cells are fixed
+  if (inside && phi[(long long)j * ld + k] > DBL_EPSILON) sf[lj][lk] |= 2;  // own element only
   const double start = sd[0][lj][lk];
+  __syncthreads();
+  // Jacobi iterations.  Per iteration only a thin curve of cells has new inputs; those cells are compacted into a
+  // list and evaluated by the first threads of the block, so the cost follows the cells that move, not the tile.
   int b = 0;
   for (int q = 0; q < inner; ++q) {
-    int ch = 0;
+    int* cnt = &s_n[q & 1];
     if (active) {
-      const double cur = sd[b][lj][lk];
-      double r = cur;
       // a cell whose eight stencil inputs did not change in the last iteration would recompute the value it has
       const bool need = q == 0 || sc[b][lj - 1][lk] || sc[b][lj + 1][lk] || sc[b][lj][lk - 1] || sc[b][lj][lk + 1] ||
                         sc[b][lj - 2][lk] || sc[b][lj + 2][lk] || sc[b][lj][lk - 2] || sc[b][lj][lk + 2];
       if (need) {
-        TileAcc A{sd[b], sf, j0, k0};
-        bool ok;
-        r = update_cell<true>(A, narrow, nr, nz, j, k, dx, order, positive, ok);
-        if (monotone && !(fabs(r) < fabs(cur))) r = cur;
-        ch = __double_as_longlong(r) != __double_as_longlong(cur);
+        s_list[atomicAdd(cnt, 1)] = (unsigned short)(lj * SW + lk);
+      } else {
+        sd[b ^ 1][lj][lk] = sd[b][lj][lk];
+        sc[b ^ 1][lj][lk] = 0;
       }
-      sd[b ^ 1][lj][lk] = r;
-      sc[b ^ 1][lj][lk] = (unsigned char)ch;
+    }
+    if (tid == 0) s_n[(q & 1) ^ 1] = 0;  // the other counter: last read before the barrier that ended iteration q-1
+    __syncthreads();
+    int ch = 0;
+    if (tid < *cnt) {
+      const int cell = s_list[tid];
+      const int clj = cell / SW, clk = cell % SW;
+      const double cur = sd[b][clj][clk];
+      TileAcc A{sd[b], sf, j0, k0};
+      bool ok;
+      double r = update_cell<true>(A, narrow, nr, nz, j0 + clj, k0 + clk, idx2, order, (sf[clj][clk] & 2) != 0, ok);
+      if (monotone && !(fabs(r) < fabs(cur))) r = cur;
+      ch = __double_as_longlong(r) != __double_as_longlong(cur);
+      sd[b ^ 1][clj][clk] = r;
+      sc[b ^ 1][clj][clk] = (unsigned char)ch;
     }
     b ^= 1;
     if (!__syncthreads_or(ch)) break;  // also orders this iteration's writes before the next one's reads
@@ -317,7 +364,7 @@ __global__ void __launch_bounds__(TW* TH)
 }
 
 __global__ void __launch_bounds__(TW* TH)
-    k_reinit_ring(int nr, int nz, long long ld, double dx, double* __restrict__ phi, const double* __restrict__ d,
+    k_reinit_ring(int nr, int nz, long long ld, double idx2, double* __restrict__ phi, const double* __restrict__ d,
                   const unsigned char* __restrict__ flag, const int* __restrict__ tile_flag,
                   const int* __restrict__ tile_list, int ntc, double narrow, int order,
                   unsigned char* __restrict__ mask_out, Ctr* ctr) {
@@ -341,7 +388,7 @@ __global__ void __launch_bounds__(TW* TH)
   if (k < nz - 1) touches |= usable(A, A.val(j, k + 1), narrow, j, k + 1);
   if (!touches) return;
   bool ok;
-  const double r = update_cell<false>(A, narrow, nr, nz, j, k, dx, order, phi[(long long)j * ld + k] > DBL_EPSILON, ok);
+  const double r = update_cell<false>(A, narrow, nr, nz, j, k, idx2, order, phi[(long long)j * ld + k] > DBL_EPSILON, ok);
   if (!ok) {
     ctr->negdet = 1;
     return;
@@ -418,7 +465,10 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   if ((e = cudaMemsetAsync(ctr, 0, sizeof(Ctr), s)) != cudaSuccess) return (int)e;
   if (mask_out && (e = cudaMemsetAsync(mask_out, 1, n, s)) != cudaSuccess) return (int)e;
   const dim3 blk(TW, TH);
-  k_reinit_front<<<dim3(ntc, ntr), blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, dA, flag, tile_flag, reach, ntr, ntc, ctr);
+  const double idx2 = 1 / g->dx / g->dx;  // the marcher's 1/dx^2, rounded the way it rounds it
+  const bool vec = !(g->ld & 1) && axb_al16(phi);
+  k_reinit_front<<<dim3((nz + 2 * FT - 1) / (2 * FT), (nr + FR - 1) / FR), FT, 0, s>>>(
+      nr, nz, g->ld, g->dx, phi, dA, flag, tile_flag, reach, ntr, ntc, vec, ctr);
   AXB_LAUNCHED();
   k_reinit_compact<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(tile_flag, (int)ntiles, tile_list, chg_prev,
                                                                     chg_cur, ctr);
@@ -442,7 +492,7 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   while (it < max_launch && !converged) {
     if ((e = cudaMemsetAsync(&ctr->changed, 0, sizeof(int), s)) != cudaSuccess) return (int)e;
     ++it;
-    k_reinit_sweep<<<nact, blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, din, dout, flag, tile_flag, tile_list, ntr, ntc,
+    k_reinit_sweep<<<nact, blk, 0, s>>>(nr, nz, g->ld, idx2, phi, din, dout, flag, tile_flag, tile_list, ntr, ntc,
                                         chg_prev, chg_cur, narrow, order, it > free_launch ? 1 : 0, inner, ctr);
     AXB_LAUNCHED();
     double* tmp = din; din = dout; dout = tmp;
@@ -457,7 +507,7 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   info_host[0] = it;
   if (!converged) info_host[1] |= 4;
   // `din` now holds the latest values
-  k_reinit_ring<<<nact, blk, 0, s>>>(nr, nz, g->ld, g->dx, phi, din, flag, tile_flag, tile_list, ntc, narrow, order,
+  k_reinit_ring<<<nact, blk, 0, s>>>(nr, nz, g->ld, idx2, phi, din, flag, tile_flag, tile_list, ntc, narrow, order,
                                      mask_out, ctr);
   AXB_LAUNCHED();
   if ((e = cudaMemcpyAsync(&h, ctr, sizeof(Ctr), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
