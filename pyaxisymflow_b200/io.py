@@ -4,9 +4,9 @@ device-resident fields without stalling the loop.
 The reference's drivers write ``np.savez("restart.npz", t=..., vorticity=..., ...)`` and reload it with
 ``np.load`` (``examples/ParticleOscillatoryFlowCases/particle_in_bubble_oscillatory_flow.py:129-147, 236-257``),
 and dump ``.vti`` images through ``utils/dump_vtk.py``.  Here a :class:`FieldSnapshotter` copies the fields into
-pinned host buffers on a side stream (ordered after the work already queued on the compute stream, so it sees a
-consistent step) and hands them to a worker thread that does the file I/O; the compute stream is never
-synchronised.  ``save_npz`` / ``load_npz`` keep the reference's on-disk format: a plain ``.npz`` with the same
+device staging buffers on the compute stream (an HBM-speed copy, ordered with the loop's kernels, so it sees a
+consistent step and the loop may overwrite the fields at once), moves those to pinned host buffers on a side
+stream, and hands them to a worker thread that does the file I/O; the compute stream is never synchronised.  ``save_npz`` / ``load_npz`` keep the reference's on-disk format: a plain ``.npz`` with the same
 keys, readable by ``np.load`` on either side.
 """
 from __future__ import annotations
@@ -43,29 +43,44 @@ class FieldSnapshotter:
         self._worker.start()
 
     def _buffer(self, t):
-        key = (tuple(t.shape), t.dtype)
+        key = (tuple(t.shape), t.dtype, "host")
         free = self._pool.setdefault(key, [])
         if free:
             return free.pop()
         return torch.empty(t.shape, dtype=t.dtype, pin_memory=self._cuda)
+
+    def _dev_buffer(self, t):
+        key = (tuple(t.shape), t.dtype, "dev")
+        free = self._pool.setdefault(key, [])
+        if free:
+            return free.pop()
+        return torch.empty(t.shape, dtype=t.dtype, device=t.device)
 
     def snapshot(self, items, sink):
         if self._err is not None:
             err, self._err = self._err, None
             raise err
         self._slots.acquire()
-        host, used = {}, []
+        host, used, used_dev = {}, [], []
         event = None
         dev = {k: _as_tensor(v) for k, v in items.items()}
         cuda_items = {k: v for k, v in dev.items() if isinstance(v, torch.Tensor) and v.is_cuda}
         if cuda_items:
+            # 1) device-to-device copy into a staging buffer ON THE COMPUTE STREAM (HBM speed, ordered with the
+            #    loop's kernels: later steps may overwrite the field at once), 2) the slow device-to-host copy of
+            #    the staging buffer on the side stream, overlapped with whatever the loop does next
+            stage = {}
+            for k, v in cuda_items.items():
+                st = self._dev_buffer(v)
+                st.copy_(v)
+                stage[k] = st
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
-                for k, v in cuda_items.items():
-                    buf = self._buffer(v)
-                    buf.copy_(v, non_blocking=True)
-                    v.record_stream(self._side)
+                for k, st in stage.items():
+                    buf = self._buffer(st)
+                    buf.copy_(st, non_blocking=True)
                     used.append(buf)
+                    used_dev.append(st)
                     host[k] = buf
                 event = torch.cuda.Event()
                 event.record(self._side)
@@ -78,7 +93,7 @@ class FieldSnapshotter:
                 host[k] = v.copy()           # the caller may overwrite it before the worker runs
             else:
                 host[k] = v
-        self._q.put((host, used, event, sink))
+        self._q.put((host, used + used_dev, event, sink))
 
     def _run(self):
         while True:
@@ -94,7 +109,7 @@ class FieldSnapshotter:
                 self._err = e
             finally:
                 for buf in used:
-                    self._pool.setdefault((tuple(buf.shape), buf.dtype), []).append(buf)
+                    self._pool.setdefault((tuple(buf.shape), buf.dtype, "dev" if buf.is_cuda else "host"), []).append(buf)
                 self._slots.release()
                 self._q.task_done()
 
@@ -143,9 +158,9 @@ def load_npz(path):
 # restart files of the device-resident steppers (keys follow the reference's restart.npz where it has them)
 # --------------------------------------------------------------------------------------
 _STATE = {
-    "RigidFlowStepper": (["vorticity"], []),
+    "RigidFlowStepper": (["vorticity", "state"], []),           # state = the 8 device-resident loop scalars
     "SoftSphereStepper": (["vorticity", "eta1", "eta2", "ball_phi", "avg_psi", "avg_phi"], ["t", "freqTimer", "it"]),
-    "ParticleFlowStepper": (["vorticity", "avg_psi", "avg_vort", "avg_part_char_func"],
+    "ParticleFlowStepper": (["vorticity", "part_char_func", "avg_psi", "avg_vort", "avg_part_char_func"],
                             ["t", "it", "U_z_cm_part", "diff", "part_Z_cm", "F_total"]),
 }
 
@@ -155,8 +170,7 @@ def save_restart(stepper, path="restart.npz", asynchronous=False):
     fields, scalars = _STATE[type(stepper).__name__]
     items = {k: getattr(stepper, k) for k in fields}
     if type(stepper).__name__ == "RigidFlowStepper":
-        sc = stepper.scalars()
-        items["t"], items["it"] = sc["t"], sc["it"]
+        items["t"] = stepper.state[0:1]                         # the key the reference's restart files lead with
     for k in scalars:
         items[k] = getattr(stepper, k)
     save_npz(path, asynchronous=asynchronous, **items)
@@ -168,11 +182,7 @@ def load_restart(stepper, path="restart.npz"):
     fields, scalars = _STATE[type(stepper).__name__]
     for k in fields:
         getattr(stepper, k).copy_(torch.from_numpy(np.ascontiguousarray(data[k])))
-    if type(stepper).__name__ == "RigidFlowStepper":
-        stepper.set_time(float(data["t"]), int(data["it"]))
     for k in scalars:
         cur = getattr(stepper, k)
         setattr(stepper, k, type(cur)(data[k]))
-    if type(stepper).__name__ == "ParticleFlowStepper":
-        stepper.refresh_body()
     return stepper

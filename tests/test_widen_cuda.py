@@ -256,3 +256,70 @@ def test_soft_sphere_stepper_with_reinit(K):
     assert_close(s.eta2.cpu().numpy(), eta2, 1e-10, "eta2")
     assert_close(s.vorticity.cpu().numpy(), w, 1e-9, "vorticity (soft sphere, reinit)")
     assert_close(s.avg_psi.cpu().numpy(), avg_psi, 1e-9, "avg_psi")
+
+
+# ---------------------------------------------------------------------------------------------
+# 8f-4 output either side of the loop: .vti dumps and restart files taken from device-resident fields
+# ---------------------------------------------------------------------------------------------
+def test_vti_and_npz_from_device_fields(K, tmp_path):
+    import os
+    import torch
+    from pyaxisymflow_b200 import io
+    from pyaxisymflow_b200.device import DeviceField
+    from pyaxisymflow_b200.utils.dump_vtk import read_vti, vtk_init, vtk_write
+
+    nr, nz = 96, 256
+    rng = np.random.default_rng(8)
+    a, b = rng.standard_normal((nr, nz)), rng.standard_normal((nr, nz))
+    da, db = DeviceField(torch.from_numpy(a).cuda()), torch.from_numpy(b).cuda()
+    image, tmp, writer = vtk_init(nz, nr)
+    writer.asynchronous = True
+    path = os.path.join(tmp_path, "dev.vti")
+    vtk_write(path, image, tmp, writer, ["avg_psi", "u_z"], [da, db], nz, nr)
+    da.t.mul_(0.0)                      # the loop goes on: `avg_psi[...] *= 0.0` right after the dump
+    db.add_(1.0)
+    writer.wait()
+    dims, name, fields = read_vti(path)
+    assert dims == (nz, nr) and np.array_equal(fields["avg_psi"], a) and np.array_equal(fields["u_z"], b)
+    rpath = os.path.join(tmp_path, "restart.npz")
+    io.save_npz(rpath, t=0.5, vorticity=db, part_phi=a)
+    with np.load(rpath) as f:
+        assert float(f["t"]) == 0.5 and np.array_equal(f["vorticity"], b + 1.0) and np.array_equal(f["part_phi"], a)
+
+
+@pytest.mark.parametrize("kind", ["rigid", "soft", "particle"])
+def test_restart_resumes_bit_identically(K, tmp_path, kind):
+    """run 3 steps, write restart.npz, run 3 more; a fresh stepper loaded from the file must land on the same bits
+    (particle_in_bubble_oscillatory_flow.py:129-147 / :236-257)"""
+    import os
+    from pyaxisymflow_b200 import io
+    from pyaxisymflow_b200.timestep import ParticleFlowStepper, RigidFlowStepper, SoftSphereStepper
+
+    def make():
+        if kind == "rigid":
+            s = RigidFlowStepper(64)
+            s.seed_vorticity()
+            return s
+        if kind == "soft":
+            return SoftSphereStepper(64, Z_cm=0.47, reinit_levelset=True)
+        return ParticleFlowStepper(64)
+
+    path = os.path.join(tmp_path, "restart.npz")
+    s = make()
+    s.step(3)
+    io.save_restart(s, path, asynchronous=True)
+    s.step(3)                           # keeps running while the file is written
+    io.wait()
+    r = make()
+    io.load_restart(r, path)
+    r.step(3)
+    assert np.array_equal(r.vorticity.cpu().numpy(), s.vorticity.cpu().numpy())
+    if kind == "rigid":
+        assert np.array_equal(r.state.cpu().numpy(), s.state.cpu().numpy())
+    else:
+        assert r.t == s.t and r.it == s.it
+    if kind == "soft":
+        assert np.array_equal(r.ball_phi.cpu().numpy(), s.ball_phi.cpu().numpy())
+        assert np.array_equal(r.eta1.cpu().numpy(), s.eta1.cpu().numpy())
+    if kind == "particle":
+        assert r.part_Z_cm == s.part_Z_cm and r.U_z_cm_part == s.U_z_cm_part
