@@ -434,11 +434,20 @@ class _ConfigRunner:
                                                         e=0.005 * (1 + (i // 8) % 8), solver=first.solver))
             self.cases = cases
             self.workload = f"ensemble of {cases} ParticleOscillatoryFlowCases per GPU at {nr}x{nz} (MP4 remeshing)"
+        self.ensemble = None
+        if name == "c5" and not os.environ.get("AXB_ENSEMBLE_SERIAL"):
+            from pyaxisymflow_b200.timestep import ParticleEnsemble
+
+            self.ensemble = ParticleEnsemble(self.members)
+            self.workload += "; members interleaved on their own streams"
         self.solver = self.members[0].solver
         self.vorticity = self.members[0].vorticity
         self.char_func = None
 
     def step(self, n=1):
+        if self.ensemble is not None:
+            self.ensemble.step(n)
+            return
         for _ in range(n):
             for m in self.members:
                 m.step(1)

@@ -565,6 +565,16 @@ class _FdBase:
         factor_pivots(grid_size_r, grid_size_z, f)
         self.plan = make_plan(grid_size_r, grid_size_z, f, self.work)
 
+    def fork(self):
+        """same factor set, private work fields and plan: for solves that run concurrently on different streams
+        (members of an ensemble)"""
+        import copy
+
+        o = copy.copy(self)
+        o.work = torch.empty_like(self.work)
+        o.plan = make_plan(self.grid_size_r, self.grid_size_z, self.factors, o.work)
+        return o
+
     def _solve(self, solution_field, rhs_field):
         st = Stage()
         sol = st.dev(solution_field, out=True)

@@ -461,17 +461,23 @@ class ParticleFlowStepper:
         for _ in range(n):
             self._one()
 
-    def _one(self):
-        s, g, dx = stream_ptr(), self.F.g, self.dx
+    # One step = three pieces, so that an ensemble can interleave its members (ParticleEnsemble): everything up to
+    # the first host decision (dt needs the vorticity maximum), everything that needs dt, and the rigid-body update
+    # on the host (needs the penalisation force sum).  `_acc` = [max |w|, sum R chi (u_z - U)].
+    def _enqueue_a(self):
+        s, g = stream_ptr(), self.F.g
         w = self.vorticity
         _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
         _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
         _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ptr(self.psi), self.nz, ptr(w), self.nz, s)
         _call("axb_velocity_from_psi", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.psi), ptr(self.r1d), 0.0, 0.0,
               None, None, s)
-        self._acc.zero_()
+        _call("axb_fill_scalars", ptr(self._acc), 1, 0.0, s)
         _call("axb_reduce_max_abs_sum", g, ptr(w), None, ptr(self._acc), s)
-        wmax = float(self._acc[0])
+
+    def _enqueue_b(self, wmax):
+        s, g, dx = stream_ptr(), self.F.g, self.dx
+        w = self.vorticity
         dt = min(0.9 * dx ** 2 / 4 / self.nu, self.CFL / (wmax + self.eps), 0.01 * self.freqTimer_limit)
         self.dt = dt
         _call("axb_add_bubble_flow", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_char_func),
@@ -483,18 +489,22 @@ class ParticleFlowStepper:
         _call("axb_axpy", g, ptr(self.avg_vort), ptr(w), a, None, s)
         _call("axb_smooth_heaviside_sphere", g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d),
               self.part_Z_cm, self.part_R_cm, self.r_part, self.moll_zone, s)
-        self._acc.zero_()
+        sum_ptr = ctypes.c_void_p(self._acc.data_ptr() + 8)
+        _call("axb_fill_scalars", sum_ptr, 1, 0.0, s)
         _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
               ptr(self.u_r_upen), ptr(self.part_char_func), self.brink_lam, dt, None, self.U_z_cm_part, 0.0, None,
-              ptr(self.r1d), ptr(self._acc), s)
+              ptr(self.r1d), sum_ptr, s)
         _call("axb_advect_vorticity_particles", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), ptr(self.z1d),
               ptr(self.rl_double), dt, None, 0, s)
         self.vorticity, self._w2 = self._w2, self.vorticity
         w = self.vorticity
         _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(w), ptr(self.r1d), self.nu, dt, None, s)
         _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(w), ptr(self._tmp), ptr(self.r1d), self.nu, dt, None, s)
+
+    def _finish(self, pen_sum):
         # rigid-body update on the host (compute_forces.py:4-17, particle_in_bubble_oscillatory_flow.py:323-351)
-        F_pen = self.rho_f * self.brink_lam * float(self._acc[0])
+        dt = self.dt
+        F_pen = self.rho_f * self.brink_lam * pen_sum
         F_un = (self.diff * self.part_vol) / dt
         F_total = F_pen + F_un
         self.F_total = F_total
@@ -505,3 +515,50 @@ class ParticleFlowStepper:
         self.part_Z_cm += U_old * dt + (0.5 * dt * dt * F_total / self.part_mass)
         self.t += dt
         self.it += 1
+
+    def _one(self):
+        self._enqueue_a()
+        self._enqueue_b(float(self._acc[0]))
+        self._finish(float(self._acc[1]))
+
+
+class ParticleEnsemble:
+    """Config C5 (SURVEY.md 8e "Ensemble"): independent ``ParticleFlowStepper`` members on one GPU, no communication.
+
+    The members' kernels are small (a 1024 x 2048 field is 16 MiB) and each member has two host decisions per step
+    (dt from the vorticity maximum, the rigid-body update from the penalisation force), so run one after the other
+    they leave the GPU idle most of the time.  Here every member has its own stream and its own solve work fields
+    (``solver.fork()``: same factors), the pieces of a step are enqueued member after member, and the force of
+    step n is read together with the vorticity maximum of step n+1 -- one host read per member and step, while
+    the other members' kernels run.  Each member performs exactly the operations of ``ParticleFlowStepper.step``.
+    """
+
+    def __init__(self, members):
+        self.members = list(members)
+        first = self.members[0].solver
+        for i, m in enumerate(self.members):
+            if i > 0 and m.solver is first:
+                m.solver = first.fork()
+        self.streams = [torch.cuda.Stream() for _ in self.members]
+        self._pending = [False] * len(self.members)
+
+    def step(self, n=1):
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(cur)
+        for _ in range(n):
+            for m, st in zip(self.members, self.streams):
+                with torch.cuda.stream(st):
+                    m._enqueue_a()
+            for i, (m, st) in enumerate(zip(self.members, self.streams)):
+                with torch.cuda.stream(st):
+                    vals = m._acc.cpu()                 # waits for this member's stream only
+                    if self._pending[i]:
+                        m._finish(float(vals[1]))
+                    m._enqueue_b(float(vals[0]))
+                    self._pending[i] = True
+        for i, (m, st) in enumerate(zip(self.members, self.streams)):
+            with torch.cuda.stream(st):
+                m._finish(float(m._acc[1]))
+            self._pending[i] = False
+            cur.wait_stream(st)

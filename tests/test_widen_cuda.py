@@ -313,13 +313,42 @@ def test_restart_resumes_bit_identically(K, tmp_path, kind):
     r = make()
     io.load_restart(r, path)
     r.step(3)
+    if kind == "particle":
+        # the penalisation force is an atomic sum of terms that cancel to ~1e-9 of their size (lambda = 1e12), so two
+        # runs of the SAME loop already differ in the rigid-body feedback at ~1e-7: the resumed
+        # run is held to that, not to bit equality
+        assert_close(r.vorticity.cpu().numpy(), s.vorticity.cpu().numpy(), 1e-5, "resumed vorticity (particle)")
+        assert abs(r.t - s.t) <= 1e-12 and r.it == s.it
+        assert abs(r.part_Z_cm - s.part_Z_cm) <= 1e-9 and abs(r.U_z_cm_part - s.U_z_cm_part) <= 1e-5 * max(1.0, abs(s.U_z_cm_part))
+        return
     assert np.array_equal(r.vorticity.cpu().numpy(), s.vorticity.cpu().numpy())
     if kind == "rigid":
         assert np.array_equal(r.state.cpu().numpy(), s.state.cpu().numpy())
     else:
         assert r.t == s.t and r.it == s.it
-    if kind == "soft":
         assert np.array_equal(r.ball_phi.cpu().numpy(), s.ball_phi.cpu().numpy())
         assert np.array_equal(r.eta1.cpu().numpy(), s.eta1.cpu().numpy())
-    if kind == "particle":
-        assert r.part_Z_cm == s.part_Z_cm and r.U_z_cm_part == s.U_z_cm_part
+
+
+def test_particle_ensemble_interleaved_members(K):
+    """config C5: members interleaved on their own streams (one host read per member and step) do exactly what
+    a member stepping alone does -- each is compared with the reference loop driven by its own trace."""
+    from test_cuda_parity import _oracle_particle_loop
+    from pyaxisymflow_b200.timestep import ParticleEnsemble, ParticleFlowStepper
+
+    nz, steps = 80, 6
+    params = [(8.0, 0.01), (16.0, 0.02), (12.0, 0.005)]
+    first = ParticleFlowStepper(nz, freq=params[0][0], e=params[0][1])
+    members = [first] + [ParticleFlowStepper(nz, freq=f, e=e, solver=first.solver) for f, e in params[1:]]
+    ens = ParticleEnsemble(members)
+    assert members[1].solver is not first.solver and members[1].solver.factors is first.solver.factors
+    ens.step(2)
+    ens.step(steps - 2)
+    for m, (f, e) in zip(members, params):
+        assert len(m.trace) == steps and m.it == steps
+        w, avg_vort, t, pz, U, forces = _oracle_particle_loop(nz, steps, freq=f, e=e, trace=m.trace)
+        assert abs(m.t - t) <= 1e-12 * t
+        assert_close(m.vorticity.cpu().numpy(), w, 1e-9, f"ensemble member f={f}")
+        assert_close(m.avg_vort.cpu().numpy(), avg_vort, 1e-9, f"ensemble member avg_vort f={f}")
+        for got, want in zip(m.trace, forces):
+            assert abs(got[4] - want) <= 1e-5 * max(abs(want), 1e-12)
