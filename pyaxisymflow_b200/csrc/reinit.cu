@@ -260,7 +260,12 @@ __global__ void __launch_bounds__(TW* TH)
 // One launch = up to `inner` Jacobi iterations of every active tile in shared memory.  `chg_prev[t]` says whether
 // tile t changed in the previous launch; a tile whose own and neighbouring tiles did not change has nothing to do
 // (its inputs are what they were and both global buffers already hold its values).
-__global__ void __launch_bounds__(TW* TH)
+// 512 threads per tile (two cells each in the selection phase): two tiles share an SM, so the ~250 active tiles of
+// the 2048 x 8192 case run in one wave -- the kernel is bound by the sequential depth of the iterations, not by
+// throughput.
+constexpr int SWEEP_ROWS = TH / 2, SWEEP_THREADS = TW * SWEEP_ROWS;
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 2)
     k_reinit_sweep(int nr, int nz, long long ld, double idx2, const double* __restrict__ phi,
                    const double* __restrict__ din, double* __restrict__ dout, const unsigned char* __restrict__ flag,
                    const int* __restrict__ tile_flag, const int* __restrict__ tile_list, int ntr, int ntc,
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(TW* TH)
     return;
   }
   const int j0 = tj * TH - HALO, k0 = tc * TW - HALO;
-  for (int idx = tid; idx < SH * SW; idx += TW * TH) {
+  for (int idx = tid; idx < SH * SW; idx += SWEEP_THREADS) {
     const int lj = idx / SW, lk = idx % SW;
     const int jj = j0 + lj, kk = k0 + lk;
     double v = MAXD;
@@ -309,19 +314,30 @@ __global__ void __launch_bounds__(TW* TH)
     sc[1][lj][lk] = 0;
   }
   __syncthreads();
-  const int lj = threadIdx.y + HALO, lk = threadIdx.x + HALO;
-  const int j = j0 + lj, k = k0 + lk;
-  const bool inside = j < nr && k < nz;
-  const bool active = inside && !(sf[lj][lk] & 1);  // front cells are fixed
-  if (inside && phi[(long long)j * ld + k] > DBL_EPSILON) sf[lj][lk] |= 2;  // own element only
-  const double start = sd[0][lj][lk];
+  // this thread's two cells: rows threadIdx.y and threadIdx.y + SWEEP_ROWS of the tile
+  const int lk = threadIdx.x + HALO, k = k0 + lk;
+  int ljc[2];
+  bool active[2];
+  double start[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    ljc[c] = threadIdx.y + c * SWEEP_ROWS + HALO;
+    const int j = j0 + ljc[c];
+    const bool inside = j < nr && k < nz;
+    active[c] = inside && !(sf[ljc[c]][lk] & 1);  // front cells are fixed
+    if (inside && phi[(long long)j * ld + k] > DBL_EPSILON) sf[ljc[c]][lk] |= 2;  // own elements only
+    start[c] = sd[0][ljc[c]][lk];
+  }
   __syncthreads();
   // Jacobi iterations.  Per iteration only a thin curve of cells has new inputs; those cells are compacted into a
   // list and evaluated by the first threads of the block, so the cost follows the cells that move, not the tile.
   int b = 0;
   for (int q = 0; q < inner; ++q) {
     int* cnt = &s_n[q & 1];
-    if (active) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (!active[c]) continue;
+      const int lj = ljc[c];
       // a cell whose eight stencil inputs did not change in the last iteration would recompute the value it has
       const bool need = q == 0 || sc[b][lj - 1][lk] || sc[b][lj + 1][lk] || sc[b][lj][lk - 1] || sc[b][lj][lk + 1] ||
                         sc[b][lj - 2][lk] || sc[b][lj + 2][lk] || sc[b][lj][lk - 2] || sc[b][lj][lk + 2];
@@ -335,26 +351,30 @@ __global__ void __launch_bounds__(TW* TH)
     if (tid == 0) s_n[(q & 1) ^ 1] = 0;  // the other counter: last read before the barrier that ended iteration q-1
     __syncthreads();
     int ch = 0;
-    if (tid < *cnt) {
-      const int cell = s_list[tid];
+    const int n = *cnt;
+    for (int e = tid; e < n; e += SWEEP_THREADS) {
+      const int cell = s_list[e];
       const int clj = cell / SW, clk = cell % SW;
       const double cur = sd[b][clj][clk];
       TileAcc A{sd[b], sf, j0, k0};
       bool ok;
       double r = update_cell<true>(A, narrow, nr, nz, j0 + clj, k0 + clk, idx2, order, (sf[clj][clk] & 2) != 0, ok);
       if (monotone && !(fabs(r) < fabs(cur))) r = cur;
-      ch = __double_as_longlong(r) != __double_as_longlong(cur);
+      const int c1 = __double_as_longlong(r) != __double_as_longlong(cur);
+      ch |= c1;
       sd[b ^ 1][clj][clk] = r;
-      sc[b ^ 1][clj][clk] = (unsigned char)ch;
+      sc[b ^ 1][clj][clk] = (unsigned char)c1;
     }
     b ^= 1;
     if (!__syncthreads_or(ch)) break;  // also orders this iteration's writes before the next one's reads
   }
   int c1 = 0;
-  if (active) {
-    const double fin = sd[b][lj][lk];
-    dout[(long long)j * nz + k] = fin;
-    c1 = __double_as_longlong(fin) != __double_as_longlong(start);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (!active[c]) continue;
+    const double fin = sd[b][ljc[c]][lk];
+    dout[(long long)(j0 + ljc[c]) * nz + k] = fin;
+    c1 |= __double_as_longlong(fin) != __double_as_longlong(start[c]);
   }
   const int any1 = __syncthreads_or(c1);
   if (tid == 0) {
@@ -492,7 +512,7 @@ int axb_reinit_distance(const axb_grid_t* g, double* phi, double narrow, int ord
   while (it < max_launch && !converged) {
     if ((e = cudaMemsetAsync(&ctr->changed, 0, sizeof(int), s)) != cudaSuccess) return (int)e;
     ++it;
-    k_reinit_sweep<<<nact, blk, 0, s>>>(nr, nz, g->ld, idx2, phi, din, dout, flag, tile_flag, tile_list, ntr, ntc,
+    k_reinit_sweep<<<nact, dim3(TW, SWEEP_ROWS), 0, s>>>(nr, nz, g->ld, idx2, phi, din, dout, flag, tile_flag, tile_list, ntr, ntc,
                                         chg_prev, chg_cur, narrow, order, it > free_launch ? 1 : 0, inner, ctr);
     AXB_LAUNCHED();
     double* tmp = din; din = dout; dout = tmp;
