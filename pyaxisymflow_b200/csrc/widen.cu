@@ -11,17 +11,82 @@
 
 #include "axb_common.cuh"
 
+extern int g_axb_legacy_stencils;  // capi.cu: 1 = 2-D tiled kernels only
+
 namespace {
 
 __device__ __forceinline__ const double* rowp(const double* f, long long ld, int j) { return f + (long long)j * ld; }
 __device__ __forceinline__ double* rowp(double* f, long long ld, int j) { return f + (long long)j * ld; }
 
 // -------------------------------------------------------------------------------------
+// Interior fast path (same idea as stencils_march.cu): a block owns 256 adjacent columns (two per thread, 128-bit
+// accesses) and marches over RBW rows with the r-neighbourhood in a rolling register window, so every input row
+// is loaded once; z neighbours come from warp shuffles.  Blocks that touch a domain edge, a slab halo or an
+// unaligned view are left to the 2-D tiled kernels below, which skip the interior blocks.  Both evaluate the same
+// expressions (true divisions), so a cell gets the same bits whichever kernel computes it.
+// -------------------------------------------------------------------------------------
+constexpr int MTW = 128, RBW = 16, URW = 4;
+
+__device__ __forceinline__ bool march_interior(const GridD& g, int mbx, int j0, bool vec) {
+  const int kb0 = 2 * mbx * MTW, kb1 = kb0 + 2 * MTW;
+  return vec && (j0 >= 1) && (j0 + RBW + 1 <= g.nr) && (kb0 >= g.ku0) && (kb1 <= g.ku1) && (kb0 + g.kz0 >= 1) &&
+         (kb1 - 1 + g.kz0 <= g.nzg - 2) && (kb0 >= 1) && (kb1 < g.nz);
+}
+// the march block a tile of the 2-D kernels (TBX*2 columns x TBY rows) lies in
+__device__ __forceinline__ bool tile_in_interior_march_block(const GridD& g, bool vec) {
+  const int mbx = (blockIdx.x * 2 * TBX) / (2 * MTW);
+  const int j0 = ((blockIdx.y * TBY) / RBW) * RBW;
+  return march_interior(g, mbx, j0, vec);
+}
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+__global__ void __launch_bounds__(MTW)
+    km_velocity_phi(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ phi) {
+  const int j0 = blockIdx.y * RBW;
+  if (!march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTW + threadIdx.x), lane = threadIdx.x & 31;
+  const double h = 2 * g.dx;
+  const long long ld = g.ld;
+  const double* p = phi + (long long)(j0 - 1) * ld + k;
+  double2 pm = ld2(p), pc = ld2(p + ld);
+  p += 2 * ld;  // row j + 1
+  double* oz = u_z + (long long)j0 * ld + k;
+  double* orr = u_r + (long long)j0 * ld + k;
+  for (int jb = 0; jb < RBW; jb += URW) {
+    double2 pn[URW];
+    double le[URW], re[URW];
+#pragma unroll
+    for (int u = 0; u < URW; ++u) pn[u] = ld2(p + u * ld);
+#pragma unroll
+    for (int u = 0; u < URW; ++u) {  // warp-edge z neighbours of rows j .. j+3
+      const double* rr = p + (u - 1) * ld;
+      le[u] = (lane == 0) ? rr[-1] : 0.0;
+      re[u] = (lane == 31) ? rr[2] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < URW; ++u) {
+      double left = __shfl_up_sync(0xffffffffu, pc.y, 1), right = __shfl_down_sync(0xffffffffu, pc.x, 1);
+      if (lane == 0) left = le[u];
+      if (lane == 31) right = re[u];
+      st2(oz + u * ld, make_double2((pc.y - left) / h, (right - pc.x) / h));
+      st2(orr + u * ld, make_double2((pn[u].x - pm.x) / h, (pn[u].y - pm.y) / h));
+      pm = pc;
+      pc = pn[u];
+    }
+    p += URW * ld;
+    oz += URW * ld;
+    orr += URW * ld;
+  }
+}
+
+// -------------------------------------------------------------------------------------
 // 8f-2  u_z = d(phi)/dz, u_r = d(phi)/dr, centred inside, second-order one-sided at the ends
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TBX* TBY)
     k_velocity_phi(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ phi,
-                   bool vec) {
+                   bool vec, bool skip_interior) {
+  if (skip_interior && tile_in_interior_march_block(g, vec)) return;  // done by km_velocity_phi
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
@@ -144,7 +209,12 @@ int axb_velocity_from_phi(const axb_grid_t* g, double* u_z, double* u_r, const d
   const GridD d = to_dev(g);
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
   const bool vec = vec_ok(d, {u_z, u_r, phi});
-  k_velocity_phi<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, phi, vec);
+  const bool march = vec && !g_axb_legacy_stencils && d.nr >= RBW + 2 && d.nz >= 2 * MTW + 2;
+  if (march) {
+    km_velocity_phi<<<dim3((d.nz + 2 * MTW - 1) / (2 * MTW), (d.nr + RBW - 1) / RBW), MTW, 0, s>>>(d, u_z, u_r, phi);
+    AXB_LAUNCHED();
+  }
+  k_velocity_phi<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, phi, vec, march);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

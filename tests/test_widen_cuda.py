@@ -43,7 +43,8 @@ def test_velocity_from_phi(K):
     K.compute_velocity_from_phi_unb(uz, ur, g["phi"], float(g["dx"]))
     assert np.array_equal(uz, g["uz"]) and np.array_equal(ur, g["ur"])
     rng = np.random.default_rng(3)
-    for nr, nz in SHAPES:
+    # the larger shapes reach the row-marching interior kernel (>= 258 columns, >= 18 rows, even pitch)
+    for nr, nz in SHAPES + [(70, 600), (130, 1030), (40, 777), (18, 258), (35, 2048)]:
         dx = 1.0 / nz
         phi = _rand(rng, nr, nz)
         a, b, c, d = (np.full((nr, nz), 7.0) for _ in range(4))
