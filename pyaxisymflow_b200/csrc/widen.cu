@@ -21,8 +21,8 @@ __device__ __forceinline__ double* rowp(double* f, long long ld, int j) { return
 // -------------------------------------------------------------------------------------
 // Interior fast path (same idea as stencils_march.cu): a block owns 256 adjacent columns (two per thread, 128-bit
 // accesses) and marches over RBW rows with the r-neighbourhood in a rolling register window, so every input row
-// is loaded once; z neighbours come from warp shuffles.  Blocks that touch a domain edge, a slab halo or an
-// unaligned view are left to the 2-D tiled kernels below, which skip the interior blocks.  Both evaluate the same
+// is loaded once; z neighbours come from warp shuffles.  Blocks that touch a domain edge, a slab halo or a
+// ragged end run the general per-row form on the same grid; small or unaligned grids take the 2-D tiled kernels.  Both evaluate the same
 // expressions (true divisions), so a cell gets the same bits whichever kernel computes it.
 // -------------------------------------------------------------------------------------
 constexpr int MTW = 128, RBW = 16, URW = 4;
@@ -31,12 +31,6 @@ __device__ __forceinline__ bool march_interior(const GridD& g, int mbx, int j0, 
   const int kb0 = 2 * mbx * MTW, kb1 = kb0 + 2 * MTW;
   return vec && (j0 >= 1) && (j0 + RBW + 1 <= g.nr) && (kb0 >= g.ku0) && (kb1 <= g.ku1) && (kb0 + g.kz0 >= 1) &&
          (kb1 - 1 + g.kz0 <= g.nzg - 2) && (kb0 >= 1) && (kb1 < g.nz);
-}
-// the march block a tile of the 2-D kernels (TBX*2 columns x TBY rows) lies in
-__device__ __forceinline__ bool tile_in_interior_march_block(const GridD& g, bool vec) {
-  const int mbx = (blockIdx.x * 2 * TBX) / (2 * MTW);
-  const int j0 = ((blockIdx.y * TBY) / RBW) * RBW;
-  return march_interior(g, mbx, j0, vec);
 }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
@@ -83,12 +77,9 @@ __global__ void __launch_bounds__(MTW)
 // -------------------------------------------------------------------------------------
 // 8f-2  u_z = d(phi)/dz, u_r = d(phi)/dr, centred inside, second-order one-sided at the ends
 // -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TBX* TBY)
-    k_velocity_phi(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ phi,
-                   bool vec, bool skip_interior) {
-  if (skip_interior && tile_in_interior_march_block(g, vec)) return;  // done by km_velocity_phi
-  const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
-  const int j = blockIdx.y * TBY + threadIdx.y;
+// general form for one column pair of one row: any row, global z ends by global index, slab ownership, any pitch
+__device__ __forceinline__ void phi_pair(const GridD& g, double* __restrict__ u_z, double* __restrict__ u_r,
+                                         const double* __restrict__ phi, int j, int k, bool vec) {
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
   const double h = 2 * g.dx;
   const int nz = g.nz;
@@ -129,6 +120,22 @@ __global__ void __launch_bounds__(TBX* TBY)
   }
   st_pair(rowp(u_z, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(v[0], v[1]));
   st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, ur);
+}
+
+// 2-D tiled kernel: small grids, unaligned views, axb_set_stencil_path(1)
+__global__ void __launch_bounds__(TBX* TBY)
+    k_velocity_phi(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ phi,
+                   bool vec) {
+  phi_pair(g, u_z, u_r, phi, blockIdx.y * TBY + threadIdx.y, 2 * (blockIdx.x * TBX + threadIdx.x), vec);
+}
+
+// the blocks km_velocity_phi leaves out (same grid): domain edges, slab halos, ragged ends
+__global__ void __launch_bounds__(MTW)
+    km_velocity_phi_edge(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ phi) {
+  const int j0 = blockIdx.y * RBW;
+  if (march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTW + threadIdx.x);
+  for (int j = j0; j < min(j0 + RBW, g.nr); ++j) phi_pair(g, u_z, u_r, phi, j, k, true);
 }
 
 // -------------------------------------------------------------------------------------
@@ -211,10 +218,13 @@ int axb_velocity_from_phi(const axb_grid_t* g, double* u_z, double* u_r, const d
   const bool vec = vec_ok(d, {u_z, u_r, phi});
   const bool march = vec && !g_axb_legacy_stencils && d.nr >= RBW + 2 && d.nz >= 2 * MTW + 2;
   if (march) {
-    km_velocity_phi<<<dim3((d.nz + 2 * MTW - 1) / (2 * MTW), (d.nr + RBW - 1) / RBW), MTW, 0, s>>>(d, u_z, u_r, phi);
+    const dim3 mg((d.nz + 2 * MTW - 1) / (2 * MTW), (d.nr + RBW - 1) / RBW);
+    km_velocity_phi<<<mg, MTW, 0, s>>>(d, u_z, u_r, phi);
     AXB_LAUNCHED();
+    km_velocity_phi_edge<<<mg, MTW, 0, s>>>(d, u_z, u_r, phi);
+  } else {
+    k_velocity_phi<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, phi, vec);
   }
-  k_velocity_phi<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, phi, vec, march);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
