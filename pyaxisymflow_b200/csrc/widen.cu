@@ -142,14 +142,13 @@ __global__ void __launch_bounds__(MTW)
 // 8f-4  baroclinic vorticity source.  MODE 0: update_baroclinic_vorticity (:5-35),
 //       MODE 1: ..._penal (:38-67), MODE 2: ..._diff_penal (:70-127).
 // -------------------------------------------------------------------------------------
+// exact form (the reference's operation order, true divisions) for one column pair of one row
 template <int MODE>
-__global__ void __launch_bounds__(TBX* TBY)
-    k_baroclinic(GridD g, double* __restrict__ w, const double* __restrict__ u_z, const double* __restrict__ u_r,
-                 const double* __restrict__ o_z, const double* __restrict__ o_r, const double* __restrict__ rho,
-                 const double* __restrict__ p_z, const double* __restrict__ p_r, const double* __restrict__ r1d,
-                 double nu, double dt) {
-  const int k0 = 2 * (blockIdx.x * TBX + threadIdx.x);
-  const int j = blockIdx.y * TBY + threadIdx.y;
+__device__ __forceinline__ void baro_pair(const GridD& g, double* __restrict__ w, const double* __restrict__ u_z,
+                                          const double* __restrict__ u_r, const double* __restrict__ o_z,
+                                          const double* __restrict__ o_r, const double* __restrict__ rho,
+                                          const double* __restrict__ p_z, const double* __restrict__ p_r,
+                                          const double* __restrict__ r1d, double nu, double dt, int j, int k0) {
   if (j < 1 || j >= g.nr - 1) return;
   const double h = 2 * g.dx;
   const double* zc = rowp(u_z, g.ld, j);
@@ -188,6 +187,106 @@ __global__ void __launch_bounds__(TBX* TBY)
     }
     const double src = dt * (Dz * (du[k] - dd[k]) / h - Dr * (dc[k + 1] - dc[k - 1]) / h) / dc[k];
     out[k] = out[k] + src;
+  }
+}
+
+// 2-D tiled kernel: the reference's divisions bit for bit (small grids, unaligned views, axb_set_stencil_path(1))
+template <int MODE>
+__global__ void __launch_bounds__(TBX* TBY)
+    k_baroclinic(GridD g, double* __restrict__ w, const double* __restrict__ u_z, const double* __restrict__ u_r,
+                 const double* __restrict__ o_z, const double* __restrict__ o_r, const double* __restrict__ rho,
+                 const double* __restrict__ p_z, const double* __restrict__ p_r, const double* __restrict__ r1d,
+                 double nu, double dt) {
+  baro_pair<MODE>(g, w, u_z, u_r, o_z, o_r, rho, p_z, p_r, r1d, nu, dt, blockIdx.y * TBY + threadIdx.y,
+                  2 * (blockIdx.x * TBX + threadIdx.x));
+}
+
+// edge blocks of the march grid: exact form
+template <int MODE>
+__global__ void __launch_bounds__(MTW)
+    km_baroclinic_edge(GridD g, double* __restrict__ w, const double* __restrict__ u_z, const double* __restrict__ u_r,
+                       const double* __restrict__ o_z, const double* __restrict__ o_r, const double* __restrict__ rho,
+                       const double* __restrict__ p_z, const double* __restrict__ p_r, const double* __restrict__ r1d,
+                       double nu, double dt) {
+  const int j0 = blockIdx.y * RBW;
+  if (march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTW + threadIdx.x);
+  if (k >= g.nz) return;
+  for (int j = j0; j < min(j0 + RBW, g.nr); ++j) baro_pair<MODE>(g, w, u_z, u_r, o_z, o_r, rho, p_z, p_r, r1d, nu, dt, j, k);
+}
+
+// Interior blocks, row marching.  The reference's expression has 9 (13 with the viscous terms) divisions per cell,
+// which makes the exact form FP64-issue bound at a third to a half of the HBM rate; here the divisions by 2 dx, dt,
+// dx^2 and r become multiplications by reciprocals computed once (<= a few ulp per term from the reference's
+// sequence, like the marching kernels of stencils_march.cu) and only the division by the density stays.
+struct Win3 {  // rows j-1, j, j+1 of one field for the thread's column pair
+  double2 m, c, n;
+};
+__device__ __forceinline__ void z_nb(const double2 c, const double* __restrict__ row, int lane, double& left, double& right) {
+  left = __shfl_up_sync(0xffffffffu, c.y, 1);
+  right = __shfl_down_sync(0xffffffffu, c.x, 1);
+  if (lane == 0) left = row[-1];
+  if (lane == 31) right = row[2];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MTW)
+    km_baroclinic(GridD g, double* __restrict__ w, const double* __restrict__ u_z, const double* __restrict__ u_r,
+                  const double* __restrict__ o_z, const double* __restrict__ o_r, const double* __restrict__ rho,
+                  const double* __restrict__ p_z, const double* __restrict__ p_r, const double* __restrict__ r1d,
+                  double nu, double dt) {
+  const int j0 = blockIdx.y * RBW;
+  if (!march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTW + threadIdx.x), lane = threadIdx.x & 31;
+  const long long ld = g.ld;
+  const double inv_h = 1.0 / (2 * g.dx), inv_dt = 1.0 / dt, inv_dx2 = 1.0 / (g.dx * g.dx);
+  long long o = (long long)(j0 - 1) * ld + k;
+  Win3 Z, R, D;
+  Z.m = ld2(u_z + o); R.m = ld2(u_r + o); D.m = ld2(rho + o);
+  o += ld;
+  Z.c = ld2(u_z + o); R.c = ld2(u_r + o); D.c = ld2(rho + o);
+  for (int j = j0; j < j0 + RBW; ++j, o += ld) {
+    Z.n = ld2(u_z + o + ld); R.n = ld2(u_r + o + ld); D.n = ld2(rho + o + ld);
+    const double2 oz = ld2(o_z + o), orr = ld2(o_r + o), wc = ld2(w + o);
+    double2 pz = make_double2(0, 0), pr = make_double2(0, 0);
+    if (MODE >= 1) { pz = ld2(p_z + o); pr = ld2(p_r + o); }
+    double zl, zr, rl, rr, dl, dr;
+    z_nb(Z.c, u_z + o, lane, zl, zr);
+    z_nb(R.c, u_r + o, lane, rl, rr);
+    z_nb(D.c, rho + o, lane, dl, dr);
+    double inv_r = 0.0, inv_r2 = 0.0;
+    if (MODE == 2) {
+      const double r = r1d[j];
+      inv_r = 1.0 / r;
+      inv_r2 = 1.0 / (r * r);
+    }
+    double out[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double uz = c ? Z.c.y : Z.c.x, ur = c ? R.c.y : R.c.x;
+      const double zL = c ? Z.c.x : zl, zR = c ? zr : Z.c.y, zU = c ? Z.n.y : Z.n.x, zD = c ? Z.m.y : Z.m.x;
+      const double rL = c ? R.c.x : rl, rR = c ? rr : R.c.y, rU = c ? R.n.y : R.n.x, rD = c ? R.m.y : R.m.x;
+      const double dL = c ? D.c.x : dl, dR = c ? dr : D.c.y, dU = c ? D.n.y : D.n.x, dD = c ? D.m.y : D.m.x;
+      const double dC = c ? D.c.y : D.c.x;
+      double Dz = (uz - (c ? oz.y : oz.x)) * inv_dt + uz * (zR - zL) * inv_h + ur * (zU - zD) * inv_h;
+      double Dr = (ur - (c ? orr.y : orr.x)) * inv_dt + uz * (rR - rL) * inv_h + ur * (rU - rD) * inv_h;
+      if (MODE >= 1) {
+        Dz = Dz - (c ? pz.y : pz.x);
+        Dr = Dr - (c ? pr.y : pr.x);
+      }
+      if (MODE == 2) {
+        const double lz = (zU + zD + zR + zL - 4 * uz) * inv_dx2 + (zU - zD) * inv_h * inv_r;
+        const double lr = (rU + rD + rR + rL - 4 * ur) * inv_dx2 + (rU - rD) * inv_h * inv_r - ur * inv_r2;
+        Dz = Dz - nu * lz;
+        Dr = Dr - nu * lr;
+      }
+      const double src = dt * (Dz * (dU - dD) * inv_h - Dr * (dR - dL) * inv_h) / dC;
+      out[c] = (c ? wc.y : wc.x) + src;
+    }
+    st2(w + o, make_double2(out[0], out[1]));
+    Z.m = Z.c; Z.c = Z.n;
+    R.m = R.c; R.c = R.n;
+    D.m = D.c; D.c = D.n;
   }
 }
 
@@ -244,13 +343,26 @@ int axb_baroclinic_vorticity_update(const axb_grid_t* g, double* w, const double
   if (rc) return rc;
   const GridD d = to_dev(g);
   if (d.nr < 3 || d.nzg < 3) return AXB_OK;  // no interior: the reference's slices are empty
+  const bool vec = vec_ok(d, {w, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r});
+  const bool march = vec && !g_axb_legacy_stencils && d.nr >= RBW + 2 && d.nz >= 2 * MTW + 2;
   const dim3 blk(TBX, TBY), grd = grid2d(d);
-  if (mode == 0)
-    k_baroclinic<0><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, nullptr, nullptr, nullptr, 0.0, dt);
-  else if (mode == 1)
-    k_baroclinic<1><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r, nullptr, 0.0, dt);
-  else
-    k_baroclinic<2><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, penal_z, penal_r, r1d, nu, dt);
+  const dim3 mg((d.nz + 2 * MTW - 1) / (2 * MTW), (d.nr + RBW - 1) / RBW);
+#define BARO(M, PZ, PR, R1, NU)                                                                                        \
+  if (march) {                                                                                                         \
+    km_baroclinic<M><<<mg, MTW, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, PZ, PR, R1, NU, dt);              \
+    AXB_LAUNCHED();                                                                                                    \
+    km_baroclinic_edge<M><<<mg, MTW, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, PZ, PR, R1, NU, dt);         \
+  } else {                                                                                                             \
+    k_baroclinic<M><<<grd, blk, 0, s>>>(d, w, u_z, u_r, old_u_z, old_u_r, density, PZ, PR, R1, NU, dt);              \
+  }
+  if (mode == 0) {
+    BARO(0, nullptr, nullptr, nullptr, 0.0)
+  } else if (mode == 1) {
+    BARO(1, penal_z, penal_r, nullptr, 0.0)
+  } else {
+    BARO(2, penal_z, penal_r, r1d, nu)
+  }
+#undef BARO
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

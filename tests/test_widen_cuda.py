@@ -37,7 +37,18 @@ def K():
     return ops
 
 
-def test_velocity_from_phi(K):
+@pytest.mark.parametrize("path", ["march", "tiled"])
+def test_velocity_from_phi(K, path):
+    from pyaxisymflow_b200 import _lib
+
+    _lib.call("axb_set_stencil_path", 1 if path == "tiled" else 0)
+    try:
+        _velocity_from_phi_cases(K)
+    finally:
+        _lib.call("axb_set_stencil_path", 0)
+
+
+def _velocity_from_phi_cases(K):
     g = golden("velocity_from_phi")
     uz, ur = np.zeros_like(g["phi"]), np.zeros_like(g["phi"])
     K.compute_velocity_from_phi_unb(uz, ur, g["phi"], float(g["dx"]))
@@ -74,43 +85,56 @@ def test_velocity_from_phi_device_fields(K):
     assert np.array_equal(uz.t.cpu().numpy(), c) and np.array_equal(ur.t.cpu().numpy(), d)
 
 
-def test_baroclinic(K):
-    g = golden("baroclinic")
-    dx, dt, nu = float(g["dx"]), float(g["dt"]), float(g["nu"])
-    _, _, _, Z, R = _grid(*g["w0"].shape, dx)
-    base = (g["u_z"], g["u_r"], g["o_z"], g["o_r"], g["rho"])
-    w = g["w0"].copy()
-    K.update_baroclinic_vorticity(w, *base, dt, dx)
-    assert_close(w, g["w_plain"], 1e-13, "baroclinic")
-    w = g["w0"].copy()
-    K.update_baroclinic_vorticity_penal(w, *base, g["p_z"], g["p_r"], dt, dx)
-    assert_close(w, g["w_penal"], 1e-13, "baroclinic penal")
-    w = g["w0"].copy()
-    K.update_baroclinic_vorticity_diff_penal(w, *base, g["p_z"], g["p_r"], R, nu, dt, dx)
-    assert_close(w, g["w_diff_penal"], 1e-13, "baroclinic diff penal")
-    rng = np.random.default_rng(5)
-    for nr, nz in SHAPES:
-        dx, _, _, Z, R = _grid(nr, nz)
-        uz, ur = _rand(rng, nr, nz), _rand(rng, nr, nz)
-        oz, orr = uz + 1e-3 * _rand(rng, nr, nz), ur + 1e-3 * _rand(rng, nr, nz)
-        rho = 1.0 + 0.5 * np.clip(_rand(rng, nr, nz) + 0.5, 0, 1)
-        pz, pr = _rand(rng, nr, nz, 5.0), _rand(rng, nr, nz, 5.0)
-        w0 = _rand(rng, nr, nz, 3.0)
-        for mode in range(3):
-            a, b = w0.copy(), w0.copy()
-            if mode == 0:
-                K.update_baroclinic_vorticity(a, uz, ur, oz, orr, rho, 2e-3, dx)
-                ox.update_baroclinic_vorticity(b, uz, ur, oz, orr, rho, 2e-3, dx)
-            elif mode == 1:
-                K.update_baroclinic_vorticity_penal(a, uz, ur, oz, orr, rho, pz, pr, 2e-3, dx)
-                ox.update_baroclinic_vorticity(b, uz, ur, oz, orr, rho, 2e-3, dx, penal_term_z=pz, penal_term_r=pr)
-            else:
-                K.update_baroclinic_vorticity_diff_penal(a, uz, ur, oz, orr, rho, pz, pr, R, 1e-2, 2e-3, dx)
-                ox.update_baroclinic_vorticity(b, uz, ur, oz, orr, rho, 2e-3, dx, penal_term_z=pz, penal_term_r=pr,
-                                               R=R, nu=1e-2)
-            assert np.array_equal(a, b), (nr, nz, mode)
-            # the rim is not touched
-            assert np.array_equal(a[0], w0[0]) and np.array_equal(a[:, -1], w0[:, -1])
+@pytest.mark.parametrize("path", ["march", "tiled"])
+def test_baroclinic(K, path):
+    """tiled path: the reference's divisions bit for bit; marching path (interior blocks of grids with >= 258 columns):
+    reciprocal multiplications, held to 1e-12 (the bar is 1e-10)"""
+    from pyaxisymflow_b200 import _lib
+
+    _lib.call("axb_set_stencil_path", 1 if path == "tiled" else 0)
+    try:
+        g = golden("baroclinic")
+        dx, dt, nu = float(g["dx"]), float(g["dt"]), float(g["nu"])
+        _, _, _, Z, R = _grid(*g["w0"].shape, dx)
+        base = (g["u_z"], g["u_r"], g["o_z"], g["o_r"], g["rho"])
+        w = g["w0"].copy()
+        K.update_baroclinic_vorticity(w, *base, dt, dx)
+        assert_close(w, g["w_plain"], 1e-13, "baroclinic")
+        w = g["w0"].copy()
+        K.update_baroclinic_vorticity_penal(w, *base, g["p_z"], g["p_r"], dt, dx)
+        assert_close(w, g["w_penal"], 1e-13, "baroclinic penal")
+        w = g["w0"].copy()
+        K.update_baroclinic_vorticity_diff_penal(w, *base, g["p_z"], g["p_r"], R, nu, dt, dx)
+        assert_close(w, g["w_diff_penal"], 1e-13, "baroclinic diff penal")
+        rng = np.random.default_rng(5)
+        for nr, nz in SHAPES + [(70, 600), (40, 777), (18, 258), (35, 1030)]:
+            dx, _, _, Z, R = _grid(nr, nz)
+            uz, ur = _rand(rng, nr, nz), _rand(rng, nr, nz)
+            oz, orr = uz + 1e-3 * _rand(rng, nr, nz), ur + 1e-3 * _rand(rng, nr, nz)
+            rho = 1.0 + 0.5 * np.clip(_rand(rng, nr, nz) + 0.5, 0, 1)
+            pz, pr = _rand(rng, nr, nz, 5.0), _rand(rng, nr, nz, 5.0)
+            w0 = _rand(rng, nr, nz, 3.0)
+            for mode in range(3):
+                a, b = w0.copy(), w0.copy()
+                if mode == 0:
+                    K.update_baroclinic_vorticity(a, uz, ur, oz, orr, rho, 2e-3, dx)
+                    ox.update_baroclinic_vorticity(b, uz, ur, oz, orr, rho, 2e-3, dx)
+                elif mode == 1:
+                    K.update_baroclinic_vorticity_penal(a, uz, ur, oz, orr, rho, pz, pr, 2e-3, dx)
+                    ox.update_baroclinic_vorticity(b, uz, ur, oz, orr, rho, 2e-3, dx, penal_term_z=pz, penal_term_r=pr)
+                else:
+                    K.update_baroclinic_vorticity_diff_penal(a, uz, ur, oz, orr, rho, pz, pr, R, 1e-2, 2e-3, dx)
+                    ox.update_baroclinic_vorticity(b, uz, ur, oz, orr, rho, 2e-3, dx, penal_term_z=pz, penal_term_r=pr,
+                                                   R=R, nu=1e-2)
+                if path == "tiled" or nz < 258:
+                    assert np.array_equal(a, b), (nr, nz, mode)
+                else:
+                    assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b - w0)), (nr, nz, mode)
+                    assert np.array_equal(a[:, :2], b[:, :2]) and np.array_equal(a[-1], b[-1])   # edge blocks: exact form
+                # the rim is not touched
+                assert np.array_equal(a[0], w0[0]) and np.array_equal(a[:, -1], w0[:, -1])
+    finally:
+        _lib.call("axb_set_stencil_path", 0)
 
 
 # ---------------------------------------------------------------------------------------------
