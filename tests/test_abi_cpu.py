@@ -58,6 +58,26 @@ def test_argument_validation_without_a_gpu():
     ptrs = (ctypes.c_uint64 * 2)(16, 0)
     assert lib.axb_peer_block_put(2, 0, ptrs, 0, 64, p16, 0, 64, 2, 64, None) == -1                     # null peer
     assert lib.axb_peer_block_put(17, 0, ptrs, 0, 64, p16, 0, 64, 2, 64, None) == -1                    # > AXB_MAX_PEERS
+    # SURVEY 8f entries
+    g = _lib.AxbGrid(8, 8, 8, 1.0, 0, 8, 0, 8)
+    gb = ctypes.byref(g)
+    assert lib.axb_velocity_from_phi(gb, p16, p16, None, None) == -1
+    assert lib.axb_velocity_from_phi(gb, p16, ctypes.c_void_p(20), p16, None) == -2
+    assert lib.axb_baroclinic_vorticity_update(gb, p16, p16, p16, p16, p16, p16, None, None, None, 0.0, 1.0, 3, None) == -1
+    assert lib.axb_baroclinic_vorticity_update(gb, p16, p16, p16, p16, p16, p16, None, None, None, 0.0, 1.0, 1, None) == -1
+    q32 = ctypes.c_void_p(32)                                                                          # w aliases u_z
+    assert lib.axb_baroclinic_vorticity_update(gb, q32, q32, p16, p16, p16, p16, None, None, None, 0.0, 1.0, 0, None) == -1
+    info = (ctypes.c_int * 2)()
+    need = lib.axb_reinit_workspace_bytes(8, 8)
+    assert need >= 2 * 8 * 64 + 64 and lib.axb_reinit_workspace_bytes(0, 8) == 0
+    w256 = ctypes.c_void_p(256)
+    assert lib.axb_reinit_distance(gb, p16, 0.5, 2, None, None, need, info, None) == -1                 # no workspace
+    assert lib.axb_reinit_distance(gb, p16, 0.5, 3, None, w256, need, info, None) == -1                 # order
+    assert lib.axb_reinit_distance(gb, p16, 0.0, 2, None, w256, need, info, None) == -1                 # narrow <= 0
+    assert lib.axb_reinit_distance(gb, p16, 0.5, 2, None, ctypes.c_void_p(264), need, info, None) == -2 # work alignment
+    assert lib.axb_reinit_distance(gb, p16, 0.5, 2, None, w256, need - 1, info, None) == -4             # work too small
+    slab = _lib.AxbGrid(8, 8, 8, 1.0, 4, 16, 2, 6)
+    assert lib.axb_reinit_distance(ctypes.byref(slab), p16, 0.5, 2, None, w256, need, info, None) == -3 # z-slab
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -94,6 +114,10 @@ def test_mirrored_module_tree_matches_the_reference_layout():
         "kernels.compute_forces": ["compute_force_on_body"],
         "kernels.force_projection": ["force_projection"],
         "kernels.vortex_stretching": ["vortex_stretching"],
+        "kernels.compute_velocity_from_phi": ["compute_velocity_from_phi_unb"],
+        "kernels.update_baroclinic_vorticity": ["update_baroclinic_vorticity", "update_baroclinic_vorticity_penal",
+                                                "update_baroclinic_vorticity_diff_penal"],
+        "utils.dump_vtk": ["vtk_init", "vtk_write"],
         "pyst_kernels.advection_flux": ["gen_advection_flux_conservative_eno3_pyst_kernel"],
         "pyst_kernels.advection_timestep": ["gen_advection_timestep_euler_forward_conservative_eno3_pyst_kernel"],
         "pyst_kernels.elementwise_ops": ["gen_elementwise_sum_pyst_kernel", "gen_set_fixed_val_pyst_kernel"],
