@@ -1,0 +1,19 @@
+"""tiny driver for ncu: a few steps of config C3 (soft sphere, 2048 x 8192) or C5 (one particle case, 1024 x 2048)"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pyaxisymflow_b200.timestep import ParticleFlowStepper, SoftSphereStepper  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c3"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+if which == "c3":
+    s = SoftSphereStepper(8192, grid_size_r=2048, Z_cm=0.47, reinit_levelset=True)
+else:
+    s = ParticleFlowStepper(2048, grid_size_r=1024)
+torch.cuda.synchronize()
+s.step(steps)
+torch.cuda.synchronize()
+print(which, "steps", steps, "t", s.t)
