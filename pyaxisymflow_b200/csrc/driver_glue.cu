@@ -51,12 +51,11 @@ __global__ void __launch_bounds__(TBX* TBY)
   st_pair(rowp(phi, g.ld, j), k, g.ku0, g.ku1, vec, p);
 }
 
+// same as stencils.cu: outside the band the reference's blend term is multiplied by an exact zero, so the division and
+// the sine are only evaluated for band cells (same bits)
 __device__ __forceinline__ double heav1(double phi, double w) {
-  double H = 0.0;
-  H = H + ((phi >= w) ? 1.0 : 0.0);
-  const double band = (fabs(phi) < w) ? 1.0 : 0.0;
-  H = H + band * 0.5 * (1 + phi / w + sin(CUDART_PI * phi / w) / CUDART_PI);
-  return H;
+  if (fabs(phi) < w) return 0.0 + 0.5 * (1 + phi / w + sin(CUDART_PI * phi / w) / CUDART_PI);
+  return (phi >= w) ? 1.0 : 0.0;
 }
 // H = smooth_Heaviside(phi) and mask = (H > thresh) as a dense (nr, nz) uint8   (soft_sphere_streaming.py:205-206)
 __global__ void k_heav_mask(GridD g, double* __restrict__ H, unsigned char* __restrict__ mask,

@@ -26,8 +26,21 @@ __device__ __forceinline__ void grad_eta(const GridD& g, const double* __restric
   const int nz = g.nz;
   const double h = 2 * g.dx;
   const double* e = rowp(eta, g.ld, j);
-  gz = ld_pair(rowp(ez, g.ld, j), k, nz, vec);  // stale values where not recomputed
-  gr = ld_pair(rowp(er, g.ld, j), k, nz, vec);
+  // Cells the reference does not recompute (first / last global column for d/dz; last row, and those columns of the
+  // rows >= 1, for d/dr) keep their stale contents, which the stress then reads.  Only pairs that contain such a
+  // cell load the old gradients; everywhere else they are overwritten (saves 32 B/pt of reads).
+  bool stale = (j == g.nr - 1);
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int kk = k + cc, kg = kk + g.kz0;
+    if (kk >= g.ku0 && kk < g.ku1 && (kg < 1 || kg > g.nzg - 2)) stale = true;
+  }
+  gz = make_double2(0.0, 0.0);
+  gr = make_double2(0.0, 0.0);
+  if (stale) {
+    gz = ld_pair(rowp(ez, g.ld, j), k, nz, vec);
+    gr = ld_pair(rowp(er, g.ld, j), k, nz, vec);
+  }
   const double2 c = ld_pair(e, k, nz, vec);
   double2 up = c, dn = c;
   if (j >= 1 && j < g.nr - 1) {

@@ -331,12 +331,12 @@ __global__ void __launch_bounds__(TBX* TBY)
 // -------------------------------------------------------------------------------------
 // G-HEAV  kernels/smooth_Heaviside.py:10-14
 // -------------------------------------------------------------------------------------
+// The reference evaluates the blend expression everywhere and multiplies it by the 0/1 band indicator; outside the
+// band that product is an exact zero, so only band cells need the division and the sine (whose argument is in the
+// thousands far from the interface: the slow range-reduction path).  Same bits, ~5x less FP64 work per field.
 __device__ __forceinline__ double heav1(double phi, double w) {
-  double H = 0.0;
-  H = H + ((phi >= w) ? 1.0 : 0.0);
-  const double band = (fabs(phi) < w) ? 1.0 : 0.0;
-  H = H + band * 0.5 * (1 + phi / w + sin(CUDART_PI * phi / w) / CUDART_PI);
-  return H;
+  if (fabs(phi) < w) return 0.0 + 0.5 * (1 + phi / w + sin(CUDART_PI * phi / w) / CUDART_PI);
+  return (phi >= w) ? 1.0 : 0.0;
 }
 
 template <bool SPHERE>
@@ -351,8 +351,21 @@ __global__ void __launch_bounds__(TBX* TBY)
   if (SPHERE) {
     const double dr = r1d[j] - r_cm;
     const double za = z1d[k] - z_cm, zb = z1d[(k + 1 < g.nz) ? k + 1 : k] - z_cm;
-    p.x = -sqrt(za * za + dr * dr) + radius;
-    p.y = -sqrt(zb * zb + dr * dr) + radius;
+    const double da = za * za + dr * dr, db = zb * zb + dr * dr;
+    if (!phi_out) {
+      // phi itself is not wanted: cells safely inside / outside the blend shell (1e-9 relative margin on the squared
+      // distance, far above the rounding of sqrt and of the subtraction) are 1 / 0 without the square root
+      const double lo = radius - w, hi = radius + w;
+      const double lo2 = (lo > 1e-3 * radius) ? lo * lo * (1 - 1e-9) : -1.0, hi2 = hi * hi * (1 + 1e-9);
+      const bool in = da < lo2 && db < lo2, out = da > hi2 && db > hi2;
+      if (in || out) {
+        const double v = in ? 1.0 : 0.0;
+        st_pair(rowp(H, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(v, v));
+        return;
+      }
+    }
+    p.x = -sqrt(da) + radius;
+    p.y = -sqrt(db) + radius;
     if (phi_out) st_pair(rowp(phi_out, g.ld, j), k, g.ku0, g.ku1, vec, p);
   } else {
     p = ld_pair(rowp(phi, g.ld, j), k, g.nz, vec);

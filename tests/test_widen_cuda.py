@@ -377,3 +377,32 @@ def test_particle_ensemble_interleaved_members(K):
         assert_close(m.avg_vort.cpu().numpy(), avg_vort, 1e-9, f"ensemble member avg_vort f={f}")
         for got, want in zip(m.trace, forces):
             assert abs(got[4] - want) <= 1e-5 * max(abs(want), 1e-12)
+
+
+def test_heaviside_shortcuts_are_bit_identical(K):
+    """smooth_Heaviside only evaluates the blend expression inside the band, and the analytic-sphere form skips the
+    square root for cells safely inside / outside the blend shell when phi is not requested: same bits as the
+    reference expression evaluated everywhere (kernels/smooth_Heaviside.py:10-14)."""
+    rng = np.random.default_rng(12)
+    for nr, nz, zc, rc, rad, wf in [(96, 300, 0.47, 0.0, 0.15, 2.0), (64, 128, 0.3, 0.05, 0.02, 2 ** 0.5),
+                                    (50, 200, 0.6, 0.1, 0.01, 3.0), (33, 77, 0.5, 0.0, 0.4, 1.0)]:
+        dx, z, r, Z, R = _grid(nr, nz)
+        w = wf * dx
+        phi = -np.sqrt((Z - zc) ** 2 + (R - rc) ** 2) + rad
+        Href = np.zeros_like(phi)
+        ox.smooth_Heaviside(Href, phi, w)
+        H1, H2, ps = np.zeros_like(phi), np.zeros_like(phi), np.zeros_like(phi)
+        K.smooth_Heaviside_sphere(H1, Z, R, zc, rc, rad, w, phi_out=ps)      # exact path
+        K.smooth_Heaviside_sphere(H2, Z, R, zc, rc, rad, w)                  # with the shortcuts
+        assert np.array_equal(H1, H2), (nr, nz)
+        assert np.max(np.abs(H1 - Href)) <= 1e-12
+        H3 = np.full_like(phi, 7.0)
+        K.smooth_Heaviside(H3, phi, w)
+        assert np.max(np.abs(H3 - Href)) <= 1e-15 and np.array_equal(H3[np.abs(phi) >= w], Href[np.abs(phi) >= w])
+    # a rough level set with values exactly on the band edges
+    phi = rng.standard_normal((40, 90)) * 0.05
+    phi[3, 4], phi[5, 6] = 0.02, -0.02
+    Href, H = np.zeros_like(phi), np.zeros_like(phi)
+    ox.smooth_Heaviside(Href, phi, 0.02)
+    K.smooth_Heaviside(H, phi, 0.02)
+    assert np.max(np.abs(H - Href)) <= 1e-15 and H[3, 4] == 1.0 and H[5, 6] == 0.0
