@@ -3,6 +3,8 @@
 //   G-SOL-2  elasto_kernels/div_tau.py:8-28           tau = div(sigma) with the 1/r terms
 //   G-SOL-3  elasto_kernels/div_tau.py:30-34          w[int] += dt * curl(tau)
 // Same thread layout as stencils.cu (two z columns per thread, 64 x 8 tiles), -fmad=false.
+#include <stdlib.h>
+
 #include <initializer_list>
 
 #include "axb_common.cuh"
@@ -22,14 +24,15 @@ inline bool vec_ok(const GridD& g, std::initializer_list<const void*> ptrs) {
 // One reference map: writes eta_z (cols 1..nz-2, all rows) and eta_r (interior + row 0);
 // cells the reference leaves untouched keep their old contents, which the stress then reads.
 __device__ __forceinline__ void grad_eta(const GridD& g, const double* __restrict__ eta, double* __restrict__ ez,
-                                         double* __restrict__ er, int j, int k, bool vec, double2& gz, double2& gr) {
+                                         double* __restrict__ er, int j, int k, bool vec, bool eager, double2& gz,
+                                         double2& gr) {
   const int nz = g.nz;
   const double h = 2 * g.dx;
   const double* e = rowp(eta, g.ld, j);
   // Cells the reference does not recompute (first / last global column for d/dz; last row, and those columns of the
   // rows >= 1, for d/dr) keep their stale contents, which the stress then reads.  Only pairs that contain such a
   // cell load the old gradients; everywhere else they are overwritten (saves 32 B/pt of reads).
-  bool stale = (j == g.nr - 1);
+  bool stale = eager || (j == g.nr - 1);
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     const int kk = k + cc, kg = kk + g.kz0;
@@ -77,13 +80,13 @@ __global__ void __launch_bounds__(TBX* TBY)
     k_solid_sigma(GridD g, double* __restrict__ s11, double* __restrict__ s12, double* __restrict__ s22, double G,
                   const double* __restrict__ eta1, const double* __restrict__ eta2, double* __restrict__ e1z,
                   double* __restrict__ e1r, double* __restrict__ e2z, double* __restrict__ e2r,
-                  const double* __restrict__ chi, bool vec) {
+                  const double* __restrict__ chi, bool vec, bool eager) {
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
   double2 z1, r1, z2, r2;
-  grad_eta(g, eta1, e1z, e1r, j, k, vec, z1, r1);
-  grad_eta(g, eta2, e2z, e2r, j, k, vec, z2, r2);
+  grad_eta(g, eta1, e1z, e1r, j, k, vec, eager, z1, r1);
+  grad_eta(g, eta2, e2z, e2r, j, k, vec, eager, z2, r2);
   double2 a12, a11, a22;
   a12.x = -G * (z1.x * r1.x + z2.x * r2.x);
   a12.y = -G * (z1.y * r1.y + z2.y * r2.y);
@@ -181,8 +184,9 @@ int axb_solid_sigma(const axb_grid_t* g, double* s11, double* s12, double* s22, 
   const GridD d = to_dev(g);
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
   const bool vec = vec_ok(d, {s11, s12, s22, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi});
+  static const bool eager = getenv("AXB_SIGMA_EAGER") != nullptr;  // load the old gradients everywhere (A/B switch)
   k_solid_sigma<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, s11, s12, s22, G, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi,
-                                                     vec);
+                                                     vec, eager);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
