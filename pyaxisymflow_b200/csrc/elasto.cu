@@ -9,6 +9,8 @@
 
 #include "axb_common.cuh"
 
+extern int g_axb_legacy_stencils;  // capi.cu: 1 = 2-D tiled kernels only
+
 namespace {
 
 __device__ __forceinline__ const double* rowp(const double* f, long long ld, int j) { return f + (long long)j * ld; }
@@ -76,13 +78,11 @@ __device__ __forceinline__ void grad_eta(const GridD& g, const double* __restric
   st_pair(rowp(er, g.ld, j), k, g.ku0, g.ku1, vec, gr);
 }
 
-__global__ void __launch_bounds__(TBX* TBY)
-    k_solid_sigma(GridD g, double* __restrict__ s11, double* __restrict__ s12, double* __restrict__ s22, double G,
-                  const double* __restrict__ eta1, const double* __restrict__ eta2, double* __restrict__ e1z,
-                  double* __restrict__ e1r, double* __restrict__ e2z, double* __restrict__ e2r,
-                  const double* __restrict__ chi, bool vec, bool eager) {
-  const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
-  const int j = blockIdx.y * TBY + threadIdx.y;
+__device__ __forceinline__ void sigma_pair(const GridD& g, double* __restrict__ s11, double* __restrict__ s12,
+                                           double* __restrict__ s22, double G, const double* __restrict__ eta1,
+                                           const double* __restrict__ eta2, double* __restrict__ e1z,
+                                           double* __restrict__ e1r, double* __restrict__ e2z, double* __restrict__ e2r,
+                                           const double* __restrict__ chi, bool vec, bool eager, int j, int k) {
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
   double2 z1, r1, z2, r2;
   grad_eta(g, eta1, e1z, e1r, j, k, vec, eager, z1, r1);
@@ -104,13 +104,20 @@ __global__ void __launch_bounds__(TBX* TBY)
   st_pair(rowp(s22, g.ld, j), k, g.ku0, g.ku1, vec, a22);
 }
 
-// tau_z = d_z t11 + d_r t12 + t12/r ; tau_r = d_z t12 + d_r t22 + t22/r   (rows 0..nr-2, cols 1..nz-2)
 __global__ void __launch_bounds__(TBX* TBY)
-    k_solid_tau(GridD g, double* __restrict__ tau_z, double* __restrict__ tau_r, const double* __restrict__ t11,
-                const double* __restrict__ t12, const double* __restrict__ t22, const double* __restrict__ r1d,
-                bool vec) {
-  const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
-  const int j = blockIdx.y * TBY + threadIdx.y;
+    k_solid_sigma(GridD g, double* __restrict__ s11, double* __restrict__ s12, double* __restrict__ s22, double G,
+                  const double* __restrict__ eta1, const double* __restrict__ eta2, double* __restrict__ e1z,
+                  double* __restrict__ e1r, double* __restrict__ e2z, double* __restrict__ e2r,
+                  const double* __restrict__ chi, bool vec, bool eager) {
+  sigma_pair(g, s11, s12, s22, G, eta1, eta2, e1z, e1r, e2z, e2r, chi, vec, eager, blockIdx.y * TBY + threadIdx.y,
+             2 * (blockIdx.x * TBX + threadIdx.x));
+}
+
+// tau_z = d_z t11 + d_r t12 + t12/r ; tau_r = d_z t12 + d_r t22 + t22/r   (rows 0..nr-2, cols 1..nz-2)
+__device__ __forceinline__ void tau_pair(const GridD& g, double* __restrict__ tau_z, double* __restrict__ tau_r,
+                                         const double* __restrict__ t11, const double* __restrict__ t12,
+                                         const double* __restrict__ t22, const double* __restrict__ r1d, bool vec, int j,
+                                         int k) {
   if (j >= g.nr - 1 || k >= g.ku1 || k + 1 < g.ku0) return;
   const int nz = g.nz;
   const double h = 2 * g.dx;
@@ -146,6 +153,137 @@ __global__ void __launch_bounds__(TBX* TBY)
     oz[kk] = tz;
     orr[kk] = tr;
   }
+}
+
+__global__ void __launch_bounds__(TBX* TBY)
+    k_solid_tau(GridD g, double* __restrict__ tau_z, double* __restrict__ tau_r, const double* __restrict__ t11,
+                const double* __restrict__ t12, const double* __restrict__ t22, const double* __restrict__ r1d,
+                bool vec) {
+  tau_pair(g, tau_z, tau_r, t11, t12, t22, r1d, vec, blockIdx.y * TBY + threadIdx.y,
+           2 * (blockIdx.x * TBX + threadIdx.x));
+}
+
+// -------------------------------------------------------------------------------------
+// Row-marching forms of G-SOL-1 / G-SOL-2 (same idea as stencils_march.cu): a block owns 256 adjacent columns (two
+// per thread, 128-bit accesses) and marches over RBM rows with the r-neighbourhood in a rolling register window;
+// z neighbours come from warp shuffles.  Interior blocks only -- every cell there is recomputed by the reference,
+// so no old gradient is read; edge blocks run the general per-pair code above on the same grid.  Same expressions
+// and true divisions as the tiled kernels: a cell gets the same bits whichever kernel computes it.
+// -------------------------------------------------------------------------------------
+constexpr int MTM = 128, RBM = 16;
+
+__device__ __forceinline__ bool march_interior(const GridD& g, int mbx, int j0, bool vec) {
+  const int kb0 = 2 * mbx * MTM, kb1 = kb0 + 2 * MTM;
+  return vec && (j0 >= 1) && (j0 + RBM + 1 <= g.nr) && (kb0 >= g.ku0) && (kb1 <= g.ku1) && (kb0 + g.kz0 >= 1) &&
+         (kb1 - 1 + g.kz0 <= g.nzg - 2) && (kb0 >= 1) && (kb1 < g.nz);
+}
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+// left = f[k-1], right = f[k+2] of the thread's pair c = (f[k], f[k+1]); `row` points at f[k]
+__device__ __forceinline__ void z_nb(const double2 c, const double* __restrict__ row, int lane, double& left, double& right) {
+  left = __shfl_up_sync(0xffffffffu, c.y, 1);
+  right = __shfl_down_sync(0xffffffffu, c.x, 1);
+  if (lane == 0) left = row[-1];
+  if (lane == 31) right = row[2];
+}
+
+template <bool CHI>
+__global__ void __launch_bounds__(MTM)
+    km_solid_sigma(GridD g, double* __restrict__ s11, double* __restrict__ s12, double* __restrict__ s22, double G,
+                   const double* __restrict__ eta1, const double* __restrict__ eta2, double* __restrict__ e1z,
+                   double* __restrict__ e1r, double* __restrict__ e2z, double* __restrict__ e2r,
+                   const double* __restrict__ chi) {
+  const int j0 = blockIdx.y * RBM;
+  if (!march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTM + threadIdx.x), lane = threadIdx.x & 31;
+  const long long ld = g.ld;
+  const double h = 2 * g.dx;
+  long long o = (long long)(j0 - 1) * ld + k;
+  double2 m1 = ld2(eta1 + o), m2 = ld2(eta2 + o);
+  o += ld;
+  double2 c1 = ld2(eta1 + o), c2 = ld2(eta2 + o);
+  for (int j = j0; j < j0 + RBM; ++j, o += ld) {
+    const double2 n1 = ld2(eta1 + o + ld), n2 = ld2(eta2 + o + ld);
+    double2 cx = make_double2(1.0, 1.0);
+    if (CHI) cx = ld2(chi + o);
+    double l1, r1n, l2, r2n;
+    z_nb(c1, eta1 + o, lane, l1, r1n);
+    z_nb(c2, eta2 + o, lane, l2, r2n);
+    double2 z1, r1, z2, r2;
+    z1.x = (c1.y - l1) / h;   z1.y = (r1n - c1.x) / h;
+    z2.x = (c2.y - l2) / h;   z2.y = (r2n - c2.x) / h;
+    r1.x = (n1.x - m1.x) / h; r1.y = (n1.y - m1.y) / h;
+    r2.x = (n2.x - m2.x) / h; r2.y = (n2.y - m2.y) / h;
+    double2 a12, a11, a22;
+    a12.x = -G * (z1.x * r1.x + z2.x * r2.x);
+    a12.y = -G * (z1.y * r1.y + z2.y * r2.y);
+    a11.x = (0.5 * G) * (r1.x * r1.x + r2.x * r2.x - z1.x * z1.x - z2.x * z2.x);
+    a11.y = (0.5 * G) * (r1.y * r1.y + r2.y * r2.y - z1.y * z1.y - z2.y * z2.y);
+    a22.x = -a11.x; a22.y = -a11.y;
+    if (CHI) {
+      a11.x = cx.x * a11.x; a11.y = cx.y * a11.y;
+      a12.x = cx.x * a12.x; a12.y = cx.y * a12.y;
+      a22.x = cx.x * a22.x; a22.y = cx.y * a22.y;
+    }
+    st2(e1z + o, z1); st2(e1r + o, r1); st2(e2z + o, z2); st2(e2r + o, r2);
+    st2(s11 + o, a11); st2(s12 + o, a12); st2(s22 + o, a22);
+    m1 = c1; c1 = n1;
+    m2 = c2; c2 = n2;
+  }
+}
+
+__global__ void __launch_bounds__(MTM)
+    km_solid_sigma_edge(GridD g, double* __restrict__ s11, double* __restrict__ s12, double* __restrict__ s22, double G,
+                        const double* __restrict__ eta1, const double* __restrict__ eta2, double* __restrict__ e1z,
+                        double* __restrict__ e1r, double* __restrict__ e2z, double* __restrict__ e2r,
+                        const double* __restrict__ chi, bool eager) {
+  const int j0 = blockIdx.y * RBM;
+  if (march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTM + threadIdx.x);
+  if (k >= g.nz) return;
+  for (int j = j0; j < min(j0 + RBM, g.nr); ++j)
+    sigma_pair(g, s11, s12, s22, G, eta1, eta2, e1z, e1r, e2z, e2r, chi, true, eager, j, k);
+}
+
+__global__ void __launch_bounds__(MTM)
+    km_solid_tau(GridD g, double* __restrict__ tau_z, double* __restrict__ tau_r, const double* __restrict__ t11,
+                 const double* __restrict__ t12, const double* __restrict__ t22, const double* __restrict__ r1d) {
+  const int j0 = blockIdx.y * RBM;
+  if (!march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTM + threadIdx.x), lane = threadIdx.x & 31;
+  const long long ld = g.ld;
+  const double h = 2 * g.dx;
+  long long o = (long long)(j0 - 1) * ld + k;
+  double2 bm = ld2(t12 + o), cm = ld2(t22 + o);
+  o += ld;
+  double2 bc = ld2(t12 + o), cc = ld2(t22 + o);
+  for (int j = j0; j < j0 + RBM; ++j, o += ld) {
+    const double2 bn = ld2(t12 + o + ld), cn = ld2(t22 + o + ld);
+    const double2 ac = ld2(t11 + o);
+    const double r = r1d[j];
+    double al, ar, bl, br;
+    z_nb(ac, t11 + o, lane, al, ar);
+    z_nb(bc, t12 + o, lane, bl, br);
+    double2 tz, tr;
+    tz.x = (ac.y - al + bn.x - bm.x) / h + bc.x / r;
+    tz.y = (ar - ac.x + bn.y - bm.y) / h + bc.y / r;
+    tr.x = (bc.y - bl + cn.x - cm.x) / h + cc.x / r;
+    tr.y = (br - bc.x + cn.y - cm.y) / h + cc.y / r;
+    st2(tau_z + o, tz);
+    st2(tau_r + o, tr);
+    bm = bc; bc = bn;
+    cm = cc; cc = cn;
+  }
+}
+
+__global__ void __launch_bounds__(MTM)
+    km_solid_tau_edge(GridD g, double* __restrict__ tau_z, double* __restrict__ tau_r, const double* __restrict__ t11,
+                      const double* __restrict__ t12, const double* __restrict__ t22, const double* __restrict__ r1d) {
+  const int j0 = blockIdx.y * RBM;
+  if (march_interior(g, blockIdx.x, j0, true)) return;
+  const int k = 2 * (blockIdx.x * MTM + threadIdx.x);
+  if (k >= g.nz) return;
+  for (int j = j0; j < min(j0 + RBM, g.nr); ++j) tau_pair(g, tau_z, tau_r, t11, t12, t22, r1d, true, j, k);
 }
 
 __global__ void __launch_bounds__(TBX* TBY)
@@ -185,8 +323,20 @@ int axb_solid_sigma(const axb_grid_t* g, double* s11, double* s12, double* s22, 
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
   const bool vec = vec_ok(d, {s11, s12, s22, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi});
   static const bool eager = getenv("AXB_SIGMA_EAGER") != nullptr;  // load the old gradients everywhere (A/B switch)
-  k_solid_sigma<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, s11, s12, s22, G, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi,
-                                                     vec, eager);
+  static const bool no_march = getenv("AXB_SOLID_TILED") != nullptr;
+  const bool march = vec && !no_march && !g_axb_legacy_stencils && d.nr >= RBM + 2 && d.nz >= 2 * MTM + 2;
+  if (march) {
+    const dim3 mg((d.nz + 2 * MTM - 1) / (2 * MTM), (d.nr + RBM - 1) / RBM);
+    if (chi)
+      km_solid_sigma<true><<<mg, MTM, 0, s>>>(d, s11, s12, s22, G, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi);
+    else
+      km_solid_sigma<false><<<mg, MTM, 0, s>>>(d, s11, s12, s22, G, eta1, eta2, eta1z, eta1r, eta2z, eta2r, nullptr);
+    AXB_LAUNCHED();
+    km_solid_sigma_edge<<<mg, MTM, 0, s>>>(d, s11, s12, s22, G, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi, eager);
+  } else {
+    k_solid_sigma<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, s11, s12, s22, G, eta1, eta2, eta1z, eta1r, eta2z, eta2r,
+                                                       chi, vec, eager);
+  }
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
@@ -199,7 +349,16 @@ int axb_solid_tau(const axb_grid_t* g, double* tau_z, double* tau_r, const doubl
   const GridD d = to_dev(g);
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
   const bool vec = vec_ok(d, {tau_z, tau_r, t11, t12, t22});
-  k_solid_tau<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, tau_z, tau_r, t11, t12, t22, r1d, vec);
+  static const bool no_march = getenv("AXB_SOLID_TILED") != nullptr;
+  const bool march = vec && !no_march && !g_axb_legacy_stencils && d.nr >= RBM + 2 && d.nz >= 2 * MTM + 2;
+  if (march) {
+    const dim3 mg((d.nz + 2 * MTM - 1) / (2 * MTM), (d.nr + RBM - 1) / RBM);
+    km_solid_tau<<<mg, MTM, 0, s>>>(d, tau_z, tau_r, t11, t12, t22, r1d);
+    AXB_LAUNCHED();
+    km_solid_tau_edge<<<mg, MTM, 0, s>>>(d, tau_z, tau_r, t11, t12, t22, r1d);
+  } else {
+    k_solid_tau<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, tau_z, tau_r, t11, t12, t22, r1d, vec);
+  }
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

@@ -406,3 +406,50 @@ def test_heaviside_shortcuts_are_bit_identical(K):
     ox.smooth_Heaviside(Href, phi, 0.02)
     K.smooth_Heaviside(H, phi, 0.02)
     assert np.max(np.abs(H - Href)) <= 1e-15 and H[3, 4] == 1.0 and H[5, 6] == 0.0
+
+
+@pytest.mark.parametrize("nr,nz", [(70, 600), (130, 1030), (18, 258), (40, 777), (35, 2048)])
+def test_solid_stress_marching_equals_tiled(K, nr, nz):
+    """G-SOL-1/2 (a18, a19): the row-marching interior kernels (grids with >= 258 columns and >= 18 rows) produce the
+    bits of the 2-D tiled kernels, which repeat the reference's operation order; both are checked against the oracle."""
+    from pyaxisymflow_b200 import _lib
+
+    rng = np.random.default_rng(nr * 7 + nz)
+    dx, _, _, Z, R = _grid(nr, nz)
+    eta1, eta2 = Z + 0.05 * _rand(rng, nr, nz), R + 0.05 * _rand(rng, nr, nz)
+    chi = np.clip(_rand(rng, nr, nz) + 0.5, 0, 1)
+    names = ("s11", "s12", "s22", "e1z", "e1r", "e2z", "e2r")
+    init = {k: rng.standard_normal((nr, nz)) for k in names}          # stale contents the rim keeps
+    tau_init = (rng.standard_normal((nr, nz)), rng.standard_normal((nr, nz)))
+    w0 = _rand(rng, nr, nz, 3.0)
+    results = {}
+    for path in ("march", "tiled"):
+        _lib.call("axb_set_stencil_path", 1 if path == "tiled" else 0)
+        try:
+            out = {}
+            for tag, c in (("plain", None), ("blend", chi)):
+                o = {k: v.copy() for k, v in init.items()}
+                K.solid_sigma(o["s11"], o["s12"], o["s22"], 3.7, dx, eta1, eta2, o["e1z"], o["e1r"], o["e2z"], o["e2r"],
+                              _chi=c)
+                out[tag] = o
+            b = out["blend"]
+            tz, tr, w = tau_init[0].copy(), tau_init[1].copy(), w0.copy()
+            K.update_vorticity_from_solid_stress(w, tz, tr, b["s11"], b["s12"], b["s22"], R, 2e-3, dx)
+            out["tau"] = {"tz": tz, "tr": tr, "w": w}
+            results[path] = out
+        finally:
+            _lib.call("axb_set_stencil_path", 0)
+    for tag in ("plain", "blend", "tau"):
+        for k in results["tiled"][tag]:
+            assert np.array_equal(results["march"][tag][k], results["tiled"][tag][k]), (tag, k)
+    # and against the oracle (the tiled path is the reference's sequence: 1e-13 covers numba-vs-NumPy last bits)
+    o = {k: v.copy() for k, v in init.items()}
+    ox.solid_sigma(o["s11"], o["s12"], o["s22"], 3.7, dx, eta1, eta2, o["e1z"], o["e1r"], o["e2z"], o["e2r"])
+    for k in names:
+        assert_close(results["march"]["plain"][k], o[k], 1e-13, "solid_sigma " + k)
+    tz, tr, w = tau_init[0].copy(), tau_init[1].copy(), w0.copy()
+    b = results["march"]["blend"]
+    ox.update_vorticity_from_solid_stress(w, tz, tr, b["s11"], b["s12"], b["s22"], R, 2e-3, dx)
+    assert_close(results["march"]["tau"]["tz"], tz, 1e-13, "tau_z")
+    assert_close(results["march"]["tau"]["tr"], tr, 1e-13, "tau_r")
+    assert_close(results["march"]["tau"]["w"], w, 1e-13, "vorticity after the solid stress")
