@@ -56,6 +56,9 @@ int64_t axb_launch_count(void);
 /* 0 (default): row-marching kernels for G-VEL / G-PEN / G-ADV / G-REF / G-DIF (stencils_march.cu);
  * 1: the 2-D tiled kernels (stencils.cu, eno3.cu) that repeat the reference's divisions bit for bit. */
 int axb_set_stencil_path(int legacy_tiled);
+/* 1: row-marching kernels for G-SOL-1 / G-SOL-2 (axb_solid_sigma, axb_solid_tau) on grids with >= 258 columns;
+ * 0 (default): the 2-D tiled kernels.  Bit-identical results; see DESIGN.md section 6.1. */
+int axb_set_solid_march(int on);
 
 /* ---- G-BND: kernels/kill_boundary_vorticity_sine.py:4-14 and :17-27 ------------------ */
 int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const double* z1d, int width,

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "axb_version": [],
     "axb_launch_count": [],
     "axb_set_stencil_path": [_I],
+    "axb_set_solid_march": [_I],
     "axb_kill_boundary_vorticity_sine_z": [_G, _P, _P, _I, _S],
     "axb_kill_boundary_vorticity_sine_r": [_G, _P, _P, _I, _S],
     "axb_periodic_ghost_comm": [_G, _P, _I, _D, _D, _S],

@@ -3,12 +3,17 @@
 
 int64_t g_axb_launches = 0;
 int g_axb_legacy_stencils = 0;
+int g_axb_solid_march = 0;
 
 extern "C" {
 int axb_version(void) { return 100; }
 int64_t axb_launch_count(void) { return g_axb_launches; }
 int axb_set_stencil_path(int legacy_tiled) {
   g_axb_legacy_stencils = legacy_tiled;
+  return AXB_OK;
+}
+int axb_set_solid_march(int on) {
+  g_axb_solid_march = on;
   return AXB_OK;
 }
 }

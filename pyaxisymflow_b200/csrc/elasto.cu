@@ -10,6 +10,7 @@
 #include "axb_common.cuh"
 
 extern int g_axb_legacy_stencils;  // capi.cu: 1 = 2-D tiled kernels only
+extern int g_axb_solid_march;      // capi.cu: 1 = row-marching G-SOL-1/2 kernels (axb_set_solid_march)
 
 namespace {
 
@@ -169,6 +170,9 @@ __global__ void __launch_bounds__(TBX* TBY)
 // z neighbours come from warp shuffles.  Interior blocks only -- every cell there is recomputed by the reference,
 // so no old gradient is read; edge blocks run the general per-pair code above on the same grid.  Same expressions
 // and true divisions as the tiled kernels: a cell gets the same bits whichever kernel computes it.
+// OPT-IN (axb_set_solid_march(1)): measured inside the 2048 x 8192 soft-sphere step the pair interior + edge launch
+// is slower than the tiled kernels (3.24 vs 3.05 ms per step) -- the edge kernel runs after the interior one on the
+// same stream instead of beside it (stencils_march.cu forks it to a side stream); kept for that follow-up.
 // -------------------------------------------------------------------------------------
 constexpr int MTM = 128, RBM = 16;
 
@@ -323,8 +327,7 @@ int axb_solid_sigma(const axb_grid_t* g, double* s11, double* s12, double* s22, 
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
   const bool vec = vec_ok(d, {s11, s12, s22, eta1, eta2, eta1z, eta1r, eta2z, eta2r, chi});
   static const bool eager = getenv("AXB_SIGMA_EAGER") != nullptr;  // load the old gradients everywhere (A/B switch)
-  static const bool no_march = getenv("AXB_SOLID_TILED") != nullptr;
-  const bool march = vec && !no_march && !g_axb_legacy_stencils && d.nr >= RBM + 2 && d.nz >= 2 * MTM + 2;
+  const bool march = vec && g_axb_solid_march && !g_axb_legacy_stencils && d.nr >= RBM + 2 && d.nz >= 2 * MTM + 2;
   if (march) {
     const dim3 mg((d.nz + 2 * MTM - 1) / (2 * MTM), (d.nr + RBM - 1) / RBM);
     if (chi)
@@ -349,8 +352,7 @@ int axb_solid_tau(const axb_grid_t* g, double* tau_z, double* tau_r, const doubl
   const GridD d = to_dev(g);
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
   const bool vec = vec_ok(d, {tau_z, tau_r, t11, t12, t22});
-  static const bool no_march = getenv("AXB_SOLID_TILED") != nullptr;
-  const bool march = vec && !no_march && !g_axb_legacy_stencils && d.nr >= RBM + 2 && d.nz >= 2 * MTM + 2;
+  const bool march = vec && g_axb_solid_march && !g_axb_legacy_stencils && d.nr >= RBM + 2 && d.nz >= 2 * MTM + 2;
   if (march) {
     const dim3 mg((d.nz + 2 * MTM - 1) / (2 * MTM), (d.nr + RBM - 1) / RBM);
     km_solid_tau<<<mg, MTM, 0, s>>>(d, tau_z, tau_r, t11, t12, t22, r1d);

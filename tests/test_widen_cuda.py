@@ -410,8 +410,9 @@ def test_heaviside_shortcuts_are_bit_identical(K):
 
 @pytest.mark.parametrize("nr,nz", [(70, 600), (130, 1030), (18, 258), (40, 777), (35, 2048)])
 def test_solid_stress_marching_equals_tiled(K, nr, nz):
-    """G-SOL-1/2 (a18, a19): the row-marching interior kernels (grids with >= 258 columns and >= 18 rows) produce the
-    bits of the 2-D tiled kernels, which repeat the reference's operation order; both are checked against the oracle."""
+    """G-SOL-1/2 (a18, a19): the opt-in row-marching interior kernels (axb_set_solid_march; grids with >= 258 columns
+    and >= 18 rows) produce the bits of the default 2-D tiled kernels, which repeat the reference's operation order;
+    both are checked against the oracle."""
     from pyaxisymflow_b200 import _lib
 
     rng = np.random.default_rng(nr * 7 + nz)
@@ -424,7 +425,7 @@ def test_solid_stress_marching_equals_tiled(K, nr, nz):
     w0 = _rand(rng, nr, nz, 3.0)
     results = {}
     for path in ("march", "tiled"):
-        _lib.call("axb_set_stencil_path", 1 if path == "tiled" else 0)
+        _lib.call("axb_set_solid_march", 1 if path == "march" else 0)
         try:
             out = {}
             for tag, c in (("plain", None), ("blend", chi)):
@@ -438,7 +439,7 @@ def test_solid_stress_marching_equals_tiled(K, nr, nz):
             out["tau"] = {"tz": tz, "tr": tr, "w": w}
             results[path] = out
         finally:
-            _lib.call("axb_set_stencil_path", 0)
+            _lib.call("axb_set_solid_march", 0)
     for tag in ("plain", "blend", "tau"):
         for k in results["tiled"][tag]:
             assert np.array_equal(results["march"][tag][k], results["tiled"][tag][k]), (tag, k)
