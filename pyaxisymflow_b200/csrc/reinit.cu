@@ -5,7 +5,7 @@
 //  examples/SoftSphereInTaylorGreenVortex/soft_sphere_in_taylor_green_vortex.py:160).
 // scikit-fmm 2022.8.15 is a third-party dependency (poetry.lock:628-629) that is not vendored in the
 // reference: PARITY UNPINNED.  oracle/axisym_oracle.py:fmm_distance restates its published
-// fast-marching algorithm; tools/reinit_model.py models what this file does and is checked against
+// fast-marching algorithm; tests/reinit_model.py models what this file does and is checked against
 // that restatement on the CPU.
 //
 // The marcher accepts one cell at a time from a heap -- serial.  Here the same upwind update is iterated

@@ -61,6 +61,14 @@ class FieldSnapshotter:
             err, self._err = self._err, None
             raise err
         self._slots.acquire()
+        try:
+            job = self._stage(items, sink)
+        except BaseException:
+            self._slots.release()
+            raise
+        self._q.put(job)
+
+    def _stage(self, items, sink):
         host, used, used_dev = {}, [], []
         event = None
         dev = {k: _as_tensor(v) for k, v in items.items()}
@@ -93,7 +101,7 @@ class FieldSnapshotter:
                 host[k] = v.copy()           # the caller may overwrite it before the worker runs
             else:
                 host[k] = v
-        self._q.put((host, used + used_dev, event, sink))
+        return host, used + used_dev, event, sink
 
     def _run(self):
         while True:

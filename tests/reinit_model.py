@@ -17,7 +17,7 @@ SAME upwind update to its fixed point, all band cells at once:
 
 tests/test_widen_oracle_cpu.py checks this model against the heap-based restatement
 (oracle.fmm_distance) for equality; the CUDA kernels repeat this arithmetic operation by operation.
-This file is test/tooling code, not product code.
+This file is test code (it imports the oracle), not product code.
 """
 import numpy as np
 

@@ -42,7 +42,7 @@ def test_baroclinic_golden():
 # ---------------------------------------------------------------------------------------------
 # 8f-3 narrow-band re-initialisation: third party (scikit-fmm), PARITY UNPINNED.  What can be pinned on
 # the CPU: the restated marcher behaves like a distance solver, and the fixed-point iteration the GPU
-# runs (tools/reinit_model.py) reproduces the marcher bit for bit wherever the field is smooth.
+# runs (tests/reinit_model.py) reproduces the marcher bit for bit wherever the field is smooth.
 # ---------------------------------------------------------------------------------------------
 def _sphere(nr, nz, zc, rc, rad):
     dx = 1.0 / nz
@@ -73,10 +73,6 @@ def test_marcher_restatement_is_a_distance_solver():
 
 
 def test_gpu_iteration_model_reproduces_the_marcher():
-    import os
-    import sys
-
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import reinit_model as rm
 
     rng = np.random.default_rng(11)
@@ -103,10 +99,6 @@ def test_gpu_iteration_model_reproduces_the_marcher():
 
 
 def test_gpu_iteration_model_terminates_where_fronts_collide():
-    import os
-    import sys
-
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import reinit_model as rm
 
     dx, Z, R, a = _sphere(18, 36, 0.3, 0.05, 0.1)
