@@ -1,4 +1,4 @@
-// widen.cu -- kernels of the SURVEY.md section 8f "next" rows (sm_100a).
+// phi_baroclinic.cu -- kernels of the SURVEY.md section 8f "next" rows (sm_100a).
 //
 //   8f-2  kernels/compute_velocity_from_phi.py:4-17        -> axb_velocity_from_phi
 //   8f-4  kernels/update_baroclinic_vorticity.py:4-127     -> axb_baroclinic_vorticity_update

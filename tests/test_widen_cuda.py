@@ -1,4 +1,4 @@
-"""GPU parity of the SURVEY.md 8f rows (kernels of csrc/widen.cu) against the oracle and the
+"""GPU parity of the SURVEY.md 8f rows (kernels of csrc/phi_baroclinic.cu) against the oracle and the
 reference-generated fixtures.  Bar: <= 1e-10 relative L-infinity; these kernels repeat the reference's
 operation order without FMA contraction, so bit equality is asserted where it holds."""
 import numpy as np
