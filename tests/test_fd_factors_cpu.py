@@ -142,3 +142,20 @@ def test_fft_factors_solve_the_operator():
         fd.build_factors("stokes", BCS[0], nr, nz, dx, "analytic", z_method="fft")      # needs the direct r solve
     with pytest.raises(ValueError):
         fd.build_factors("stokes", BCS[1], nr, nz, dx, "analytic", r_method="tridiagonal", z_method="fft")
+
+
+def test_periodic_fourstep_model():
+    """tools/periodic_fourstep_model.py (preparation for an FFT-class periodic-z solve at Nz - 4 = 4092 = 62 x 66, see
+    DESIGN.md section 10): the two small real-embedded DFT GEMMs + twiddle / transpose passes reproduce numpy.fft,
+    round-trip, and solve the periodic operator like a dense solve."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import periodic_fourstep_model as pm
+
+    for n in (12, 132, 4092):
+        fs, ef, eb = pm._check(n, nr=3)
+        assert ef <= 1e-13 and eb <= 1e-13, (n, ef, eb)
+    assert (fs.n1, fs.n2) == (62, 66)
+    assert pm._check_solve(6, 60) <= 1e-12
