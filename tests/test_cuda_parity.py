@@ -339,6 +339,78 @@ def test_pyst_closures(K, conservative):
         K.gen_elementwise_sum_pyst_kernel(field_type="tensor")
 
 
+def test_eno3_against_reference_kernel_definitions(K):
+    """a1-a7, a17 against tests/golden/eno3.npz: outputs of the reference's own pystencils kernel definitions
+    and wrappers, imported unmodified and run through tests/pystencils_shim.py (make_golden_eno3.py).  The CUDA
+    kernels are compiled without FMA contraction and keep the source's evaluation order; 1e-14 allows the
+    shared-face evaluation (front face of cell k = back face of cell k+1, one rounding of the sum differs)."""
+    g = golden("eno3")
+    f0, vel, flux0 = g["raw_field"], g["raw_vel"], g["raw_flux0"]
+    n0, n1 = f0.shape
+    rim = np.ones(f0.shape, bool)
+    rim[2:-2, 2:-2] = False
+    for tag, cons in (("cons", True), ("noncons", False)):
+        gen_flux = (K.gen_advection_flux_conservative_eno3_pyst_kernel if cons
+                    else K.gen_advection_flux_non_conservative_eno3_pyst_kernel)
+        gen_step = (K.gen_advection_timestep_euler_forward_conservative_eno3_pyst_kernel if cons
+                    else K.gen_advection_timestep_euler_forward_non_conservative_eno3_pyst_kernel)
+        for fixed in (False, (n0, n1)):
+            flux = flux0.copy()
+            gen_flux(fixed_grid_size=fixed)(advection_flux=flux, field=f0, velocity=vel, inv_dx=float(g["raw_inv_dx"]))
+            assert_close(flux, g[f"raw_flux_{tag}"], 1e-14, "a3/a4 flux closure " + tag)
+            assert np.array_equal(flux[rim], flux0[rim])
+            f, flux = f0.copy(), flux0.copy()
+            gen_step(fixed_grid_size=fixed)(field=f, advection_flux=flux, velocity=vel,
+                                            dt_by_dx=float(g["step_dt_by_dx"]))
+            assert_close(f, g[f"step_field_{tag}"], 1e-14, "a5/a6 step closure " + tag)
+            assert_close(flux, g[f"step_flux_{tag}"], 1e-13, "a5/a6 flux scratch " + tag)
+            assert np.all(flux[rim] == 0) and np.array_equal(f[rim], f0[rim])
+    s = np.zeros_like(f0)
+    K.gen_elementwise_sum_pyst_kernel()(sum_field=s, field_1=g["ew_a"], field_2=g["ew_b"])
+    assert np.array_equal(s, g["ew_sum"])
+    alias = g["ew_a"].copy()
+    K.gen_elementwise_sum_pyst_kernel()(sum_field=alias, field_1=alias, field_2=g["ew_b"])
+    assert np.array_equal(alias, g["ew_alias"])
+    vs = np.zeros_like(g["ew_va"])
+    K.gen_elementwise_sum_pyst_kernel(field_type="vector")(sum_field=vs, field_1=g["ew_va"], field_2=g["ew_vb"])
+    assert np.array_equal(vs, g["ew_vsum"])
+    fill = np.ones_like(f0)
+    K.gen_set_fixed_val_pyst_kernel()(field=fill, fixed_val=-2.5)
+    assert np.array_equal(fill, g["ew_fill"])
+    vfill = np.ones_like(g["ew_va"])
+    K.gen_set_fixed_val_pyst_kernel(field_type="vector")(vector_field=vfill, fixed_vals=[1.25, -0.75])
+    assert np.array_equal(vfill, g["ew_vfill"])
+    # a7
+    w0, uz0, ur0 = g["adv_w0"], g["adv_uz0"], g["adv_ur0"]
+    nr, nz = w0.shape
+    dt, dx = float(g["adv_dt"]), float(g["adv_dx"])
+    adv = K.gen_advect_vorticity_via_eno3(dx, nr, nz)
+    w = w0.copy()
+    adv(w, uz0.copy(), ur0.copy(), dt)
+    assert_close(w, g["adv_w_unb"], 1e-14, "a7 unbounded")
+    assert np.array_equal(w[-2:], w0[-2:]) and np.array_equal(w[:, :2], w0[:, :2])
+    assert np.array_equal(w[:, -2:], w0[:, -2:])
+    for _ in range(2):
+        adv(w, uz0.copy(), ur0.copy(), dt)
+    assert_close(w, g["adv_w_unb_3steps"], 1e-13, "a7 three steps")
+    per = K.gen_periodic_boundary_ghost_comm(2)
+    w, uz, ur = w0.copy(), uz0.copy(), ur0.copy()
+    K.gen_advect_vorticity_via_eno3_periodic(dx, nr, nz, per)(w, uz, ur, dt)
+    assert_close(w, g["adv_w_per"], 1e-14, "a7 periodic")
+    assert np.array_equal(uz, g["adv_uz_per"]) and np.array_equal(ur, g["adv_ur_per"])
+    # a17
+    e1, e2 = g["ref_e1_0"].copy(), g["ref_e2_0"].copy()
+    K.gen_advect_refmap_via_eno3(dx, nr, nz)(e1, e2, uz0.copy(), ur0.copy(), dt)
+    assert_close(e1, g["ref_e1_unb"], 1e-14, "a17 eta1")
+    assert_close(e2, g["ref_e2_unb"], 1e-14, "a17 eta2")
+    per_eta = K.gen_periodic_boundary_ghost_comm_eta(2, float(g["ref_z_max"]), dx)
+    e1, e2, uz, ur = g["ref_e1_0"].copy(), g["ref_e2_0"].copy(), uz0.copy(), ur0.copy()
+    K.gen_advect_refmap_via_eno3_periodic(dx, nr, nz, per, per_eta)(e1, e2, uz, ur, dt)
+    assert_close(e1, g["ref_e1_per"], 1e-14, "a17 eta1 periodic")
+    assert_close(e2, g["ref_e2_per"], 1e-14, "a17 eta2 periodic")
+    assert np.array_equal(uz, g["ref_uz_per"]) and np.array_equal(ur, g["ref_ur_per"])
+
+
 def test_eno3_conservation_full_size(K):
     """size-independent property at the C2 grid (1024 x 4096): with zero velocity on the rim the
     conservative update telescopes, so the mirrored-domain sum changes only by rounding."""

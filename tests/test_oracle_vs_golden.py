@@ -193,8 +193,103 @@ def test_p2m_golden_bit_exact():
     assert np.array_equal(wp, g["wp_after"])
 
 
+def test_eno3_golden_from_reference_kernel_definitions():
+    """a1-a7, a17: tests/golden/eno3.npz holds the outputs of the reference's OWN pystencils kernel
+    definitions (pyst_kernels/advection_flux.py:9-332, advection_timestep.py:14-104, elementwise_ops.py:9-104,
+    kernels/advect_vorticity_via_eno3.py:8-91, elasto_kernels/advect_refmap_via_eno3.py:8-115), imported
+    unmodified and executed through tests/pystencils_shim.py (tests/golden/make_golden_eno3.py).  Both
+    restatements (NumPy and C) must reproduce them; they follow the source's evaluation order, so bit for bit."""
+    g = golden("eno3")
+    assert bool(g["generated_with_shim"])
+    f0, vel, flux0 = g["raw_field"], g["raw_vel"], g["raw_flux0"]
+    rim = np.ones(f0.shape, bool)
+    rim[2:-2, 2:-2] = False
+    for tag, cons in (("cons", True), ("noncons", False)):
+        for step in (ox.eno3_step_numpy, ox.eno3_step):
+            f = f0.copy()
+            step(f, vel[0].copy(), vel[1].copy(), float(g["step_dt_by_dx"]), cons)
+            assert np.array_equal(f, g[f"step_field_{tag}"]), (tag, step.__name__)
+            # the raw flux closure (a3 / a4): flux += ENO3(field; inv_dx) on [2:-2, 2:-2]; rim untouched
+            f = f0.copy()
+            step(f, vel[0].copy(), vel[1].copy(), -float(g["raw_inv_dx"]), cons)
+            got = flux0.copy()
+            got[2:-2, 2:-2] += (f - f0)[2:-2, 2:-2]
+            assert_close(got, g[f"raw_flux_{tag}"], 1e-15, "raw flux " + tag)
+        assert np.array_equal(g[f"raw_flux_{tag}"][rim], flux0[rim])
+        # a5 / a6: the flux scratch holds the step's flux, its rim the fill value 0 (a1 ran on the whole array)
+        assert np.all(g[f"step_flux_{tag}"][rim] == 0)
+        assert np.array_equal(f0 + g[f"step_flux_{tag}"], g[f"step_field_{tag}"])
+        assert np.array_equal(g[f"step_field_{tag}"][rim], f0[rim])
+    # a1 / a2 elementwise closures: whole array (ghost layers 0), vector flavour = both components
+    assert np.array_equal(g["ew_sum"], g["ew_a"] + g["ew_b"]) and np.array_equal(g["ew_alias"], g["ew_sum"])
+    assert np.array_equal(g["ew_vsum"], g["ew_va"] + g["ew_vb"])
+    assert np.all(g["ew_fill"] == -2.5) and np.all(g["ew_vfill"][0] == 1.25) and np.all(g["ew_vfill"][1] == -0.75)
+    # a7 wrappers
+    dt, dx = float(g["adv_dt"]), float(g["adv_dx"])
+    for use_c in (False, True):
+        w = g["adv_w0"].copy()
+        ox.advect_vorticity_via_eno3(w, g["adv_uz0"].copy(), g["adv_ur0"].copy(), dt, dx, use_c=use_c)
+        assert np.array_equal(w, g["adv_w_unb"])
+        for _ in range(2):
+            ox.advect_vorticity_via_eno3(w, g["adv_uz0"].copy(), g["adv_ur0"].copy(), dt, dx, use_c=use_c)
+        assert np.array_equal(w, g["adv_w_unb_3steps"])
+        w, uz, ur = g["adv_w0"].copy(), g["adv_uz0"].copy(), g["adv_ur0"].copy()
+        ox.advect_vorticity_via_eno3(w, uz, ur, dt, dx, periodic_ghost=2, use_c=use_c)
+        assert np.array_equal(w, g["adv_w_per"]) and np.array_equal(uz, g["adv_uz_per"])
+        assert np.array_equal(ur, g["adv_ur_per"])
+        # a17 wrappers
+        e1, e2 = g["ref_e1_0"].copy(), g["ref_e2_0"].copy()
+        ox.advect_refmap_via_eno3(e1, e2, g["adv_uz0"].copy(), g["adv_ur0"].copy(), dt, dx, use_c=use_c)
+        assert np.array_equal(e1, g["ref_e1_unb"]) and np.array_equal(e2, g["ref_e2_unb"])
+        e1, e2, uz, ur = g["ref_e1_0"].copy(), g["ref_e2_0"].copy(), g["adv_uz0"].copy(), g["adv_ur0"].copy()
+        ox.advect_refmap_via_eno3_periodic(e1, e2, uz, ur, dt, dx, 2, float(g["ref_z_max"]), use_c=use_c)
+        assert np.array_equal(e1, g["ref_e1_per"]) and np.array_equal(e2, g["ref_e2_per"])
+        assert np.array_equal(uz, g["ref_uz_per"]) and np.array_equal(ur, g["ref_ur_per"])
+    # physical rows advected by the mirrored-domain step: j in [0, Nr-3], k in [2, Nz-3]
+    w0, w1 = g["adv_w0"], g["adv_w_unb"]
+    assert np.array_equal(w1[-2:], w0[-2:]) and np.array_equal(w1[:, :2], w0[:, :2])
+    assert np.array_equal(w1[:, -2:], w0[:, -2:]) and np.all(w1[:-2, 2:-2] != w0[:-2, 2:-2])
+
+
+def test_pystencils_shim_rules():
+    """the stand-in used to generate eno3.npz: ghost layers = max |offset| on every side of every axis
+    (pystencils create_domain_kernel with ghost_layers=None), source evaluation order, shape check."""
+    import pytest
+
+    import pystencils_shim as ps
+
+    @ps.kernel
+    def _k():
+        a, b = ps.fields("a, b : float64[2D]")
+        a[0, 0] @= (b[0, 1] if b[0, 0] > -b[0, -2] else 2.0 * b[1, 0]) - a[0, 0]
+
+    k = ps.create_kernel(_k, config=ps.CreateKernelConfig(cpu_openmp=False)).compile()
+    assert k.ghost == 2
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((9, 11)), rng.standard_normal((9, 11))
+    a0 = a.copy()
+    k(a=a, b=b)
+    exp = a0.copy()
+    for j in range(2, 7):
+        for i in range(2, 9):
+            exp[j, i] = (b[j, i + 1] if b[j, i] > -b[j, i - 2] else 2.0 * b[j + 1, i]) - a0[j, i]
+    assert np.array_equal(a, exp)
+
+    @ps.kernel
+    def _fixed():
+        f = ps.fields("f : float64[4, 6]")
+        f[0, 0] @= 1.5
+
+    kf = ps.create_kernel(_fixed).compile()
+    with pytest.raises(ValueError):
+        kf(f=np.zeros((4, 7)))
+    x = np.zeros((4, 6))
+    kf(f=x)
+    assert np.all(x == 1.5)
+
+
 def test_eno3_numpy_vs_c_restatement():
-    """ENO3 is parity-unpinned (pystencils); the two independent restatements must agree."""
+    """the two independent restatements must agree on a second seeded case."""
     rng = np.random.default_rng(3)
     n0, n1 = 36, 52
     for cons in (True, False):
