@@ -818,12 +818,46 @@ def test_rigid_flow_stepper_tridiagonal_r(K):
     assert_close(s.psi.cpu().numpy(), psi, 1e-9, "psi (tridiagonal r solve)")
 
 
+def _stokes_residual(psi, rhs, nr, nz, dx, bc, per):
+    """relative residual of the discrete equation A_r psi + psi A_z^T = r o rhs, evaluated with torch stencils
+    (FastDiagonalisationStokesSolver.py:41-97 operators), row block by row block to bound the temporaries"""
+    import torch
+
+    from pyaxisymflow_b200.fd import radial_tridiagonal
+
+    sub, diag, sup, r = (torch.from_numpy(x).cuda() for x in radial_tridiagonal("stokes", bc, nr, dx))
+    i2 = 1 / dx / dx
+    worst, scale = 0.0, 0.0
+    rb = 512
+    for j0 in range(0, nr, rb):
+        j1 = min(nr, j0 + rb)
+        p = psi[j0:j1]
+        res = diag[j0:j1, None] * p
+        lo = max(j0, 1)
+        res[lo - j0:] += sub[lo - 1:j1 - 1, None] * psi[lo - 1:j1 - 1]
+        hi = min(j1, nr - 1)
+        res[:hi - j0] += sup[j0:hi, None] * psi[j0 + 1:hi + 1]
+        if per:
+            res += i2 * (2 * p - torch.roll(p, 1, 1) - torch.roll(p, -1, 1))
+        else:
+            res += 2 * i2 * p
+            res[:, 1:] -= i2 * p[:, :-1]
+            res[:, :-1] -= i2 * p[:, 1:]
+            res[:, 0] -= i2 * p[:, 0]
+            res[:, -1] -= i2 * p[:, -1]
+        rr = r[j0:j1, None] * rhs[j0:j1]
+        res -= rr
+        worst = max(worst, res.abs().max().item())
+        scale = max(scale, rr.abs().max().item())
+    return worst / scale
+
+
 def test_fast_diagonalisation_residual_full_size(K):
     """C2 grid (1024 x 4092 inner, periodic z) and an unbounded 1024 x 2048: the solution must
     satisfy the discrete equation A_r psi + psi A_z^T = r o rhs (checked with the stencils)."""
     import torch
 
-    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver, radial_tridiagonal
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
 
     for nr, nz, bc, per in ((1024, 4092, "homogenous_neumann_along_r_and_periodic_along_z", True),
                             (1024, 2048, "homogenous_neumann_along_z_and_r", False)):
@@ -833,23 +867,107 @@ def test_fast_diagonalisation_residual_full_size(K):
         s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, basis="analytic")
         psi = torch.zeros_like(rhs)
         s.solve(psi, rhs)
-        sub, diag, sup, r = radial_tridiagonal("stokes", bc, nr, dx)
-        sub, diag, sup, r = (torch.from_numpy(x).cuda() for x in (sub, diag, sup, r))
-        Ar_psi = diag[:, None] * psi
-        Ar_psi[1:] += sub[:, None] * psi[:-1]
-        Ar_psi[:-1] += sup[:, None] * psi[1:]
-        i2 = 1 / dx / dx
-        if per:
-            psi_Az = i2 * (2 * psi - torch.roll(psi, 1, 1) - torch.roll(psi, -1, 1))
-        else:
-            psi_Az = 2 * i2 * psi
-            psi_Az[:, 1:] -= i2 * psi[:, :-1]
-            psi_Az[:, :-1] -= i2 * psi[:, 1:]
-            psi_Az[:, 0] -= i2 * psi[:, 0]
-            psi_Az[:, -1] -= i2 * psi[:, -1]
-        res = Ar_psi + psi_Az - r[:, None] * rhs
-        rel = (res.abs().max() / (r[:, None] * rhs).abs().max()).item()
+        rel = _stokes_residual(psi, rhs, nr, nz, dx, bc, per)
         assert rel < 1e-9, rel
+
+
+def test_headline_size_solve_and_step(K, stencil_path):
+    """The configuration the benchmark is quoted on, 4096 x 16384 (BASELINE.json configs[3]): (i) the default solve
+    (DCT-II -> factored tridiagonal sweeps -> DCT-III) satisfies the discrete Stokes equation to < 1e-9 for a
+    white-noise right-hand side and for the smooth one of a flow step; (ii) linearity, a size-independent
+    property: solve(a x + b y) = a solve(x) + b solve(y); (iii) two full RigidFlowStepper steps on the
+    row-marching kernels agree with the 2-D tiled kernels (the reference's operation sequence) to <= 1e-10;
+    (iv) a 64-row band of the advection and of the penalisation of that step against the CPU oracle."""
+    import torch
+
+    if stencil_path == "tiled":
+        pytest.skip("one pass: the test switches the stencil path itself")
+    from pyaxisymflow_b200 import _lib
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    nr, nz = 4096, 16384
+    dx = 1.0 / nz
+    bc = "homogenous_neumann_along_z_and_r"
+    s = FastDiagonalisationStokesSolver(nr, nz, dx)
+    assert "dct" in s.kernel_note().lower() or "cosine" in s.kernel_note().lower(), s.kernel_note()
+    torch.manual_seed(2)
+    x = torch.randn((nr, nz), dtype=torch.float64, device="cuda")
+    px = torch.zeros_like(x)
+    s.solve(px, x)
+    rel = _stokes_residual(px, x, nr, nz, dx, bc, False)
+    assert rel < 1e-9, rel
+    zz = torch.linspace(dx / 2, 1 - dx / 2, nz, dtype=torch.float64, device="cuda")
+    rr = torch.linspace(dx / 2, nr * dx - dx / 2, nr, dtype=torch.float64, device="cuda")
+    y = torch.exp(-((zz[None, :] - 0.3) ** 2 + (rr[:, None] - 0.1) ** 2) / 0.002) * torch.sin(300 * zz)[None, :]
+    py = torch.zeros_like(y)
+    s.solve(py, y)
+    rel = _stokes_residual(py, y, nr, nz, dx, bc, False)
+    assert rel < 1e-9, rel
+    comb = torch.zeros_like(x)
+    s.solve(comb, 0.75 * x - 1.5 * y)
+    lin = ((comb - (0.75 * px - 1.5 * py)).abs().max() / comb.abs().max()).item()
+    assert lin < 1e-11, lin
+    del x, px, y, py, comb, s
+    torch.cuda.empty_cache()
+
+    outs = {}
+    for path in (0, 1):
+        _lib.call("axb_set_stencil_path", path)
+        st = RigidFlowStepper(nz, grid_size_r=nr, use_graph=False)
+        assert (st.nr, st.nz) == (nr, nz)
+        st.step(2)
+        torch.cuda.synchronize()
+        outs[path] = (st.vorticity.clone(), st.psi.clone(), st.u_z.clone(), st.u_r.clone(), st.scalars())
+        if path == 0:
+            # (iv) band check of this step's advection against the CPU oracle: rows 0..63 of the mirrored
+            # domain need rows 0..65 of the inputs; the oracle runs on an 80-row band and rows < 64 compare
+            nb = 80
+            w, uz, ur = st.vorticity[:nb].cpu().numpy(), st.u_z[:nb].cpu().numpy(), st.u_r[:nb].cpu().numpy()
+            dt = 0.05 * dx
+            ref = w.copy()
+            ox.advect_vorticity_via_eno3(ref, uz.copy(), ur.copy(), dt, dx)
+            got = st.vorticity.clone()
+            K.gen_advect_vorticity_via_eno3(dx, nr, nz)(got, st.u_z, st.u_r, dt)
+            assert_close(got[:64].cpu().numpy(), ref[:64], 1e-13, "ENO3 band at 4096 x 16384")
+        del st
+        torch.cuda.empty_cache()
+    _lib.call("axb_set_stencil_path", 0)
+    for a, b, name in zip(outs[0][:4], outs[1][:4], ("vorticity", "psi", "u_z", "u_r")):
+        err = ((a - b).abs().max() / b.abs().max()).item()
+        assert err <= 1e-10, (name, err)
+    assert abs(outs[0][4]["t"] - outs[1][4]["t"]) <= 1e-12 * outs[1][4]["t"]
+    assert outs[0][0].abs().max().item() > 0
+
+
+def test_potential_solver_on_the_gpu(K):
+    """FastDiagonalisationPotentialSolver.py:119-145 through the GPU GEMM path.  The all-Neumann operator is
+    singular: the reference's 1/lambda turns the null mode (constants) into an offset of ~1e11 and what is
+    left is accurate to ~1e-6 only (DESIGN.md "Reference defects").  Compared (a) with the reference's own
+    output as it is, (b) with the null mode projected out (mean removed) on a compatible right-hand side
+    (sum r rhs = 0, r being the left null vector), and (c) through the gradient the callers take of it
+    (compute_velocity_from_phi.py:4-17), which does not see the constant."""
+    from pyaxisymflow_b200.fd import FastDiagonalisationPotentialSolver
+
+    g = golden("fast_diag")
+    rhs, dx = g["rhs"], float(g["dx"])
+    nr, nz = rhs.shape
+    s = FastDiagonalisationPotentialSolver(nr, nz, dx, basis="lapack")
+    sol = np.zeros_like(rhs)
+    s.solve(sol, rhs)
+    assert_close(sol, g["potential"], 1e-6, "potential vs reference output")
+    rj = (np.arange(nr) + 0.5) * dx
+    rc = rhs - (rj[:, None] * rhs).sum() / (rj.sum() * nz)
+    s.solve(sol, rc)
+    o = ox.FastDiagonalisationOracle(nr, nz, dx, "potential")
+    ref = np.zeros_like(rc)
+    o.solve(ref, rc)
+    assert_close(sol - sol.mean(), ref - ref.mean(), 1e-4, "potential, null mode projected out")
+    uz, ur, vz, vr = (np.zeros_like(rc) for _ in range(4))
+    K.compute_velocity_from_phi_unb(uz, ur, sol, dx)
+    ox.compute_velocity_from_phi(vz, vr, ref, dx)
+    scale = max(np.abs(vz).max(), np.abs(vr).max())
+    assert np.abs(uz - vz).max() <= 1e-4 * scale and np.abs(ur - vr).max() <= 1e-4 * scale
 
 
 # ---------------------------------------------------------------------------------------------

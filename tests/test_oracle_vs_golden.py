@@ -322,3 +322,32 @@ def test_eno3_advects_a_gaussian():
     unmoved = np.max(np.abs(before - g(0.5 + 0.8 * dt)))
     assert moved < 0.05 * unmoved
     assert abs(w.sum() - before.sum()) < 1e-12 * before.sum()
+
+
+def test_c_ports_of_the_numba_kernels_match_the_numpy_forms():
+    """bench.py's CPU legs run C/OpenMP ports of the four numba kernels of the rigid-flow loop; they must
+    agree with the NumPy restatements (which the reference-generated goldens pin) to rounding."""
+    rng = np.random.default_rng(11)
+    nr, nz = 37, 61
+    dx = 1.0 / nz
+    Z, R = _grid(nr, nz, dx)
+    w0, psi = rng.standard_normal((nr, nz)), rng.standard_normal((nr, nz))
+    a, ta, b, tb = w0.copy(), np.zeros_like(w0), w0.copy(), np.zeros_like(w0)
+    ox.diffusion_RK2(a, ta, R, 2e-3, 0.2 * dx * dx / 2e-3, dx)
+    ox.c_kernels.diffusion_RK2(b, tb, R, 2e-3, 0.2 * dx * dx / 2e-3, dx)
+    assert_close(b, a, 1e-14, "diffusion")
+    assert_close(tb, ta, 1e-14, "diffusion tmp")
+    uz, ur, vz, vr = (np.zeros_like(w0) for _ in range(4))
+    ox.compute_velocity_from_psi(uz, ur, psi, R, dx)
+    ox.c_kernels.compute_velocity_from_psi(vz, vr, psi, R, dx)
+    assert np.array_equal(uz, vz) and np.array_equal(ur, vr)
+    chi = np.clip(rng.standard_normal((nr, nz)), 0, 1)
+    pz, pr, qz, qr = (np.zeros_like(w0) for _ in range(4))
+    ox.brinkmann_penalize(1e4, 3e-3, chi, 0.7, -0.2, uz, ur, pz, pr)
+    ox.c_kernels.brinkmann_penalize(1e4, 3e-3, chi, 0.7, -0.2, uz, ur, qz, qr)
+    assert np.array_equal(pz, qz) and np.array_equal(pr, qr)
+    v1, v2 = rng.standard_normal((nr, nz)), None
+    v2 = v1.copy()
+    ox.compute_vorticity_from_velocity(v1, uz, ur, dx)
+    ox.c_kernels.compute_vorticity_from_velocity(v2, uz, ur, dx)
+    assert np.array_equal(v1, v2)
