@@ -245,6 +245,11 @@ int64_t axb_ls_workspace_bytes(int n0, int n1);
 int axb_ls_extrapolate_order1(int n0, int n1, int16_t* cur, const int16_t* tgt, double* eta_x,
                               double* eta_y, const double* gx, const double* gy, void* work,
                               int64_t work_bytes, int max_sweeps, int* sweeps_host, axb_stream_t s);
+/* core/src/extrapolate_using_least_squares.hpp:469-486 (extrapolate_using_least_squares_till_second_order):
+ * same wavefront, quadratic basis [1, x, y, x^2, xy, y^2] on the 3x3 patch (6 x 6 normal equations). */
+int axb_ls_extrapolate_order2(int n0, int n1, int16_t* cur, const int16_t* tgt, double* eta_x,
+                              double* eta_y, const double* gx, const double* gy, void* work,
+                              int64_t work_bytes, int max_sweeps, int* sweeps_host, axb_stream_t s);
 /* the wrapper elasto_kernels/extrapolate_eta_using_least_squares_unb.py:7-30 fused: mirror by
  * index, flags from phi thresholds, extrapolate, write the physical half back. */
 int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
@@ -261,6 +266,50 @@ int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const dou
 int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
                                    const double* u_r, const double* zl1d, const double* rl1d, double dt,
                                    const double* dt_dev, int periodic, axb_stream_t s);
+
+/* ---- the rest of the particle <-> mesh family of the C++ core (core/src/instantiate.yml:1-27).
+ *      kernel = one of AXB_PK_*: core/src/particle_kernels/LinearKernel.hpp, MP4.hpp, MP6.hpp,
+ *      YangSmoothThreePointKernel.hpp.  periodic = 0: the "_unbounded" (edge-clipped) functions, 1: modulo wrap.
+ *      Arrays are dense row-major, like the pybind11 bindings read them (core/src/*_bind.cpp).
+ *   axb_m2p_2d   replaces mesh_to_particles_2D_{linear_kernel,mp4,mp6,yang_smooth_three_point_kernel} and the
+ *                _unbounded_ twins (core/src/mesh_to_particles.hpp:61-253): two mesh fields (m0 x m1) sampled at
+ *                p0 x p1 particles; sums in the reference's order, results bit-identical
+ *   axb_p2m_2d   replaces particles_to_mesh_2D_* (core/src/particles_to_mesh.hpp:23-207): mesh zeroed, then the
+ *                scatter (FP64 atomics: indices / weights exact, sum order free)
+ *   axb_m2p_1d_mp4 / axb_p2m_1d_mp4   mesh_to_particles.hpp:25-37, particles_to_mesh.hpp:8-20 (periodic)
+ *   axb_wrap_particles_2d   wrap_particles_around_2D_domain (mesh_to_particles.hpp:39-55): x wraps the first /
+ *                last 10 entries of every row, y every entry of the first / last 10 rows; either pointer may be
+ *                NULL; a 1-D array is n0 = 1 with px (wrap_particles_around_1D_domain) ------------------------- */
+enum { AXB_PK_LINEAR = 0, AXB_PK_MP4 = 1, AXB_PK_MP6 = 2, AXB_PK_YANG = 3 };
+int axb_m2p_2d(int kernel, int m0, int m1, const double* field_x, const double* field_y, int p0, int p1,
+               const double* px, const double* py, double* out_x, double* out_y, double dx, double dy, int periodic,
+               axb_stream_t s);
+int axb_p2m_2d(int kernel, int m0, int m1, int p0, int p1, const double* px, const double* py, const double* val,
+               double* mesh, double dx, double dy, int periodic, axb_stream_t s);
+int axb_m2p_1d_mp4(int m, const double* field, int np, const double* pos, double* out, double dx, axb_stream_t s);
+int axb_p2m_1d_mp4(int m, int np, const double* pos, const double* val, double* mesh, double dx, axb_stream_t s);
+int axb_wrap_particles_2d(int n0, int n1, double* px, double* py, double x0, double x1, double y0, double y1,
+                          axb_stream_t s);
+
+/* ---- static-PDE extrapolation (examples/PeriodicSoftSlab/bounded_static_PDE_extrapolation.py).
+ *      Arrays are the reference's bounded arrays, dense (n0, n1) with n0, n1 >= 6; "interim" outputs are dense
+ *      (n0-4, n1-4).  phi_b is the NEGATED level set (negative inside the solid), like `bounded_phi` (:68).
+ *   axb_pde_extrap_setup   replaces _zones_setup (:142-147), _compute_normal_upwind (:149-171) and the set-up lines
+ *                          :77-93 of extrapolate(): zone bit 0 = inside_solid, bit 1 = extrap_zone; the positive /
+ *                          negative parts of the unit normal, denom = 3(|n_r| + |n_z|) + eps (interim arrays) and
+ *                          grad_eta_n = inside * n . grad(eta) (bounded array, zero rim)
+ *   axb_pde_extrap_jacobi  replaces _jacobi_iterate (:185-218): sweeps until ||update||_2 <= tol, terminated on the
+ *                          device (the host reads a 16-byte state once per batch of 32 sweeps; the entry therefore
+ *                          synchronises the stream, like the LS wavefront).  soln (bounded) is updated in place;
+ *                          rhs (bounded) may be NULL = 0.  *sweeps_host = number of sweeps performed. ------------- */
+int64_t axb_pde_extrap_workspace_bytes(int n0, int n1);
+int axb_pde_extrap_setup(int n0, int n1, const double* phi_b, const double* eta_b, double dx, double offset, double band,
+                         double eps, double* nr_pos, double* nr_neg, double* nz_pos, double* nz_neg, double* denom,
+                         uint8_t* zone, double* grad_eta_n, axb_stream_t s);
+int axb_pde_extrap_jacobi(int n0, int n1, double* soln, const double* rhs, const uint8_t* zone, const double* denom,
+                          const double* nr_pos, const double* nr_neg, const double* nz_pos, const double* nz_neg,
+                          double dx, double tol, int max_sweeps, void* work, int64_t work_bytes, int* sweeps_host,
+                          axb_stream_t s);
 
 /* ---- G-FD: kernels/FastDiagonalisationStokesSolver.py:130-156 (and the Potential /
  *      ImplicitEuler twins).  The plan holds device pointers to the caller-owned factors:

@@ -86,8 +86,17 @@ _SIGNATURES = {
     "axb_solid_vorticity_update": [_G, _P, _P, _P, _D, _P, _S],
     "axb_ls_workspace_bytes": [_I, _I],
     "axb_ls_extrapolate_order1": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
+    "axb_ls_extrapolate_order2": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_ls_extrapolate_eta": [_G, _P, _P, _P, _P, _D, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_p2m_mp4_2d": [_I, _I, _P, _P, _P, _P, _D, _D, _I, _S],
+    "axb_pde_extrap_workspace_bytes": [_I, _I],
+    "axb_pde_extrap_setup": [_I, _I, _P, _P, _D, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _S],
+    "axb_pde_extrap_jacobi": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I, _P, c_int64, POINTER(c_int), _S],
+    "axb_m2p_2d": [_I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _D, _D, _I, _S],
+    "axb_p2m_2d": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _D, _D, _I, _S],
+    "axb_m2p_1d_mp4": [_I, _P, _I, _P, _P, _D, _S],
+    "axb_p2m_1d_mp4": [_I, _I, _P, _P, _P, _D, _S],
+    "axb_wrap_particles_2d": [_I, _I, _P, _P, _D, _D, _D, _D, _S],
     "axb_advect_vorticity_particles": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _I, _S],
     "axb_fd_solve": [POINTER(AxbFdPlan), _P, c_int64, _P, c_int64, _S],
     "axb_dgemm": [_I, _I, _I, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _D, _D, _S],
@@ -109,8 +118,10 @@ _SIGNATURES = {
     "axb_rows_to_blocks": [_I, _I, _I, _P, c_int64, _P, _S],
     "axb_blocks_to_slab": [_I, _I, c_int64, _I, _P, _P, _S],
 }
-_RESTYPE = {"axb_launch_count": c_int64, "axb_ls_workspace_bytes": c_int64, "axb_reinit_workspace_bytes": c_int64}
-_NO_CHECK = {"axb_version", "axb_launch_count", "axb_ls_workspace_bytes", "axb_reinit_workspace_bytes"}
+_RESTYPE = {"axb_launch_count": c_int64, "axb_ls_workspace_bytes": c_int64, "axb_reinit_workspace_bytes": c_int64,
+            "axb_pde_extrap_workspace_bytes": c_int64}
+_NO_CHECK = {"axb_version", "axb_launch_count", "axb_ls_workspace_bytes", "axb_reinit_workspace_bytes",
+             "axb_pde_extrap_workspace_bytes"}
 
 _ERR = {-1: "AXB_EINVAL (null pointer / bad shape)", -2: "AXB_EALIGN (misaligned pointer)",
         -3: "AXB_ENOSUP (unsupported configuration)", -4: "AXB_EWORK (workspace too small)"}

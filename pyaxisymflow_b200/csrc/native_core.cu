@@ -78,38 +78,59 @@ __global__ void k_ls_classify(int n1, const short* __restrict__ cur, const int* 
   }
 }
 
-__device__ __forceinline__ void gauss3(double A[3][5], double sol[2][3]) {
-  // lstsq/least_squares.hpp:12-59 with NCoefficients = 3, NComponents = 2
+template <int NC>
+__device__ __forceinline__ void gauss_nc(double (&A)[NC][NC + 2], double (&sol)[2][NC]) {
+  // lstsq/least_squares.hpp:12-59 with NCoefficients = NC (3: order 1, 6: order 2), NComponents = 2
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < NC; ++i) {
     int piv = i;
     double best = fabs(A[i][i]);
-    for (int k = i + 1; k < 3; ++k)
+#pragma unroll
+    for (int k = i + 1; k < NC; ++k)
       if (fabs(A[k][i]) > best) { best = fabs(A[k][i]); piv = k; }
-    for (int k = i; k < 5; ++k) {
+#pragma unroll
+    for (int k = i; k < NC + 2; ++k) {
       // select-based swap keeps the arrays in registers
       const double a = A[i][k];
       double b = a;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) if (r == piv) b = A[r][k];
+      for (int r = 0; r < NC; ++r) if (r == piv) b = A[r][k];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) if (r == piv) A[r][k] = a;
+      for (int r = 0; r < NC; ++r) if (r == piv) A[r][k] = a;
       A[i][k] = b;
     }
-    for (int k = i + 1; k < 3; ++k) {
+#pragma unroll
+    for (int k = i + 1; k < NC; ++k) {
       const double c = -A[k][i] / A[i][i];
       A[k][i] = 0.0;
-      for (int j = i + 1; j < 5; ++j) A[k][j] += c * A[i][j];
+#pragma unroll
+      for (int j = i + 1; j < NC + 2; ++j) A[k][j] += c * A[i][j];
     }
   }
 #pragma unroll
   for (int comp = 0; comp < 2; ++comp)
-    for (int i = 2; i >= 0; --i) {
-      sol[comp][i] = A[i][3 + comp] / A[i][i];
-      for (int k = i - 1; k >= 0; --k) A[k][3 + comp] -= A[k][i] * sol[comp][i];
+#pragma unroll
+    for (int i = NC - 1; i >= 0; --i) {
+      sol[comp][i] = A[i][NC + comp] / A[i][i];
+#pragma unroll
+      for (int k = i - 1; k >= 0; --k) A[k][NC + comp] -= A[k][i] * sol[comp][i];
     }
 }
+// basis rows of binomial_fill_data_parallel (extrapolate_using_least_squares.hpp:43-61): each order multiplies
+// the previous order's rows, [m, m x, m y, (m x) x, (m x) y, (m y) y]
+template <int NC>
+__device__ __forceinline__ void ls_basis(double m, double x, double y, double (&b)[NC]) {
+  b[0] = m;
+  b[1] = m * x;
+  b[2] = m * y;
+  if constexpr (NC == 6) {
+    b[3] = b[1] * x;
+    b[4] = b[1] * y;
+    b[5] = b[2] * y;
+  }
+}
 
+template <int NC>
 __global__ void k_ls_solve(int n1, const short* __restrict__ cur, const int* __restrict__ cand,
                            const short* __restrict__ codes, const int* __restrict__ counters, double* eta_x,
                            double* eta_y, const double* __restrict__ gx, const double* __restrict__ gy) {
@@ -119,24 +140,25 @@ __global__ void k_ls_solve(int n1, const short* __restrict__ cur, const int* __r
   const int j = c / n1, k = c - j * n1;
   const int code = codes[t];
   const int k0 = k + ((code & 0xff) - 3), j0 = j + (((code >> 8) & 0xff) - 3);
-  double L[3][9], rhs[2][9];
-  int p = 0;
-  for (int jj = j0; jj < j0 + 3; ++jj)
-    for (int kk = k0; kk < k0 + 3; ++kk, ++p) {
-      const int gi = jj * n1 + kk;
-      const double m = (double)cur[gi];
-      L[0][p] = m;
-      L[1][p] = m * gx[kk];
-      L[2][p] = m * gy[jj];
-      // volatile-free 8-byte loads: a concurrent writer can only be an unflagged cell (m = 0)
-      rhs[0][p] = m * eta_x[gi];
-      rhs[1][p] = m * eta_y[gi];
-    }
-  double M[3][5];
+  double L[NC][9], rhs[2][9];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
+  for (int p = 0; p < 9; ++p) {
+    const int jj = j0 + p / 3, kk = k0 + p % 3;
+    const int gi = jj * n1 + kk;
+    const double m = (double)cur[gi];
+    double b[NC];
+    ls_basis<NC>(m, gx[kk], gy[jj], b);
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
+    for (int a = 0; a < NC; ++a) L[a][p] = b[a];
+    // volatile-free 8-byte loads: a concurrent writer can only be an unflagged cell (m = 0)
+    rhs[0][p] = m * eta_x[gi];
+    rhs[1][p] = m * eta_y[gi];
+  }
+  double M[NC][NC + 2];
+#pragma unroll
+  for (int a = 0; a < NC; ++a) {
+#pragma unroll
+    for (int b = 0; b < NC; ++b) {
       double s = 0.0;
 #pragma unroll
       for (int i = 0; i < 9; ++i) s += L[a][i] * L[b][i];
@@ -147,19 +169,20 @@ __global__ void k_ls_solve(int n1, const short* __restrict__ cur, const int* __r
       double s = 0.0;
 #pragma unroll
       for (int i = 0; i < 9; ++i) s += L[a][i] * rhs[d][i];
-      M[a][3 + d] = s;
+      M[a][NC + d] = s;
     }
   }
-  double sol[2][3];
-  gauss3(M, sol);
-  const double basis[3] = {1.0, gx[k], gy[j]};
+  double sol[2][NC];
+  gauss_nc<NC>(M, sol);
+  double basis[NC];
+  ls_basis<NC>(1.0, gx[k], gy[j], basis);
   double e = 0.0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) e += sol[0][i] * basis[i];
+  for (int i = 0; i < NC; ++i) e += sol[0][i] * basis[i];
   eta_x[c] = e;
   e = 0.0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) e += sol[1][i] * basis[i];
+  for (int i = 0; i < NC; ++i) e += sol[1][i] * basis[i];
   eta_y[c] = e;
 }
 
@@ -187,7 +210,7 @@ LsWork carve(void* work, long long cap) {
 }
 inline long long ls_cap_from_bytes(long long bytes) { return (bytes - 64) / 14; }
 
-int ls_run(int n0, int n1, short* cur, const short* tgt, double* eta_x, double* eta_y, const double* gx,
+int ls_run(int order, int n0, int n1, short* cur, const short* tgt, double* eta_x, double* eta_y, const double* gx,
            const double* gy, void* work, long long work_bytes, int max_sweeps, int* sweeps_host, cudaStream_t s) {
   const long long cap = ls_cap_from_bytes(work_bytes);
   if (cap < 1) return AXB_EWORK;
@@ -206,7 +229,8 @@ int ls_run(int n0, int n1, short* cur, const short* tgt, double* eta_x, double* 
   while (pending > 0 && (max_sweeps <= 0 || sweeps < max_sweeps)) {
     const int blocks = (pending + 127) / 128;
     k_ls_classify<<<blocks, 128, 0, s>>>(n1, cur, pin, pout, w.cand, w.codes, w.counters);
-    k_ls_solve<<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters, eta_x, eta_y, gx, gy);
+    if (order == 2) k_ls_solve<6><<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters, eta_x, eta_y, gx, gy);
+    else k_ls_solve<3><<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters, eta_x, eta_y, gx, gy);
     k_ls_flag<<<blocks, 128, 0, s>>>(cur, w.cand, w.counters);
     g_axb_launches += 3;
     cudaMemcpyAsync(h, w.counters, sizeof(h), cudaMemcpyDeviceToHost, s);
@@ -348,7 +372,14 @@ int axb_ls_extrapolate_order1(int n0, int n1, int16_t* cur, const int16_t* tgt, 
                               double* eta_y, const double* gx, const double* gy, void* work,
                               int64_t work_bytes, int max_sweeps, int* sweeps_host, axb_stream_t s) {
   if (!cur || !tgt || !eta_x || !eta_y || !gx || !gy || !work || n0 < 3 || n1 < 3) return AXB_EINVAL;
-  return ls_run(n0, n1, cur, tgt, eta_x, eta_y, gx, gy, work, work_bytes, max_sweeps, sweeps_host, s);
+  return ls_run(1, n0, n1, cur, tgt, eta_x, eta_y, gx, gy, work, work_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
+}
+
+int axb_ls_extrapolate_order2(int n0, int n1, int16_t* cur, const int16_t* tgt, double* eta_x,
+                              double* eta_y, const double* gx, const double* gy, void* work,
+                              int64_t work_bytes, int max_sweeps, int* sweeps_host, axb_stream_t s) {
+  if (!cur || !tgt || !eta_x || !eta_y || !gx || !gy || !work || n0 < 3 || n1 < 3) return AXB_EINVAL;
+  return ls_run(2, n0, n1, cur, tgt, eta_x, eta_y, gx, gy, work, work_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
 }
 
 int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
@@ -375,7 +406,7 @@ int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const ui
   dim3 grd((nz + 127) / 128, nr);
   k_ls_fill<<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1, eta2, extrap_zone, cur, tgt, e1, e2);
   AXB_LAUNCHED();
-  rc = ls_run(2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, s);
+  rc = ls_run(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
   if (rc) return rc;
   k_ls_unfill<<<grd, 128, 0, s>>>(nr, nz, g->ld, eta1, eta2, e1, e2);
   AXB_LAUNCHED();

@@ -559,6 +559,16 @@ def _ls_workspace(n0, n1):
 def extrapolate_using_least_squares_till_first_order(current_flag, target_flag, eta_x, eta_y, grid_x, grid_y):
     """core/src/extrapolate_using_least_squares.hpp:450-467 (pybind signature of
     core/src/extrapolate_using_least_squares_bind.cpp:11-42; flags int16, exact dtypes required)."""
+    return _ls_extrapolate("axb_ls_extrapolate_order1", current_flag, target_flag, eta_x, eta_y, grid_x, grid_y)
+
+
+def extrapolate_using_least_squares_till_second_order(current_flag, target_flag, eta_x, eta_y, grid_x, grid_y):
+    """core/src/extrapolate_using_least_squares.hpp:469-486 (binding extrapolate_using_least_squares_bind.cpp:44-75):
+    quadratic basis on the same 3 x 3 patch"""
+    return _ls_extrapolate("axb_ls_extrapolate_order2", current_flag, target_flag, eta_x, eta_y, grid_x, grid_y)
+
+
+def _ls_extrapolate(entry, current_flag, target_flag, eta_x, eta_y, grid_x, grid_y):
     st = Stage()
     cur = st.dev(current_flag, out=True, dtype=torch.int16)
     tgt = st.dev(target_flag, dtype=torch.int16)
@@ -570,7 +580,7 @@ def extrapolate_using_least_squares_till_first_order(current_flag, target_flag, 
     gx, gy = coord_1d(st, grid_x, 1, n1), coord_1d(st, grid_y, 0, n0)
     work, nbytes = _ls_workspace(n0, n1)
     sweeps = ctypes.c_int(0)
-    _call("axb_ls_extrapolate_order1", n0, n1, ptr(cur), ptr(tgt), ptr(ex), ptr(ey), ptr(gx), ptr(gy), ptr(work),
+    _call(entry, n0, n1, ptr(cur), ptr(tgt), ptr(ex), ptr(ey), ptr(gx), ptr(gy), ptr(work),
           nbytes, 0, ctypes.byref(sweeps), stream_ptr())
     st.finish()
     return sweeps.value

@@ -125,8 +125,22 @@ def test_mirrored_module_tree_matches_the_reference_layout():
         "elasto_kernels.solid_sigma": ["solid_sigma"],
         "elasto_kernels.div_tau": ["update_vorticity_from_solid_stress"],
         "elasto_kernels.extrapolate_eta_using_least_squares_unb": ["extrapolate_eta_with_least_squares"],
-        "core.particles_to_mesh": ["particles_to_mesh_2D_unbounded_mp4", "particles_to_mesh_2D_mp4"],
-        "core.extrapolate_using_least_squares": ["extrapolate_using_least_squares_till_first_order"],
+        # every name of core/src/instantiate.yml:1-34
+        "core.mesh_to_particles": [
+            "mesh_to_particles_1D_mp4", "wrap_particles_around_1D_domain", "mesh_to_particles_2D_linear_kernel",
+            "mesh_to_particles_2D_mp4", "mesh_to_particles_2D_yang_smooth_three_point_kernel",
+            "mesh_to_particles_2D_mp6", "wrap_particles_around_2D_domain",
+            "mesh_to_particles_2D_unbounded_linear_kernel",
+            "mesh_to_particles_2D_unbounded_yang_smooth_three_point_kernel", "mesh_to_particles_2D_unbounded_mp4",
+            "mesh_to_particles_2D_unbounded_mp6"],
+        "core.particles_to_mesh": [
+            "particles_to_mesh_1D_mp4", "particles_to_mesh_2D_linear_kernel",
+            "particles_to_mesh_2D_yang_smooth_three_point_kernel", "particles_to_mesh_2D_mp4",
+            "particles_to_mesh_2D_mp6", "particles_to_mesh_2D_unbounded_linear_kernel",
+            "particles_to_mesh_2D_unbounded_yang_smooth_three_point_kernel", "particles_to_mesh_2D_unbounded_mp4",
+            "particles_to_mesh_2D_unbounded_mp6"],
+        "core.extrapolate_using_least_squares": ["extrapolate_using_least_squares_till_first_order",
+                                                 "extrapolate_using_least_squares_till_second_order"],
     }.items():
         m = importlib.import_module("pyaxisymflow_b200." + mod)
         for n in names:

@@ -454,3 +454,138 @@ def test_solid_stress_marching_equals_tiled(K, nr, nz):
     assert_close(results["march"]["tau"]["tz"], tz, 1e-13, "tau_z")
     assert_close(results["march"]["tau"]["tr"], tr, 1e-13, "tau_r")
     assert_close(results["march"]["tau"]["w"], w, 1e-13, "vorticity after the solid stress")
+
+
+# ---------------------------------------------------------------------------------------------
+# the rest of the C++ core family (core/src/instantiate.yml), goldens from the reference C++ itself
+# ---------------------------------------------------------------------------------------------
+PARTICLE_KERNELS = ("linear_kernel", "mp4", "mp6", "yang_smooth_three_point_kernel")
+
+
+def test_core_particle_family_against_reference_cpp():
+    """mesh_to_particles_2D_* / particles_to_mesh_2D_* (periodic and "unbounded", four kernels), the 1-D MP4 pair and
+    the wrap routines against tests/golden/core_family.npz (reference C++ compiled as-is).  Gathers repeat the
+    reference's summation order: bit-identical (Yang's kernel goes through asin / sqrt: <= 4 ulp).  Scatters add
+    with atomics: indices and weights exact, sums to 1e-14."""
+    import pyaxisymflow_b200.core.mesh_to_particles as m2p
+    import pyaxisymflow_b200.core.particles_to_mesh as p2m
+
+    g = golden("core_family")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    for k in PARTICLE_KERNELS:
+        for per in (True, False):
+            mid = "" if per else "unbounded_"
+            px, py = (g["pxw"], g["pyw"]) if per else (g["px"], g["py"])
+            ox_, oy_ = np.full(px.shape, 3.0), np.full(px.shape, 3.0)
+            getattr(m2p, f"mesh_to_particles_2D_{mid}{k}")(g["fx"], g["fy"], px, py, ox_, oy_, dx, dy)
+            if k.startswith("yang"):
+                assert_close(ox_, g[f"m2p_{mid}{k}_x"], 1e-15, k)
+                assert_close(oy_, g[f"m2p_{mid}{k}_y"], 1e-15, k)
+            else:
+                assert np.array_equal(ox_, g[f"m2p_{mid}{k}_x"]), (k, per)
+                assert np.array_equal(oy_, g[f"m2p_{mid}{k}_y"]), (k, per)
+            mesh = np.full(g["fx"].shape, 3.0)
+            getattr(p2m, f"particles_to_mesh_2D_{mid}{k}")(px, py, g["val"], mesh, dx, dy)
+            ref = g[f"p2m_{mid}{k}"]
+            assert np.array_equal(mesh != 0, ref != 0), (k, per)          # same cells touched: index work exact
+            assert_close(mesh, ref, 1e-14, f"p2m {mid}{k}")
+    o1 = np.zeros_like(g["q1"])
+    m2p.mesh_to_particles_1D_mp4(g["f1"], g["q1"], o1, dx)
+    assert np.array_equal(o1, g["m2p_1d"])
+    m1 = np.ones_like(g["f1"])
+    p2m.particles_to_mesh_1D_mp4(g["q1"], g["v1"], m1, dx)
+    assert_close(m1, g["p2m_1d"], 1e-14, "p2m 1-D")
+    wx, wy = g["wrap_x0"].copy(), g["wrap_y0"].copy()
+    m2p.wrap_particles_around_2D_domain(wx, wy, 0.0, 1.0, 0.0, 0.5)
+    assert np.array_equal(wx, g["wrap_x"]) and np.array_equal(wy, g["wrap_y"])
+    w1 = g["wrap1_in"].copy()
+    m2p.wrap_particles_around_1D_domain(w1, 0.0, 1.0)
+    assert np.array_equal(w1, g["wrap1_out"])
+    sx, sy = g["wrap_small_in"].copy(), g["wrap_small_in"].copy()
+    m2p.wrap_particles_around_2D_domain(sx, sy, 0.0, 1.0, 0.0, 1.0)
+    assert np.array_equal(sx, g["wrap_small_x"]) and np.array_equal(sy, g["wrap_small_y"])
+    with pytest.raises(TypeError):
+        m2p.mesh_to_particles_2D_mp4(g["fx"].astype(np.float32), g["fy"], g["px"], g["py"], ox_, oy_, dx, dy)
+
+
+@pytest.mark.parametrize("kernel", PARTICLE_KERNELS)
+def test_core_particle_family_large_against_oracle(kernel):
+    """1024 x 2048 mesh (config C5's grid), 2 M particles displaced by up to 1.7 cells: gather bit-identical to the
+    oracle, scatter to 1e-13; interpolating a constant field returns the constant (partition of unity, periodic)."""
+    rng = np.random.default_rng(5)
+    m0, m1 = 1024, 2048
+    dx = 1.0 / m1
+    fx, fy = rng.standard_normal((m0, m1)), rng.standard_normal((m0, m1))
+    px = (np.arange(m1)[None, :] + 0.5 + 1.7 * rng.uniform(-1, 1, (m0, m1))) * dx
+    py = (np.arange(m0)[:, None] + 0.5 + 1.7 * rng.uniform(-1, 1, (m0, m1))) * dx
+    val = rng.standard_normal((m0, m1))
+    import pyaxisymflow_b200.core.mesh_to_particles as m2p
+    import pyaxisymflow_b200.core.particles_to_mesh as p2m
+
+    a, b, c, d = (np.zeros((m0, m1)) for _ in range(4))
+    getattr(m2p, f"mesh_to_particles_2D_unbounded_{kernel}")(fx, fy, px, py, a, b, dx, dx)
+    ox.mesh_to_particles_2D(kernel, False, fx, fy, px, py, c, d, dx, dx)
+    if kernel.startswith("yang"):
+        assert_close(a, c, 1e-15, kernel)
+        assert_close(b, d, 1e-15, kernel)
+    else:
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+    mesh, ref = np.zeros((m0, m1)), np.zeros((m0, m1))
+    getattr(p2m, f"particles_to_mesh_2D_unbounded_{kernel}")(px, py, val, mesh, dx, dx)
+    ox.particles_to_mesh_2D(kernel, False, px, py, val, ref, dx, dx)
+    assert_close(mesh, ref, 1e-13, "scatter " + kernel)
+    pxw, pyw = np.mod(px, m1 * dx), np.mod(py, m0 * dx)
+    ones = np.ones((m0, m1))
+    getattr(m2p, f"mesh_to_particles_2D_{kernel}")(ones, 2 * ones, pxw, pyw, a, b, dx, dx)
+    assert np.max(np.abs(a - 1)) < 1e-13 and np.max(np.abs(b - 2)) < 1e-13
+
+
+def test_least_squares_extrapolation_second_order():
+    """extrapolate_using_least_squares_till_second_order (core/src/extrapolate_using_least_squares.hpp:469-486)
+    against the reference C++ output: flags and values bit-exact, like the first-order routine."""
+    import pyaxisymflow_b200.core.extrapolate_using_least_squares as els
+
+    g = golden("core_family")
+    for order, fn in ((1, els.extrapolate_using_least_squares_till_first_order),
+                      (2, els.extrapolate_using_least_squares_till_second_order)):
+        c, a, b = g["ls_cur"].copy(), g["ls_ex"].copy(), g["ls_ey"].copy()
+        fn(c, g["ls_tgt"], a, b, g["ls_gx"], g["ls_gy"])
+        assert np.array_equal(c, g[f"ls{order}_cur"])
+        assert np.array_equal(a, g[f"ls{order}_ex"], equal_nan=True), order
+        assert np.array_equal(b, g[f"ls{order}_ey"], equal_nan=True), order
+
+
+def test_static_pde_extrapolation_against_reference():
+    """StaticPDEExtrapolation (examples/PeriodicSoftSlab/bounded_static_PDE_extrapolation.py) against outputs of the
+    reference class itself (tests/golden/static_pde.npz): a sphere away from the walls and a z-periodic slab.  Same
+    Jacobi iterates (every sweep reads the previous one only), termination decided on the device by the same 2-norm."""
+    from pyaxisymflow_b200.ops import gen_periodic_boundary_ghost_comm
+    from pyaxisymflow_b200.static_pde_extrapolation import StaticPDEExtrapolation
+
+    g = golden("static_pde")
+    nr, nz = g["box_phi"].shape
+    dx = float(g["box_dx"])
+    eta = g["box_eta0"].copy()
+    s = StaticPDEExtrapolation(dx, nr, nz, float(g["box_tol"]), float(g["box_band"]))
+    s.extrapolate(eta, g["box_phi"].copy())
+    assert [s.r_start, s.r_end, s.z_start, s.z_end] == list(g["box_bounds"])
+    assert_close(eta, g["box_eta"], 1e-12, "extrapolated eta (sphere)")
+    assert s.sweeps[0] > 3 and s.sweeps[1] > 3
+    # the extrapolated field is constant along the normals: outside the solid, inside the band, n . grad(eta) ~ grad_n
+    assert np.count_nonzero(eta) > np.count_nonzero(g["box_eta0"])
+    per = gen_periodic_boundary_ghost_comm(2)
+    eta2, phi2 = g["slab_eta0"].copy(), g["slab_phi"].copy()
+    s2 = StaticPDEExtrapolation(dx, nr, nz, float(g["slab_tol"]), float(g["slab_band"]), periodic=True,
+                                per_communicator_gen=per, per_communicator_eta=per)
+    s2.extrapolate(eta2, phi2)
+    assert [s2.r_start, s2.r_end, s2.z_start, s2.z_end] == list(g["slab_bounds"])
+    assert np.array_equal(phi2, g["slab_phi_after"])
+    assert_close(eta2, g["slab_eta"], 1e-12, "extrapolated eta (periodic slab)")
+    with pytest.raises(ValueError):
+        StaticPDEExtrapolation(dx, nr, nz, 1e-6, 6 * dx, periodic=True)
+    # device-resident call: tensors in place
+    import torch
+
+    te, tp = torch.from_numpy(g["box_eta0"].copy()).cuda(), torch.from_numpy(g["box_phi"].copy()).cuda()
+    StaticPDEExtrapolation(dx, nr, nz, float(g["box_tol"]), float(g["box_band"])).extrapolate(te, tp)
+    assert_close(te.cpu().numpy(), g["box_eta"], 1e-12, "device-resident call")
