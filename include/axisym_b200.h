@@ -291,6 +291,20 @@ int axb_p2m_1d_mp4(int m, int np, const double* pos, const double* val, double* 
 int axb_wrap_particles_2d(int n0, int n1, double* px, double* py, double x0, double x1, double y0, double y1,
                           axb_stream_t s);
 
+/* ---- periodic-z transforms of G-FD (kernels/FastDiagonalisationStokesSolver.py:88-93, :137-156 with the periodic
+ *      z operator): real FFT of every row in one pass over HBM, any even n = 2M whose half length has prime factors
+ *      <= 64 only and fits shared memory (M <= 4266), e.g. the 4092 inner columns of the 1024 x 4096 periodic
+ *      configuration.  Half-complex layout of a transformed row: [Re X_0 .. Re X_M | Im X_1 .. Im X_{M-1}].
+ *      tables: n + 1 (re, im) pairs  [exp(-2 pi i k / M), k < M | exp(-2 pi i k / n), k <= M]  (host-rounded).
+ *   axb_rfft_rows    dst = scale * rfft(src); columns n .. pad_to-1 of dst are zero-filled (pad_to <= ld_dst)
+ *   axb_irfft_rows   dst = scale * (M * irfft(src)), i.e. pass scale = 1/M for the inverse of axb_rfft_rows(scale 1)
+ *   axb_rfft_supported(n) -> 1 / 0 ------------------------------------------------------------------------------ */
+int axb_rfft_rows(int rows, int n, const double* src, int64_t ld_src, double* dst, int64_t ld_dst, int pad_to,
+                  const double* tables, double scale, axb_stream_t s);
+int axb_irfft_rows(int rows, int n, const double* src, int64_t ld_src, double* dst, int64_t ld_dst,
+                   const double* tables, double scale, axb_stream_t s);
+int axb_rfft_supported(int n);
+
 /* ---- static-PDE extrapolation (examples/PeriodicSoftSlab/bounded_static_PDE_extrapolation.py).
  *      Arrays are the reference's bounded arrays, dense (n0, n1) with n0, n1 >= 6; "interim" outputs are dense
  *      (n0-4, n1-4).  phi_b is the NEGATED level set (negative inside the solid), like `bounded_phi` (:68).
@@ -361,6 +375,8 @@ typedef struct axb_fd_plan {
    * inside every solve. */
   const double* r_inv_pivots;
   const double* r_row_coef;
+  int32_t nz_spec;             /* z_fft == 2 (periodic real FFT, csrc/pfft.cu): pitch of the half-complex spectral rows,
+                                  a multiple of 16 >= nz; lam_z, r_inv_pivots and work (2 * nr * nz_spec) follow it */
 } axb_fd_plan_t;
 /* Row-wise cosine transforms through a shared-memory FFT (n = 2^p, 64 <= n <= 16384):
  *   axb_dct2_rows: dst[m, k] = s_k * sum_j src[m, j] cos(pi k (2j+1) / (2n)), s_0 = scale0, s_k = scale

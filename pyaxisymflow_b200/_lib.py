@@ -34,7 +34,7 @@ class AxbFdPlan(Structure):
                 ("r_tridiagonal", c_int32),
                 ("r_sub", c_void_p), ("r_diag", c_void_p), ("r_sup", c_void_p), ("r_scale", c_void_p),
                 ("z_fft", c_int32), ("z_tables", c_void_p), ("r_inv_pivots", c_void_p),
-                ("r_row_coef", c_void_p)]
+                ("r_row_coef", c_void_p), ("nz_spec", c_int32)]
 
 
 _G = POINTER(AxbGrid)
@@ -89,6 +89,9 @@ _SIGNATURES = {
     "axb_ls_extrapolate_order2": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_ls_extrapolate_eta": [_G, _P, _P, _P, _P, _D, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_p2m_mp4_2d": [_I, _I, _P, _P, _P, _P, _D, _D, _I, _S],
+    "axb_rfft_rows": [_I, _I, _P, c_int64, _P, c_int64, _I, _P, _D, _S],
+    "axb_irfft_rows": [_I, _I, _P, c_int64, _P, c_int64, _P, _D, _S],
+    "axb_rfft_supported": [_I],
     "axb_pde_extrap_workspace_bytes": [_I, _I],
     "axb_pde_extrap_setup": [_I, _I, _P, _P, _D, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _S],
     "axb_pde_extrap_jacobi": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I, _P, c_int64, POINTER(c_int), _S],
@@ -121,7 +124,7 @@ _SIGNATURES = {
 _RESTYPE = {"axb_launch_count": c_int64, "axb_ls_workspace_bytes": c_int64, "axb_reinit_workspace_bytes": c_int64,
             "axb_pde_extrap_workspace_bytes": c_int64}
 _NO_CHECK = {"axb_version", "axb_launch_count", "axb_ls_workspace_bytes", "axb_reinit_workspace_bytes",
-             "axb_pde_extrap_workspace_bytes"}
+             "axb_pde_extrap_workspace_bytes", "axb_rfft_supported"}
 
 _ERR = {-1: "AXB_EINVAL (null pointer / bad shape)", -2: "AXB_EALIGN (misaligned pointer)",
         -3: "AXB_ENOSUP (unsupported configuration)", -4: "AXB_EWORK (workspace too small)"}

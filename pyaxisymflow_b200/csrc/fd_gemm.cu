@@ -25,6 +25,8 @@
 
 #include "axb_common.cuh"
 
+int launch_rfft_rows(int inverse, int rows, int N, const double* src, long long ld_src, double* dst, long long ld_dst,
+                     int pad_to, const double* tables, double scale, cudaStream_t st);
 int launch_dct_rows(int inverse, int rows, int N, const double* src, long long ld_src, double* dst, long long ld_dst,
                     const double* tabs, double scale0, double scale, cudaStream_t st);   // zfft.cu
 
@@ -629,18 +631,30 @@ int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const doub
                  axb_stream_t s) {
   if (!p || !sol || !rhs || !p->lam_z || !p->work) return AXB_EINVAL;
   const int nr = p->nr, nz = p->nz;
+  // spectral width: nz, except for the periodic real FFT whose half-complex rows are padded to a multiple of 16
+  const int nzs = (p->z_fft == 2) ? p->nz_spec : nz;
+  if (nzs < nz) return AXB_EINVAL;
   double* w0 = p->work;
-  double* w1 = p->work + (long long)nr * nz;
+  double* w1 = p->work + (long long)nr * nzs;
   int rc;
   auto r_solve = [&]() -> int {
-    if (p->r_row_coef && tri_fast_ok(nz, w1, nz, p->r_inv_pivots))
-      return launch_tri_factored(nr, nz, w1, nz, p->r_inv_pivots, p->r_row_coef, s);
-    return launch_thomas(nr, nz, w1, nz, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
+    if (p->r_row_coef && tri_fast_ok(nzs, w1, nzs, p->r_inv_pivots))
+      return launch_tri_factored(nr, nzs, w1, nzs, p->r_inv_pivots, p->r_row_coef, s);
+    return launch_thomas(nr, nzs, w1, nzs, p->r_sub, p->r_diag, p->r_sup, p->lam_z, p->r_scale, p->c0, p->c1, w0, s);
   };
   if (p->r_tridiagonal) {
     // z transform (parity-split leaves or dense) -> batched tridiagonal r solve per z-mode -> back
     if (!p->r_sub || !p->r_diag || !p->r_sup) return AXB_EINVAL;
     if (p->n_leaves > AXB_FD_MAX_LEAVES || p->n_folds > AXB_FD_MAX_LEAVES) return AXB_EINVAL;
+    if (p->z_fft == 2) {
+      // periodic z: real FFT of every row (half-complex spectrum) -> Thomas per column -> inverse real FFT
+      if (!p->z_tables || rhs == w1 || sol == w1) return AXB_EINVAL;
+      rc = launch_rfft_rows(0, nr, nz, rhs, ld_rhs, w1, nzs, nzs, p->z_tables, 1.0, (cudaStream_t)s);
+      if (rc) return rc;
+      rc = r_solve();
+      if (rc) return rc;
+      return launch_rfft_rows(1, nr, nz, w1, nzs, sol, ld_sol, 0, p->z_tables, 2.0 / nz, (cudaStream_t)s);
+    }
     if (p->z_fft) {
       // DCT-II of every row -> Thomas per z-mode -> DCT-III: three HBM-bound launches
       if (!p->z_tables || rhs == w1 || sol == w1) return AXB_EINVAL;

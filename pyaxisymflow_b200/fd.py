@@ -291,9 +291,59 @@ def axial_split_plan(family, sign, nz, dx, levels, device="cpu"):
     return plan
 
 
+def rfft_factors(m, max_radix=64):
+    """radices of the half-length complex FFT of csrc/pfft.cu (4s, a 2, then odd primes); None if a prime factor
+    exceeds max_radix"""
+    out, twos = [], 0
+    while m % 2 == 0:
+        m //= 2
+        twos += 1
+    out += [4] * (twos // 2) + [2] * (twos % 2)
+    p = 3
+    while p <= max_radix and m > 1:
+        while m % p == 0:
+            out.append(p)
+            m //= p
+        p += 2
+    return out if m == 1 else None
+
+
+def rfft_supported(nz):
+    """periodic z: even nz whose half length has small prime factors only and fits shared memory (csrc/pfft.cu)"""
+    return nz >= 4 and nz % 2 == 0 and rfft_factors(nz // 2) is not None and 3 * (nz // 2) * 16 <= 200 * 1024
+
+
 def fft_eligible(family, nz):
-    """the shared-memory FFT transforms cover the Neumann-z family at nz = 2^p, 64 <= nz <= 16384"""
+    """the shared-memory FFT transforms cover the Neumann-z family at nz = 2^p, 64 <= nz <= 16384 (cosine
+    transforms, csrc/zfft.cu) and the periodic family at even nz with small prime factors (real FFT, csrc/pfft.cu)"""
+    if family == "periodic":
+        return rfft_supported(nz)
     return family == "neumann" and 64 <= nz <= 16384 and (nz & (nz - 1)) == 0
+
+
+def rfft_tables(nz):
+    """tables of axb_rfft_rows / axb_irfft_rows as one (nz + 1, 2) float64 array:
+    [exp(-2 pi i k / M), k < M | exp(-2 pi i k / nz), k <= M], M = nz / 2"""
+    M = nz // 2
+    tab = np.concatenate([np.exp(-2j * np.pi * np.arange(M) / M), np.exp(-2j * np.pi * np.arange(M + 1) / nz)])
+    tab[0], tab[M], tab[M + M] = 1, 1, -1
+    return np.ascontiguousarray(np.stack([tab.real, tab.imag], axis=1))
+
+
+def rfft_spectral_width(nz):
+    """pitch of the half-complex spectral rows: a multiple of 16 so that the factored TMA sweeps apply"""
+    return (nz + 15) // 16 * 16
+
+
+def rfft_column_eigenvalues(sign, nz, dx):
+    """lam_z of every column of the half-complex layout [Re X_0 .. Re X_M | Im X_1 .. Im X_{M-1} | padding]:
+    (2 - 2 cos(2 pi m / nz)) / dx^2 of the column's Fourier mode m; padding columns (zero data) take mode 1's value"""
+    M = nz // 2
+    modes = np.concatenate([np.arange(M + 1), np.arange(1, M)])
+    lam = np.empty(rfft_spectral_width(nz))
+    lam[:nz] = sign * (2 - 2 * np.cos(2 * np.pi * modes / nz)) / dx / dx
+    lam[nz:] = sign * (2 - 2 * np.cos(2 * np.pi / nz)) / dx / dx
+    return lam
 
 
 def dct_tables(nz):
@@ -378,9 +428,12 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
         levels = split_levels(family, nz, split)
         if z_method == "fft":
             if r_method != "tridiagonal" or not fft_eligible(family, nz):
-                raise ValueError("z_method='fft' needs r_method='tridiagonal', the Neumann-z family and "
-                                 "nz = 2^p with 64 <= nz <= 16384")
-            lam_z, Rz, Rzb = axial_natural_eigenvalues(family, sign, nz, dx), None, None
+                raise ValueError("z_method='fft' needs r_method='tridiagonal' and either the Neumann-z family with "
+                                 "nz = 2^p, 64 <= nz <= 16384, or periodic z with an even nz of small prime factors")
+            if family == "periodic":
+                lam_z, Rz, Rzb = rfft_column_eigenvalues(sign, nz, dx), None, None
+            else:
+                lam_z, Rz, Rzb = axial_natural_eigenvalues(family, sign, nz, dx), None, None
         elif levels > 0:
             zsplit = axial_split_plan(family, sign, nz, dx, levels, device=device)
             lam_z, Rz, Rzb = zsplit["lam_z"], None, None
@@ -401,7 +454,8 @@ def build_factors(kind, bc_type, nr, nz, dx, basis="auto", nu_dt=None, device="c
         raise ValueError(f"z_method {z_method!r} is not available with basis {basis!r}")
     zfft = None
     if z_method == "fft":
-        zfft = {"tables": dev(dct_tables(nz)), "family": family, "sign": sign, "dx": dx}
+        zfft = {"tables": dev(rfft_tables(nz) if family == "periodic" else dct_tables(nz)), "family": family,
+                "sign": sign, "dx": dx, "nz_spec": rfft_spectral_width(nz) if family == "periodic" else nz}
     tri = None
     if r_method == "tridiagonal":
         tri = {"sub": dev(sub), "diag": dev(diag), "sup": dev(sup), "scale": dev(r) if kind == "stokes" else None}
@@ -425,6 +479,17 @@ def apply_factors_host(f, rhs):
     if f.get("tri") is not None:
         tri = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in f["tri"].items()}
         t = np.array(rhs, dtype=np.float64)
+        if f.get("zfft") is not None and f["zfft"]["family"] == "periodic":
+            # real FFT rows in the half-complex layout (host check only; numpy.fft stands in for csrc/pfft.cu)
+            n = t.shape[1]
+            M, ns = n // 2, f["zfft"]["nz_spec"]
+            X = np.fft.rfft(t, axis=1)
+            spec = np.zeros((t.shape[0], ns))
+            spec[:, :M + 1], spec[:, M + 1:n] = X.real, X.imag[:, 1:M]
+            spec = thomas_host(spec, tri["sub"], tri["diag"], tri["sup"], g["lam_z"], tri["scale"], g["c0"], g["c1"])
+            Y = np.zeros((t.shape[0], M + 1), complex)
+            Y.real, Y.imag[:, 1:M] = spec[:, :M + 1], spec[:, M + 1:n]
+            return np.fft.irfft(Y, n=n, axis=1)
         if f.get("zfft") is not None:
             # DCT-II / DCT-III written as products with the orthonormal cosine basis (host check only)
             zf = f["zfft"]
@@ -472,6 +537,8 @@ def factor_pivots(nr, nz, f):
     """reciprocal LU pivots of the nz tridiagonal r systems (axb_tridiag_factor_columns), kept with the
     factor set on the GPU; needs nz % 16 == 0 (otherwise the solve recomputes the pivots every time)"""
     tri = f.get("tri")
+    if f.get("zfft") is not None:
+        nz = f["zfft"]["nz_spec"]
     if tri is None or nz % 16 or not f["lam_z"].is_cuda:
         return
     inv = torch.empty((nr, nz), dtype=torch.float64, device=f["lam_z"].device)
@@ -499,9 +566,10 @@ def make_plan(nr, nz, f, work):
     p.r_inv_pivots = p.r_row_coef = None
     if tri is not None and tri.get("inv") is not None:
         p.r_inv_pivots, p.r_row_coef = tri["inv"].data_ptr(), tri["row_coef"].data_ptr()
-    p.z_fft = 0
+    p.z_fft, p.nz_spec = 0, nz
     if f.get("zfft") is not None:
-        p.z_fft, p.z_tables = 1, f["zfft"]["tables"].data_ptr()
+        p.z_fft, p.z_tables = (2 if f["zfft"]["family"] == "periodic" else 1), f["zfft"]["tables"].data_ptr()
+        p.nz_spec = f["zfft"]["nz_spec"]
     zs = f.get("zsplit")
     p.n_leaves = p.n_folds = 0
     if zs is not None:
@@ -560,8 +628,9 @@ class _FdBase:
                                      split=split, r_method=r_method, z_method=z_method)
         self.basis = self.factors["basis"]
         # spectral buffer of the reference (FastDiagonalisationStokesSolver.py:38-39) x 2
-        self.work = torch.empty(2 * grid_size_r * grid_size_z, dtype=torch.float64, device="cuda")
         f = self.factors
+        nzs = f["zfft"]["nz_spec"] if f.get("zfft") is not None else grid_size_z
+        self.work = torch.empty(2 * grid_size_r * nzs, dtype=torch.float64, device="cuda")
         factor_pivots(grid_size_r, grid_size_z, f)
         self.plan = make_plan(grid_size_r, grid_size_z, f, self.work)
 
@@ -614,6 +683,11 @@ class FastDiagonalisationStokesSolver(_FdBase):
         return solve_hbm_bytes(self.grid_size_r, self.grid_size_z, self.factors)
 
     def kernel_note(self):
+        if self.factors.get("zfft") is not None and self.factors["zfft"]["family"] == "periodic":
+            return ("fast-diagonalisation solve = k_rfft_rows + k_tri_sweep<fwd> + k_tri_sweep<bwd> + k_irfft_rows "
+                    "(4 launches: shared-memory mixed-radix real FFTs along periodic z, radices "
+                    f"{rfft_factors(self.grid_size_z // 2)}, factored tridiagonal sweeps along r; 80 algorithmic "
+                    "B/grid-pt)")
         if self.factors.get("zfft") is not None:
             return ("fast-diagonalisation solve = k_dct2_rows + k_tri_sweep<fwd> + k_tri_sweep<bwd> + k_dct3_rows "
                     "(4 launches: shared-memory FFT cosine transforms along z, factored tridiagonal sweeps along r; "

@@ -628,8 +628,12 @@ def _p2m(px, py, val, mesh, dx, dy, periodic):
         if t.ndim != 2 or not t.is_contiguous():
             raise ValueError("core routines read .data() and need C-contiguous 2-D arrays, like the reference")
     n0, n1 = tm.shape
-    _call("axb_p2m_mp4_2d", n0, n1, ptr(tx), ptr(ty), ptr(tv), ptr(tm), float(dx), float(dy), int(periodic),
-          stream_ptr())
+    if tuple(tx.shape) == (n0, n1):      # lattice-shaped particle arrays (the drivers' case): the 2-D launch
+        _call("axb_p2m_mp4_2d", n0, n1, ptr(tx), ptr(ty), ptr(tv), ptr(tm), float(dx), float(dy), int(periodic),
+              stream_ptr())
+    else:                                # any particle-array shape, like the reference (csrc/particles.cu)
+        _call("axb_p2m_2d", 1, n0, n1, tx.shape[0], tx.shape[1], ptr(tx), ptr(ty), ptr(tv), ptr(tm), float(dx),
+              float(dy), int(periodic), stream_ptr())
     st.finish()
 
 

@@ -693,6 +693,73 @@ def test_fast_diagonalisation_fft_z(K, nr, nz):
         FastDiagonalisationStokesSolver(nr, 96, dx, r_method="tridiagonal", z_method="fft")
 
 
+@pytest.mark.parametrize("n", [4092, 252, 60, 8, 1020, 52, 4096, 8190])
+def test_rfft_rows_against_numpy(K, n):
+    """csrc/pfft.cu: real FFT rows (mixed radix, half-complex layout) and their inverse against numpy.fft; aligned and
+    unaligned (odd pitch) views, zero-filled padding columns"""
+    import ctypes
+
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+
+    assert _lib.call("axb_rfft_supported", n) == 1 and fd.rfft_supported(n)
+    rng = np.random.default_rng(n)
+    rows, M = 37, n // 2
+    x = rng.standard_normal((rows, n))
+    tab = torch.from_numpy(fd.rfft_tables(n)).cuda()
+    ref = np.fft.rfft(x, axis=1)
+    for pitch_in, pitch_out in ((n, (n + 15) // 16 * 16), (n + 3, n + 5)):
+        src = torch.zeros((rows, pitch_in), dtype=torch.float64, device="cuda")
+        src[:, :n] = torch.from_numpy(x).cuda()
+        dst = torch.full((rows, pitch_out), np.nan, dtype=torch.float64, device="cuda")
+        _lib.call("axb_rfft_rows", rows, n, ptr(src), pitch_in, ptr(dst), pitch_out, pitch_out, ptr(tab), 1.0, stream_ptr())
+        h = dst.cpu().numpy()
+        scale = np.abs(ref).max()
+        assert np.abs(h[:, :M + 1] - ref.real).max() <= 1e-13 * scale
+        assert np.abs(h[:, M + 1:n] - ref.imag[:, 1:M]).max() <= 1e-13 * scale
+        assert np.all(h[:, n:] == 0)
+        back = torch.full((rows, pitch_in), np.nan, dtype=torch.float64, device="cuda")
+        _lib.call("axb_irfft_rows", rows, n, ptr(dst), pitch_out, ptr(back), pitch_in, ptr(tab), 1.0 / M, stream_ptr())
+        assert np.abs(back[:, :n].cpu().numpy() - x).max() <= 1e-13
+    assert _lib.call("axb_rfft_supported", 2 * 73) == 0 and _lib.call("axb_rfft_supported", 33) == 0
+    with pytest.raises(_lib.AxbError):
+        _lib.call("axb_rfft_rows", rows, 2 * 73, ptr(src), 2 * 73, ptr(dst), 2 * 73, 0, ptr(tab), 1.0, stream_ptr())
+
+
+@pytest.mark.parametrize("nr,nz", [(24, 56), (96, 252), (64, 1020), (50, 4092)])
+def test_fast_diagonalisation_periodic_fft(K, nr, nz):
+    """periodic z through real FFT rows + factored tridiagonal sweeps (what the 1024 x 4096 periodic configuration
+    runs) against the reference's eigen-decomposition: the golden output at the golden's size, the oracle elsewhere;
+    strided right-hand side / solution views like periodic_flow_past_sphere.py:100-104"""
+    import torch
+
+    from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
+
+    bc = "homogenous_neumann_along_r_and_periodic_along_z"
+    if (nr, nz) == (24, 56):
+        g = golden("fast_diag")
+        rhs, dx, ref = g["rhs"], float(g["dx"]), g["stokes_" + bc]
+    else:
+        dx = 1.0 / nz
+        rhs = np.random.default_rng(3).standard_normal((nr, nz))
+        ref = np.zeros_like(rhs)
+        ox.FastDiagonalisationOracle(nr, nz, dx, "stokes", bc).solve(ref, rhs)
+    s = FastDiagonalisationStokesSolver(nr, nz, dx, bc_type=bc, basis="analytic", r_method="tridiagonal", z_method="fft")
+    assert "rfft" in s.kernel_note()
+    sol = np.zeros_like(rhs)
+    s.solve(sol, rhs)
+    assert_close(sol, ref, 1e-10, "periodic rfft solve")
+    # device views with a pitch (ghost columns either side), in place on the solution view
+    wide = torch.zeros((nr, nz + 4), dtype=torch.float64, device="cuda")
+    wide[:, 2:-2] = torch.from_numpy(rhs).cuda()
+    out = torch.zeros_like(wide)
+    s.solve(out[:, 2:-2], wide[:, 2:-2])
+    assert_close(out[:, 2:-2].cpu().numpy(), ref, 1e-10, "periodic rfft solve, strided views")
+    assert torch.all(out[:, :2] == 0) and torch.all(out[:, -2:] == 0)
+
+
 @pytest.mark.parametrize("nr,nz", [(33, 12288), (21, 6144), (19, 96)])
 def test_factored_tridiagonal_column_blocks(K, nr, nz):
     """the 128-, 64- and 32-column variants of the streamed sweeps"""
@@ -916,6 +983,7 @@ def test_headline_size_solve_and_step(K, stencil_path):
         _lib.call("axb_set_stencil_path", path)
         st = RigidFlowStepper(nz, grid_size_r=nr, use_graph=False)
         assert (st.nr, st.nz) == (nr, nz)
+        st.seed_vorticity()                 # seeded band-limited blob: psi and u are non-trivial from the first step
         st.step(2)
         torch.cuda.synchronize()
         outs[path] = (st.vorticity.clone(), st.psi.clone(), st.u_z.clone(), st.u_r.clone(), st.scalars())

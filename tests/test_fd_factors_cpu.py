@@ -140,8 +140,11 @@ def test_fft_factors_solve_the_operator():
                             z_method="auto")["zfft"] is None
     with pytest.raises(ValueError):
         fd.build_factors("stokes", BCS[0], nr, nz, dx, "analytic", z_method="fft")      # needs the direct r solve
+    # periodic z now has its own FFT path (real FFT rows, csrc/pfft.cu); sizes with a large prime factor do not
+    assert fd.build_factors("stokes", BCS[1], nr, nz, dx, "analytic", r_method="tridiagonal",
+                            z_method="fft")["zfft"]["family"] == "periodic"
     with pytest.raises(ValueError):
-        fd.build_factors("stokes", BCS[1], nr, nz, dx, "analytic", r_method="tridiagonal", z_method="fft")
+        fd.build_factors("stokes", BCS[1], nr, 2 * 73, dx, "analytic", r_method="tridiagonal", z_method="fft")
 
 
 def test_periodic_fourstep_model():
@@ -159,3 +162,44 @@ def test_periodic_fourstep_model():
         assert ef <= 1e-13 and eb <= 1e-13, (n, ef, eb)
     assert (fs.n1, fs.n2) == (62, 66)
     assert pm._check_solve(6, 60) <= 1e-12
+
+
+def test_periodic_rfft_model():
+    """tools/rfft_model.py restates the index arithmetic of csrc/pfft.cu (Stockham passes with generic radices from
+    one table of M-th roots, real-FFT untangling, half-complex layout); it must agree with numpy.fft."""
+    import sys
+
+    sys.path.insert(0, "tools")
+    import rfft_model as rm
+
+    rng = np.random.default_rng(0)
+    for n in (4092, 252, 60, 8, 1020, 52, 4096, 16380 // 4 * 2):
+        f = rm.factorize(n // 2)
+        assert f == fd.rfft_factors(n // 2)
+        tm, tn = rm.tables(n)
+        tab = fd.rfft_tables(n)
+        assert np.allclose(tab[:n // 2, 0] + 1j * tab[:n // 2, 1], tm, atol=1e-15)
+        assert np.allclose(tab[n // 2:, 0] + 1j * tab[n // 2:, 1], tn, atol=1e-15)
+        x = rng.standard_normal(n)
+        h = rm.rfft_row(x, f, tm, tn)
+        ref = np.fft.rfft(x)
+        m = n // 2
+        assert np.abs(h[:m + 1] - ref.real).max() <= 1e-13 * np.abs(ref).max()
+        assert np.abs(h[m + 1:] - ref.imag[1:m]).max() <= 1e-13 * np.abs(ref).max()
+        assert np.abs(rm.irfft_row(h, f, tm, tn) - x).max() <= 1e-13
+        assert np.array_equal(rm.mode_of_column(n)[:m + 1], np.arange(m + 1))
+    assert fd.rfft_factors(2044 // 2) is None and not fd.rfft_supported(2044)      # 511 = 7 * 73
+    assert fd.rfft_supported(4092) and fd.rfft_spectral_width(4092) == 4096
+
+
+def test_periodic_fft_factor_set_matches_reference():
+    """periodic z through real FFT rows + the tridiagonal r solve: same solution as the reference's eigen-decomposition
+    (golden outputs of FastDiagonalisationStokesSolver with the periodic bc, full and inner grid)"""
+    g = golden("fast_diag")
+    rhs, dx = g["rhs"], float(g["dx"])
+    nr, nz = rhs.shape
+    f = fd.build_factors("stokes", BCS[1], nr, nz, dx, "analytic", r_method="tridiagonal", z_method="fft")
+    assert f["zfft"]["family"] == "periodic" and f["lam_z"].shape[0] == f["zfft"]["nz_spec"] == 64
+    assert_close(fd.apply_factors_host(f, rhs), g["stokes_" + BCS[1]], 1e-10, "periodic rfft path")
+    f = fd.build_factors("stokes", BCS[1], nr, nz - 4, dx, "analytic", r_method="tridiagonal", z_method="fft")
+    assert_close(fd.apply_factors_host(f, rhs[:, 2:-2]), g["stokes_periodic_inner"], 1e-10, "inner grid")
