@@ -32,41 +32,79 @@ __device__ __forceinline__ double2 cmulf(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// all passes of the length-M complex FFT; data starts in `a`, returns the buffer holding the result
-__device__ __forceinline__ double2* pfft_passes(double2* a, double2* b, const double2* __restrict__ tab, int M,
-                                               const PfftFactors& F) {
-  int ns = 1;
+// all passes of the length-M complex FFT; data starts in `a`, returns the buffer holding the result.
+// A work item is (butterfly j, group of PG outputs u0 .. u0+PG-1): every input of the butterfly is read once per
+// item and multiplied by its pass twiddle (global table, L1 resident) once, then feeds PG accumulators with the
+// R-point DFT weights W_R^(u t) = wt[t R + u], an R x R table per pass built once per CTA, read at the same
+// address by all lanes of a warp (items of a warp share the output group) with immediate offsets -- no index
+// arithmetic in the inner loop.
+constexpr int PG = 4;
+constexpr int PB = 512;          // threads per CTA
+__device__ __forceinline__ void pfft_build_weights(double2* wt, const double2* __restrict__ tabM, int M, const PfftFactors& F) {
+  int off = 0;
+  for (int p = 0; p < F.n; ++p) {
+    const int R = F.r[p], L = M / R;
+    for (int i = threadIdx.x; i < R * R; i += blockDim.x) {
+      const int t = i / R, u = i - t * R;
+      wt[off + i] = tabM[((u * t) % R) * L];
+    }
+    off += R * R;
+  }
+}
+__device__ __forceinline__ double2* pfft_passes(double2* a, double2* b, const double2* __restrict__ tabM,
+                                               const double2* __restrict__ wt, int M, const PfftFactors& F) {
+  int ns = 1, off = 0;
   for (int p = 0; p < F.n; ++p) {
     const int R = F.r[p];
     const int L = M / R;
     const int step_j = M / (ns * R);              // table stride of the pass twiddle per unit of jm
-    for (int q = threadIdx.x; q < M; q += blockDim.x) {
-      const int jm = q % ns;
-      const int t1 = q / ns;
-      const int u = t1 % R;
-      const int j = (t1 / R) * ns + jm;
-      int e = (int)(((long long)jm * step_j + (long long)u * L) % M);
-      double2 acc = a[j];                          // t = 0: twiddle 1
-      int idx = e;
+    const int NG = (R + PG - 1) / PG;
+    for (int w = threadIdx.x; w < L * NG; w += blockDim.x) {
+      const int ug = w / L;
+      const int j = w - ug * L;
+      const int u0 = ug * PG;
+      const int nv = min(PG, R - u0);
+      const int jm = j % ns;
+      const int dtw = jm * step_j;
+      const double2 v0 = a[j];
+      double2 acc[PG];
+#pragma unroll
+      for (int g = 0; g < PG; ++g) acc[g] = v0;
+      int ktw = 0;
+      const double2* wrow = wt + off + u0;
+#pragma unroll 2
       for (int t = 1; t < R; ++t) {
-        const double2 v = a[j + t * L];
-        const double2 w = tab[idx];
-        acc.x += v.x * w.x - v.y * w.y;
-        acc.y += v.x * w.y + v.y * w.x;
-        idx += e;
-        if (idx >= M) idx -= M;
+        double2 v = a[j + t * L];
+        if (ns > 1) {
+          ktw += dtw;
+          if (ktw >= M) ktw -= M;
+          v = cmulf(v, __ldg(&tabM[ktw]));
+        }
+        wrow += R;
+#pragma unroll
+        for (int g = 0; g < PG; ++g) {
+          if (g < nv) {
+            const double2 c = wrow[g];
+            acc[g].x += v.x * c.x - v.y * c.y;
+            acc[g].y += v.x * c.y + v.y * c.x;
+          }
+        }
       }
-      b[q] = acc;
+      const int base = (j - jm) * R + jm;
+#pragma unroll
+      for (int g = 0; g < PG; ++g)
+        if (g < nv) b[base + (u0 + g) * ns] = acc[g];
     }
     __syncthreads();
     double2* t = a; a = b; b = t;
     ns *= R;
+    off += R * R;
   }
   return a;
 }
 
 // forward: rows of N reals -> half-complex rows (pitch ld_dst >= N, tail zero-filled up to `pad_to`)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PB, 2)
     k_rfft_rows(int rows, int N, PfftFactors F, const double* __restrict__ src, long long ld_src, double* __restrict__ dst,
                 long long ld_dst, int pad_to, const double2* __restrict__ tabM, const double2* __restrict__ tabN, double scale,
                 int vec) {
@@ -74,8 +112,8 @@ __global__ void __launch_bounds__(256)
   const int M = N >> 1;
   double2* a = reinterpret_cast<double2*>(pf_smem);
   double2* b = a + M;
-  double2* tab = b + M;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = tabM[i];
+  double2* wt = b + M;
+  pfft_build_weights(wt, tabM, M, F);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const double* x = src + (long long)row * ld_src;
     if (vec) {
@@ -85,7 +123,7 @@ __global__ void __launch_bounds__(256)
       for (int n = threadIdx.x; n < M; n += blockDim.x) a[n] = make_double2(x[2 * n], x[2 * n + 1]);
     }
     __syncthreads();
-    const double2* Z = pfft_passes(a, b, tab, M, F);
+    const double2* Z = pfft_passes(a, b, tabM, wt, M, F);
     double* X = dst + (long long)row * ld_dst;
     for (int k = threadIdx.x; k <= M; k += blockDim.x) {
       const double2 zk = Z[k == M ? 0 : k];
@@ -105,15 +143,15 @@ __global__ void __launch_bounds__(256)
 }
 
 // inverse: half-complex rows -> rows of N reals, times `scale` (the caller folds 1/M = 2/N in)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PB, 2)
     k_irfft_rows(int rows, int N, PfftFactors F, const double* __restrict__ src, long long ld_src, double* __restrict__ dst,
                  long long ld_dst, const double2* __restrict__ tabM, const double2* __restrict__ tabN, double scale, int vec) {
   extern __shared__ __align__(16) unsigned char pf_smem[];
   const int M = N >> 1;
   double2* a = reinterpret_cast<double2*>(pf_smem);
   double2* b = a + M;
-  double2* tab = b + M;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) tab[i] = tabM[i];
+  double2* wt = b + M;
+  pfft_build_weights(wt, tabM, M, F);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const double* h = src + (long long)row * ld_src;
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
@@ -129,7 +167,7 @@ __global__ void __launch_bounds__(256)
       a[k] = make_double2(E.x - O.y, -(E.y + O.x));
     }
     __syncthreads();
-    const double2* z = pfft_passes(a, b, tab, M, F);
+    const double2* z = pfft_passes(a, b, tabM, wt, M, F);
     double* x = dst + (long long)row * ld_dst;
     if (vec) {
       double2* x2 = reinterpret_cast<double2*>(x);
@@ -159,6 +197,12 @@ bool pfft_factorize(int M, PfftFactors* F) {
     }
   return m == 1 && M >= 2;
 }
+// shared memory: two row buffers + the R x R weight tables of all passes
+size_t pfft_smem_bytes(int M, const PfftFactors& F) {
+  size_t w = 0;
+  for (int p = 0; p < F.n; ++p) w += (size_t)F.r[p] * F.r[p];
+  return ((size_t)2 * M + w) * sizeof(double2);
+}
 
 }  // namespace
 
@@ -169,7 +213,7 @@ int launch_rfft_rows(int inverse, int rows, int N, const double* src, long long 
   const int M = N / 2;
   PfftFactors F;
   if (!pfft_factorize(M, &F)) return AXB_ENOSUP;
-  const size_t smem = (size_t)3 * M * sizeof(double2);
+  const size_t smem = pfft_smem_bytes(M, F);
   if (smem > 200 * 1024) return AXB_ENOSUP;
   static int sms = 0;
   if (!sms) {
@@ -180,17 +224,17 @@ int launch_rfft_rows(int inverse, int rows, int N, const double* src, long long 
     cudaFuncSetAttribute(k_irfft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   int resident = (int)((227u * 1024u) / (smem + 1024));
-  if (resident > 8) resident = 8;
+  if (resident > 2) resident = 2;             // 512 threads x <= 64 registers: two CTAs per SM
   if (resident < 1) resident = 1;
   const int grid = rows < sms * resident ? rows : sms * resident;
   const double2* tabM = reinterpret_cast<const double2*>(tables);
   const double2* tabN = tabM + M;
   const int vec = (axb_al16(src) && axb_al16(dst) && (ld_src % 2 == 0) && (ld_dst % 2 == 0)) ? 1 : 0;
   if (!inverse)
-    k_rfft_rows<<<grid, 256, smem, st>>>(rows, N, F, src, ld_src, dst, ld_dst, pad_to < N ? N : pad_to, tabM, tabN, scale,
+    k_rfft_rows<<<grid, PB, smem, st>>>(rows, N, F, src, ld_src, dst, ld_dst, pad_to < N ? N : pad_to, tabM, tabN, scale,
                                          vec);
   else
-    k_irfft_rows<<<grid, 256, smem, st>>>(rows, N, F, src, ld_src, dst, ld_dst, tabM, tabN, scale, vec);
+    k_irfft_rows<<<grid, PB, smem, st>>>(rows, N, F, src, ld_src, dst, ld_dst, tabM, tabN, scale, vec);
   AXB_LAUNCHED();
   return (int)cudaGetLastError();
 }
@@ -208,7 +252,7 @@ int axb_irfft_rows(int rows, int n, const double* src, int64_t ld_src, double* d
 }
 int axb_rfft_supported(int n) {
   PfftFactors F;
-  return (n >= 4 && !(n & 1) && pfft_factorize(n / 2, &F) && (size_t)3 * (n / 2) * sizeof(double2) <= 200 * 1024) ? 1 : 0;
+  return (n >= 4 && !(n & 1) && pfft_factorize(n / 2, &F) && pfft_smem_bytes(n / 2, F) <= 200 * 1024) ? 1 : 0;
 }
 
 }  // extern "C"

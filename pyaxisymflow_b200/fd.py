@@ -309,8 +309,12 @@ def rfft_factors(m, max_radix=64):
 
 
 def rfft_supported(nz):
-    """periodic z: even nz whose half length has small prime factors only and fits shared memory (csrc/pfft.cu)"""
-    return nz >= 4 and nz % 2 == 0 and rfft_factors(nz // 2) is not None and 3 * (nz // 2) * 16 <= 200 * 1024
+    """periodic z: even nz whose half length has small prime factors only and fits shared memory (csrc/pfft.cu:
+    two row buffers + the R x R weight tables of all passes)"""
+    if nz < 4 or nz % 2:
+        return False
+    f = rfft_factors(nz // 2)
+    return f is not None and (2 * (nz // 2) + sum(r * r for r in f)) * 16 <= 200 * 1024
 
 
 def fft_eligible(family, nz):

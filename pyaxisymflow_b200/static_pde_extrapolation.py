@@ -46,7 +46,7 @@ class StaticPDEExtrapolation:
         self._find_bounding_box(t_phi)
         box = (slice(self.r_start, self.r_end), slice(self.z_start, self.z_end))
         phi_b = (-t_phi[box]).contiguous()
-        eta_b = t_eta[box].contiguous()
+        eta_b = t_eta[box].clone(memory_format=torch.contiguous_format)   # a copy even when the box spans whole rows
         n0, n1 = phi_b.shape
         ni = (n0 - 4, n1 - 4)
         nrp, nrn, nzp, nzn, den = (torch.empty(ni, dtype=torch.float64, device="cuda") for _ in range(5))

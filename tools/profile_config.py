@@ -5,11 +5,19 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pyaxisymflow_b200.timestep import ParticleFlowStepper, SoftSphereStepper  # noqa: E402
+from pyaxisymflow_b200.timestep import ParticleFlowStepper, RigidFlowStepper, SoftSphereStepper  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-if which == "c3":
+if which == "c2":
+    s = RigidFlowStepper(4096, grid_size_r=1024, periodic=True, r_sph=0.075, Z_cm=0.85)
+    s.seed_vorticity()
+    s.t = 0.0
+elif which == "c4":
+    s = RigidFlowStepper(16384, grid_size_r=4096)
+    s.seed_vorticity()
+    s.t = 0.0
+elif which == "c3":
     s = SoftSphereStepper(8192, grid_size_r=2048, Z_cm=0.47, reinit_levelset=True)
 else:
     s = ParticleFlowStepper(2048, grid_size_r=1024)
