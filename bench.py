@@ -62,7 +62,8 @@ WORKLOADS = {
 def config_dict(name, nr, nz, world, cases_per_gpu, reinit=False):
     """the `config` object -- built by this one function for both arms, so the two lines describe the same job"""
     flush = needs_flush(name, nr, nz)
-    par = "single GPU" if world == 1 else (f"z-slab x{world}" if name == "c4" else f"{world} independent replicas")
+    slab = "z-slab" if os.environ.get("AXB_SLAB_Z") else "r-slab"
+    par = "single GPU" if world == 1 else (f"{slab} x{world}" if name == "c4" else f"{world} independent replicas")
     wl = WORKLOADS[name].format(nr=nr, nz=nz, cases=cases_per_gpu)
     if name == "c3":
         wl += ("; narrow-band level-set re-initialisation included" if reinit
@@ -499,9 +500,14 @@ def make_stepper(name, nr, nz, args, world):
         return st
     if name == "c4":
         if world > 1:
-            from pyaxisymflow_b200.slab import SlabRigidFlowStepper
+            if os.environ.get("AXB_SLAB_Z"):         # the z-slab flow (two transposes per solve), for comparison
+                from pyaxisymflow_b200.slab import SlabRigidFlowStepper
 
-            st = SlabRigidFlowStepper(nz, grid_size_r=nr, r_method=args.r_method, z_method=args.z_method)
+                st = SlabRigidFlowStepper(nz, grid_size_r=nr, r_method=args.r_method, z_method=args.z_method)
+            else:                                    # rows split over the ranks: no transposes
+                from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper
+
+                st = RowSlabRigidFlowStepper(nz, grid_size_r=nr)
         else:
             st = RigidFlowStepper(nz, grid_size_r=nr, r_method=args.r_method, z_method=args.z_method,
                                   use_graph=not args.no_graph)
@@ -669,12 +675,15 @@ def e2e_generic(runner, nr, nz, steps, torch):
 
 
 def slab_vs_single(world, rank, dist, torch, nz=2048, steps=4):
-    """correctness of the multi-GPU path, outside the timed region: the z-slab stepper against the single-GPU
+    """correctness of the multi-GPU path, outside the timed region: the slab stepper against the single-GPU
     stepper on a reduced grid (nz/4 x nz), relative L-infinity of the vorticity after `steps` steps"""
-    from pyaxisymflow_b200.slab import SlabRigidFlowStepper
     from pyaxisymflow_b200.timestep import RigidFlowStepper
 
-    s = SlabRigidFlowStepper(nz, grid_size_r=nz // 4)
+    if os.environ.get("AXB_SLAB_Z"):
+        from pyaxisymflow_b200.slab import SlabRigidFlowStepper as Stepper
+    else:
+        from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper as Stepper
+    s = Stepper(nz, grid_size_r=nz // 4)
     s.seed_vorticity()
     s.step(steps)
     w = s.gather_vorticity()
@@ -742,11 +751,12 @@ def run_gpu_arm(args, name, nr, nz):
         else:
             e2e = e2e_generic(stepper, nr, nz, args.steps, torch)
     elif name == "c4":
-        # every rank stages its own z-slab through its own PCIe link (serial per call: copy in, step, copy out)
+        # every rank stages its own slab through its own PCIe link (serial per call: copy in, step, copy out)
         L = stepper.L
-        hw = torch.empty((nr, L.nzl), dtype=torch.float64).pin_memory()
-        hc = torch.empty((nr, L.nzl), dtype=torch.float64).pin_memory()
-        ho = torch.empty((nr, L.nzl), dtype=torch.float64).pin_memory()
+        own = tuple(L.owned(stepper.vorticity).shape)        # (nr, nz/P) columns or (nr/P, nz) rows
+        hw = torch.empty(own, dtype=torch.float64).pin_memory()
+        hc = torch.empty(own, dtype=torch.float64).pin_memory()
+        ho = torch.empty(own, dtype=torch.float64).pin_memory()
         hw.copy_(L.owned(stepper.vorticity))
         hc.copy_(L.owned(stepper.char_func))
         stepper.step_host(hw, hc, ho)
@@ -765,7 +775,7 @@ def run_gpu_arm(args, name, nr, nz):
         e2e_ms = t.item()
         e2e = {"value": nr * nz / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * nr * nz * 8,
                "d2h_bytes_per_step": nr * nz * 8, "ms_per_step": e2e_ms,
-               "mode": f"step_host on every rank: each of the {world} ranks stages its own z-slab (pinned host "
+               "mode": f"step_host on every rank: each of the {world} ranks stages its own slab (pinned host "
                        "buffers) over its own PCIe link, serial per call"}
         del hw, hc, ho
 

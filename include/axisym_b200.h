@@ -38,7 +38,10 @@ typedef struct CUstream_st* axb_stream_t;
 /* Shape + z-slab placement of one (nr, nz) field.  Single GPU: kz0 = 0, nz_global = nz,
  * ku0 = 0, ku1 = nz.  Under z-slab decomposition `nz` counts the locally STORED columns
  * (owned + halos), `kz0` is the global z index of local column 0 (negative on the first
- * rank's left halo), and [ku0, ku1) is the locally owned range the kernel may write. */
+ * rank's left halo), and [ku0, ku1) is the locally owned range the kernel may write.
+ * Under r-slab (row) decomposition every rank's (owned + halo rows, nz) block is an ordinary field for the
+ * kernels (r1d holds the block's own radii); [ju0, ju1) are the OWNED rows, the only ones that count in the
+ * fused reductions (CFL maximum, drag sum).  ju1 == 0 means all rows (single GPU, z-slabs). */
 typedef struct axb_grid {
   int32_t nr;
   int32_t nz;
@@ -48,6 +51,8 @@ typedef struct axb_grid {
   int32_t nz_global;
   int32_t ku0;
   int32_t ku1;
+  int32_t ju0;
+  int32_t ju1;
 } axb_grid_t;
 
 int axb_version(void);
@@ -65,6 +70,10 @@ int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const dou
                                        axb_stream_t s);
 int axb_kill_boundary_vorticity_sine_r(const axb_grid_t* g, double* w, const double* r1d, int width,
                                        axb_stream_t s);
+/* the two halves of kill_boundary_vorticity_sine_r for r-slabs: parts bit 0 = the sine ramp over the last
+ * `width` rows (the rank that holds r_max), bit 1 = row 0 := 0 (the rank that holds the axis) */
+int axb_kill_boundary_vorticity_sine_r_parts(const axb_grid_t* g, double* w, const double* r1d, int width,
+                                             int parts, axb_stream_t s);
 
 /* ---- a12: kernels/periodic_boundary_ghost_comm.py:4-15 (z_max = two_g_dx = 0) and the
  *      reference-map form :18-33: left ghosts = (src - z_max) + two_g_dx,
@@ -452,6 +461,19 @@ int axb_halo_unpack(const axb_grid_t* g, double* f, const double* buf_left, cons
  * ranks before the halos are read. */
 int axb_halo_put(const axb_grid_t* g, const double* f, double* left_peer_field, double* right_peer_field, int width,
                  double shift, axb_stream_t s);
+/* r-slab (row) decomposition: every rank stores (halo + nrl + halo) rows of pitch ld per field.  For up to 8 fields
+ * at once (src[i] = this rank's block, lower_peer[i] / upper_peer[i] = the same field's block on rank-1 / rank+1
+ * mapped into this process, 0 = no neighbour) the first `width` owned rows go into the lower neighbour's upper halo
+ * rows and the last `width` owned rows into the upper neighbour's lower halo rows.  The pointer arrays are HOST
+ * arrays.  The caller synchronises the ranks before the halos are read. */
+int axb_row_halo_put(int nfields, const uint64_t* src, const uint64_t* lower_peer, const uint64_t* upper_peer, int64_t ld,
+                     int nz, int nrl, int halo, int width, axb_stream_t s);
+/* the pull form: this rank's halo rows are READ from the neighbours' owned edge rows.  The kernels of a step write
+ * their own block's halo rows too (with values nobody uses), so with the pull form ONE rank barrier BEFORE the call
+ * orders everything: the neighbour has finished producing its rows, and this rank's own stray halo writes are
+ * stream-ordered before the pull (pyaxisymflow_b200/rowslab.py). */
+int axb_row_halo_get(int nfields, const uint64_t* mine, const uint64_t* lower_peer, const uint64_t* upper_peer, int64_t ld,
+                     int nz, int nrl, int halo, int width, axb_stream_t s);
 /* local (nr x nz_local) slab  <->  P blocks of (nr/P x nz_local) for the all-to-all transpose */
 int axb_slab_to_blocks(int nr, int nzl, int64_t ld, int P, const double* slab, double* blocks,
                        axb_stream_t s);

@@ -20,7 +20,8 @@ class AxbError(RuntimeError):
 
 class AxbGrid(Structure):
     _fields_ = [("nr", c_int32), ("nz", c_int32), ("ld", c_int64), ("dx", c_double),
-                ("kz0", c_int32), ("nz_global", c_int32), ("ku0", c_int32), ("ku1", c_int32)]
+                ("kz0", c_int32), ("nz_global", c_int32), ("ku0", c_int32), ("ku1", c_int32),
+                ("ju0", c_int32), ("ju1", c_int32)]
 
 
 class AxbFdPlan(Structure):
@@ -51,6 +52,7 @@ _SIGNATURES = {
     "axb_set_solid_march": [_I],
     "axb_kill_boundary_vorticity_sine_z": [_G, _P, _P, _I, _S],
     "axb_kill_boundary_vorticity_sine_r": [_G, _P, _P, _I, _S],
+    "axb_kill_boundary_vorticity_sine_r_parts": [_G, _P, _P, _I, _I, _S],
     "axb_periodic_ghost_comm": [_G, _P, _I, _D, _D, _S],
     "axb_velocity_from_psi": [_G, _P, _P, _P, _P, _D, _D, _P, _P, _S],
     "axb_brinkmann_penalize": [_G, _D, _D, _P, _D, _D, _P, _P, _P, _P, _P, _P, _S],
@@ -117,6 +119,8 @@ _SIGNATURES = {
     "axb_slab_to_blocks": [_I, _I, c_int64, _I, _P, _P, _S],
     "axb_blocks_to_rows": [_I, _I, _I, _P, _P, c_int64, _S],
     "axb_halo_put": [_G, _P, _P, _P, _I, _D, _S],
+    "axb_row_halo_put": [_I, _P, _P, _P, c_int64, _I, _I, _I, _I, _S],
+    "axb_row_halo_get": [_I, _P, _P, _P, c_int64, _I, _I, _I, _I, _S],
     "axb_peer_block_put": [_I, _I, _P, c_int64, c_int64, _P, c_int64, c_int64, _I, _I, _S],
     "axb_rows_to_blocks": [_I, _I, _I, _P, c_int64, _P, _S],
     "axb_blocks_to_slab": [_I, _I, c_int64, _I, _P, _P, _S],

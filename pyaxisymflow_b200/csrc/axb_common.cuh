@@ -23,6 +23,7 @@ static inline int axb_check_grid(const axb_grid_t* g) {
   if (g->nr < 1 || g->nz < 1 || g->ld < g->nz) return AXB_EINVAL;
   if (g->ku0 < 0 || g->ku1 > g->nz || g->ku0 > g->ku1) return AXB_EINVAL;
   if (g->nz_global < 1) return AXB_EINVAL;
+  if (g->ju1 != 0 && (g->ju0 < 0 || g->ju1 > g->nr || g->ju0 > g->ju1)) return AXB_EINVAL;
   return AXB_OK;
 }
 static inline bool axb_al8(const void* p) { return (((uintptr_t)p) & 7u) == 0; }
@@ -34,11 +35,13 @@ struct GridD {
   long long ld;
   double dx;
   int kz0, nzg, ku0, ku1;
+  int ju0, ju1;      // owned rows: the ones fused reductions count
 };
 static inline GridD to_dev(const axb_grid_t* g) {
   GridD d;
   d.nr = g->nr; d.nz = g->nz; d.ld = g->ld; d.dx = g->dx;
   d.kz0 = g->kz0; d.nzg = g->nz_global; d.ku0 = g->ku0; d.ku1 = g->ku1;
+  d.ju0 = g->ju1 ? g->ju0 : 0; d.ju1 = g->ju1 ? g->ju1 : g->nr;
   return d;
 }
 

@@ -94,7 +94,75 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- r-slab (row) halos over peer memory: the first / last `w` owned rows of up to 8 fields go straight into the
+// upper halo rows of the lower neighbour / the lower halo rows of the upper neighbour.  Every rank stores its block
+// as (halo + nrl + halo) rows of pitch ld, so the rows are contiguous runs on both sides.
+struct RowHaloFields {
+  const double* src[8];
+  double* lower[8];
+  double* upper[8];
+};
+template <bool GET>
+__global__ void __launch_bounds__(256)
+    k_row_halo_put(RowHaloFields f, long long ld, int nz, int nrl, int halo, int w, bool vec) {
+  const int fi = blockIdx.z, up = blockIdx.y;
+  double* peer = up ? f.upper[fi] : f.lower[fi];
+  if (!peer) return;
+  double* mine = const_cast<double*>(f.src[fi]);
+  // put: my edge rows -> the neighbour's halo rows;  get: the neighbour's edge rows -> my halo rows
+  const double* s = GET ? peer + (long long)(up ? halo : halo + nrl - w) * ld
+                        : mine + (long long)(up ? halo + nrl - w : halo) * ld;
+  double* d = GET ? mine + (long long)(up ? halo + nrl : halo - w) * ld
+                  : peer + (long long)(up ? halo - w : halo + nrl) * ld;
+  const int per_row = (nz + 1) / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * per_row; i += gridDim.x * blockDim.x) {
+    const int r = i / per_row, c = 2 * (i - r * per_row);
+    const long long o = (long long)r * ld + c;
+    if (vec && c + 1 < nz) {
+      *reinterpret_cast<double2*>(d + o) = *reinterpret_cast<const double2*>(s + o);
+    } else {
+      d[o] = s[o];
+      if (c + 1 < nz) d[o + 1] = s[o + 1];
+    }
+  }
+}
+
 extern "C" {
+
+static int row_halo(bool get, int nfields, const uint64_t* src, const uint64_t* lower_peer, const uint64_t* upper_peer,
+                    int64_t ld, int nz, int nrl, int halo, int width, axb_stream_t s) {
+  if (nfields < 1 || nfields > 8 || !src || !lower_peer || !upper_peer || nz < 1 || ld < nz || width < 1 || width > halo ||
+      nrl < width)
+    return AXB_EINVAL;
+  RowHaloFields f;
+  bool vec = (ld % 2 == 0), any = false;
+  for (int i = 0; i < 8; ++i) {
+    f.src[i] = nullptr; f.lower[i] = nullptr; f.upper[i] = nullptr;
+    if (i >= nfields) continue;
+    f.src[i] = reinterpret_cast<const double*>(src[i]);
+    f.lower[i] = reinterpret_cast<double*>(lower_peer[i]);
+    f.upper[i] = reinterpret_cast<double*>(upper_peer[i]);
+    if (!f.src[i]) return AXB_EINVAL;
+    vec = vec && axb_al16(f.src[i]) && axb_al16(f.lower[i]) && axb_al16(f.upper[i]);
+    any = any || f.lower[i] || f.upper[i];
+  }
+  if (!any) return AXB_OK;
+  const int work = width * ((nz + 1) / 2);
+  int bx = (work + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (get) k_row_halo_put<true><<<dim3(bx, 2, nfields), 256, 0, (cudaStream_t)s>>>(f, ld, nz, nrl, halo, width, vec);
+  else k_row_halo_put<false><<<dim3(bx, 2, nfields), 256, 0, (cudaStream_t)s>>>(f, ld, nz, nrl, halo, width, vec);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+int axb_row_halo_put(int nfields, const uint64_t* src, const uint64_t* lower_peer, const uint64_t* upper_peer, int64_t ld,
+                     int nz, int nrl, int halo, int width, axb_stream_t s) {
+  return row_halo(false, nfields, src, lower_peer, upper_peer, ld, nz, nrl, halo, width, s);
+}
+int axb_row_halo_get(int nfields, const uint64_t* mine, const uint64_t* lower_peer, const uint64_t* upper_peer, int64_t ld,
+                     int nz, int nrl, int halo, int width, axb_stream_t s) {
+  return row_halo(true, nfields, mine, lower_peer, upper_peer, ld, nz, nrl, halo, width, s);
+}
 
 int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
                   axb_stream_t s) {

@@ -56,16 +56,18 @@ __global__ void k_kill_z(GridD g, double* __restrict__ w, const double* __restri
   }
 }
 
-__global__ void k_kill_r(GridD g, double* __restrict__ w, const double* __restrict__ r1d, int width) {
+__global__ void k_kill_r(GridD g, double* __restrict__ w, const double* __restrict__ r1d, int width, int parts) {
   const int k = g.ku0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= g.ku1) return;
-  const double den = (double)(width - 1);
-  const double src = rowp(w, g.ld, g.nr - width)[k];
-  for (int j = g.nr - width; j < g.nr; ++j) {
-    const double ramp = sin(CUDART_PI * (1 - r1d[j] - 0.5 * g.dx) / 2 / den / g.dx);
-    rowp(w, g.ld, j)[k] = ramp * src;
+  if (parts & 1) {
+    const double den = (double)(width - 1);
+    const double src = rowp(w, g.ld, g.nr - width)[k];
+    for (int j = g.nr - width; j < g.nr; ++j) {
+      const double ramp = sin(CUDART_PI * (1 - r1d[j] - 0.5 * g.dx) / 2 / den / g.dx);
+      rowp(w, g.ld, j)[k] = ramp * src;
+    }
   }
-  rowp(w, g.ld, 0)[k] = 0.0;
+  if (parts & 2) rowp(w, g.ld, 0)[k] = 0.0;
 }
 
 // -------------------------------------------------------------------------------------
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(TBX* TBY)
     ur.x += ur_add; ur.y += ur_add;
     st_pair(rowp(u_z, g.ld, j), k, g.ku0, g.ku1, vec, uz);
     st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, ur);
-    if (REDUCE) {
+    if (REDUCE && j >= g.ju0 && j < g.ju1) {
       if (k >= g.ku0 && k < g.ku1) local_max = fmax(local_max, fabs(uz.x) + fabs(ur.x));
       if (k + 1 >= g.ku0 && k + 1 < g.ku1) local_max = fmax(local_max, fabs(uz.y) + fabs(ur.y));
     }
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(TBX* TBY)
     const double2 pr = make_double2(pen1(r0.x, lamdt, c0.x, U_r), pen1(r0.y, lamdt, c0.y, U_r));
     st_pair(rowp(u_z, g.ld, j), k, g.ku0, g.ku1, vec, pz);
     st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, pr);
-    if (REDUCE) {
+    if (REDUCE && j >= g.ju0 && j < g.ju1) {
       const double r = r1d[j];
       if (k >= g.ku0 && k < g.ku1) local += r * c0.x * (pz.x - U_z);
       if (k + 1 >= g.ku0 && k + 1 < g.ku1) local += r * c0.y * (pz.y - U_z);
@@ -514,16 +516,20 @@ int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const dou
   AXB_RETURN_LAST();
 }
 
-int axb_kill_boundary_vorticity_sine_r(const axb_grid_t* g, double* w, const double* r1d, int width,
-                                       axb_stream_t s) {
-  if (!w || !r1d || width < 2) return AXB_EINVAL;
+int axb_kill_boundary_vorticity_sine_r_parts(const axb_grid_t* g, double* w, const double* r1d, int width,
+                                             int parts, axb_stream_t s) {
+  if (!w || !r1d || width < 2 || parts < 0 || parts > 3) return AXB_EINVAL;
   GRID_PROLOGUE(w, r1d)
   if (width > d.nr) return AXB_EINVAL;
   const int n = d.ku1 - d.ku0;
-  if (n <= 0) return AXB_OK;
-  k_kill_r<<<(n + 127) / 128, 128, 0, s>>>(d, w, r1d, width);
+  if (n <= 0 || !parts) return AXB_OK;
+  k_kill_r<<<(n + 127) / 128, 128, 0, s>>>(d, w, r1d, width, parts);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
+}
+int axb_kill_boundary_vorticity_sine_r(const axb_grid_t* g, double* w, const double* r1d, int width,
+                                       axb_stream_t s) {
+  return axb_kill_boundary_vorticity_sine_r_parts(g, w, r1d, width, 3, s);
 }
 
 int axb_periodic_ghost_comm(const axb_grid_t* g, double* f, int ghost, double z_max, double two_g_dx,

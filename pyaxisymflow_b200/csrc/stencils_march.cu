@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(MT)
                 double* umax_out, bool vec) {
   extern __shared__ double s_inv[];
   const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
-  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
+  // a block that straddles the owned-row window [ju0, ju1) reduces row by row on the general path
+  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec) && (!REDUCE || (j0 >= g.ju0 && j1 <= g.ju1));
   if ((PATH == 1) != interior) return;
   for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
   __syncthreads();
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(MT)
       ur.x += ur_add; ur.y += ur_add;
       st_pair(rowp(u_z, g.ld, j), c.ks, g.ku0, g.ku1, vec, uz);
       st_pair(rowp(u_r, g.ld, j), c.ks, g.ku0, g.ku1, vec, ur);
-      if (REDUCE) {
+      if (REDUCE && j >= g.ju0 && j < g.ju1) {
         if (c.own0) local_max = fmax(local_max, fabs(uz.x) + fabs(ur.x));
         if (c.own1) local_max = fmax(local_max, fabs(uz.y) + fabs(ur.y));
       }
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(MT)
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local = 0.0;
-  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
+  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec) && (!REDUCE || (j0 >= g.ju0 && j1 <= g.ju1));
   if ((PATH == 1) != interior) return;
   if (dt_dev) dt = *dt_dev;
   if (U_dev) { U_z = U_dev[0]; U_r = U_dev[1]; }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(MT)
       if (j + 1 < g.nr) nxt = pen_row(uzu, uru, chi, g.ld, j + 1, k, nz, vec, lamdt, U_z, U_r);
       st_pair(rowp(u_z, g.ld, j), c.ks, g.ku0, g.ku1, vec, cur.pz);
       st_pair(rowp(u_r, g.ld, j), c.ks, g.ku0, g.ku1, vec, cur.pr);
-      if (REDUCE) {
+      if (REDUCE && j >= g.ju0 && j < g.ju1) {
         const double r = r1d[j];
         if (c.own0) local += r * cur.chi.x * (cur.pz.x - U_z);
         if (c.own1) local += r * cur.chi.y * (cur.pz.y - U_z);

@@ -123,12 +123,14 @@ class Stage:
             host[...] = t.cpu().numpy()
 
 
-def make_grid(nr, nz, ld, dx, slab=None):
-    """axb_grid_t for a full single-GPU field, or for a z-slab (kz0, nz_global, ku0, ku1)."""
+def make_grid(nr, nz, ld, dx, slab=None, rows=None):
+    """axb_grid_t for a full single-GPU field, for a z-slab (kz0, nz_global, ku0, ku1), or -- ``rows=(ju0, ju1)``
+    -- for an r-slab block whose rows [ju0, ju1) are the owned ones (the only rows fused reductions count)."""
+    ju0, ju1 = (0, 0) if rows is None else rows
     if slab is None:
-        return AxbGrid(nr, nz, ld, float(dx), 0, nz, 0, nz)
+        return AxbGrid(nr, nz, ld, float(dx), 0, nz, 0, nz, ju0, ju1)
     kz0, nzg, ku0, ku1 = slab
-    return AxbGrid(nr, nz, ld, float(dx), kz0, nzg, ku0, ku1)
+    return AxbGrid(nr, nz, ld, float(dx), kz0, nzg, ku0, ku1, ju0, ju1)
 
 
 def coord_1d(stage, X, axis, n):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(_lib.AxbGrid) == 40        # 2*i32, i64, f64, 4*i32
+    assert ctypes.sizeof(_lib.AxbGrid) == 48        # 2*i32, i64, f64, 6*i32
     assert _lib.AxbGrid.ld.offset == 8 and _lib.AxbGrid.dx.offset == 16 and _lib.AxbGrid.kz0.offset == 24
     assert ctypes.sizeof(_lib.AxbFdPlan) == 8 + 6 * 8 + 2 * 8 + 8 + 8 + 3 * 32 + 2 * 64 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
     assert _lib.AxbFdPlan.leaf_fwd.offset == 8 + 6 * 8 + 2 * 8 + 8 + 8 + 3 * 32
