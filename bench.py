@@ -507,7 +507,7 @@ def make_stepper(name, nr, nz, args, world):
             else:                                    # rows split over the ranks: no transposes
                 from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper
 
-                st = RowSlabRigidFlowStepper(nz, grid_size_r=nr)
+                st = RowSlabRigidFlowStepper(nz, grid_size_r=nr, use_graph=not args.no_graph)
         else:
             st = RigidFlowStepper(nz, grid_size_r=nr, r_method=args.r_method, z_method=args.z_method,
                                   use_graph=not args.no_graph)
@@ -683,7 +683,7 @@ def slab_vs_single(world, rank, dist, torch, nz=2048, steps=4):
         from pyaxisymflow_b200.slab import SlabRigidFlowStepper as Stepper
     else:
         from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper as Stepper
-    s = Stepper(nz, grid_size_r=nz // 4)
+    s = Stepper(nz, grid_size_r=nz // 4, **({} if os.environ.get("AXB_SLAB_Z") else {"use_graph": True}))
     s.seed_vorticity()
     s.step(steps)
     w = s.gather_vorticity()
@@ -696,6 +696,8 @@ def slab_vs_single(world, rank, dist, torch, nz=2048, steps=4):
         err = ((w - ref.vorticity).abs().max() / ref.vorticity.abs().max()).item()
         del ref
     dist.barrier()
+    if hasattr(s, "close"):
+        s.close()
     del s
     torch.cuda.empty_cache()
     return err, f"{nz // 4}x{nz}, {steps} steps"
@@ -785,6 +787,9 @@ def run_gpu_arm(args, name, nr, nz):
         err, what = slab_vs_single(world, rank, dist, torch)
         extra = {"slab_vs_single_rel_linf": err, "slab_vs_single_case": what, "phases_ms": phases}
 
+    if hasattr(stepper, "close"):
+        torch.cuda.synchronize()
+        stepper.close()                      # captured graphs go before the process group does
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:

@@ -450,6 +450,21 @@ int axb_dgemm_set_path(int force_ldgsts);
 int axb_peer_block_put(int P, int me, const uint64_t* peer_ptrs, int64_t dst_off, int64_t ld_dst, const double* src,
                        int64_t src_peer_stride, int64_t ld_src, int rows, int cols, axb_stream_t s);
 
+/* ---- rank synchronisation through flags in peer-mapped memory: plain kernels (no collective library call), so a
+ *      whole multi-GPU timestep can be captured in a CUDA graph.  Every rank owns a zero-initialised control block of
+ *      AXB_CTL_WORDS 64-bit words mapped into all processes (ctl_ptrs[q] = rank q's block) and a LOCAL zero-initialised
+ *      counter block of AXB_CTL_COUNTERS words holding the epochs (word 7 is raised if a wait gave up after ~2 s).
+ *      axb_peer_sync: all-rank barrier.  axb_peer_allreduce_max: *value = max over the ranks (the CFL reduction of
+ *      flow_past_sphere.py:150-153).  axb_row_halo_exchange: axb_row_halo_get fused with the neighbour handshake that
+ *      must precede it (ctl_lower / ctl_upper = the neighbours' control blocks, NULL where there is none). ---------- */
+#define AXB_CTL_WORDS 160
+#define AXB_CTL_COUNTERS 8
+int axb_peer_sync(int P, int me, const uint64_t* ctl_ptrs, uint64_t* counters, axb_stream_t s);
+int axb_peer_allreduce_max(int P, int me, const uint64_t* ctl_ptrs, double* value, uint64_t* counters, axb_stream_t s);
+int axb_row_halo_exchange(int nfields, const uint64_t* mine, const uint64_t* lower_peer, const uint64_t* upper_peer,
+                          int64_t ld, int nz, int nrl, int halo, int width, uint64_t* ctl_mine, uint64_t* ctl_lower,
+                          uint64_t* ctl_upper, uint64_t* counters, axb_stream_t s);
+
 /* ---- z-slab plumbing (multi-GPU): pack / unpack `width` halo columns of a field ----------- */
 int axb_halo_pack(const axb_grid_t* g, const double* f, double* buf_left, double* buf_right, int width,
                   axb_stream_t s);

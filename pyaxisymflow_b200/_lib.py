@@ -121,6 +121,9 @@ _SIGNATURES = {
     "axb_halo_put": [_G, _P, _P, _P, _I, _D, _S],
     "axb_row_halo_put": [_I, _P, _P, _P, c_int64, _I, _I, _I, _I, _S],
     "axb_row_halo_get": [_I, _P, _P, _P, c_int64, _I, _I, _I, _I, _S],
+    "axb_peer_sync": [_I, _I, _P, _P, _S],
+    "axb_peer_allreduce_max": [_I, _I, _P, _P, _P, _S],
+    "axb_row_halo_exchange": [_I, _P, _P, _P, c_int64, _I, _I, _I, _I, _P, _P, _P, _P, _S],
     "axb_peer_block_put": [_I, _I, _P, c_int64, c_int64, _P, c_int64, c_int64, _I, _I, _S],
     "axb_rows_to_blocks": [_I, _I, _I, _P, c_int64, _P, _S],
     "axb_blocks_to_slab": [_I, _I, c_int64, _I, _P, _P, _S],

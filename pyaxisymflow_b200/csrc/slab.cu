@@ -127,7 +127,184 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- rank synchronisation by flags in peer-mapped memory (no collective library, CUDA-graph capturable) -----------
+// Every rank owns a control block (AXB_CTL_WORDS 64-bit words, zero-initialised, mapped into all processes):
+//   [0] flag written by the LOWER neighbour, [1] flag written by the UPPER neighbour   (row-halo exchange)
+//   [8, 8 + 16)        barrier flags, one per rank
+//   [32, 32 + 2*16*2)  all-reduce slots: [parity][rank] x {value, epoch}
+// Epochs live in a LOCAL device counter block (3 words + tickets) so that a captured graph advances them itself.
+// Spins give up after ~2 s of clock64 and raise word [7] of the local counters instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long e, unsigned long long* err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < e) {
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(err, 1ULL);
+      return false;
+    }
+    __nanosleep(64);
+  }
+  return true;
+}
+
+struct CtlPtrs {
+  unsigned long long* p[AXB_MAX_PEERS];
+};
+
+// all-rank barrier: one block, thread q talks to rank q
+__global__ void k_peer_sync(CtlPtrs ctl, int P, int me, unsigned long long* cnt) {
+  __shared__ unsigned long long e_s;
+  if (threadIdx.x == 0) e_s = cnt[1] + 1;
+  __syncthreads();
+  const unsigned long long e = e_s;
+  const int q = threadIdx.x;
+  if (q < P) {
+    __threadfence_system();
+    st_release_sys(ctl.p[q] + 8 + me, e);
+    spin_until(ctl.p[me] + 8 + q, e, cnt + 7);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) cnt[1] = e;
+}
+
+// MAX all-reduce of one double (in place): thread q sends to / receives from rank q
+__global__ void k_peer_allreduce_max(CtlPtrs ctl, int P, int me, double* val, unsigned long long* cnt) {
+  __shared__ unsigned long long e_s;
+  __shared__ double v_s[AXB_MAX_PEERS];
+  if (threadIdx.x == 0) e_s = cnt[2] + 1;
+  __syncthreads();
+  const unsigned long long e = e_s;
+  const int q = threadIdx.x;
+  if (q < P) {
+    const double mine = *val;
+    unsigned long long* dst = ctl.p[q] + 32 + ((e & 1) * AXB_MAX_PEERS + me) * 2;
+    dst[0] = (unsigned long long)__double_as_longlong(mine);
+    __threadfence_system();
+    st_release_sys(dst + 1, e);
+    unsigned long long* src = ctl.p[me] + 32 + ((e & 1) * AXB_MAX_PEERS + q) * 2;
+    const bool ok = spin_until(src + 1, e, cnt + 7);
+    v_s[q] = ok ? __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long*>(src)) : mine;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = v_s[0];
+    for (int i = 1; i < P; ++i) m = fmax(m, v_s[i]);
+    *val = m;
+    cnt[2] = e;
+  }
+}
+
+// row-halo exchange in one launch: block (0,0,0) tells both neighbours "my rows of epoch e are ready", every block
+// waits for the neighbour it reads from and then pulls that neighbour's edge rows into this rank's halo rows.
+__global__ void __launch_bounds__(256)
+    k_row_halo_exchange(RowHaloFields f, long long ld, int nz, int nrl, int halo, int w, bool vec,
+                        unsigned long long* ctl_mine, unsigned long long* ctl_lower, unsigned long long* ctl_upper,
+                        unsigned long long* cnt) {
+  __shared__ unsigned long long e_s;
+  __shared__ int ok_s;
+  const int fi = blockIdx.z, up = blockIdx.y;
+  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  if (threadIdx.x == 0) {
+    const unsigned long long e = cnt[0] + 1;          // bumped by the last block to leave (ticket in cnt[4])
+    e_s = e;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      __threadfence_system();
+      if (ctl_lower) st_release_sys(ctl_lower + 1, e);  // I am the lower neighbour's UPPER neighbour
+      if (ctl_upper) st_release_sys(ctl_upper + 0, e);
+    }
+    const unsigned long long* peer_ctl = up ? ctl_upper : ctl_lower;
+    ok_s = peer_ctl ? (spin_until(ctl_mine + (up ? 1 : 0), e, cnt + 7) ? 1 : 0) : 0;
+  }
+  __syncthreads();
+  double* peer = up ? f.upper[fi] : f.lower[fi];
+  if (peer && ok_s) {
+    double* mine = const_cast<double*>(f.src[fi]);
+    const double* s = peer + (long long)(up ? halo : halo + nrl - w) * ld;
+    double* d = mine + (long long)(up ? halo + nrl : halo - w) * ld;
+    const int per_row = (nz + 1) / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * per_row; i += gridDim.x * blockDim.x) {
+      const int r = i / per_row, c = 2 * (i - r * per_row);
+      const long long o = (long long)r * ld + c;
+      if (vec && c + 1 < nz) {
+        *reinterpret_cast<double2*>(d + o) = *reinterpret_cast<const double2*>(s + o);
+      } else {
+        d[o] = s[o];
+        if (c + 1 < nz) d[o + 1] = s[o + 1];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(cnt + 4, 1ULL);
+    if (t == (unsigned long long)nblocks - 1) {
+      cnt[4] = 0;
+      cnt[0] = e_s;
+      __threadfence();
+    }
+  }
+}
+
 extern "C" {
+
+int axb_peer_sync(int P, int me, const uint64_t* ctl_ptrs, uint64_t* counters, axb_stream_t s) {
+  if (P < 1 || P > AXB_MAX_PEERS || me < 0 || me >= P || !ctl_ptrs || !counters) return AXB_EINVAL;
+  CtlPtrs c;
+  for (int q = 0; q < AXB_MAX_PEERS; ++q) c.p[q] = q < P ? reinterpret_cast<unsigned long long*>(ctl_ptrs[q]) : nullptr;
+  for (int q = 0; q < P; ++q)
+    if (!c.p[q]) return AXB_EINVAL;
+  k_peer_sync<<<1, 32, 0, (cudaStream_t)s>>>(c, P, me, reinterpret_cast<unsigned long long*>(counters));
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_peer_allreduce_max(int P, int me, const uint64_t* ctl_ptrs, double* value, uint64_t* counters, axb_stream_t s) {
+  if (P < 1 || P > AXB_MAX_PEERS || me < 0 || me >= P || !ctl_ptrs || !counters || !value) return AXB_EINVAL;
+  CtlPtrs c;
+  for (int q = 0; q < AXB_MAX_PEERS; ++q) c.p[q] = q < P ? reinterpret_cast<unsigned long long*>(ctl_ptrs[q]) : nullptr;
+  for (int q = 0; q < P; ++q)
+    if (!c.p[q]) return AXB_EINVAL;
+  k_peer_allreduce_max<<<1, 32, 0, (cudaStream_t)s>>>(c, P, me, value, reinterpret_cast<unsigned long long*>(counters));
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_row_halo_exchange(int nfields, const uint64_t* mine, const uint64_t* lower_peer, const uint64_t* upper_peer,
+                          int64_t ld, int nz, int nrl, int halo, int width, uint64_t* ctl_mine, uint64_t* ctl_lower,
+                          uint64_t* ctl_upper, uint64_t* counters, axb_stream_t s) {
+  if (nfields < 1 || nfields > 8 || !mine || !lower_peer || !upper_peer || nz < 1 || ld < nz || width < 1 ||
+      width > halo || nrl < width || !ctl_mine || !counters)
+    return AXB_EINVAL;
+  RowHaloFields f;
+  bool vec = (ld % 2 == 0);
+  for (int i = 0; i < 8; ++i) {
+    f.src[i] = nullptr; f.lower[i] = nullptr; f.upper[i] = nullptr;
+    if (i >= nfields) continue;
+    f.src[i] = reinterpret_cast<const double*>(mine[i]);
+    f.lower[i] = reinterpret_cast<double*>(lower_peer[i]);
+    f.upper[i] = reinterpret_cast<double*>(upper_peer[i]);
+    if (!f.src[i]) return AXB_EINVAL;
+    if ((f.lower[i] != nullptr) != (ctl_lower != nullptr) || (f.upper[i] != nullptr) != (ctl_upper != nullptr))
+      return AXB_EINVAL;
+    vec = vec && axb_al16(f.src[i]) && axb_al16(f.lower[i]) && axb_al16(f.upper[i]);
+  }
+  const int work = width * ((nz + 1) / 2);
+  int bx = (work + 255) / 256;
+  if (bx > 32) bx = 32;
+  k_row_halo_exchange<<<dim3(bx, 2, nfields), 256, 0, (cudaStream_t)s>>>(
+      f, ld, nz, nrl, halo, width, vec, reinterpret_cast<unsigned long long*>(ctl_mine),
+      reinterpret_cast<unsigned long long*>(ctl_lower), reinterpret_cast<unsigned long long*>(ctl_upper),
+      reinterpret_cast<unsigned long long*>(counters));
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
 
 static int row_halo(bool get, int nfields, const uint64_t* src, const uint64_t* lower_peer, const uint64_t* upper_peer,
                     int64_t ld, int nz, int nrl, int halo, int width, axb_stream_t s) {

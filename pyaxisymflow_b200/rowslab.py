@@ -107,6 +107,32 @@ class RowSlabComm:
     def peer_info(self, t):
         return self._peer_fields[t.data_ptr()]
 
+    # -- flag-based synchronisation (plain kernels: a whole step can be captured in a CUDA graph) -----------------
+    def enable_flag_sync(self):
+        """control block in peer-mapped memory + local epoch counters (include/axisym_b200.h, axb_peer_sync)"""
+        import torch.distributed._symmetric_memory as symm
+
+        L = self.L
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.ctl = symm.empty((160,), dtype=torch.int64, device=dev)
+        self.ctl.zero_()
+        h = symm.rendezvous(self.ctl, self.group if self.group is not None else dist.group.WORLD)
+        self._ctl_handle = h
+        self.ctl_ptrs = (ctypes.c_uint64 * L.world)(*h.buffer_ptrs)
+        self.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)        # every rank's control block is zero before anyone signals
+        self.flag_sync = True
+
+    def sync(self):
+        L = self.L
+        _call("axb_peer_sync", L.world, L.rank, self.ctl_ptrs, ptr(self.counters), stream_ptr())
+
+    def check(self):
+        """raise if a device-side wait gave up (host synchronisation: diagnostics only)"""
+        if getattr(self, "flag_sync", False) and int(self.counters[7].item()) != 0:
+            raise _lib.AxbError("a rank-synchronisation wait timed out on the device (peer flags never arrived)")
+
     def _exchange_peer(self, fields, width):
         L = self.L
         n = len(fields)
@@ -119,10 +145,16 @@ class RowSlabComm:
             lo[i] = ptrs[L.lower] if L.lower is not None else 0
             up[i] = ptrs[L.upper] if L.upper is not None else 0
         # Pull, not push: a step's kernels also write their own block's halo rows (values nobody uses), so a
-        # neighbour's store could be overwritten by a kernel still running here.  With the pull form ONE barrier
+        # neighbour's store could be overwritten by a kernel still running here.  With the pull form ONE handshake
         # before it orders everything -- the neighbours have produced their edge rows, this rank's stray halo
         # writes are stream-ordered before its own pull, and a neighbour cannot overwrite the rows being read
-        # before it has passed the next exchange's barrier, which this rank only reaches after the pull.
+        # before it has passed the next exchange's handshake, which this rank only answers after the pull.
+        if getattr(self, "flag_sync", False):       # handshake with the two neighbours + pull, one launch
+            cp = self.ctl_ptrs
+            _call("axb_row_halo_exchange", n, src, lo, up, fields[0].stride(0), L.nz, L.nrl, L.halo, width,
+                  ctypes.c_void_p(cp[L.rank]), ctypes.c_void_p(cp[L.lower]) if L.lower is not None else None,
+                  ctypes.c_void_p(cp[L.upper]) if L.upper is not None else None, ptr(self.counters), stream_ptr())
+            return
         h.barrier(channel=1)
         _call("axb_row_halo_get", n, src, lo, up, fields[0].stride(0), L.nz, L.nrl, L.halo, width, stream_ptr())
 
@@ -147,7 +179,11 @@ class RowSlabComm:
                 w.wait()
 
     def allreduce(self, t, op="max"):
-        if self.L.world > 1:
+        L = self.L
+        if L.world > 1:
+            if op == "max" and t.numel() == 1 and t.is_cuda and getattr(self, "flag_sync", False):
+                _call("axb_peer_allreduce_max", L.world, L.rank, self.ctl_ptrs, ptr(t), ptr(self.counters), stream_ptr())
+                return t
             dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
         return t
 
@@ -222,7 +258,7 @@ class RowSlabRigidFlowStepper:
 
     def __init__(self, grid_size_z, grid_size_r=None, domain_AR=0.5, Re=100.0, U_0=1.0, r_sph=0.1, Z_cm=0.25,
                  R_cm=0.0, brink_lam=1e12, CFL=0.1, basis="analytic", group=None, device="cuda", ops=None,
-                 factors=None, dct=None, host_tridiagonal=False):
+                 factors=None, dct=None, host_tridiagonal=False, use_graph=False):
         from .fd import build_factors
 
         cuda = device != "cpu"
@@ -261,6 +297,8 @@ class RowSlabRigidFlowStepper:
                     print(f"[pyaxisymflow_b200] peer-memory halos unavailable ({e!r}); using NCCL send/recv", flush=True)
         if not self.peer_halos:
             self.vorticity = field()
+        if self.peer_halos and not os.environ.get("AXB_SLAB_TORCH_BARRIER"):
+            self.comm.enable_flag_sync()
         self.psi, self.u_r, self._w2, self.char_func = xfield(), xfield(), xfield(), xfield()
         self.u_z, self.u_z_upen, self.u_r_upen, self._tmp = field(), field(), field(), field()
         self.state = torch.zeros(8, dtype=torch.float64, device=device)
@@ -275,7 +313,12 @@ class RowSlabRigidFlowStepper:
                 t = self.comm.symmetric_field(shape)
                 h, ptrs = self.comm.peer_info(t)
                 return t, h, ptrs
-        self.part = PartitionedTridiagonal(L, self.factors, group, peer_ptrs=peer_buf, host=host_tridiagonal)
+        flag_sync = getattr(self.comm, "flag_sync", False)
+        self.part = PartitionedTridiagonal(L, self.factors, group, peer_ptrs=peer_buf, host=host_tridiagonal,
+                                           sync=self.comm.sync if flag_sync else None)
+        # a captured step needs every launch to be a plain kernel: the flag-based synchronisation, or one rank
+        self._use_graph = bool(use_graph) and cuda and (world == 1 or flag_sync)
+        self._graph, self._graphs3, self.graph_launches, self.launches_replayed = None, None, 0, 0
         self.solver = RowSlabFdSolver(L, self.factors, self.part, dct=dct)
         self._sc = (self.U_0, self.T_ramp, 0.0, self.dt_diff_limit, self.CFL * self.dx)
 
@@ -291,22 +334,27 @@ class RowSlabRigidFlowStepper:
         self.vorticity.copy_(L.scatter_global(amplitude * noise * env))
 
     # -- one step, enqueued on the current stream --------------------------------------------------------------
-    def _enqueue(self, probe=None, mark=None):
-        """probe: (event, event) recorded around the solve; mark(name): called after every phase (phase_times)"""
+    def _enqueue(self, probe=None, mark=None, phases=(0, 1, 2)):
+        """probe: (event, event) recorded around the solve; mark(name): called after every phase (phase_times);
+        phases: 0 = everything before the solve, 1 = the solve, 2 = everything after it"""
         L, o, B = self.L, self.ops, self.L.block
         w, psi = self.vorticity, self.psi
         mark = mark or (lambda name: None)
-        o.scalars(0, self._sc)
-        o.kill_z(B(w))
-        parts = (1 if L.upper is None else 0) | (2 if L.lower is None else 0)
-        if parts:
-            o.kill_r(B(w), parts)
-        mark("boundaries")
+        if 0 in phases:
+            o.scalars(0, self._sc)
+            o.kill_z(B(w))
+            parts = (1 if L.upper is None else 0) | (2 if L.lower is None else 0)
+            if parts:
+                o.kill_r(B(w), parts)
+            mark("boundaries")
         if probe is not None:
             probe[0].record()
-        self.solver.solve(L.owned(psi), L.owned(w), mark)
+        if 1 in phases:
+            self.solver.solve(L.owned(psi), L.owned(w), mark)
         if probe is not None:
             probe[1].record()
+        if 2 not in phases:
+            return
         self.comm.exchange([psi], 2)
         mark("halo_psi")
         o.velocity(B(self.u_z_upen), B(self.u_r_upen), B(psi))
@@ -346,14 +394,54 @@ class RowSlabRigidFlowStepper:
                 acc[n] = acc.get(n, 0.0) + evs[i].elapsed_time(evs[i + 1]) / steps
         return {k: round(v, 4) for k, v in acc.items()}
 
+    def _capture(self, phases):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            self._enqueue(phases=phases)
+        return graph, _lib.launch_count() - before
+
     def step(self, n=1):
+        """advance n timesteps (asynchronous).  With ``use_graph`` the step -- kernels, halo handshakes, the CFL
+        all-reduce -- is captured once and replayed; every rank replays the same graph, the device-side flags keep
+        the ranks in step."""
+        if self._use_graph:
+            if self._graph is None:
+                self._enqueue()                      # warm-up outside capture (sets kernel attributes)
+                torch.cuda.synchronize()
+                self._graph, self.graph_launches = self._capture((0, 1, 2))
+                n -= 1
+            for _ in range(n):
+                self._graph.replay()
+                self.launches_replayed += self.graph_launches
+            return
         for _ in range(n):
             self._enqueue()
 
     def step_probed(self):
+        """one step with CUDA events around the solve (bench.py's roofline leg); with ``use_graph`` three graphs"""
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        self._enqueue(probe=ev)
+        if not self._use_graph:
+            self._enqueue(probe=ev)
+            return ev
+        if self._graphs3 is None:
+            self._enqueue()
+            torch.cuda.synchronize()
+            self._graphs3 = [self._capture((p,)) for p in (0, 1, 2)]
+        (g0, n0), (g1, n1), (g2, n2) = self._graphs3
+        g0.replay()
+        ev[0].record()
+        g1.replay()
+        ev[1].record()
+        g2.replay()
+        self.launches_replayed += n0 + n1 + n2
         return ev
+
+    def close(self):
+        """drop the captured graphs (before the process group goes away)"""
+        self._graph, self._graphs3 = None, None
 
     def step_host(self, vorticity_rows_host, char_func_rows_host, out_rows_host):
         """End-to-end form for host-resident callers: this rank's owned rows (pinned ``(Nr/P, Nz)`` host arrays --
@@ -392,6 +480,7 @@ class RowSlabRigidFlowStepper:
                 ") + k_dct_rows (DCT-III)")
 
     def scalars(self):
+        self.comm.check()
         st = self.state.clone()
         self.comm.allreduce(st[7:8], "sum")
         st = st.cpu().numpy()

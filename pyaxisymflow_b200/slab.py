@@ -276,10 +276,11 @@ class PartitionedTridiagonal:
     only and prepared here once.  Compared with transposing to z-mode slabs and back this trades two
     all-to-all transposes for a 2 P Nz gather and one 32 B/pt correction pass."""
 
-    def __init__(self, layout, factors, group=None, peer_ptrs=None, host=False):
+    def __init__(self, layout, factors, group=None, peer_ptrs=None, host=False, sync=None):
         L, f = self.L, self.f = layout, factors
         tri = f["tri"]
         self.group, self.host = group, host
+        self.sync = sync              # rank barrier after the interface put (default: the symmetric-memory barrier)
         c0, c1 = float(f["c0"]), float(f["c1"])
         r0, r1, n = L.r_begin, L.r_begin + L.nrl, L.nrl
         sub, diag, sup, scale, lam = tri["sub"], tri["diag"], tri["sup"], tri["scale"], f["lam_z"]
@@ -355,7 +356,10 @@ class PartitionedTridiagonal:
         if self.G_ptrs is not None:                   # rows 0 and n-1 straight into every rank's G over NVLink
             _call("axb_peer_block_put", L.world, L.rank, self.G_ptrs, L.rank * 2 * nz, nz, ptr(x), 0,
                   (n - 1) * x.stride(0), 2, nz, stream_ptr())
-            self.G_handle.barrier(channel=0)
+            if self.sync is not None:
+                self.sync()
+            else:
+                self.G_handle.barrier(channel=0)
         else:
             mine = torch.stack([x[0], x[-1]]).contiguous()
             if L.world > 1:

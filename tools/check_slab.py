@@ -18,7 +18,10 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-s = (RowSlabRigidFlowStepper if mode == "rows" else SlabRigidFlowStepper)(nz, grid_size_r=nz // 4)
+if mode == "z":
+    s = SlabRigidFlowStepper(nz, grid_size_r=nz // 4)
+else:       # rows: flag-synchronised, replayed as a CUDA graph; rows-eager: the same launched kernel by kernel
+    s = RowSlabRigidFlowStepper(nz, grid_size_r=nz // 4, use_graph=(mode == "rows"))
 s.seed_vorticity()
 s.step(steps)
 w = s.gather_vorticity()
@@ -35,5 +38,7 @@ if rank == 0:
           f"t {sc['t']:.12e} vs {rs['t']:.12e}; Cd {sc['Cd']:.10e} vs {rs['Cd']:.10e}")
     assert err < 1e-10, err
     assert abs(sc["t"] - rs["t"]) <= 1e-14 * abs(rs["t"])
+if hasattr(s, "close"):
+    s.close()
 dist.barrier()
 dist.destroy_process_group()
