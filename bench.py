@@ -535,8 +535,12 @@ def measure_gpu(name, nr, nz, args, steps, warmup, world, rank, dist, sampler=No
             dist.barrier()
             torch.cuda.synchronize()
 
+    # N > 1: the timed steps replay the whole step as ONE graph on every rank; the solve is probed on separate
+    # steps right after the timed region (three graphs with events in between cost 0.1 ms of a 0.6 ms step)
+    split_probe = world > 1 and getattr(stepper, "_use_graph", False)
+
     def one():
-        if whole_graph:
+        if whole_graph or split_probe:
             stepper.step(1)
             return None
         return stepper.step_probed()
@@ -590,6 +594,12 @@ def measure_gpu(name, nr, nz, args, steps, warmup, world, rank, dist, sampler=No
     # ---- roofline of the dominant operation (the solve): algorithmic bytes or flops / its device time
     if probes and probes[0] is not None:
         solve_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
+    elif split_probe:
+        for _ in range(2):
+            stepper.step_probed()
+        extra_probes = [stepper.step_probed() for _ in range(steps)]
+        barrier()
+        solve_ms = float(np.mean([a.elapsed_time(b) for a, b in extra_probes]))
     else:
         solve_ms = solve_probe(stepper, torch)
     flops = stepper.solve_flops()

@@ -7,7 +7,10 @@ and dump ``.vti`` images through ``utils/dump_vtk.py``.  Here a :class:`FieldSna
 device staging buffers on the compute stream (an HBM-speed copy, ordered with the loop's kernels, so it sees a
 consistent step and the loop may overwrite the fields at once), moves those to pinned host buffers on a side
 stream, and hands them to a worker thread that does the file I/O; the compute stream is never synchronised.  ``save_npz`` / ``load_npz`` keep the reference's on-disk format: a plain ``.npz`` with the same
-keys, readable by ``np.load`` on either side.
+keys, readable by ``np.load`` on either side.  ``save_restart`` / ``load_restart`` of the device-resident steppers
+use a PRIVATE key set (``_STATE`` below: the stepper's own fields and loop scalars -- e.g. ``part_char_func`` rather
+than the reference's ``part_phi``, no trajectory lists): they round-trip a stepper bit for bit but are not
+interchangeable with a ``restart.npz`` written by the reference's driver; ``load_restart`` names the missing keys.
 """
 from __future__ import annotations
 
@@ -34,7 +37,7 @@ class FieldSnapshotter:
     def __init__(self, depth=2):
         self.depth = int(depth)
         self._cuda = torch.cuda.is_available()
-        self._side = torch.cuda.Stream() if self._cuda else None
+        self._sides = {}                      # one side stream per device
         self._pool = {}
         self._slots = threading.Semaphore(self.depth)
         self._q = queue.Queue()
@@ -50,7 +53,7 @@ class FieldSnapshotter:
         return torch.empty(t.shape, dtype=t.dtype, pin_memory=self._cuda)
 
     def _dev_buffer(self, t):
-        key = (tuple(t.shape), t.dtype, "dev")
+        key = (tuple(t.shape), t.dtype, "dev", t.device)
         free = self._pool.setdefault(key, [])
         if free:
             return free.pop()
@@ -82,8 +85,12 @@ class FieldSnapshotter:
                 st = self._dev_buffer(v)
                 st.copy_(v)
                 stage[k] = st
-            self._side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self._side):
+            device = next(iter(cuda_items.values())).device
+            side = self._sides.get(device)
+            if side is None:
+                side = self._sides[device] = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
                 for k, st in stage.items():
                     buf = self._buffer(st)
                     buf.copy_(st, non_blocking=True)
@@ -91,7 +98,7 @@ class FieldSnapshotter:
                     used_dev.append(st)
                     host[k] = buf
                 event = torch.cuda.Event()
-                event.record(self._side)
+                event.record(side)
         for k, v in dev.items():
             if k in host:
                 continue
@@ -117,7 +124,9 @@ class FieldSnapshotter:
                 self._err = e
             finally:
                 for buf in used:
-                    self._pool.setdefault((tuple(buf.shape), buf.dtype, "dev" if buf.is_cuda else "host"), []).append(buf)
+                    key = ((tuple(buf.shape), buf.dtype, "dev", buf.device) if buf.is_cuda
+                           else (tuple(buf.shape), buf.dtype, "host"))
+                    self._pool.setdefault(key, []).append(buf)
                 self._slots.release()
                 self._q.task_done()
 
@@ -169,7 +178,8 @@ _STATE = {
     "RigidFlowStepper": (["vorticity", "state"], []),           # state = the 8 device-resident loop scalars
     "SoftSphereStepper": (["vorticity", "eta1", "eta2", "ball_phi", "avg_psi", "avg_phi"], ["t", "freqTimer", "it"]),
     "ParticleFlowStepper": (["vorticity", "part_char_func", "avg_psi", "avg_vort", "avg_part_char_func"],
-                            ["t", "it", "U_z_cm_part", "diff", "part_Z_cm", "F_total"]),
+                            ["t", "it", "U_z_cm_part", "diff", "part_Z_cm", "F_total", "freqTimer", "avg_Z_cm",
+                             "avg_time"]),
 }
 
 
@@ -188,6 +198,10 @@ def load_restart(stepper, path="restart.npz"):
     """particle_in_bubble_oscillatory_flow.py:129-147: fields are copied in place, scalars restored"""
     data = load_npz(path)
     fields, scalars = _STATE[type(stepper).__name__]
+    missing = [k for k in fields + scalars if k not in data]
+    if missing:
+        raise KeyError(f"{path} is not a restart file of {type(stepper).__name__}: missing {missing} "
+                       "(stepper restarts use their own key set, see the module docstring)")
     for k in fields:
         getattr(stepper, k).copy_(torch.from_numpy(np.ascontiguousarray(data[k])))
     for k in scalars:

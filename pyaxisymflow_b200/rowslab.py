@@ -427,9 +427,10 @@ class RowSlabRigidFlowStepper:
             self._enqueue(probe=ev)
             return ev
         if self._graphs3 is None:
-            self._enqueue()
+            self._enqueue(probe=ev)                  # the first call is the warm-up: it IS the step, launched eagerly
             torch.cuda.synchronize()
             self._graphs3 = [self._capture((p,)) for p in (0, 1, 2)]
+            return ev
         (g0, n0), (g1, n1), (g2, n2) = self._graphs3
         g0.replay()
         ev[0].record()

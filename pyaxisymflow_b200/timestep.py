@@ -29,10 +29,11 @@ class RigidFlowStepper:
     """Flow past a Brinkman-penalised rigid sphere, one fused step per call.
 
     Fields (CUDA float64 tensors, shape (Nr, Nz)): ``vorticity, psi, u_z, u_r, char_func``.
-    Launch sequence of one step (18 launches):
-      scalars(0) -> kill_z -> kill_r -> 4 x DGEMM (psi) -> velocity(+U, max) -> scalars(1: dt)
-      -> penalise+curl+drag -> ENO3 advect (w -> w2) -> RK2 stage 1 (w2 -> tmp)
-      -> RK2 stage 2 (w2, tmp -> w) -> scalars(2: t += dt)
+    Launch sequence of one step:
+      scalars(0) -> kill_z -> kill_r -> solve (psi; DCT-II / rfft + two tridiagonal sweeps + DCT-III / irfft on large
+      grids, the four DMMA GEMMs of the eigen-decomposition on small ones) -> velocity(+U, max) -> scalars(1: dt)
+      -> penalise+curl+drag -> ENO3 advect (w -> w2) -> fused RK2 diffusion (w2 -> w; two stages with ghost
+      refreshes in between when z is periodic) -> scalars(2: t += dt)
     """
 
     def __init__(self, grid_size_z, domain_AR=0.5, Re=100.0, U_0=1.0, r_sph=0.1, Z_cm=0.25, R_cm=0.0,
@@ -172,9 +173,10 @@ class RigidFlowStepper:
             self._enqueue(probe=ev)
             return ev
         if self._graphs3 is None:
-            self._enqueue()                          # warm-up outside capture (sets kernel attributes)
-            torch.cuda.synchronize()
+            self._enqueue(probe=ev)                  # the first call is the warm-up (sets kernel attributes): it IS
+            torch.cuda.synchronize()                 # the step, launched kernel by kernel; later calls replay
             self._graphs3 = [self._capture((p,)) for p in (0, 1, 2)]
+            return ev
         (g0, n0), (g1, n1), (g2, n2) = self._graphs3
         g0.replay()
         ev[0].record()
@@ -344,6 +346,7 @@ class SoftSphereStepper:
 
             self._reinit = NarrowBandReinit(nr, nz)
         self.t, self.freqTimer, self.it, self.dt = 0.0, 0.0, 0, 0.0
+        self.cycles, self.on_cycle = 0, None      # on_cycle(stepper): called with the completed-cycle averages
         self.tEnd = 30 / freq
 
     def step(self, n=1):
@@ -404,7 +407,14 @@ class SoftSphereStepper:
         self.t += dt
         self.freqTimer += dt
         if self.freqTimer >= self.freqTimer_limit:
+            # end of an oscillation cycle (soft_sphere_streaming.py:139-165): the driver's hook sees the completed
+            # cycle averages (the reference plots them here), then they start again from zero
             self.freqTimer = 0.0
+            self.cycles += 1
+            if self.on_cycle is not None:
+                self.on_cycle(self)
+            _call("axb_set_fixed_val", g, ptr(self.avg_psi), 0.0, s)
+            _call("axb_set_fixed_val", g, ptr(self.avg_phi), 0.0, s)
         self.it += 1
 
 
@@ -453,6 +463,10 @@ class ParticleFlowStepper:
         del ones
         self.solver = solver if solver is not None else FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis)
         self.t, self.it, self.dt = 0.0, 0, 0.0
+        # per-cycle averages (particle_in_bubble_oscillatory_flow.py:102-109, 168-263, 297-301, 355)
+        self.freqTimer, self.avg_Z_cm, self.avg_time = 0.0, 0.0, 0.0
+        self.cycles, self.on_cycle = 0, None      # on_cycle(stepper): called with the completed-cycle averages
+        self.avg_T, self.avg_part_trajectory = [], []
         self.U_z_cm_part, self.diff = 0.0, 0.0
         self.F_total = 0.0
         self.trace = []       # per step: (t, dt, U_z_cm_part, part_Z_cm, F_total) at the start of the step
@@ -478,6 +492,19 @@ class ParticleFlowStepper:
     def _enqueue_b(self, wmax):
         s, g, dx = stream_ptr(), self.F.g, self.dx
         w = self.vorticity
+        if self.freqTimer >= self.freqTimer_limit:
+            # a cycle is complete (particle_in_bubble_oscillatory_flow.py:168-263): hand the averages to the driver's
+            # hook (the reference dumps them here), record the cycle-mean trajectory point, start again from zero
+            self.freqTimer = 0.0
+            self.cycles += 1
+            cycle_time = self.freqTimer_limit
+            self.avg_T.append(self.avg_time / cycle_time)
+            self.avg_part_trajectory.append((self.avg_Z_cm / cycle_time - self.bubble_Z_cm) / self.r0_bubble)
+            if self.on_cycle is not None:
+                self.on_cycle(self)
+            for f in (self.avg_part_char_func, self.avg_psi, self.avg_vort):
+                _call("axb_set_fixed_val", g, ptr(f), 0.0, s)
+            self.avg_Z_cm, self.avg_time = 0.0, 0.0
         dt = min(0.9 * dx ** 2 / 4 / self.nu, self.CFL / (wmax + self.eps), 0.01 * self.freqTimer_limit)
         self.dt = dt
         _call("axb_add_bubble_flow", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_char_func),
@@ -487,6 +514,9 @@ class ParticleFlowStepper:
         _call("axb_axpy", g, ptr(self.avg_part_char_func), ptr(self.part_char_func), a, None, s)
         _call("axb_axpy", g, ptr(self.avg_psi), ptr(self.psi), a, None, s)
         _call("axb_axpy", g, ptr(self.avg_vort), ptr(w), a, None, s)
+        self.avg_Z_cm += self.part_Z_cm * dt
+        self.avg_time += self.t * dt
+        self.freqTimer += dt
         _call("axb_smooth_heaviside_sphere", g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d),
               self.part_Z_cm, self.part_R_cm, self.r_part, self.moll_zone, s)
         sum_ptr = ctypes.c_void_p(self._acc.data_ptr() + 8)

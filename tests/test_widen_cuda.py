@@ -589,3 +589,36 @@ def test_static_pde_extrapolation_against_reference():
     te, tp = torch.from_numpy(g["box_eta0"].copy()).cuda(), torch.from_numpy(g["box_phi"].copy()).cuda()
     StaticPDEExtrapolation(dx, nr, nz, float(g["box_tol"]), float(g["box_band"])).extrapolate(te, tp)
     assert_close(te.cpu().numpy(), g["box_eta"], 1e-12, "device-resident call")
+
+
+def test_cycle_averages_restart_every_cycle(K):
+    """the reference zeroes its running averages when the oscillation-cycle timer wraps
+    (particle_in_bubble_oscillatory_flow.py:168-263, soft_sphere_streaming.py:139-165); the steppers hand the
+    completed-cycle averages to `on_cycle` and start again from zero."""
+    import torch
+    from pyaxisymflow_b200.timestep import ParticleFlowStepper, SoftSphereStepper
+
+    p = ParticleFlowStepper(64, freq=16.0, e=0.02)
+    seen = []
+    p.on_cycle = lambda s: seen.append((s.it, s.avg_vort.clone(), s.avg_time, s.avg_Z_cm))
+    p.step(104)                                   # dt <= 0.01 cycle: the first cycle ends after >= 100 steps
+    assert p.cycles == 1 and len(seen) == 1 and len(p.avg_T) == 1 and len(p.avg_part_trajectory) == 1
+    it_wrap, full_avg, avg_time, avg_Z = seen[0]
+    assert it_wrap >= 100 and full_avg.abs().max().item() > 0
+    assert abs(p.avg_T[0] - avg_time * 16.0) <= 1e-12 and 0.0 < p.avg_T[0] < 1.0 / 16.0
+    # what has accumulated since the wrap is a few steps' worth, not the whole run
+    since = p.it - it_wrap
+    assert 0 < since <= 5
+    assert p.avg_vort.abs().max().item() <= 0.2 * full_avg.abs().max().item()
+    assert p.freqTimer <= (since + 1) * 0.01 / 16.0 + 1e-15
+
+    s = SoftSphereStepper(64, Z_cm=0.47)
+    s.step(3)
+    assert float(s.avg_phi.abs().max()) > 0.0
+    s.freqTimer = 0.9999 * s.freqTimer_limit                   # (a cycle is ~600 steps at this size) jump to its end
+    calls = []
+    s.on_cycle = lambda st: calls.append(float(st.avg_phi.abs().max()))
+    s.step(1)                                                  # dt is clipped to end the cycle exactly
+    assert s.cycles == 1 and len(calls) == 1 and calls[0] > 0.0
+    assert float(s.avg_psi.abs().max()) == 0.0 and float(s.avg_phi.abs().max()) == 0.0 and s.freqTimer == 0.0
+    torch.cuda.synchronize()
