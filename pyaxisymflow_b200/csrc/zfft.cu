@@ -605,6 +605,265 @@ __global__ void __launch_bounds__(512, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-local variant for N = 16384 (M = 8192 = 32 x 256), modelled line by line in tools/dct_w_model.py.
+// The register-resident kernel above exchanges its 16 points per thread through shared memory after EVERY radix-16
+// pass with block-wide barriers, so all 16 warps sit in the same phase -- butterflies (FP64 pipe), then exchange
+// (shared-memory pipe), then barrier -- and neither pipe is busy half of the time (ncu: FP64 pipe 36 %).  Here the
+// row is split m = n1 + 32 n2:
+//   phase 1  the 256-point FFT over n2 of residue n1 is done by ONE HALF-WARP (two radix-16 passes, exchange X1
+//            inside the half-warp: __syncwarp only);
+//   phase 2  one block-wide exchange X2 and a radix-16 over d (n1 = c + 2 d) give E / O, the two half-length FFTs;
+//   phase 3  radix 2 + real-FFT untangling + quarter-wave rotation work on quadruples {k, k+M/2, M/2-k, M-k} that
+//            live in 4 threads of one warp (exchange X3: __syncwarp only).
+// Everything between two X2 phases -- three DFT-16s, the twiddles, X3, the untangling, the stores, the next row's
+// loads and X1 -- is free of block barriers, so the warps drift apart and the FP64 pipe of one overlaps the
+// shared-memory traffic of another.  The next row is staged by cp.async (16-byte chunks, XOR-swizzled so that the
+// stride-32-sector reads of phase 1 are conflict free; completion through an mbarrier) while the current one is
+// transformed.  All exchanges are conflict free per 16 lanes (XOR placements, no padding): the exchange buffer is
+// exactly one row of doubles (real parts, then imaginary parts).
+// ---------------------------------------------------------------------------------------------
+constexpr int WN = 16384, WM = WN / 2, WH = WM / 2;
+
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+
+// `opaque(t)` hides a loop-invariant value from the optimiser: everything derived from it afterwards is recomputed
+// where it is used (integer ALU work, the FP64 and shared-memory pipes are the busy ones) instead of being kept in
+// registers across the whole row loop -- the 16 complex points of a thread already take 64 of its 128 registers.
+__device__ __forceinline__ int opaque(int t) {
+  asm volatile("" : "+r"(t));
+  return t;
+}
+
+// Stage layout.  The row arrives by TMA (one tensor map over (16 doubles, 8 x 1 KB, 8 x 128 B, 16 x 8 KB, rows), 128-byte
+// swizzle): source byte offset B = 8192 i3 + 1024 i1 + 128 i2 + 16 cc + .. lands in shared-memory line
+// 64 i3 + 8 i2 + i1 at chunk cc ^ i1.  Phase 1 reads sectors 32 apart (i1 = a & 7 differs from lane to lane), so the
+// XOR spreads the 16 lanes of a half-warp over all banks (tools/dct_w_model.py counts the conflicts: none).
+__device__ __forceinline__ int stage_addr8(int s, int h, int word) {     // sector s (32 B), half h, 8-byte word
+  const int i1 = (s >> 5) & 7, i2 = (s >> 2) & 7, i3 = s >> 8;
+  return i3 * 1024 + i2 * 128 + i1 * 16 + 2 * (((2 * s + h) & 7) ^ i1) + word;
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(512, 1)
+    k_dct_rows_w(const __grid_constant__ CUtensorMap tmS, int rows, const double* __restrict__ src, long long ld_src,
+                 double* __restrict__ dst, long long ld_dst, const double2* __restrict__ tabs, double scale0,
+                 double scale, unsigned skew_ns) {
+  extern __shared__ __align__(1024) unsigned char w_smem[];
+  double* S = reinterpret_cast<double*>(w_smem);                         // staged row, swizzled 16-byte chunks
+  double* XB = S + WN;                                                   // exchange buffer: WM doubles
+  double2* Stab = reinterpret_cast<double2*>(XB + WM);                   // W_256^(d ka), 16 x 16
+  double2* tq = Stab + 256;                                              // Q[0 .. M/8]
+  double2* T4 = tq + (WM >> 3) + 1;                                      // W_4096^d, d < 16
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(T4 + 16);
+  const Tabs tb = split_tabs(tabs, WM);
+  const int tid0 = threadIdx.x;
+  const unsigned bar_a = rr_u32(bar);
+  // ---- tables on chip
+  for (int i = tid0; i < 256; i += 512) Stab[i] = tb.M[(32 * (i >> 4) * (i & 15)) & (WM - 1)];
+  for (int i = tid0; i <= (WM >> 3); i += 512) tq[i] = tb.Q[i];
+  if (tid0 < 16) T4[tid0] = tb.M[2 * tid0];
+
+  const unsigned s_base = rr_u32(S);
+  auto issue = [&](int row) {                                            // thread 0: fetch one row, 4 x 32 KB boxes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_a), "r"(WN * 8) : "memory");
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::
+              "r"(s_base + 32768u * q),
+          "l"(reinterpret_cast<unsigned long long>(&tmS)), "r"(0), "r"(0), "r"(0), "r"(4 * q), "r"(row), "r"(bar_a)
+          : "memory");
+  };
+  if (tid0 == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_a), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if ((int)blockIdx.x < rows) issue(blockIdx.x);
+  }
+  __syncthreads();
+
+  int it = 0;
+#pragma unroll 1
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    double2 v[16];
+    {
+      // ---- phase-1 roles: half-warp hw of warp w does the 256-point FFT of residue n1
+      const int tid = opaque(tid0), w = tid >> 5, lane = tid & 31;
+      const int hw = (lane >> 3) & 1;
+      const int j = (lane & 7) | ((lane >> 4) << 3);
+      const int n1 = hw ? 31 - w : w;
+      const int a = hw ? 15 - j : j;
+      const int kb = hw ? (j ^ 8) : j;
+      const int d = n1 >> 1;
+      // tw1 base: W_4096^(16 a + d) = W_256^a W_4096^d, negated when the slots are rotated by 8 ((-1)^kb)
+      double2 w1 = cmul(Stab[16 + a], T4[d]);
+      if (hw) { w1.x = -w1.x; w1.y = -w1.y; }
+      double2 w4 = cmul(w1, w1);
+      w4 = cmul(w4, w4);
+      // stage addresses (8-byte words): slots 0..7 then 8..15, see the model (stage_word)
+      int sA_re, sA_im, sB_re, sB_im;
+      {
+        const int s0 = n1 + 32 * a;                                      // sectors with b < 8: words 0 (re), 2 (im)
+        const int lo_re = stage_addr8(s0, 0, 0), lo_im = stage_addr8(s0, 1, 0);
+        const int s1 = (31 - n1) + 32 * (15 - a);                        // mirrored sectors: words 3 (re), 1 (im)
+        const int hi_re = stage_addr8(s1, 1, 1), hi_im = stage_addr8(s1, 0, 1);
+        if (!hw) { sA_re = lo_re; sA_im = lo_im; sB_re = hi_re + 7 * 2048; sB_im = hi_im + 7 * 2048; }
+        else { sA_re = hi_re + 7 * 2048; sA_im = hi_im + 7 * 2048; sB_re = lo_re; sB_im = lo_im; }
+      }
+      const int stepA = hw ? -2048 : 2048;                               // slot i < 8: + i stepA; i >= 8: - (i-8) stepA
+      rr_mb_wait(bar_a, it & 1);
+      // ---- phase 1a: 16 points z[n1 + 32 (a + 16 b)]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = make_double2(S[sA_re + i * stepA], S[sA_im + i * stepA]);
+#pragma unroll
+      for (int i = 8; i < 16; ++i) v[i] = make_double2(S[sB_re - (i - 8) * stepA], S[sB_im - (i - 8) * stepA]);
+      dft<16>(v);
+      {                                                                  // tw1: v[t] *= w1^t
+        double2 wa[4], wb[4];
+        wb[1] = w1;
+        wa[1] = w4;
+        wb[2] = cmul(wb[1], wb[1]);
+        wb[3] = cmul(wb[2], wb[1]);
+        wa[2] = cmul(wa[1], wa[1]);
+        wa[3] = cmul(wa[2], wa[1]);
+#pragma unroll
+        for (int t = 1; t < 16; ++t) {
+          const int hi = t >> 2, lo = t & 3;
+          const double2 ww = (hi == 0) ? wb[lo] : (lo == 0 ? wa[hi] : cmul(wa[hi], wb[lo]));
+          v[t] = cmul(v[t], ww);
+        }
+      }
+      // ---- X1: 16 x 16 transpose inside the half-warp (real parts, then imaginary parts)
+      const int x1w = 512 * w + 256 * hw + 16 * a;                       // element (a, k) at + (k ^ a)
+      const int x1r = 512 * w + 256 * hw;                                // read (aa, kb) at + 16 aa + (kb ^ aa)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) XB[x1w + (k ^ a)] = v[k].x;
+      __syncwarp();
+#pragma unroll
+      for (int aa = 0; aa < 16; ++aa) v[aa].x = XB[x1r + 16 * aa + (kb ^ aa)];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) XB[x1w + (k ^ a)] = v[k].y;
+      __syncwarp();
+#pragma unroll
+      for (int aa = 0; aa < 16; ++aa) v[aa].y = XB[x1r + 16 * aa + (kb ^ aa)];
+      dft<16>(v);
+#pragma unroll
+      for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], Stab[16 * d + t]);  // tw2 (broadcast reads)
+    }
+    __syncthreads();                        // A: every warp has left the stage and its X1 region
+    if (tid0 == 0 && row + (int)gridDim.x < rows) issue(row + gridDim.x);
+    {
+      // ---- X2: block-wide, A(n1, k2) = 256 n1 + (k2 ^ sigma(n1)); readers are the phase-3 threads
+      const int tid = opaque(tid0), w = tid >> 5, lane = tid & 31;
+      const int hw = (lane >> 3) & 1;
+      const int j = (lane & 7) | ((lane >> 4) << 3);
+      const int n1 = hw ? 31 - w : w;
+      const int kb = hw ? (j ^ 8) : j;
+      const int sg = 8 * ((n1 & 1) ^ (n1 >> 4));
+      const int x2w = 256 * n1 + (kb ^ sg);                              // + 16 q
+      const int mu = lane >> 4, c = (lane >> 3) & 1, G = lane & 7;
+      int k2 = mu ? 256 - 8 * w - G : 8 * w + G;
+      if (w == 0 && G == 0 && mu) k2 = 128;
+      const int x2r_lo = 256 * c + (k2 ^ (8 * c)), x2r_hi = 256 * c + (k2 ^ (8 * (c ^ 1)));   // + 512 dd
+#pragma unroll
+      for (int q = 0; q < 16; ++q) XB[x2w + 16 * q] = v[q].x;
+      __syncthreads();
+#pragma unroll
+      for (int dd = 0; dd < 8; ++dd) v[dd].x = XB[x2r_lo + 512 * dd];
+#pragma unroll
+      for (int dd = 8; dd < 16; ++dd) v[dd].x = XB[x2r_hi + 512 * dd];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) XB[x2w + 16 * q] = v[q].y;
+      __syncthreads();
+#pragma unroll
+      for (int dd = 0; dd < 8; ++dd) v[dd].y = XB[x2r_lo + 512 * dd];
+#pragma unroll
+      for (int dd = 8; dd < 16; ++dd) v[dd].y = XB[x2r_hi + 512 * dd];
+    }
+    __syncthreads();                        // E: the exchange buffer is warp-private again
+    // The block barriers of X2 leave all 16 warps at the same point of the same instruction sequence, and left alone
+    // they stay in step: FP64 phases and shared-memory phases of all warps coincide and the two pipes take turns.
+    // Holding back two of the four warps of every scheduler by about one phase makes them complementary.
+    if (skew_ns && ((opaque(tid0) >> 7) & 1)) __nanosleep(skew_ns);
+    dft<16>(v);                             // v[e] = E (c = 0) / O (c = 1) [k2 + 256 e]
+    {
+      // ---- phase 3: member mm = 2 mu + c of group G of warp w holds E/O of residue k2 (mu: the mirrored residue)
+      const int tid = opaque(tid0), w = tid >> 5, lane = tid & 31;
+      const int mu = lane >> 4, c = (lane >> 3) & 1, G = lane & 7, mm = 2 * mu + c;
+      const bool special = (w == 0) && (G == 0);                         // residues 0 and 128 pair with themselves
+      const int x3b = 512 * w + 64 * G;
+      const int ph0 = (2 * G) & 15, ph1 = (2 * G + 1) & 15;             // XOR of the members with even / odd index
+      const int phw = c ? ph1 : ph0;
+      const int x3w = x3b + 16 * mm;                                     // element e at + (e ^ phw)
+      // quadruple i: e_i = eb + i es; sources: members (mlo, mlo + 1) at e_i and (mhi, mhi + 1) at et - e_i
+      int eb = mm, es = 4, et = 15, mlo = 0, mhi = 2, kres = 8 * w + G;
+      if (special) {
+        es = 2;
+        if (mu) { eb = c; mlo = 2; kres = 128; }
+        else { eb = 1 + c; et = 16; mhi = 0; kres = 0; }
+      }
+      const bool first = special && mm == 1;                             // this thread also emits k = 0 and k = M/2
+      double2 e0 = make_double2(0.0, 0.0), o0 = e0;
+      // X3: after it v[4 i + s] = E[k], O[k], E[M/2 - k], O[M/2 - k] of quadruple i (real parts, then imaginary)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) XB[x3w + (e ^ phw)] = v[e].x;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = eb + i * es, em = et - e;
+        v[4 * i].x = XB[x3b + 16 * mlo + (e ^ ph0)];
+        v[4 * i + 1].x = XB[x3b + 16 * (mlo + 1) + (e ^ ph1)];
+        v[4 * i + 2].x = XB[x3b + 16 * mhi + (em ^ ph0)];
+        v[4 * i + 3].x = XB[x3b + 16 * (mhi + 1) + (em ^ ph1)];
+      }
+      if (first) { e0.x = XB[x3b + ph0]; o0.x = XB[x3b + 16 + ph1]; }
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) XB[x3w + (e ^ phw)] = v[e].y;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = eb + i * es, em = et - e;
+        v[4 * i].y = XB[x3b + 16 * mlo + (e ^ ph0)];
+        v[4 * i + 1].y = XB[x3b + 16 * (mlo + 1) + (e ^ ph1)];
+        v[4 * i + 2].y = XB[x3b + 16 * mhi + (em ^ ph0)];
+        v[4 * i + 3].y = XB[x3b + 16 * (mhi + 1) + (em ^ ph1)];
+      }
+      if (first) { e0.y = XB[x3b + ph0]; o0.y = XB[x3b + 16 + ph1]; }
+      __syncwarp();
+      // ---- radix 2 + untangling + quarter-wave rotation, 8 outputs per quadruple
+      double* out = dst + (long long)row * ld_dst;
+      if (first) {
+        const double2 z0 = cadd(e0, o0), zh = csub(e0, o0);
+        out[0] = (z0.x + z0.y) * scale0;
+        out[WM] = (z0.x - z0.y) * RH * scale;
+        dct2_emit(out, WH, WM, WN, zh, zh, make_double2(0.92387953251128675613, -0.38268343236508977173),
+                  make_double2(0.0, -1.0), scale);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = kres + 256 * (eb + i * es);
+        const double2 q = q_at(tq, k, WM);
+        const double2 qq = cmul(q, q);
+        const double2 tn = cmul(qq, qq);                                 // exp(-2 pi i k / N)
+        const double2 wk = cmul(tn, tn);                                 // exp(-2 pi i k / M)
+        const double2 wb = cmul(wk, v[4 * i + 1]);
+        const double2 cwd = cmul(make_double2(wk.x, -wk.y), v[4 * i + 3]);
+        const double2 z_k = cadd(v[4 * i], wb), z_kh = csub(v[4 * i], wb);
+        const double2 z_hk = csub(v[4 * i + 2], cwd), z_mk = cadd(v[4 * i + 2], cwd);
+        const double2 q2 = cmul(make_double2(0.92387953251128675613, -0.38268343236508977173), make_double2(q.x, -q.y));
+        dct2_emit(out, k, WM, WN, z_k, z_mk, q, tn, scale);
+        dct2_emit(out, WH - k, WM, WN, z_hk, z_kh, q2, make_double2(-tn.y, -tn.x), scale);
+      }
+    }
+  }
+}
+
 int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -652,6 +911,39 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
   }
   static int rr_off = -1;
   if (rr_off < 0) rr_off = getenv("AXB_DCT_SMEM") ? 1 : 0;
+  static int w_off = -1;
+  if (w_off < 0) w_off = getenv("AXB_DCT_RR") ? 1 : 0;                 // A/B switch: the register-resident kernel
+  if (vec && !rr_off && !w_off && N == WN && !inverse) {
+    const size_t wb_bytes = (size_t)(WN + WM) * sizeof(double) + (256 + (WM >> 3) + 1 + 16) * sizeof(double2) + 16;
+    static bool w_once = false;
+    if (!w_once) {
+      cudaFuncSetAttribute(k_dct_rows_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      w_once = true;
+    }
+    const int grid = rows < sms ? rows : sms;
+    static int skew = -1;
+    if (skew < 0) skew = getenv("AXB_DCT_SKEW") ? atoi(getenv("AXB_DCT_SKEW")) : 600;
+    CUtensorMap tmW;
+    memset(&tmW, 0, sizeof(tmW));
+    bool ok = false;
+    if (DctEncodeFn enc = dct_encoder()) {
+      // (16 doubles, 8 x 1 KB, 8 x 128 B, 16 x 8 KB, rows): the 1 KB dimension before the 128 B one, see stage_addr8
+      const cuuint64_t dims[5] = {16, 8, 8, 16, (cuuint64_t)rows};
+      const cuuint64_t strides[4] = {1024, 128, 8192, (cuuint64_t)ld_src * 8};
+      const cuuint32_t box[5] = {16u, 8u, 8u, 4u, 1u};
+      const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+      ok = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double*>(src), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (ok) {
+      k_dct_rows_w<false><<<grid, 512, wb_bytes, st>>>(tmW, rows, src, ld_src, dst, ld_dst,
+                                                        reinterpret_cast<const double2*>(tabs), scale0, scale,
+                                                        (unsigned)skew);
+      AXB_LAUNCHED();
+      return (int)cudaGetLastError();
+    }
+  }
   if (vec && !rr_off && ((ilog2(M) - 1) % 4 == 0)) {
     // register-resident kernel with the next row prefetched by TMA
     int rr_rpc = 1;

@@ -1520,3 +1520,32 @@ def test_particle_flow_stepper_and_ensemble(K):
     a.step(steps)
     wa = _oracle_particle_loop(nz, steps, freq=16.0, e=0.02, trace=a.trace)[0]
     assert_close(a.vorticity.cpu().numpy(), wa, 1e-9, "second ensemble member")
+
+
+def test_dct_rows_full_width_many_rows(K):
+    """N = 16384 with more rows than resident blocks (every block loops over several rows, the last wave is
+    partial): the warp-local kernels (csrc/zfft.cu k_dct_rows_w) against scipy's cosine transforms, and the
+    round trip."""
+    import scipy.fft as sf
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+
+    n, rows = 16384, 333
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((rows, n)) * (1.0 + np.arange(rows))[:, None]
+    tabs = torch.from_numpy(fd.dct_tables(n)).cuda()
+    src = torch.from_numpy(x).cuda()
+    dst = torch.zeros_like(src)
+    _lib.call("axb_dct2_rows", rows, n, ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(tabs), 1.0, 1.0, stream_ptr())
+    want = sf.dct(x, type=2, axis=1) / 2
+    got = dst.cpu().numpy()
+    for r in (0, 1, 147, 148, 149, 295, 296, 332):
+        assert_close(got[r], want[r], 1e-13, f"DCT-II row {r}")
+    assert_close(got, want, 1e-13, "DCT-II 333 x 16384")
+    _lib.call("axb_dct2_rows", rows, n, ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(tabs), 1.0 / n, 2.0 / n,
+              stream_ptr())
+    back = torch.zeros_like(src)
+    _lib.call("axb_dct3_rows", rows, n, ptr(dst), dst.stride(0), ptr(back), back.stride(0), ptr(tabs), stream_ptr())
+    assert_close(back.cpu().numpy(), x, 2e-13, "DCT-III(DCT-II) 333 x 16384")

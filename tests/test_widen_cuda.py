@@ -601,16 +601,18 @@ def test_cycle_averages_restart_every_cycle(K):
     p = ParticleFlowStepper(64, freq=16.0, e=0.02)
     seen = []
     p.on_cycle = lambda s: seen.append((s.it, s.avg_vort.clone(), s.avg_time, s.avg_Z_cm))
-    p.step(104)                                   # dt <= 0.01 cycle: the first cycle ends after >= 100 steps
+    p.step(20)
+    assert p.cycles == 0 and 0.0 < p.freqTimer < p.freqTimer_limit
+    full_avg, avg_time = p.avg_vort.clone(), p.avg_time
+    assert full_avg.abs().max().item() > 0 and avg_time > 0
+    p.freqTimer = p.freqTimer_limit               # (a cycle is > 100 steps) jump to its end: the next step wraps
+    p.step(1)
     assert p.cycles == 1 and len(seen) == 1 and len(p.avg_T) == 1 and len(p.avg_part_trajectory) == 1
-    it_wrap, full_avg, avg_time, avg_Z = seen[0]
-    assert it_wrap >= 100 and full_avg.abs().max().item() > 0
-    assert abs(p.avg_T[0] - avg_time * 16.0) <= 1e-12 and 0.0 < p.avg_T[0] < 1.0 / 16.0
-    # what has accumulated since the wrap is a few steps' worth, not the whole run
-    since = p.it - it_wrap
-    assert 0 < since <= 5
-    assert p.avg_vort.abs().max().item() <= 0.2 * full_avg.abs().max().item()
-    assert p.freqTimer <= (since + 1) * 0.01 / 16.0 + 1e-15
+    assert seen[0][0] == 20 and torch.equal(seen[0][1], full_avg)          # the hook saw the completed averages
+    assert abs(p.avg_T[0] - avg_time * 16.0) <= 1e-15
+    # what has accumulated since the wrap is one step's worth, not the whole run
+    assert 0.0 < p.avg_vort.abs().max().item() <= 0.5 * full_avg.abs().max().item()
+    assert abs(p.freqTimer - p.dt) <= 1e-18 and abs(p.avg_time - (p.t - p.dt) * p.dt) <= 1e-18
 
     s = SoftSphereStepper(64, Z_cm=0.47)
     s.step(3)
