@@ -646,6 +646,15 @@ __device__ __forceinline__ int stage_addr8(int s, int h, int word) {     // sect
   return i3 * 1024 + i2 * 128 + i1 * 16 + 2 * (((2 * s + h) & 7) ^ i1) + word;
 }
 
+// DCT-III stage: the spectrum is read at k, N-k, M-k, M+k with k = n1 + 32 (a + 16 b), 32 DOUBLES apart from lane to
+// lane, so the tensor map is (16 doubles, 8 x 256 B, 2 x 128 B, 64 x 2 KB, rows): source offset
+// 8 k = 2048 i3 + 256 i1 + 128 i2 + 16 cc + .. lands in line 16 i3 + 8 i2 + i1 at chunk cc ^ i1 (i1 = a & 7).
+// (All four indices have the parity of n1, and so have both half-warps of a warp: 2-way conflicts remain.)
+__device__ __forceinline__ int stage3_addr8(int k) {
+  const int cc = (k >> 1) & 7, i2 = (k >> 4) & 1, i1 = (k >> 5) & 7, i3 = k >> 8;
+  return (16 * i3 + 8 * i2 + i1) * 16 + 2 * (cc ^ i1) + (k & 1);
+}
+
 template <bool INV>
 __global__ void __launch_bounds__(512, 1)
     k_dct_rows_w(const __grid_constant__ CUtensorMap tmS, int rows, const double* __restrict__ src, long long ld_src,
@@ -656,8 +665,8 @@ __global__ void __launch_bounds__(512, 1)
   double* XB = S + WN;                                                   // exchange buffer: WM doubles
   double2* Stab = reinterpret_cast<double2*>(XB + WM);                   // W_256^(d ka), 16 x 16
   double2* tq = Stab + 256;                                              // Q[0 .. M/8]
-  double2* T4 = tq + (WM >> 3) + 1;                                      // W_4096^d, d < 16
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(T4 + 16);
+  double2* T4 = tq + (WM >> 3) + 1;                                      // W_4096^d, d < 16; [16] = exp(-2 pi i / M)
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(T4 + 17);
   const Tabs tb = split_tabs(tabs, WM);
   const int tid0 = threadIdx.x;
   const unsigned bar_a = rr_u32(bar);
@@ -665,6 +674,7 @@ __global__ void __launch_bounds__(512, 1)
   for (int i = tid0; i < 256; i += 512) Stab[i] = tb.M[(32 * (i >> 4) * (i & 15)) & (WM - 1)];
   for (int i = tid0; i <= (WM >> 3); i += 512) tq[i] = tb.Q[i];
   if (tid0 < 16) T4[tid0] = tb.M[2 * tid0];
+  if (tid0 == 16) T4[16] = tb.M[1];
 
   const unsigned s_base = rr_u32(S);
   auto issue = [&](int row) {                                            // thread 0: fetch one row, 4 x 32 KB boxes
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(512, 1)
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::
               "r"(s_base + 32768u * q),
-          "l"(reinterpret_cast<unsigned long long>(&tmS)), "r"(0), "r"(0), "r"(0), "r"(4 * q), "r"(row), "r"(bar_a)
+          "l"(reinterpret_cast<unsigned long long>(&tmS)), "r"(0), "r"(0), "r"(0), "r"((INV ? 16 : 4) * q), "r"(row), "r"(bar_a)
           : "memory");
   };
   if (tid0 == 0) {
@@ -694,32 +704,71 @@ __global__ void __launch_bounds__(512, 1)
       const int tid = opaque(tid0), w = tid >> 5, lane = tid & 31;
       const int hw = (lane >> 3) & 1;
       const int j = (lane & 7) | ((lane >> 4) << 3);
-      const int n1 = hw ? 31 - w : w;
-      const int a = hw ? 15 - j : j;
-      const int kb = hw ? (j ^ 8) : j;
+      // DCT-II : n1 = w | 31 - w (sectors m and M-1-m share a warp), hw1 mirrored (a = 15 - j) and rotated by 8
+      // DCT-III: n1 = w | 32 - w (Z[k] and Z[M-k] come as pairs; warp 0: 0 | 16), natural roles
+      int n1 = INV ? (hw ? 32 - w : w) : (hw ? 31 - w : w);
+      if (INV && w == 0 && hw) n1 = 16;
+      const int a = (!INV && hw) ? 15 - j : j;
+      const int kb = (!INV && hw) ? (j ^ 8) : j;
+      const int x1x = (INV && hw) ? 8 : 0;                               // X1 placement of the second half-warp
       const int d = n1 >> 1;
       // tw1 base: W_4096^(16 a + d) = W_256^a W_4096^d, negated when the slots are rotated by 8 ((-1)^kb)
       double2 w1 = cmul(Stab[16 + a], T4[d]);
-      if (hw) { w1.x = -w1.x; w1.y = -w1.y; }
+      if (!INV && hw) { w1.x = -w1.x; w1.y = -w1.y; }
       double2 w4 = cmul(w1, w1);
       w4 = cmul(w4, w4);
-      // stage addresses (8-byte words): slots 0..7 then 8..15, see the model (stage_word)
-      int sA_re, sA_im, sB_re, sB_im;
-      {
-        const int s0 = n1 + 32 * a;                                      // sectors with b < 8: words 0 (re), 2 (im)
-        const int lo_re = stage_addr8(s0, 0, 0), lo_im = stage_addr8(s0, 1, 0);
-        const int s1 = (31 - n1) + 32 * (15 - a);                        // mirrored sectors: words 3 (re), 1 (im)
-        const int hi_re = stage_addr8(s1, 1, 1), hi_im = stage_addr8(s1, 0, 1);
-        if (!hw) { sA_re = lo_re; sA_im = lo_im; sB_re = hi_re + 7 * 2048; sB_im = hi_im + 7 * 2048; }
-        else { sA_re = hi_re + 7 * 2048; sA_im = hi_im + 7 * 2048; sB_re = lo_re; sB_im = lo_im; }
+      if constexpr (!INV) {
+        // stage addresses (8-byte words): slots 0..7 then 8..15, see the model (stage_word)
+        int sA_re, sA_im, sB_re, sB_im;
+        {
+          const int s0 = n1 + 32 * a;                                    // sectors with b < 8: words 0 (re), 2 (im)
+          const int lo_re = stage_addr8(s0, 0, 0), lo_im = stage_addr8(s0, 1, 0);
+          const int s1 = (31 - n1) + 32 * (15 - a);                      // mirrored sectors: words 3 (re), 1 (im)
+          const int hi_re = stage_addr8(s1, 1, 1), hi_im = stage_addr8(s1, 0, 1);
+          if (!hw) { sA_re = lo_re; sA_im = lo_im; sB_re = hi_re + 7 * 2048; sB_im = hi_im + 7 * 2048; }
+          else { sA_re = hi_re + 7 * 2048; sA_im = hi_im + 7 * 2048; sB_re = lo_re; sB_im = lo_im; }
+        }
+        const int stepA = hw ? -2048 : 2048;                             // slot i < 8: + i stepA; i >= 8: - (i-8) stepA
+        rr_mb_wait(bar_a, it & 1);
+        // ---- phase 1a: 16 points z[n1 + 32 (a + 16 b)]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = make_double2(S[sA_re + i * stepA], S[sA_im + i * stepA]);
+#pragma unroll
+        for (int i = 8; i < 16; ++i) v[i] = make_double2(S[sB_re - (i - 8) * stepA], S[sB_im - (i - 8) * stepA]);
+      } else {
+        // ---- phase 1a: Z[k] for the own slots b < 8 (k = n1 + 32 a + 512 b < M/2) from the quadruple
+        //      a[k], a[N-k], a[M-k], a[M+k]; the same quadruple gives Z[M-k], slot 15 - b of the thread that holds
+        //      residue 32 - n1 at a' = 15 - a (warp 0: residue 0 pairs n2 <-> 256 - n2, residue 16 n2 <-> 255 - n2)
+        const int k0 = n1 + 32 * a;
+        const int pk = stage3_addr8(k0), pnk = stage3_addr8(WN - k0), pmk = stage3_addr8(WM - k0),
+                  ppk = stage3_addr8(WM + k0);                           // slot i: +-512 i
+        const bool sp0 = (k0 == 0);                                      // the thread that holds Z[0] and Z[M/2]
+        int dh = hw ^ 1, dj = 15 - j;
+        if (w == 0) { dh = hw; dj = hw ? 15 - j : ((16 - j) & 15); }
+        double2* XP = reinterpret_cast<double2*>(XB) + 256 * w;          // pair exchange: one warp's 256 complex
+        const int dst0 = dh * 128 + (dj ^ (8 * dh)) + (sp0 ? 16 : 0);    // slot 15 - i (+ 1 for residue 0, a = 0)
+        rr_mb_wait(bar_a, it & 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = k0 + 512 * i;
+          double2 zm;
+          if (i == 0 && sp0) {
+            const double a0 = S[stage3_addr8(0)], am = S[stage3_addr8(WM)] * RH;
+            v[0] = make_double2(a0 - am, a0 + am);                       // Z[0], stored swapped (im, re)
+            double2 dummy;
+            dct3_pair(S[stage3_addr8(WH)], S[stage3_addr8(WN - WH)], S[stage3_addr8(WM - WH)], S[stage3_addr8(WM + WH)],
+                      make_double2(0.92387953251128675613, -0.38268343236508977173), zm, dummy);   // Z[M/2]: slot 8
+            XP[0] = zm;
+          } else {
+            dct3_pair(S[pk + 512 * i], S[pnk - 512 * i], S[pmk - 512 * i], S[ppk + 512 * i], q_at(tq, k, WM), v[i], zm);
+            XP[dst0 + 16 * (7 - i)] = zm;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 8; i < 16; ++i) v[i] = XP[hw * 128 + 16 * (i - 8) + (j ^ (8 * hw))];
+        __syncwarp();
       }
-      const int stepA = hw ? -2048 : 2048;                               // slot i < 8: + i stepA; i >= 8: - (i-8) stepA
-      rr_mb_wait(bar_a, it & 1);
-      // ---- phase 1a: 16 points z[n1 + 32 (a + 16 b)]
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = make_double2(S[sA_re + i * stepA], S[sA_im + i * stepA]);
-#pragma unroll
-      for (int i = 8; i < 16; ++i) v[i] = make_double2(S[sB_re - (i - 8) * stepA], S[sB_im - (i - 8) * stepA]);
       dft<16>(v);
       {                                                                  // tw1: v[t] *= w1^t
         double2 wa[4], wb[4];
@@ -739,17 +788,18 @@ __global__ void __launch_bounds__(512, 1)
       // ---- X1: 16 x 16 transpose inside the half-warp (real parts, then imaginary parts)
       const int x1w = 512 * w + 256 * hw + 16 * a;                       // element (a, k) at + (k ^ a)
       const int x1r = 512 * w + 256 * hw;                                // read (aa, kb) at + 16 aa + (kb ^ aa)
+      const int ax = a ^ x1x, kx = kb ^ x1x;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) XB[x1w + (k ^ a)] = v[k].x;
+      for (int k = 0; k < 16; ++k) XB[x1w + (k ^ ax)] = v[k].x;
       __syncwarp();
 #pragma unroll
-      for (int aa = 0; aa < 16; ++aa) v[aa].x = XB[x1r + 16 * aa + (kb ^ aa)];
+      for (int aa = 0; aa < 16; ++aa) v[aa].x = XB[x1r + 16 * aa + (kx ^ aa)];
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < 16; ++k) XB[x1w + (k ^ a)] = v[k].y;
+      for (int k = 0; k < 16; ++k) XB[x1w + (k ^ ax)] = v[k].y;
       __syncwarp();
 #pragma unroll
-      for (int aa = 0; aa < 16; ++aa) v[aa].y = XB[x1r + 16 * aa + (kb ^ aa)];
+      for (int aa = 0; aa < 16; ++aa) v[aa].y = XB[x1r + 16 * aa + (kx ^ aa)];
       dft<16>(v);
 #pragma unroll
       for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], Stab[16 * d + t]);  // tw2 (broadcast reads)
@@ -761,13 +811,15 @@ __global__ void __launch_bounds__(512, 1)
       const int tid = opaque(tid0), w = tid >> 5, lane = tid & 31;
       const int hw = (lane >> 3) & 1;
       const int j = (lane & 7) | ((lane >> 4) << 3);
-      const int n1 = hw ? 31 - w : w;
-      const int kb = hw ? (j ^ 8) : j;
+      int n1 = INV ? (hw ? 32 - w : w) : (hw ? 31 - w : w);
+      if (INV && w == 0 && hw) n1 = 16;
+      const int kb = (!INV && hw) ? (j ^ 8) : j;
       const int sg = 8 * ((n1 & 1) ^ (n1 >> 4));
       const int x2w = 256 * n1 + (kb ^ sg);                              // + 16 q
       const int mu = lane >> 4, c = (lane >> 3) & 1, G = lane & 7;
-      int k2 = mu ? 256 - 8 * w - G : 8 * w + G;
-      if (w == 0 && G == 0 && mu) k2 = 128;
+      // DCT-II residues pair as k2 <-> 256 - k2 (0 and 128 with themselves), DCT-III as k2 <-> 255 - k2
+      int k2 = mu ? (INV ? 255 : 256) - 8 * w - G : 8 * w + G;
+      if (!INV && w == 0 && G == 0 && mu) k2 = 128;
       const int x2r_lo = 256 * c + (k2 ^ (8 * c)), x2r_hi = 256 * c + (k2 ^ (8 * (c ^ 1)));   // + 512 dd
 #pragma unroll
       for (int q = 0; q < 16; ++q) XB[x2w + 16 * q] = v[q].x;
@@ -795,7 +847,7 @@ __global__ void __launch_bounds__(512, 1)
       // ---- phase 3: member mm = 2 mu + c of group G of warp w holds E/O of residue k2 (mu: the mirrored residue)
       const int tid = opaque(tid0), w = tid >> 5, lane = tid & 31;
       const int mu = lane >> 4, c = (lane >> 3) & 1, G = lane & 7, mm = 2 * mu + c;
-      const bool special = (w == 0) && (G == 0);                         // residues 0 and 128 pair with themselves
+      const bool special = !INV && (w == 0) && (G == 0);                 // residues 0 and 128 pair with themselves
       const int x3b = 512 * w + 64 * G;
       const int ph0 = (2 * G) & 15, ph1 = (2 * G + 1) & 15;             // XOR of the members with even / odd index
       const int phw = c ? ph1 : ph0;
@@ -836,8 +888,32 @@ __global__ void __launch_bounds__(512, 1)
       }
       if (first) { e0.y = XB[x3b + ph0]; o0.y = XB[x3b + 16 + ph1]; }
       __syncwarp();
-      // ---- radix 2 + untangling + quarter-wave rotation, 8 outputs per quadruple
       double* out = dst + (long long)row * ld_dst;
+      if constexpr (INV) {
+        // ---- radix 2 + the two sectors y[4n .. 4n+3], y[4n' .. 4n'+3] (n' = M/2 - 1 - n) of every quadruple
+        const double2 wm1 = T4[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = kres + 256 * (eb + i * es), n2 = WH - 1 - n;
+          // exp(-2 pi i n / M) = Q[n]^8; exp(-2 pi i (M/2 - 1 - n) / M) = -conj(exp(-2 pi i (n + 1) / M))
+          const double2 q = q_at(tq, n, WM);
+          const double2 qq = cmul(q, q);
+          const double2 q4 = cmul(qq, qq);
+          const double2 wn = cmul(q4, q4);
+          const double2 w1n = cmul(wn, wm1);
+          const double2 wb = cmul(wn, v[4 * i + 1]);
+          const double2 wd = cmul(make_double2(-w1n.x, w1n.y), v[4 * i + 3]);
+          const double2 z_n = cadd(v[4 * i], wb), z_nh = csub(v[4 * i], wb);          // z[n], z[n + M/2]
+          const double2 z_c = cadd(v[4 * i + 2], wd), z_m = csub(v[4 * i + 2], wd);   // z[M/2-1-n], z[M-1-n]
+          // stored swapped: (.y, .x) = (re, im)
+          *reinterpret_cast<double2*>(out + 4 * n) = make_double2(z_n.y, z_m.x);
+          *reinterpret_cast<double2*>(out + 4 * n + 2) = make_double2(z_n.x, z_m.y);
+          *reinterpret_cast<double2*>(out + 4 * n2) = make_double2(z_c.y, z_nh.x);
+          *reinterpret_cast<double2*>(out + 4 * n2 + 2) = make_double2(z_c.x, z_nh.y);
+        }
+        continue;
+      }
+      // ---- radix 2 + untangling + quarter-wave rotation, 8 outputs per quadruple
       if (first) {
         const double2 z0 = cadd(e0, o0), zh = csub(e0, o0);
         out[0] = (z0.x + z0.y) * scale0;
@@ -913,11 +989,12 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
   if (rr_off < 0) rr_off = getenv("AXB_DCT_SMEM") ? 1 : 0;
   static int w_off = -1;
   if (w_off < 0) w_off = getenv("AXB_DCT_RR") ? 1 : 0;                 // A/B switch: the register-resident kernel
-  if (vec && !rr_off && !w_off && N == WN && !inverse) {
-    const size_t wb_bytes = (size_t)(WN + WM) * sizeof(double) + (256 + (WM >> 3) + 1 + 16) * sizeof(double2) + 16;
+  if (vec && !rr_off && !w_off && N == WN) {
+    const size_t wb_bytes = (size_t)(WN + WM) * sizeof(double) + (256 + (WM >> 3) + 1 + 17) * sizeof(double2) + 16;
     static bool w_once = false;
     if (!w_once) {
       cudaFuncSetAttribute(k_dct_rows_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(k_dct_rows_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       w_once = true;
     }
     const int grid = rows < sms ? rows : sms;
@@ -927,17 +1004,26 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
     memset(&tmW, 0, sizeof(tmW));
     bool ok = false;
     if (DctEncodeFn enc = dct_encoder()) {
-      // (16 doubles, 8 x 1 KB, 8 x 128 B, 16 x 8 KB, rows): the 1 KB dimension before the 128 B one, see stage_addr8
-      const cuuint64_t dims[5] = {16, 8, 8, 16, (cuuint64_t)rows};
-      const cuuint64_t strides[4] = {1024, 128, 8192, (cuuint64_t)ld_src * 8};
-      const cuuint32_t box[5] = {16u, 8u, 8u, 4u, 1u};
+      // DCT-II : (16 doubles, 8 x 1 KB, 8 x 128 B, 16 x 8 KB, rows), the 1 KB dimension first (stage_addr8)
+      // DCT-III: (16 doubles, 8 x 256 B, 2 x 128 B, 64 x 2 KB, rows) (stage3_addr8); 4 boxes of 32 KB either way
+      const cuuint64_t dims2[5] = {16, 8, 8, 16, (cuuint64_t)rows}, dims3[5] = {16, 8, 2, 64, (cuuint64_t)rows};
+      const cuuint64_t str2[4] = {1024, 128, 8192, (cuuint64_t)ld_src * 8}, str3[4] = {256, 128, 2048, (cuuint64_t)ld_src * 8};
+      const cuuint32_t box2[5] = {16u, 8u, 8u, 4u, 1u}, box3[5] = {16u, 8u, 2u, 16u, 1u};
+      const cuuint64_t* dims = inverse ? dims3 : dims2;
+      const cuuint64_t* strides = inverse ? str3 : str2;
+      const cuuint32_t* box = inverse ? box3 : box2;
       const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
       ok = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double*>(src), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
     if (ok) {
-      k_dct_rows_w<false><<<grid, 512, wb_bytes, st>>>(tmW, rows, src, ld_src, dst, ld_dst,
+      if (inverse)
+        k_dct_rows_w<true><<<grid, 512, wb_bytes, st>>>(tmW, rows, src, ld_src, dst, ld_dst,
+                                                         reinterpret_cast<const double2*>(tabs), scale0, scale,
+                                                         (unsigned)skew);
+      else
+        k_dct_rows_w<false><<<grid, 512, wb_bytes, st>>>(tmW, rows, src, ld_src, dst, ld_dst,
                                                         reinterpret_cast<const double2*>(tabs), scale0, scale,
                                                         (unsigned)skew);
       AXB_LAUNCHED();

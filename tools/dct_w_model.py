@@ -78,7 +78,7 @@ def stage_fill(x):
     return S
 
 
-def fft_core(v, n1, a_role, kb_role, bk, tabM, sign=1.0):
+def fft_core(v, n1, a_role, kb_role, bk, tabM, sign=1.0, x1x=0, mirror=256):
     """phases 1b .. 2 shared by both transforms.  v[tid, b]: the 16 points z[n1 + 32 (a + 16 b)] of every thread.
     Returns vq[tid, e] = E/O[k2 + 256 e] in the phase-3 thread layout together with (k2, c, mu, G)."""
     tid, w, lane, hw, j = ids()
@@ -93,12 +93,12 @@ def fft_core(v, n1, a_role, kb_role, bk, tabM, sign=1.0):
     XB = np.zeros(M, complex)
     R = 512 * w + 256 * hw
     for k in range(16):
-        addr = R + 16 * a_role + (k ^ a_role)
+        addr = R + 16 * a_role + (k ^ a_role ^ x1x)
         bk.check("X1 write", addr)
         XB[addr] = v[:, k]
     u = np.empty_like(v)
     for a in range(16):
-        addr = R + 16 * a + (kb_role ^ a)
+        addr = R + 16 * a + (kb_role ^ a ^ x1x)
         bk.check("X1 read", addr)
         u[:, a] = XB[addr]
     u = dft16(u)                                              # Y[n1][kb + 16 ka] (times b0)
@@ -113,8 +113,11 @@ def fft_core(v, n1, a_role, kb_role, bk, tabM, sign=1.0):
         bk.check("X2 write", addr)
         XB[addr] = u[:, q]
     mu, c, G = lane >> 4, (lane >> 3) & 1, lane & 7
-    k2 = np.where(mu == 0, 8 * w + G, 256 - 8 * w - G)
-    k2 = np.where((mu == 1) & (w == 0) & (G == 0), 128, k2)
+    if mirror == 255:                                       # DCT-III: residues pair as k2 <-> 255 - k2
+        k2 = np.where(mu == 0, 8 * w + G, 255 - 8 * w - G)
+    else:                                                   # DCT-II: k2 <-> 256 - k2, 0 and 128 pair with themselves
+        k2 = np.where(mu == 0, 8 * w + G, 256 - 8 * w - G)
+        k2 = np.where((mu == 1) & (w == 0) & (G == 0), 128, k2)
     vq = np.empty_like(u)
     for dd in range(16):
         nn = c + 2 * dd
@@ -227,6 +230,117 @@ def dct2_w(x, tabs, bk=None):
     return X, bk
 
 
+def stage_word3(k):
+    """DCT-III stage: TMA box (16 doubles, 8 x 256 B, 2 x 128 B, 64 x 2 KB), 128-byte swizzle: source offset
+    B = 8 k = 2048 i3 + 256 i1 + 128 i2 + 16 cc + .. lands in line 16 i3 + 8 i2 + i1 at chunk cc ^ i1"""
+    cc, i2, i1, i3 = (k >> 1) & 7, (k >> 4) & 1, (k >> 5) & 7, k >> 8
+    return (16 * i3 + 8 * i2 + i1) * 16 + 2 * (cc ^ i1) + (k & 1)
+
+
+def stage_fill3(x):
+    S = np.zeros(x.size)
+    k = np.arange(x.size)
+    S[stage_word3(k)] = x
+    return S
+
+
+def dct3_w(a_in, tabs, bk=None):
+    """DCT-III of one row: y[j] = sum_k a[k] cos(pi k (2j+1) / 2N), through the same forward FFT on swapped (im, re)"""
+    bk = bk or Banks()
+    tabM, tabN, tabQ = tabs
+    tid, w, lane, hw, j = ids()
+    S = stage_fill3(a_in)
+    # ---- phase-1 roles: hw0 does residue n1 = w, hw1 residue 32 - w (Z[k] and Z[M-k] come as pairs); warp 0: 0 and 16
+    n1 = np.where(hw == 0, w, 32 - w)
+    n1 = np.where((w == 0) & (hw == 1), 16, n1)
+    a_role = j.copy()
+    kb_role = j.copy()
+    v = np.zeros((T, 16), complex)
+    XB = np.zeros(M, complex)
+
+    def pair(k):
+        """(Z[k], Z[M-k]) swapped (im, re), 1 <= k < M/2"""
+        ak, ank, amk, apk = (S[stage_word3(k)], S[stage_word3(N - k)], S[stage_word3(M - k)], S[stage_word3(M + k)])
+        qk = tabQ[k]
+        qm = RH * (qk.real - qk.imag) - 1j * RH * (qk.real + qk.imag)
+        bkk = np.conj(qk) * (0.5 * ak - 0.5j * ank)
+        bm = np.conj(qm) * (0.5 * amk - 0.5j * apk)
+        sx, sy = bkk.real + bm.real, bkk.imag - bm.imag
+        dd = (bkk.real - bm.real) + 1j * (bkk.imag + bm.imag)
+        q = np.conj(tabN[k]) * dd
+        return (sy + q.real) + 1j * (sx - q.imag), (-sy + q.real) + 1j * (sx + q.imag)
+
+    for i in range(8):                                      # bank check of the four stage reads of own slot i
+        k = n1 + 32 * (a_role + 16 * i)
+        for idx in (k, N - k, M - k, M + k):
+            bk.check("stage3 read", stage_word3(np.where((idx >= 0) & (idx < N), idx, 0)))
+    for t in range(T):
+        ww, hh, jj, nn, aa = w[t], hw[t], j[t], n1[t], a_role[t]
+        base = 512 * ww
+        for i in range(8):
+            k = nn + 32 * (aa + 16 * i)
+            if k == 0:
+                a0, am = S[stage_word3(0)], S[stage_word3(M)] * RH
+                v[t, 0] = (a0 - am) + 1j * (a0 + am)
+                # Z[M/2] (its own mirror): slot 8 of the same thread
+                ak, ank = S[stage_word3(H)], S[stage_word3(N - H)]
+                amk, apk = S[stage_word3(M - H)], S[stage_word3(M + H)]
+                qk = np.exp(-1j * np.pi / 8)
+                qm = RH * (qk.real - qk.imag) - 1j * RH * (qk.real + qk.imag)
+                bkk = np.conj(qk) * (0.5 * ak - 0.5j * ank)
+                bm = np.conj(qm) * (0.5 * amk - 0.5j * apk)
+                sx, sy = bkk.real + bm.real, bkk.imag - bm.imag
+                dd = (bkk.real - bm.real) + 1j * (bkk.imag + bm.imag)
+                q = np.conj(-1j) * dd
+                v[t, 8] = (sy + q.real) + 1j * (sx - q.imag)
+                continue
+            zk, zm = pair(k)
+            v[t, i] = zk
+            # destination of Z[M-k]
+            if ww > 0:
+                dh, dj, ds = hh ^ 1, 15 - jj, 15 - i
+            elif hh == 0:                                   # residue 0: n2 <-> 256 - n2
+                if aa == 0:
+                    dh, dj, ds = 0, 0, 16 - i
+                else:
+                    dh, dj, ds = 0, 16 - jj, 15 - i
+            else:                                           # residue 16: n2 <-> 255 - n2
+                dh, dj, ds = 1, 15 - jj, 15 - i
+            XB[base + dh * 128 + (ds - 8) * 16 + (dj ^ (8 * dh))] = zm
+    for t in range(T):
+        ww, hh, jj = w[t], hw[t], j[t]
+        for sl in range(8, 16):
+            if ww == 0 and hh == 0 and jj == 0 and sl == 8:
+                continue                                    # Z[M/2], already in place
+            v[t, sl] = XB[512 * ww + hh * 128 + (sl - 8) * 16 + (jj ^ (8 * hh))]
+    x1x = np.where(hw == 0, 0, 8)
+    vq, k2, c, mu, G = fft_core(v, n1, a_role, kb_role, bk, tabM, 1.0, x1x, mirror=255)
+    # ---- phase 3: quadruples {n, n + M/2, M/2 - 1 - n, M - 1 - n}, n = (8 w + G) + 256 e
+    m = 2 * mu + c
+    XB = np.zeros(M, complex)
+    for e in range(16):
+        addr = x3_addr(w, G, m, e)
+        bk.check("X3 write", addr)
+        XB[addr] = vq[:, e]
+    y = np.zeros(N)
+    wm1 = tabM[1]
+    for t in range(T):
+        ww, gg, mm = w[t], G[t], m[t]
+        for i in range(4):
+            e = 4 * i + mm
+            n = 8 * ww + gg + 256 * e
+            n2 = H - 1 - n
+            v0, v1 = XB[x3_addr(ww, gg, 0, e)], XB[x3_addr(ww, gg, 1, e)]
+            v2, v3 = XB[x3_addr(ww, gg, 2, 15 - e)], XB[x3_addr(ww, gg, 3, 15 - e)]
+            wn = tabM[n]
+            w1 = wn * wm1
+            wb, wd = wn * v1, (-np.conj(w1)) * v3
+            z_n, z_nh, z_c, z_m = v0 + wb, v0 - wb, v2 + wd, v2 - wd
+            y[4 * n:4 * n + 4] = z_n.imag, z_m.real, z_n.real, z_m.imag
+            y[4 * n2:4 * n2 + 4] = z_c.imag, z_nh.real, z_c.real, z_nh.imag
+    return y, bk
+
+
 def tables():
     import os
     import sys
@@ -247,3 +361,8 @@ if __name__ == "__main__":
     ref = sf.dct(x, 2) / 2
     print("dct2_w vs scipy:", np.abs(X - ref).max() / np.abs(ref).max())
     print("worst bank multiplicity per 16-lane group:", bk.worst)
+    a = rng.standard_normal(N)
+    y, bk3 = dct3_w(a, tables())
+    ref3 = sf.dct(a, 3) / 2 + a[0] / 2                      # scipy's DCT-III halves the k = 0 term
+    print("dct3_w vs scipy:", np.abs(y - ref3).max() / np.abs(ref3).max())
+    print("worst bank multiplicity per 16-lane group:", bk3.worst)
