@@ -841,7 +841,11 @@ __global__ void __launch_bounds__(512, 1)
     // The block barriers of X2 leave all 16 warps at the same point of the same instruction sequence, and left alone
     // they stay in step: FP64 phases and shared-memory phases of all warps coincide and the two pipes take turns.
     // Holding back two of the four warps of every scheduler by about one phase makes them complementary.
-    if (skew_ns && ((opaque(tid0) >> 7) & 1)) __nanosleep(skew_ns);
+    if (skew_ns) {
+      const int g = (opaque(tid0) >> 7) & 3;                             // the four warps of a scheduler: 0 .. 3
+      const unsigned ns = (skew_ns >> 16) ? (skew_ns & 0xffff) * g : ((g & 1) ? skew_ns : 0);
+      if (ns) __nanosleep(ns);
+    }
     dft<16>(v);                             // v[e] = E (c = 0) / O (c = 1) [k2 + 256 e]
     {
       // ---- phase 3: member mm = 2 mu + c of group G of warp w holds E/O of residue k2 (mu: the mirrored residue)
