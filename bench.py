@@ -391,24 +391,29 @@ class _ConfigRunner:
 
         self.torch = torch
         self.cases = 1
+        self.ensemble = None
         if name == "c3":
             # Z_cm off the grid's mirror plane when re-initialising: exact ties make the marcher (and the GPU
             # iteration) order/rounding dependent and cost extra sweeps
             self.members = [SoftSphereStepper(nz, grid_size_r=nr, basis=basis, reinit_levelset=reinit,
                                               Z_cm=0.47 if reinit else 0.5)]
         else:
-            first = ParticleFlowStepper(nz, grid_size_r=nr, basis=basis)
-            self.members = [first]
-            freqs = [4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0, 32.0]
-            for i in range(1, cases):
-                self.members.append(ParticleFlowStepper(nz, grid_size_r=nr, freq=freqs[i % 8],
-                                                        e=0.005 * (1 + (i // 8) % 8), solver=first.solver))
-            self.cases = cases
-        self.ensemble = None
-        if name == "c5" and not os.environ.get("AXB_ENSEMBLE_SERIAL"):
             from pyaxisymflow_b200.timestep import ParticleEnsemble
 
-            self.ensemble = ParticleEnsemble(self.members)
+            freqs = [4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0, 32.0]
+            params = [(8.0, 0.01)] + [(freqs[i % 8], 0.005 * (1 + (i // 8) % 8)) for i in range(1, cases)]
+            self.cases = cases
+            mode = os.environ.get("AXB_ENSEMBLE", "batched")
+            if mode == "batched":
+                # SURVEY 8e "Ensemble": one (nr, cases nz) tensor per field, one solve for all members, loop scalars
+                # on the device, the whole ensemble step replayed as one CUDA graph
+                self.ensemble = ParticleEnsemble.batched_ensemble(params, nz, nr, use_graph=True, basis=basis)
+                self.members = self.ensemble.members
+            else:
+                first = ParticleFlowStepper(nz, grid_size_r=nr, basis=basis, freq=params[0][0], e=params[0][1])
+                self.members = [first] + [ParticleFlowStepper(nz, grid_size_r=nr, freq=f, e=e, solver=first.solver)
+                                          for f, e in params[1:]]
+                self.ensemble = ParticleEnsemble(self.members) if mode == "streams" else None   # else "serial"
         self.name = name
         self.solver = self.members[0].solver
         self.vorticity = self.members[0].vorticity
@@ -432,6 +437,9 @@ class _ConfigRunner:
         if self.name == "c3":
             m = self.members[0]
             return [m.vorticity, m.eta1, m.eta2, m.ball_phi], [m.vorticity, m.eta1, m.eta2, m.ball_phi]
+        if getattr(self.ensemble, "batched", False):
+            w = self.ensemble._w_wide                        # all members' vorticity, one (nr, cases nz) tensor
+            return [w], [w]
         return [m.vorticity for m in self.members], [m.vorticity for m in self.members]
 
     def solve_flops(self):

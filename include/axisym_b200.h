@@ -231,6 +231,30 @@ int axb_smooth_heaviside_mask(const axb_grid_t* g, double* H, uint8_t* mask, con
 int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
                         const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble,
                         double U_0, double sin_omega_t, axb_stream_t s);
+/* ---- the particle driver without host round trips: the loop scalars of
+ *      particle_in_bubble_oscillatory_flow.py live in a device block `state` of >= 19 doubles
+ *        [0] t  [1] dt  [2] max|w| (reduction target)  [3] penalisation sum (reduction target)  [4] U_z_cm_part
+ *        [5] 0 (U_r)  [6] part_Z_cm  [7] F_total  [8] it  [9] sin(omega t)  [10] dt / cycle  [11] freqTimer
+ *        [12] avg_Z_cm  [13] avg_time  [14] cycles  [15] wrap flag of this step  [16] diff  [17], [18] last cycle's
+ *        avg_T / avg_part_trajectory point
+ *      axb_particle_scalars phase 1 = :168-170 + :255-270 + :297-301 (cycle wrap, dt from max|w|, averages of the host
+ *      scalars), phase 2 = compute_forces.py:4-17 + :323-355 (force, rigid-body update, t += dt); `trace`, if given, is
+ *      a ring of trace_cap rows (t, dt, U_z_cm_part, part_Z_cm, F_total) written at the start-of-step values.
+ *      axb_cycle_average3 = the three running averages of :297-299 in one pass, restarted (completed averages kept in
+ *      last_i, may be NULL) when state[15] is set.  The _dev forms of the bubble flow and the sphere Heaviside read
+ *      sin(omega t) / the sphere's z centre from device memory. ------------------------------------------------ */
+int axb_particle_scalars(int phase, double* state, double* trace, int trace_cap, double dt_diff_limit, double cfl,
+                         double eps, double cycle, double omega, double rho_lam, double part_vol, double part_mass,
+                         double bubble_z_cm, double r0_bubble, axb_stream_t s);
+int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, double* last0, double* avg1, const double* x1,
+                       double* last1, double* avg2, const double* x2, double* last2, const double* a_dev,
+                       const double* wrap_dev, axb_stream_t s);
+int axb_add_bubble_flow_dev(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
+                            const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
+                            double r0_bubble, double U_0, const double* sin_omega_t_dev, axb_stream_t s);
+int axb_smooth_heaviside_sphere_dev(const axb_grid_t* g, double* H, double* phi_out, const double* z1d,
+                                    const double* r1d, const double* z_cm_dev, double r_cm, double radius,
+                                    double blend_w, axb_stream_t s);
 
 /* ---- a18: elasto_kernels/solid_sigma.py:4-29 (all seven caller-visible outputs).
  *      chi != NULL additionally applies the driver's blend sigma *= chi

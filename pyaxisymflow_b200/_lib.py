@@ -83,6 +83,10 @@ _SIGNATURES = {
     "axb_pin_level_set": [_G, _P, _P, _P, _P, _D, _D, _D, _D, _S],
     "axb_smooth_heaviside_mask": [_G, _P, _P, _P, _D, _D, _I, _S],
     "axb_add_bubble_flow": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D, _S],
+    "axb_add_bubble_flow_dev": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _S],
+    "axb_smooth_heaviside_sphere_dev": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _S],
+    "axb_particle_scalars": [_I, _P, _P, _I, _D, _D, _D, _D, _D, _D, _D, _D, _D, _D, _S],
+    "axb_cycle_average3": [_G, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_sigma": [_G, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_tau": [_G, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_vorticity_update": [_G, _P, _P, _P, _D, _P, _S],

@@ -72,10 +72,11 @@ __global__ void k_heav_mask(GridD g, double* __restrict__ H, unsigned char* __re
 __global__ void __launch_bounds__(TBX* TBY)
     k_bubble(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ chi_b,
              const double* __restrict__ z1d, const double* __restrict__ r1d, double bz, double br, double r0, double U0,
-             double s, bool vec) {
+             double s, const double* __restrict__ s_dev, bool vec) {
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
+  if (s_dev) s = *s_dev;
   const double2 c = ld_pair(rowp(chi_b, g.ld, j), k, g.nz, vec);
   double2 uz = ld_pair(rowp(u_z, g.ld, j), k, g.nz, vec), ur = ld_pair(rowp(u_r, g.ld, j), k, g.nz, vec);
   const double dr = r1d[j] - br;
@@ -95,9 +96,114 @@ __global__ void __launch_bounds__(TBX* TBY)
   st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(vr[0], vr[1]));
 }
 
+// running averages of three fields in one pass, restarted when the cycle timer wrapped (device flag):
+//   avg_i = (wrap ? 0 : avg_i) + a x_i;  on a wrap the completed averages are kept in last_i (may be null)
+struct Avg3 {
+  double* avg[3];
+  const double* x[3];
+  double* last[3];
+};
+__global__ void __launch_bounds__(TBX* TBY)
+    k_cycle_avg3(GridD g, Avg3 f, const double* __restrict__ a_dev, const double* __restrict__ wrap_dev, bool vec) {
+  const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
+  const int j = blockIdx.y * TBY + threadIdx.y;
+  if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
+  const double a = *a_dev;
+  const bool wrap = *wrap_dev != 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double2 xv = ld_pair(rowp(f.x[i], g.ld, j), k, g.nz, vec);
+    double2 yv = ld_pair(rowp(f.avg[i], g.ld, j), k, g.nz, vec);
+    if (wrap) {
+      if (f.last[i]) st_pair(rowp(f.last[i], g.ld, j), k, g.ku0, g.ku1, vec, yv);
+      yv = make_double2(0.0, 0.0);
+    }
+    yv.x = yv.x + xv.x * a;
+    yv.y = yv.y + xv.y * a;
+    st_pair(rowp(f.avg[i], g.ld, j), k, g.ku0, g.ku1, vec, yv);
+  }
+}
+
+// The host decisions of one particle step (particle_in_bubble_oscillatory_flow.py:168-170, 255-270, 297-301,
+// 323-355) on a device-resident scalar block, so that the step needs no host round trip:
+//   st[0] t, [1] dt, [2] max|w| (reduction target), [3] penalisation sum (reduction target), [4] U_z_cm_part,
+//   [5] 0 (U_r), [6] part_Z_cm, [7] F_total, [8] it, [9] sin(omega t), [10] dt / cycle, [11] freqTimer, [12] avg_Z_cm,
+//   [13] avg_time, [14] cycles, [15] wrap flag of this step, [16] diff, [17] last avg_T, [18] last avg trajectory point
+struct ParticleParams {
+  double dt_diff, cfl, eps, cycle, omega, rho_lam, part_vol, part_mass, bubble_z, r0;
+};
+__global__ void k_particle_scalars(int phase, double* st, double* trace, int trace_cap, ParticleParams p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (phase == 1) {
+    double wrap = 0.0;
+    if (st[11] >= p.cycle) {
+      wrap = 1.0;
+      st[11] = 0.0;
+      st[14] = st[14] + 1.0;
+      st[17] = st[13] / p.cycle;
+      st[18] = (st[12] / p.cycle - p.bubble_z) / p.r0;
+      st[12] = 0.0;
+      st[13] = 0.0;
+    }
+    st[15] = wrap;
+    const double dt = fmin(fmin(p.dt_diff, p.cfl / (st[2] + p.eps)), 0.01 * p.cycle);
+    st[1] = dt;
+    st[9] = sin(p.omega * st[0]);
+    st[10] = dt / p.cycle;
+    st[12] = st[12] + st[6] * dt;
+    st[13] = st[13] + st[0] * dt;
+    st[11] = st[11] + dt;
+    st[3] = 0.0;
+  } else {
+    const double dt = st[1];
+    const double F_pen = p.rho_lam * st[3];
+    const double F_un = (st[16] * p.part_vol) / dt;
+    const double F = F_pen + F_un;
+    st[7] = F;
+    if (trace && trace_cap > 0) {
+      double* row = trace + 5 * ((long long)st[8] % trace_cap);
+      row[0] = st[0]; row[1] = dt; row[2] = st[4]; row[3] = st[6]; row[4] = F;
+    }
+    const double U_old = st[4];
+    st[4] = st[4] + 0.5 * dt * (st[16] / dt + (F / p.part_mass));
+    st[16] = dt * F / p.part_mass;
+    st[6] = st[6] + (U_old * dt + (0.5 * dt * dt * F / p.part_mass));
+    st[0] = st[0] + dt;
+    st[8] = st[8] + 1.0;
+    st[2] = 0.0;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, double* last0, double* avg1, const double* x1,
+                       double* last1, double* avg2, const double* x2, double* last2, const double* a_dev,
+                       const double* wrap_dev, axb_stream_t s) {
+  if (!avg0 || !x0 || !avg1 || !x1 || !avg2 || !x2 || !a_dev || !wrap_dev) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  Avg3 f;
+  f.avg[0] = avg0; f.avg[1] = avg1; f.avg[2] = avg2;
+  f.x[0] = x0; f.x[1] = x1; f.x[2] = x2;
+  f.last[0] = last0; f.last[1] = last1; f.last[2] = last2;
+  k_cycle_avg3<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, f, a_dev, wrap_dev,
+                                                   vec_ok(d, {avg0, x0, last0, avg1, x1, last1, avg2, x2, last2}));
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_particle_scalars(int phase, double* state, double* trace, int trace_cap, double dt_diff_limit, double cfl,
+                         double eps, double cycle, double omega, double rho_lam, double part_vol, double part_mass,
+                         double bubble_z_cm, double r0_bubble, axb_stream_t s) {
+  if (!state || (phase != 1 && phase != 2) || trace_cap < 0) return AXB_EINVAL;
+  const ParticleParams p = {dt_diff_limit, cfl, eps, cycle, omega, rho_lam, part_vol, part_mass, bubble_z_cm, r0_bubble};
+  k_particle_scalars<<<1, 32, 0, s>>>(phase, state, trace, trace_cap, p);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
 
 int axb_axpy(const axb_grid_t* g, double* y, const double* x, double a, const double* a_dev, axb_stream_t s) {
   if (!y || !x) return AXB_EINVAL;
@@ -133,17 +239,31 @@ int axb_smooth_heaviside_mask(const axb_grid_t* g, double* H, uint8_t* mask, con
   AXB_RETURN_LAST();
 }
 
-int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
-                        const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble,
-                        double U_0, double sin_omega_t, axb_stream_t s) {
+static int bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func, const double* z1d,
+                       const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble, double U_0,
+                       double sin_omega_t, const double* sin_dev, axb_stream_t s) {
   if (!u_z || !u_r || !bubble_char_func || !z1d || !r1d) return AXB_EINVAL;
   int rc = axb_check_grid(g);
   if (rc) return rc;
   const GridD d = to_dev(g);
   k_bubble<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm,
-                                              r0_bubble, U_0, sin_omega_t, vec_ok(d, {u_z, u_r, bubble_char_func}));
+                                              r0_bubble, U_0, sin_omega_t, sin_dev,
+                                              vec_ok(d, {u_z, u_r, bubble_char_func}));
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
+}
+int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
+                        const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble,
+                        double U_0, double sin_omega_t, axb_stream_t s) {
+  return bubble_flow(g, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm, r0_bubble, U_0, sin_omega_t,
+                     nullptr, s);
+}
+int axb_add_bubble_flow_dev(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
+                            const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
+                            double r0_bubble, double U_0, const double* sin_omega_t_dev, axb_stream_t s) {
+  if (!sin_omega_t_dev) return AXB_EINVAL;
+  return bubble_flow(g, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm, r0_bubble, U_0, 0.0,
+                     sin_omega_t_dev, s);
 }
 
 }  // extern "C"

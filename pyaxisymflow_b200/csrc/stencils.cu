@@ -345,12 +345,13 @@ template <bool SPHERE>
 __global__ void __launch_bounds__(TBX* TBY)
     k_heaviside(GridD g, double* __restrict__ H, double* __restrict__ phi_out, const double* __restrict__ phi,
                 const double* __restrict__ z1d, const double* __restrict__ r1d, double z_cm, double r_cm,
-                double radius, double w, bool vec) {
+                double radius, double w, bool vec, const double* __restrict__ z_cm_dev = nullptr) {
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
   double2 p;
   if (SPHERE) {
+    if (z_cm_dev) z_cm = *z_cm_dev;
     const double dr = r1d[j] - r_cm;
     const double za = z1d[k] - z_cm, zb = z1d[(k + 1 < g.nz) ? k + 1 : k] - z_cm;
     const double da = za * za + dr * dr, db = zb * zb + dr * dr;
@@ -675,6 +676,16 @@ int axb_smooth_heaviside_sphere(const axb_grid_t* g, double* H, double* phi_out,
   if (!H || !z1d || !r1d) return AXB_EINVAL;
   GRID_PROLOGUE(H, phi_out)
   k_heaviside<true><<<grd, blk, 0, s>>>(d, H, phi_out, nullptr, z1d, r1d, z_cm, r_cm, radius, blend_w, vec);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_smooth_heaviside_sphere_dev(const axb_grid_t* g, double* H, double* phi_out, const double* z1d,
+                                    const double* r1d, const double* z_cm_dev, double r_cm, double radius,
+                                    double blend_w, axb_stream_t s) {
+  if (!H || !z1d || !r1d || !z_cm_dev) return AXB_EINVAL;
+  GRID_PROLOGUE(H, phi_out)
+  k_heaviside<true><<<grd, blk, 0, s>>>(d, H, phi_out, nullptr, z1d, r1d, 0.0, r_cm, radius, blend_w, vec, z_cm_dev);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

@@ -267,16 +267,39 @@ class HostStepPipeline:
 
 
 class _FieldSet:
-    """small helper: float64 CUDA fields of one (nr, nz) grid plus the ctypes grid descriptor"""
+    """small helper: float64 CUDA fields of one (nr, nz) grid plus the ctypes grid descriptor.  With a ``pool``
+    (:class:`_WidePool`) the fields are this member's column blocks of (nr, batch nz) tensors shared by an
+    ensemble, so the row pitch is batch nz."""
 
-    def __init__(self, nr, nz, dx):
+    def __init__(self, nr, nz, dx, pool=None, member=0):
         self.nr, self.nz, self.dx = nr, nz, dx
-        self.grid = make_grid(nr, nz, nz, dx)
+        self.pool, self.member, self._n = pool, member, 0
+        self.grid = make_grid(nr, nz, nz if pool is None else pool.batch * nz, dx)
         self.g = ctypes.byref(self.grid)
 
     def new(self, n=1):
-        f = [torch.zeros((self.nr, self.nz), dtype=torch.float64, device="cuda") for _ in range(n)]
+        if self.pool is None:
+            f = [torch.zeros((self.nr, self.nz), dtype=torch.float64, device="cuda") for _ in range(n)]
+        else:
+            f = [self.pool.view(self._n + i, self.member) for i in range(n)]
+            self._n += n
         return f[0] if n == 1 else f
+
+
+class _WidePool:
+    """Storage of a batched ensemble (SURVEY.md 8e "Ensemble"): field i of all members lives in ONE (nr, batch nz)
+    tensor, member m owning the columns [m nz, (m+1) nz).  Every per-member kernel sees an ordinary (nr, nz) field of
+    pitch batch nz; the solve sees (batch nr) rows of nz doubles for the z transforms -- element (j, m nz + k) is
+    row 8 j + m -- and batch nz independent columns for the r sweeps, so one launch serves all members."""
+
+    def __init__(self, nr, nz, batch):
+        self.nr, self.nz, self.batch = nr, nz, batch
+        self.wide = []
+
+    def view(self, i, member):
+        while len(self.wide) <= i:
+            self.wide.append(torch.zeros((self.nr, self.batch * self.nz), dtype=torch.float64, device="cuda"))
+        return self.wide[i][:, member * self.nz:(member + 1) * self.nz]
 
 
 class SoftSphereStepper:
@@ -425,13 +448,14 @@ class ParticleFlowStepper:
     Members of an ensemble on one GPU share the solver factors (``solver=``)."""
 
     def __init__(self, grid_size_z=400, domain_AR=0.5, grid_size_r=None, freq=8.0, e=0.01, lambda_part=20.0,
-                 r0_bubble=0.25, rp=2.0, brink_lam=1e12, CFL=0.1, rho_f=1.0, rho_s=1.0, solver=None, basis="auto"):
+                 r0_bubble=0.25, rp=2.0, brink_lam=1e12, CFL=0.1, rho_f=1.0, rho_s=1.0, solver=None, basis="auto",
+                 device_scalars=False, use_graph=False, trace_capacity=4096, _pool=None, _member=0):
         if not torch.cuda.is_available():
             raise _lib.AxbError("ParticleFlowStepper needs a CUDA device (no CPU fallback)")
         nz = int(grid_size_z)
         nr = int(grid_size_r) if grid_size_r is not None else int(domain_AR * nz)
         dx = 1.0 / nz
-        self.F = F = _FieldSet(nr, nz, dx)
+        self.F = F = _FieldSet(nr, nz, dx, _pool, _member)
         self.nr, self.nz, self.dx = nr, nz, dx
         self.CFL, self.brink_lam, self.rho_f, self.rho_s = CFL, brink_lam, rho_f, rho_s
         self.moll_zone = np.sqrt(2) * dx
@@ -456,12 +480,22 @@ class ParticleFlowStepper:
         _call("axb_smooth_heaviside_sphere", F.g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d),
               self.part_Z_cm, self.part_R_cm, self.r_part, self.moll_zone, s)
         self._acc = torch.zeros(2, dtype=torch.float64, device="cuda")
-        ones = torch.ones((nr, nz), dtype=torch.float64, device="cuda")
+        ones = F.new(1) if _pool is not None else torch.empty((nr, nz), dtype=torch.float64, device="cuda")
+        ones.fill_(1.0)
         _call("axb_reduce_weighted_sum", F.g, ptr(self.r1d), ptr(self.part_char_func), ptr(ones), 0.0, ptr(self._acc), s)
         self.part_vol = float(self._acc[0])          # np.sum(part_char_func * R)
         self.part_mass = rho_s * self.part_vol
         del ones
         self.solver = solver if solver is not None else FastDiagonalisationStokesSolver(nr, nz, dx, basis=basis)
+        # device-resident loop scalars (include/axisym_b200.h, axb_particle_scalars): no host round trip per step
+        self.device_scalars = bool(device_scalars)
+        self._use_graph = bool(use_graph) and self.device_scalars
+        self._graph = None
+        if self.device_scalars:
+            self.state = torch.zeros(24, dtype=torch.float64, device="cuda")
+            self.state[6] = self.part_Z_cm
+            self.trace_dev = torch.zeros((int(trace_capacity), 5), dtype=torch.float64, device="cuda")
+            self.avg_psi_last, self.avg_vort_last, self.avg_part_char_func_last = F.new(3)
         self.t, self.it, self.dt = 0.0, 0, 0.0
         # per-cycle averages (particle_in_bubble_oscillatory_flow.py:102-109, 168-263, 297-301, 355)
         self.freqTimer, self.avg_Z_cm, self.avg_time = 0.0, 0.0, 0.0
@@ -472,8 +506,95 @@ class ParticleFlowStepper:
         self.trace = []       # per step: (t, dt, U_z_cm_part, part_Z_cm, F_total) at the start of the step
 
     def step(self, n=1):
+        if self.device_scalars:
+            if not self._use_graph:
+                for _ in range(n):
+                    self._one_dev()
+                return
+            if self._graph is None:
+                self._one_dev()                      # warm-up outside capture
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._one_dev()
+                n -= 1
+            for _ in range(n):
+                self._graph.replay()
+            return
         for _ in range(n):
             self._one()
+
+    # ---- device-resident form: the same kernels, every host decision replaced by axb_particle_scalars ------------
+    def _sp(self, i):
+        return ctypes.c_void_p(self.state.data_ptr() + 8 * i)
+
+    def _scalars_dev(self, phase):
+        dx = self.dx
+        _call("axb_particle_scalars", phase, ptr(self.state), ptr(self.trace_dev), self.trace_dev.shape[0],
+              0.9 * dx ** 2 / 4 / self.nu, self.CFL, self.eps, self.freqTimer_limit, self.omega,
+              self.rho_f * self.brink_lam, self.part_vol, self.part_mass, self.bubble_Z_cm, self.r0_bubble, stream_ptr())
+
+    def _enqueue_dev_pre(self):
+        s, g = stream_ptr(), self.F.g
+        w = self.vorticity
+        _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
+        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
+
+    def _enqueue_dev_solve(self):
+        ld = self.vorticity.stride(0)
+        _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ptr(self.psi), ld, ptr(self.vorticity), ld, stream_ptr())
+
+    def _enqueue_dev_post(self):
+        s, g, sp = stream_ptr(), self.F.g, self._sp
+        w = self.vorticity
+        _call("axb_velocity_from_psi", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.psi), ptr(self.r1d), 0.0, 0.0,
+              None, None, s)
+        _call("axb_reduce_max_abs_sum", g, ptr(w), None, sp(2), s)         # state[2] was zeroed by phase 2
+        self._scalars_dev(1)
+        _call("axb_add_bubble_flow_dev", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_char_func),
+              ptr(self.z1d), ptr(self.r1d), self.bubble_Z_cm, self.bubble_R_cm, self.r0_bubble, self.U_0, sp(9), s)
+        _call("axb_cycle_average3", g, ptr(self.avg_part_char_func), ptr(self.part_char_func),
+              ptr(self.avg_part_char_func_last), ptr(self.avg_psi), ptr(self.psi), ptr(self.avg_psi_last),
+              ptr(self.avg_vort), ptr(w), ptr(self.avg_vort_last), sp(10), sp(15), s)
+        _call("axb_smooth_heaviside_sphere_dev", g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d), sp(6),
+              self.part_R_cm, self.r_part, self.moll_zone, s)
+        _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
+              ptr(self.u_r_upen), ptr(self.part_char_func), self.brink_lam, 0.0, sp(1), 0.0, 0.0, sp(4), ptr(self.r1d),
+              sp(3), s)
+        _call("axb_advect_vorticity_particles", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), ptr(self.z1d),
+              ptr(self.rl_double), 0.0, sp(1), 0, s)
+        # RK2 diffusion lands the result back in `vorticity` (stage 2 takes its base field from _w2): no buffer swap,
+        # so the launch sequence is the same every step and can be replayed as a CUDA graph
+        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(self._w2), ptr(self.r1d), self.nu, 0.0, sp(1), s)
+        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(self._w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0, sp(1), s)
+        self._scalars_dev(2)
+
+    def _one_dev(self):
+        self._enqueue_dev_pre()
+        self._enqueue_dev_solve()
+        self._enqueue_dev_post()
+
+    def sync_scalars(self):
+        """device mode: copy the loop scalars (and the trace rows written so far) to the host attributes the host
+        mode keeps (one synchronising D2H; call it when a value is wanted, at least once per oscillation cycle if the
+        per-cycle lists ``avg_T`` / ``avg_part_trajectory`` are wanted complete)"""
+        if not self.device_scalars:
+            return self
+        st = self.state.cpu().numpy()
+        self.t, self.dt, self.U_z_cm_part, self.part_Z_cm, self.F_total = st[0], st[1], st[4], st[6], st[7]
+        self.it, self.freqTimer, self.avg_Z_cm, self.avg_time, self.diff = int(st[8]), st[11], st[12], st[13], st[16]
+        if int(st[14]) > self.cycles:
+            self.cycles = int(st[14])
+            self.avg_T.append(float(st[17]))
+            self.avg_part_trajectory.append(float(st[18]))
+        cap = self.trace_dev.shape[0]
+        rows = self.trace_dev[:min(self.it, cap)].cpu().numpy()
+        if self.it > cap:                            # the ring has wrapped: oldest kept row first
+            rows = np.roll(rows, -(self.it % cap), axis=0)
+        self.trace = [tuple(r) for r in rows]
+        return self
 
     # One step = three pieces, so that an ensemble can interleave its members (ParticleEnsemble): everything up to
     # the first host decision (dt needs the vorticity maximum), everything that needs dt, and the rigid-body update
@@ -552,6 +673,33 @@ class ParticleFlowStepper:
         self._finish(float(self._acc[1]))
 
 
+class _BatchedFdSolver:
+    """One fast-diagonalisation solve for all members of a :class:`_WidePool` ensemble (cosine-transform z path +
+    tridiagonal r path): DCT-II over batch nr rows, factored sweeps over batch nz columns (the pivots of the nz
+    z-modes tiled batch times), DCT-III -- 3 + 1 launches whatever the ensemble size, and the r sweeps, which march
+    row by row and are latency bound on a single 2048-column member, get batch times the columns."""
+
+    def __init__(self, nr, nz, batch, factors):
+        f, tri = factors, factors["tri"]
+        self.nr, self.nz, self.batch, self.tables = nr, nz, batch, f["zfft"]["tables"]
+        dev = f["lam_z"].device
+        lam = f["lam_z"].repeat(batch).contiguous()
+        cols = batch * nz
+        self.inv = torch.empty((nr, cols), dtype=torch.float64, device=dev)
+        self.rc = torch.empty((nr, 4), dtype=torch.float64, device=dev)
+        _call("axb_tridiag_factor_columns", nr, cols, ptr(tri["sub"]), ptr(tri["diag"]), ptr(tri["sup"]), ptr(lam),
+              ptr(tri["scale"]), float(f["c0"]), float(f["c1"]), ptr(self.inv), ptr(self.rc), stream_ptr())
+        self.spec = torch.empty((nr, cols), dtype=torch.float64, device=dev)
+
+    def solve(self, psi_wide, rhs_wide):
+        nr, nz, b = self.nr, self.nz, self.batch
+        s = stream_ptr()
+        rows = b * nr
+        _call("axb_dct2_rows", rows, nz, ptr(rhs_wide), nz, ptr(self.spec), nz, ptr(self.tables), 1.0 / nz, 2.0 / nz, s)
+        _call("axb_tridiag_solve_factored", nr, b * nz, ptr(self.spec), b * nz, ptr(self.inv), ptr(self.rc), s)
+        _call("axb_dct3_rows", rows, nz, ptr(self.spec), nz, ptr(psi_wide), nz, ptr(self.tables), s)
+
+
 class ParticleEnsemble:
     """Config C5 (SURVEY.md 8e "Ensemble"): independent ``ParticleFlowStepper`` members on one GPU, no communication.
 
@@ -565,6 +713,7 @@ class ParticleEnsemble:
 
     def __init__(self, members):
         self.members = list(members)
+        self.batched = False
         first = self.members[0].solver
         for i, m in enumerate(self.members):
             if i > 0 and m.solver is first:
@@ -572,7 +721,76 @@ class ParticleEnsemble:
         self.streams = [torch.cuda.Stream() for _ in self.members]
         self._pending = [False] * len(self.members)
 
+    @classmethod
+    def batched_ensemble(cls, params, grid_size_z, grid_size_r=None, use_graph=True, branches=4, solver=None, **kw):
+        """SURVEY.md 8e "Ensemble": ``params`` = [(freq, e), ...]; all members share one set of (nr, batch nz) field
+        tensors (:class:`_WidePool`), keep their loop scalars on the device, and one step of the WHOLE ensemble is a
+        fixed launch sequence -- per-member boundary damping, ONE solve for all members (z transforms over batch nr
+        rows, r sweeps over batch nz columns), the per-member rest on `branches` parallel graph branches -- captured
+        once and replayed.  No host round trip, no per-member solve."""
+        nz = int(grid_size_z)
+        nr = int(grid_size_r) if grid_size_r is not None else int(kw.get("domain_AR", 0.5) * nz)
+        pool = _WidePool(nr, nz, len(params))
+        members = []
+        for i, (f, e) in enumerate(params):
+            m = ParticleFlowStepper(nz, grid_size_r=nr, freq=f, e=e, solver=solver, device_scalars=True,
+                                    _pool=pool, _member=i, **kw)
+            solver = m.solver
+            members.append(m)
+        self = cls.__new__(cls)
+        self.members, self.batched, self.pool = members, True, pool
+        self._use_graph, self._graph, self._branches = bool(use_graph), None, max(1, int(branches))
+        self._solver = _BatchedFdSolver(nr, nz, len(params), solver.factors) if solver.factors.get("zfft") is not None \
+            and solver.factors.get("tri") is not None else None
+        self._w_wide = pool.wide[0]        # field 0 = vorticity, field 1 = psi (ParticleFlowStepper's F.new order)
+        self._psi_wide = pool.wide[1]
+        self._side = [torch.cuda.Stream() for _ in range(self._branches)]
+        return self
+
+    def _enqueue_batched(self):
+        for m in self.members:
+            m._enqueue_dev_pre()
+        if self._solver is not None:
+            self._solver.solve(self._psi_wide, self._w_wide)
+        else:
+            for m in self.members:
+                m._enqueue_dev_solve()
+        cur = torch.cuda.current_stream()
+        if self._branches == 1:
+            for m in self.members:
+                m._enqueue_dev_post()
+            return
+        for st in self._side:
+            st.wait_stream(cur)
+        for i, m in enumerate(self.members):
+            with torch.cuda.stream(self._side[i % self._branches]):
+                m._enqueue_dev_post()
+        for st in self._side:
+            cur.wait_stream(st)
+
+    def sync_scalars(self):
+        for m in self.members:
+            m.sync_scalars()
+        return self
+
     def step(self, n=1):
+        if self.batched:
+            if not self._use_graph:
+                for _ in range(n):
+                    self._enqueue_batched()
+                return
+            if self._graph is None:
+                self._enqueue_batched()              # warm-up outside capture
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._enqueue_batched()
+                n -= 1
+            for _ in range(n):
+                self._graph.replay()
+            return
         cur = torch.cuda.current_stream()
         for st in self.streams:
             st.wait_stream(cur)

@@ -19,6 +19,11 @@ elif which == "c4":
     s.t = 0.0
 elif which == "c3":
     s = SoftSphereStepper(8192, grid_size_r=2048, Z_cm=0.47, reinit_levelset=True)
+elif which == "c5b":                                  # the batched, device-resident 8-member ensemble (eager launches)
+    from pyaxisymflow_b200.timestep import ParticleEnsemble
+    freqs = [4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0, 32.0]
+    s = ParticleEnsemble.batched_ensemble([(f, 0.01) for f in freqs], 2048, 1024, use_graph=False)
+    s.t = 0.0
 else:
     s = ParticleFlowStepper(2048, grid_size_r=1024)
 torch.cuda.synchronize()
