@@ -404,10 +404,12 @@ class _ConfigRunner:
             params = [(8.0, 0.01)] + [(freqs[i % 8], 0.005 * (1 + (i // 8) % 8)) for i in range(1, cases)]
             self.cases = cases
             mode = os.environ.get("AXB_ENSEMBLE", "batched")
-            if mode == "batched":
-                # SURVEY 8e "Ensemble": one (nr, cases nz) tensor per field, one solve for all members, loop scalars
-                # on the device, the whole ensemble step replayed as one CUDA graph
-                self.ensemble = ParticleEnsemble.batched_ensemble(params, nz, nr, use_graph=True, basis=basis)
+            if mode in ("batched", "members"):
+                # SURVEY 8e "Ensemble": one (nr, cases nz) tensor per field, every operation ONE launch over all
+                # members (axb_grid_t.batch), one solve for all members, loop scalars on the device, the whole ensemble
+                # step replayed as one CUDA graph ("members": one launch per member and operation instead)
+                self.ensemble = ParticleEnsemble.batched_ensemble(params, nz, nr, use_graph=True, basis=basis,
+                                                                  launch=mode)
                 self.members = self.ensemble.members
             else:
                 first = ParticleFlowStepper(nz, grid_size_r=nr, basis=basis, freq=params[0][0], e=params[0][1])

@@ -41,7 +41,13 @@ typedef struct CUstream_st* axb_stream_t;
  * rank's left halo), and [ku0, ku1) is the locally owned range the kernel may write.
  * Under r-slab (row) decomposition every rank's (owned + halo rows, nz) block is an ordinary field for the
  * kernels (r1d holds the block's own radii); [ju0, ju1) are the OWNED rows, the only ones that count in the
- * fused reductions (CFL maximum, drag sum).  ju1 == 0 means all rows (single GPU, z-slabs). */
+ * fused reductions (CFL maximum, drag sum).  ju1 == 0 means all rows (single GPU, z-slabs).
+ * Ensembles: batch > 1 describes `batch` independent members of the same shape whose fields
+ * lie batch_stride ELEMENTS apart (member m of a field = pointer + m * batch_stride; batch_stride = nz for members
+ * stored as column blocks of one (nr, batch nz) array with ld = batch nz) and whose device-resident scalars
+ * (dt_dev, U_dev, reduction targets, ...) lie scalar_stride doubles apart.  One launch then serves every member
+ * (the member index is the grid's z dimension); the 1-D coordinate arrays are shared.  Entries that are not
+ * documented as "batched" refuse batch > 1 with AXB_ENOSUP.  batch = 0 or 1: a single field. */
 typedef struct axb_grid {
   int32_t nr;
   int32_t nz;
@@ -53,6 +59,9 @@ typedef struct axb_grid {
   int32_t ku1;
   int32_t ju0;
   int32_t ju1;
+  int32_t batch;
+  int32_t scalar_stride;
+  int64_t batch_stride;
 } axb_grid_t;
 
 int axb_version(void);
@@ -147,6 +156,12 @@ int axb_diffusion_rk2_stage1(const axb_grid_t* g, double* tmp, const double* w, 
 int axb_diffusion_rk2_stage2(const axb_grid_t* g, double* w, const double* w_src, const double* tmp,
                              const double* r1d, double nu, double dt, const double* dt_dev,
                              axb_stream_t s);
+/* The same two stages with nu AND dt read from device memory (batched: member m reads nu_dev[m scalar_stride],
+ * dt_dev[m scalar_stride]) -- the members of a particle ensemble differ in nu. */
+int axb_diffusion_rk2_stage1_dev(const axb_grid_t* g, double* tmp, const double* w, const double* r1d,
+                                 const double* nu_dev, const double* dt_dev, axb_stream_t s);
+int axb_diffusion_rk2_stage2_dev(const axb_grid_t* g, double* w, const double* w_src, const double* tmp,
+                                 const double* r1d, const double* nu_dev, const double* dt_dev, axb_stream_t s);
 /* Both stages in one pass over HBM (16 instead of 40 B/pt): w = w_src + nu dt L(tmp), tmp = w_src + nu dt/2
  * L(w_src) held on chip (row-marching kernels; needs a width-2 halo of w_src on z-slabs).  Same bits as
  * stage1 followed by stage2.  tmp is only used (as scratch) by the 2-D tiled code path; w != w_src. */
@@ -242,7 +257,11 @@ int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const dou
  *      a ring of trace_cap rows (t, dt, U_z_cm_part, part_Z_cm, F_total) written at the start-of-step values.
  *      axb_cycle_average3 = the three running averages of :297-299 in one pass, restarted (completed averages kept in
  *      last_i, may be NULL) when state[15] is set.  The _dev forms of the bubble flow and the sphere Heaviside read
- *      sin(omega t) / the sphere's z centre from device memory. ------------------------------------------------ */
+ *      sin(omega t) (and U_0, if U_0_dev is given) / the sphere's z centre from device memory.
+ *      Batched (axb_grid_t.batch > 1, one launch for every member of an ensemble): axb_kill_boundary_vorticity_sine_z/_r,
+ *      axb_velocity_from_psi, axb_reduce_max_abs_sum, axb_add_bubble_flow_dev, axb_cycle_average3,
+ *      axb_smooth_heaviside_sphere_dev, axb_penalise_update_vorticity, axb_advect_vorticity_particles,
+ *      axb_diffusion_rk2_stage1/2(_dev) -- the row-marching stencil path only. ---------------------------------- */
 int axb_particle_scalars(int phase, double* state, double* trace, int trace_cap, double dt_diff_limit, double cfl,
                          double eps, double cycle, double omega, double rho_lam, double part_vol, double part_mass,
                          double bubble_z_cm, double r0_bubble, axb_stream_t s);
@@ -251,7 +270,15 @@ int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, doub
                        const double* wrap_dev, axb_stream_t s);
 int axb_add_bubble_flow_dev(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
                             const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
-                            double r0_bubble, double U_0, const double* sin_omega_t_dev, axb_stream_t s);
+                            double r0_bubble, double U_0, const double* U_0_dev, const double* sin_omega_t_dev,
+                            axb_stream_t s);
+/* One launch for all members of an ensemble (batched): member m's scalar block is state + m scalar_stride
+ * (scalar_stride >= 24) and additionally holds the constants that differ between members,
+ *   [19] omega  [20] cycle time  [21] U_0  [22] nu  [23] diffusive dt limit,
+ * its trace ring is trace + m 5 trace_cap. */
+int axb_particle_scalars_batched(int phase, int batch, int scalar_stride, double* state, double* trace, int trace_cap,
+                                 double cfl, double eps, double rho_lam, double part_vol, double part_mass,
+                                 double bubble_z_cm, double r0_bubble, axb_stream_t s);
 int axb_smooth_heaviside_sphere_dev(const axb_grid_t* g, double* H, double* phi_out, const double* z1d,
                                     const double* r1d, const double* z_cm_dev, double r_cm, double radius,
                                     double blend_w, axb_stream_t s);

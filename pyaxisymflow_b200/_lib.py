@@ -21,7 +21,8 @@ class AxbError(RuntimeError):
 class AxbGrid(Structure):
     _fields_ = [("nr", c_int32), ("nz", c_int32), ("ld", c_int64), ("dx", c_double),
                 ("kz0", c_int32), ("nz_global", c_int32), ("ku0", c_int32), ("ku1", c_int32),
-                ("ju0", c_int32), ("ju1", c_int32)]
+                ("ju0", c_int32), ("ju1", c_int32),
+                ("batch", c_int32), ("scalar_stride", c_int32), ("batch_stride", c_int64)]
 
 
 class AxbFdPlan(Structure):
@@ -83,7 +84,10 @@ _SIGNATURES = {
     "axb_pin_level_set": [_G, _P, _P, _P, _P, _D, _D, _D, _D, _S],
     "axb_smooth_heaviside_mask": [_G, _P, _P, _P, _D, _D, _I, _S],
     "axb_add_bubble_flow": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D, _S],
-    "axb_add_bubble_flow_dev": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _S],
+    "axb_add_bubble_flow_dev": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _S],
+    "axb_particle_scalars_batched": [_I, _I, _I, _P, _P, _I, _D, _D, _D, _D, _D, _D, _D, _S],
+    "axb_diffusion_rk2_stage1_dev": [_G, _P, _P, _P, _P, _P, _S],
+    "axb_diffusion_rk2_stage2_dev": [_G, _P, _P, _P, _P, _P, _P, _S],
     "axb_smooth_heaviside_sphere_dev": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _S],
     "axb_particle_scalars": [_I, _P, _P, _I, _D, _D, _D, _D, _D, _D, _D, _D, _D, _D, _S],
     "axb_cycle_average3": [_G, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S],

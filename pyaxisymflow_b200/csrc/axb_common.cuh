@@ -24,6 +24,18 @@ static inline int axb_check_grid(const axb_grid_t* g) {
   if (g->ku0 < 0 || g->ku1 > g->nz || g->ku0 > g->ku1) return AXB_EINVAL;
   if (g->nz_global < 1) return AXB_EINVAL;
   if (g->ju1 != 0 && (g->ju0 < 0 || g->ju1 > g->nr || g->ju0 > g->ju1)) return AXB_EINVAL;
+  if (g->batch > 1) return AXB_ENOSUP;       // batched entries validate with axb_check_grid_batched
+  return AXB_OK;
+}
+// for the entries that serve an ensemble with one launch (member index = blockIdx.z)
+static inline int axb_check_grid_batched(const axb_grid_t* g) {
+  if (!g) return AXB_EINVAL;
+  if (g->batch <= 1) return axb_check_grid(g);
+  axb_grid_t one = *g;
+  one.batch = 0;
+  const int rc = axb_check_grid(&one);
+  if (rc) return rc;
+  if (g->batch > 65535 || g->batch_stride < g->nz || g->scalar_stride < 0) return AXB_EINVAL;
   return AXB_OK;
 }
 static inline bool axb_al8(const void* p) { return (((uintptr_t)p) & 7u) == 0; }
@@ -36,20 +48,33 @@ struct GridD {
   double dx;
   int kz0, nzg, ku0, ku1;
   int ju0, ju1;      // owned rows: the ones fused reductions count
+  int batch, sstride;   // ensemble members per launch (>= 1), doubles between their device scalars
+  long long bstride;    // elements between the members' fields
 };
 static inline GridD to_dev(const axb_grid_t* g) {
   GridD d;
   d.nr = g->nr; d.nz = g->nz; d.ld = g->ld; d.dx = g->dx;
   d.kz0 = g->kz0; d.nzg = g->nz_global; d.ku0 = g->ku0; d.ku1 = g->ku1;
   d.ju0 = g->ju1 ? g->ju0 : 0; d.ju1 = g->ju1 ? g->ju1 : g->nr;
+  d.batch = g->batch > 1 ? g->batch : 1;
+  d.sstride = g->batch > 1 ? g->scalar_stride : 0;
+  d.bstride = g->batch > 1 ? g->batch_stride : 0;
   return d;
 }
+#ifdef __CUDACC__
+// Batched launches: blockIdx.z is the ensemble member.  A kernel moves its field pointers by member_field(g)
+// elements and its device-scalar pointers by member_scalar(g) doubles (both 0 for a single field); null stays null.
+__device__ __forceinline__ long long member_field(const GridD& g) { return (long long)blockIdx.z * g.bstride; }
+__device__ __forceinline__ int member_scalar(const GridD& g) { return (int)blockIdx.z * g.sstride; }
+template <class T>
+__device__ __forceinline__ T* moved(T* p, long long o) { return p ? p + o : p; }
+#endif
 
 // 2 columns per thread, (32 x 8) threads per block: a block covers 64 columns x 8 rows.
 constexpr int TBX = 32, TBY = 8;
 static inline dim3 grid2d(const GridD& g) {
   const int kpairs = (g.nz + 1) / 2;
-  return dim3((kpairs + TBX - 1) / TBX, (g.nr + TBY - 1) / TBY, 1);
+  return dim3((kpairs + TBX - 1) / TBX, (g.nr + TBY - 1) / TBY, g.batch);
 }
 
 // (f[k], f[k+1]) of one row; 128-bit load when the row is 16-byte aligned, k even and

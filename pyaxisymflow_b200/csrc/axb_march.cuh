@@ -8,7 +8,7 @@ int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const do
                    const double* chi, double lam, double dt, const double* dt_dev, double U_z, double U_r,
                    const double* U_dev, const double* r1d, double* sum_out, bool vec, cudaStream_t s);
 int march_diffusion(int stage, const GridD& d, double* out, const double* in, const double* src2, const double* r1d,
-                    double nu, double dt, const double* dt_dev, bool vec, cudaStream_t s);
+                    double nu, const double* nu_dev, double dt, const double* dt_dev, bool vec, cudaStream_t s);
 int march_diffusion_fused(const GridD& d, double* out, const double* in, const double* r1d, double nu, double dt,
                           const double* dt_dev, bool vec, cudaStream_t s);
 int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, double* out0, double* out1,

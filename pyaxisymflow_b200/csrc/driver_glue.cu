@@ -12,7 +12,7 @@ namespace {
 __device__ __forceinline__ const double* rowp(const double* f, long long ld, int j) { return f + (long long)j * ld; }
 __device__ __forceinline__ double* rowp(double* f, long long ld, int j) { return f + (long long)j * ld; }
 inline bool vec_ok(const GridD& g, std::initializer_list<const void*> ptrs) {
-  if (g.ld & 1) return false;
+  if ((g.ld & 1) || (g.bstride & 1)) return false;
   for (const void* p : ptrs)
     if (p && !axb_al16(p)) return false;
   return true;
@@ -72,11 +72,16 @@ __global__ void k_heav_mask(GridD g, double* __restrict__ H, unsigned char* __re
 __global__ void __launch_bounds__(TBX* TBY)
     k_bubble(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ chi_b,
              const double* __restrict__ z1d, const double* __restrict__ r1d, double bz, double br, double r0, double U0,
-             double s, const double* __restrict__ s_dev, bool vec) {
+             double s, const double* __restrict__ s_dev, const double* __restrict__ U0_dev, bool vec) {
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
-  if (s_dev) s = *s_dev;
+  {
+    const long long fo = member_field(g);
+    u_z += fo; u_r += fo; chi_b += fo;
+  }
+  if (s_dev) s = s_dev[member_scalar(g)];
+  if (U0_dev) U0 = U0_dev[member_scalar(g)];
   const double2 c = ld_pair(rowp(chi_b, g.ld, j), k, g.nz, vec);
   double2 uz = ld_pair(rowp(u_z, g.ld, j), k, g.nz, vec), ur = ld_pair(rowp(u_r, g.ld, j), k, g.nz, vec);
   const double dr = r1d[j] - br;
@@ -108,19 +113,20 @@ __global__ void __launch_bounds__(TBX* TBY)
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
-  const double a = *a_dev;
-  const bool wrap = *wrap_dev != 0.0;
+  const double a = a_dev[member_scalar(g)];
+  const bool wrap = wrap_dev[member_scalar(g)] != 0.0;
+  const long long fo = member_field(g);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double2 xv = ld_pair(rowp(f.x[i], g.ld, j), k, g.nz, vec);
-    double2 yv = ld_pair(rowp(f.avg[i], g.ld, j), k, g.nz, vec);
+    const double2 xv = ld_pair(rowp(f.x[i] + fo, g.ld, j), k, g.nz, vec);
+    double2 yv = ld_pair(rowp(f.avg[i] + fo, g.ld, j), k, g.nz, vec);
     if (wrap) {
-      if (f.last[i]) st_pair(rowp(f.last[i], g.ld, j), k, g.ku0, g.ku1, vec, yv);
+      if (f.last[i]) st_pair(rowp(f.last[i] + fo, g.ld, j), k, g.ku0, g.ku1, vec, yv);
       yv = make_double2(0.0, 0.0);
     }
     yv.x = yv.x + xv.x * a;
     yv.y = yv.y + xv.y * a;
-    st_pair(rowp(f.avg[i], g.ld, j), k, g.ku0, g.ku1, vec, yv);
+    st_pair(rowp(f.avg[i] + fo, g.ld, j), k, g.ku0, g.ku1, vec, yv);
   }
 }
 
@@ -129,11 +135,22 @@ __global__ void __launch_bounds__(TBX* TBY)
 //   st[0] t, [1] dt, [2] max|w| (reduction target), [3] penalisation sum (reduction target), [4] U_z_cm_part,
 //   [5] 0 (U_r), [6] part_Z_cm, [7] F_total, [8] it, [9] sin(omega t), [10] dt / cycle, [11] freqTimer, [12] avg_Z_cm,
 //   [13] avg_time, [14] cycles, [15] wrap flag of this step, [16] diff, [17] last avg_T, [18] last avg trajectory point
+//   [19] omega  [20] cycle time  [21] U_0  [22] nu  [23] diffusive dt limit: the constants that differ between the
+//   members of an ensemble; read from the block instead of the by-value parameters when `member_consts` is set.
+// One block per ensemble member: member m's scalars are st + m * stride, its trace ring trace + m * 5 * trace_cap.
 struct ParticleParams {
   double dt_diff, cfl, eps, cycle, omega, rho_lam, part_vol, part_mass, bubble_z, r0;
 };
-__global__ void k_particle_scalars(int phase, double* st, double* trace, int trace_cap, ParticleParams p) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_particle_scalars(int phase, double* st, double* trace, int trace_cap, ParticleParams p, int stride,
+                                   int member_consts) {
+  if (threadIdx.x != 0) return;
+  st += (long long)blockIdx.x * stride;
+  if (trace) trace += (long long)blockIdx.x * 5 * trace_cap;
+  if (member_consts) {
+    p.omega = st[19];
+    p.cycle = st[20];
+    p.dt_diff = st[23];
+  }
   if (phase == 1) {
     double wrap = 0.0;
     if (st[11] >= p.cycle) {
@@ -182,7 +199,7 @@ int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, doub
                        double* last1, double* avg2, const double* x2, double* last2, const double* a_dev,
                        const double* wrap_dev, axb_stream_t s) {
   if (!avg0 || !x0 || !avg1 || !x1 || !avg2 || !x2 || !a_dev || !wrap_dev) return AXB_EINVAL;
-  int rc = axb_check_grid(g);
+  int rc = axb_check_grid_batched(g);
   if (rc) return rc;
   const GridD d = to_dev(g);
   Avg3 f;
@@ -200,7 +217,16 @@ int axb_particle_scalars(int phase, double* state, double* trace, int trace_cap,
                          double bubble_z_cm, double r0_bubble, axb_stream_t s) {
   if (!state || (phase != 1 && phase != 2) || trace_cap < 0) return AXB_EINVAL;
   const ParticleParams p = {dt_diff_limit, cfl, eps, cycle, omega, rho_lam, part_vol, part_mass, bubble_z_cm, r0_bubble};
-  k_particle_scalars<<<1, 32, 0, s>>>(phase, state, trace, trace_cap, p);
+  k_particle_scalars<<<1, 32, 0, s>>>(phase, state, trace, trace_cap, p, 0, 0);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+int axb_particle_scalars_batched(int phase, int batch, int scalar_stride, double* state, double* trace, int trace_cap,
+                                 double cfl, double eps, double rho_lam, double part_vol, double part_mass,
+                                 double bubble_z_cm, double r0_bubble, axb_stream_t s) {
+  if (!state || (phase != 1 && phase != 2) || trace_cap < 0 || batch < 1 || scalar_stride < 24) return AXB_EINVAL;
+  const ParticleParams p = {0.0, cfl, eps, 0.0, 0.0, rho_lam, part_vol, part_mass, bubble_z_cm, r0_bubble};
+  k_particle_scalars<<<batch, 32, 0, s>>>(phase, state, trace, trace_cap, p, scalar_stride, 1);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
@@ -241,13 +267,13 @@ int axb_smooth_heaviside_mask(const axb_grid_t* g, double* H, uint8_t* mask, con
 
 static int bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func, const double* z1d,
                        const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble, double U_0,
-                       double sin_omega_t, const double* sin_dev, axb_stream_t s) {
+                       double sin_omega_t, const double* sin_dev, const double* U0_dev, axb_stream_t s) {
   if (!u_z || !u_r || !bubble_char_func || !z1d || !r1d) return AXB_EINVAL;
-  int rc = axb_check_grid(g);
+  int rc = sin_dev ? axb_check_grid_batched(g) : axb_check_grid(g);
   if (rc) return rc;
   const GridD d = to_dev(g);
   k_bubble<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm,
-                                              r0_bubble, U_0, sin_omega_t, sin_dev,
+                                              r0_bubble, U_0, sin_omega_t, sin_dev, U0_dev,
                                               vec_ok(d, {u_z, u_r, bubble_char_func}));
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
@@ -256,14 +282,15 @@ int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const dou
                         const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm, double r0_bubble,
                         double U_0, double sin_omega_t, axb_stream_t s) {
   return bubble_flow(g, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm, r0_bubble, U_0, sin_omega_t,
-                     nullptr, s);
+                     nullptr, nullptr, s);
 }
 int axb_add_bubble_flow_dev(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
                             const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
-                            double r0_bubble, double U_0, const double* sin_omega_t_dev, axb_stream_t s) {
+                            double r0_bubble, double U_0, const double* U_0_dev, const double* sin_omega_t_dev,
+                            axb_stream_t s) {
   if (!sin_omega_t_dev) return AXB_EINVAL;
   return bubble_flow(g, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm, r0_bubble, U_0, 0.0,
-                     sin_omega_t_dev, s);
+                     sin_omega_t_dev, U_0_dev, s);
 }
 
 }  // extern "C"

@@ -340,7 +340,11 @@ __global__ void k_p2m_lattice(GridD g, double* w_out, const double* __restrict__
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int jd = blockIdx.y;
   if (k >= g.nz) return;
-  if (dt_dev) dt = *dt_dev;
+  {
+    const long long fo = member_field(g);
+    w_out += fo; w_in += fo; u_z += fo; u_r += fo;
+  }
+  if (dt_dev) dt = dt_dev[member_scalar(g)];
   const bool upper = jd >= g.nr;
   const int j = upper ? jd - g.nr : g.nr - 1 - jd;
   const long long src = (long long)j * g.ld + k;
@@ -426,13 +430,18 @@ int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const dou
                                    const double* u_r, const double* zl1d, const double* rl1d, double dt,
                                    const double* dt_dev, int periodic, axb_stream_t s) {
   if (!w_out || !w_in || !u_z || !u_r || !zl1d || !rl1d || w_out == w_in) return AXB_EINVAL;
-  int rc = axb_check_grid(g);
+  int rc = axb_check_grid_batched(g);
   if (rc) return rc;
   if (g->ku0 != 0 || g->ku1 != g->nz || g->nz_global != g->nz) return AXB_ENOSUP;
   const GridD d = to_dev(g);
-  cudaMemset2DAsync(w_out, d.ld * sizeof(double), 0, d.nz * sizeof(double), d.nr, s);
-  k_p2m_lattice<<<dim3((d.nz + 127) / 128, 2 * d.nr), 128, 0, s>>>(d, w_out, w_in, u_z, u_r, zl1d, rl1d, dt, dt_dev,
-                                                                  periodic != 0);
+  if (d.batch > 1 && d.bstride == d.nz) {          // members are adjacent column blocks: one memset
+    cudaMemset2DAsync(w_out, d.ld * sizeof(double), 0, (size_t)d.batch * d.nz * sizeof(double), d.nr, s);
+  } else {
+    for (int m = 0; m < d.batch; ++m)
+      cudaMemset2DAsync(w_out + m * d.bstride, d.ld * sizeof(double), 0, d.nz * sizeof(double), d.nr, s);
+  }
+  k_p2m_lattice<<<dim3((d.nz + 127) / 128, 2 * d.nr, d.batch), 128, 0, s>>>(d, w_out, w_in, u_z, u_r, zl1d, rl1d, dt,
+                                                                           dt_dev, periodic != 0);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

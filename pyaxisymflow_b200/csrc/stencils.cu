@@ -26,6 +26,7 @@ __device__ __forceinline__ double* rowp(double* f, long long ld, int j) { return
 __global__ void k_kill_z(GridD g, double* __restrict__ w, const double* __restrict__ z1d, int width) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= g.nr) return;
+  w += member_field(g);
   double* row = rowp(w, g.ld, j);
   const double den = (double)(width - 1);
   // left end: global columns [0, width)
@@ -59,6 +60,7 @@ __global__ void k_kill_z(GridD g, double* __restrict__ w, const double* __restri
 __global__ void k_kill_r(GridD g, double* __restrict__ w, const double* __restrict__ r1d, int width, int parts) {
   const int k = g.ku0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= g.ku1) return;
+  w += member_field(g);
   if (parts & 1) {
     const double den = (double)(width - 1);
     const double src = rowp(w, g.ld, g.nr - width)[k];
@@ -349,9 +351,12 @@ __global__ void __launch_bounds__(TBX* TBY)
   const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
   const int j = blockIdx.y * TBY + threadIdx.y;
   if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
+  H += member_field(g);
+  phi_out = moved(phi_out, member_field(g));
+  phi = moved(phi, member_field(g));
   double2 p;
   if (SPHERE) {
-    if (z_cm_dev) z_cm = *z_cm_dev;
+    if (z_cm_dev) z_cm = z_cm_dev[member_scalar(g)];
     const double dr = r1d[j] - r_cm;
     const double za = z1d[k] - z_cm, zb = z1d[(k + 1 < g.nz) ? k + 1 : k] - z_cm;
     const double da = za * za + dr * dr, db = zb * zb + dr * dr;
@@ -417,6 +422,9 @@ template <int MODE>
 __global__ void __launch_bounds__(TBX* TBY)
     k_reduce(GridD g, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ r1d,
              double off, double* out, bool vec) {
+  a += member_field(g);
+  b = moved(b, member_field(g));
+  out += member_scalar(g);
   double acc = (MODE == 1) ? -INFINITY : 0.0;
   // grid-stride over row blocks so the number of atomics stays small
   for (int j = blockIdx.y * TBY + threadIdx.y; j < g.nr; j += gridDim.y * TBY) {
@@ -482,7 +490,7 @@ __global__ void k_rigid_scalars(int phase, double* st, double U0, double T_ramp,
 }
 
 inline bool vec_ok(const GridD& g, std::initializer_list<const void*> ptrs) {
-  if (g.ld & 1) return false;
+  if ((g.ld & 1) || (g.bstride & 1)) return false;
   for (const void* p : ptrs)
     if (p && !axb_al16(p)) return false;
   return true;
@@ -495,8 +503,8 @@ inline int al_check(std::initializer_list<const void*> ptrs) {
 
 }  // namespace
 
-#define GRID_PROLOGUE(...)                      \
-  int rc__ = axb_check_grid(g);                 \
+#define GRID_PROLOGUE_(CHECK, ...)               \
+  int rc__ = CHECK(g);                          \
   if (rc__) return rc__;                        \
   rc__ = al_check({__VA_ARGS__});               \
   if (rc__) return rc__;                        \
@@ -504,15 +512,18 @@ inline int al_check(std::initializer_list<const void*> ptrs) {
   const bool vec = vec_ok(d, {__VA_ARGS__});    \
   const dim3 blk(TBX, TBY), grd = grid2d(d);    \
   (void)vec; (void)blk; (void)grd;
+#define GRID_PROLOGUE(...) GRID_PROLOGUE_(axb_check_grid, __VA_ARGS__)
+// entries that serve an ensemble with one launch: the grid's z dimension is the member (axb_grid_t.batch)
+#define GRID_PROLOGUE_BATCHED(...) GRID_PROLOGUE_(axb_check_grid_batched, __VA_ARGS__)
 
 extern "C" {
 
 int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const double* z1d, int width,
                                        axb_stream_t s) {
   if (!w || !z1d || width < 2) return AXB_EINVAL;
-  GRID_PROLOGUE(w, z1d)
+  GRID_PROLOGUE_BATCHED(w, z1d)
   if (2 * width > d.nzg) return AXB_EINVAL;
-  k_kill_z<<<(d.nr + 127) / 128, 128, 0, s>>>(d, w, z1d, width);
+  k_kill_z<<<dim3((d.nr + 127) / 128, 1, d.batch), 128, 0, s>>>(d, w, z1d, width);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
@@ -520,11 +531,11 @@ int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const dou
 int axb_kill_boundary_vorticity_sine_r_parts(const axb_grid_t* g, double* w, const double* r1d, int width,
                                              int parts, axb_stream_t s) {
   if (!w || !r1d || width < 2 || parts < 0 || parts > 3) return AXB_EINVAL;
-  GRID_PROLOGUE(w, r1d)
+  GRID_PROLOGUE_BATCHED(w, r1d)
   if (width > d.nr) return AXB_EINVAL;
   const int n = d.ku1 - d.ku0;
   if (n <= 0 || !parts) return AXB_OK;
-  k_kill_r<<<(n + 127) / 128, 128, 0, s>>>(d, w, r1d, width, parts);
+  k_kill_r<<<dim3((n + 127) / 128, 1, d.batch), 128, 0, s>>>(d, w, r1d, width, parts);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }
@@ -548,8 +559,9 @@ int axb_velocity_from_psi(const axb_grid_t* g, double* u_z, double* u_r, const d
                           const double* r1d, double uz_add, double ur_add, const double* add_dev,
                           double* umax_out, axb_stream_t s) {
   if (!u_z || !u_r || !psi || !r1d) return AXB_EINVAL;
-  GRID_PROLOGUE(u_z, u_r, psi)
+  GRID_PROLOGUE_BATCHED(u_z, u_r, psi)
   if (d.nr < 3 || d.nzg < 3) return AXB_EINVAL;
+  if (d.batch > 1 && g_axb_legacy_stencils) return AXB_ENOSUP;     // ensembles: row-marching kernels only
   if (!g_axb_legacy_stencils) {
     const int rc = march_velocity(d, u_z, u_r, psi, r1d, uz_add, ur_add, add_dev, umax_out, vec, s);
     AXB_LAUNCHED();
@@ -599,7 +611,8 @@ int axb_penalise_update_vorticity(const axb_grid_t* g, double* u_z, double* u_r,
   if (!u_z || !u_r || !w || !u_z_upen || !u_r_upen || !chi) return AXB_EINVAL;
   if (u_z == u_z_upen || u_r == u_r_upen) return AXB_EINVAL;  // neighbours are read un-penalised
   if (sum_out && !r1d) return AXB_EINVAL;
-  GRID_PROLOGUE(u_z, u_r, w, u_z_upen, u_r_upen, chi)
+  GRID_PROLOGUE_BATCHED(u_z, u_r, w, u_z_upen, u_r_upen, chi)
+  if (d.batch > 1 && g_axb_legacy_stencils) return AXB_ENOSUP;
   if (!g_axb_legacy_stencils) {
     const int rc = march_penalise(d, u_z, u_r, w, u_z_upen, u_r_upen, chi, lam, dt, dt_dev, U_z, U_r, U_dev, r1d,
                                   sum_out, vec, s);
@@ -616,32 +629,41 @@ int axb_penalise_update_vorticity(const axb_grid_t* g, double* u_z, double* u_r,
   AXB_RETURN_LAST();
 }
 
-int axb_diffusion_rk2_stage1(const axb_grid_t* g, double* tmp, const double* w, const double* r1d,
-                             double nu, double dt, const double* dt_dev, axb_stream_t s) {
-  if (!tmp || !w || !r1d || tmp == w) return AXB_EINVAL;
-  GRID_PROLOGUE(tmp, w)
+static int diffusion_stage(int stage, const axb_grid_t* g, double* out, const double* in, const double* src2,
+                           const double* r1d, double nu, const double* nu_dev, double dt, const double* dt_dev,
+                           axb_stream_t s) {
+  GRID_PROLOGUE_BATCHED(out, in, src2)
+  if (g_axb_legacy_stencils && (d.batch > 1 || nu_dev)) return AXB_ENOSUP;
   if (!g_axb_legacy_stencils) {
-    const int rc = march_diffusion(1, d, tmp, w, nullptr, r1d, nu, dt, dt_dev, vec, s);
+    const int rc = march_diffusion(stage, d, out, in, src2, r1d, nu, nu_dev, dt, dt_dev, vec, s);
     AXB_LAUNCHED();
     return rc;
   }
-  k_diffusion<1><<<grd, blk, 0, s>>>(d, tmp, w, nullptr, r1d, nu, dt, dt_dev, vec);
+  if (stage == 1) k_diffusion<1><<<grd, blk, 0, s>>>(d, out, in, nullptr, r1d, nu, dt, dt_dev, vec);
+  else k_diffusion<2><<<grd, blk, 0, s>>>(d, out, in, src2, r1d, nu, dt, dt_dev, vec);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
+}
+int axb_diffusion_rk2_stage1(const axb_grid_t* g, double* tmp, const double* w, const double* r1d,
+                             double nu, double dt, const double* dt_dev, axb_stream_t s) {
+  if (!tmp || !w || !r1d || tmp == w) return AXB_EINVAL;
+  return diffusion_stage(1, g, tmp, w, nullptr, r1d, nu, nullptr, dt, dt_dev, s);
 }
 int axb_diffusion_rk2_stage2(const axb_grid_t* g, double* w, const double* w_src, const double* tmp,
                              const double* r1d, double nu, double dt, const double* dt_dev,
                              axb_stream_t s) {
   if (!tmp || !w || !w_src || !r1d || tmp == w) return AXB_EINVAL;
-  GRID_PROLOGUE(tmp, w, w_src)
-  if (!g_axb_legacy_stencils) {
-    const int rc = march_diffusion(2, d, w, tmp, w_src, r1d, nu, dt, dt_dev, vec, s);
-    AXB_LAUNCHED();
-    return rc;
-  }
-  k_diffusion<2><<<grd, blk, 0, s>>>(d, w, tmp, w_src, r1d, nu, dt, dt_dev, vec);
-  AXB_LAUNCHED();
-  AXB_RETURN_LAST();
+  return diffusion_stage(2, g, w, tmp, w_src, r1d, nu, nullptr, dt, dt_dev, s);
+}
+int axb_diffusion_rk2_stage1_dev(const axb_grid_t* g, double* tmp, const double* w, const double* r1d,
+                                 const double* nu_dev, const double* dt_dev, axb_stream_t s) {
+  if (!tmp || !w || !r1d || tmp == w || !nu_dev || !dt_dev) return AXB_EINVAL;
+  return diffusion_stage(1, g, tmp, w, nullptr, r1d, 0.0, nu_dev, 0.0, dt_dev, s);
+}
+int axb_diffusion_rk2_stage2_dev(const axb_grid_t* g, double* w, const double* w_src, const double* tmp,
+                                 const double* r1d, const double* nu_dev, const double* dt_dev, axb_stream_t s) {
+  if (!tmp || !w || !w_src || !r1d || tmp == w || !nu_dev || !dt_dev) return AXB_EINVAL;
+  return diffusion_stage(2, g, w, tmp, w_src, r1d, 0.0, nu_dev, 0.0, dt_dev, s);
 }
 
 int axb_diffusion_rk2_fused(const axb_grid_t* g, double* w, const double* w_src, double* tmp, const double* r1d,
@@ -684,7 +706,7 @@ int axb_smooth_heaviside_sphere_dev(const axb_grid_t* g, double* H, double* phi_
                                     const double* r1d, const double* z_cm_dev, double r_cm, double radius,
                                     double blend_w, axb_stream_t s) {
   if (!H || !z1d || !r1d || !z_cm_dev) return AXB_EINVAL;
-  GRID_PROLOGUE(H, phi_out)
+  GRID_PROLOGUE_BATCHED(H, phi_out)
   k_heaviside<true><<<grd, blk, 0, s>>>(d, H, phi_out, nullptr, z1d, r1d, 0.0, r_cm, radius, blend_w, vec, z_cm_dev);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
@@ -722,13 +744,13 @@ static dim3 reduce_grid(const GridD& d) {
   unsigned gx = full.x, gy = full.y;
   while ((unsigned long long)gx * gy > maxb && gy > 1) gy = (gy + 1) / 2;
   while ((unsigned long long)gx * gy > maxb && gx > 1) gx = (gx + 1) / 2;
-  return dim3(gx, gy, 1);
+  return dim3(gx, gy, d.batch);
 }
 
 int axb_reduce_max_abs_sum(const axb_grid_t* g, const double* a, const double* b, double* out,
                            axb_stream_t s) {
   if (!a || !out) return AXB_EINVAL;
-  GRID_PROLOGUE(a, b)
+  GRID_PROLOGUE_BATCHED(a, b)
   k_reduce<0><<<reduce_grid(d), blk, 0, s>>>(d, a, b, nullptr, 0.0, out, vec);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();

@@ -99,6 +99,12 @@ __global__ void __launch_bounds__(MT)
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local_max = 0.0;
+  {
+    const long long fo = member_field(g);
+    u_z += fo; u_r += fo; psi += fo;
+    add_dev = moved(add_dev, member_scalar(g));
+    umax_out = moved(umax_out, member_scalar(g));
+  }
   if (add_dev) { uz_add = add_dev[0]; ur_add = add_dev[1]; }
   if (PATH == 1) {
     const double inv_h = 1.0 / (2 * g.dx);
@@ -243,6 +249,13 @@ __global__ void __launch_bounds__(MT)
   double local = 0.0;
   const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec) && (!REDUCE || (j0 >= g.ju0 && j1 <= g.ju1));
   if ((PATH == 1) != interior) return;
+  {
+    const long long fo = member_field(g);
+    u_z += fo; u_r += fo; w += fo; uzu += fo; uru += fo; chi += fo;
+    dt_dev = moved(dt_dev, member_scalar(g));
+    U_dev = moved(U_dev, member_scalar(g));
+    sum_out = moved(sum_out, member_scalar(g));
+  }
   if (dt_dev) dt = *dt_dev;
   if (U_dev) { U_z = U_dev[0]; U_r = U_dev[1]; }
   if (PATH == 1) {
@@ -345,7 +358,8 @@ __global__ void __launch_bounds__(MT)
 template <int STAGE, int PATH>
 __global__ void __launch_bounds__(MT)
     km_diffusion(GridD g, int RB, double* out, const double* __restrict__ in, const double* src2,
-                 const double* __restrict__ r1d, double nu, double dt, const double* __restrict__ dt_dev, bool vec) {
+                 const double* __restrict__ r1d, double nu, const double* __restrict__ nu_dev, double dt,
+                 const double* __restrict__ dt_dev, bool vec) {
   extern __shared__ double s_inv[];
   const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
   const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
@@ -354,7 +368,12 @@ __global__ void __launch_bounds__(MT)
   __syncthreads();
   const Cols c = make_cols(g);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
-  if (dt_dev) dt = *dt_dev;
+  {
+    const long long fo = member_field(g);
+    out += fo; in += fo; src2 = moved(src2, fo);
+  }
+  if (dt_dev) dt = dt_dev[member_scalar(g)];
+  if (nu_dev) nu = nu_dev[member_scalar(g)];
   const double coef = (STAGE == 1) ? (0.5 * nu * dt) : (nu * dt);
   const double inv_dx2 = 1.0 / (g.dx * g.dx), inv_h = 1.0 / (2 * g.dx);
   if (PATH == 1) {
@@ -790,11 +809,11 @@ inline int pick_rb(const GridD& d) {
   // (1-4 extra row loads) amortised over 32 rows
   const long long colb = ((d.nz + 1) / 2 + MT - 1) / MT;
   for (int rb = 32; rb >= 8; rb >>= 1)
-    if (colb * ((d.nr + rb - 1) / rb) >= 148LL * 12) return rb;
+    if (colb * ((d.nr + rb - 1) / rb) * d.batch >= 148LL * 12) return rb;
   return 8;
 }
 inline dim3 march_grid(const GridD& d, int rb) {
-  return dim3(((d.nz + 1) / 2 + MT - 1) / MT, (d.nr + rb - 1) / rb, 1);
+  return dim3(((d.nz + 1) / 2 + MT - 1) / MT, (d.nr + rb - 1) / rb, d.batch);
 }
 
 // The edge kernel of a pair (few blocks, latency bound: 40-90 us at 4096 x 16384) runs on a side stream
@@ -870,12 +889,12 @@ int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const do
 }
 
 int march_diffusion(int stage, const GridD& d, double* out, const double* in, const double* src2, const double* r1d,
-                    double nu, double dt, const double* dt_dev, bool vec, cudaStream_t s) {
+                    double nu, const double* nu_dev, double dt, const double* dt_dev, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
   EdgeFork* ef;
   cudaStream_t se = edge_begin(s, ef);
-#define DIF(S, P, ST) km_diffusion<S, P><<<march_grid(d, rb), MT, rb * sizeof(double), ST>>>(d, rb, out, in, src2, r1d, nu, dt, \
-                                                                                       dt_dev, vec)
+#define DIF(S, P, ST) km_diffusion<S, P><<<march_grid(d, rb), MT, rb * sizeof(double), ST>>>(d, rb, out, in, src2, r1d, nu, nu_dev, \
+                                                                                       dt, dt_dev, vec)
   if (stage == 1) { DIF(1, 2, se); DIF(1, 1, s); }
   else { DIF(2, 2, se); DIF(2, 1, s); }
 #undef DIF

@@ -123,14 +123,17 @@ class Stage:
             host[...] = t.cpu().numpy()
 
 
-def make_grid(nr, nz, ld, dx, slab=None, rows=None):
+def make_grid(nr, nz, ld, dx, slab=None, rows=None, batch=None):
     """axb_grid_t for a full single-GPU field, for a z-slab (kz0, nz_global, ku0, ku1), or -- ``rows=(ju0, ju1)``
-    -- for an r-slab block whose rows [ju0, ju1) are the owned ones (the only rows fused reductions count)."""
+    -- for an r-slab block whose rows [ju0, ju1) are the owned ones (the only rows fused reductions count).
+    ``batch=(members, field stride in elements, scalar stride in doubles)`` describes an ensemble served by one
+    launch per operation (include/axisym_b200.h, axb_grid_t)."""
     ju0, ju1 = (0, 0) if rows is None else rows
+    b, bs, ss = (0, 0, 0) if batch is None else batch
     if slab is None:
-        return AxbGrid(nr, nz, ld, float(dx), 0, nz, 0, nz, ju0, ju1)
+        return AxbGrid(nr, nz, ld, float(dx), 0, nz, 0, nz, ju0, ju1, b, ss, bs)
     kz0, nzg, ku0, ku1 = slab
-    return AxbGrid(nr, nz, ld, float(dx), kz0, nzg, ku0, ku1, ju0, ju1)
+    return AxbGrid(nr, nz, ld, float(dx), kz0, nzg, ku0, ku1, ju0, ju1, b, ss, bs)
 
 
 def coord_1d(stage, X, axis, n):

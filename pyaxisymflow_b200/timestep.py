@@ -554,7 +554,7 @@ class ParticleFlowStepper:
         _call("axb_reduce_max_abs_sum", g, ptr(w), None, sp(2), s)         # state[2] was zeroed by phase 2
         self._scalars_dev(1)
         _call("axb_add_bubble_flow_dev", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_char_func),
-              ptr(self.z1d), ptr(self.r1d), self.bubble_Z_cm, self.bubble_R_cm, self.r0_bubble, self.U_0, sp(9), s)
+              ptr(self.z1d), ptr(self.r1d), self.bubble_Z_cm, self.bubble_R_cm, self.r0_bubble, self.U_0, None, sp(9), s)
         _call("axb_cycle_average3", g, ptr(self.avg_part_char_func), ptr(self.part_char_func),
               ptr(self.avg_part_char_func_last), ptr(self.avg_psi), ptr(self.psi), ptr(self.avg_psi_last),
               ptr(self.avg_vort), ptr(w), ptr(self.avg_vort_last), sp(10), sp(15), s)
@@ -722,12 +722,15 @@ class ParticleEnsemble:
         self._pending = [False] * len(self.members)
 
     @classmethod
-    def batched_ensemble(cls, params, grid_size_z, grid_size_r=None, use_graph=True, branches=4, solver=None, **kw):
+    def batched_ensemble(cls, params, grid_size_z, grid_size_r=None, use_graph=True, branches=4, solver=None,
+                         launch="batched", **kw):
         """SURVEY.md 8e "Ensemble": ``params`` = [(freq, e), ...]; all members share one set of (nr, batch nz) field
-        tensors (:class:`_WidePool`), keep their loop scalars on the device, and one step of the WHOLE ensemble is a
-        fixed launch sequence -- per-member boundary damping, ONE solve for all members (z transforms over batch nr
-        rows, r sweeps over batch nz columns), the per-member rest on `branches` parallel graph branches -- captured
-        once and replayed.  No host round trip, no per-member solve."""
+        tensors (:class:`_WidePool`) and keep their loop scalars in one (batch, 24) device block; a step of the WHOLE
+        ensemble is a fixed launch sequence captured once and replayed -- no host round trip.  ``launch="batched"``:
+        every operation is ONE launch over all members (``axb_grid_t.batch``: the member is the grid's z dimension,
+        per-member dt / U / omega / nu / ... read from the scalar block), 14 launches + the 4 of the solve whatever
+        the ensemble size.  ``launch="members"``: one launch per member and operation on `branches` parallel graph
+        branches around the shared solve (the cross-check of the batched kernels)."""
         nz = int(grid_size_z)
         nr = int(grid_size_r) if grid_size_r is not None else int(kw.get("domain_AR", 0.5) * nz)
         pool = _WidePool(nr, nz, len(params))
@@ -745,9 +748,67 @@ class ParticleEnsemble:
         self._w_wide = pool.wide[0]        # field 0 = vorticity, field 1 = psi (ParticleFlowStepper's F.new order)
         self._psi_wide = pool.wide[1]
         self._side = [torch.cuda.Stream() for _ in range(self._branches)]
+        # one scalar block / trace ring for the ensemble; the members keep views of their rows
+        b, m0 = len(members), members[0]
+        self.state = torch.zeros((b, 24), dtype=torch.float64, device="cuda")
+        self.trace_dev = torch.zeros((b,) + tuple(m0.trace_dev.shape), dtype=torch.float64, device="cuda")
+        for i, m in enumerate(members):
+            self.state[i].copy_(m.state)
+            self.state[i, 19:24] = torch.tensor([m.omega, m.freqTimer_limit, m.U_0, m.nu, 0.9 * m.dx ** 2 / 4 / m.nu],
+                                                dtype=torch.float64)
+            m.state, m.trace_dev = self.state[i], self.trace_dev[i]
+            if abs(m.part_vol - m0.part_vol) > 1e-14 * m0.part_vol or (m.bubble_Z_cm, m.r0_bubble, m.r_part) != \
+                    (m0.bubble_Z_cm, m0.r0_bubble, m0.r_part):
+                raise ValueError("the members of a batched ensemble differ in (freq, e) only")
+        if launch not in ("batched", "members"):
+            raise ValueError(f"launch {launch!r}")
+        self._launch = launch
+        self._grid_b = make_grid(nr, nz, b * nz, m0.dx, batch=(b, nz, 24))
         return self
 
+    def _enqueue_one_launch_per_op(self):
+        """the step of every member, each operation one launch (grid z dimension = member)"""
+        m, b = self.members[0], len(self.members)
+        g, s = ctypes.byref(self._grid_b), stream_ptr()
+        base = self.state.data_ptr()
+
+        def sp(i):
+            return ctypes.c_void_p(base + 8 * i)
+
+        def scalars(phase):
+            _call("axb_particle_scalars_batched", phase, b, 24, ptr(self.state), ptr(self.trace_dev),
+                  self.trace_dev.shape[1], m.CFL, m.eps, m.rho_f * m.brink_lam, m.part_vol, m.part_mass, m.bubble_Z_cm,
+                  m.r0_bubble, s)
+
+        w = m.vorticity
+        _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(m.z1d), 3, s)
+        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(m.r1d), 3, s)
+        if self._solver is not None:
+            self._solver.solve(self._psi_wide, self._w_wide)
+        else:
+            for mm in self.members:
+                mm._enqueue_dev_solve()
+        _call("axb_velocity_from_psi", g, ptr(m.u_z_upen), ptr(m.u_r_upen), ptr(m.psi), ptr(m.r1d), 0.0, 0.0, None, None, s)
+        _call("axb_reduce_max_abs_sum", g, ptr(w), None, sp(2), s)
+        scalars(1)
+        _call("axb_add_bubble_flow_dev", g, ptr(m.u_z_upen), ptr(m.u_r_upen), ptr(m.bubble_char_func), ptr(m.z1d),
+              ptr(m.r1d), m.bubble_Z_cm, m.bubble_R_cm, m.r0_bubble, 0.0, sp(21), sp(9), s)
+        _call("axb_cycle_average3", g, ptr(m.avg_part_char_func), ptr(m.part_char_func), ptr(m.avg_part_char_func_last),
+              ptr(m.avg_psi), ptr(m.psi), ptr(m.avg_psi_last), ptr(m.avg_vort), ptr(w), ptr(m.avg_vort_last), sp(10),
+              sp(15), s)
+        _call("axb_smooth_heaviside_sphere_dev", g, ptr(m.part_char_func), None, ptr(m.z1d), ptr(m.r1d), sp(6),
+              m.part_R_cm, m.r_part, m.moll_zone, s)
+        _call("axb_penalise_update_vorticity", g, ptr(m.u_z), ptr(m.u_r), ptr(w), ptr(m.u_z_upen), ptr(m.u_r_upen),
+              ptr(m.part_char_func), m.brink_lam, 0.0, sp(1), 0.0, 0.0, sp(4), ptr(m.r1d), sp(3), s)
+        _call("axb_advect_vorticity_particles", g, ptr(m._w2), ptr(w), ptr(m.u_z), ptr(m.u_r), ptr(m.z1d),
+              ptr(m.rl_double), 0.0, sp(1), 0, s)
+        _call("axb_diffusion_rk2_stage1_dev", g, ptr(m._tmp), ptr(m._w2), ptr(m.r1d), sp(22), sp(1), s)
+        _call("axb_diffusion_rk2_stage2_dev", g, ptr(w), ptr(m._w2), ptr(m._tmp), ptr(m.r1d), sp(22), sp(1), s)
+        scalars(2)
+
     def _enqueue_batched(self):
+        if self._launch == "batched":
+            return self._enqueue_one_launch_per_op()
         for m in self.members:
             m._enqueue_dev_pre()
         if self._solver is not None:

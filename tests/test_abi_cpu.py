@@ -31,8 +31,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(_lib.AxbGrid) == 48        # 2*i32, i64, f64, 6*i32
+    assert ctypes.sizeof(_lib.AxbGrid) == 64        # 2*i32, i64, f64, 6*i32, 2*i32 (batch, scalar_stride), i64
     assert _lib.AxbGrid.ld.offset == 8 and _lib.AxbGrid.dx.offset == 16 and _lib.AxbGrid.kz0.offset == 24
+    assert _lib.AxbGrid.batch.offset == 48 and _lib.AxbGrid.batch_stride.offset == 56
     assert ctypes.sizeof(_lib.AxbFdPlan) == 8 + 6 * 8 + 2 * 8 + 8 + 8 + 3 * 32 + 2 * 64 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
     assert _lib.AxbFdPlan.leaf_fwd.offset == 8 + 6 * 8 + 2 * 8 + 8 + 8 + 3 * 32
 
@@ -58,6 +59,14 @@ def test_argument_validation_without_a_gpu():
     ptrs = (ctypes.c_uint64 * 2)(16, 0)
     assert lib.axb_peer_block_put(2, 0, ptrs, 0, 64, p16, 0, 64, 2, 64, None) == -1                     # null peer
     assert lib.axb_peer_block_put(17, 0, ptrs, 0, 64, p16, 0, 64, 2, 64, None) == -1                    # > AXB_MAX_PEERS
+    # ensembles (axb_grid_t.batch > 1): entries that are not batched refuse, batched ones validate the strides
+    g = _lib.AxbGrid(8, 8, 32, 1.0, 0, 8, 0, 8, 0, 0, 4, 24, 8)
+    assert lib.axb_set_fixed_val(ctypes.byref(g), p16, 1.0, None) == -3
+    assert lib.axb_diffusion_rk2_fused(ctypes.byref(g), p16, ctypes.c_void_p(32), p16, p16, 1.0, 1.0, None, None) == -3
+    assert lib.axb_diffusion_rk2_stage1_dev(ctypes.byref(g), p16, ctypes.c_void_p(32), p16, None, p16, None) == -1
+    g.batch_stride = 4                                                                                  # < nz
+    assert lib.axb_diffusion_rk2_stage1_dev(ctypes.byref(g), p16, ctypes.c_void_p(32), p16, p16, p16, None) == -1
+    assert lib.axb_particle_scalars_batched(1, 4, 8, p16, None, 0, .1, .1, 1., 1., 1., 0., 1., None) == -1   # stride < 24
     # SURVEY 8f entries
     g = _lib.AxbGrid(8, 8, 8, 1.0, 0, 8, 0, 8)
     gb = ctypes.byref(g)

@@ -680,27 +680,37 @@ def test_particle_stepper_device_scalars_match_host_loop(K, graph):
     assert abs(d.freqTimer - d.dt) <= 1e-18
 
 
-@pytest.mark.parametrize("fft", [True, False])
-def test_batched_particle_ensemble(K, fft):
+@pytest.mark.parametrize("fft,launch,nz", [(True, "batched", 512), (False, "batched", 128), (True, "members", 128)])
+def test_batched_particle_ensemble(K, fft, launch, nz):
     """SURVEY 8e "Ensemble": members stored as column blocks of shared (nr, batch nz) tensors, one solve for the
     whole ensemble (DCT rows = batch nr, sweep columns = batch nz), per-member scalars on the device, the whole
-    ensemble step one replayed graph -- every member equals the same member stepping alone under host control."""
+    ensemble step one replayed graph -- every member equals the same member stepping alone under host control.
+    launch="batched": every operation is one launch over all members (axb_grid_t.batch; 512 columns reach the
+    interior row-marching kernels); "members": one launch per member and operation on parallel graph branches."""
     from pyaxisymflow_b200.fd import FastDiagonalisationStokesSolver
     from pyaxisymflow_b200.timestep import ParticleEnsemble, ParticleFlowStepper
 
-    nz, nr, steps = 128, 64, 7
+    nr, steps = 64, 7
     params = [(8.0, 0.01), (16.0, 0.02), (12.0, 0.005), (20.0, 0.01), (24.0, 0.015)]
     kw = dict(basis="analytic", r_method="tridiagonal", z_method="fft") if fft else {}
     solver = FastDiagonalisationStokesSolver(nr, nz, 1.0 / nz, **kw)
-    ens = ParticleEnsemble.batched_ensemble(params, nz, nr, use_graph=True, branches=3, solver=solver)
+    ens = ParticleEnsemble.batched_ensemble(params, nz, nr, use_graph=True, branches=3, solver=solver, launch=launch)
     assert (ens._solver is not None) == fft
     assert ens.members[2].vorticity.stride(0) == len(params) * nz
-    ens.step(3)
+    hosts = [ParticleFlowStepper(nz, grid_size_r=nr, freq=f, e=e, solver=solver) for f, e in params]
+    # the first step has no feedback from the (ill-conditioned) force yet: fields agree to rounding
+    ens.step(1)
+    for m, h in zip(ens.members, hosts):
+        h.step(1)
+        for fld in ("vorticity", "psi", "u_z", "u_r", "avg_vort", "part_char_func"):
+            assert_close(getattr(m, fld).cpu().numpy(), getattr(h, fld).cpu().numpy(), 1e-12, f"{fld} after one step")
+    ens.step(2)
     ens.step(steps - 3)
     ens.sync_scalars()
-    for m, (f, e) in zip(ens.members, params):
-        h = ParticleFlowStepper(nz, grid_size_r=nr, freq=f, e=e, solver=solver)
-        h.step(steps)
+    # later steps carry U_z_cm_part = integral of F (agrees to the conditioning of the force sum, see
+    # _assert_particle_state) into the penalised velocity, so the fields agree to that, not to rounding
+    for m, h, (f, e) in zip(ens.members, hosts, params):
+        h.step(steps - 1)
         _assert_particle_state(m, h, f)
         for fld in ("vorticity", "psi", "avg_vort", "part_char_func"):
-            assert_close(getattr(m, fld).cpu().numpy(), getattr(h, fld).cpu().numpy(), 1e-9, f"{fld} f={f}")
+            assert_close(getattr(m, fld).cpu().numpy(), getattr(h, fld).cpu().numpy(), 1e-6, f"{fld} f={f}")
