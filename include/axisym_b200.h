@@ -272,6 +272,16 @@ int axb_add_bubble_flow_dev(const axb_grid_t* g, double* u_z, double* u_r, const
                             const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
                             double r0_bubble, double U_0, const double* U_0_dev, const double* sin_omega_t_dev,
                             axb_stream_t s);
+/* The bubble does not move: axb_bubble_flow_geometry fills geom = -/+ ((Z - z_cm)^2 + (R - r_cm)^2)^1.5 (minus inside the
+ * bubble, bubble_char_func >= 0.5) once, axb_add_bubble_flow_geom adds the flow of :273-294 from it with the bits of
+ * axb_add_bubble_flow (the term that does not apply to a cell is an exact zero there) -- no pow() per step.  Batched;
+ * geom (pitch ld_geom) is shared by the members. */
+int axb_bubble_flow_geometry(const axb_grid_t* g, double* geom, const double* bubble_char_func, const double* z1d,
+                             const double* r1d, double bubble_z_cm, double bubble_r_cm, axb_stream_t s);
+int axb_add_bubble_flow_geom(const axb_grid_t* g, double* u_z, double* u_r, const double* geom, int64_t ld_geom,
+                             const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
+                             double r0_bubble, double U_0, const double* U_0_dev, const double* sin_omega_t_dev,
+                             axb_stream_t s);
 /* One launch for all members of an ensemble (batched): member m's scalar block is state + m scalar_stride
  * (scalar_stride >= 24) and additionally holds the constants that differ between members,
  *   [19] omega  [20] cycle time  [21] U_0  [22] nu  [23] diffusive dt limit,
@@ -322,10 +332,20 @@ int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const ui
 int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const double* val, double* mesh,
                    double dx, double dy, int periodic, axb_stream_t s);
 /* kernels/advect_particle.py:5-35 fused for lattice particles: push the mirrored lattice by
- * u*dt, remesh with MP4 on the doubled grid, return the physical half (w_out != w_in). ----- */
+ * u*dt, remesh with MP4 on the doubled grid, return the physical half (w_out != w_in).
+ * periodic = 0 runs the gather form: particles that move less than a cell are remeshed without atomics, every node
+ * summed in the order of the reference's sequential particle loop (particles_to_mesh_2D.hpp:273-321) -- the result
+ * is the reference's bit for bit; particles that move a cell or more are added by an atomic scatter pass.  The
+ * _flagged form takes a caller-owned device int: the scatter pass returns at once when the gather pass saw no such
+ * particle (the plain form always scans for them).  periodic = 1, or axb_set_p2m_atomic(1): the atomic scatter
+ * (sums agree to rounding, order not fixed). ----- */
 int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
                                    const double* u_r, const double* zl1d, const double* rl1d, double dt,
                                    const double* dt_dev, int periodic, axb_stream_t s);
+int axb_advect_vorticity_particles_flagged(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
+                                           const double* u_r, const double* zl1d, const double* rl1d, double dt,
+                                           const double* dt_dev, int32_t* far_flag, axb_stream_t s);
+int axb_set_p2m_atomic(int on);
 
 /* ---- the rest of the particle <-> mesh family of the C++ core (core/src/instantiate.yml:1-27).
  *      kernel = one of AXB_PK_*: core/src/particle_kernels/LinearKernel.hpp, MP4.hpp, MP6.hpp,

@@ -85,6 +85,8 @@ _SIGNATURES = {
     "axb_smooth_heaviside_mask": [_G, _P, _P, _P, _D, _D, _I, _S],
     "axb_add_bubble_flow": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D, _S],
     "axb_add_bubble_flow_dev": [_G, _P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _S],
+    "axb_bubble_flow_geometry": [_G, _P, _P, _P, _P, _D, _D, _S],
+    "axb_add_bubble_flow_geom": [_G, _P, _P, _P, c_int64, _P, _P, _D, _D, _D, _D, _P, _P, _S],
     "axb_particle_scalars_batched": [_I, _I, _I, _P, _P, _I, _D, _D, _D, _D, _D, _D, _D, _S],
     "axb_diffusion_rk2_stage1_dev": [_G, _P, _P, _P, _P, _P, _S],
     "axb_diffusion_rk2_stage2_dev": [_G, _P, _P, _P, _P, _P, _P, _S],
@@ -111,6 +113,8 @@ _SIGNATURES = {
     "axb_p2m_1d_mp4": [_I, _I, _P, _P, _P, _D, _S],
     "axb_wrap_particles_2d": [_I, _I, _P, _P, _D, _D, _D, _D, _S],
     "axb_advect_vorticity_particles": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _I, _S],
+    "axb_advect_vorticity_particles_flagged": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _P, _S],
+    "axb_set_p2m_atomic": [_I],
     "axb_fd_solve": [POINTER(AxbFdPlan), _P, c_int64, _P, c_int64, _S],
     "axb_dgemm": [_I, _I, _I, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _D, _D, _S],
     "axb_dgemm_set_path": [_I],

@@ -101,6 +101,54 @@ __global__ void __launch_bounds__(TBX* TBY)
   st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(vr[0], vr[1]));
 }
 
+// The same update from a precomputed geometry field (the bubble does not move): geom = -(d^2)^1.5 inside the bubble
+// (bubble_char_func >= 0.5), +(d^2)^1.5 outside.  A cell inside takes only the breathing term, a cell outside only
+// the potential-flow term -- the other term of particle_in_bubble_oscillatory_flow.py:273-294 is an exact zero -- so
+// the result has the bits of k_bubble without its pow() and with two instead of four divisions per cell.  `geom` is
+// shared by the members of an ensemble (not moved by the member index).
+__global__ void __launch_bounds__(TBX* TBY)
+    k_bubble_geometry(GridD g, double* __restrict__ geom, const double* __restrict__ chi_b, const double* __restrict__ z1d,
+                      const double* __restrict__ r1d, double bz, double br) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= g.nr || k >= g.nz) return;
+  const double dz = z1d[k] - bz, dr = r1d[j] - br;
+  const double d15 = pow(dz * dz + dr * dr, 1.5);
+  geom[(long long)j * g.ld + k] = (chi_b[(long long)j * g.ld + k] >= 0.5) ? -d15 : d15;
+}
+__global__ void __launch_bounds__(TBX* TBY)
+    k_bubble_pre(GridD g, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ geom, long long ld_geom,
+                 const double* __restrict__ z1d, const double* __restrict__ r1d, double bz, double br, double r0, double U0,
+                 const double* __restrict__ s_dev, const double* __restrict__ U0_dev, bool vec) {
+  const int k = 2 * (blockIdx.x * TBX + threadIdx.x);
+  const int j = blockIdx.y * TBY + threadIdx.y;
+  if (j >= g.nr || k >= g.ku1 || k + 1 < g.ku0) return;
+  {
+    const long long fo = member_field(g);
+    u_z += fo; u_r += fo;
+  }
+  const double s = s_dev[member_scalar(g)];
+  if (U0_dev) U0 = U0_dev[member_scalar(g)];
+  const double2 gm = ld_pair(rowp(geom, ld_geom, j), k, g.nz, vec && !(ld_geom & 1));
+  double2 uz = ld_pair(rowp(u_z, g.ld, j), k, g.nz, vec), ur = ld_pair(rowp(u_r, g.ld, j), k, g.nz, vec);
+  const double dr = r1d[j] - br;
+  const double dz[2] = {z1d[k] - bz, z1d[(k + 1 < g.nz) ? k + 1 : k] - bz};
+  const double gg[2] = {gm.x, gm.y};
+  double vz[2] = {uz.x, uz.y}, vr[2] = {ur.x, ur.y};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (gg[i] < 0.0) {
+      vz[i] = vz[i] + U0 * dz[i] * s / r0;
+      vr[i] = vr[i] + U0 * dr * s / r0;
+    } else {
+      vz[i] = vz[i] + U0 * dz[i] * s * (r0 * r0) / gg[i];
+      vr[i] = vr[i] + U0 * dr * s * (r0 * r0) / gg[i];
+    }
+  }
+  st_pair(rowp(u_z, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(vz[0], vz[1]));
+  st_pair(rowp(u_r, g.ld, j), k, g.ku0, g.ku1, vec, make_double2(vr[0], vr[1]));
+}
+
 // running averages of three fields in one pass, restarted when the cycle timer wrapped (device flag):
 //   avg_i = (wrap ? 0 : avg_i) + a x_i;  on a wrap the completed averages are kept in last_i (may be null)
 struct Avg3 {
@@ -283,6 +331,31 @@ int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const dou
                         double U_0, double sin_omega_t, axb_stream_t s) {
   return bubble_flow(g, u_z, u_r, bubble_char_func, z1d, r1d, bubble_z_cm, bubble_r_cm, r0_bubble, U_0, sin_omega_t,
                      nullptr, nullptr, s);
+}
+int axb_bubble_flow_geometry(const axb_grid_t* g, double* geom, const double* bubble_char_func, const double* z1d,
+                             const double* r1d, double bubble_z_cm, double bubble_r_cm, axb_stream_t s) {
+  if (!geom || !bubble_char_func || !z1d || !r1d) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  const GridD d = to_dev(g);
+  k_bubble_geometry<<<dim3((d.nz + 31) / 32, (d.nr + 7) / 8), dim3(32, 8), 0, s>>>(d, geom, bubble_char_func, z1d, r1d,
+                                                                                 bubble_z_cm, bubble_r_cm);
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+int axb_add_bubble_flow_geom(const axb_grid_t* g, double* u_z, double* u_r, const double* geom, int64_t ld_geom,
+                             const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,
+                             double r0_bubble, double U_0, const double* U_0_dev, const double* sin_omega_t_dev,
+                             axb_stream_t s) {
+  if (!u_z || !u_r || !geom || !z1d || !r1d || !sin_omega_t_dev) return AXB_EINVAL;
+  int rc = axb_check_grid_batched(g);
+  if (rc) return rc;
+  if (ld_geom < g->nz) return AXB_EINVAL;
+  const GridD d = to_dev(g);
+  k_bubble_pre<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, u_z, u_r, geom, ld_geom, z1d, r1d, bubble_z_cm, bubble_r_cm,
+                                                  r0_bubble, U_0, sin_omega_t_dev, U_0_dev, vec_ok(d, {u_z, u_r, geom}));
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
 }
 int axb_add_bubble_flow_dev(const axb_grid_t* g, double* u_z, double* u_r, const double* bubble_char_func,
                             const double* z1d, const double* r1d, double bubble_z_cm, double bubble_r_cm,

@@ -359,6 +359,133 @@ __global__ void k_p2m_lattice(GridD g, double* w_out, const double* __restrict__
   mp4_scatter(w_out, g.nr, g.nz, g.ld, 2 * g.nr, g.nr, hx, hy, wx, wy, v, periodic);
 }
 
+
+// ---- gather form of the lattice remesh (no atomics) --------------------------------------------------------------
+// A lattice particle that moves less than one cell (|u dt| < dx in both directions; the driver's dt keeps it far
+// below that) lands with its nearest-upper index hi in {i, i + 1}, so its 4 x 4 MP4 footprint lies inside the 5 x 5
+// nodes around its own lattice node, and node (R, c) only receives from the particles of rows R-2..R+2, columns
+// c-2..c+2.  A warp takes 32 adjacent particle columns and marches down the particle rows: every lane evaluates its
+// particle once (weights as in mp4_axis, zero-padded to 5 per axis), the 25 products (wy wx) v travel to the lanes of
+// their target columns by warp shuffles and are added to five rolling row accumulators; the accumulator of row
+// jd - 2 is complete after particle row jd and is stored.  Lanes 2..29 own an output column (warps overlap by 4
+// columns, row chunks by 4 particle rows).  Contributions reach every node in the order the reference's sequential
+// loop produces them (particle rows ascending -- the mirror half first --, columns ascending; particles_to_mesh_2D.hpp
+// :273-321), with the same product expression, so the result is the reference's bit for bit -- the atomic scatter is
+// not.  Particles that move a cell or more ("far") are left out here, flagged, and scattered by k_p2m_lattice_far.
+constexpr int PG_OUT = 28;             // output columns per warp
+constexpr int PG_WARPS = 4;
+constexpr double PG_FAR = 0.99;        // |u dt| >= PG_FAR dx -> far particle (margin against rounding of pos / dx)
+
+__device__ __forceinline__ void pad5(const double w[4], int d, double o[5]) {   // d = hi - i in {0, 1}
+  o[0] = d ? 0.0 : w[0];
+  o[1] = d ? w[0] : w[1];
+  o[2] = d ? w[1] : w[2];
+  o[3] = d ? w[2] : w[3];
+  o[4] = d ? w[3] : 0.0;
+}
+__device__ __forceinline__ double shfl_from(double v, int delta) {   // value of lane (own lane - delta)
+  return delta > 0 ? __shfl_up_sync(0xffffffffu, v, delta) : (delta < 0 ? __shfl_down_sync(0xffffffffu, v, -delta) : v);
+}
+
+__global__ void __launch_bounds__(32 * PG_WARPS)
+    k_p2m_lattice_gather(GridD g, int RB, double* __restrict__ w_out, const double* __restrict__ w_in,
+                         const double* __restrict__ u_z, const double* __restrict__ u_r, const double* __restrict__ zl,
+                         const double* __restrict__ rl, double dt, const double* __restrict__ dt_dev, int* far_flag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * PG_WARPS + warp) * PG_OUT;       // first output column of the warp
+  if (c0 >= g.nz) return;
+  const int i = c0 - 2 + lane;                                   // particle column of the lane (= its output column)
+  const bool col_ok = i >= 0 && i < g.nz;
+  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  {
+    const long long fo = member_field(g);
+    w_out += fo; w_in += fo; u_z += fo; u_r += fo;
+  }
+  if (dt_dev) dt = dt_dev[member_scalar(g)];
+  const double zi = col_ok ? zl[i] : 0.0;
+  const double far = PG_FAR * g.dx;
+  const bool owner = lane >= 2 && lane < 2 + PG_OUT && col_ok;
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};                      // output rows jd-2 .. jd+2 (doubled-grid rows)
+  const int jd_first = g.nr + j0 - 2, jd_last = g.nr + j1 + 1;
+  // particle row jd: source row j of the physical half, mirrored (sign -1) below the axis
+  auto fetch = [&](int jd, double& uz, double& ur, double& v) {
+    uz = 0.0; ur = 0.0; v = 0.0;
+    if (jd < 0 || jd >= 2 * g.nr || !col_ok) return;
+    const bool upper = jd >= g.nr;
+    const long long src = (long long)(upper ? jd - g.nr : g.nr - 1 - jd) * g.ld + i;
+    uz = u_z[src];
+    ur = upper ? u_r[src] : -u_r[src];
+    v = upper ? w_in[src] : -w_in[src];
+  };
+  double uz_n, ur_n, v_n;
+  fetch(jd_first, uz_n, ur_n, v_n);
+  bool any_far = false;
+  for (int jd = jd_first; jd <= jd_last; ++jd) {
+    const double uz = uz_n, ur = ur_n, v = v_n;
+    fetch(jd + 1 <= jd_last ? jd + 1 : -1, uz_n, ur_n, v_n);      // next row's loads fly during this row's arithmetic
+    double wxp[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, wyp[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double val = 0.0;
+    const bool live = col_ok && jd >= 0 && jd < 2 * g.nr;
+    if (live) {
+      const double mz = uz * dt, mr = ur * dt;
+      if (fabs(mz) >= far || fabs(mr) >= far) {
+        // recorded once: by the lane that owns the column, for the physical-half row of the block's own rows
+        if (owner && jd >= g.nr + j0 && jd < g.nr + j1) any_far = true;
+      } else {
+        double wx[4], wy[4];
+        const int hx = mp4_axis(zi + mz, g.dx, wx);
+        const int hy = mp4_axis(rl[jd] + mr, g.dx, wy);
+        pad5(wx, hx - i, wxp);
+        pad5(wy, hy - jd, wyp);
+        val = v;
+      }
+    }
+#pragma unroll
+    for (int dr = 0; dr < 5; ++dr) {
+#pragma unroll
+      for (int dc = 4; dc >= 0; --dc) {                           // source columns ascending: i = c-2 .. c+2
+        const double t = (wyp[dr] * wxp[dc]) * val;               // particles_to_mesh_2D.hpp:316-318
+        acc[dr] = acc[dr] + shfl_from(t, dc - 2);
+      }
+    }
+    const int R = jd - 2 - g.nr;                                  // completed physical row
+    if (owner && R >= j0 && R < j1) w_out[(long long)R * g.ld + i] = acc[0];
+#pragma unroll
+    for (int dr = 0; dr < 4; ++dr) acc[dr] = acc[dr + 1];
+    acc[4] = 0.0;
+  }
+  if (far_flag && any_far) *far_flag = 1;
+}
+
+// far particles (|u dt| >= PG_FAR dx) of the gather form: atomic scatter of the particle and of its mirror image.
+// Skipped when the gather pass found none (far_flag given and zero).
+__global__ void k_p2m_lattice_far(GridD g, double* w_out, const double* __restrict__ w_in, const double* __restrict__ u_z,
+                                  const double* __restrict__ u_r, const double* __restrict__ zl, const double* __restrict__ rl,
+                                  double dt, const double* __restrict__ dt_dev, const int* far_flag) {
+  if (far_flag && *far_flag == 0) return;
+  {
+    const long long fo = member_field(g);
+    w_out += fo; w_in += fo; u_z += fo; u_r += fo;
+  }
+  if (dt_dev) dt = dt_dev[member_scalar(g)];
+  const double far = PG_FAR * g.dx;
+  for (int j = blockIdx.y; j < g.nr; j += gridDim.y) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.nz; k += gridDim.x * blockDim.x) {
+      const long long src = (long long)j * g.ld + k;
+      const double uz = u_z[src], ur = u_r[src];
+      if (!(fabs(uz * dt) >= far || fabs(ur * dt) >= far)) continue;
+      const double v = w_in[src];
+      const double pz = zl[k] + uz * dt;
+      double wx[4], wy[4];
+      const int hx = mp4_axis(pz, g.dx, wx);
+      int hy = mp4_axis(rl[g.nr + j] + ur * dt, g.dx, wy);
+      mp4_scatter(w_out, g.nr, g.nz, g.ld, 2 * g.nr, g.nr, hx, hy, wx, wy, v, false);
+      hy = mp4_axis(rl[g.nr - 1 - j] + (-ur) * dt, g.dx, wy);
+      mp4_scatter(w_out, g.nr, g.nz, g.ld, 2 * g.nr, g.nr, hx, hy, wx, wy, -v, false);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -426,14 +553,32 @@ int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const dou
   AXB_RETURN_LAST();
 }
 
-int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
-                                   const double* u_r, const double* zl1d, const double* rl1d, double dt,
-                                   const double* dt_dev, int periodic, axb_stream_t s) {
+static int g_p2m_atomic = 0;
+int axb_set_p2m_atomic(int on) {
+  g_p2m_atomic = on ? 1 : 0;
+  return AXB_OK;
+}
+
+static int advect_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z, const double* u_r,
+                            const double* zl1d, const double* rl1d, double dt, const double* dt_dev, int periodic,
+                            int32_t* far_flag, axb_stream_t s) {
   if (!w_out || !w_in || !u_z || !u_r || !zl1d || !rl1d || w_out == w_in) return AXB_EINVAL;
   int rc = axb_check_grid_batched(g);
   if (rc) return rc;
   if (g->ku0 != 0 || g->ku1 != g->nz || g->nz_global != g->nz) return AXB_ENOSUP;
   const GridD d = to_dev(g);
+  if (!periodic && !g_p2m_atomic && d.nr >= 2) {
+    // gather form: every node written exactly once (no memset), reference summation order
+    if (far_flag) cudaMemsetAsync(far_flag, 0, sizeof(int32_t), s);
+    const int rb = 64;
+    const dim3 grd((d.nz + PG_OUT * PG_WARPS - 1) / (PG_OUT * PG_WARPS), (d.nr + rb - 1) / rb, d.batch);
+    k_p2m_lattice_gather<<<grd, 32 * PG_WARPS, 0, s>>>(d, rb, w_out, w_in, u_z, u_r, zl1d, rl1d, dt, dt_dev, far_flag);
+    AXB_LAUNCHED();
+    const dim3 fg(min((d.nz + 127) / 128, 16), min(d.nr, 64), d.batch);
+    k_p2m_lattice_far<<<fg, 128, 0, s>>>(d, w_out, w_in, u_z, u_r, zl1d, rl1d, dt, dt_dev, far_flag);
+    AXB_LAUNCHED();
+    AXB_RETURN_LAST();
+  }
   if (d.batch > 1 && d.bstride == d.nz) {          // members are adjacent column blocks: one memset
     cudaMemset2DAsync(w_out, d.ld * sizeof(double), 0, (size_t)d.batch * d.nz * sizeof(double), d.nr, s);
   } else {
@@ -444,6 +589,18 @@ int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const dou
                                                                            dt_dev, periodic != 0);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
+}
+
+int axb_advect_vorticity_particles(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
+                                   const double* u_r, const double* zl1d, const double* rl1d, double dt,
+                                   const double* dt_dev, int periodic, axb_stream_t s) {
+  return advect_particles(g, w_out, w_in, u_z, u_r, zl1d, rl1d, dt, dt_dev, periodic, nullptr, s);
+}
+int axb_advect_vorticity_particles_flagged(const axb_grid_t* g, double* w_out, const double* w_in, const double* u_z,
+                                           const double* u_r, const double* zl1d, const double* rl1d, double dt,
+                                           const double* dt_dev, int32_t* far_flag, axb_stream_t s) {
+  if (!far_flag) return AXB_EINVAL;
+  return advect_particles(g, w_out, w_in, u_z, u_r, zl1d, rl1d, dt, dt_dev, 0, far_flag, s);
 }
 
 }  // extern "C"

@@ -480,6 +480,7 @@ class ParticleFlowStepper:
         _call("axb_smooth_heaviside_sphere", F.g, ptr(self.part_char_func), None, ptr(self.z1d), ptr(self.r1d),
               self.part_Z_cm, self.part_R_cm, self.r_part, self.moll_zone, s)
         self._acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+        self._far_flag = torch.zeros(1, dtype=torch.int32, device="cuda")   # remesh: set when a particle moved >= a cell
         ones = F.new(1) if _pool is not None else torch.empty((nr, nz), dtype=torch.float64, device="cuda")
         ones.fill_(1.0)
         _call("axb_reduce_weighted_sum", F.g, ptr(self.r1d), ptr(self.part_char_func), ptr(ones), 0.0, ptr(self._acc), s)
@@ -496,6 +497,13 @@ class ParticleFlowStepper:
             self.state[6] = self.part_Z_cm
             self.trace_dev = torch.zeros((int(trace_capacity), 5), dtype=torch.float64, device="cuda")
             self.avg_psi_last, self.avg_vort_last, self.avg_part_char_func_last = F.new(3)
+            # the bubble does not move: (d^2)^1.5 and the inside flag once (axb_bubble_flow_geometry)
+            self.bubble_geom = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
+            gg = make_grid(nr, nz, nz, dx)
+            chi_b = self.bubble_char_func.contiguous()
+            _call("axb_bubble_flow_geometry", ctypes.byref(gg), ptr(self.bubble_geom), ptr(chi_b), ptr(self.z1d),
+                  ptr(self.r1d), self.bubble_Z_cm, self.bubble_R_cm, s)
+            torch.cuda.current_stream().synchronize()
         self.t, self.it, self.dt = 0.0, 0, 0.0
         # per-cycle averages (particle_in_bubble_oscillatory_flow.py:102-109, 168-263, 297-301, 355)
         self.freqTimer, self.avg_Z_cm, self.avg_time = 0.0, 0.0, 0.0
@@ -553,7 +561,7 @@ class ParticleFlowStepper:
               None, None, s)
         _call("axb_reduce_max_abs_sum", g, ptr(w), None, sp(2), s)         # state[2] was zeroed by phase 2
         self._scalars_dev(1)
-        _call("axb_add_bubble_flow_dev", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_char_func),
+        _call("axb_add_bubble_flow_geom", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.bubble_geom), self.nz,
               ptr(self.z1d), ptr(self.r1d), self.bubble_Z_cm, self.bubble_R_cm, self.r0_bubble, self.U_0, None, sp(9), s)
         _call("axb_cycle_average3", g, ptr(self.avg_part_char_func), ptr(self.part_char_func),
               ptr(self.avg_part_char_func_last), ptr(self.avg_psi), ptr(self.psi), ptr(self.avg_psi_last),
@@ -563,8 +571,8 @@ class ParticleFlowStepper:
         _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
               ptr(self.u_r_upen), ptr(self.part_char_func), self.brink_lam, 0.0, sp(1), 0.0, 0.0, sp(4), ptr(self.r1d),
               sp(3), s)
-        _call("axb_advect_vorticity_particles", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), ptr(self.z1d),
-              ptr(self.rl_double), 0.0, sp(1), 0, s)
+        _call("axb_advect_vorticity_particles_flagged", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r),
+              ptr(self.z1d), ptr(self.rl_double), 0.0, sp(1), ptr(self._far_flag), s)
         # RK2 diffusion lands the result back in `vorticity` (stage 2 takes its base field from _w2): no buffer swap,
         # so the launch sequence is the same every step and can be replayed as a CUDA graph
         _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(self._w2), ptr(self.r1d), self.nu, 0.0, sp(1), s)
@@ -645,8 +653,8 @@ class ParticleFlowStepper:
         _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w), ptr(self.u_z_upen),
               ptr(self.u_r_upen), ptr(self.part_char_func), self.brink_lam, dt, None, self.U_z_cm_part, 0.0, None,
               ptr(self.r1d), sum_ptr, s)
-        _call("axb_advect_vorticity_particles", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r), ptr(self.z1d),
-              ptr(self.rl_double), dt, None, 0, s)
+        _call("axb_advect_vorticity_particles_flagged", g, ptr(self._w2), ptr(w), ptr(self.u_z), ptr(self.u_r),
+              ptr(self.z1d), ptr(self.rl_double), dt, None, ptr(self._far_flag), s)
         self.vorticity, self._w2 = self._w2, self.vorticity
         w = self.vorticity
         _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(w), ptr(self.r1d), self.nu, dt, None, s)
@@ -757,6 +765,7 @@ class ParticleEnsemble:
             self.state[i, 19:24] = torch.tensor([m.omega, m.freqTimer_limit, m.U_0, m.nu, 0.9 * m.dx ** 2 / 4 / m.nu],
                                                 dtype=torch.float64)
             m.state, m.trace_dev = self.state[i], self.trace_dev[i]
+            m.bubble_geom = m0.bubble_geom               # same bubble for every member
             if abs(m.part_vol - m0.part_vol) > 1e-14 * m0.part_vol or (m.bubble_Z_cm, m.r0_bubble, m.r_part) != \
                     (m0.bubble_Z_cm, m0.r0_bubble, m0.r_part):
                 raise ValueError("the members of a batched ensemble differ in (freq, e) only")
@@ -791,7 +800,7 @@ class ParticleEnsemble:
         _call("axb_velocity_from_psi", g, ptr(m.u_z_upen), ptr(m.u_r_upen), ptr(m.psi), ptr(m.r1d), 0.0, 0.0, None, None, s)
         _call("axb_reduce_max_abs_sum", g, ptr(w), None, sp(2), s)
         scalars(1)
-        _call("axb_add_bubble_flow_dev", g, ptr(m.u_z_upen), ptr(m.u_r_upen), ptr(m.bubble_char_func), ptr(m.z1d),
+        _call("axb_add_bubble_flow_geom", g, ptr(m.u_z_upen), ptr(m.u_r_upen), ptr(m.bubble_geom), m.nz, ptr(m.z1d),
               ptr(m.r1d), m.bubble_Z_cm, m.bubble_R_cm, m.r0_bubble, 0.0, sp(21), sp(9), s)
         _call("axb_cycle_average3", g, ptr(m.avg_part_char_func), ptr(m.part_char_func), ptr(m.avg_part_char_func_last),
               ptr(m.avg_psi), ptr(m.psi), ptr(m.avg_psi_last), ptr(m.avg_vort), ptr(w), ptr(m.avg_vort_last), sp(10),
@@ -800,8 +809,8 @@ class ParticleEnsemble:
               m.part_R_cm, m.r_part, m.moll_zone, s)
         _call("axb_penalise_update_vorticity", g, ptr(m.u_z), ptr(m.u_r), ptr(w), ptr(m.u_z_upen), ptr(m.u_r_upen),
               ptr(m.part_char_func), m.brink_lam, 0.0, sp(1), 0.0, 0.0, sp(4), ptr(m.r1d), sp(3), s)
-        _call("axb_advect_vorticity_particles", g, ptr(m._w2), ptr(w), ptr(m.u_z), ptr(m.u_r), ptr(m.z1d),
-              ptr(m.rl_double), 0.0, sp(1), 0, s)
+        _call("axb_advect_vorticity_particles_flagged", g, ptr(m._w2), ptr(w), ptr(m.u_z), ptr(m.u_r), ptr(m.z1d),
+              ptr(m.rl_double), 0.0, sp(1), ptr(m._far_flag), s)
         _call("axb_diffusion_rk2_stage1_dev", g, ptr(m._tmp), ptr(m._w2), ptr(m.r1d), sp(22), sp(1), s)
         _call("axb_diffusion_rk2_stage2_dev", g, ptr(w), ptr(m._w2), ptr(m._tmp), ptr(m.r1d), sp(22), sp(1), s)
         scalars(2)

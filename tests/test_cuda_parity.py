@@ -1129,7 +1129,15 @@ def test_p2m(K):
     w2 = np.zeros_like(g["w0"])
     K.advect_vorticity_via_lattice_particles(w2, g["w0"], g["uz"], g["ur"], g["Zl"][0], g["Rl"][:, 0], dx,
                                              float(g["dt"]))
-    assert_close(w2, g["w_adv"], 1e-14, "fused lattice remesh")
+    assert np.array_equal(w2, g["w_adv"]), "gather form: the reference's summation order, bit for bit"
+    from pyaxisymflow_b200 import _lib
+    _lib.call("axb_set_p2m_atomic", 1)
+    try:
+        K.advect_vorticity_via_lattice_particles(w2, g["w0"], g["uz"], g["ur"], g["Zl"][0], g["Rl"][:, 0], dx,
+                                                 float(g["dt"]))
+    finally:
+        _lib.call("axb_set_p2m_atomic", 0)
+    assert_close(w2, g["w_adv"], 1e-14, "fused lattice remesh, atomic scatter")
     # mass conservation away from the edges: MP4 weights sum to one
     n0, n1 = 64, 96
     rng = np.random.default_rng(10)
@@ -1140,6 +1148,34 @@ def test_p2m(K):
     mesh = np.zeros((n0, n1))
     K.particles_to_mesh_2D_unbounded_mp4(px, py, val, mesh, dx, dx)
     assert abs(mesh.sum() - val.sum()) <= 1e-12 * np.abs(val).sum()
+
+
+@pytest.mark.parametrize("nr,nz,far", [(150, 300, 0), (150, 300, 40), (7, 29, 0), (2, 5, 3), (70, 113, 9)])
+def test_lattice_remesh_gather_form(K, nr, nz, far):
+    """axb_advect_vorticity_particles (periodic = 0): warp-shuffle gather, bit-identical to the sequential remesh of
+    kernels/advect_particle.py:18-35 for displacements below one cell (several warps / row chunks, ragged edges);
+    `far` particles moved by 1-3 cells go through the atomic pass (agreement to rounding)."""
+    rng = np.random.default_rng(nr * 1000 + nz + far)
+    dx = 1.0 / nz
+    dt = 0.37 * dx
+    z = np.linspace(dx / 2, 1 - dx / 2, nz)
+    rd = np.linspace(dx / 2, 2 * nr * dx - dx / 2, 2 * nr)
+    uz = rng.uniform(-0.95, 0.95, (nr, nz)) * dx / dt
+    ur = rng.uniform(-0.95, 0.95, (nr, nz)) * dx / dt
+    for _ in range(far):
+        j, k = rng.integers(0, nr), rng.integers(0, nz)
+        uz[j, k] = rng.choice([-1, 1]) * rng.uniform(1.0, 3.0) * dx / dt
+        ur[j, k] = rng.choice([-1, 1]) * rng.uniform(0.0, 3.0) * dx / dt
+    w0 = rng.standard_normal((nr, nz))
+    Zd, Rd = np.meshgrid(z, rd)
+    want = w0.copy()
+    ox.advect_vorticity_via_particles(Zd.copy(), Rd.copy(), 0 * Zd, want, Zd, Rd, nr, uz, ur, dx, dt)
+    got = np.full_like(w0, 3.0)
+    K.advect_vorticity_via_lattice_particles(got, w0, uz, ur, z, rd, dx, dt)
+    if far == 0:
+        assert np.array_equal(got, want)
+    else:
+        assert_close(got, want, 1e-14, "gather + far-particle scatter")
 
 
 # ---------------------------------------------------------------------------------------------

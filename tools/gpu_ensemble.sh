@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 T=${TAG:-r02w}
 timeout 600 python -m pytest tests/test_widen_cuda.py -q --timeout=300 -m gpu 2>&1 | tail -15 | cut -c1-400 > gpurun_out/${T}_widen_tests.txt
-timeout 200 python -m pytest tests/test_cuda_parity.py -q --timeout=180 -m gpu -k "particle or soft_sphere" 2>&1 | tail -3 >> gpurun_out/${T}_widen_tests.txt
+timeout 200 python -m pytest tests/test_cuda_parity.py -q --timeout=180 -m gpu -k "particle or soft_sphere or p2m or remesh" 2>&1 | tail -15 | cut -c1-300 >> gpurun_out/${T}_widen_tests.txt
 for mode in streams members batched; do
   AXB_ENSEMBLE=$mode timeout 300 python bench.py --config c5 --no-cpu --steps 20 --warmup 3 > gpurun_out/${T}_bench_c5_$mode.json 2> gpurun_out/${T}_bench_c5_$mode.err
 done
