@@ -395,8 +395,11 @@ class _ConfigRunner:
         if name == "c3":
             # Z_cm off the grid's mirror plane when re-initialising: exact ties make the marcher (and the GPU
             # iteration) order/rounding dependent and cost extra sweeps
+            # without the re-initialisation the step runs device resident (loop scalars and the LS sweep loop on the
+            # device) as one replayed CUDA graph; AXB_SOFT_HOST=1 keeps the host-driven loop
+            dev = not reinit and not os.environ.get("AXB_SOFT_HOST")
             self.members = [SoftSphereStepper(nz, grid_size_r=nr, basis=basis, reinit_levelset=reinit,
-                                              Z_cm=0.47 if reinit else 0.5)]
+                                              Z_cm=0.47 if reinit else 0.5, device_scalars=dev, use_graph=dev)]
         else:
             from pyaxisymflow_b200.timestep import ParticleEnsemble
 

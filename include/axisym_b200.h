@@ -265,6 +265,15 @@ int axb_add_bubble_flow(const axb_grid_t* g, double* u_z, double* u_r, const dou
 int axb_particle_scalars(int phase, double* state, double* trace, int trace_cap, double dt_diff_limit, double cfl,
                          double eps, double cycle, double omega, double rho_lam, double part_vol, double part_mass,
                          double bubble_z_cm, double r0_bubble, axb_stream_t s);
+/* the soft-sphere driver's scalars (soft_sphere_streaming.py:139-176, 201-203, 236-241, 262-264)
+ * on a device block of >= 10 doubles:  [0] t  [1] dt  [2] max(|u_z|+|u_r|) (reduction target)  [3] freqTimer
+ * [4] U_0 cos(omega t)  [5] 0  [6] Z_cm + amplitude sin(omega t)  [7] cycles  [8] wrap flag of the previous step  [9] it.
+ * phase 1 (after the velocity maximum): dt with the cycle / tEnd clamps and the tether's velocity and position;
+ * phase 2 (end of the step): t, the cycle timer and its wrap.  axb_cycle_average3 accepts fewer than three fields
+ * (avg1 / avg2 NULL). */
+int axb_soft_sphere_scalars(int phase, double* state, double dt_wave_limit, double cfl_dx, double eps, double dt_diff_limit,
+                            double cycle, double t_end, double omega, double U_0, double Z_cm, double amplitude,
+                            axb_stream_t s);
 int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, double* last0, double* avg1, const double* x1,
                        double* last1, double* avg2, const double* x2, double* last2, const double* a_dev,
                        const double* wrap_dev, axb_stream_t s);
@@ -326,6 +335,16 @@ int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const ui
                            double* eta1, double* eta2, double extrap_zone, const double* gx,
                            const double* gy, void* work, int64_t work_bytes, int max_sweeps,
                            int* sweeps_host, axb_stream_t s);
+/* The same without a host round trip (graph capturable): exactly `sweeps` (1..28) sweeps are enqueued on a fixed grid,
+ * each reading its cell counts from the device; a sweep with nothing left to do costs an empty launch, a sweep that
+ * finds no candidate ends the extrapolation like the reference's early return.  status_dev (device int[2], may be NULL)
+ * <- {bit 0: pending list overflowed the workspace, bit 1: cells were still being added in the last sweep; number of
+ * sweeps that added cells}.  Input and output reference maps may be different arrays (the output is written for every
+ * cell), which lets a driver advect into a scratch pair and land the extrapolated maps back in the original one. */
+int axb_ls_extrapolate_eta_device(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                                  const double* eta1_in, const double* eta2_in, double* eta1_out, double* eta2_out,
+                                  double extrap_zone, const double* gx, const double* gy, void* work,
+                                  int64_t work_bytes, int sweeps, int32_t* status_dev, axb_stream_t s);
 
 /* ---- a21: core/src/particles_to_mesh.hpp:163-184 (periodic = 0) and the periodic twin
  *      particles_to_mesh_2D_mp4.  mesh is zeroed first, like the reference. ------------------ */

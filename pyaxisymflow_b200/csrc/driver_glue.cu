@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(TBX* TBY)
   const long long fo = member_field(g);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
+    if (!f.avg[i]) continue;                       // fewer than three fields
     const double2 xv = ld_pair(rowp(f.x[i] + fo, g.ld, j), k, g.nz, vec);
     double2 yv = ld_pair(rowp(f.avg[i] + fo, g.ld, j), k, g.nz, vec);
     if (wrap) {
@@ -239,6 +240,38 @@ __global__ void k_particle_scalars(int phase, double* st, double* trace, int tra
   }
 }
 
+
+// The host decisions of one soft-sphere step (soft_sphere_streaming.py:139-176, 201-203, 236-241, 262-264) on a
+// device block:  st[0] t  [1] dt  [2] max(|u_z| + |u_r|) (reduction target)  [3] freqTimer  [4] U_0 cos(omega t)
+//   [5] 0 (U_r)  [6] Z_cm + e r_ball sin(omega t)  [7] cycles  [8] wrap flag: the previous step completed a cycle (the
+//   running averages restart)  [9] it
+struct SoftParams {
+  double dt_wave, cfl_dx, eps, dt_diff, cycle, t_end, omega, U0, Z_cm, amp;
+};
+__global__ void k_soft_scalars(int phase, double* st, SoftParams p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (phase == 1) {
+    double dt = fmin(fmin(p.dt_wave, p.cfl_dx / (st[2] + p.eps)), p.dt_diff);
+    if (st[3] + dt > p.cycle) dt = p.cycle - st[3];
+    if (st[0] + dt > p.t_end) dt = p.t_end - st[0];
+    st[1] = dt;
+    st[4] = p.U0 * cos(p.omega * st[0]);
+    st[6] = p.Z_cm + p.amp * sin(p.omega * st[0]);
+  } else {
+    st[0] = st[0] + st[1];
+    st[3] = st[3] + st[1];
+    double wrap = 0.0;
+    if (st[3] >= p.cycle) {
+      st[3] = 0.0;
+      st[7] = st[7] + 1.0;
+      wrap = 1.0;
+    }
+    st[8] = wrap;
+    st[2] = 0.0;
+    st[9] = st[9] + 1.0;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -246,7 +279,7 @@ extern "C" {
 int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, double* last0, double* avg1, const double* x1,
                        double* last1, double* avg2, const double* x2, double* last2, const double* a_dev,
                        const double* wrap_dev, axb_stream_t s) {
-  if (!avg0 || !x0 || !avg1 || !x1 || !avg2 || !x2 || !a_dev || !wrap_dev) return AXB_EINVAL;
+  if (!avg0 || !x0 || (!avg1 != !x1) || (!avg2 != !x2) || !a_dev || !wrap_dev) return AXB_EINVAL;
   int rc = axb_check_grid_batched(g);
   if (rc) return rc;
   const GridD d = to_dev(g);
@@ -256,6 +289,16 @@ int axb_cycle_average3(const axb_grid_t* g, double* avg0, const double* x0, doub
   f.last[0] = last0; f.last[1] = last1; f.last[2] = last2;
   k_cycle_avg3<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, f, a_dev, wrap_dev,
                                                    vec_ok(d, {avg0, x0, last0, avg1, x1, last1, avg2, x2, last2}));
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_soft_sphere_scalars(int phase, double* state, double dt_wave_limit, double cfl_dx, double eps, double dt_diff_limit,
+                            double cycle, double t_end, double omega, double U_0, double Z_cm, double amplitude,
+                            axb_stream_t s) {
+  if (!state || (phase != 1 && phase != 2)) return AXB_EINVAL;
+  const SoftParams p = {dt_wave_limit, cfl_dx, eps, dt_diff_limit, cycle, t_end, omega, U_0, Z_cm, amplitude};
+  k_soft_scalars<<<1, 32, 0, s>>>(phase, state, p);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

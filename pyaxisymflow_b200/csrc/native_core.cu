@@ -52,29 +52,33 @@ __global__ void k_ls_collect(int n, const short* __restrict__ cur, const short* 
   }
 }
 
-// pending -> (candidate with codes | still pending)
+// pending -> (candidate with codes | still pending).  Counts live on the device (n_in pending cells, clamped to the
+// list capacity); grid-stride, so the same kernel serves the host-driven loop (grid sized from the host's copy of the
+// count) and the device-terminated one (fixed grid, the count may be anything including zero).
 __global__ void k_ls_classify(int n1, const short* __restrict__ cur, const int* __restrict__ pend_in, int* pend_out,
-                              int* cand, short* codes, int* counters) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= counters[0]) return;
-  const int c = pend_in[t];
-  short cnt = 0, sx = 0, sy = 0;
+                              int* cand, short* codes, const int* __restrict__ n_in, int* n_out, int* n_cand,
+                              long long cap) {
+  const int n = (int)min((long long)*n_in, cap);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int c = pend_in[t];
+    short cnt = 0, sx = 0, sy = 0;
 #pragma unroll
-  for (int dj = -1; dj <= 1; ++dj)
+    for (int dj = -1; dj <= 1; ++dj)
 #pragma unroll
-    for (int dk = -1; dk <= 1; ++dk) {
-      const short f = cur[c + dj * n1 + dk];
-      if (dj != 0 || dk != 0) cnt += f;
-      sx += f * (short)(dk + 1);
-      sy += f * (short)(dj + 1);
+      for (int dk = -1; dk <= 1; ++dk) {
+        const short f = cur[c + dj * n1 + dk];
+        if (dj != 0 || dk != 0) cnt += f;
+        sx += f * (short)(dk + 1);
+        sy += f * (short)(dj + 1);
+      }
+    if (cnt) {
+      const int slot = atomicAdd(n_cand, 1);
+      cand[slot] = c;
+      codes[slot] = (short)((ls_start(sx, cnt) + 3) | ((ls_start(sy, cnt) + 3) << 8));
+    } else {
+      const int slot = atomicAdd(n_out, 1);
+      pend_out[slot] = c;
     }
-  if (cnt) {
-    const int slot = atomicAdd(&counters[2], 1);
-    cand[slot] = c;
-    codes[slot] = (short)((ls_start(sx, cnt) + 3) | ((ls_start(sy, cnt) + 3) << 8));
-  } else {
-    const int slot = atomicAdd(&counters[1], 1);
-    pend_out[slot] = c;
   }
 }
 
@@ -132,10 +136,10 @@ __device__ __forceinline__ void ls_basis(double m, double x, double y, double (&
 
 template <int NC>
 __global__ void k_ls_solve(int n1, const short* __restrict__ cur, const int* __restrict__ cand,
-                           const short* __restrict__ codes, const int* __restrict__ counters, double* eta_x,
+                           const short* __restrict__ codes, const int* __restrict__ n_cand, double* eta_x,
                            double* eta_y, const double* __restrict__ gx, const double* __restrict__ gy) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= counters[2]) return;
+  const int n = *n_cand;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
   const int c = cand[t];
   const int j = c / n1, k = c - j * n1;
   const int code = codes[t];
@@ -184,11 +188,24 @@ __global__ void k_ls_solve(int n1, const short* __restrict__ cur, const int* __r
 #pragma unroll
   for (int i = 0; i < NC; ++i) e += sol[1][i] * basis[i];
   eta_y[c] = e;
+  }
 }
 
-__global__ void k_ls_flag(short* cur, const int* __restrict__ cand, int* counters) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < counters[2]) cur[cand[t]] = 1;
+// sweeps_done (may be null) <- sweep + 1 when this sweep added cells
+__global__ void k_ls_flag(short* cur, const int* __restrict__ cand, const int* __restrict__ n_cand, int* sweeps_done,
+                          int sweep) {
+  const int n = *n_cand;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) cur[cand[t]] = 1;
+  if (sweeps_done && n > 0 && blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep + 1;
+}
+// device-terminated form, after the last sweep: status bit 0 = the pending list overflowed its capacity, bit 1 = the
+// sweep budget ran out while cells were still being added; out = {status, sweeps that added cells}
+__global__ void k_ls_finish(const int* __restrict__ ctr, int sweeps, long long cap, int* out) {
+  int st = 0;
+  if (ctr[4] > cap) st |= 1;
+  if (ctr[4 + 2 * sweeps] > 0 && ctr[4 + 2 * (sweeps - 1) + 1] > 0) st |= 2;
+  out[0] = st;
+  out[1] = ctr[1];
 }
 // after a sweep: pending-in <- pending-out, zero the other counters (single thread)
 __global__ void k_ls_roll(int* counters) {
@@ -228,10 +245,11 @@ int ls_run(int order, int n0, int n1, short* cur, const short* tgt, double* eta_
   int *pin = w.pend_a, *pout = w.pend_b;
   while (pending > 0 && (max_sweeps <= 0 || sweeps < max_sweeps)) {
     const int blocks = (pending + 127) / 128;
-    k_ls_classify<<<blocks, 128, 0, s>>>(n1, cur, pin, pout, w.cand, w.codes, w.counters);
-    if (order == 2) k_ls_solve<6><<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters, eta_x, eta_y, gx, gy);
-    else k_ls_solve<3><<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters, eta_x, eta_y, gx, gy);
-    k_ls_flag<<<blocks, 128, 0, s>>>(cur, w.cand, w.counters);
+    k_ls_classify<<<blocks, 128, 0, s>>>(n1, cur, pin, pout, w.cand, w.codes, w.counters, w.counters + 1,
+                                         w.counters + 2, cap);
+    if (order == 2) k_ls_solve<6><<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters + 2, eta_x, eta_y, gx, gy);
+    else k_ls_solve<3><<<blocks, 128, 0, s>>>(n1, cur, w.cand, w.codes, w.counters + 2, eta_x, eta_y, gx, gy);
+    k_ls_flag<<<blocks, 128, 0, s>>>(cur, w.cand, w.counters + 2, nullptr, 0);
     g_axb_launches += 3;
     cudaMemcpyAsync(h, w.counters, sizeof(h), cudaMemcpyDeviceToHost, s);
     k_ls_roll<<<1, 1, 0, s>>>(w.counters);
@@ -244,6 +262,44 @@ int ls_run(int order, int n0, int n1, short* cur, const short* tgt, double* eta_
     int* t = pin; pin = pout; pout = t;
   }
   if (sweeps_host) *sweeps_host = sweeps;
+  return (int)cudaGetLastError();
+}
+
+// The same sweeps without a host round trip (graph capturable): every sweep has its own counter pair
+//   ctr[4 + 2 s] = cells pending before sweep s,  ctr[4 + 2 s + 1] = candidates found in sweep s   (ctr[1] = sweeps done)
+// so nothing has to be rolled between sweeps; the kernels run on a fixed grid and read their counts from the device.
+// A sweep that finds no candidate leaves the pending list as it is, and so do all later ones: the result is the one
+// of the host-driven loop, which stops there (extrapolate_using_least_squares.hpp:372-375).
+constexpr int LS_MAX_SWEEPS = 28;            // 4 + 2 (sweeps + 1) ints fit the 256-byte counter block
+int ls_run_device(int order, int n0, int n1, short* cur, const short* tgt, double* eta_x, double* eta_y, const double* gx,
+                  const double* gy, void* work, long long work_bytes, int sweeps, int* status_dev, cudaStream_t s) {
+  if (sweeps < 1 || sweeps > LS_MAX_SWEEPS) return AXB_EINVAL;
+  const long long cap = (work_bytes - 256) / 14;
+  if (cap < 1) return AXB_EWORK;
+  char* p = (char*)work;
+  int* ctr = (int*)p; p += 256;
+  int* pend[2];
+  pend[0] = (int*)p; p += cap * 4;
+  pend[1] = (int*)p; p += cap * 4;
+  int* cand = (int*)p; p += cap * 4;
+  short* codes = (short*)p;
+  const int n = n0 * n1;
+  cudaMemsetAsync(ctr, 0, 256, s);
+  k_ls_collect<<<(n + 255) / 256, 256, 0, s>>>(n, cur, tgt, pend[0], ctr + 4, cap);
+  AXB_LAUNCHED();
+  const int blocks = (int)min((cap + 127) / 128, 148LL * 4);
+  for (int i = 0; i < sweeps; ++i) {
+    int *n_in = ctr + 4 + 2 * i, *n_cand = n_in + 1, *n_out = n_in + 2;
+    k_ls_classify<<<blocks, 128, 0, s>>>(n1, cur, pend[i & 1], pend[(i + 1) & 1], cand, codes, n_in, n_out, n_cand, cap);
+    if (order == 2) k_ls_solve<6><<<blocks, 128, 0, s>>>(n1, cur, cand, codes, n_cand, eta_x, eta_y, gx, gy);
+    else k_ls_solve<3><<<blocks, 128, 0, s>>>(n1, cur, cand, codes, n_cand, eta_x, eta_y, gx, gy);
+    k_ls_flag<<<blocks, 128, 0, s>>>(cur, cand, n_cand, ctr + 1, i);
+    g_axb_launches += 3;
+  }
+  if (status_dev) {
+    k_ls_finish<<<1, 1, 0, s>>>(ctr, sweeps, cap, status_dev);
+    AXB_LAUNCHED();
+  }
   return (int)cudaGetLastError();
 }
 
@@ -496,7 +552,7 @@ int64_t axb_ls_workspace_bytes(int n0, int n1) {
   // fused wrapper is appended (20 bytes per cell).
   const long long n = (long long)n0 * n1;
   long long cap = n / 4 + 4096;
-  return 64 + cap * 14 + 256 + n * 20;
+  return 512 + cap * 14 + 256 + n * 20;
 }
 
 int axb_ls_extrapolate_order1(int n0, int n1, int16_t* cur, const int16_t* tgt, double* eta_x,
@@ -513,11 +569,11 @@ int axb_ls_extrapolate_order2(int n0, int n1, int16_t* cur, const int16_t* tgt, 
   return ls_run(2, n0, n1, cur, tgt, eta_x, eta_y, gx, gy, work, work_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
 }
 
-int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
-                           double* eta1, double* eta2, double extrap_zone, const double* gx,
-                           const double* gy, void* work, int64_t work_bytes, int max_sweeps,
-                           int* sweeps_host, axb_stream_t s) {
-  if (!ball_phi || !inside_solid || !eta1 || !eta2 || !gx || !gy || !work) return AXB_EINVAL;
+static int ls_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid, const double* eta1_in,
+                  const double* eta2_in, double* eta1, double* eta2, double extrap_zone, const double* gx,
+                  const double* gy, void* work, int64_t work_bytes, int max_sweeps, int* sweeps_host, int* status_dev,
+                  bool device_loop, axb_stream_t s) {
+  if (!ball_phi || !inside_solid || !eta1 || !eta2 || !eta1_in || !eta2_in || !gx || !gy || !work) return AXB_EINVAL;
   int rc = axb_check_grid(g);
   if (rc) return rc;
   if (g->ku0 != 0 || g->ku1 != g->nz || g->nz_global != g->nz) return AXB_ENOSUP;  // single-slab only
@@ -526,7 +582,7 @@ int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const ui
   // staging: e1, e2 (double), cur, tgt (int16) on the doubled grid, 256-byte aligned
   char* p = (char*)work;
   const long long stage = n * 20;
-  if (work_bytes < stage + 256 + 64 + 14) return AXB_EWORK;
+  if (work_bytes < stage + 256 + 256 + 14) return AXB_EWORK;
   double* e1 = (double*)p;
   double* e2 = e1 + n;
   short* cur = (short*)(e2 + n);
@@ -535,13 +591,31 @@ int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const ui
   rest = (char*)(((uintptr_t)rest + 255) & ~(uintptr_t)255);
   const long long rest_bytes = work_bytes - (rest - p);
   dim3 grd((nz + 127) / 128, nr);
-  k_ls_fill<<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1, eta2, extrap_zone, cur, tgt, e1, e2);
+  k_ls_fill<<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt, e1, e2);
   AXB_LAUNCHED();
-  rc = ls_run(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
+  if (device_loop)
+    rc = ls_run_device(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, status_dev, (cudaStream_t)s);
+  else
+    rc = ls_run(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
   if (rc) return rc;
   k_ls_unfill<<<grd, 128, 0, s>>>(nr, nz, g->ld, eta1, eta2, e1, e2);
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
+}
+
+int axb_ls_extrapolate_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                           double* eta1, double* eta2, double extrap_zone, const double* gx,
+                           const double* gy, void* work, int64_t work_bytes, int max_sweeps,
+                           int* sweeps_host, axb_stream_t s) {
+  return ls_eta(g, ball_phi, inside_solid, eta1, eta2, eta1, eta2, extrap_zone, gx, gy, work, work_bytes, max_sweeps,
+                sweeps_host, nullptr, false, s);
+}
+int axb_ls_extrapolate_eta_device(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                                  const double* eta1_in, const double* eta2_in, double* eta1_out, double* eta2_out,
+                                  double extrap_zone, const double* gx, const double* gy, void* work,
+                                  int64_t work_bytes, int sweeps, int32_t* status_dev, axb_stream_t s) {
+  return ls_eta(g, ball_phi, inside_solid, eta1_in, eta2_in, eta1_out, eta2_out, extrap_zone, gx, gy, work, work_bytes,
+                sweeps, nullptr, status_dev, true, s);
 }
 
 int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const double* val, double* mesh,

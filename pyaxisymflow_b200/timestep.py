@@ -321,9 +321,11 @@ class SoftSphereStepper:
 
     def __init__(self, grid_size_z=256, domain_AR=0.5, grid_size_r=None, r_ball=0.15, freq=16.0, nond_AC=0.125,
                  e=0.1, Cauchy=0.1, zeta=0.25, brink_lam=1e8, CFL=0.1, rho_f=1.0, Z_cm=0.5, R_cm=0.0, basis="auto",
-                 reinit_levelset=False):
+                 reinit_levelset=False, device_scalars=False, use_graph=False, ls_sweeps=12):
         if not torch.cuda.is_available():
             raise _lib.AxbError("SoftSphereStepper needs a CUDA device (no CPU fallback)")
+        if device_scalars and reinit_levelset:
+            raise ValueError("the level-set re-initialisation polls a host flag: not available with device_scalars")
         nz = int(grid_size_z)
         nr = int(grid_size_r) if grid_size_r is not None else int(domain_AR * nz)
         dx = 1.0 / nz
@@ -371,10 +373,99 @@ class SoftSphereStepper:
         self.t, self.freqTimer, self.it, self.dt = 0.0, 0.0, 0, 0.0
         self.cycles, self.on_cycle = 0, None      # on_cycle(stepper): called with the completed-cycle averages
         self.tEnd = 30 / freq
+        # device-resident loop scalars (include/axisym_b200.h, axb_soft_sphere_scalars): no host round trip per step,
+        # the LS extrapolation with device-terminated sweeps, the whole step one replayed CUDA graph
+        self.device_scalars = bool(device_scalars)
+        self._use_graph, self._graph = bool(use_graph) and self.device_scalars, None
+        if self.device_scalars:
+            self.state = torch.zeros(16, dtype=torch.float64, device="cuda")
+            self._ls_status = torch.zeros(2, dtype=torch.int32, device="cuda")
+            self._ls_sweeps = int(ls_sweeps)
+            self.avg_psi_last, self.avg_phi_last = F.new(2)
+            self.ls_sweeps = 0
 
     def step(self, n=1):
+        if not self.device_scalars:
+            for _ in range(n):
+                self._one()
+            return
+        if not self._use_graph:
+            for _ in range(n):
+                self._one_dev()
+            return
+        if self._graph is None:
+            self._one_dev()                          # warm-up outside capture
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=side):
+                self._one_dev()
+            n -= 1
         for _ in range(n):
-            self._one()
+            self._graph.replay()
+
+    def _one_dev(self):
+        """the step of `_one` with every host decision on the device (state block, axb_soft_sphere_scalars) and no
+        buffer swap -- the advected reference maps / vorticity live in the scratch fields for the rest of the step
+        and the LS extrapolation / the last RK2 stage land them back in `eta1`, `eta2` / `vorticity` -- so the launch
+        sequence is the same every step"""
+        s, g, dx = stream_ptr(), self.F.g, self.dx
+        w, w2, e1b, e2b = self.vorticity, self._w2, self._e1b, self._e2b
+        base = self.state.data_ptr()
+
+        def sp(i):
+            return ctypes.c_void_p(base + 8 * i)
+
+        def scalars(phase):
+            _call("axb_soft_sphere_scalars", phase, ptr(self.state), self.CFL * dx / np.sqrt(self.G / self.rho_f),
+                  self.CFL * dx, self.eps, 0.9 * dx ** 2 / 4 / self.nu, self.freqTimer_limit, self.tEnd, self.omega,
+                  self.U_0, self.Z_cm, self.e * self.r_ball, s)
+
+        _call("axb_kill_boundary_vorticity_sine_z", g, ptr(w), ptr(self.z1d), 3, s)
+        _call("axb_kill_boundary_vorticity_sine_r", g, ptr(w), ptr(self.r1d), 3, s)
+        _lib.call("axb_fd_solve", ctypes.byref(self.solver.plan), ptr(self.psi), self.nz, ptr(w), self.nz, s)
+        _call("axb_velocity_from_psi", g, ptr(self.u_z_upen), ptr(self.u_r_upen), ptr(self.psi), ptr(self.r1d), 0.0, 0.0,
+              None, sp(2), s)                          # state[2] was zeroed by phase 2
+        scalars(1)
+        _call("axb_cycle_average3", g, ptr(self.avg_psi), ptr(self.psi), ptr(self.avg_psi_last), ptr(self.avg_phi),
+              ptr(self.ball_phi), ptr(self.avg_phi_last), None, None, None, sp(1), sp(8), s)
+        _call("axb_advect_refmap_eno3", g, ptr(e1b), ptr(e2b), ptr(self.eta1), ptr(self.eta2), ptr(self.u_z_upen),
+              ptr(self.u_r_upen), 0.0, sp(1), s)
+        _call("axb_pin_level_set", g, ptr(self.ball_phi), None, ptr(e1b), ptr(e2b), self.Z_cm, self.R_cm, self.r_ball,
+              -3 * dx, s)
+        _call("axb_advect_vorticity_eno3", g, ptr(w2), ptr(w), ptr(self.u_z_upen), ptr(self.u_r_upen), 0.0, sp(1), s)
+        _call("axb_smooth_heaviside_mask", g, ptr(self.ball_char_func), ptr(self.inside_solid), ptr(self.ball_phi),
+              self.moll_zone, 0.5, 0, s)
+        _call("axb_ls_extrapolate_eta_device", g, ptr(self.ball_phi), ptr(self.inside_solid), ptr(e1b), ptr(e2b),
+              ptr(self.eta1), ptr(self.eta2), self.extrap_zone, ptr(self.z1d), ptr(self.gy), ptr(self._ls_work),
+              self._ls_bytes, self._ls_sweeps, ptr(self._ls_status), s)
+        _call("axb_solid_sigma", g, ptr(self.s11), ptr(self.s12), ptr(self.s22), self.G, ptr(self.eta1), ptr(self.eta2),
+              ptr(self.e1z), ptr(self.e1r), ptr(self.e2z), ptr(self.e2r), ptr(self.ball_char_func), s)
+        _call("axb_solid_tau", g, ptr(self.tau_z), ptr(self.tau_r), ptr(self.s11), ptr(self.s12), ptr(self.s22),
+              ptr(self.r1d), s)
+        _call("axb_solid_vorticity_update", g, ptr(w2), ptr(self.tau_z), ptr(self.tau_r), 0.0, sp(1), s)
+        _call("axb_smooth_heaviside_sphere_dev", g, ptr(self.tether_char_func), None, ptr(self.z1d), ptr(self.r1d), sp(6),
+              self.R_cm, self.fixed_rad, self.moll_zone, s)
+        _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w2), ptr(self.u_z_upen),
+              ptr(self.u_r_upen), ptr(self.tether_char_func), self.brink_lam, 0.0, sp(1), 0.0, 0.0, sp(4), ptr(self.r1d),
+              None, s)
+        _call("axb_diffusion_rk2_stage1", g, ptr(self._tmp), ptr(w2), ptr(self.r1d), self.nu, 0.0, sp(1), s)
+        _call("axb_diffusion_rk2_stage2", g, ptr(w), ptr(w2), ptr(self._tmp), ptr(self.r1d), self.nu, 0.0, sp(1), s)
+        scalars(2)
+
+    def sync_scalars(self):
+        """device mode: one synchronising D2H of the loop scalars into the attributes the host mode keeps; raises if
+        the LS extrapolation ran out of workspace or sweeps"""
+        if not self.device_scalars:
+            return self
+        st = self.state.cpu().numpy()
+        self.t, self.dt, self.freqTimer, self.cycles, self.it = st[0], st[1], st[3], int(st[7]), int(st[9])
+        status, self.ls_sweeps = (int(v) for v in self._ls_status.cpu().numpy())
+        if status:
+            raise _lib.AxbError(f"LS extrapolation (device loop): status {status} "
+                                "(1: pending list overflow, 2: sweep budget exhausted)")
+        return self
 
     def _one(self):
         F, s, g = self.F, stream_ptr(), self.F.g

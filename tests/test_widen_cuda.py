@@ -714,3 +714,46 @@ def test_batched_particle_ensemble(K, fft, launch, nz):
         _assert_particle_state(m, h, f)
         for fld in ("vorticity", "psi", "avg_vort", "part_char_func"):
             assert_close(getattr(m, fld).cpu().numpy(), getattr(h, fld).cpu().numpy(), 1e-6, f"{fld} f={f}")
+
+
+@pytest.mark.parametrize("graph,nz", [(False, 64), (True, 64), (True, 320)])
+def test_soft_sphere_stepper_device_scalars_match_host_loop(K, graph, nz):
+    """SURVEY 8f-1 (config C3): dt with its cycle / tEnd clamps, the tether's velocity and position and the cycle timer
+    on a device block (axb_soft_sphere_scalars, soft_sphere_streaming.py:139-176, 201-203, 262-264), LS extrapolation
+    with device-terminated sweeps (axb_ls_extrapolate_eta_device), no buffer swap: the step is a fixed launch sequence
+    without a host read, replayed as a CUDA graph.  Same kernels on the same inputs as the host-driven stepper; the
+    only different arithmetic is the device's sin / cos of omega t."""
+    import torch
+    from pyaxisymflow_b200.timestep import SoftSphereStepper
+
+    steps = 7
+    h = SoftSphereStepper(nz, Z_cm=0.47)
+    d = SoftSphereStepper(nz, Z_cm=0.47, device_scalars=True, use_graph=graph)
+    h.step(steps)
+    d.step(3)
+    d.step(steps - 3)
+    d.sync_scalars()
+    assert d.it == steps and abs(d.t - h.t) <= 1e-13 * h.t and abs(d.dt - h.dt) <= 1e-13 * h.dt
+    assert d.ls_sweeps == h.ls_sweeps >= 4
+    for f in ("eta1", "eta2", "ball_phi", "vorticity", "psi", "avg_psi", "avg_phi", "ball_char_func", "tether_char_func",
+              "u_z", "u_r"):
+        assert_close(getattr(d, f).cpu().numpy(), getattr(h, f).cpu().numpy(), 1e-11, f)
+    # cycle wrap on the device: the step that completes the cycle is clamped to its end, the next one restarts the
+    # averages and keeps the completed ones
+    d.state[3] = d.freqTimer_limit - 0.25 * d.dt
+    d.step(1)
+    d.sync_scalars()
+    assert d.cycles == 1 and d.freqTimer == 0.0 and abs(d.dt - 0.25 * h.dt) <= 1e-9 * h.dt
+    full = d.avg_psi.clone()
+    psi_before = d.psi.clone()
+    d.step(1)
+    d.sync_scalars()
+    assert torch.equal(d.avg_psi_last, full)
+    # the restarted average holds this step's psi (solved at the start of the step) times dt
+    assert float((d.avg_psi - d.psi * d.dt).abs().max()) <= 1e-15 * float((d.psi * d.dt).abs().max())
+    assert not torch.equal(psi_before, d.psi)
+    # a sweep budget that is too small is reported, not silently accepted
+    few = SoftSphereStepper(nz, Z_cm=0.47, device_scalars=True, ls_sweeps=2)
+    few.step(1)
+    with pytest.raises(Exception, match="sweep budget"):
+        few.sync_scalars()

@@ -19,6 +19,8 @@ elif which == "c4":
     s.t = 0.0
 elif which == "c3":
     s = SoftSphereStepper(8192, grid_size_r=2048, Z_cm=0.47, reinit_levelset=True)
+elif which == "c3d":                                  # device-resident soft-sphere step (eager launches)
+    s = SoftSphereStepper(8192, grid_size_r=2048, device_scalars=True)
 elif which == "c5b":                                  # the batched, device-resident 8-member ensemble (eager launches)
     from pyaxisymflow_b200.timestep import ParticleEnsemble
     freqs = [4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0, 32.0]
