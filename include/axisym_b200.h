@@ -314,6 +314,15 @@ int axb_solid_tau(const axb_grid_t* g, double* tau_z, double* tau_r, const doubl
                   const double* t22, const double* r1d, axb_stream_t s);
 int axb_solid_vorticity_update(const axb_grid_t* g, double* w, const double* tau_z, const double* tau_r,
                                double dt, const double* dt_dev, axb_stream_t s);
+/* a18 + a19 in one pass for a driver that does not look at the intermediate arrays (soft_sphere_streaming.py:208-234):
+ * w[1:-1, 1:-1] += dt curl(div(chi sigma(eta1, eta2))) with the bits of axb_solid_sigma -> axb_solid_tau ->
+ * axb_solid_vorticity_update run on ZERO-INITIALISED gradient / stress / tau work arrays (the cells those calls leave
+ * untouched then hold zeros for ever).  eta1, eta2, chi read once, w updated: ~50 instead of 152 B per cell.
+ * exact_divisions = 1: those bits exactly (true FP64 divisions, issue bound); 0: divisions by 2 dx and r become
+ * multiplications by reciprocals (<= 1e-13 relative to the exact form, several times faster). */
+int axb_solid_stress_vorticity_update(const axb_grid_t* g, double* w, const double* eta1, const double* eta2,
+                                      const double* chi, const double* r1d, double G, double dt, const double* dt_dev,
+                                      int exact_divisions, axb_stream_t s);
 
 /* ---- a20: core/src/extrapolate_using_least_squares.hpp:450-467 (order 1, 3x3 patch).
  *      cur/tgt int16 (n0, n1); eta_x / eta_y (n0, n1); gx[n1], gy[n0].  work holds

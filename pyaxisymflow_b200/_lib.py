@@ -97,6 +97,7 @@ _SIGNATURES = {
     "axb_solid_sigma": [_G, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_tau": [_G, _P, _P, _P, _P, _P, _P, _S],
     "axb_solid_vorticity_update": [_G, _P, _P, _P, _D, _P, _S],
+    "axb_solid_stress_vorticity_update": [_G, _P, _P, _P, _P, _P, _D, _D, _P, _I, _S],
     "axb_ls_workspace_bytes": [_I, _I],
     "axb_ls_extrapolate_order1": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_ls_extrapolate_order2": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],

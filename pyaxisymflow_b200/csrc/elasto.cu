@@ -313,6 +313,124 @@ __global__ void __launch_bounds__(TBX* TBY)
   }
 }
 
+
+// -------------------------------------------------------------------------------------
+// G-SOL fused (stepper form): eta -> sigma -> tau -> w += dt curl(tau) in ONE pass.
+// The three reference calls move 152 B per cell through seven intermediate arrays the driver never looks at
+// (soft_sphere_streaming.py:208-234); here a block stages the (16 + 6) x (64 + 6) neighbourhood of the two reference
+// maps in shared memory, evaluates sigma on the (16 + 4) x (64 + 4) ring, tau on (16 + 2) x (64 + 2) and updates its
+// 16 x 64 cells of w: eta1, eta2, chi read once (x 1.3-1.5 for the halos), w read and written -- about 50 B per cell.
+// Every stage evaluates the expressions of sigma_pair / tau_pair / k_solid_curl (true divisions, -fmad=false), and
+// cells the reference leaves untouched (first / last column, last row: "stale" above) read as zero, which is what
+// they hold in a driver whose work arrays start zeroed -- so w gets the bits of the three separate calls.
+// -------------------------------------------------------------------------------------
+constexpr int FT_R = 16, FT_C = 64;
+constexpr int FE_R = FT_R + 6, FE_C = FT_C + 6, FS_R = FT_R + 4, FS_C = FT_C + 4, FQ_R = FT_R + 2, FQ_C = FT_C + 2;
+
+// EXACT: true divisions (the bits of the three calls; FP64-issue bound: ~9 divisions per cell, 0.76 ms at 2048 x 8192);
+// otherwise divisions by 2 dx and r are multiplications by reciprocals computed once (<= 2 ulp per operation, like the
+// row-marching stencils; the parity bar is 1e-10).
+template <bool EXACT>
+__device__ __forceinline__ double qdiv(double a, double b, double inv_b) { return EXACT ? a / b : a * inv_b; }
+
+template <bool CHI, bool EXACT>
+__global__ void __launch_bounds__(256)
+    k_solid_fused(GridD g, double* __restrict__ w, const double* __restrict__ eta1, const double* __restrict__ eta2,
+                  const double* __restrict__ chi, const double* __restrict__ r1d, double G, double dt,
+                  const double* __restrict__ dt_dev) {
+  __shared__ double e1[FE_R * FE_C], e2[FE_R * FE_C], s11[FS_R * FS_C], s12[FS_R * FS_C];
+  __shared__ double inv_r[FQ_R];
+  double* tz = e1;     // tau re-uses the staging arrays once sigma is done
+  double* tr = e2;
+  const int J0 = blockIdx.y * FT_R, K0 = blockIdx.x * FT_C;
+  const int nr = g.nr, nz = g.nz;
+  const double h = 2 * g.dx, ih = 1.0 / h;
+  if (dt_dev) dt = *dt_dev;
+  if (!EXACT && threadIdx.x < FQ_R) {
+    const int j = J0 - 1 + (int)threadIdx.x;
+    inv_r[threadIdx.x] = (j >= 0 && j < nr) ? 1.0 / r1d[j] : 0.0;
+  }
+  // stage 1: reference maps on rows J0-3 .. J0+FT_R+2, columns K0-3 .. K0+FT_C+2 (zero outside the domain)
+  for (int i = threadIdx.x; i < FE_R * FE_C; i += 256) {
+    const int rr = i / FE_C, cc = i - rr * FE_C;
+    const int j = J0 - 3 + rr, k = K0 - 3 + cc;
+    double a = 0.0, b = 0.0;
+    if (j >= 0 && j < nr && k >= 0 && k < nz) {
+      a = eta1[(long long)j * g.ld + k];
+      b = eta2[(long long)j * g.ld + k];
+    }
+    e1[i] = a;
+    e2[i] = b;
+  }
+  __syncthreads();
+  // stage 2: sigma on rows J0-2 .. , columns K0-2 ..
+  for (int i = threadIdx.x; i < FS_R * FS_C; i += 256) {
+    const int rr = i / FS_C, cc = i - rr * FS_C;
+    const int j = J0 - 2 + rr, k = K0 - 2 + cc;
+    double a11 = 0.0, a12 = 0.0;
+    if (j >= 0 && j < nr && k >= 0 && k < nz) {
+      const int c = (rr + 1) * FE_C + (cc + 1);                 // this cell in the eta staging
+      const bool zin = (k >= 1 && k <= nz - 2);
+      double z1 = 0.0, r1 = 0.0, z2 = 0.0, r2 = 0.0;
+      if (zin) {
+        z1 = qdiv<EXACT>(e1[c + 1] - e1[c - 1], h, ih);
+        z2 = qdiv<EXACT>(e2[c + 1] - e2[c - 1], h, ih);
+      }
+      if (j == 0) {
+        // rows 1 and 2 (one-sided); row 0 of the domain is staging row 3 of the first row block
+        const int c1 = c + FE_C, c2 = c + 2 * FE_C;
+        r1 = qdiv<EXACT>(-e1[c2] + 4 * e1[c1] - 3 * e1[c], h, ih);
+        r2 = qdiv<EXACT>(-e2[c2] + 4 * e2[c1] - 3 * e2[c], h, ih);
+      } else if (j < nr - 1 && zin) {
+        r1 = qdiv<EXACT>(e1[c + FE_C] - e1[c - FE_C], h, ih);
+        r2 = qdiv<EXACT>(e2[c + FE_C] - e2[c - FE_C], h, ih);
+      }
+      a12 = -G * (z1 * r1 + z2 * r2);
+      a11 = (0.5 * G) * (r1 * r1 + r2 * r2 - z1 * z1 - z2 * z2);
+      if (CHI) {
+        const double x = chi[(long long)j * g.ld + k];
+        a11 = x * a11;
+        a12 = x * a12;
+      }
+    }
+    s11[i] = a11;
+    s12[i] = a12;
+  }
+  __syncthreads();
+  // stage 3: tau on rows J0-1 .. , columns K0-1 ..  (rows 0 .. nr-2, columns 1 .. nz-2; zero elsewhere); t22 = -t11
+  for (int i = threadIdx.x; i < FQ_R * FQ_C; i += 256) {
+    const int rr = i / FQ_C, cc = i - rr * FQ_C;
+    const int j = J0 - 1 + rr, k = K0 - 1 + cc;
+    double vz = 0.0, vr = 0.0;
+    if (j >= 0 && j < nr - 1 && k >= 1 && k <= nz - 2) {
+      const int c = (rr + 1) * FS_C + (cc + 1);                 // this cell in the sigma arrays
+      const double r = EXACT ? r1d[j] : 0.0, ir = EXACT ? 0.0 : inv_r[rr];
+      const double b_c = s12[c], c_c = -s11[c];
+      if (j > 0) {
+        const double b_u = s12[c + FS_C], b_d = s12[c - FS_C], c_u = -s11[c + FS_C], c_d = -s11[c - FS_C];
+        vz = qdiv<EXACT>(s11[c + 1] - s11[c - 1] + b_u - b_d, h, ih) + qdiv<EXACT>(b_c, r, ir);
+        vr = qdiv<EXACT>(s12[c + 1] - s12[c - 1] + c_u - c_d, h, ih) + qdiv<EXACT>(c_c, r, ir);
+      } else {
+        const double b_u = s12[c + FS_C], b_d = s12[c + 2 * FS_C], c_u = -s11[c + FS_C], c_d = -s11[c + 2 * FS_C];
+        vz = qdiv<EXACT>(s11[c + 1] - s11[c - 1] - b_d + 4 * b_u - 3 * b_c, h, ih) + qdiv<EXACT>(b_c, r, ir);
+        vr = qdiv<EXACT>(s12[c + 1] - s12[c - 1] - c_d + 4 * c_u - 3 * c_c, h, ih) + qdiv<EXACT>(c_c, r, ir);
+      }
+    }
+    tz[i] = vz;
+    tr[i] = vr;
+  }
+  __syncthreads();
+  // stage 4: the block's own cells
+  for (int i = threadIdx.x; i < FT_R * FT_C; i += 256) {
+    const int rr = i / FT_C, cc = i - rr * FT_C;
+    const int j = J0 + rr, k = K0 + cc;
+    if (j < 1 || j >= nr - 1 || k < 1 || k > nz - 2) continue;
+    const int c = (rr + 1) * FQ_C + (cc + 1);
+    double* wp = w + (long long)j * g.ld + k;
+    *wp = *wp + qdiv<EXACT>(dt * (tr[c + 1] - tr[c - 1] - tz[c + FQ_C] + tz[c - FQ_C]), h, ih);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -361,6 +479,23 @@ int axb_solid_tau(const axb_grid_t* g, double* tau_z, double* tau_r, const doubl
   } else {
     k_solid_tau<<<grid2d(d), dim3(TBX, TBY), 0, s>>>(d, tau_z, tau_r, t11, t12, t22, r1d, vec);
   }
+  AXB_LAUNCHED();
+  AXB_RETURN_LAST();
+}
+
+int axb_solid_stress_vorticity_update(const axb_grid_t* g, double* w, const double* eta1, const double* eta2,
+                                      const double* chi, const double* r1d, double G, double dt, const double* dt_dev,
+                                      int exact_divisions, axb_stream_t s) {
+  if (!w || !eta1 || !eta2 || !r1d || w == eta1 || w == eta2) return AXB_EINVAL;
+  int rc = axb_check_grid(g);
+  if (rc) return rc;
+  if (g->ku0 != 0 || g->ku1 != g->nz || g->nz_global != g->nz || g->nr < 3 || g->nz < 3) return AXB_ENOSUP;
+  const GridD d = to_dev(g);
+  const dim3 grd((d.nz + FT_C - 1) / FT_C, (d.nr + FT_R - 1) / FT_R);
+#define FUSED(C, E) k_solid_fused<C, E><<<grd, 256, 0, s>>>(d, w, eta1, eta2, chi, r1d, G, dt, dt_dev)
+  if (chi) { if (exact_divisions) FUSED(true, true); else FUSED(true, false); }
+  else { if (exact_divisions) FUSED(false, true); else FUSED(false, false); }
+#undef FUSED
   AXB_LAUNCHED();
   AXB_RETURN_LAST();
 }

@@ -271,22 +271,42 @@ int ls_run(int order, int n0, int n1, short* cur, const short* tgt, double* eta_
 // A sweep that finds no candidate leaves the pending list as it is, and so do all later ones: the result is the one
 // of the host-driven loop, which stops there (extrapolate_using_least_squares.hpp:372-375).
 constexpr int LS_MAX_SWEEPS = 28;            // 4 + 2 (sweeps + 1) ints fit the 256-byte counter block
-int ls_run_device(int order, int n0, int n1, short* cur, const short* tgt, double* eta_x, double* eta_y, const double* gx,
-                  const double* gy, void* work, long long work_bytes, int sweeps, int* status_dev, cudaStream_t s) {
-  if (sweeps < 1 || sweeps > LS_MAX_SWEEPS) return AXB_EINVAL;
-  const long long cap = (work_bytes - 256) / 14;
-  if (cap < 1) return AXB_EWORK;
-  char* p = (char*)work;
-  int* ctr = (int*)p; p += 256;
+struct LsDevWork {
+  int* ctr;
   int* pend[2];
-  pend[0] = (int*)p; p += cap * 4;
-  pend[1] = (int*)p; p += cap * 4;
-  int* cand = (int*)p; p += cap * 4;
-  short* codes = (short*)p;
+  int* cand;
+  short* codes;
+  long long cap;
+};
+LsDevWork carve_device(void* work, long long work_bytes) {
+  LsDevWork w;
+  w.cap = (work_bytes - 256) / 14;
+  char* p = (char*)work;
+  w.ctr = (int*)p; p += 256;
+  w.pend[0] = (int*)p; p += w.cap * 4;
+  w.pend[1] = (int*)p; p += w.cap * 4;
+  w.cand = (int*)p; p += w.cap * 4;
+  w.codes = (short*)p;
+  return w;
+}
+// `collected`: the caller has zeroed the counters and filled the first pending list (k_ls_fill<true>)
+int ls_run_device(int order, int n0, int n1, short* cur, const short* tgt, double* eta_x, double* eta_y, const double* gx,
+                  const double* gy, void* work, long long work_bytes, int sweeps, int* status_dev, bool collected,
+                  cudaStream_t s) {
+  if (sweeps < 1 || sweeps > LS_MAX_SWEEPS) return AXB_EINVAL;
+  const LsDevWork w = carve_device(work, work_bytes);
+  const long long cap = w.cap;
+  if (cap < 1) return AXB_EWORK;
+  int* ctr = w.ctr;
+  int* const* pend = w.pend;
+  int* cand = w.cand;
+  short* codes = w.codes;
   const int n = n0 * n1;
-  cudaMemsetAsync(ctr, 0, 256, s);
-  k_ls_collect<<<(n + 255) / 256, 256, 0, s>>>(n, cur, tgt, pend[0], ctr + 4, cap);
-  AXB_LAUNCHED();
+  if (!collected) {
+    cudaMemsetAsync(ctr, 0, 256, s);
+    k_ls_collect<<<(n + 255) / 256, 256, 0, s>>>(n, cur, tgt, pend[0], ctr + 4, cap);
+    AXB_LAUNCHED();
+  }
   const int blocks = (int)min((cap + 127) / 128, 148LL * 4);
   for (int i = 0; i < sweeps; ++i) {
     int *n_in = ctr + 4 + 2 * i, *n_cand = n_in + 1, *n_out = n_in + 2;
@@ -305,10 +325,13 @@ int ls_run_device(int order, int n0, int n1, short* cur, const short* tgt, doubl
 
 // fill of the doubled work arrays, elasto_kernels/extrapolate_eta_using_least_squares_unb.py:20-25
 // + the flag construction of elasto_kernels/extrapolate_using_least_squares.py:33-36
+// COLLECT: the pending list (cells with cur != tgt, k_ls_collect) is built here as well -- its order does not matter
+// to the sweeps -- and the target flags, which only the collection reads, are not stored.
+template <bool COLLECT>
 __global__ void k_ls_fill(int nr, int nz, long long ld, const double* __restrict__ phi,
                           const unsigned char* __restrict__ inside, const double* __restrict__ eta1,
                           const double* __restrict__ eta2, double zone, short* cur, short* tgt, double* e1,
-                          double* e2) {
+                          double* e2, int* pend, int* n_pend, long long cap) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
   if (k >= nz) return;
@@ -319,9 +342,16 @@ __global__ void k_ls_fill(int nr, int nz, long long ld, const double* __restrict
   const short c = (short)(p < 0), t = (short)(p < zone);
   const long long up = (long long)(nr + j) * nz + k, dn = (long long)(nr - 1 - j) * nz + k;
   cur[up] = c; cur[dn] = c;
-  tgt[up] = t; tgt[dn] = t;
   e1[up] = a; e1[dn] = a;
   e2[up] = b; e2[dn] = -b;
+  if (COLLECT) {
+    if (c ^ t) {
+      const int slot = atomicAdd(n_pend, 2);
+      if (slot + 1 < cap) { pend[slot] = (int)up; pend[slot + 1] = (int)dn; }
+    }
+  } else {
+    tgt[up] = t; tgt[dn] = t;
+  }
 }
 __global__ void k_ls_unfill(int nr, int nz, long long ld, double* eta1, double* eta2, const double* __restrict__ e1,
                             const double* __restrict__ e2) {
@@ -591,12 +621,21 @@ static int ls_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* in
   rest = (char*)(((uintptr_t)rest + 255) & ~(uintptr_t)255);
   const long long rest_bytes = work_bytes - (rest - p);
   dim3 grd((nz + 127) / 128, nr);
-  k_ls_fill<<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt, e1, e2);
-  AXB_LAUNCHED();
-  if (device_loop)
-    rc = ls_run_device(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, status_dev, (cudaStream_t)s);
-  else
+  if (device_loop) {
+    const LsDevWork w = carve_device(rest, rest_bytes);
+    if (w.cap < 2) return AXB_EWORK;
+    cudaMemsetAsync(w.ctr, 0, 256, s);
+    k_ls_fill<true><<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt, e1,
+                                        e2, w.pend[0], w.ctr + 4, w.cap);
+    AXB_LAUNCHED();
+    rc = ls_run_device(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, status_dev, true,
+                       (cudaStream_t)s);
+  } else {
+    k_ls_fill<false><<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt, e1,
+                                         e2, nullptr, nullptr, 0);
+    AXB_LAUNCHED();
     rc = ls_run(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
+  }
   if (rc) return rc;
   k_ls_unfill<<<grd, 128, 0, s>>>(nr, nz, g->ld, eta1, eta2, e1, e2);
   AXB_LAUNCHED();

@@ -321,7 +321,7 @@ class SoftSphereStepper:
 
     def __init__(self, grid_size_z=256, domain_AR=0.5, grid_size_r=None, r_ball=0.15, freq=16.0, nond_AC=0.125,
                  e=0.1, Cauchy=0.1, zeta=0.25, brink_lam=1e8, CFL=0.1, rho_f=1.0, Z_cm=0.5, R_cm=0.0, basis="auto",
-                 reinit_levelset=False, device_scalars=False, use_graph=False, ls_sweeps=12):
+                 reinit_levelset=False, device_scalars=False, use_graph=False, ls_sweeps=12, fused_solid=True):
         if not torch.cuda.is_available():
             raise _lib.AxbError("SoftSphereStepper needs a CUDA device (no CPU fallback)")
         if device_scalars and reinit_levelset:
@@ -376,6 +376,7 @@ class SoftSphereStepper:
         # device-resident loop scalars (include/axisym_b200.h, axb_soft_sphere_scalars): no host round trip per step,
         # the LS extrapolation with device-terminated sweeps, the whole step one replayed CUDA graph
         self.device_scalars = bool(device_scalars)
+        self.fused_solid = bool(fused_solid)          # device mode: one pass for the elastic stress (else 3 calls)
         self._use_graph, self._graph = bool(use_graph) and self.device_scalars, None
         if self.device_scalars:
             self.state = torch.zeros(16, dtype=torch.float64, device="cuda")
@@ -440,11 +441,16 @@ class SoftSphereStepper:
         _call("axb_ls_extrapolate_eta_device", g, ptr(self.ball_phi), ptr(self.inside_solid), ptr(e1b), ptr(e2b),
               ptr(self.eta1), ptr(self.eta2), self.extrap_zone, ptr(self.z1d), ptr(self.gy), ptr(self._ls_work),
               self._ls_bytes, self._ls_sweeps, ptr(self._ls_status), s)
-        _call("axb_solid_sigma", g, ptr(self.s11), ptr(self.s12), ptr(self.s22), self.G, ptr(self.eta1), ptr(self.eta2),
-              ptr(self.e1z), ptr(self.e1r), ptr(self.e2z), ptr(self.e2r), ptr(self.ball_char_func), s)
-        _call("axb_solid_tau", g, ptr(self.tau_z), ptr(self.tau_r), ptr(self.s11), ptr(self.s12), ptr(self.s22),
-              ptr(self.r1d), s)
-        _call("axb_solid_vorticity_update", g, ptr(w2), ptr(self.tau_z), ptr(self.tau_r), 0.0, sp(1), s)
+        if self.fused_solid:
+            # sigma -> tau -> curl in one shared-memory pass (the driver never looks at the seven intermediates)
+            _call("axb_solid_stress_vorticity_update", g, ptr(w2), ptr(self.eta1), ptr(self.eta2),
+                  ptr(self.ball_char_func), ptr(self.r1d), self.G, 0.0, sp(1), 0, s)
+        else:
+            _call("axb_solid_sigma", g, ptr(self.s11), ptr(self.s12), ptr(self.s22), self.G, ptr(self.eta1),
+                  ptr(self.eta2), ptr(self.e1z), ptr(self.e1r), ptr(self.e2z), ptr(self.e2r), ptr(self.ball_char_func), s)
+            _call("axb_solid_tau", g, ptr(self.tau_z), ptr(self.tau_r), ptr(self.s11), ptr(self.s12), ptr(self.s22),
+                  ptr(self.r1d), s)
+            _call("axb_solid_vorticity_update", g, ptr(w2), ptr(self.tau_z), ptr(self.tau_r), 0.0, sp(1), s)
         _call("axb_smooth_heaviside_sphere_dev", g, ptr(self.tether_char_func), None, ptr(self.z1d), ptr(self.r1d), sp(6),
               self.R_cm, self.fixed_rad, self.moll_zone, s)
         _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w2), ptr(self.u_z_upen),

@@ -757,3 +757,47 @@ def test_soft_sphere_stepper_device_scalars_match_host_loop(K, graph, nz):
     few.step(1)
     with pytest.raises(Exception, match="sweep budget"):
         few.sync_scalars()
+
+
+@pytest.mark.parametrize("nr,nz", [(40, 70), (16, 64), (3, 3), (35, 130), (50, 200), (17, 65), (130, 1030)])
+def test_fused_solid_stress_equals_the_three_calls(K, nr, nz):
+    """axb_solid_stress_vorticity_update (the soft-sphere stepper's form of a18 + a19): one shared-memory pass
+    eta -> sigma -> tau -> w, bit-identical to solid_sigma -> update_vorticity_from_solid_stress on zero-initialised
+    work arrays (what the reference driver has), and against the oracle's sequence."""
+    import ctypes
+
+    import torch
+    from pyaxisymflow_b200 import _lib
+    from pyaxisymflow_b200.device import make_grid, ptr, stream_ptr
+
+    rng = np.random.default_rng(nr * 11 + nz)
+    dx, _, r, Z, R = _grid(nr, nz)
+    eta1, eta2 = Z + 0.05 * _rand(rng, nr, nz), R + 0.05 * _rand(rng, nr, nz)
+    chi = np.clip(_rand(rng, nr, nz) + 0.5, 0, 1)
+    w0 = _rand(rng, nr, nz, 3.0)
+    G, dt = 3.7, 2e-3
+    for c in (chi, None):
+        z = {k: np.zeros((nr, nz)) for k in ("s11", "s12", "s22", "e1z", "e1r", "e2z", "e2r", "tz", "tr")}
+        K.solid_sigma(z["s11"], z["s12"], z["s22"], G, dx, eta1, eta2, z["e1z"], z["e1r"], z["e2z"], z["e2r"], _chi=c)
+        want = w0.copy()
+        K.update_vorticity_from_solid_stress(want, z["tz"], z["tr"], z["s11"], z["s12"], z["s22"], R, dt, dx)
+        g = make_grid(nr, nz, nz, dx)
+        dev = [torch.from_numpy(a).cuda() for a in (w0.copy(), eta1, eta2, chi, r)]
+        _lib.call("axb_solid_stress_vorticity_update", ctypes.byref(g), ptr(dev[0]), ptr(dev[1]), ptr(dev[2]),
+                  ptr(dev[3]) if c is not None else None, ptr(dev[4]), G, dt, None, 1, stream_ptr())
+        got = dev[0].cpu().numpy()
+        assert np.array_equal(got, want), ("blend" if c is not None else "plain", np.abs(got - want).max())
+        # reciprocal multiplications instead of the divisions by 2 dx and r (the stepper's default)
+        dev[0].copy_(torch.from_numpy(w0))
+        _lib.call("axb_solid_stress_vorticity_update", ctypes.byref(g), ptr(dev[0]), ptr(dev[1]), ptr(dev[2]),
+                  ptr(dev[3]) if c is not None else None, ptr(dev[4]), G, dt, None, 0, stream_ptr())
+        assert_close(dev[0].cpu().numpy(), want, 1e-12, "fused solid stress, reciprocal form")
+        # the oracle's sequence (numba-vs-NumPy last bits)
+        o = {k: np.zeros((nr, nz)) for k in z}
+        ox.solid_sigma(o["s11"], o["s12"], o["s22"], G, dx, eta1, eta2, o["e1z"], o["e1r"], o["e2z"], o["e2r"])
+        if c is not None:
+            for k in ("s11", "s12", "s22"):
+                o[k] = c * o[k]
+        wo = w0.copy()
+        ox.update_vorticity_from_solid_stress(wo, o["tz"], o["tr"], o["s11"], o["s12"], o["s22"], R, dt, dx)
+        assert_close(got, wo, 1e-12, "fused solid stress vs oracle")
