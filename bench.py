@@ -437,6 +437,12 @@ class _ConfigRunner:
         self.step(1)
         return None
 
+    @property
+    def launches_replayed(self):
+        """kernels launched through CUDA-graph replays (the library's launch counter only sees eager launches)"""
+        objs = [self.ensemble] if getattr(self.ensemble, "batched", False) else self.members
+        return sum(getattr(o, "launches_replayed", 0) for o in objs)
+
     def host_state(self):
         """device fields a host-resident caller has to supply for a step / gets back from it (e2e leg)"""
         if self.name == "c3":
@@ -462,6 +468,19 @@ class _ConfigRunner:
 
 def solve_probe(stepper, torch, reps=3):
     """device time of one solve (of one member), measured outside the timed steps"""
+    ens = getattr(stepper, "ensemble", None)
+    if getattr(ens, "batched", False) and ens._solver is not None:
+        # batched ensemble: ONE solve serves all members; report the per-member share of its time
+        keep = ens._psi_wide.clone()
+        ens._solver.solve(ens._psi_wide, ens._w_wide)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ens._solver.solve(ens._psi_wide, ens._w_wide)
+        b.record()
+        torch.cuda.synchronize()
+        ens._psi_wide.copy_(keep)
+        return a.elapsed_time(b) / reps / len(ens.members)
     m = stepper.members[0] if hasattr(stepper, "members") else stepper
     per = getattr(m, "periodic", False)
     sol = m.psi[:, 2:-2] if per else m.psi
@@ -476,6 +495,26 @@ def solve_probe(stepper, torch, reps=3):
     torch.cuda.synchronize()
     sol.copy_(keep)
     return a.elapsed_time(b) / reps
+
+
+# algorithmic HBM bytes per grid point of one WHOLE step (DESIGN.md sections 3 and 6: every field a pass must read or
+# write, counted once per pass; O(band) work and halos not counted):
+#   c4 / c1 / c2 rigid flow: solve 80 + velocity 24 + penalisation 56 + ENO3 32 + one-pass RK2 16 = 208
+#   c3 soft sphere (device-resident step): solve 80 + velocity 24 + 2 running averages 48 + reference-map ENO3 48 +
+#      level-set pin 32 + vorticity ENO3 32 + Heaviside/mask 17 + masked map write-back of the LS extrapolation 33 +
+#      fused elastic stress 40 + tether Heaviside 8 + penalisation 56 + two-stage RK2 40 = 458
+#   c5 particle case: solve 80 + velocity 24 + max reduction 8 + bubble flow 40 + 3 running averages 72 + particle
+#      Heaviside 8 + penalisation 56 + lattice remesh 32 + two-stage RK2 40 = 360
+STEP_BYTES_PER_POINT = {"c4": 208, "c1": 208, "c2": 208, "c3": 458, "c5": 360}
+
+
+def step_roofline(name, points, ms_per_step, mp):
+    """whole-step HBM roofline: algorithmic bytes of all passes / measured copy bandwidth against the step time"""
+    peak = mp.get("hbm_gbs") or 6650.0
+    bpp = STEP_BYTES_PER_POINT[name]
+    floor_ms = bpp * points / (peak * 1e9) * 1e3
+    return {"bound": "hbm", "algorithmic_bytes_per_point": bpp, "points": points, "peak": peak, "unit": "GB/s",
+            "achieved": bpp * points / (ms_per_step * 1e-3) / 1e9, "floor_ms": floor_ms, "frac": floor_ms / ms_per_step}
 
 
 def roofline(stepper, mp, fp64_peak, tflops, hbm_bytes, traffic, solve_ms, share):
@@ -759,6 +798,8 @@ def run_gpu_arm(args, name, nr, nz):
              "config": cfg, "solver_basis": st.solver_basis(),
              "roofline": roofline(st, mp, peak_holder[0], achieved, m["hbm_bytes"], traffic, m["solve_ms"], share),
              "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": m["gpu_launches"], "clocks": m["clocks"]}
+        if world == 1:
+            d["step_roofline"] = step_roofline(cname, m["cases"] * cnr * cnz, m["ms_per_step"], mp)
         if m["ms_per_step_l2_warm"] is not None:
             d["ms_per_step_l2_warm"] = m["ms_per_step_l2_warm"]
         return d

@@ -266,6 +266,21 @@ class HostStepPipeline:
         torch.cuda.current_stream().synchronize()
 
 
+
+def _capture_step(obj, enqueue):
+    """warm-up call + capture of one step as a CUDA graph; records how many kernels a replay launches"""
+    enqueue()                                        # warm-up outside capture
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    n0 = _lib.launch_count()
+    with torch.cuda.graph(graph, stream=side):
+        enqueue()
+    obj.graph_launches = _lib.launch_count() - n0
+    return graph
+
+
 class _FieldSet:
     """small helper: float64 CUDA fields of one (nr, nz) grid plus the ctypes grid descriptor.  With a ``pool``
     (:class:`_WidePool`) the fields are this member's column blocks of (nr, batch nz) tensors shared by an
@@ -378,6 +393,7 @@ class SoftSphereStepper:
         self.device_scalars = bool(device_scalars)
         self.fused_solid = bool(fused_solid)          # device mode: one pass for the elastic stress (else 3 calls)
         self._use_graph, self._graph = bool(use_graph) and self.device_scalars, None
+        self.graph_launches, self.launches_replayed = 0, 0
         if self.device_scalars:
             self.state = torch.zeros(16, dtype=torch.float64, device="cuda")
             self._ls_status = torch.zeros(2, dtype=torch.int32, device="cuda")
@@ -395,16 +411,11 @@ class SoftSphereStepper:
                 self._one_dev()
             return
         if self._graph is None:
-            self._one_dev()                          # warm-up outside capture
-            torch.cuda.synchronize()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph, stream=side):
-                self._one_dev()
+            self._graph = _capture_step(self, self._one_dev)
             n -= 1
         for _ in range(n):
             self._graph.replay()
+            self.launches_replayed += self.graph_launches
 
     def _one_dev(self):
         """the step of `_one` with every host decision on the device (state block, axb_soft_sphere_scalars) and no
@@ -589,6 +600,7 @@ class ParticleFlowStepper:
         self.device_scalars = bool(device_scalars)
         self._use_graph = bool(use_graph) and self.device_scalars
         self._graph = None
+        self.graph_launches, self.launches_replayed = 0, 0
         if self.device_scalars:
             self.state = torch.zeros(24, dtype=torch.float64, device="cuda")
             self.state[6] = self.part_Z_cm
@@ -617,16 +629,11 @@ class ParticleFlowStepper:
                     self._one_dev()
                 return
             if self._graph is None:
-                self._one_dev()                      # warm-up outside capture
-                torch.cuda.synchronize()
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph, stream=side):
-                    self._one_dev()
+                self._graph = _capture_step(self, self._one_dev)
                 n -= 1
             for _ in range(n):
                 self._graph.replay()
+                self.launches_replayed += self.graph_launches
             return
         for _ in range(n):
             self._one()
@@ -848,6 +855,7 @@ class ParticleEnsemble:
         self = cls.__new__(cls)
         self.members, self.batched, self.pool = members, True, pool
         self._use_graph, self._graph, self._branches = bool(use_graph), None, max(1, int(branches))
+        self.graph_launches, self.launches_replayed = 0, 0
         self._solver = _BatchedFdSolver(nr, nz, len(params), solver.factors) if solver.factors.get("zfft") is not None \
             and solver.factors.get("tri") is not None else None
         self._w_wide = pool.wide[0]        # field 0 = vorticity, field 1 = psi (ParticleFlowStepper's F.new order)
@@ -947,16 +955,11 @@ class ParticleEnsemble:
                     self._enqueue_batched()
                 return
             if self._graph is None:
-                self._enqueue_batched()              # warm-up outside capture
-                torch.cuda.synchronize()
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph, stream=side):
-                    self._enqueue_batched()
+                self._graph = _capture_step(self, self._enqueue_batched)
                 n -= 1
             for _ in range(n):
                 self._graph.replay()
+                self.launches_replayed += self.graph_launches
             return
         cur = torch.cuda.current_stream()
         for st in self.streams:
