@@ -686,18 +686,25 @@ def e2e_rigid(stepper, nr, nz, steps, torch):
     torch.cuda.synchronize()
     serial_ms = a.elapsed_time(b) / k
     pipe = HostStepPipeline(stepper)
-    for i in range(2):
-        pipe.submit(hw[i & 1], hc, ho[i & 1])
-    pipe.drain()
-    t0 = time.perf_counter()
-    for i in range(k):
-        pipe.submit(hw[i & 1], hc, ho[i & 1])
-    pipe.drain()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / k       # three streams: wall clock around a full drain
-    return {"value": nr * nz / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * nr * nz * 8,
+
+    def piped(char):
+        for i in range(2):
+            pipe.submit(hw[i & 1], char, ho[i & 1])
+        pipe.drain()
+        t0 = time.perf_counter()
+        for i in range(k):
+            pipe.submit(hw[i & 1], char, ho[i & 1])
+        pipe.drain()
+        return (time.perf_counter() - t0) * 1e3 / k       # three streams: wall clock around a full drain
+
+    both_ms = piped(hc)          # every case brings its own characteristic function (a different body per case)
+    e2e_ms = piped(None)         # the reference loop: fixed body, char_func set once, per-step input = the vorticity
+    return {"value": nr * nz / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nr * nz * 8,
             "d2h_bytes_per_step": nr * nz * 8, "ms_per_step": e2e_ms,
-            "mode": "HostStepPipeline: pinned host buffers (vorticity + characteristic function in, vorticity out), "
-                    "H2D of case k+1 and D2H of case k-1 overlap the step of case k",
+            "mode": "HostStepPipeline: pinned host buffers, vorticity in / vorticity out every step (the characteristic "
+                    "function of the fixed body is resident, set once before the loop like flow_past_sphere.py:88-96); "
+                    "H2D of step k+1 and D2H of step k-1 overlap step k",
+            "with_char_func_upload_ms_per_step": both_ms, "with_char_func_upload_value": nr * nz / (both_ms * 1e-3),
             "serial_ms_per_step": serial_ms, "serial_value": nr * nz / (serial_ms * 1e-3)}
 
 
@@ -825,24 +832,25 @@ def run_gpu_arm(args, name, nr, nz):
         ho = torch.empty(own, dtype=torch.float64).pin_memory()
         hw.copy_(L.owned(stepper.vorticity))
         hc.copy_(L.owned(stepper.char_func))
-        stepper.step_host(hw, hc, ho)
+        stepper.step_host(hw, hc, ho)                        # sets the (fixed) body once
         torch.cuda.synchronize()
         dist.barrier()
         k = max(2, min(args.steps, 6))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(k):
-            stepper.step_host(hw, hc, ho)
+            stepper.step_host(hw, None, ho)                  # per-step input = the vorticity
         b.record()
         torch.cuda.synchronize()
         dist.barrier()
         t = torch.tensor([a.elapsed_time(b) / k], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
-        e2e = {"value": nr * nz / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * nr * nz * 8,
+        e2e = {"value": nr * nz / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nr * nz * 8,
                "d2h_bytes_per_step": nr * nz * 8, "ms_per_step": e2e_ms,
-               "mode": f"step_host on every rank: each of the {world} ranks stages its own slab (pinned host "
-                       "buffers) over its own PCIe link, serial per call"}
+               "mode": f"step_host on every rank: each of the {world} ranks stages its own slab of the vorticity (pinned "
+                       "host buffers) over its own PCIe link, serial per call; the fixed body's characteristic "
+                       "function is resident"}
         del hw, hc, ho
 
     extra = {}

@@ -186,6 +186,8 @@ _STATE = {
 def save_restart(stepper, path="restart.npz", asynchronous=False):
     """particle_in_bubble_oscillatory_flow.py:236-257 for a device-resident stepper"""
     fields, scalars = _STATE[type(stepper).__name__]
+    if getattr(stepper, "device_scalars", False):
+        stepper.sync_scalars()                                   # device-resident loop scalars -> host attributes
     items = {k: getattr(stepper, k) for k in fields}
     if type(stepper).__name__ == "RigidFlowStepper":
         items["t"] = stepper.state[0:1]                         # the key the reference's restart files lead with
@@ -207,4 +209,6 @@ def load_restart(stepper, path="restart.npz"):
     for k in scalars:
         cur = getattr(stepper, k)
         setattr(stepper, k, type(cur)(data[k]))
+    if getattr(stepper, "device_scalars", False):
+        stepper.push_scalars()                                   # ... and back into the device block
     return stepper

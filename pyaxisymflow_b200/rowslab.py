@@ -450,8 +450,9 @@ class RowSlabRigidFlowStepper:
         share over its own PCIe link."""
         L = self.L
         L.owned(self.vorticity).copy_(vorticity_rows_host, non_blocking=True)
-        L.owned(self.char_func).copy_(char_func_rows_host, non_blocking=True)
-        self.comm.exchange([self.char_func], 2)              # the penalisation reads chi on the halo rows
+        if char_func_rows_host is not None:                  # None: fixed body, the resident chi is kept
+            L.owned(self.char_func).copy_(char_func_rows_host, non_blocking=True)
+            self.comm.exchange([self.char_func], 2)          # the penalisation reads chi on the halo rows
         self.step(1)
         out_rows_host.copy_(L.owned(self.vorticity), non_blocking=True)
 

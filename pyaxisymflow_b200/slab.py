@@ -629,8 +629,9 @@ class SlabRigidFlowStepper:
         arrays) in, one step, owned vorticity columns out; every rank moves its share over its own PCIe link."""
         L = self.L
         L.owned(self.vorticity).copy_(vorticity_slab_host, non_blocking=True)
-        L.owned(self.char_func).copy_(char_func_slab_host, non_blocking=True)
-        self._refresh_char_halo()                            # the penalisation reads chi one column into the halo
+        if char_func_slab_host is not None:                  # None: fixed body, the resident chi is kept
+            L.owned(self.char_func).copy_(char_func_slab_host, non_blocking=True)
+            self._refresh_char_halo()                        # the penalisation reads chi one column into the halo
         self.step(1)
         out_slab_host.copy_(L.owned(self.vorticity), non_blocking=True)
 

@@ -872,6 +872,15 @@ def test_host_step_pipeline_matches_step_host(K):
     assert torch.equal(outs[0], want[0])
     for o, w in zip(outs, want):
         assert torch.equal(o, w)
+    # fixed body: the resident characteristic function is used when none is passed (same results, half the H2D)
+    s3 = RigidFlowStepper(nz)
+    pipe3 = HostStepPipeline(s3)
+    outs3 = [torch.empty_like(c).pin_memory() for c in cases]
+    for c, o in zip(cases, outs3):
+        pipe3.submit(c, None, o)
+    pipe3.drain()
+    for o, w in zip(outs3, want):
+        assert torch.equal(o, w)
 
 
 def test_rigid_flow_stepper_tridiagonal_r(K):

@@ -312,7 +312,7 @@ def test_vti_and_npz_from_device_fields(K, tmp_path):
         assert float(f["t"]) == 0.5 and np.array_equal(f["vorticity"], b + 1.0) and np.array_equal(f["part_phi"], a)
 
 
-@pytest.mark.parametrize("kind", ["rigid", "soft", "particle"])
+@pytest.mark.parametrize("kind", ["rigid", "soft", "particle", "soft-device", "particle-device"])
 def test_restart_resumes_bit_identically(K, tmp_path, kind):
     """run 3 steps, write restart.npz, run 3 more; a fresh stepper loaded from the file must land on the same bits
     (particle_in_bubble_oscillatory_flow.py:129-147 / :236-257)"""
@@ -327,6 +327,10 @@ def test_restart_resumes_bit_identically(K, tmp_path, kind):
             return s
         if kind == "soft":
             return SoftSphereStepper(64, Z_cm=0.47, reinit_levelset=True)
+        if kind == "soft-device":
+            return SoftSphereStepper(64, Z_cm=0.47, device_scalars=True, use_graph=True)
+        if kind == "particle-device":
+            return ParticleFlowStepper(64, device_scalars=True, use_graph=True)
         return ParticleFlowStepper(64)
 
     path = os.path.join(tmp_path, "restart.npz")
@@ -338,7 +342,11 @@ def test_restart_resumes_bit_identically(K, tmp_path, kind):
     r = make()
     io.load_restart(r, path)
     r.step(3)
-    if kind == "particle":
+    if kind.endswith("-device"):
+        # device-resident loop scalars: save_restart reads them through sync_scalars, load_restart pushes them back
+        s.sync_scalars()
+        r.sync_scalars()
+    if kind.startswith("particle"):
         # the penalisation force is an atomic sum of terms that cancel to ~1e-9 of their size (lambda = 1e12), so two
         # runs of the SAME loop already differ in the rigid-body feedback at ~1e-7: the resumed
         # run is held to that, not to bit equality
@@ -350,7 +358,7 @@ def test_restart_resumes_bit_identically(K, tmp_path, kind):
     if kind == "rigid":
         assert np.array_equal(r.state.cpu().numpy(), s.state.cpu().numpy())
     else:
-        assert r.t == s.t and r.it == s.it
+        assert r.t == s.t and r.it == s.it and r.it == 6
         assert np.array_equal(r.ball_phi.cpu().numpy(), s.ball_phi.cpu().numpy())
         assert np.array_equal(r.eta1.cpu().numpy(), s.eta1.cpu().numpy())
 
