@@ -541,8 +541,12 @@ def make_stepper(name, nr, nz, args, world):
 
     if name == "c1":
         # the reference's own CPU-runnable case (FlowPastSphere CLI default 128x256): launch bound, so the
-        # whole step is replayed as one CUDA graph
-        st = RigidFlowStepper(nz, grid_size_r=nr, use_graph=True)
+        # whole step is replayed as one CUDA graph.  --r-method / --z-method left on "auto" select the cosine-transform
+        # + tridiagonal solve here as well (the library's own "auto" keeps the reference's four small GEMMs on LAPACK
+        # bases below 1536 points a side: 0.13 ms of a 0.19 ms step on two CTAs)
+        rm = "tridiagonal" if args.r_method == "auto" else args.r_method
+        zm = "fft" if args.z_method == "auto" else args.z_method
+        st = RigidFlowStepper(nz, grid_size_r=nr, use_graph=True, r_method=rm, z_method=zm)
         st.seed_vorticity()
         return st
     if name == "c2":

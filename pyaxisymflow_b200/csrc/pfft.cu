@@ -26,79 +26,153 @@ namespace {
 struct PfftFactors {
   int n;         // number of passes
   int r[12];     // radix of each pass
+  int pg[12];    // odd radices: output pairs per work item (1..3)
 };
 
 __device__ __forceinline__ double2 cmulf(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// all passes of the length-M complex FFT; data starts in `a`, returns the buffer holding the result.
-// A work item is (butterfly j, group of PG outputs u0 .. u0+PG-1): every input of the butterfly is read once per
-// item and multiplied by its pass twiddle (global table, L1 resident) once, then feeds PG accumulators with the
-// R-point DFT weights W_R^(u t) = wt[t R + u], an R x R table per pass built once per CTA, read at the same
-// address by all lanes of a warp (items of a warp share the output group) with immediate offsets -- no index
-// arithmetic in the inner loop.
-constexpr int PG = 4;
+// All passes of the length-M complex FFT; data starts in `a`, returns the buffer holding the result
+// (tools/rfft_model.py: cfft_passes_paired).
+//   * The pass twiddle W_M^(jm t M / (ns R)) of input (j, t) is applied when the PREVIOUS pass stores that element
+//     (every element is read by exactly one (j, t) of the next pass): a butterfly reads plain values, and nothing is
+//     twiddled more than once.
+//   * An odd radix R pairs the inputs t, R-t and the outputs u, R-u:
+//         S_t = x_t + x_(R-t),  D_t = x_t - x_(R-t),  A_u = sum_t S_t cos(2 pi u t / R),  B_u = sum_t D_t sin(2 pi u t / R)
+//         X_u = x_0 + A_u - i B_u,   X_(R-u) = x_0 + A_u + i B_u,   X_0 = x_0 + sum_t S_t
+//     -- a quarter of the multiplications of the R x R sum (R = 31: 900 instead of 3720 FMAs per butterfly).  A work
+//     item is (butterfly j, group of PGP output pairs); the (cos, sin) weights of a pass are an H x H table
+//     (H = (R-1)/2) in shared memory, read at the same address by all lanes of a warp.  PGP is chosen per pass on the
+//     host so that the items of the pass fill the 512 threads in as few rounds as possible (F.pg).
+//   * Radix 2 and 4 are the usual butterflies.
 constexpr int PB = 512;          // threads per CTA
+
+struct NextTw {                  // pre-twiddle of the next pass, by output position
+  int on, Ln, nsn, stepn;
+};
+__device__ __forceinline__ void pf_store(double2* __restrict__ b, int pos, double2 v, const NextTw& nt,
+                                         const double2* __restrict__ tabM) {
+  if (nt.on) {
+    const int tn = pos / nt.Ln;
+    const int jn = pos - tn * nt.Ln;
+    const int k = (jn % nt.nsn) * tn * nt.stepn;                 // < M by construction
+    if (k) v = cmulf(v, __ldg(&tabM[k]));
+  }
+  b[pos] = v;
+}
+
 __device__ __forceinline__ void pfft_build_weights(double2* wt, const double2* __restrict__ tabM, int M, const PfftFactors& F) {
   int off = 0;
   for (int p = 0; p < F.n; ++p) {
     const int R = F.r[p], L = M / R;
-    for (int i = threadIdx.x; i < R * R; i += blockDim.x) {
-      const int t = i / R, u = i - t * R;
-      wt[off + i] = tabM[((u * t) % R) * L];
+    if (!(R & 1)) continue;
+    const int H = (R - 1) / 2;
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+      const int t = i / H + 1, u = i - (t - 1) * H + 1;          // [t][u]: the outputs of a group are adjacent
+      const double2 v = tabM[((u * t) % R) * L];                 // (cos, -sin) of 2 pi u t / R
+      wt[off + i] = make_double2(v.x, -v.y);
     }
-    off += R * R;
+    off += H * H;
   }
 }
+
+template <int PGP>
+__device__ __forceinline__ void pfft_pass_odd(const double2* __restrict__ a, double2* __restrict__ b,
+                                              const double2* __restrict__ wt, int M, int R, int ns, const NextTw nt,
+                                              const double2* __restrict__ tabM) {
+  const int H = (R - 1) / 2, L = M / R, NG = (H + PGP - 1) / PGP;
+  for (int w = threadIdx.x; w < L * NG; w += blockDim.x) {
+    const int ug = w / L;
+    const int j = w - ug * L;
+    const int u0 = ug * PGP;                                     // pairs u0 + 1 .. u0 + nv
+    const int nv = min(PGP, H - u0);
+    const double2 x0 = a[j];
+    double2 sum0 = x0;
+    double2 A[PGP], B[PGP];
+#pragma unroll
+    for (int g = 0; g < PGP; ++g) { A[g] = make_double2(0.0, 0.0); B[g] = make_double2(0.0, 0.0); }
+    const double2* row = wt + u0;
+#pragma unroll 1
+    for (int t = 1; t <= H; ++t) {
+      const double2 xp = a[j + t * L], xm = a[j + (R - t) * L];
+      const double2 S = make_double2(xp.x + xm.x, xp.y + xm.y), D = make_double2(xp.x - xm.x, xp.y - xm.y);
+      sum0.x += S.x;
+      sum0.y += S.y;
+#pragma unroll
+      for (int g = 0; g < PGP; ++g) {
+        if (g < nv) {
+          const double2 cs = row[g];
+          A[g].x += S.x * cs.x;
+          A[g].y += S.y * cs.x;
+          B[g].x += D.x * cs.y;
+          B[g].y += D.y * cs.y;
+        }
+      }
+      row += H;
+    }
+    const int jm = j % ns;
+    const int base = (j - jm) * R + jm;
+#pragma unroll
+    for (int g = 0; g < PGP; ++g) {
+      if (g < nv) {
+        const int u = u0 + g + 1;
+        const double ax = x0.x + A[g].x, ay = x0.y + A[g].y;
+        pf_store(b, base + u * ns, make_double2(ax + B[g].y, ay - B[g].x), nt, tabM);
+        pf_store(b, base + (R - u) * ns, make_double2(ax - B[g].y, ay + B[g].x), nt, tabM);
+      }
+    }
+    if (ug == 0) pf_store(b, base, sum0, nt, tabM);
+  }
+}
+
 __device__ __forceinline__ double2* pfft_passes(double2* a, double2* b, const double2* __restrict__ tabM,
                                                const double2* __restrict__ wt, int M, const PfftFactors& F) {
   int ns = 1, off = 0;
   for (int p = 0; p < F.n; ++p) {
     const int R = F.r[p];
     const int L = M / R;
-    const int step_j = M / (ns * R);              // table stride of the pass twiddle per unit of jm
-    const int NG = (R + PG - 1) / PG;
-    for (int w = threadIdx.x; w < L * NG; w += blockDim.x) {
-      const int ug = w / L;
-      const int j = w - ug * L;
-      const int u0 = ug * PG;
-      const int nv = min(PG, R - u0);
-      const int jm = j % ns;
-      const int dtw = jm * step_j;
-      const double2 v0 = a[j];
-      double2 acc[PG];
-#pragma unroll
-      for (int g = 0; g < PG; ++g) acc[g] = v0;
-      int ktw = 0;
-      const double2* wrow = wt + off + u0;
-#pragma unroll 2
-      for (int t = 1; t < R; ++t) {
-        double2 v = a[j + t * L];
-        if (ns > 1) {
-          ktw += dtw;
-          if (ktw >= M) ktw -= M;
-          v = cmulf(v, __ldg(&tabM[ktw]));
-        }
-        wrow += R;
-#pragma unroll
-        for (int g = 0; g < PG; ++g) {
-          if (g < nv) {
-            const double2 c = wrow[g];
-            acc[g].x += v.x * c.x - v.y * c.y;
-            acc[g].y += v.x * c.y + v.y * c.x;
-          }
-        }
+    NextTw nt;
+    nt.on = (p + 1 < F.n);
+    if (nt.on) {
+      const int Rn = F.r[p + 1];
+      nt.Ln = M / Rn;
+      nt.nsn = ns * R;
+      nt.stepn = M / (nt.nsn * Rn);
+    } else {
+      nt.Ln = 1; nt.nsn = 1; nt.stepn = 0;
+    }
+    if (R == 2) {
+      for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const double2 x0 = a[j], x1 = a[j + L];
+        const int jm = j % ns;
+        const int base = (j - jm) * 2 + jm;
+        pf_store(b, base, make_double2(x0.x + x1.x, x0.y + x1.y), nt, tabM);
+        pf_store(b, base + ns, make_double2(x0.x - x1.x, x0.y - x1.y), nt, tabM);
       }
-      const int base = (j - jm) * R + jm;
-#pragma unroll
-      for (int g = 0; g < PG; ++g)
-        if (g < nv) b[base + (u0 + g) * ns] = acc[g];
+    } else if (R == 4) {
+      for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const double2 x0 = a[j], x1 = a[j + L], x2 = a[j + 2 * L], x3 = a[j + 3 * L];
+        const double2 t0 = make_double2(x0.x + x2.x, x0.y + x2.y), t1 = make_double2(x0.x - x2.x, x0.y - x2.y);
+        const double2 t2 = make_double2(x1.x + x3.x, x1.y + x3.y), t3 = make_double2(x1.x - x3.x, x1.y - x3.y);
+        const int jm = j % ns;
+        const int base = (j - jm) * 4 + jm;
+        pf_store(b, base, make_double2(t0.x + t2.x, t0.y + t2.y), nt, tabM);
+        pf_store(b, base + ns, make_double2(t1.x + t3.y, t1.y - t3.x), nt, tabM);          // t1 - i t3
+        pf_store(b, base + 2 * ns, make_double2(t0.x - t2.x, t0.y - t2.y), nt, tabM);
+        pf_store(b, base + 3 * ns, make_double2(t1.x - t3.y, t1.y + t3.x), nt, tabM);      // t1 + i t3
+      }
+    } else {
+      switch (F.pg[p]) {
+        case 1: pfft_pass_odd<1>(a, b, wt + off, M, R, ns, nt, tabM); break;
+        case 2: pfft_pass_odd<2>(a, b, wt + off, M, R, ns, nt, tabM); break;
+        default: pfft_pass_odd<3>(a, b, wt + off, M, R, ns, nt, tabM); break;
+      }
+      off += ((R - 1) / 2) * ((R - 1) / 2);
     }
     __syncthreads();
     double2* t = a; a = b; b = t;
     ns *= R;
-    off += R * R;
   }
   return a;
 }
@@ -195,7 +269,22 @@ bool pfft_factorize(int M, PfftFactors* F) {
       F->r[F->n++] = p;
       m /= p;
     }
-  return m == 1 && M >= 2;
+  if (!(m == 1 && M >= 2)) return false;
+  // odd radices: output pairs per work item -- the fewest rounds of PB threads, then the least work per item
+  for (int p = 0; p < F->n; ++p) {
+    const int R = F->r[p];
+    F->pg[p] = 1;
+    if (!(R & 1)) continue;
+    const int H = (R - 1) / 2, L = M / R;
+    long long best = -1;
+    for (int g = 1; g <= 3; ++g) {                               // 4 pairs per item would spill at 64 registers
+      const int items = L * ((H + g - 1) / g);
+      const long long rounds = (items + PB - 1) / PB;
+      const long long cost = rounds * (6 + 5 * g);               // per t: 2 loads + 4 adds + g x (1 load + 4 FMA)
+      if (best < 0 || cost < best) { best = cost; F->pg[p] = g; }
+    }
+  }
+  return true;
 }
 // shared memory: two row buffers + the R x R weight tables of all passes
 size_t pfft_smem_bytes(int M, const PfftFactors& F) {

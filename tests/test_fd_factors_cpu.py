@@ -188,6 +188,11 @@ def test_periodic_rfft_model():
         assert np.abs(h[m + 1:] - ref.imag[1:m]).max() <= 1e-13 * np.abs(ref).max()
         assert np.abs(rm.irfft_row(h, f, tm, tn) - x).max() <= 1e-13
         assert np.array_equal(rm.mode_of_column(n)[:m + 1], np.arange(m + 1))
+        # the passes as the kernel runs them (twiddles applied at the previous pass's store, odd radices with paired
+        # inputs / outputs): same FFT
+        z = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+        want = np.fft.fft(z)
+        assert np.abs(rm.cfft_passes_paired(z, f, tm) - want).max() <= 1e-13 * np.abs(want).max()
     assert fd.rfft_factors(2044 // 2) is None and not fd.rfft_supported(2044)      # 511 = 7 * 73
     assert fd.rfft_supported(4092) and fd.rfft_spectral_width(4092) == 4096
 

@@ -53,6 +53,57 @@ def cfft_passes(z, factors, tab_m):
     return cur
 
 
+def cfft_passes_paired(z, factors, tab_m):
+    """the passes as csrc/pfft.cu runs them since round 2 (same result as cfft_passes):
+      * the pass twiddle W_M^(jm t M/(ns R)) of input (j, t) is applied when the PREVIOUS pass stores that element
+        (every element is read by exactly one (j, t) of the next pass), so a butterfly reads plain values;
+      * an odd radix R pairs the inputs t, R-t and the outputs u, R-u:
+            S_t = x_t + x_(R-t),  D_t = x_t - x_(R-t),  A_u = sum_t S_t cos(2 pi u t / R),  B_u = sum_t D_t sin(..)
+            X_u = x_0 + A_u - i B_u,   X_(R-u) = x_0 + A_u + i B_u,   X_0 = x_0 + sum_t S_t
+        -- a quarter of the multiplications of the R x R sum;
+      * radix 2 and 4 are the usual butterflies."""
+    m = z.size
+    ns = 1
+    cur = z.astype(complex).copy()
+    for p, r in enumerate(factors):
+        L = m // r
+        out = np.zeros(m, complex)
+        j = np.arange(L)
+        jm = j % ns
+        base = (j - jm) * r + jm
+        x = [cur[j + t * L] for t in range(r)]
+        if r == 2:
+            res = {0: x[0] + x[1], 1: x[0] - x[1]}
+        elif r == 4:
+            t0, t1, t2, t3 = x[0] + x[2], x[0] - x[2], x[1] + x[3], x[1] - x[3]
+            res = {0: t0 + t2, 2: t0 - t2, 1: t1 - 1j * t3, 3: t1 + 1j * t3}
+        else:
+            h = (r - 1) // 2
+            S = [x[t] + x[r - t] for t in range(1, h + 1)]
+            D = [x[t] - x[r - t] for t in range(1, h + 1)]
+            res = {0: x[0] + sum(S)}
+            for u in range(1, h + 1):
+                w = [tab_m[((u * t) % r) * L] for t in range(1, h + 1)]       # (cos, -sin) of 2 pi u t / R
+                A = sum(S[t] * w[t].real for t in range(h))
+                B = sum(D[t] * (-w[t].imag) for t in range(h))
+                res[u] = x[0] + A - 1j * B
+                res[r - u] = x[0] + A + 1j * B
+        for u, v in res.items():
+            out[base + u * ns] = v
+        ns *= r
+        if p + 1 < len(factors):                  # pre-twiddle for the next pass, by output position
+            rn = factors[p + 1]
+            Ln = m // rn
+            pos = np.arange(m)
+            tn = pos // Ln
+            jn = pos - tn * Ln
+            k = (jn % ns) * tn * (m // (ns * rn))
+            assert k.max() < m
+            out = out * tab_m[k]
+        cur = out
+    return cur
+
+
 def rfft_row(x, factors, tab_m, tab_n):
     """x (N reals) -> half-complex layout of length N, unnormalised"""
     n = x.size
@@ -107,4 +158,6 @@ if __name__ == "__main__":
         m = n // 2
         err = max(np.abs(h[:m + 1] - ref.real).max(), np.abs(h[m + 1:] - ref.imag[1:m]).max()) / np.abs(ref).max()
         back = np.abs(irfft_row(h, f, tm, tn) - x).max()
-        print(n, f, err, back)
+        z = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+        pair = np.abs(cfft_passes_paired(z, f, tm) - np.fft.fft(z)).max() / np.abs(np.fft.fft(z)).max()
+        print(n, f, err, back, pair)
