@@ -48,15 +48,20 @@ __device__ __forceinline__ double2 cmulf(double2 a, double2 b) {
 //   * Radix 2 and 4 are the usual butterflies.
 constexpr int PB = 512;          // threads per CTA
 
+// a / d for 0 <= a < 2^15, 1 <= d < 2^15 without the integer-division sequence: (a + 0.5) / d is at least 0.5 / d
+// > 1.5e-5 away from an integer, far more than the rounding of the float product (< 2^15 * 2^-22), so the floor is exact
+__device__ __forceinline__ int qdiv_small(int a, float inv_d) { return __float2int_rd(((float)a + 0.5f) * inv_d); }
+
 struct NextTw {                  // pre-twiddle of the next pass, by output position
   int on, Ln, nsn, stepn;
+  float inv_Ln, inv_nsn;
 };
 __device__ __forceinline__ void pf_store(double2* __restrict__ b, int pos, double2 v, const NextTw& nt,
                                          const double2* __restrict__ tabM) {
   if (nt.on) {
-    const int tn = pos / nt.Ln;
+    const int tn = qdiv_small(pos, nt.inv_Ln);
     const int jn = pos - tn * nt.Ln;
-    const int k = (jn % nt.nsn) * tn * nt.stepn;                 // < M by construction
+    const int k = (jn - qdiv_small(jn, nt.inv_nsn) * nt.nsn) * tn * nt.stepn;   // (jn mod nsn) tn stepn < M
     if (k) v = cmulf(v, __ldg(&tabM[k]));
   }
   b[pos] = v;
@@ -79,11 +84,11 @@ __device__ __forceinline__ void pfft_build_weights(double2* wt, const double2* _
 
 template <int PGP>
 __device__ __forceinline__ void pfft_pass_odd(const double2* __restrict__ a, double2* __restrict__ b,
-                                              const double2* __restrict__ wt, int M, int R, int ns, const NextTw nt,
-                                              const double2* __restrict__ tabM) {
+                                              const double2* __restrict__ wt, int M, int R, int ns, float inv_L,
+                                              float inv_ns, const NextTw nt, const double2* __restrict__ tabM) {
   const int H = (R - 1) / 2, L = M / R, NG = (H + PGP - 1) / PGP;
   for (int w = threadIdx.x; w < L * NG; w += blockDim.x) {
-    const int ug = w / L;
+    const int ug = qdiv_small(w, inv_L);
     const int j = w - ug * L;
     const int u0 = ug * PGP;                                     // pairs u0 + 1 .. u0 + nv
     const int nv = min(PGP, H - u0);
@@ -111,7 +116,7 @@ __device__ __forceinline__ void pfft_pass_odd(const double2* __restrict__ a, dou
       }
       row += H;
     }
-    const int jm = j % ns;
+    const int jm = j - qdiv_small(j, inv_ns) * ns;
     const int base = (j - jm) * R + jm;
 #pragma unroll
     for (int g = 0; g < PGP; ++g) {
@@ -142,10 +147,13 @@ __device__ __forceinline__ double2* pfft_passes(double2* a, double2* b, const do
     } else {
       nt.Ln = 1; nt.nsn = 1; nt.stepn = 0;
     }
+    nt.inv_Ln = 1.0f / (float)nt.Ln;
+    nt.inv_nsn = 1.0f / (float)nt.nsn;
+    const float inv_L = 1.0f / (float)L, inv_ns = 1.0f / (float)ns;
     if (R == 2) {
       for (int j = threadIdx.x; j < L; j += blockDim.x) {
         const double2 x0 = a[j], x1 = a[j + L];
-        const int jm = j % ns;
+        const int jm = j - qdiv_small(j, inv_ns) * ns;
         const int base = (j - jm) * 2 + jm;
         pf_store(b, base, make_double2(x0.x + x1.x, x0.y + x1.y), nt, tabM);
         pf_store(b, base + ns, make_double2(x0.x - x1.x, x0.y - x1.y), nt, tabM);
@@ -155,7 +163,7 @@ __device__ __forceinline__ double2* pfft_passes(double2* a, double2* b, const do
         const double2 x0 = a[j], x1 = a[j + L], x2 = a[j + 2 * L], x3 = a[j + 3 * L];
         const double2 t0 = make_double2(x0.x + x2.x, x0.y + x2.y), t1 = make_double2(x0.x - x2.x, x0.y - x2.y);
         const double2 t2 = make_double2(x1.x + x3.x, x1.y + x3.y), t3 = make_double2(x1.x - x3.x, x1.y - x3.y);
-        const int jm = j % ns;
+        const int jm = j - qdiv_small(j, inv_ns) * ns;
         const int base = (j - jm) * 4 + jm;
         pf_store(b, base, make_double2(t0.x + t2.x, t0.y + t2.y), nt, tabM);
         pf_store(b, base + ns, make_double2(t1.x + t3.y, t1.y - t3.x), nt, tabM);          // t1 - i t3
@@ -164,9 +172,9 @@ __device__ __forceinline__ double2* pfft_passes(double2* a, double2* b, const do
       }
     } else {
       switch (F.pg[p]) {
-        case 1: pfft_pass_odd<1>(a, b, wt + off, M, R, ns, nt, tabM); break;
-        case 2: pfft_pass_odd<2>(a, b, wt + off, M, R, ns, nt, tabM); break;
-        default: pfft_pass_odd<3>(a, b, wt + off, M, R, ns, nt, tabM); break;
+        case 1: pfft_pass_odd<1>(a, b, wt + off, M, R, ns, inv_L, inv_ns, nt, tabM); break;
+        case 2: pfft_pass_odd<2>(a, b, wt + off, M, R, ns, inv_L, inv_ns, nt, tabM); break;
+        default: pfft_pass_odd<3>(a, b, wt + off, M, R, ns, inv_L, inv_ns, nt, tabM); break;
       }
       off += ((R - 1) / 2) * ((R - 1) / 2);
     }
