@@ -334,7 +334,7 @@ template <bool EXACT>
 __device__ __forceinline__ double qdiv(double a, double b, double inv_b) { return EXACT ? a / b : a * inv_b; }
 
 template <bool CHI, bool EXACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     k_solid_fused(GridD g, double* __restrict__ w, const double* __restrict__ eta1, const double* __restrict__ eta2,
                   const double* __restrict__ chi, const double* __restrict__ r1d, double G, double dt,
                   const double* __restrict__ dt_dev) {
@@ -350,21 +350,51 @@ __global__ void __launch_bounds__(256)
     const int j = J0 - 1 + (int)threadIdx.x;
     inv_r[threadIdx.x] = (j >= 0 && j < nr) ? 1.0 / r1d[j] : 0.0;
   }
-  // stage 1: reference maps on rows J0-3 .. J0+FT_R+2, columns K0-3 .. K0+FT_C+2 (zero outside the domain)
-  for (int i = threadIdx.x; i < FE_R * FE_C; i += 256) {
+  // stage 1: reference maps on rows J0-3 .. J0+FT_R+2, columns K0-3 .. K0+FT_C+2 (zero outside the domain).  All global
+  // loads of the block -- the two maps, chi for the sigma ring, the block's own w -- are issued before the first use.
+  constexpr int N1 = (FE_R * FE_C + 255) / 256, N2 = (FS_R * FS_C + 255) / 256, N4 = (FT_R * FT_C) / 256;
+  double va[N1], vb[N1], cx[N2], w0[N4];
+#pragma unroll
+  for (int it = 0; it < N1; ++it) {
+    const int i = threadIdx.x + it * 256;
     const int rr = i / FE_C, cc = i - rr * FE_C;
     const int j = J0 - 3 + rr, k = K0 - 3 + cc;
-    double a = 0.0, b = 0.0;
-    if (j >= 0 && j < nr && k >= 0 && k < nz) {
-      a = eta1[(long long)j * g.ld + k];
-      b = eta2[(long long)j * g.ld + k];
+    va[it] = 0.0;
+    vb[it] = 0.0;
+    if (i < FE_R * FE_C && j >= 0 && j < nr && k >= 0 && k < nz) {
+      va[it] = eta1[(long long)j * g.ld + k];
+      vb[it] = eta2[(long long)j * g.ld + k];
     }
-    e1[i] = a;
-    e2[i] = b;
+  }
+#pragma unroll
+  for (int it = 0; it < N2; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int rr = i / FS_C, cc = i - rr * FS_C;
+    const int j = J0 - 2 + rr, k = K0 - 2 + cc;
+    cx[it] = 1.0;
+    if (CHI && i < FS_R * FS_C && j >= 0 && j < nr && k >= 0 && k < nz) cx[it] = chi[(long long)j * g.ld + k];
+  }
+#pragma unroll
+  for (int it = 0; it < N4; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int rr = i / FT_C, cc = i - rr * FT_C;
+    const int j = J0 + rr, k = K0 + cc;
+    w0[it] = (j >= 1 && j < nr - 1 && k >= 1 && k <= nz - 2) ? w[(long long)j * g.ld + k] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < N1; ++it) {
+    const int i = threadIdx.x + it * 256;
+    if (i < FE_R * FE_C) {
+      e1[i] = va[it];
+      e2[i] = vb[it];
+    }
   }
   __syncthreads();
   // stage 2: sigma on rows J0-2 .. , columns K0-2 ..
-  for (int i = threadIdx.x; i < FS_R * FS_C; i += 256) {
+#pragma unroll
+  for (int it = 0; it < N2; ++it) {
+    const int i = threadIdx.x + it * 256;
+    if (i >= FS_R * FS_C) break;
     const int rr = i / FS_C, cc = i - rr * FS_C;
     const int j = J0 - 2 + rr, k = K0 - 2 + cc;
     double a11 = 0.0, a12 = 0.0;
@@ -388,9 +418,8 @@ __global__ void __launch_bounds__(256)
       a12 = -G * (z1 * r1 + z2 * r2);
       a11 = (0.5 * G) * (r1 * r1 + r2 * r2 - z1 * z1 - z2 * z2);
       if (CHI) {
-        const double x = chi[(long long)j * g.ld + k];
-        a11 = x * a11;
-        a12 = x * a12;
+        a11 = cx[it] * a11;
+        a12 = cx[it] * a12;
       }
     }
     s11[i] = a11;
@@ -421,13 +450,14 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   // stage 4: the block's own cells
-  for (int i = threadIdx.x; i < FT_R * FT_C; i += 256) {
+#pragma unroll
+  for (int it = 0; it < N4; ++it) {
+    const int i = threadIdx.x + it * 256;
     const int rr = i / FT_C, cc = i - rr * FT_C;
     const int j = J0 + rr, k = K0 + cc;
     if (j < 1 || j >= nr - 1 || k < 1 || k > nz - 2) continue;
     const int c = (rr + 1) * FQ_C + (cc + 1);
-    double* wp = w + (long long)j * g.ld + k;
-    *wp = *wp + qdiv<EXACT>(dt * (tr[c + 1] - tr[c - 1] - tz[c + FQ_C] + tz[c - FQ_C]), h, ih);
+    w[(long long)j * g.ld + k] = w0[it] + qdiv<EXACT>(dt * (tr[c + 1] - tr[c - 1] - tz[c + FQ_C] + tz[c - FQ_C]), h, ih);
   }
 }
 

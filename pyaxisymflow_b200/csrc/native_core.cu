@@ -473,7 +473,7 @@ __device__ __forceinline__ double shfl_from(double v, int delta) {   // value of
   return delta > 0 ? __shfl_up_sync(0xffffffffu, v, delta) : (delta < 0 ? __shfl_down_sync(0xffffffffu, v, -delta) : v);
 }
 
-__global__ void __launch_bounds__(32 * PG_WARPS)
+__global__ void __launch_bounds__(32 * PG_WARPS, 8)
     k_p2m_lattice_gather(GridD g, int RB, double* __restrict__ w_out, const double* __restrict__ w_in,
                          const double* __restrict__ u_z, const double* __restrict__ u_r, const double* __restrict__ zl,
                          const double* __restrict__ rl, double dt, const double* __restrict__ dt_dev, int* far_flag) {
