@@ -809,3 +809,31 @@ def test_fused_solid_stress_equals_the_three_calls(K, nr, nz):
         wo = w0.copy()
         ox.update_vorticity_from_solid_stress(wo, o["tz"], o["tr"], o["s11"], o["s12"], o["s22"], R, dt, dx)
         assert_close(got, wo, 1e-12, "fused solid stress vs oracle")
+
+
+@pytest.mark.parametrize("nr,nz", [(24, 64), (37, 53), (8, 130), (5, 4), (16, 1028)])
+def test_heaviside_with_mask(K, nr, nz):
+    """axb_smooth_heaviside_mask (soft_sphere_streaming.py:205-206): H = smooth_Heaviside(phi) and the dense uint8
+    mask H > 0.5 in one pass -- four columns per thread where the rows allow it, scalar otherwise; same bits as the
+    plain Heaviside entry, which is pinned by the golden vectors."""
+    import ctypes
+
+    import torch
+    from pyaxisymflow_b200 import _lib
+    from pyaxisymflow_b200.device import make_grid, ptr, stream_ptr
+
+    rng = np.random.default_rng(nr + nz)
+    dx = 1.0 / nz
+    phi = (rng.standard_normal((nr, nz)) * 3 * dx)
+    want = np.zeros_like(phi)
+    ox.smooth_Heaviside(want, phi, 2 * dx)
+    g = make_grid(nr, nz, nz, dx)
+    d_phi = torch.from_numpy(phi).cuda()
+    H = torch.full_like(d_phi, -1.0)
+    for ge in (0, 1):
+        mask = torch.full((nr, nz), 7, dtype=torch.uint8, device="cuda")
+        _lib.call("axb_smooth_heaviside_mask", ctypes.byref(g), ptr(H), ptr(mask), ptr(d_phi), 2 * dx, 0.5, ge, stream_ptr())
+        got = H.cpu().numpy()
+        assert_close(got, want, 1e-14, "Heaviside with mask")
+        m = mask.cpu().numpy().astype(bool)
+        assert np.array_equal(m, (got >= 0.5) if ge else (got > 0.5))
