@@ -63,7 +63,7 @@ def config_dict(name, nr, nz, world, cases_per_gpu, reinit=False):
     """the `config` object -- built by this one function for both arms, so the two lines describe the same job"""
     flush = needs_flush(name, nr, nz)
     slab = "z-slab" if os.environ.get("AXB_SLAB_Z") else "r-slab"
-    par = "single GPU" if world == 1 else (f"{slab} x{world}" if name == "c4" else f"{world} independent replicas")
+    par = "single GPU" if world == 1 else (f"{slab} x{world}" if name in ("c4", "c2") else f"{world} independent replicas")
     wl = WORKLOADS[name].format(nr=nr, nz=nz, cases=cases_per_gpu)
     if name == "c3":
         wl += ("; narrow-band level-set re-initialisation included" if reinit
@@ -345,7 +345,7 @@ def run_reference_arm(args, name, nr, nz):
     value = s.points / secs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
-            "scaling": "strong" if name == "c4" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if name in ("c4", "c2") else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(name, nr, nz, world, args.cases, args.reinit),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": s.cores, "kind": "port",
                              "sample": s.describe() + f"; each of the {args.steps} timed steps is one sample step "
@@ -550,8 +550,14 @@ def make_stepper(name, nr, nz, args, world):
         st.seed_vorticity()
         return st
     if name == "c2":
-        st = RigidFlowStepper(nz, grid_size_r=nr, periodic=True, r_sph=0.075, Z_cm=0.85,
-                              use_graph=not args.no_graph)
+        if world > 1:                                # rows split over the ranks; the periodic wrap stays inside a row
+            from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper
+
+            st = RowSlabRigidFlowStepper(nz, grid_size_r=nr, periodic=True, r_sph=0.075, Z_cm=0.85,
+                                         use_graph=not args.no_graph)
+        else:
+            st = RigidFlowStepper(nz, grid_size_r=nr, periodic=True, r_sph=0.075, Z_cm=0.85,
+                                  use_graph=not args.no_graph)
         st.seed_vorticity()
         return st
     if name == "c4":
@@ -636,7 +642,8 @@ def measure_gpu(name, nr, nz, args, steps, warmup, world, rank, dist, sampler=No
     clocks = sampler.stop() if sampler is not None else None
     ms_per_step = ms / steps
     per_gpu_cases = cases
-    value = per_gpu_cases * world * nr * nz / (ms_per_step * 1e-3) if name != "c4" else nr * nz / (ms_per_step * 1e-3)
+    slabbed = name in ("c4", "c2")                         # one domain split over the ranks (strong scaling)
+    value = nr * nz / (ms_per_step * 1e-3) if slabbed else per_gpu_cases * world * nr * nz / (ms_per_step * 1e-3)
     warm_ms = None
     if flush is not None:                                   # the same steps back to back, L2-warm, for comparison
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -747,22 +754,27 @@ def e2e_generic(runner, nr, nz, steps, torch):
             "mode": "serial per step: state fields H2D from pinned host memory, one step, state fields D2H"}
 
 
-def slab_vs_single(world, rank, dist, torch, nz=2048, steps=4):
+def slab_vs_single(world, rank, dist, torch, nz=2048, steps=4, periodic=False):
     """correctness of the multi-GPU path, outside the timed region: the slab stepper against the single-GPU
     stepper on a reduced grid (nz/4 x nz), relative L-infinity of the vorticity after `steps` steps"""
     from pyaxisymflow_b200.timestep import RigidFlowStepper
 
-    if os.environ.get("AXB_SLAB_Z"):
+    pk = {"periodic": True, "r_sph": 0.075, "Z_cm": 0.85} if periodic else {}
+    if periodic:
+        nz += 4                                      # inner width 2^11 + 2 x 2 ghost columns
+    if os.environ.get("AXB_SLAB_Z") and not periodic:
         from pyaxisymflow_b200.slab import SlabRigidFlowStepper as Stepper
     else:
         from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper as Stepper
-    s = Stepper(nz, grid_size_r=nz // 4, **({} if os.environ.get("AXB_SLAB_Z") else {"use_graph": True}))
+    kw = {} if (os.environ.get("AXB_SLAB_Z") and not periodic) else {"use_graph": True}
+    s = Stepper(nz, grid_size_r=(nz - 4 if periodic else nz) // 4, **kw, **pk)
     s.seed_vorticity()
     s.step(steps)
     w = s.gather_vorticity()
     err = None
+    nr = (nz - 4 if periodic else nz) // 4
     if rank == 0:
-        ref = RigidFlowStepper(nz, grid_size_r=nz // 4)
+        ref = RigidFlowStepper(nz, grid_size_r=nr, **pk)
         ref.seed_vorticity()
         ref.step(steps)
         torch.cuda.synchronize()
@@ -773,7 +785,7 @@ def slab_vs_single(world, rank, dist, torch, nz=2048, steps=4):
         s.close()
     del s
     torch.cuda.empty_cache()
-    return err, f"{nz // 4}x{nz}, {steps} steps"
+    return err, f"{nr}x{nz}{' periodic' if periodic else ''}, {steps} steps"
 
 
 def run_gpu_arm(args, name, nr, nz):
@@ -827,7 +839,7 @@ def run_gpu_arm(args, name, nr, nz):
             e2e = e2e_rigid(stepper, nr, nz, args.steps, torch)
         else:
             e2e = e2e_generic(stepper, nr, nz, args.steps, torch)
-    elif name == "c4":
+    elif name in ("c4", "c2"):
         # every rank stages its own slab through its own PCIe link (serial per call: copy in, step, copy out)
         L = stepper.L
         own = tuple(L.owned(stepper.vorticity).shape)        # (nr, nz/P) columns or (nr/P, nz) rows
@@ -858,9 +870,9 @@ def run_gpu_arm(args, name, nr, nz):
         del hw, hc, ho
 
     extra = {}
-    if world > 1 and name == "c4":
+    if world > 1 and name in ("c4", "c2"):
         phases = stepper.phase_times() if hasattr(stepper, "phase_times") else None
-        err, what = slab_vs_single(world, rank, dist, torch)
+        err, what = slab_vs_single(world, rank, dist, torch, periodic=(name == "c2"))
         extra = {"slab_vs_single_rel_linf": err, "slab_vs_single_case": what, "phases_ms": phases}
 
     if hasattr(stepper, "close"):
@@ -871,7 +883,7 @@ def run_gpu_arm(args, name, nr, nz):
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(name, nr, nz)
         line = {"metric": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "higher_is_better": True, "scaling": "strong" if name == "c4" else "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "strong" if name in ("c4", "c2") else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic"}
         line.update(config_line(name, nr, nz, m, peak_holder, e2e, cpu))
         line.update(extra)

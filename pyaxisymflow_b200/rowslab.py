@@ -188,21 +188,43 @@ class RowSlabComm:
         return t
 
 
-class RowSlabFdSolver:
-    """Fast-diagonalisation solve with the rows split over the ranks: DCT-II of the owned rows, partitioned r solve,
-    DCT-III -- nothing but the 2P interface rows leaves the GPU.  ``dct`` is injectable for the CPU tests."""
+def _cuda_rfft(dst, src, tables, inverse):
+    """periodic z: real FFT rows (csrc/pfft.cu); dst / src are the half-complex spectral block and the inner columns"""
+    if inverse:
+        rows, n = dst.shape
+        _call("axb_irfft_rows", rows, n, ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(tables), 2.0 / n,
+              stream_ptr())
+    else:
+        rows, n = src.shape
+        _call("axb_rfft_rows", rows, n, ptr(src), src.stride(0), ptr(dst), dst.stride(0), dst.shape[1], ptr(tables), 1.0,
+              stream_ptr())
 
-    def __init__(self, layout, factors, part, dct=None):
+
+class RowSlabFdSolver:
+    """Fast-diagonalisation solve with the rows split over the ranks: z transform of the owned rows (DCT-II, or the
+    real FFT of the inner columns when z is periodic), partitioned r solve, inverse transform -- nothing but the 2P
+    interface rows leaves the GPU.  ``dct`` (the z transform, ``(dst, src, tables, inverse)``) is injectable for the
+    CPU tests."""
+
+    def __init__(self, layout, factors, part, dct=None, ghost=0):
         if factors.get("zfft") is None or factors.get("tri") is None:
-            raise _lib.AxbError("the r-slab solve needs the cosine-transform z path and the tridiagonal r path "
-                                "(power-of-two Nz); use pyaxisymflow_b200.slab.SlabRigidFlowStepper otherwise")
+            raise _lib.AxbError("the r-slab solve needs an FFT z path (cosine transforms: power-of-two Nz; periodic z: "
+                                "even inner width with small prime factors) and the tridiagonal r path; use "
+                                "pyaxisymflow_b200.slab.SlabRigidFlowStepper otherwise")
         self.L, self.f, self.part = layout, factors, part
-        self.dct = dct or _cuda_dct
-        self.spec = torch.empty((layout.nrl, layout.nz), dtype=torch.float64, device=factors["lam_z"].device)
+        self.periodic = factors["zfft"]["family"] == "periodic"
+        self.ghost = int(ghost) if self.periodic else 0
+        self.dct = dct or (_cuda_rfft if self.periodic else _cuda_dct)
+        width = factors["zfft"]["nz_spec"]
+        self.spec = torch.empty((layout.nrl, width), dtype=torch.float64, device=factors["lam_z"].device)
 
     def solve(self, psi_owned, rhs_owned, mark=None):
         tables = self.f["zfft"]["tables"]
         mark = mark or (lambda name: None)
+        g = self.ghost
+        if g:                                        # periodic z: the solve lives on the inner columns
+            nz = psi_owned.shape[1]
+            psi_owned, rhs_owned = psi_owned[:, g:nz - g], rhs_owned[:, g:nz - g]
         self.dct(self.spec, rhs_owned, tables, False)
         mark("solve_dct2")
         self.part(self.spec)
@@ -247,18 +269,32 @@ class CudaOps:
         _call("axb_diffusion_rk2_fused", self.g, ptr(w), ptr(w2), ptr(tmp), ptr(self.r1d), self.nu, 0.0, self.sp(1),
               stream_ptr())
 
+    # periodic z (periodic_flow_past_sphere.py:95-183): ghost columns are refreshed inside every row -- local to a rank
+    def ghost(self, f, ghost):
+        _call("axb_periodic_ghost_comm", self.g, ptr(f), int(ghost), 0.0, 0.0, stream_ptr())
+
+    def diffuse_stage1(self, tmp, w2):
+        _call("axb_diffusion_rk2_stage1", self.g, ptr(tmp), ptr(w2), ptr(self.r1d), self.nu, 0.0, self.sp(1), stream_ptr())
+
+    def diffuse_stage2(self, w, w2, tmp):
+        _call("axb_diffusion_rk2_stage2", self.g, ptr(w), ptr(w2), ptr(tmp), ptr(self.r1d), self.nu, 0.0, self.sp(1),
+              stream_ptr())
+
     def heaviside_sphere(self, chi, Z_cm, R_cm, r_sph):
         _call("axb_smooth_heaviside_sphere", self.g, ptr(chi), None, ptr(self.z1d), ptr(self.r1d), float(Z_cm),
               float(R_cm), float(r_sph), float(self.dx * 2 ** 0.5), stream_ptr())
 
 
 class RowSlabRigidFlowStepper:
-    """r-slab version of :class:`pyaxisymflow_b200.timestep.RigidFlowStepper` (non-periodic z; same physics, same
-    kernels, same launch order -- see the module docstring for the exchanges and why the halos are valid)."""
+    """r-slab version of :class:`pyaxisymflow_b200.timestep.RigidFlowStepper` (same physics, same kernels, same launch
+    order -- see the module docstring for the exchanges and why the halos are valid).  ``periodic=True`` is the loop of
+    ``periodic_flow_past_sphere.py:95-183`` (config C2): z is periodic with ``ghost_size`` ghost columns, which live
+    inside every row -- the wrap-around never leaves a rank, the real FFT of the inner columns is as local as the cosine
+    transforms, and the row halos travel exactly as in the non-periodic case."""
 
     def __init__(self, grid_size_z, grid_size_r=None, domain_AR=0.5, Re=100.0, U_0=1.0, r_sph=0.1, Z_cm=0.25,
                  R_cm=0.0, brink_lam=1e12, CFL=0.1, basis="analytic", group=None, device="cuda", ops=None,
-                 factors=None, dct=None, host_tridiagonal=False, use_graph=False):
+                 factors=None, dct=None, host_tridiagonal=False, use_graph=False, periodic=False, ghost_size=2):
         from .fd import build_factors
 
         cuda = device != "cpu"
@@ -273,6 +309,7 @@ class RowSlabRigidFlowStepper:
         self.dx = dx = 1.0 / self.nz
         self.L = L = RowSlabLayout(self.nr, self.nz, world, rank)
         self.comm = RowSlabComm(L, group)
+        self.periodic, self.ghost = bool(periodic), int(ghost_size)
         self.U_0, self.r_sph, self.brink_lam, self.CFL = U_0, r_sph, brink_lam, CFL
         self.Z_cm, self.R_cm = Z_cm, R_cm
         self.nu = U_0 * 2 * r_sph / Re
@@ -304,9 +341,18 @@ class RowSlabRigidFlowStepper:
         self.state = torch.zeros(8, dtype=torch.float64, device=device)
         self.ops = ops if ops is not None else CudaOps(L, dx, self.r1d, self.z1d, self.state, self.nu, brink_lam)
         self.ops.heaviside_sphere(L.block(self.char_func), Z_cm, R_cm, r_sph)       # analytic: halo rows included
-        self.factors = factors if factors is not None else build_factors(
-            "stokes", "homogenous_neumann_along_z_and_r", self.nr, self.nz, dx, basis, device=device,
-            r_method="tridiagonal", z_method="auto")
+        if self.periodic:
+            self.ops.ghost(L.block(self.char_func), self.ghost)
+            self.factors = factors if factors is not None else build_factors(
+                "stokes", "homogenous_neumann_along_r_and_periodic_along_z", self.nr, self.nz - 2 * self.ghost, dx, basis,
+                device=device, r_method="tridiagonal", z_method="fft")
+        else:
+            self.factors = factors if factors is not None else build_factors(
+                "stokes", "homogenous_neumann_along_z_and_r", self.nr, self.nz, dx, basis, device=device,
+                r_method="tridiagonal", z_method="auto")
+        # the r solve sees the spectral width (= Nz for the cosine transforms, the padded half-complex width when periodic)
+        zf = self.factors.get("zfft")
+        Ls = L if (zf is None or zf["nz_spec"] == self.nz) else RowSlabLayout(self.nr, zf["nz_spec"], world, rank)
         peer_buf = None
         if self.peer_halos:
             def peer_buf(shape):
@@ -314,13 +360,13 @@ class RowSlabRigidFlowStepper:
                 h, ptrs = self.comm.peer_info(t)
                 return t, h, ptrs
         flag_sync = getattr(self.comm, "flag_sync", False)
-        self.part = PartitionedTridiagonal(L, self.factors, group, peer_ptrs=peer_buf, host=host_tridiagonal,
+        self.part = PartitionedTridiagonal(Ls, self.factors, group, peer_ptrs=peer_buf, host=host_tridiagonal,
                                            sync=self.comm.sync if flag_sync else None)
         # a captured step needs every launch to be a plain kernel: the flag-based synchronisation, or one rank
         self._use_graph = bool(use_graph) and cuda and (world == 1 or flag_sync)
         self._graph, self._graphs3, self.graph_launches, self.launches_replayed = None, None, 0, 0
-        self.solver = RowSlabFdSolver(L, self.factors, self.part, dct=dct)
-        self._sc = (self.U_0, self.T_ramp, 0.0, self.dt_diff_limit, self.CFL * self.dx)
+        self.solver = RowSlabFdSolver(L, self.factors, self.part, dct=dct, ghost=self.ghost)
+        self._sc = (self.U_0, self.T_ramp, 5e-2 if self.periodic else 0.0, self.dt_diff_limit, self.CFL * self.dx)
 
     def seed_vorticity(self, seed=0, amplitude=1.0):
         """same global field as RigidFlowStepper.seed_vorticity, cut to this rank's rows"""
@@ -342,7 +388,8 @@ class RowSlabRigidFlowStepper:
         mark = mark or (lambda name: None)
         if 0 in phases:
             o.scalars(0, self._sc)
-            o.kill_z(B(w))
+            if not self.periodic:
+                o.kill_z(B(w))
             parts = (1 if L.upper is None else 0) | (2 if L.lower is None else 0)
             if parts:
                 o.kill_r(B(w), parts)
@@ -355,6 +402,9 @@ class RowSlabRigidFlowStepper:
             probe[1].record()
         if 2 not in phases:
             return
+        per, gh = self.periodic, self.ghost
+        if per:
+            o.ghost(B(psi), gh)                      # per row; the halo rows arrive from the neighbours with their ghosts
         self.comm.exchange([psi], 2)
         mark("halo_psi")
         o.velocity(B(self.u_z_upen), B(self.u_r_upen), B(psi))
@@ -362,15 +412,27 @@ class RowSlabRigidFlowStepper:
         self.comm.allreduce(self.state[2:3], "max")
         o.scalars(1, self._sc)
         mark("allreduce_cfl")
+        if per:
+            o.ghost(B(self.u_r_upen), gh)
+            o.ghost(B(self.u_z_upen), gh)
         o.penalise(B(self.u_z), B(self.u_r), B(w), B(self.u_z_upen), B(self.u_r_upen), B(self.char_func))
         mark("penalise")
         self.comm.exchange([w, self.u_r], 2)
         mark("halo_w_ur")
         o.advect(B(self._w2), B(w), B(self.u_z), B(self.u_r))
+        if per:
+            o.ghost(B(self._w2), gh)
         mark("advect")
         self.comm.exchange([self._w2], 2)
         mark("halo_w2")
-        o.diffuse(B(w), B(self._w2), B(self._tmp))
+        if per:
+            # two stages with a ghost refresh in between (RigidFlowStepper does the same); the intermediate field is valid
+            # on the block rows [1, n-2], which is what the owned rows of stage 2 read
+            o.diffuse_stage1(B(self._tmp), B(self._w2))
+            o.ghost(B(self._tmp), gh)
+            o.diffuse_stage2(B(w), B(self._w2), B(self._tmp))
+        else:
+            o.diffuse(B(w), B(self._w2), B(self._tmp))
         o.scalars(2, self._sc)
         mark("diffuse")
 

@@ -11,7 +11,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["rows", "rows-eager", "z"])
+@pytest.mark.parametrize("mode", ["rows", "rows-eager", "rows-periodic", "z"])
 def test_two_rank_slab_stepper_matches_one_gpu(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -196,3 +196,29 @@ def test_rowslab_stepper_world1_matches_rigid_stepper(T):
     assert abs(sa["t"] - sb["t"]) <= 1e-14 * sb["t"] and sa["iterations"] == sb["iterations"] == 4
     ph = a.phase_times(2)
     assert set(ph) >= {"solve_dct2", "solve_r_partitioned", "solve_dct3", "halo_psi", "advect", "diffuse"}
+
+
+def test_rowslab_stepper_world1_periodic_matches_rigid_stepper(T):
+    """periodic z (config C2's loop, periodic_flow_past_sphere.py:95-183) on the r-slab stepper: ghost columns live
+    inside every row, so the wrap-around is local to a rank; with one rank the stepper must reproduce
+    RigidFlowStepper(periodic=True) on the same solve path (real FFT of the inner columns + tridiagonal r)."""
+    from pyaxisymflow_b200.rowslab import RowSlabRigidFlowStepper
+    from pyaxisymflow_b200.timestep import RigidFlowStepper
+
+    torch = T
+    nz, nr = 512 + 4, 128
+    kw = dict(periodic=True, r_sph=0.075, Z_cm=0.85)
+    a = RowSlabRigidFlowStepper(nz, grid_size_r=nr, **kw)
+    b = RigidFlowStepper(nz, grid_size_r=nr, basis="analytic", r_method="tridiagonal", z_method="fft", **kw)
+    assert a.solver.periodic and b.solver.plan.z_fft == 2
+    a.seed_vorticity()
+    b.seed_vorticity()
+    assert torch.equal(a.gather_vorticity(), b.vorticity)
+    assert torch.equal(a.L.owned(a.char_func), b.char_func)
+    a.step(5)
+    b.step(5)
+    torch.cuda.synchronize()
+    err = ((a.gather_vorticity() - b.vorticity).abs().max() / b.vorticity.abs().max()).item()
+    assert err < 1e-10, err
+    sa, sb = a.scalars(), b.scalars()
+    assert abs(sa["t"] - sb["t"]) <= 1e-14 * sb["t"] and sa["iterations"] == sb["iterations"] == 5
