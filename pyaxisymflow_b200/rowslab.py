@@ -375,7 +375,8 @@ class RowSlabRigidFlowStepper:
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed)
         noise = torch.randn((self.nr, self.nz), dtype=torch.float64, device=dev, generator=gen)
-        rf = torch.linspace(self.dx / 2, self.nr * self.dx - self.dx / 2, self.nr, dtype=torch.float64, device=dev)
+        # the same radii as RigidFlowStepper's r1d (np.linspace; torch.linspace rounds differently when dx is no power of 2)
+        rf = torch.from_numpy(np.linspace(self.dx / 2, self.nr * self.dx - self.dx / 2, self.nr)).to(dev)
         env = torch.exp(-((self.z1d[None, :] - 0.5) ** 2 + rf[:, None] ** 2) / 0.02)
         self.vorticity.copy_(L.scatter_global(amplitude * noise * env))
 
