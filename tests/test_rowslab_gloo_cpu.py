@@ -37,6 +37,24 @@ def _host_dct(dst, src, tables, inverse):
     dst.copy_((src / ck) @ V.T if inverse else (src @ V) * ck)
 
 
+def _host_rfft(dst, src, tables, inverse):
+    """periodic z: the real FFT of a row block in the half-complex layout of csrc/pfft.cu (numpy.fft stands in)"""
+    if inverse:
+        n = dst.shape[1]
+        M = n // 2
+        spec = src.numpy()
+        Y = np.zeros((spec.shape[0], M + 1), complex)
+        Y.real, Y.imag[:, 1:M] = spec[:, :M + 1], spec[:, M + 1:n]
+        dst.copy_(torch.from_numpy(np.fft.irfft(Y, n=n, axis=1)))
+    else:
+        n = src.shape[1]
+        M = n // 2
+        X = np.fft.rfft(src.numpy(), axis=1)
+        out = np.zeros(tuple(dst.shape))
+        out[:, :M + 1], out[:, M + 1:n] = X.real, X.imag[:, 1:M]
+        dst.copy_(torch.from_numpy(out))
+
+
 class OracleOps:
     """one rigid-flow step's kernels on a (rows, nz) block, from the oracle (NumPy views of the torch storage)"""
 
@@ -105,9 +123,25 @@ class OracleOps:
         phi = r_sph - np.sqrt((self.Z - Z_cm) ** 2 + (self.R - R_cm) ** 2)
         self.o.smooth_Heaviside(chi.numpy(), phi, self.dx * 2 ** 0.5)
 
+    # periodic z: the ghost refresh and the two RK2 stages as separate calls (kernels/diffusion_RK2.py:48-89)
+    def ghost(self, f, ghost):
+        self.o.periodic_ghost_comm(f.numpy(), ghost)
 
-def _single_domain(nr, nz, steps, seed_field, kw):
+    def diffuse_stage1(self, tmp, w2):
+        a, t = w2.numpy(), tmp.numpy()
+        t[...] = a
+        t[1:-1, 1:-1] += 0.5 * self.nu * self.st[1].item() * self.o._diffusion_operator(a, self.R, self.dx)
+
+    def diffuse_stage2(self, w, w2, tmp):
+        a, out = w2.numpy(), w.numpy()
+        out[...] = a
+        out[1:-1, 1:-1] += self.nu * self.st[1].item() * self.o._diffusion_operator(tmp.numpy(), self.R, self.dx)
+
+
+def _single_domain(nr, nz, steps, seed_field, kw, periodic=False):
     """the same oracle sequence on the undivided field (what one GPU computes)"""
+    if periodic:
+        return _single_domain_periodic(nr, nz, steps, seed_field, kw)
     dx = 1.0 / nz
     st = torch.zeros(8, dtype=torch.float64)
     z1d = torch.from_numpy(np.linspace(dx / 2, 1 - dx / 2, nz))
@@ -134,7 +168,41 @@ def _single_domain(nr, nz, steps, seed_field, kw):
     return w, st
 
 
-def _worker(rank, world, port, nr, nz, steps, q):
+def _single_domain_periodic(nr, nz, steps, seed_field, kw, gh=2):
+    """RigidFlowStepper(periodic=True)'s sequence (periodic_flow_past_sphere.py:95-183) with the oracle's kernels"""
+    dx = 1.0 / nz
+    st = torch.zeros(8, dtype=torch.float64)
+    z1d = torch.from_numpy(np.linspace(dx / 2, 1 - dx / 2, nz))
+    r1d = torch.from_numpy(np.linspace(dx / 2, nr * dx - dx / 2, nr))
+    nu = kw["U_0"] * 2 * kw["r_sph"] / kw["Re"]
+    ops = OracleOps(dx, r1d, z1d, st, nu, kw["brink_lam"], 0, nr)
+    fac = fd.build_factors("stokes", "homogenous_neumann_along_r_and_periodic_along_z", nr, nz - 2 * gh, dx, "analytic",
+                           r_method="tridiagonal", z_method="fft")
+    f = lambda: torch.zeros((nr, nz), dtype=torch.float64)  # noqa: E731
+    w, psi, uz, ur, uzu, uru, chi, tmp, w2 = seed_field.clone(), f(), f(), f(), f(), f(), f(), f(), f()
+    ops.heaviside_sphere(chi, kw["Z_cm"], 0.0, kw["r_sph"])
+    ops.ghost(chi, gh)
+    sc = (kw["U_0"], 20 * kw["r_sph"] / kw["U_0"], 5e-2, 0.9 * dx ** 2 / 4 / nu, kw["CFL"] * dx)
+    for _ in range(steps):
+        ops.scalars(0, sc)
+        ops.kill_r(w, 3)
+        psi[:, gh:nz - gh] = torch.from_numpy(fd.apply_factors_host(fac, w[:, gh:nz - gh].numpy()))
+        ops.ghost(psi, gh)
+        ops.velocity(uzu, uru, psi)
+        ops.scalars(1, sc)
+        ops.ghost(uru, gh)
+        ops.ghost(uzu, gh)
+        ops.penalise(uz, ur, w, uzu, uru, chi)
+        ops.advect(w2, w, uz, ur)
+        ops.ghost(w2, gh)
+        ops.diffuse_stage1(tmp, w2)
+        ops.ghost(tmp, gh)
+        ops.diffuse_stage2(w, w2, tmp)
+        ops.scalars(2, sc)
+    return w, st
+
+
+def _worker(rank, world, port, nr, nz, steps, q, periodic=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -167,16 +235,21 @@ def _worker(rank, world, port, nr, nz, steps, q):
         r_blk = torch.from_numpy(r_full[L.g0:L.g0 + L.nv].copy())
         nu = kw["U_0"] * 2 * kw["r_sph"] / kw["Re"]
         ops = OracleOps(dx, r_blk, z1d, state, nu, kw["brink_lam"], L.ju0, L.ju1)
-        fac = fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx, "analytic",
-                               r_method="tridiagonal", z_method="fft")
-        s = RowSlabRigidFlowStepper(nz, grid_size_r=nr, device="cpu", ops=ops, factors=fac, dct=_host_dct,
-                                    host_tridiagonal=True, Z_cm=kw["Z_cm"], brink_lam=kw["brink_lam"])
+        if periodic:
+            fac = fd.build_factors("stokes", "homogenous_neumann_along_r_and_periodic_along_z", nr, nz - 4, dx, "analytic",
+                                   r_method="tridiagonal", z_method="fft")
+        else:
+            fac = fd.build_factors("stokes", "homogenous_neumann_along_z_and_r", nr, nz, dx, "analytic",
+                                   r_method="tridiagonal", z_method="fft")
+        s = RowSlabRigidFlowStepper(nz, grid_size_r=nr, device="cpu", ops=ops, factors=fac,
+                                    dct=_host_rfft if periodic else _host_dct, host_tridiagonal=True, Z_cm=kw["Z_cm"],
+                                    brink_lam=kw["brink_lam"], periodic=periodic)
         s.state = state
         zz, rr = np.meshgrid(z1d.numpy(), r_full)
         seed = torch.from_numpy(rng.standard_normal((nr, nz)) * np.exp(-((zz - 0.5) ** 2 + rr ** 2) / 0.02))
         s.vorticity.copy_(L.scatter_global(seed))
         s.step(steps)
-        ref_w, ref_st = _single_domain(nr, nz, steps, seed, kw)
+        ref_w, ref_st = _single_domain(nr, nz, steps, seed, kw, periodic)
         got = s.gather_vorticity()
         err = (got - ref_w).abs().max().item() / ref_w.abs().max().item()
         assert err < 1e-10, f"r-slab step differs from the undivided field by {err:.2e}"
@@ -192,12 +265,15 @@ def _worker(rank, world, port, nr, nz, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_rowslab_step_over_gloo(world):
+@pytest.mark.parametrize("world,periodic", [(2, False), (4, False), (2, True), (4, True)])
+def test_rowslab_step_over_gloo(world, periodic):
+    """periodic: config C2's loop -- ghost columns inside every row, real FFT of the inner 64 columns, two RK2 stages with
+    a ghost refresh in between; the wrap-around must never need a neighbour"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 32, 64, 4, q)) for r in range(world)]
+    nz = 64 + 4 if periodic else 64
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 32, nz, 4, q, periodic)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
