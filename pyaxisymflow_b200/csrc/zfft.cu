@@ -315,12 +315,17 @@ __device__ __forceinline__ void rr_mb_wait(unsigned bar, unsigned parity) {
 
 // Q[k] = exp(-i pi k / 2N), 0 <= k <= M/2, from the shared-memory copy of its first M/8 + 1 entries:
 // Q[M/2 - k] = exp(-i pi / 8) conj(Q[k]),  Q[M/4 - k] = exp(-i pi / 16) conj(Q[k])
+// PAD: the table is stored with one spare slot per 32 entries (entry t at t + (t >> 5)).  The DCT-III of the warp-local
+// kernel reads it at k = n1 + 32 a + 512 i, 32 entries = 512 bytes apart from lane to lane -- all 16 lanes of a half-warp
+// in the same banks (ncu: 32 wavefronts per LDS.128 instead of 4, 14.7 M of that kernel's 23 M conflicts); with the
+// spare slots the stride is 33 entries and a quarter-warp covers all banks.
+template <bool PAD = false>
 __device__ __forceinline__ double2 q_at(const double2* __restrict__ tq, int k, int M) {
   const bool r1 = k > (M >> 2);
   const int k1 = r1 ? (M >> 1) - k : k;
   const bool r2 = k1 > (M >> 3);
   const int k2 = r2 ? (M >> 2) - k1 : k1;
-  double2 q = tq[k2];
+  double2 q = tq[PAD ? k2 + (k2 >> 5) : k2];
   if (r2) q = cmul(make_double2(0.98078528040323044913, -0.19509032201612826785), make_double2(q.x, -q.y));
   if (r1) q = cmul(make_double2(0.92387953251128675613, -0.38268343236508977173), make_double2(q.x, -q.y));
   return q;
@@ -665,14 +670,14 @@ __global__ void __launch_bounds__(512, 1)
   double* XB = S + WN;                                                   // exchange buffer: WM doubles
   double2* Stab = reinterpret_cast<double2*>(XB + WM);                   // W_256^(d ka), 16 x 16
   double2* tq = Stab + 256;                                              // Q[0 .. M/8]
-  double2* T4 = tq + (WM >> 3) + 1;                                      // W_4096^d, d < 16; [16] = exp(-2 pi i / M)
+  double2* T4 = tq + (WM >> 3) + 1 + 33;                                 // W_4096^d, d < 16; [16] = exp(-2 pi i / M)
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(T4 + 17);
   const Tabs tb = split_tabs(tabs, WM);
   const int tid0 = threadIdx.x;
   const unsigned bar_a = rr_u32(bar);
   // ---- tables on chip
   for (int i = tid0; i < 256; i += 512) Stab[i] = tb.M[(32 * (i >> 4) * (i & 15)) & (WM - 1)];
-  for (int i = tid0; i <= (WM >> 3); i += 512) tq[i] = tb.Q[i];
+  for (int i = tid0; i <= (WM >> 3); i += 512) tq[i + (i >> 5)] = tb.Q[i];   // padded: q_at<true>
   if (tid0 < 16) T4[tid0] = tb.M[2 * tid0];
   if (tid0 == 16) T4[16] = tb.M[1];
 
@@ -760,7 +765,7 @@ __global__ void __launch_bounds__(512, 1)
                       make_double2(0.92387953251128675613, -0.38268343236508977173), zm, dummy);   // Z[M/2]: slot 8
             XP[0] = zm;
           } else {
-            dct3_pair(S[pk + 512 * i], S[pnk - 512 * i], S[pmk - 512 * i], S[ppk + 512 * i], q_at(tq, k, WM), v[i], zm);
+            dct3_pair(S[pk + 512 * i], S[pnk - 512 * i], S[pmk - 512 * i], S[ppk + 512 * i], q_at<true>(tq, k, WM), v[i], zm);
             XP[dst0 + 16 * (7 - i)] = zm;
           }
         }
@@ -900,7 +905,7 @@ __global__ void __launch_bounds__(512, 1)
         for (int i = 0; i < 4; ++i) {
           const int n = kres + 256 * (eb + i * es), n2 = WH - 1 - n;
           // exp(-2 pi i n / M) = Q[n]^8; exp(-2 pi i (M/2 - 1 - n) / M) = -conj(exp(-2 pi i (n + 1) / M))
-          const double2 q = q_at(tq, n, WM);
+          const double2 q = q_at<true>(tq, n, WM);
           const double2 qq = cmul(q, q);
           const double2 q4 = cmul(qq, qq);
           const double2 wn = cmul(q4, q4);
@@ -928,7 +933,7 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int k = kres + 256 * (eb + i * es);
-        const double2 q = q_at(tq, k, WM);
+        const double2 q = q_at<true>(tq, k, WM);
         const double2 qq = cmul(q, q);
         const double2 tn = cmul(qq, qq);                                 // exp(-2 pi i k / N)
         const double2 wk = cmul(tn, tn);                                 // exp(-2 pi i k / M)
@@ -994,7 +999,7 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
   static int w_off = -1;
   if (w_off < 0) w_off = getenv("AXB_DCT_RR") ? 1 : 0;                 // A/B switch: the register-resident kernel
   if (vec && !rr_off && !w_off && N == WN) {
-    const size_t wb_bytes = (size_t)(WN + WM) * sizeof(double) + (256 + (WM >> 3) + 1 + 17) * sizeof(double2) + 16;
+    const size_t wb_bytes = (size_t)(WN + WM) * sizeof(double) + (256 + (WM >> 3) + 1 + 33 + 17) * sizeof(double2) + 16;
     static bool w_once = false;
     if (!w_once) {
       cudaFuncSetAttribute(k_dct_rows_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
