@@ -526,6 +526,12 @@ int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const doub
  * interface system, all operator-only and prepared once (pyaxisymflow_b200/slab.py).  X, V, W: rows x nz. */
 int axb_tridiag_partition_correct(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
                                   const double* G, const double* CL, const double* CR, int n_iface, axb_stream_t s);
+/* The same with the decay of the spikes exploited: vcut_blk[b] / wcut_blk[b] (device, one entry per group of 256
+ * columns, (nz / 2 + 128) / 128 groups) = the first row from which |V| is negligible / the first row |W| reaches in that
+ * group; 32-row blocks in between are skipped (X is corrected in place).  NULL, NULL = correct everything. */
+int axb_tridiag_partition_correct_banded(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
+                                         const double* G, const double* CL, const double* CR, int n_iface,
+                                         const int32_t* vcut_blk, const int32_t* wcut_blk, axb_stream_t s);
 int axb_fd_solve(const axb_fd_plan_t* p, double* sol, int64_t ld_sol, const double* rhs, int64_t ld_rhs,
                  axb_stream_t s);
 /* Plain row-major FP64 GEMM C = A*B (+ optional spectral scaling), the building block above:

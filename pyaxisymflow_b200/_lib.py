@@ -128,6 +128,7 @@ _SIGNATURES = {
     "axb_tridiag_factor_columns": [_I, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _S],
     "axb_tridiag_solve_factored": [_I, _I, _P, c_int64, _P, _P, _S],
     "axb_tridiag_partition_correct": [_I, _I, _P, c_int64, _P, _P, _P, _P, _P, _I, _S],
+    "axb_tridiag_partition_correct_banded": [_I, _I, _P, c_int64, _P, _P, _P, _P, _P, _I, _P, _P, _S],
     "axb_tridiag_solve_columns": [_I, _I, _P, c_int64, _P, _P, _P, _P, _P, _D, _D, _P, _S],
     "axb_halo_pack": [_G, _P, _P, _P, _I, _S],
     "axb_halo_unpack": [_G, _P, _P, _P, _I, _D, _S],

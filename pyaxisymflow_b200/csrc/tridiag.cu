@@ -308,7 +308,16 @@ bool tri_map(CUtensorMap* m, const double* ptr, int nr, int nz, long long ld, in
 __global__ void __launch_bounds__(128)
     k_tri_partition_correct(int rows, int nz, double* __restrict__ X, long long ld, const double* __restrict__ V,
                             const double* __restrict__ W, const double* __restrict__ G, const double* __restrict__ CL,
-                            const double* __restrict__ CR, int n_iface, int rows_per_block) {
+                            const double* __restrict__ CR, int n_iface, int rows_per_block,
+                            const int* __restrict__ vcut_blk, const int* __restrict__ wcut_blk) {
+  // The spikes decay away from the interfaces (mode k of the Poisson-like operator like rho_k^m, rho_k < 1): for all
+  // but the lowest modes V is below 1e-20 of its maximum after a few dozen rows, W before the last few dozen.  vcut_blk /
+  // wcut_blk (optional) hold, per 256-column group, the first row from which V is negligible and the first row that W
+  // reaches; a block whose rows lie in between has nothing to correct and leaves (X is corrected in place).
+  if (vcut_blk) {
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    if (r0 >= vcut_blk[blockIdx.x] && r1 <= wcut_blk[blockIdx.x]) return;
+  }
   const int k = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (k >= nz) return;
   const bool two = k + 1 < nz;
@@ -396,14 +405,20 @@ int axb_tridiag_factor_columns(int nr, int nz, const double* sub, const double* 
   return (int)cudaGetLastError();
 }
 
-int axb_tridiag_partition_correct(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
-                                  const double* G, const double* CL, const double* CR, int n_iface, axb_stream_t s) {
+int axb_tridiag_partition_correct_banded(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
+                                         const double* G, const double* CL, const double* CR, int n_iface,
+                                         const int32_t* vcut_blk, const int32_t* wcut_blk, axb_stream_t s) {
   if (rows < 1 || nz < 1 || !X || !V || !W || !G || !CL || !CR || n_iface < 2 || ld < nz) return AXB_EINVAL;
+  if ((vcut_blk == nullptr) != (wcut_blk == nullptr)) return AXB_EINVAL;
   const int rpb = 32;
   k_tri_partition_correct<<<dim3((nz / 2 + 128) / 128, (rows + rpb - 1) / rpb), 128, 0, (cudaStream_t)s>>>(
-      rows, nz, X, ld, V, W, G, CL, CR, n_iface, rpb);
+      rows, nz, X, ld, V, W, G, CL, CR, n_iface, rpb, vcut_blk, wcut_blk);
   AXB_LAUNCHED();
   return (int)cudaGetLastError();
+}
+int axb_tridiag_partition_correct(int rows, int nz, double* X, int64_t ld, const double* V, const double* W,
+                                  const double* G, const double* CL, const double* CR, int n_iface, axb_stream_t s) {
+  return axb_tridiag_partition_correct_banded(rows, nz, X, ld, V, W, G, CL, CR, n_iface, nullptr, nullptr, s);
 }
 
 int axb_tridiag_solve_factored(int nr, int nz, double* X, int64_t ld, const double* inv_pivots, const double* row_coef,

@@ -304,6 +304,12 @@ class PartitionedTridiagonal:
         if L.rank < L.world - 1:
             self.W[-1] = c1 * float(sup[r1 - 1])
             self._local_solve(self.W, unit=True)
+        # where the spikes matter: V decays from the first row down, W from the last row up (mode k like rho_k^m), so for
+        # all but the lowest z modes the correction x = g - V xl - W xr touches a few dozen rows next to the interfaces.
+        # Per 256-column group of the correction kernel: rows [0, vcut) need V, rows [wcut, n) need W.
+        self.vcut = self.wcut = None
+        if not host and not os.environ.get("AXB_PARTITION_FULL"):
+            self.vcut, self.wcut = self._spike_cutoffs(self.V, self.W)
         # reduced interface system, inverted once on the host: unknowns (first, last) of every rank
         mine = torch.stack([self.V[0], self.V[-1], self.W[0], self.W[-1]]).contiguous()
         parts = [torch.empty_like(mine) for _ in range(L.world)]
@@ -335,6 +341,25 @@ class PartitionedTridiagonal:
             self.G_ptrs = (ctypes.c_uint64 * L.world)(*ptrs)
         else:
             self.G = torch.zeros((P2, L.nz), dtype=torch.float64, device=dev)
+
+    @staticmethod
+    def _spike_cutoffs(V, W, tol=1e-20, group=256):
+        """int32 device arrays, one entry per `group` columns: first row from which |V| <= tol max|V| in every column
+        of the group, first row in which |W| > tol max|W| in some column of the group"""
+        n, nz = V.shape
+        rows = torch.arange(n, device=V.device)[:, None]
+        mv = V.abs() > tol * max(float(V.abs().max()), 1e-300)
+        mw = W.abs() > tol * max(float(W.abs().max()), 1e-300)
+        vcol = torch.where(mv, rows + 1, torch.zeros_like(rows)).amax(0)          # rows [0, vcol) matter
+        wcol = torch.where(mw, rows, torch.full_like(rows, n)).amin(0)            # rows [wcol, n) matter
+        ng = (nz // 2 + 128) // 128                                               # the kernel's column groups
+        pad = ng * group - nz
+        if pad > 0:
+            vcol = torch.cat([vcol, vcol.new_zeros(pad)])
+            wcol = torch.cat([wcol, wcol.new_full((pad,), n)])
+        vcut = vcol[:ng * group].view(ng, group).amax(1).to(torch.int32).contiguous()
+        wcut = wcol[:ng * group].view(ng, group).amin(1).to(torch.int32).contiguous()
+        return vcut, wcut
 
     def _local_solve(self, x, unit=False):
         from . import fd
@@ -371,8 +396,9 @@ class PartitionedTridiagonal:
             xr = (self.CR * self.G).sum(0)
             x.copy_((x - self.V * xl) - self.W * xr)
             return
-        _call("axb_tridiag_partition_correct", n, nz, ptr(x), x.stride(0), ptr(self.V), ptr(self.W), ptr(self.G),
-              ptr(self.CL), ptr(self.CR), self.n_iface, stream_ptr())
+        _call("axb_tridiag_partition_correct_banded", n, nz, ptr(x), x.stride(0), ptr(self.V), ptr(self.W), ptr(self.G),
+              ptr(self.CL), ptr(self.CR), self.n_iface, ptr(self.vcut) if self.vcut is not None else None,
+              ptr(self.wcut) if self.wcut is not None else None, stream_ptr())
 
 
 class SlabFdSolver:
