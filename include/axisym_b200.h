@@ -73,6 +73,11 @@ int axb_set_stencil_path(int legacy_tiled);
 /* 1: row-marching kernels for G-SOL-1 / G-SOL-2 (axb_solid_sigma, axb_solid_tau) on grids with >= 258 columns;
  * 0 (default): the 2-D tiled kernels.  Bit-identical results; see DESIGN.md section 6.1. */
 int axb_set_solid_march(int on);
+/* factored tridiagonal sweeps (axb_tridiag_solve_factored and the solves built on it): 0 (default): the
+ * warp-specialised kernel -- three producer lanes feed the TMA ring (8 / 16 / 32 boxes by column count), a fourth warp
+ * runs the chain and stores the rows; 1 (or the environment variable AXB_TRI_ONE_WARP=1 at load): the single-warp TMA
+ * kernel.  Bit-identical results. */
+int axb_set_tridiag_sweep(int one_warp);
 
 /* ---- G-BND: kernels/kill_boundary_vorticity_sine.py:4-14 and :17-27 ------------------ */
 int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const double* z1d, int width,

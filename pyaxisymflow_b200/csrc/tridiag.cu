@@ -18,6 +18,8 @@
 
 #include "axb_common.cuh"
 
+extern int g_axb_tri_one_warp;   // capi.cu: axb_set_tridiag_sweep
+
 namespace {
 
 constexpr int TR = 8;    // rows per stage
@@ -270,6 +272,185 @@ __global__ void __launch_bounds__(32)
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 }
 
+// ---- warp-specialised TMA variant -------------------------------------------------------------
+// In k_tri_sweep_tma the only warp also issues the TMA loads, fences and stores of every box: ~100 cycles per
+// row of which the dependent chain is ~10 (an already-complete mbarrier try_wait costs ~90 cycles, the proxy fence
+// before a TMA store ~110, each tensor load issue an ELECT loop).  With <= 8192 columns there are fewer warps than SM
+// sub-partitions, so that instruction stream IS the duration (2048 rows x 52 ns = 0.107 ms whatever the width).
+// Here warp 0's elected lane is the producer (empty[] barriers -> expect_tx + 3 tensor loads per box) and warp 1
+// consumes: the try_wait on box i + 1 is issued before the chain of box i and confirmed after it, box i + 1 moves
+// from shared memory to a second register set while the rows of box i leave with plain 256-byte row stores (no
+// staging buffer, no proxy fence, no bulk-group wait).
+__device__ __forceinline__ unsigned mb_try(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mb_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+template <int DIR>
+struct SweepBox {
+  double r[TR], p[TR], co[TR], sc[TR];
+};
+
+// NS = boxes in the ring (8 / 16 / 32: 4.3 KB each).  With <= 8192 columns there are <= 256 CTAs and the bytes in
+// flight (CTAs x NS x 4.3 KB) bound the sweep before the chain does, so narrow problems get a deeper ring.
+// NP = producer warps.  Issuing a tensor load costs the issuing warp ~150 cycles (measured: with one producer lane for
+// the three loads of a box the sweep took ~500 cycles per box whatever the ring depth and the chain length), so with
+// NP = 3 three warps issue one load each -- X, pivots, row coefficients -- and the box's barrier collects their three
+// expect_tx arrivals.  128 threads at ~190 registers fit twice on an SM: NP = 3 serves the narrow problems (<= 2 CTAs
+// per SM), NP = 1 (64 threads, 5 CTAs per SM) the wide, HBM-bound ones.
+template <int DIR, int NS, int NP>
+__global__ void __launch_bounds__(32 * (NP + 1))
+    k_tri_sweep_ws(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP,
+                   const __grid_constant__ CUtensorMap tmC, int nr, int nz, double* __restrict__ X, long long ld) {
+  extern __shared__ __align__(128) double ws_smem[];
+  double* sx = ws_smem;
+  double* sp = sx + NS * W_STAGE;
+  double* sc4 = sp + NS * W_STAGE;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sc4 + NS * TR * 4);
+  unsigned long long* empty = full + NS;
+  const int lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * WC;
+  const int nb = (nr + TR - 1) / TR;
+  auto row0 = [&](int i) { return (DIR > 0) ? i * TR : (nb - 1 - i) * TR; };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      mb_init(s_u32(&full[i]), NP);                             // one arrival (+ bytes) per producer warp
+      mb_init(s_u32(&empty[i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  if (warp < NP) {                                              // producer warps: one lane each
+    if (lane == 0) {
+      if (NP == 3) {                                            // one tensor map per warp
+        const CUtensorMap* map = (warp == 0) ? &tmX : (warp == 1) ? &tmP : &tmC;
+        double* base = (warp == 0) ? sx : (warp == 1) ? sp : sc4;
+        const int per = (warp == 2) ? TR * 4 : W_STAGE;         // doubles per box of this array
+        const int c0 = (warp == 2) ? 0 : k0;
+        for (int i = 0; i < nb; ++i) {
+          const int st = i % NS;
+          if (i >= NS) mb_wait(s_u32(&empty[st]), ((i / NS) - 1) & 1);   // the consumer has taken use (i / NS) - 1
+          mb_expect(s_u32(&full[st]), (unsigned)per * 8u);
+          tma_ld(s_u32(base + st * per), map, c0, row0(i), s_u32(&full[st]));
+        }
+      } else {
+        for (int i = 0; i < nb; ++i) {
+          const int st = i % NS;
+          if (i >= NS) mb_wait(s_u32(&empty[st]), ((i / NS) - 1) & 1);
+          mb_expect(s_u32(&full[st]), STAGE_TX);
+          tma_ld(s_u32(sx + st * W_STAGE), &tmX, k0, row0(i), s_u32(&full[st]));
+          tma_ld(s_u32(sp + st * W_STAGE), &tmP, k0, row0(i), s_u32(&full[st]));
+          tma_ld(s_u32(sc4 + st * TR * 4), &tmC, 0, row0(i), s_u32(&full[st]));
+        }
+      }
+    }
+    return;
+  }
+  const bool col_ok = k0 + lane < nz;
+  auto fetch = [&](SweepBox<DIR>& b, int i) {                   // box i: shared memory -> registers
+    const int st = i % NS;
+#pragma unroll
+    for (int u = 0; u < TR; ++u) {
+      b.r[u] = sx[st * W_STAGE + u * WC + lane];
+      b.p[u] = sp[st * W_STAGE + u * WC + lane];
+      if (DIR > 0) {
+        const double2 c = *reinterpret_cast<const double2*>(sc4 + (st * TR + u) * 4);   // broadcast read
+        b.co[u] = c.x;
+        b.sc[u] = c.y;
+      } else {
+        b.co[u] = sc4[(st * TR + u) * 4 + 2];
+      }
+    }
+  };
+  double carry = 0.0, pprev = 0.0;
+  double out[TR];
+  auto chain = [&](const SweepBox<DIR>& b) {
+    if (DIR > 0) {
+#pragma unroll
+      for (int u = 0; u < TR; ++u) {
+        carry = b.r[u] * b.sc[u] - (b.co[u] * pprev) * carry;
+        pprev = b.p[u];
+        out[u] = carry;
+      }
+    } else {
+#pragma unroll
+      for (int u = TR - 1; u >= 0; --u) {
+        carry = (b.r[u] - b.co[u] * carry) * b.p[u];
+        out[u] = carry;
+      }
+    }
+  };
+  const bool cols_full = k0 + WC <= nz;                         // CTA-uniform
+  auto store = [&](int i) {
+    const int m0 = row0(i);
+    double* xo = X + (long long)m0 * ld + k0 + lane;
+    if (cols_full && m0 + TR <= nr) {                           // whole box inside: eight unpredicated row stores
+#pragma unroll
+      for (int u = 0; u < TR; ++u) xo[(long long)u * ld] = out[u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < TR; ++u)
+        if (col_ok && m0 + u < nr) xo[(long long)u * ld] = out[u];
+    }
+  };
+  // one iteration: (try box i + 1) -> chain of box i -> (confirm, fetch box i + 1 into `nxt`) -> store box i, release
+  auto step = [&](const SweepBox<DIR>& cur, SweepBox<DIR>& nxt, int i) {
+    const bool more = i + 1 < nb;
+    const unsigned nbar = s_u32(&full[(i + 1) % NS]);
+    const unsigned npar = ((i + 1) / NS) & 1;
+    unsigned ok = 1;
+    if (more) ok = mb_try(nbar, npar);
+    chain(cur);
+    if (more) {
+      if (!ok) mb_wait(nbar, npar);
+      fetch(nxt, i + 1);
+    }
+    store(i);
+    __syncwarp();                                               // every lane has box i in registers
+    if (lane == 0) mb_arrive(s_u32(&empty[i % NS]));
+  };
+  SweepBox<DIR> A, B;
+  mb_wait(s_u32(&full[0]), 0);
+  fetch(A, 0);
+  int i = 0;
+  for (; i + 1 < nb; i += 2) {
+    step(A, B, i);
+    step(B, A, i + 1);
+  }
+  if (i < nb) step(A, B, i);
+}
+
+template <int NS, int NP>
+static void launch_ws(int grid, const CUtensorMap& tmX, const CUtensorMap& tmP, const CUtensorMap& tmC, int nr, int nz,
+                      double* X, long long ld, cudaStream_t s) {
+  constexpr size_t smem = (size_t)(2 * NS * W_STAGE + NS * TR * 4 + 2 * NS) * sizeof(double);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(k_tri_sweep_ws<1, NS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tri_sweep_ws<-1, NS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  k_tri_sweep_ws<1, NS, NP><<<grid, 32 * (NP + 1), smem, s>>>(tmX, tmP, tmC, nr, nz, X, ld);
+  AXB_LAUNCHED();
+  k_tri_sweep_ws<-1, NS, NP><<<grid, 32 * (NP + 1), smem, s>>>(tmX, tmP, tmC, nr, nz, X, ld);
+  AXB_LAUNCHED();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -367,14 +548,37 @@ int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* i
     const char* e = getenv("AXB_TRI_COLS");     // 16 / 32 / 64 / 128: cp.async variants; unset: TMA
     force = e ? atoi(e) : 0;
   }
+  if (g_axb_tri_one_warp < 0) {
+    const char* e = getenv("AXB_TRI_ONE_WARP");   // 1: the single-warp TMA kernel (loads, chain and TMA stores in one warp)
+    g_axb_tri_one_warp = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  const int one_warp = g_axb_tri_one_warp;
   if (force == 0) {
     CUtensorMap tmX, tmP, tmC;
     if (tri_map(&tmX, X, nr, nz, ld) && tri_map(&tmP, inv, nr, nz, nz) && tri_map(&tmC, rc, nr, 4, 4, 4)) {
       const int grid = (nz + WC - 1) / WC;
-      k_tri_sweep_tma<1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
-      AXB_LAUNCHED();
-      k_tri_sweep_tma<-1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
-      AXB_LAUNCHED();
+      if (one_warp == 1) {
+        k_tri_sweep_tma<1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
+        AXB_LAUNCHED();
+        k_tri_sweep_tma<-1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
+        AXB_LAUNCHED();
+      } else {
+        // ring depth and producer warps by CTAs per SM (bytes in flight = CTAs x depth x 4.3 KB; the three-producer
+        // form fits twice on an SM); AXB_TRI_RING=8/16/32 forces a depth (8: one producer, else three)
+        static int ring = -1, sms = 0;
+        if (ring < 0) {
+          const char* e = getenv("AXB_TRI_RING");
+          ring = e ? atoi(e) : 0;
+          int dev = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        int ns = (grid <= sms) ? 32 : (grid <= 2 * sms) ? 16 : 8;
+        if (ring == 8 || ring == 16 || ring == 32) ns = ring;
+        if (ns == 32) launch_ws<32, 3>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
+        else if (ns == 16) launch_ws<16, 3>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
+        else launch_ws<8, 1>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
+      }
       return (int)cudaGetLastError();
     }
   }

@@ -1088,11 +1088,25 @@ int launch_dct_rows(int inverse, int rows, int N, const double* src, long long l
     AXB_LAUNCHED();
     return (int)cudaGetLastError();
   }
+  const int threads = rpc * T;
+  // persistent CTAs: exactly as many as are resident at once (the kernels take 128 registers, so the register file and
+  // not shared memory bounds the residency at N >= 2048; a grid sized by shared memory alone ran a second, half-empty
+  // wave); AXB_DCT_GRID_SMEM=1 restores the shared-memory estimate for an A/B
+  int occ = 0;
+  if (!inverse) {
+    if (vec) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dct2_rows<true>, threads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dct2_rows<false>, threads, smem);
+  } else {
+    if (vec) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dct3_rows<true>, threads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dct3_rows<false>, threads, smem);
+  }
+  static int by_smem = -1;
+  if (by_smem < 0) by_smem = getenv("AXB_DCT_GRID_SMEM") ? 1 : 0;
   const int per_sm = (int)((227u * 1024u) / (smem + 1024));
-  const int resident = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  int resident = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  if (!by_smem && occ >= 1 && occ < resident) resident = occ;
   const int nblocks = (rows + rpc - 1) / rpc;
   const int grid = nblocks < sms * resident ? nblocks : sms * resident;
-  const int threads = rpc * T;
   const double2* tb = reinterpret_cast<const double2*>(tabs);
   const int logM = ilog2(M);
   if (!inverse) {

@@ -785,6 +785,46 @@ def test_factored_tridiagonal_column_blocks(K, nr, nz):
     assert_close(tx.cpu().numpy(), want, 1e-12, f"factored sweeps {nr}x{nz}")
 
 
+@pytest.mark.parametrize("nr,nz,pad", [(8, 32, 0), (19, 96, 0), (133, 48, 4), (1000, 1040, 16), (2051, 4096, 0),
+                                       (300, 6144, 0), (200, 12288, 0)])
+def test_factored_tridiagonal_sweep_kernels_agree(K, nr, nz, pad):
+    """the warp-specialised sweep kernel (producer lane + chain warp, plain row stores) against the single-warp TMA
+    kernel: bit-identical, also with a last box that sticks out (nr % 8 != 0), a half-filled last column group
+    (nz % 32 == 16), a pitched right-hand side and many turns of the 32-, 16- and 8-box rings (chosen by column count)"""
+    import torch
+
+    from pyaxisymflow_b200 import _lib, fd
+    from pyaxisymflow_b200.device import ptr, stream_ptr
+
+    rng = np.random.default_rng(nr + nz)
+    dx = 1.0 / nz
+    sub, diag, sup, r = fd.radial_tridiagonal("stokes", "homogenous_neumann_along_z_and_r", nr, dx)
+    lam = fd.axial_natural_eigenvalues("neumann", 1.0, nz, dx)
+    lam[0] = lam[1]
+    x = rng.standard_normal((nr, nz))
+    dev = [torch.from_numpy(a).cuda() for a in (sub, diag, sup, lam, r)]
+    inv = torch.empty((nr, nz), dtype=torch.float64, device="cuda")
+    rc = torch.empty((nr, 4), dtype=torch.float64, device="cuda")
+    _lib.call("axb_tridiag_factor_columns", nr, nz, ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), ptr(dev[4]), 0.0,
+              1.0, ptr(inv), ptr(rc), stream_ptr())
+    got = {}
+    try:
+        for one_warp in (1, 0):
+            _lib.call("axb_set_tridiag_sweep", one_warp)
+            buf = torch.full((nr, nz + pad), 7.0, dtype=torch.float64, device="cuda")
+            buf[:, :nz] = torch.from_numpy(x).cuda()
+            _lib.call("axb_tridiag_solve_factored", nr, nz, ptr(buf), nz + pad, ptr(inv), ptr(rc), stream_ptr())
+            torch.cuda.synchronize()
+            got[one_warp] = buf.cpu().numpy()
+    finally:
+        _lib.call("axb_set_tridiag_sweep", 0)
+    assert np.array_equal(got[0], got[1])
+    assert np.all(got[0][:, nz:] == 7.0)                       # the pitch padding is untouched
+    if nr * nz <= 1100 * 1100:
+        want = fd.thomas_host(x, sub, diag, sup, lam, r, 0.0, 1.0)
+        assert_close(got[0][:, :nz], want, 1e-12, f"warp-specialised sweeps {nr}x{nz}")
+
+
 def test_rigid_flow_stepper_fft(K):
     from pyaxisymflow_b200.timestep import RigidFlowStepper
 
