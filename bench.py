@@ -399,7 +399,8 @@ class _ConfigRunner:
             # device) as one replayed CUDA graph; AXB_SOFT_HOST=1 keeps the host-driven loop
             dev = not reinit and not os.environ.get("AXB_SOFT_HOST")
             self.members = [SoftSphereStepper(nz, grid_size_r=nr, basis=basis, reinit_levelset=reinit,
-                                              Z_cm=0.47 if reinit else 0.5, device_scalars=dev, use_graph=dev)]
+                                              Z_cm=0.47 if reinit else 0.5, device_scalars=dev, use_graph=dev,
+                                              overlap_ls=not os.environ.get("AXB_SOFT_NO_OVERLAP"))]
         else:
             from pyaxisymflow_b200.timestep import ParticleEnsemble
 

@@ -74,7 +74,7 @@ int axb_set_stencil_path(int legacy_tiled);
  * 0 (default): the 2-D tiled kernels.  Bit-identical results; see DESIGN.md section 6.1. */
 int axb_set_solid_march(int on);
 /* factored tridiagonal sweeps (axb_tridiag_solve_factored and the solves built on it): 0 (default): the
- * warp-specialised kernel -- three producer lanes feed the TMA ring (8 / 16 / 32 boxes by column count), a fourth warp
+ * warp-specialised kernel -- a producer lane feeds the TMA ring (8 / 16 / 32 boxes by column count), a second warp
  * runs the chain and stores the rows; 1 (or the environment variable AXB_TRI_ONE_WARP=1 at load): the single-warp TMA
  * kernel.  Bit-identical results. */
 int axb_set_tridiag_sweep(int one_warp);
@@ -359,6 +359,14 @@ int axb_ls_extrapolate_eta_device(const axb_grid_t* g, const double* ball_phi, c
                                   const double* eta1_in, const double* eta2_in, double* eta1_out, double* eta2_out,
                                   double extrap_zone, const double* gx, const double* gy, void* work,
                                   int64_t work_bytes, int sweeps, int32_t* status_dev, axb_stream_t s);
+/* The device form in pieces, so that a driver can run independent work on a second stream while the (latency-bound,
+ * nearly empty) sweep launches run: parts = 1 fill of the doubled work arrays and the first pending list, 2 the sweeps,
+ * 4 the write-back into eta1_out / eta2_out; any sum of them in that order over one or more calls with the same
+ * arguments and workspace is the call above (elasto_kernels/extrapolate_eta_using_least_squares_unb.py:7-30). */
+int axb_ls_extrapolate_eta_device_parts(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                                        const double* eta1_in, const double* eta2_in, double* eta1_out, double* eta2_out,
+                                        double extrap_zone, const double* gx, const double* gy, void* work,
+                                        int64_t work_bytes, int sweeps, int32_t* status_dev, int parts, axb_stream_t s);
 
 /* ---- a21: core/src/particles_to_mesh.hpp:163-184 (periodic = 0) and the periodic twin
  *      particles_to_mesh_2D_mp4.  mesh is zeroed first, like the reference. ------------------ */

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "axb_ls_extrapolate_order2": [_I, _I, _P, _P, _P, _P, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_ls_extrapolate_eta": [_G, _P, _P, _P, _P, _D, _P, _P, _P, c_int64, _I, POINTER(c_int), _S],
     "axb_ls_extrapolate_eta_device": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, c_int64, _I, _P, _S],
+    "axb_ls_extrapolate_eta_device_parts": [_G, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, c_int64, _I, _P, _I, _S],
     "axb_p2m_mp4_2d": [_I, _I, _P, _P, _P, _P, _D, _D, _I, _S],
     "axb_rfft_rows": [_I, _I, _P, c_int64, _P, c_int64, _I, _P, _D, _S],
     "axb_irfft_rows": [_I, _I, _P, c_int64, _P, c_int64, _P, _D, _S],

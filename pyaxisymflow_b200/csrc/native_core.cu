@@ -604,7 +604,7 @@ int axb_ls_extrapolate_order2(int n0, int n1, int16_t* cur, const int16_t* tgt, 
 static int ls_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid, const double* eta1_in,
                   const double* eta2_in, double* eta1, double* eta2, double extrap_zone, const double* gx,
                   const double* gy, void* work, int64_t work_bytes, int max_sweeps, int* sweeps_host, int* status_dev,
-                  bool device_loop, axb_stream_t s) {
+                  bool device_loop, axb_stream_t s, int parts = 7) {
   if (!ball_phi || !inside_solid || !eta1 || !eta2 || !eta1_in || !eta2_in || !gx || !gy || !work) return AXB_EINVAL;
   int rc = axb_check_grid(g);
   if (rc) return rc;
@@ -624,14 +624,18 @@ static int ls_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* in
   const long long rest_bytes = work_bytes - (rest - p);
   dim3 grd((nz + 127) / 128, nr);
   if (device_loop) {
+    // parts (device loop only): 1 = fill of the doubled work arrays + first pending list, 2 = the sweeps, 4 = write-back
     const LsDevWork w = carve_device(rest, rest_bytes);
     if (w.cap < 2) return AXB_EWORK;
-    cudaMemsetAsync(w.ctr, 0, 256, s);
-    k_ls_fill<true><<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt, e1,
-                                        e2, w.pend[0], w.ctr + 4, w.cap);
-    AXB_LAUNCHED();
-    rc = ls_run_device(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, status_dev, true,
-                       (cudaStream_t)s);
+    if (parts & 1) {
+      cudaMemsetAsync(w.ctr, 0, 256, s);
+      k_ls_fill<true><<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt,
+                                          e1, e2, w.pend[0], w.ctr + 4, w.cap);
+      AXB_LAUNCHED();
+    }
+    if (parts & 2)
+      rc = ls_run_device(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, status_dev, true,
+                         (cudaStream_t)s);
   } else {
     k_ls_fill<false><<<grd, 128, 0, s>>>(nr, nz, g->ld, ball_phi, inside_solid, eta1_in, eta2_in, extrap_zone, cur, tgt, e1,
                                          e2, nullptr, nullptr, 0);
@@ -639,8 +643,10 @@ static int ls_eta(const axb_grid_t* g, const double* ball_phi, const uint8_t* in
     rc = ls_run(1, 2 * nr, nz, cur, tgt, e1, e2, gx, gy, rest, rest_bytes, max_sweeps, sweeps_host, (cudaStream_t)s);
   }
   if (rc) return rc;
-  k_ls_unfill<<<grd, 128, 0, s>>>(nr, nz, g->ld, eta1, eta2, e1, e2);
-  AXB_LAUNCHED();
+  if (parts & 4) {
+    k_ls_unfill<<<grd, 128, 0, s>>>(nr, nz, g->ld, eta1, eta2, e1, e2);
+    AXB_LAUNCHED();
+  }
   AXB_RETURN_LAST();
 }
 
@@ -657,6 +663,14 @@ int axb_ls_extrapolate_eta_device(const axb_grid_t* g, const double* ball_phi, c
                                   int64_t work_bytes, int sweeps, int32_t* status_dev, axb_stream_t s) {
   return ls_eta(g, ball_phi, inside_solid, eta1_in, eta2_in, eta1_out, eta2_out, extrap_zone, gx, gy, work, work_bytes,
                 sweeps, nullptr, status_dev, true, s);
+}
+int axb_ls_extrapolate_eta_device_parts(const axb_grid_t* g, const double* ball_phi, const uint8_t* inside_solid,
+                                        const double* eta1_in, const double* eta2_in, double* eta1_out, double* eta2_out,
+                                        double extrap_zone, const double* gx, const double* gy, void* work,
+                                        int64_t work_bytes, int sweeps, int32_t* status_dev, int parts, axb_stream_t s) {
+  if (parts < 1 || parts > 7) return AXB_EINVAL;
+  return ls_eta(g, ball_phi, inside_solid, eta1_in, eta2_in, eta1_out, eta2_out, extrap_zone, gx, gy, work, work_bytes,
+                sweeps, nullptr, status_dev, true, s, parts);
 }
 
 int axb_p2m_mp4_2d(int n0, int n1, const double* px, const double* py, const double* val, double* mesh,

@@ -305,13 +305,11 @@ struct SweepBox {
 
 // NS = boxes in the ring (8 / 16 / 32: 4.3 KB each).  With <= 8192 columns there are <= 256 CTAs and the bytes in
 // flight (CTAs x NS x 4.3 KB) bound the sweep before the chain does, so narrow problems get a deeper ring.
-// NP = producer warps.  Issuing a tensor load costs the issuing warp ~150 cycles (measured: with one producer lane for
-// the three loads of a box the sweep took ~500 cycles per box whatever the ring depth and the chain length), so with
-// NP = 3 three warps issue one load each -- X, pivots, row coefficients -- and the box's barrier collects their three
-// expect_tx arrivals.  128 threads at ~190 registers fit twice on an SM: NP = 3 serves the narrow problems (<= 2 CTAs
-// per SM), NP = 1 (64 threads, 5 CTAs per SM) the wide, HBM-bound ones.
-template <int DIR, int NS, int NP>
-__global__ void __launch_bounds__(32 * (NP + 1))
+// (Measured at 1024 x 4096, ncu: the consumer warp issues ~170 instructions per box at one instruction per ~3 cycles --
+// fixed-latency dependency waits of a single in-order warp -- so neither a deeper ring, nor a shorter chain (one FMA per
+// row), nor three producer warps issuing one tensor load each changed the ~500 cycles per box.)
+template <int DIR, int NS>
+__global__ void __launch_bounds__(64)
     k_tri_sweep_ws(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP,
                    const __grid_constant__ CUtensorMap tmC, int nr, int nz, double* __restrict__ X, long long ld) {
   extern __shared__ __align__(128) double ws_smem[];
@@ -327,36 +325,22 @@ __global__ void __launch_bounds__(32 * (NP + 1))
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      mb_init(s_u32(&full[i]), NP);                             // one arrival (+ bytes) per producer warp
+      mb_init(s_u32(&full[i]), 1);
       mb_init(s_u32(&empty[i]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  if (warp < NP) {                                              // producer warps: one lane each
+  if (threadIdx.x < 32) {                                       // producer warp: one lane
     if (lane == 0) {
-      if (NP == 3) {                                            // one tensor map per warp
-        const CUtensorMap* map = (warp == 0) ? &tmX : (warp == 1) ? &tmP : &tmC;
-        double* base = (warp == 0) ? sx : (warp == 1) ? sp : sc4;
-        const int per = (warp == 2) ? TR * 4 : W_STAGE;         // doubles per box of this array
-        const int c0 = (warp == 2) ? 0 : k0;
-        for (int i = 0; i < nb; ++i) {
-          const int st = i % NS;
-          if (i >= NS) mb_wait(s_u32(&empty[st]), ((i / NS) - 1) & 1);   // the consumer has taken use (i / NS) - 1
-          mb_expect(s_u32(&full[st]), (unsigned)per * 8u);
-          tma_ld(s_u32(base + st * per), map, c0, row0(i), s_u32(&full[st]));
-        }
-      } else {
-        for (int i = 0; i < nb; ++i) {
-          const int st = i % NS;
-          if (i >= NS) mb_wait(s_u32(&empty[st]), ((i / NS) - 1) & 1);
-          mb_expect(s_u32(&full[st]), STAGE_TX);
-          tma_ld(s_u32(sx + st * W_STAGE), &tmX, k0, row0(i), s_u32(&full[st]));
-          tma_ld(s_u32(sp + st * W_STAGE), &tmP, k0, row0(i), s_u32(&full[st]));
-          tma_ld(s_u32(sc4 + st * TR * 4), &tmC, 0, row0(i), s_u32(&full[st]));
-        }
+      for (int i = 0; i < nb; ++i) {
+        const int st = i % NS;
+        if (i >= NS) mb_wait(s_u32(&empty[st]), ((i / NS) - 1) & 1);   // the consumer has taken use (i / NS) - 1
+        mb_expect(s_u32(&full[st]), STAGE_TX);
+        tma_ld(s_u32(sx + st * W_STAGE), &tmX, k0, row0(i), s_u32(&full[st]));
+        tma_ld(s_u32(sp + st * W_STAGE), &tmP, k0, row0(i), s_u32(&full[st]));
+        tma_ld(s_u32(sc4 + st * TR * 4), &tmC, 0, row0(i), s_u32(&full[st]));
       }
     }
     return;
@@ -435,19 +419,19 @@ __global__ void __launch_bounds__(32 * (NP + 1))
   if (i < nb) step(A, B, i);
 }
 
-template <int NS, int NP>
+template <int NS>
 static void launch_ws(int grid, const CUtensorMap& tmX, const CUtensorMap& tmP, const CUtensorMap& tmC, int nr, int nz,
                       double* X, long long ld, cudaStream_t s) {
   constexpr size_t smem = (size_t)(2 * NS * W_STAGE + NS * TR * 4 + 2 * NS) * sizeof(double);
   static bool once = false;
   if (!once) {
-    cudaFuncSetAttribute(k_tri_sweep_ws<1, NS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_tri_sweep_ws<-1, NS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tri_sweep_ws<1, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tri_sweep_ws<-1, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     once = true;
   }
-  k_tri_sweep_ws<1, NS, NP><<<grid, 32 * (NP + 1), smem, s>>>(tmX, tmP, tmC, nr, nz, X, ld);
+  k_tri_sweep_ws<1, NS><<<grid, 64, smem, s>>>(tmX, tmP, tmC, nr, nz, X, ld);
   AXB_LAUNCHED();
-  k_tri_sweep_ws<-1, NS, NP><<<grid, 32 * (NP + 1), smem, s>>>(tmX, tmP, tmC, nr, nz, X, ld);
+  k_tri_sweep_ws<-1, NS><<<grid, 64, smem, s>>>(tmX, tmP, tmC, nr, nz, X, ld);
   AXB_LAUNCHED();
 }
 
@@ -563,8 +547,8 @@ int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* i
         k_tri_sweep_tma<-1><<<grid, 32, 0, s>>>(tmX, tmP, tmC, nr);
         AXB_LAUNCHED();
       } else {
-        // ring depth and producer warps by CTAs per SM (bytes in flight = CTAs x depth x 4.3 KB; the three-producer
-        // form fits twice on an SM); AXB_TRI_RING=8/16/32 forces a depth (8: one producer, else three)
+        // ring depth by CTAs per SM (bytes in flight = CTAs x depth x 4.3 KB; 5 / 3 / 1 CTAs of 35 / 70 / 139 KB fit on an
+        // SM); AXB_TRI_RING=8/16/32 forces a depth
         static int ring = -1, sms = 0;
         if (ring < 0) {
           const char* e = getenv("AXB_TRI_RING");
@@ -575,9 +559,9 @@ int launch_tri_factored(int nr, int nz, double* X, long long ld, const double* i
         }
         int ns = (grid <= sms) ? 32 : (grid <= 2 * sms) ? 16 : 8;
         if (ring == 8 || ring == 16 || ring == 32) ns = ring;
-        if (ns == 32) launch_ws<32, 3>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
-        else if (ns == 16) launch_ws<16, 3>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
-        else launch_ws<8, 1>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
+        if (ns == 32) launch_ws<32>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
+        else if (ns == 16) launch_ws<16>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
+        else launch_ws<8>(grid, tmX, tmP, tmC, nr, nz, X, ld, s);
       }
       return (int)cudaGetLastError();
     }

@@ -343,7 +343,8 @@ class SoftSphereStepper:
 
     def __init__(self, grid_size_z=256, domain_AR=0.5, grid_size_r=None, r_ball=0.15, freq=16.0, nond_AC=0.125,
                  e=0.1, Cauchy=0.1, zeta=0.25, brink_lam=1e8, CFL=0.1, rho_f=1.0, Z_cm=0.5, R_cm=0.0, basis="auto",
-                 reinit_levelset=False, device_scalars=False, use_graph=False, ls_sweeps=12, fused_solid=True):
+                 reinit_levelset=False, device_scalars=False, use_graph=False, ls_sweeps=12, fused_solid=True,
+                 overlap_ls=True):
         if not torch.cuda.is_available():
             raise _lib.AxbError("SoftSphereStepper needs a CUDA device (no CPU fallback)")
         if device_scalars and reinit_levelset:
@@ -399,6 +400,10 @@ class SoftSphereStepper:
         # the LS extrapolation with device-terminated sweeps, the whole step one replayed CUDA graph
         self.device_scalars = bool(device_scalars)
         self.fused_solid = bool(fused_solid)          # device mode: one pass for the elastic stress (else 3 calls)
+        # device mode: the LS sweeps (36 nearly empty launches, ~0.2 ms at 2048 x 8192) run on a high-priority side
+        # stream while the vorticity advection and the tether Heaviside, which do not depend on them, use the GPU
+        self.overlap_ls = bool(overlap_ls)
+        self._ls_stream = None
         self._use_graph, self._graph = bool(use_graph) and self.device_scalars, None
         self.graph_launches, self.launches_replayed = 0, 0
         if self.device_scalars:
@@ -453,12 +458,36 @@ class SoftSphereStepper:
               ptr(self.u_r_upen), 0.0, sp(1), s)
         _call("axb_pin_level_set", g, ptr(self.ball_phi), None, ptr(e1b), ptr(e2b), self.Z_cm, self.R_cm, self.r_ball,
               -3 * dx, s)
-        _call("axb_advect_vorticity_eno3", g, ptr(w2), ptr(w), ptr(self.u_z_upen), ptr(self.u_r_upen), 0.0, sp(1), s)
-        _call("axb_smooth_heaviside_mask", g, ptr(self.ball_char_func), ptr(self.inside_solid), ptr(self.ball_phi),
-              self.moll_zone, 0.5, 0, s)
-        _call("axb_ls_extrapolate_eta_device", g, ptr(self.ball_phi), ptr(self.inside_solid), ptr(e1b), ptr(e2b),
-              ptr(self.eta1), ptr(self.eta2), self.extrap_zone, ptr(self.z1d), ptr(self.gy), ptr(self._ls_work),
-              self._ls_bytes, self._ls_sweeps, ptr(self._ls_status), s)
+
+        def ls(parts, stream):
+            _call("axb_ls_extrapolate_eta_device_parts", g, ptr(self.ball_phi), ptr(self.inside_solid), ptr(e1b), ptr(e2b),
+                  ptr(self.eta1), ptr(self.eta2), self.extrap_zone, ptr(self.z1d), ptr(self.gy), ptr(self._ls_work),
+                  self._ls_bytes, self._ls_sweeps, ptr(self._ls_status), parts, stream)
+
+        def tether():
+            _call("axb_smooth_heaviside_sphere_dev", g, ptr(self.tether_char_func), None, ptr(self.z1d), ptr(self.r1d),
+                  sp(6), self.R_cm, self.fixed_rad, self.moll_zone, s)
+
+        if self.overlap_ls:
+            _call("axb_smooth_heaviside_mask", g, ptr(self.ball_char_func), ptr(self.inside_solid), ptr(self.ball_phi),
+                  self.moll_zone, 0.5, 0, s)
+            ls(1, s)
+            # fork: the sweeps on the side stream, the independent HBM-bound passes on this one (same data flow as below)
+            if self._ls_stream is None:
+                self._ls_stream = torch.cuda.Stream(priority=-1)
+            cur, side = torch.cuda.current_stream(), self._ls_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ls(2, stream_ptr())
+            _call("axb_advect_vorticity_eno3", g, ptr(w2), ptr(w), ptr(self.u_z_upen), ptr(self.u_r_upen), 0.0, sp(1), s)
+            tether()
+            cur.wait_stream(side)
+            ls(4, s)
+        else:
+            _call("axb_advect_vorticity_eno3", g, ptr(w2), ptr(w), ptr(self.u_z_upen), ptr(self.u_r_upen), 0.0, sp(1), s)
+            _call("axb_smooth_heaviside_mask", g, ptr(self.ball_char_func), ptr(self.inside_solid), ptr(self.ball_phi),
+                  self.moll_zone, 0.5, 0, s)
+            ls(7, s)
         if self.fused_solid:
             # sigma -> tau -> curl in one shared-memory pass (the driver never looks at the seven intermediates)
             _call("axb_solid_stress_vorticity_update", g, ptr(w2), ptr(self.eta1), ptr(self.eta2),
@@ -469,8 +498,8 @@ class SoftSphereStepper:
             _call("axb_solid_tau", g, ptr(self.tau_z), ptr(self.tau_r), ptr(self.s11), ptr(self.s12), ptr(self.s22),
                   ptr(self.r1d), s)
             _call("axb_solid_vorticity_update", g, ptr(w2), ptr(self.tau_z), ptr(self.tau_r), 0.0, sp(1), s)
-        _call("axb_smooth_heaviside_sphere_dev", g, ptr(self.tether_char_func), None, ptr(self.z1d), ptr(self.r1d), sp(6),
-              self.R_cm, self.fixed_rad, self.moll_zone, s)
+        if not self.overlap_ls:
+            tether()
         _call("axb_penalise_update_vorticity", g, ptr(self.u_z), ptr(self.u_r), ptr(w2), ptr(self.u_z_upen),
               ptr(self.u_r_upen), ptr(self.tether_char_func), self.brink_lam, 0.0, sp(1), 0.0, 0.0, sp(4), ptr(self.r1d),
               None, s)

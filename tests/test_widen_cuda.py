@@ -746,6 +746,13 @@ def test_soft_sphere_stepper_device_scalars_match_host_loop(K, graph, nz):
     for f in ("eta1", "eta2", "ball_phi", "vorticity", "psi", "avg_psi", "avg_phi", "ball_char_func", "tether_char_func",
               "u_z", "u_r"):
         assert_close(getattr(d, f).cpu().numpy(), getattr(h, f).cpu().numpy(), 1e-11, f)
+    # the LS sweeps forked onto a side stream (default) against the single-stream launch order: same kernels, same data
+    one = SoftSphereStepper(nz, Z_cm=0.47, device_scalars=True, use_graph=graph, overlap_ls=False)
+    assert d.overlap_ls and not one.overlap_ls
+    one.step(steps)
+    one.sync_scalars()
+    for f in ("eta1", "eta2", "ball_phi", "vorticity", "psi", "tether_char_func", "u_z", "u_r"):
+        assert torch.equal(getattr(d, f), getattr(one, f)), f
     # cycle wrap on the device: the step that completes the cycle is clamped to its end, the next one restarts the
     # averages and keeps the completed ones
     d.state[3] = d.freqTimer_limit - 0.25 * d.dt
