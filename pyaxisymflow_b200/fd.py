@@ -688,14 +688,17 @@ class FastDiagonalisationStokesSolver(_FdBase):
 
     def kernel_note(self):
         if self.factors.get("zfft") is not None and self.factors["zfft"]["family"] == "periodic":
-            return ("fast-diagonalisation solve = k_rfft_rows + k_tri_sweep<fwd> + k_tri_sweep<bwd> + k_irfft_rows "
+            return ("fast-diagonalisation solve = k_rfft_rows + k_tri_sweep_ws<fwd> + k_tri_sweep_ws<bwd> + k_irfft_rows "
                     "(4 launches: shared-memory mixed-radix real FFTs along periodic z, radices "
                     f"{rfft_factors(self.grid_size_z // 2)}, factored tridiagonal sweeps along r; 80 algorithmic "
                     "B/grid-pt)")
         if self.factors.get("zfft") is not None:
-            return ("fast-diagonalisation solve = k_dct2_rows + k_tri_sweep<fwd> + k_tri_sweep<bwd> + k_dct3_rows "
-                    "(4 launches: shared-memory FFT cosine transforms along z, factored tridiagonal sweeps along r; "
-                    "80 algorithmic B/grid-pt)")
+            nz = self.grid_size_z
+            dct = ("k_dct_rows_w<II> + {} + k_dct_rows_w<III>" if nz == 16384 else
+                   "k_dct_rows_rr<II> + {} + k_dct_rows_rr<III>" if nz in (64, 1024) else "k_dct2_rows + {} + k_dct3_rows")
+            return ("fast-diagonalisation solve = " + dct.format("k_tri_sweep_ws<fwd> + k_tri_sweep_ws<bwd>") +
+                    " (4 launches: on-chip FFT cosine transforms along z, factored tridiagonal sweeps along r through a "
+                    "TMA ring; 80 algorithmic B/grid-pt)")
         zs = self.factors.get("zsplit")
         tri = self.factors.get("tri") is not None
         rpart = "batched tridiagonal r solve" if tri else "2 r-transforms"

@@ -11,7 +11,7 @@ tail -2 gpurun_out/${T}_bench_1gpu.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference_arm.json 2> gpurun_out/${T}_bench_reference_arm.err
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/${T}_launches_c4.csv python tools/profile_step.py 16384 3 > gpurun_out/${T}_launches_c4.log 2>&1
 python tools/launch_summary.py gpurun_out/${T}_launches_c4.csv 40 2>&1 | grep -v "at::" | head -40 > gpurun_out/${T}_kernel_summary_c4.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_dct_rows_w|k_tri_sweep_tma" -c 8 -o gpurun_out/${T}_ncu_full_solve_c4 -f python tools/profile_step.py 16384 2 > gpurun_out/${T}_ncu_full_solve_c4.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_dct_rows_w|k_tri_sweep_ws|k_tri_sweep_tma" -c 8 -o gpurun_out/${T}_ncu_full_solve_c4 -f python tools/profile_step.py 16384 2 > gpurun_out/${T}_ncu_full_solve_c4.log 2>&1
 python tools/ncu_summary.py gpurun_out/${T}_ncu_full_solve_c4.ncu-rep > gpurun_out/${T}_ncu_full_solve_c4_summary.csv 2>/dev/null
 python - <<PY
 import json
@@ -22,3 +22,9 @@ for k, c in (d.get("configs") or {}).items():
 PY
 cut -c1-400 gpurun_out/${T}_bench_reference_arm.json
 cat gpurun_out/${T}_kernel_summary_c4.txt
+# launch lists of the other configurations' steps (eager launches of the device-resident steppers)
+for c in c2 c3d c5b; do
+  timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/${T}_launches_$c.csv python tools/profile_config.py $c 3 > gpurun_out/${T}_launches_$c.log 2>&1
+  python tools/launch_summary.py gpurun_out/${T}_launches_$c.csv 40 2>&1 | grep -v "at::" | head -36 > gpurun_out/${T}_kernel_summary_$c.txt
+done
+head -24 gpurun_out/${T}_kernel_summary_c3d.txt
