@@ -14,6 +14,7 @@
 // j is re-used as the back face of row j+1.  Compiled with -fmad=false like stencils.cu.
 #include <math_constants.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <initializer_list>
 
@@ -51,9 +52,9 @@ struct Cols {
 };
 // Threads whose pair lies beyond the stored row stay alive (the kernels use full-mask warp shuffles):
 // they are parked on column 0 with every ownership flag false, so they load valid memory and never store.
-__device__ __forceinline__ Cols make_cols(const GridD& g) {
+__device__ __forceinline__ Cols make_cols(const GridD& g, int bx) {
   Cols c;
-  c.k = 2 * (blockIdx.x * MT + threadIdx.x);
+  c.k = 2 * (bx * MT + threadIdx.x);
   c.valid = c.k < g.nz;
   c.ks = c.valid ? c.k : (g.nz + 2);
   if (!c.valid) c.k = 0;
@@ -69,10 +70,66 @@ __device__ __forceinline__ Cols make_cols(const GridD& g) {
 // least `hz` columns away from the global z ends, rows [j0, j1) are a full chunk at least `hr` rows
 // away from both r ends, and 128-bit accesses are legal.  The fast and the general code evaluate the
 // same floating-point expressions, so a cell gets the same bits whichever path computes it.
-__device__ __forceinline__ bool block_interior(const GridD& g, int j0, int j1, int RB, int hr, int hz, bool vec) {
-  const int kb0 = 2 * blockIdx.x * MT, kb1 = kb0 + 2 * MT;
-  return vec && (j1 - j0 == RB) && (j0 >= hr) && (j1 + hr <= g.nr) && (kb0 >= g.ku0) && (kb1 <= g.ku1) &&
-         (kb0 + g.kz0 >= hz) && (kb1 - 1 + g.kz0 <= g.nzg - 1 - hz) && (kb0 - hz >= 0) && (kb1 - 1 + hz < g.nz);
+// (Separable in the column block and the row chunk; the launchers evaluate the same two predicates on the host to
+// enumerate the edge blocks.)
+__host__ __device__ inline bool cols_interior(const GridD& g, int bx, int hz) {
+  const int kb0 = 2 * bx * MT, kb1 = kb0 + 2 * MT;
+  return (kb0 >= g.ku0) && (kb1 <= g.ku1) && (kb0 + g.kz0 >= hz) && (kb1 - 1 + g.kz0 <= g.nzg - 1 - hz) && (kb0 - hz >= 0) &&
+         (kb1 - 1 + hz < g.nz);
+}
+__host__ __device__ inline bool rows_interior(const GridD& g, int p0, int p1, int RB, int hr, bool owned_window) {
+  return (p1 - p0 == RB) && (p0 >= hr) && (p1 + hr <= g.nr) && (!owned_window || (p0 >= g.ju0 && p1 <= g.ju1));
+}
+// Compact enumeration of the edge blocks of one launch (built by edge_map() on the host): the non-interior column blocks
+// over all fine row chunks, then the remaining column blocks over the fine chunks whose parent chunk is not
+// row-interior.  on = 0: plain 2-D grid (x = column block, y = fine chunk).
+struct EdgeMap {
+  int on, total, nfy;
+  int n_bc, bc[4];
+  int n_rr, r0[4], r1[4], rows_r;
+  int n_col_part;
+};
+// Row chunk of this block.  Interior kernels (PATH 1) walk chunks of RB rows.  The edge kernels (PATH 2) walk FINE chunks
+// of RE rows (RE divides RB) and take the interior test from the parent RB-chunk: an edge block is latency bound
+// (a row's loads are consumed before the next row's are issued, few blocks per SM), so its duration is its row count --
+// 32-row edge blocks took 50-100 us whatever the grid, as long as the interior kernel of a small grid or of one rank's
+// row slab.  Returns false when the block belongs to the other kernel of the pair.
+template <int PATH>
+__device__ __forceinline__ bool row_chunk(const GridD& g, int RB, int RE, const EdgeMap& em, int hr, int hz, bool vec,
+                                          bool owned_window, int& bx, int& j0, int& j1) {
+  int p0, p1;
+  if (PATH == 1) {
+    bx = blockIdx.x;
+    j0 = blockIdx.y * RB; j1 = min(j0 + RB, g.nr);
+    p0 = j0; p1 = j1;
+  } else {
+    int fy;
+    if (!em.on) {
+      bx = blockIdx.x; fy = blockIdx.y;
+    } else {
+      int e = blockIdx.x;
+      if (e >= em.total) return false;
+      if (e < em.n_col_part) {
+        bx = em.bc[e / em.nfy]; fy = e % em.nfy;
+      } else {
+        e -= em.n_col_part;
+        bx = e / em.rows_r;
+        int ri = e % em.rows_r;
+        for (int i = 0; i < em.n_bc; ++i)
+          if (em.bc[i] <= bx) ++bx;
+        fy = 0;
+        for (int i = 0; i < em.n_rr; ++i) {
+          const int len = em.r1[i] - em.r0[i];
+          if (ri < len) { fy = em.r0[i] + ri; break; }
+          ri -= len;
+        }
+      }
+    }
+    j0 = fy * RE; j1 = min(j0 + RE, g.nr);
+    p0 = (j0 / RB) * RB; p1 = min(p0 + RB, g.nr);
+  }
+  const bool interior = vec && rows_interior(g, p0, p1, RB, hr, owned_window) && cols_interior(g, bx, hz);
+  return (PATH == 1) == interior;
 }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
@@ -86,17 +143,16 @@ constexpr int UR = 4;   // rows per unrolled step of the fast paths (RB is a mul
 // is the hot one), blocks that belong to the other kernel leave at once.
 template <bool REDUCE, int PATH>
 __global__ void __launch_bounds__(MT)
-    km_velocity(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ psi,
+    km_velocity(GridD g, int RB, int RE, EdgeMap em, double* __restrict__ u_z, double* __restrict__ u_r, const double* __restrict__ psi,
                 const double* __restrict__ r1d, double uz_add, double ur_add, const double* __restrict__ add_dev,
                 double* umax_out, bool vec) {
   extern __shared__ double s_inv[];
-  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
+  int bx, j0, j1;
   // a block that straddles the owned-row window [ju0, ju1) reduces row by row on the general path
-  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec) && (!REDUCE || (j0 >= g.ju0 && j1 <= g.ju1));
-  if ((PATH == 1) != interior) return;
+  if (!row_chunk<PATH>(g, RB, RE, em, 1, 1, vec, REDUCE, bx, j0, j1)) return;
   for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
   __syncthreads();
-  const Cols c = make_cols(g);
+  const Cols c = make_cols(g, bx);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local_max = 0.0;
   {
@@ -239,16 +295,15 @@ __device__ __forceinline__ double pen_defect(double cc, double uu, double lamdt,
 
 template <bool REDUCE, int PATH>
 __global__ void __launch_bounds__(MT)
-    km_penalise(GridD g, int RB, double* __restrict__ u_z, double* __restrict__ u_r, double* __restrict__ w,
+    km_penalise(GridD g, int RB, int RE, EdgeMap em, double* __restrict__ u_z, double* __restrict__ u_r, double* __restrict__ w,
                 const double* __restrict__ uzu, const double* __restrict__ uru, const double* __restrict__ chi,
                 double lam, double dt, const double* __restrict__ dt_dev, double U_z, double U_r,
                 const double* __restrict__ U_dev, const double* __restrict__ r1d, double* sum_out, bool vec) {
-  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
-  const Cols c = make_cols(g);
+  int bx, j0, j1;
+  if (!row_chunk<PATH>(g, RB, RE, em, 1, 1, vec, REDUCE, bx, j0, j1)) return;
+  const Cols c = make_cols(g, bx);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   double local = 0.0;
-  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec) && (!REDUCE || (j0 >= g.ju0 && j1 <= g.ju1));
-  if ((PATH == 1) != interior) return;
   {
     const long long fo = member_field(g);
     u_z += fo; u_r += fo; w += fo; uzu += fo; uru += fo; chi += fo;
@@ -357,16 +412,15 @@ __global__ void __launch_bounds__(MT)
 // -------------------------------------------------------------------------------------
 template <int STAGE, int PATH>
 __global__ void __launch_bounds__(MT)
-    km_diffusion(GridD g, int RB, double* out, const double* __restrict__ in, const double* src2,
+    km_diffusion(GridD g, int RB, int RE, EdgeMap em, double* out, const double* __restrict__ in, const double* src2,
                  const double* __restrict__ r1d, double nu, const double* __restrict__ nu_dev, double dt,
                  const double* __restrict__ dt_dev, bool vec) {
   extern __shared__ double s_inv[];
-  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
-  const bool interior = block_interior(g, j0, j1, RB, 1, 1, vec);
-  if ((PATH == 1) != interior) return;
+  int bx, j0, j1;
+  if (!row_chunk<PATH>(g, RB, RE, em, 1, 1, vec, false, bx, j0, j1)) return;
   for (int i = threadIdx.x; i < j1 - j0; i += MT) s_inv[i] = 1.0 / r1d[j0 + i];
   __syncthreads();
-  const Cols c = make_cols(g);
+  const Cols c = make_cols(g, bx);
   const int lane = threadIdx.x & 31, nz = g.nz, k = c.k;
   {
     const long long fo = member_field(g);
@@ -460,18 +514,17 @@ __device__ __forceinline__ double dif_cell(double base, double c, double up, dou
 
 template <int PATH>
 __global__ void __launch_bounds__(MT)
-    km_diffusion_fused(GridD g, int RB, double* __restrict__ out, const double* __restrict__ in,
+    km_diffusion_fused(GridD g, int RB, int RE, EdgeMap em, double* __restrict__ out, const double* __restrict__ in,
                        const double* __restrict__ r1d, double nu, double dt, const double* __restrict__ dt_dev, bool vec) {
   extern __shared__ double s_inv[];          // 1 / r for rows j0 - 1 .. j1
-  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
-  const bool interior = block_interior(g, j0, j1, RB, 2, 2, vec);
-  if ((PATH == 1) != interior) return;
+  int bx, j0, j1;
+  if (!row_chunk<PATH>(g, RB, RE, em, 2, 2, vec, false, bx, j0, j1)) return;
   for (int i = threadIdx.x; i < j1 - j0 + 2; i += MT) {
     const int j = j0 - 1 + i;
     s_inv[i] = (j >= 0 && j < g.nr) ? 1.0 / r1d[j] : 0.0;
   }
   __syncthreads();
-  const Cols c = make_cols(g);
+  const Cols c = make_cols(g, bx);
   const int lane = threadIdx.x & 31, k = c.k;
   if (dt_dev) dt = *dt_dev;
   DifK K;
@@ -612,14 +665,13 @@ __device__ __forceinline__ double2 ld_row_m(const double* f, long long ld, int j
 // with u_r when CONS), centre values w0 = f[j], w1 = f[j+1], w2 = f[j+2]; per-thread rolling back face.
 template <int NF, bool CONS, bool MIRROR, bool FLUXONLY, int PATH>
 __global__ void __launch_bounds__(MT)
-    km_eno3(GridD g, int RB, double* __restrict__ out0, double* __restrict__ out1, const double* __restrict__ in0,
+    km_eno3(GridD g, int RB, int RE, EdgeMap em, double* __restrict__ out0, double* __restrict__ out1, const double* __restrict__ in0,
             const double* __restrict__ in1, const double* __restrict__ u_z, const double* __restrict__ u_r,
             double inv_dx, double dt, const double* __restrict__ dt_dev, double sign0, double sign1, bool vec) {
   const int j_lo = MIRROR ? 0 : 2, j_hi = g.nr - 3;   // rows that are advected
-  const int j0 = blockIdx.y * RB, j1 = min(j0 + RB, g.nr);
-  const bool interior = block_interior(g, j0, j1, RB, 2, 2, vec);
-  if ((PATH == 1) != interior) return;
-  const Cols c = make_cols(g);
+  int bx, j0, j1;
+  if (!row_chunk<PATH>(g, RB, RE, em, 2, 2, vec, false, bx, j0, j1)) return;
+  const Cols c = make_cols(g, bx);
   const int nz = g.nz, k = c.k;
   if (!c.own0 && !c.own1) return;   // no shuffles in this kernel: idle threads may leave
   if (dt_dev) dt = *dt_dev;
@@ -815,6 +867,52 @@ inline int pick_rb(const GridD& d) {
 inline dim3 march_grid(const GridD& d, int rb) {
   return dim3(((d.nz + 1) / 2 + MT - 1) / MT, (d.nr + rb - 1) / rb, d.batch);
 }
+// Edge blocks of a launch, enumerated with the predicates the kernels use (a block the host lists but the device finds
+// interior returns at once and is done by the interior kernel; the reverse cannot happen).  Falls back to the plain 2-D
+// grid -- every block launched, the interior ones leave -- when 128-bit accesses are off (then every block is an edge
+// block), when more than four column blocks or row ranges are irregular, or with AXB_EDGE_FULL_GRID=1.
+inline EdgeMap edge_map(const GridD& d, int rb, int re, int hr, int hz, bool vec, bool owned_window, dim3& grid) {
+  EdgeMap m;
+  memset(&m, 0, sizeof(m));
+  const int nbx = ((d.nz + 1) / 2 + MT - 1) / MT, nby = (d.nr + rb - 1) / rb;
+  m.nfy = (d.nr + re - 1) / re;
+  grid = dim3(nbx, m.nfy, d.batch);
+  static const bool off = getenv("AXB_EDGE_FULL_GRID") != nullptr;
+  if (off || !vec) return m;
+  for (int bx = 0; bx < nbx; ++bx) {
+    if (cols_interior(d, bx, hz)) continue;
+    if (m.n_bc == 4) return m;
+    m.bc[m.n_bc++] = bx;
+  }
+  const int per = rb / re;
+  for (int by = 0; by < nby; ++by) {
+    const int p0 = by * rb, p1 = (p0 + rb < d.nr) ? p0 + rb : d.nr;
+    if (rows_interior(d, p0, p1, rb, hr, owned_window)) continue;
+    const int f0 = by * per, f1 = (f0 + per < m.nfy) ? f0 + per : m.nfy;
+    if (m.n_rr && m.r1[m.n_rr - 1] == f0) { m.r1[m.n_rr - 1] = f1; continue; }
+    if (m.n_rr == 4) { m.n_bc = 0; m.n_rr = 0; return m; }
+    m.r0[m.n_rr] = f0; m.r1[m.n_rr] = f1; ++m.n_rr;
+  }
+  for (int i = 0; i < m.n_rr; ++i) m.rows_r += m.r1[i] - m.r0[i];
+  m.n_col_part = m.n_bc * m.nfy;
+  m.total = m.n_col_part + (nbx - m.n_bc) * m.rows_r;
+  m.on = 1;
+  grid = dim3(m.total > 0 ? m.total : 1, 1, d.batch);
+  return m;
+}
+// rows per block of the edge kernels (see row_chunk): 8, and 4 on grids so small that the interior chunk is already 8 rows
+// (measured, compact edge grid: 516 x 16384 -- one rank's slab of the 8-GPU run -- 0.466 / 0.447 / 0.450 ms per step with
+// 32 / 8 / 4 rows, 128 x 256 0.089 / 0.089 / 0.073, 4096 x 16384 2.851 / 2.849 / 2.856); AXB_EDGE_RB=4/8/16/32 forces one
+inline int pick_re(int rb) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("AXB_EDGE_RB");
+    forced = e ? atoi(e) : 0;
+    if (forced != 4 && forced != 8 && forced != 16 && forced != 32) forced = 0;
+  }
+  const int re = forced ? forced : (rb <= 8 ? 4 : 8);
+  return re < rb ? re : rb;
+}
 
 // The edge kernel of a pair (few blocks, latency bound: 40-90 us at 4096 x 16384) runs on a side stream
 // forked from and joined back into the caller's stream, so it hides behind the interior kernel.  The two
@@ -864,8 +962,11 @@ int march_velocity(const GridD& d, double* u_z, double* u_r, const double* psi, 
   const int rb = pick_rb(d);
   EdgeFork* ef;
   cudaStream_t se = edge_begin(s, ef);
-#define VEL(R, P, ST) km_velocity<R, P><<<march_grid(d, rb), MT, rb * sizeof(double), ST>>>(d, rb, u_z, u_r, psi, r1d, uz_add, \
-                                                                                      ur_add, add_dev, umax_out, vec)
+  const int re = pick_re(rb);
+  dim3 ge;
+  const EdgeMap em = edge_map(d, rb, re, 1, 1, vec, umax_out != nullptr, ge);
+#define VEL(R, P, ST) km_velocity<R, P><<<P == 2 ? ge : march_grid(d, rb), MT, rb * sizeof(double), ST>>>(                \
+    d, rb, re, em, u_z, u_r, psi, r1d, uz_add, ur_add, add_dev, umax_out, vec)
   if (umax_out) { VEL(true, 2, se); VEL(true, 1, s); }
   else { VEL(false, 2, se); VEL(false, 1, s); }
 #undef VEL
@@ -879,8 +980,11 @@ int march_penalise(const GridD& d, double* u_z, double* u_r, double* w, const do
   const int rb = pick_rb(d);
   EdgeFork* ef;
   cudaStream_t se = edge_begin(s, ef);
-#define PEN(R, P, ST) km_penalise<R, P><<<march_grid(d, rb), MT, 0, ST>>>(d, rb, u_z, u_r, w, uzu, uru, chi, lam, dt, dt_dev, U_z, \
-                                                                    U_r, U_dev, r1d, sum_out, vec)
+  const int re = pick_re(rb);
+  dim3 ge;
+  const EdgeMap em = edge_map(d, rb, re, 1, 1, vec, sum_out != nullptr, ge);
+#define PEN(R, P, ST) km_penalise<R, P><<<P == 2 ? ge : march_grid(d, rb), MT, 0, ST>>>(d, rb, re, em, u_z, u_r, w, uzu, uru, chi, \
+                                                                                  lam, dt, dt_dev, U_z, U_r, U_dev, r1d, sum_out, vec)
   if (sum_out) { PEN(true, 2, se); PEN(true, 1, s); }
   else { PEN(false, 2, se); PEN(false, 1, s); }
 #undef PEN
@@ -893,8 +997,11 @@ int march_diffusion(int stage, const GridD& d, double* out, const double* in, co
   const int rb = pick_rb(d);
   EdgeFork* ef;
   cudaStream_t se = edge_begin(s, ef);
-#define DIF(S, P, ST) km_diffusion<S, P><<<march_grid(d, rb), MT, rb * sizeof(double), ST>>>(d, rb, out, in, src2, r1d, nu, nu_dev, \
-                                                                                       dt, dt_dev, vec)
+  const int re = pick_re(rb);
+  dim3 ge;
+  const EdgeMap em = edge_map(d, rb, re, 1, 1, vec, false, ge);
+#define DIF(S, P, ST) km_diffusion<S, P><<<P == 2 ? ge : march_grid(d, rb), MT, rb * sizeof(double), ST>>>(                \
+    d, rb, re, em, out, in, src2, r1d, nu, nu_dev, dt, dt_dev, vec)
   if (stage == 1) { DIF(1, 2, se); DIF(1, 1, s); }
   else { DIF(2, 2, se); DIF(2, 1, s); }
 #undef DIF
@@ -907,8 +1014,11 @@ int march_diffusion_fused(const GridD& d, double* out, const double* in, const d
   const int rb = pick_rb(d);
   EdgeFork* ef;
   cudaStream_t se = edge_begin(s, ef);
-  km_diffusion_fused<2><<<march_grid(d, rb), MT, (rb + 2) * sizeof(double), se>>>(d, rb, out, in, r1d, nu, dt, dt_dev, vec);
-  km_diffusion_fused<1><<<march_grid(d, rb), MT, (rb + 2) * sizeof(double), s>>>(d, rb, out, in, r1d, nu, dt, dt_dev, vec);
+  const int re = pick_re(rb);
+  dim3 ge;
+  const EdgeMap em = edge_map(d, rb, re, 2, 2, vec, false, ge);
+  km_diffusion_fused<2><<<ge, MT, (rb + 2) * sizeof(double), se>>>(d, rb, re, em, out, in, r1d, nu, dt, dt_dev, vec);
+  km_diffusion_fused<1><<<march_grid(d, rb), MT, (rb + 2) * sizeof(double), s>>>(d, rb, re, em, out, in, r1d, nu, dt, dt_dev, vec);
   edge_end(s, ef);
   return (int)cudaGetLastError();
 }
@@ -917,15 +1027,18 @@ int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, do
                const double* in0, const double* in1, const double* u_z, const double* u_r, double inv_dx, double dt,
                const double* dt_dev, double sign0, double sign1, bool vec, cudaStream_t s) {
   const int rb = pick_rb(d);
+  const int re = pick_re(rb);
   const dim3 grd = march_grid(d, rb);
+  dim3 grde;
+  const EdgeMap em = edge_map(d, rb, re, 2, 2, vec, false, grde);
   EdgeFork* ef;
   cudaStream_t se = edge_begin(s, ef);
-#define LAUNCH(NF, C, M, F)                                                                                               \
-  do {                                                                                                                   \
-    km_eno3<NF, C, M, F, 2><<<grd, MT, 0, se>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1, \
-                                                vec);                                                                    \
-    km_eno3<NF, C, M, F, 1><<<grd, MT, 0, s>>>(d, rb, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0, sign1,  \
-                                               vec);                                                                     \
+#define LAUNCH(NF, C, M, F)                                                                                                  \
+  do {                                                                                                                      \
+    km_eno3<NF, C, M, F, 2><<<grde, MT, 0, se>>>(d, rb, re, em, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0,  \
+                                                 sign1, vec);                                                               \
+    km_eno3<NF, C, M, F, 1><<<grd, MT, 0, s>>>(d, rb, re, em, out0, out1, in0, in1, u_z, u_r, inv_dx, dt, dt_dev, sign0,    \
+                                               sign1, vec);                                                                 \
   } while (0)
   if (nf == 1 && cons && mirror && !fluxonly) LAUNCH(1, true, true, false);
   else if (nf == 2 && !cons && mirror && !fluxonly) LAUNCH(2, false, true, false);
