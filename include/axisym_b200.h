@@ -78,6 +78,12 @@ int axb_set_solid_march(int on);
  * runs the chain and stores the rows; 1 (or the environment variable AXB_TRI_ONE_WARP=1 at load): the single-warp TMA
  * kernel.  Bit-identical results. */
 int axb_set_tridiag_sweep(int one_warp);
+/* Test hook, no kernel launch (runs without a GPU): the blocks the EDGE kernel of a row-marching stencil pass
+ * (G-VEL / G-PEN / G-ADV / G-REF / G-DIF; halo hr rows, hz columns) is launched on for grid g -- (column block of 256
+ * columns, fine row chunk) pairs -- and info = {rows per interior chunk, rows per edge chunk, 1 if the compact edge grid
+ * is used, launched blocks}.  The interior blocks of the same decomposition belong to the interior kernel. */
+int axb_debug_edge_blocks(const axb_grid_t* g, int hr, int hz, int vec, int owned_window, int32_t* pairs, int cap,
+                          int32_t* info);
 
 /* ---- G-BND: kernels/kill_boundary_vorticity_sine.py:4-14 and :17-27 ------------------ */
 int axb_kill_boundary_vorticity_sine_z(const axb_grid_t* g, double* w, const double* z1d, int width,

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "axb_set_stencil_path": [_I],
     "axb_set_solid_march": [_I],
     "axb_set_tridiag_sweep": [_I],
+    "axb_debug_edge_blocks": [_G, _I, _I, _I, _I, _P, _I, _P],
     "axb_kill_boundary_vorticity_sine_z": [_G, _P, _P, _I, _S],
     "axb_kill_boundary_vorticity_sine_r": [_G, _P, _P, _I, _S],
     "axb_kill_boundary_vorticity_sine_r_parts": [_G, _P, _P, _I, _I, _S],

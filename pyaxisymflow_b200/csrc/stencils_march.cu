@@ -94,6 +94,25 @@ struct EdgeMap {
 // (a row's loads are consumed before the next row's are issued, few blocks per SM), so its duration is its row count --
 // 32-row edge blocks took 50-100 us whatever the grid, as long as the interior kernel of a small grid or of one rank's
 // row slab.  Returns false when the block belongs to the other kernel of the pair.
+// launched block (ex, ey) of an edge kernel -> column block bx, fine row chunk fy; false: nothing to do
+__host__ __device__ inline bool edge_decode(const EdgeMap& em, int ex, int ey, int& bx, int& fy) {
+  if (!em.on) { bx = ex; fy = ey; return true; }
+  int e = ex;
+  if (e >= em.total) return false;
+  if (e < em.n_col_part) { bx = em.bc[e / em.nfy]; fy = e % em.nfy; return true; }
+  e -= em.n_col_part;
+  bx = e / em.rows_r;
+  int ri = e % em.rows_r;
+  for (int i = 0; i < em.n_bc; ++i)
+    if (em.bc[i] <= bx) ++bx;
+  fy = 0;
+  for (int i = 0; i < em.n_rr; ++i) {
+    const int len = em.r1[i] - em.r0[i];
+    if (ri < len) { fy = em.r0[i] + ri; break; }
+    ri -= len;
+  }
+  return true;
+}
 template <int PATH>
 __device__ __forceinline__ bool row_chunk(const GridD& g, int RB, int RE, const EdgeMap& em, int hr, int hz, bool vec,
                                           bool owned_window, int& bx, int& j0, int& j1) {
@@ -104,27 +123,7 @@ __device__ __forceinline__ bool row_chunk(const GridD& g, int RB, int RE, const 
     p0 = j0; p1 = j1;
   } else {
     int fy;
-    if (!em.on) {
-      bx = blockIdx.x; fy = blockIdx.y;
-    } else {
-      int e = blockIdx.x;
-      if (e >= em.total) return false;
-      if (e < em.n_col_part) {
-        bx = em.bc[e / em.nfy]; fy = e % em.nfy;
-      } else {
-        e -= em.n_col_part;
-        bx = e / em.rows_r;
-        int ri = e % em.rows_r;
-        for (int i = 0; i < em.n_bc; ++i)
-          if (em.bc[i] <= bx) ++bx;
-        fy = 0;
-        for (int i = 0; i < em.n_rr; ++i) {
-          const int len = em.r1[i] - em.r0[i];
-          if (ri < len) { fy = em.r0[i] + ri; break; }
-          ri -= len;
-        }
-      }
-    }
+    if (!edge_decode(em, (int)blockIdx.x, (int)blockIdx.y, bx, fy)) return false;
     j0 = fy * RE; j1 = min(j0 + RE, g.nr);
     p0 = (j0 / RB) * RB; p1 = min(p0 + RB, g.nr);
   }
@@ -1050,4 +1049,27 @@ int march_eno3(int nf, bool cons, bool mirror, bool fluxonly, const GridD& d, do
 #undef LAUNCH
   edge_end(s, ef);
   return (int)cudaGetLastError();
+}
+
+// Test hook (no kernel launch, runs without a GPU): the edge blocks one launch of a row-marching pass would start on
+// grid `g` -- (column block, fine row chunk) pairs in launch order -- with info = {rows per interior chunk, rows per
+// edge chunk, compact grid on / off, launched blocks}.  tests/test_abi_cpu.py checks them against the definition.
+extern "C" int axb_debug_edge_blocks(const axb_grid_t* g, int hr, int hz, int vec, int owned_window, int32_t* pairs,
+                                     int cap, int32_t* info) {
+  if (!g || !pairs || !info || cap < 0 || hr < 1 || hz < 1) return AXB_EINVAL;
+  const GridD d = to_dev(g);
+  if (d.nr < 1 || d.nz < 1) return AXB_EINVAL;
+  const int rb = pick_rb(d), re = pick_re(rb);
+  dim3 grid;
+  const EdgeMap em = edge_map(d, rb, re, hr, hz, vec != 0, owned_window != 0, grid);
+  int n = 0;
+  for (unsigned ey = 0; ey < grid.y; ++ey)
+    for (unsigned ex = 0; ex < grid.x; ++ex) {
+      int bx, fy;
+      if (!edge_decode(em, (int)ex, (int)ey, bx, fy)) continue;
+      if (n < cap) { pairs[2 * n] = bx; pairs[2 * n + 1] = fy; }
+      ++n;
+    }
+  info[0] = rb; info[1] = re; info[2] = em.on; info[3] = n;
+  return AXB_OK;
 }

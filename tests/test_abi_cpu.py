@@ -154,3 +154,65 @@ def test_mirrored_module_tree_matches_the_reference_layout():
         m = importlib.import_module("pyaxisymflow_b200." + mod)
         for n in names:
             assert callable(getattr(m, n)), f"{mod}.{n}"
+
+
+def test_edge_block_enumeration_of_the_marching_stencil_passes():
+    """The row-marching stencil passes launch their edge kernel on a compact grid of the edge blocks only, enumerated
+    on the host with the kernels' own predicates (csrc/stencils_march.cu: edge_map / edge_decode).  A block the
+    enumeration missed would be computed by nobody, so the launched set is compared with the definition -- every
+    (column block, fine row chunk) whose parent chunk is not interior -- on single-GPU grids, z-slabs (owned column
+    window, global offset) and r-slabs (owned row window, which only the kernels with fused reductions honour)."""
+    from pyaxisymflow_b200.device import make_grid
+
+    lib = _lib.load()
+    MT = 128
+
+    def interior(g, bx, p0, p1, rb, hr, hz, vec, owned):
+        kb0 = 2 * bx * MT
+        kb1 = kb0 + 2 * MT
+        ju0, ju1 = (g.ju0, g.ju1) if g.ju1 else (0, g.nr)
+        cols = (kb0 >= g.ku0 and kb1 <= g.ku1 and kb0 + g.kz0 >= hz and kb1 - 1 + g.kz0 <= g.nz_global - 1 - hz
+                and kb0 - hz >= 0 and kb1 - 1 + hz < g.nz)
+        rows = p1 - p0 == rb and p0 >= hr and p1 + hr <= g.nr and (not owned or (p0 >= ju0 and p1 <= ju1))
+        return bool(vec and cols and rows)
+
+    rng = np.random.default_rng(5)
+    grids = [make_grid(4096, 16384, 16384, 1.0), make_grid(128, 256, 256, 1.0), make_grid(1024, 4096, 4096, 1.0),
+             make_grid(516, 16384, 16384, 1.0, rows=(2, 514)), make_grid(2052, 16384, 16384, 1.0, rows=(2, 2050)),
+             make_grid(1024, 2052, 2052, 1.0, slab=(0, 16384, 0, 2050)),
+             make_grid(1024, 2052, 2052, 1.0, slab=(14332, 16384, 2, 2052)),
+             make_grid(1024, 2048, 8 * 2048, 1.0, batch=(8, 2048, 24)), make_grid(3, 12, 12, 1.0),
+             make_grid(37, 1030, 1030, 1.0), make_grid(1000, 3000, 3000, 1.0, rows=(100, 433))]
+    for _ in range(40):
+        nr, nz = int(rng.integers(3, 700)), int(rng.integers(4, 5000))
+        grids.append(make_grid(nr, nz, nz, 1.0, rows=(int(rng.integers(0, nr // 2)), int(rng.integers(nr // 2 + 1, nr + 1)))))
+    seen_compact = 0
+    for g in grids:
+        for hr, hz in ((1, 1), (2, 2)):
+            for vec in (1, 0):
+                for owned in (0, 1):
+                    cap = 1 << 18
+                    pairs = np.zeros(2 * cap, dtype=np.int32)
+                    info = np.zeros(4, dtype=np.int32)
+                    rc = lib.axb_debug_edge_blocks(ctypes.byref(g), hr, hz, vec, owned, pairs.ctypes.data, cap,
+                                                   info.ctypes.data)
+                    assert rc == 0
+                    rb, re, compact, n = (int(v) for v in info)
+                    assert rb % re == 0 and re in (4, 8, 16, 32) and n <= cap
+                    seen_compact += compact
+                    launched = [(int(pairs[2 * i]), int(pairs[2 * i + 1])) for i in range(n)]
+                    nbx, nfy = ((g.nz + 1) // 2 + MT - 1) // MT, (g.nr + re - 1) // re
+                    want = set()
+                    for bx in range(nbx):
+                        for fy in range(nfy):
+                            p0 = (fy * re // rb) * rb
+                            if not interior(g, bx, p0, min(p0 + rb, g.nr), rb, hr, hz, vec, owned):
+                                want.add((bx, fy))
+                    edge = [p for p in launched
+                            if not interior(g, p[0], (p[1] * re // rb) * rb, min((p[1] * re // rb) * rb + rb, g.nr), rb, hr,
+                                            hz, vec, owned)]
+                    assert len(edge) == len(set(edge)), "an edge block is launched twice"
+                    assert set(edge) == want, (g.nr, g.nz, hr, hz, vec, owned)
+                    if compact:
+                        assert len(launched) == len(want), "the compact grid launches interior blocks"
+    assert seen_compact > 50
