@@ -295,9 +295,10 @@ __device__ __forceinline__ double pen_defect(double cc, double uu, double lamdt,
 // (interior kernel capped at 128 registers = 4 blocks per SM: with the fused reduction it took 162 and ran at 0.87 of HBM
 // where the 128-register form without it runs at 0.92; ptxas spills 76 bytes.  Measured with the same cap on the one-pass
 // RK2 -- 168 -> 128 registers, 4 bytes spilled --: C4 2.850 -> 2.828 / 2.831 with either, 2.806 with both; the same
-// treatment of ENO3 and G-VEL, 94 -> 80 registers for 6 blocks per SM, LOST 2.5 % on C4 and 7 % on C3 and is not used.)
+// treatment of ENO3 and G-VEL, 94 -> 80 registers for 6 blocks per SM, LOST 2.5 % on C4 and 7 % on C3 and is not used; the
+// form without the reduction (150 registers, config C3) measured the same capped or not, 1.832 vs 1.834 ms, and stays free.)
 template <bool REDUCE, int PATH>
-__global__ void __launch_bounds__(MT, PATH == 1 ? 4 : 1)
+__global__ void __launch_bounds__(MT, (PATH == 1 && REDUCE) ? 4 : 1)
     km_penalise(GridD g, int RB, int RE, EdgeMap em, double* __restrict__ u_z, double* __restrict__ u_r, double* __restrict__ w,
                 const double* __restrict__ uzu, const double* __restrict__ uru, const double* __restrict__ chi,
                 double lam, double dt, const double* __restrict__ dt_dev, double U_z, double U_r,
