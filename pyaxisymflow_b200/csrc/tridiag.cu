@@ -9,10 +9,13 @@
 // streaming sweeps without a division:
 //     forward :  y_m = rhs_m * scale_m - (a_m / den_{m-1}) y_{m-1}
 //     backward:  x_m = (y_m - u_m x_{m+1}) / den_m
-// A CTA of TC threads owns TC adjacent columns (TC = 128: 1 KB row segments, so every visit of a
-// DRAM page moves a useful amount) and walks down the rows in lockstep; the right-hand side and the
-// reciprocal pivots arrive through an 8-stage cp.async ring in shared memory, so each SM keeps
-// ~100 KB of loads in flight although only nz chains exist.
+// Three generations of the sweep kernel live here (all walk 32- to 128-column groups down the rows in lockstep):
+//   k_tri_sweep<DIR, TC>      cp.async ring, TC columns per CTA (AXB_TRI_COLS; operands that are not TMA friendly);
+//   k_tri_sweep_tma<DIR>      one warp per 32 columns: TMA loads, chain and TMA stores in that warp (round-2 start,
+//                             axb_set_tridiag_sweep(1));
+//   k_tri_sweep_ws<DIR, NS>   the default: a producer lane feeds a ring of NS boxes (8 rows x 32 columns of the field
+//                             and of the reciprocal pivots + the row coefficients) by TMA, a second warp runs the
+//                             dependent chain out of registers and stores the rows.
 #include <cuda.h>   // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
