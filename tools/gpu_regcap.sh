@@ -1,6 +1,9 @@
 #!/bin/bash
-# A/B of the register cap on the interior penalisation kernel WITHOUT the fused reduction (config C3's form): prebuilt
-# libraries under tools/_alt (capreduce = 150 registers, capall = 128 with 76 bytes spilled), C3 line three times each
+# A/B of library builds that differ in a compile-time choice (here: __launch_bounds__ register caps of the interior
+# row-marching kernels, profiles/r02_register_caps_ab.txt).  Build each variant here (edit, `make -C pyaxisymflow_b200/csrc`,
+# copy libaxisym_b200.so to tools/_alt/<name>.so -- *.so is git-ignored but travels with gpurun), list the names below;
+# the script swaps them in turn under the package and restores the original.  Last use: capreduce (penalisation kernel
+# without the fused reduction left at 150 registers) against capall (capped at 128, 76 bytes spilled), C3 line three times each
 mkdir -p gpurun_out
 T=${TAG:-r02bn}
 cp pyaxisymflow_b200/libaxisym_b200.so /tmp/orig.so
